@@ -1,0 +1,154 @@
+/*
+ * sgdx.h -- C ABI of the B200-native sample-barcode assignment path for sgdemux.
+ *
+ * This is the drop-in boundary.  The reference (Rust, /root/reference/src/lib) has no FFI; the seams
+ * this ABI replaces are cited per entry point:
+ *
+ *   per-read seam   trait Matcher { fn find(&self, barcode: Vec<u8>) -> MatchResult }   matcher.rs:75-77
+ *                   CachedHammingDistanceMatcher::new / PreComputeMatcher::new           matcher.rs:87-96,143-151
+ *   call site       Demultiplexer::demultiplex, N gate + find + index + counters + hop   demux.rs:524-556,581
+ *   selection       PreCompute for <= 12 bp, cached Hamming otherwise                    run.rs:196-236
+ *   counters        DemuxedGroupSampleMetrics::update_with_match                         metrics.rs:428-437
+ *                   SampleBarcodeHopChecker::try_new / Tracker::check_barcode            metrics.rs:575-614,658-676
+ *                   DemuxedGroupMetrics::update_with (merge by sum)                      metrics.rs:315-328
+ *
+ * Conventions: every function returns 0 on success and a negative SGDX_E* code on failure (the text
+ * is available from sgdx_last_error(), thread-local); no exception or abort crosses the boundary; the
+ * caller owns every host buffer, the library owns device memory.  A handle may be used from several
+ * host threads at once as long as each thread uses its own `slot` (mirrors `M: Matcher + Send + Sync`,
+ * demux.rs:422).  There is no CPU fallback: without a CUDA device sgdx_create fails.
+ *
+ * Barcodes are passed the way the reference passes them: raw ASCII bytes, all sample-barcode (B)
+ * segments of a template concatenated in FASTQ order (demux.rs:404-405,504-522), exactly
+ * barcode_len bytes per read (run.rs:109-119 guarantees it outside --sample-barcode-in-fastq-header).
+ */
+#ifndef SGDX_H
+#define SGDX_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SGDX_OK 0
+#define SGDX_EINVAL (-1)   /* bad argument / unsupported configuration */
+#define SGDX_ECUDA (-2)    /* CUDA runtime error (no device, launch failure, ...) */
+#define SGDX_ENOMEM (-3)
+#define SGDX_ESTATE (-4)   /* call made in the wrong state (e.g. slot busy with an unsynced batch) */
+
+/* matcher kinds: MatcherKind, matcher.rs:49-53 */
+#define SGDX_MATCHER_AUTO 0u              /* run.rs:196 rule: barcode_len <= 12 -> PreCompute, else CachedHamming */
+#define SGDX_MATCHER_CACHED_HAMMING 1u    /* rule set A.2 (matcher.rs:273-348) */
+#define SGDX_MATCHER_PRECOMPUTE 2u        /* rule set A.3 (matcher.rs:121-262) */
+
+/* kernel variants (both are hand-written sm_100a kernels with identical results) */
+#define SGDX_KERNEL_AUTO 0u
+#define SGDX_KERNEL_DIRECT 1u     /* per (read, sample) XOR/OR/POPC scan with best/second-best keys */
+#define SGDX_KERNEL_BITSLICED 2u  /* sample-transposed mismatch planes + carry-save threshold filter */
+
+#define SGDX_MAX_BARCODE_LEN 32u
+#define SGDX_MAX_SAMPLES 8192u
+#define SGDX_NO_DIST 0xFFu        /* out_dist value of a NoMatch read */
+
+typedef struct sgdx_handle sgdx_handle;
+
+typedef struct sgdx_config {
+    uint32_t num_samples;     /* S, Undetermined excluded (run.rs:201,220); 1..SGDX_MAX_SAMPLES */
+    uint32_t barcode_len;     /* L, 1..32 */
+    uint32_t max_mismatches;  /* --allowed-mismatches, opts.rs:118 */
+    uint32_t min_delta;       /* --min-delta, opts.rs:123 */
+    uint32_t free_ns;         /* --free-ns, opts.rs:127 (ignored by PreCompute, as in the reference) */
+    int32_t  max_no_calls;    /* --max-no-calls, opts.rs:135; -1 = None */
+    uint32_t matcher;         /* SGDX_MATCHER_* */
+    uint32_t index1_len;      /* hop checker (metrics.rs:587-595): summed B lengths of the 1st barcode read */
+    uint32_t index2_len;      /*   ... of the 2nd; both 0 = fewer/more than two barcode reads -> checker off */
+    int32_t  device;          /* CUDA device ordinal */
+    uint32_t slots;           /* independent in-flight batches (one stream each); 0 -> 2 */
+    uint32_t kernel;          /* SGDX_KERNEL_* */
+} sgdx_config;
+
+/* 16-byte packed read record (2-bit base planes + no-call mask + foreign-byte mask); bit j = base j */
+typedef struct sgdx_read {
+    uint32_t lo, hi;  /* code = (ascii >> 1) & 3 : A=0 C=1 T=2 G=3 ; lo = bit 0, hi = bit 1 */
+    uint32_t nmask;   /* byte == 'N' */
+    uint32_t xmask;   /* byte not in {A,C,G,T,N}: mismatches every sample, is not a no-call */
+} sgdx_read;
+
+/* cumulative counters of a handle; per_sample is [(S+1)][3] = {total, perfect, one_mismatch},
+ * Undetermined last (metrics.rs:407-437; demux.rs:259) */
+typedef struct sgdx_totals {
+    uint64_t total_templates;   /* demux.rs:581 */
+    uint64_t matched;           /* reads assigned to a real sample */
+    uint64_t undetermined;
+    uint64_t hop_reads;         /* NoMatch reads counted by the hop tracker */
+} sgdx_totals;
+
+const char *sgdx_last_error(void);
+const char *sgdx_version(void);
+
+/* Matcher construction: replaces CachedHammingDistanceMatcher::new / PreComputeMatcher::new plus
+ * SampleBarcodeHopChecker::try_new.  barcodes_ascii = S*L bytes, upper-case ACGT only
+ * (sample_metadata.rs:219-226); anything else is SGDX_EINVAL. */
+int sgdx_create(const sgdx_config *cfg, const uint8_t *barcodes_ascii, sgdx_handle **out);
+void sgdx_destroy(sgdx_handle *h);
+int sgdx_get_config(const sgdx_handle *h, sgdx_config *effective); /* AUTO fields resolved */
+
+/* pinned host memory for batch buffers (plain memory also works, through an internal staging copy) */
+int sgdx_alloc_host(size_t bytes, void **out);
+int sgdx_free_host(void *p);
+
+/* Batched Matcher::find + demux.rs:524-556 counting, HOST buffers.  Asynchronous: queues
+ * H2D(n*L bytes) -> assign kernel -> D2H(idx, dist) on the slot's stream and returns; the outputs are
+ * valid after sgdx_sync(h, slot).  out_idx[r] in [0,S], S = Undetermined; out_dist[r] = reported
+ * hamming_dist (free-N discounted, matcher.rs:301) or SGDX_NO_DIST.  out_dist may be NULL. */
+int sgdx_match_batch(sgdx_handle *h, uint32_t slot, const uint8_t *barcodes_ascii, uint64_t n,
+                     uint16_t *out_idx, uint8_t *out_dist);
+int sgdx_sync(sgdx_handle *h, uint32_t slot, float *device_ms /* nullable: kernel time of last batch */);
+
+/* Same, buffers already resident on the handle's device (no copies). */
+int sgdx_match_device(sgdx_handle *h, uint32_t slot, const uint8_t *d_barcodes_ascii, uint64_t n,
+                      uint16_t *d_out_idx, uint8_t *d_out_dist);
+/* Two-stage form: pack kernel (ASCII -> 16-byte records, 128-bit stores) and match on packed records. */
+int sgdx_pack_device(sgdx_handle *h, uint32_t slot, const uint8_t *d_barcodes_ascii, uint64_t n,
+                     sgdx_read *d_packed);
+int sgdx_match_packed_device(sgdx_handle *h, uint32_t slot, const sgdx_read *d_packed, uint64_t n,
+                             uint16_t *d_out_idx, uint8_t *d_out_dist);
+/* Run the slot on a caller-owned stream (cudaStream_t passed as void*); NULL restores the slot's own. */
+int sgdx_set_stream(sgdx_handle *h, uint32_t slot, void *cuda_stream);
+/* Number of kernel launches issued through this handle so far. */
+uint64_t sgdx_launch_count(const sgdx_handle *h);
+
+/* Counters (device-resident, cumulative over all slots; synchronises the device).
+ * per_sample: (S+1)*3 u64, nullable.  Replaces reading DemuxedGroupMetrics after the fold/reduce. */
+int sgdx_counters(sgdx_handle *h, uint64_t *per_sample, sgdx_totals *totals);
+int sgdx_reset_counters(sgdx_handle *h);
+/* Hop tracker contents (metrics.rs:658-676): number of distinct hop barcodes, then export of
+ * (concatenated observed barcode [L bytes], count) pairs in unspecified order. */
+int sgdx_hop_count(sgdx_handle *h, uint64_t *n_keys);
+int sgdx_hop_export(sgdx_handle *h, uint8_t *keys /* cap*L */, uint64_t *counts /* cap */, uint64_t cap,
+                    uint64_t *n_written);
+
+/* ---- host batching stage (the new stage between segment extraction demux.rs:522 and assignment
+ * demux.rs:528): accumulates the barcodes of many 1000-read chunks into pinned super-batches, keeps
+ * `slots` batches in flight and hands results back in submission order. */
+typedef struct sgdx_batcher sgdx_batcher;
+int sgdx_batcher_create(sgdx_handle *h, uint64_t batch_reads, sgdx_batcher **out);
+void sgdx_batcher_destroy(sgdx_batcher *b);
+/* append n barcodes (n*L ASCII bytes); launches a batch whenever one fills */
+int sgdx_batcher_push(sgdx_batcher *b, const uint8_t *barcodes_ascii, uint64_t n);
+/* launch the partially filled batch, if any */
+int sgdx_batcher_flush(sgdx_batcher *b);
+/* Oldest unconsumed batch: blocks until it is done; pointers stay valid until the next call of
+ * sgdx_batcher_next/destroy.  *n == 0 when nothing is pending. */
+int sgdx_batcher_next(sgdx_batcher *b, const uint16_t **idx, const uint8_t **dist, uint64_t *n);
+
+/* ---- measurement support */
+/* Integer-pipe micro-benchmark on `device`: sustained 32-bit POPC and LOP3 results per second. */
+int sgdx_measure_int_peak(int device, double *popc_per_s, double *lop3_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SGDX_H */

@@ -1,0 +1,41 @@
+/*
+ * sgdx_synth.h -- seeded synthetic input generator, measurement/test support.
+ * The same counter-based generator runs on the host (C++) and on the device (CUDA) and produces
+ * byte-identical reads for any (seed, read id), so any shard of a workload can be regenerated on
+ * the CPU for the oracle.  Not part of the reference's interface.
+ */
+#ifndef SGDX_SYNTH_H
+#define SGDX_SYNTH_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct sgdx_synth_params {
+    uint64_t seed;
+    uint32_t num_samples;  /* S */
+    uint32_t barcode_len;  /* L */
+    uint32_t index1_len;   /* 0 = single index (no hop reads are generated) */
+    uint32_t zipf;         /* 1 = skewed sample weights (k ~ S*u^2), 0 = uniform */
+    /* probabilities as fractions of 2^32 */
+    uint32_t p_true;       /* read drawn from one sample (then per-base substitutions) */
+    uint32_t p_hop;        /* index1 of sample a + index2 of sample b != a */
+    uint32_t p_sub;        /* per-base substitution, applied to true/hop reads */
+    uint32_t p_n;          /* per-base no-call injection, all reads */
+    uint32_t p_x;          /* per-base foreign byte ('R') injection, all reads */
+} sgdx_synth_params;
+
+/* Expected-barcode table: S distinct barcodes; for dual index each half set has pairwise Hamming
+ * distance >= min_dist (greedy accept), single index likewise on the whole barcode. out = S*L bytes. */
+int sgdx_synth_table(uint64_t seed, uint32_t num_samples, uint32_t barcode_len, uint32_t index1_len,
+                     uint32_t min_dist, uint8_t *out);
+/* reads [first, first+n) as n*L ASCII bytes */
+int sgdx_synth_reads_host(const sgdx_synth_params *p, const uint8_t *table, uint64_t first, uint64_t n,
+                          uint8_t *out, int threads);
+int sgdx_synth_reads_device(const sgdx_synth_params *p, const uint8_t *d_table, uint64_t first, uint64_t n,
+                            uint8_t *d_out, void *cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,588 @@
+// sgdx_api.cu -- C-ABI layer (include/sgdx.h): handle, slots/streams, counters, hop export, batcher.
+// No torch types, no CPU fallback: every entry point that computes needs a CUDA device.
+#include <algorithm>
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <deque>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/sgdx.h"
+#include "sgdx_kernels.h"
+
+using namespace sgdx;
+
+static thread_local std::string g_err;
+
+static int fail(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CU(call)                                                                                           \
+    do {                                                                                                   \
+        cudaError_t e__ = (call);                                                                          \
+        if (e__ != cudaSuccess)                                                                            \
+            return fail(SGDX_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+struct Slot {
+    cudaStream_t own = nullptr;
+    cudaStream_t stream = nullptr;  // own or caller-provided
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    uint8_t *d_in = nullptr;
+    uint16_t *d_idx = nullptr;
+    uint8_t *d_dist = nullptr;
+    uint64_t cap = 0;  // reads
+    bool timed = false;
+};
+
+struct sgdx_handle {
+    sgdx_config cfg;  // effective (AUTO resolved)
+    uint32_t mode = kModeHamming;
+    int sms = 148;
+    DevParams base{};  // everything but the per-batch pointers
+    uint2 *d_table = nullptr;
+    uint32_t *d_planes = nullptr;
+    HopSlot *d_hash1 = nullptr, *d_hash2 = nullptr;
+    unsigned long long *d_hop_fwd = nullptr, *d_hop_rev = nullptr;
+    unsigned long long *d_counters = nullptr;
+    std::vector<std::string> keys1, keys2;  // distinct index1 / index2 halves (ASCII), id order
+    std::vector<Slot> slots;
+    std::atomic<uint64_t> launches{0};
+};
+
+extern "C" const char *sgdx_last_error(void) { return g_err.c_str(); }
+extern "C" const char *sgdx_version(void) { return "sgdx 0.1.0 (sm_100a)"; }
+
+static inline uint32_t base_code(uint8_t c) { return (c >> 1) & 3u; }  // A0 C1 T2 G3
+
+static void encode_planes(const uint8_t *s, uint32_t len, uint32_t *lo, uint32_t *hi) {
+    uint32_t l = 0, h = 0;
+    for (uint32_t j = 0; j < len; j++) {
+        uint32_t c = base_code(s[j]);
+        l |= (c & 1u) << j;
+        h |= (c >> 1) << j;
+    }
+    *lo = l;
+    *hi = h;
+}
+
+static void build_hash(const std::vector<std::string> &keys, uint32_t len, std::vector<HopSlot> &tab, uint32_t *mask,
+                       uint32_t *alln_id) {
+    uint32_t cap = 16;
+    while (cap < keys.size() * 2 + 2) cap <<= 1;
+    tab.assign(cap, HopSlot{0ull, 0xFFFFFFFFu, 0u});
+    *mask = cap - 1;
+    *alln_id = 0xFFFFFFFFu;
+    for (uint32_t id = 0; id < keys.size(); id++) {
+        const std::string &k = keys[id];
+        if (k.find('N') != std::string::npos) {  // only Undetermined's all-N half
+            *alln_id = id;
+            continue;
+        }
+        uint32_t lo, hi;
+        encode_planes(reinterpret_cast<const uint8_t *>(k.data()), len, &lo, &hi);
+        uint64_t key = ((uint64_t)hi << 32) | lo;
+        uint32_t i = (uint32_t)mix64(key ^ ((uint64_t)len << 58)) & *mask;
+        while (tab[i].id != 0xFFFFFFFFu) i = (i + 1) & *mask;
+        tab[i] = HopSlot{key, id, 0u};
+    }
+}
+
+extern "C" int sgdx_create(const sgdx_config *cfg, const uint8_t *barcodes, sgdx_handle **out) {
+    if (!cfg || !barcodes || !out) return fail(SGDX_EINVAL, "sgdx_create: null argument");
+    *out = nullptr;
+    const uint32_t S = cfg->num_samples, L = cfg->barcode_len;
+    if (S < 1 || S > SGDX_MAX_SAMPLES) return fail(SGDX_EINVAL, "num_samples %u outside 1..%u", S, SGDX_MAX_SAMPLES);
+    if (L < 1 || L > SGDX_MAX_BARCODE_LEN)
+        return fail(SGDX_EINVAL, "barcode_len %u outside 1..%u", L, SGDX_MAX_BARCODE_LEN);
+    if (cfg->matcher > SGDX_MATCHER_PRECOMPUTE) return fail(SGDX_EINVAL, "unknown matcher kind %u", cfg->matcher);
+    if (cfg->kernel > SGDX_KERNEL_BITSLICED) return fail(SGDX_EINVAL, "unknown kernel kind %u", cfg->kernel);
+    if ((cfg->index1_len == 0) != (cfg->index2_len == 0) ||
+        (cfg->index1_len && cfg->index1_len + cfg->index2_len != L))
+        return fail(SGDX_EINVAL, "index1_len + index2_len must equal barcode_len (or both be 0)");
+    for (uint64_t i = 0; i < (uint64_t)S * L; i++) {
+        uint8_t c = barcodes[i];
+        if (c != 'A' && c != 'C' && c != 'G' && c != 'T')
+            return fail(SGDX_EINVAL, "expected barcode %llu has byte 0x%02x at %llu (must be upper-case ACGT)",
+                        (unsigned long long)(i / L), c, (unsigned long long)(i % L));
+    }
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0)
+        return fail(SGDX_ECUDA, "no CUDA device available (%s); sgdx has no CPU fallback", cudaGetErrorString(ce));
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(SGDX_EINVAL, "device %d not in 0..%d", cfg->device, ndev - 1);
+    CU(cudaSetDevice(cfg->device));
+
+    sgdx_handle *h = new sgdx_handle();
+    h->cfg = *cfg;
+    if (h->cfg.matcher == SGDX_MATCHER_AUTO)  // run.rs:196-198
+        h->cfg.matcher = L <= 12 ? SGDX_MATCHER_PRECOMPUTE : SGDX_MATCHER_CACHED_HAMMING;
+    if (h->cfg.slots == 0) h->cfg.slots = 2;
+    if (h->cfg.slots > 64) h->cfg.slots = 64;
+    if (h->cfg.kernel == SGDX_KERNEL_AUTO) h->cfg.kernel = SGDX_KERNEL_DIRECT;
+    h->mode = h->cfg.matcher == SGDX_MATCHER_PRECOMPUTE ? kModePreCompute : kModeHamming;
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, cfg->device));
+    h->sms = prop.multiProcessorCount;
+
+    DevParams &p = h->base;
+    p.S = S;
+    p.L = L;
+    // distances never exceed L <= 32, so clamping the thresholds at 64 changes no verdict and keeps
+    // the 16-bit distance field of the keys safe
+    p.M = std::min<uint32_t>(cfg->max_mismatches, 64u);
+    p.delta = std::min<uint32_t>(cfg->min_delta, 64u);
+    p.free_ns = std::min<uint32_t>(cfg->free_ns, 64u);
+    p.max_no_calls = cfg->max_no_calls < 0 ? -1 : std::min<int32_t>(cfg->max_no_calls, 64);
+    {
+        // matcher.rs:175: `max_mismatches + min_delta - 1` wraps when both are 0 and is then clamped to L (201)
+        uint64_t md = (uint64_t)cfg->max_mismatches + cfg->min_delta;
+        uint64_t hi = md == 0 ? L : md - 1;
+        if (hi > L) hi = L;
+        p.pc_limit = (uint32_t)std::max<uint64_t>(hi, std::min<uint32_t>(cfg->max_mismatches, L));
+    }
+    p.table_pad = (S + 1u) & ~1u;
+    p.hop_on = cfg->index1_len > 0 ? 1u : 0u;
+    p.i1 = cfg->index1_len;
+    p.i2 = cfg->index2_len;
+
+    std::vector<uint2> table(p.table_pad, make_uint2(0u, 0u));
+    for (uint32_t s = 0; s < S; s++) encode_planes(barcodes + (uint64_t)s * L, L, &table[s].x, &table[s].y);
+    CU(cudaMalloc(&h->d_table, table.size() * sizeof(uint2)));
+    CU(cudaMemcpy(h->d_table, table.data(), table.size() * sizeof(uint2), cudaMemcpyHostToDevice));
+    p.table = h->d_table;
+
+    const size_t ncounters = (size_t)(S + 1) * 3;
+    CU(cudaMalloc(&h->d_counters, ncounters * sizeof(unsigned long long)));
+    CU(cudaMemset(h->d_counters, 0, ncounters * sizeof(unsigned long long)));
+    p.counters = h->d_counters;
+
+    if (p.hop_on) {
+        // SampleBarcodeHopChecker::try_new (metrics.rs:596-609): halves of every sample AND of Undetermined
+        std::map<std::string, uint32_t> m1, m2;
+        auto add = [](std::map<std::string, uint32_t> &m, std::vector<std::string> &v, const std::string &k) {
+            if (m.emplace(k, (uint32_t)v.size()).second) v.push_back(k);
+        };
+        for (uint32_t s = 0; s <= S; s++) {
+            std::string bc = s < S ? std::string(reinterpret_cast<const char *>(barcodes) + (uint64_t)s * L, L)
+                                   : std::string(L, 'N');
+            add(m1, h->keys1, bc.substr(0, p.i1));
+            add(m2, h->keys2, bc.substr(p.i1));
+        }
+        p.u1 = (uint32_t)h->keys1.size();
+        p.u2 = (uint32_t)h->keys2.size();
+        std::vector<HopSlot> t1, t2;
+        build_hash(h->keys1, p.i1, t1, &p.hmask1, &p.alln1);
+        build_hash(h->keys2, p.i2, t2, &p.hmask2, &p.alln2);
+        CU(cudaMalloc(&h->d_hash1, t1.size() * sizeof(HopSlot)));
+        CU(cudaMalloc(&h->d_hash2, t2.size() * sizeof(HopSlot)));
+        CU(cudaMemcpy(h->d_hash1, t1.data(), t1.size() * sizeof(HopSlot), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(h->d_hash2, t2.data(), t2.size() * sizeof(HopSlot), cudaMemcpyHostToDevice));
+        p.hash1 = h->d_hash1;
+        p.hash2 = h->d_hash2;
+        size_t cells = (size_t)p.u1 * p.u2;
+        CU(cudaMalloc(&h->d_hop_fwd, cells * sizeof(unsigned long long)));
+        CU(cudaMalloc(&h->d_hop_rev, cells * sizeof(unsigned long long)));
+        CU(cudaMemset(h->d_hop_fwd, 0, cells * sizeof(unsigned long long)));
+        CU(cudaMemset(h->d_hop_rev, 0, cells * sizeof(unsigned long long)));
+        p.hop_fwd = h->d_hop_fwd;
+        p.hop_rev = h->d_hop_rev;
+    }
+
+    h->slots.resize(h->cfg.slots);
+    for (Slot &s : h->slots) {
+        CU(cudaStreamCreateWithFlags(&s.own, cudaStreamNonBlocking));
+        s.stream = s.own;
+        CU(cudaEventCreate(&s.e0));
+        CU(cudaEventCreate(&s.e1));
+    }
+    *out = h;
+    return SGDX_OK;
+}
+
+extern "C" void sgdx_destroy(sgdx_handle *h) {
+    if (!h) return;
+    cudaSetDevice(h->cfg.device);
+    for (Slot &s : h->slots) {
+        if (s.own) cudaStreamSynchronize(s.own);
+        cudaFree(s.d_in);
+        cudaFree(s.d_idx);
+        cudaFree(s.d_dist);
+        if (s.e0) cudaEventDestroy(s.e0);
+        if (s.e1) cudaEventDestroy(s.e1);
+        if (s.own) cudaStreamDestroy(s.own);
+    }
+    cudaFree(h->d_table);
+    cudaFree(h->d_planes);
+    cudaFree(h->d_hash1);
+    cudaFree(h->d_hash2);
+    cudaFree(h->d_hop_fwd);
+    cudaFree(h->d_hop_rev);
+    cudaFree(h->d_counters);
+    delete h;
+}
+
+extern "C" int sgdx_get_config(const sgdx_handle *h, sgdx_config *effective) {
+    if (!h || !effective) return fail(SGDX_EINVAL, "sgdx_get_config: null argument");
+    *effective = h->cfg;
+    return SGDX_OK;
+}
+
+extern "C" int sgdx_alloc_host(size_t bytes, void **out) {
+    if (!out) return fail(SGDX_EINVAL, "sgdx_alloc_host: null out");
+    CU(cudaMallocHost(out, bytes ? bytes : 1));
+    return SGDX_OK;
+}
+extern "C" int sgdx_free_host(void *p) {
+    if (p) CU(cudaFreeHost(p));
+    return SGDX_OK;
+}
+
+static int check_slot(sgdx_handle *h, uint32_t slot) {
+    if (!h) return fail(SGDX_EINVAL, "null handle");
+    if (slot >= h->slots.size()) return fail(SGDX_EINVAL, "slot %u >= %zu", slot, h->slots.size());
+    return SGDX_OK;
+}
+
+static int run_kernels(sgdx_handle *h, Slot &s, const uint8_t *d_ascii, const uint4 *d_packed, uint64_t n,
+                       uint16_t *d_idx, uint8_t *d_dist) {
+    DevParams p = h->base;
+    p.reads_ascii = d_ascii;
+    p.reads_packed = d_packed;
+    p.n = n;
+    p.out_idx = d_idx;
+    p.out_dist = d_dist;
+    CU(cudaEventRecord(s.e0, s.stream));
+    CU(launch_direct(p, h->mode, d_packed != nullptr, h->sms, s.stream));
+    CU(cudaEventRecord(s.e1, s.stream));
+    s.timed = true;
+    if (n) h->launches.fetch_add(1);
+    return SGDX_OK;
+}
+
+extern "C" int sgdx_match_device(sgdx_handle *h, uint32_t slot, const uint8_t *d_ascii, uint64_t n, uint16_t *d_idx,
+                                 uint8_t *d_dist) {
+    if (int rc = check_slot(h, slot)) return rc;
+    if (n && (!d_ascii || !d_idx)) return fail(SGDX_EINVAL, "sgdx_match_device: null buffer");
+    if (n >> 40) return fail(SGDX_EINVAL, "batch too large");
+    CU(cudaSetDevice(h->cfg.device));
+    return run_kernels(h, h->slots[slot], d_ascii, nullptr, n, d_idx, d_dist);
+}
+
+extern "C" int sgdx_match_packed_device(sgdx_handle *h, uint32_t slot, const sgdx_read *d_packed, uint64_t n,
+                                        uint16_t *d_idx, uint8_t *d_dist) {
+    if (int rc = check_slot(h, slot)) return rc;
+    if (n && (!d_packed || !d_idx)) return fail(SGDX_EINVAL, "sgdx_match_packed_device: null buffer");
+    if (reinterpret_cast<uintptr_t>(d_packed) & 15u) return fail(SGDX_EINVAL, "packed records must be 16-byte aligned");
+    CU(cudaSetDevice(h->cfg.device));
+    return run_kernels(h, h->slots[slot], nullptr, reinterpret_cast<const uint4 *>(d_packed), n, d_idx, d_dist);
+}
+
+extern "C" int sgdx_pack_device(sgdx_handle *h, uint32_t slot, const uint8_t *d_ascii, uint64_t n, sgdx_read *d_packed) {
+    if (int rc = check_slot(h, slot)) return rc;
+    if (n && (!d_ascii || !d_packed)) return fail(SGDX_EINVAL, "sgdx_pack_device: null buffer");
+    if (reinterpret_cast<uintptr_t>(d_packed) & 15u) return fail(SGDX_EINVAL, "packed records must be 16-byte aligned");
+    CU(cudaSetDevice(h->cfg.device));
+    CU(launch_pack(d_ascii, n, h->cfg.barcode_len, reinterpret_cast<uint4 *>(d_packed), h->sms, h->slots[slot].stream));
+    if (n) h->launches.fetch_add(1);
+    return SGDX_OK;
+}
+
+static int ensure_capacity(Slot &s, uint64_t n, uint32_t L) {
+    if (n <= s.cap) return SGDX_OK;
+    CU(cudaStreamSynchronize(s.stream));
+    cudaFree(s.d_in);
+    cudaFree(s.d_idx);
+    cudaFree(s.d_dist);
+    s.d_in = nullptr;
+    s.d_idx = nullptr;
+    s.d_dist = nullptr;
+    s.cap = 0;
+    uint64_t cap = n + n / 8 + 1024;
+    CU(cudaMalloc(&s.d_in, cap * L));
+    CU(cudaMalloc(&s.d_idx, cap * sizeof(uint16_t)));
+    CU(cudaMalloc(&s.d_dist, cap));
+    s.cap = cap;
+    return SGDX_OK;
+}
+
+extern "C" int sgdx_match_batch(sgdx_handle *h, uint32_t slot, const uint8_t *ascii, uint64_t n, uint16_t *out_idx,
+                                uint8_t *out_dist) {
+    if (int rc = check_slot(h, slot)) return rc;
+    if (n && (!ascii || !out_idx)) return fail(SGDX_EINVAL, "sgdx_match_batch: null buffer");
+    if (n >> 34) return fail(SGDX_EINVAL, "batch of %llu reads too large; split it", (unsigned long long)n);
+    CU(cudaSetDevice(h->cfg.device));
+    Slot &s = h->slots[slot];
+    const uint32_t L = h->cfg.barcode_len;
+    if (int rc = ensure_capacity(s, n, L)) return rc;
+    if (n) CU(cudaMemcpyAsync(s.d_in, ascii, n * L, cudaMemcpyHostToDevice, s.stream));
+    if (int rc = run_kernels(h, s, s.d_in, nullptr, n, s.d_idx, s.d_dist)) return rc;
+    if (n) {
+        CU(cudaMemcpyAsync(out_idx, s.d_idx, n * sizeof(uint16_t), cudaMemcpyDeviceToHost, s.stream));
+        if (out_dist) CU(cudaMemcpyAsync(out_dist, s.d_dist, n, cudaMemcpyDeviceToHost, s.stream));
+    }
+    return SGDX_OK;
+}
+
+extern "C" int sgdx_sync(sgdx_handle *h, uint32_t slot, float *device_ms) {
+    if (int rc = check_slot(h, slot)) return rc;
+    Slot &s = h->slots[slot];
+    CU(cudaStreamSynchronize(s.stream));
+    if (device_ms) {
+        *device_ms = 0.f;
+        if (s.timed) CU(cudaEventElapsedTime(device_ms, s.e0, s.e1));
+    }
+    return SGDX_OK;
+}
+
+extern "C" int sgdx_set_stream(sgdx_handle *h, uint32_t slot, void *stream) {
+    if (int rc = check_slot(h, slot)) return rc;
+    Slot &s = h->slots[slot];
+    CU(cudaStreamSynchronize(s.stream));
+    s.stream = stream ? static_cast<cudaStream_t>(stream) : s.own;
+    s.timed = false;
+    return SGDX_OK;
+}
+
+extern "C" uint64_t sgdx_launch_count(const sgdx_handle *h) { return h ? h->launches.load() : 0; }
+
+static int fetch_hop(sgdx_handle *h, std::vector<unsigned long long> &fwd, std::vector<unsigned long long> &rev) {
+    size_t cells = (size_t)h->base.u1 * h->base.u2;
+    fwd.resize(cells);
+    rev.resize(cells);
+    CU(cudaMemcpy(fwd.data(), h->d_hop_fwd, cells * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(rev.data(), h->d_hop_rev, cells * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    return SGDX_OK;
+}
+
+extern "C" int sgdx_counters(sgdx_handle *h, uint64_t *per_sample, sgdx_totals *totals) {
+    if (!h) return fail(SGDX_EINVAL, "null handle");
+    CU(cudaSetDevice(h->cfg.device));
+    CU(cudaDeviceSynchronize());
+    const uint32_t S = h->cfg.num_samples;
+    std::vector<unsigned long long> raw((size_t)(S + 1) * 3);
+    CU(cudaMemcpy(raw.data(), h->d_counters, raw.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    sgdx_totals t{};
+    for (uint32_t b = 0; b <= S; b++) {
+        uint64_t other = raw[b * 3 + 0], perfect = raw[b * 3 + 1], one = raw[b * 3 + 2];
+        uint64_t total = other + perfect + one;
+        if (per_sample) {
+            per_sample[b * 3 + 0] = total;
+            per_sample[b * 3 + 1] = perfect;
+            per_sample[b * 3 + 2] = one;
+        }
+        t.total_templates += total;
+        (b < S ? t.matched : t.undetermined) += total;
+    }
+    if (h->base.hop_on) {
+        std::vector<unsigned long long> fwd, rev;
+        if (int rc = fetch_hop(h, fwd, rev)) return rc;
+        for (size_t i = 0; i < fwd.size(); i++) t.hop_reads += fwd[i] + rev[i];
+    }
+    if (totals) *totals = t;
+    return SGDX_OK;
+}
+
+extern "C" int sgdx_reset_counters(sgdx_handle *h) {
+    if (!h) return fail(SGDX_EINVAL, "null handle");
+    CU(cudaSetDevice(h->cfg.device));
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemset(h->d_counters, 0, (size_t)(h->cfg.num_samples + 1) * 3 * sizeof(unsigned long long)));
+    if (h->base.hop_on) {
+        size_t cells = (size_t)h->base.u1 * h->base.u2;
+        CU(cudaMemset(h->d_hop_fwd, 0, cells * sizeof(unsigned long long)));
+        CU(cudaMemset(h->d_hop_rev, 0, cells * sizeof(unsigned long long)));
+    }
+    return SGDX_OK;
+}
+
+// dense (index1 id, index2 id) cells -> {observed barcode: count}; a barcode that satisfies the forward
+// rule is always booked in hop_fwd, so the two tables never hold the same string twice -- but sum anyway.
+static int hop_entries(sgdx_handle *h, std::map<std::string, uint64_t> &out) {
+    if (!h->base.hop_on) return SGDX_OK;
+    CU(cudaSetDevice(h->cfg.device));
+    CU(cudaDeviceSynchronize());
+    std::vector<unsigned long long> fwd, rev;
+    if (int rc = fetch_hop(h, fwd, rev)) return rc;
+    const uint32_t u2 = h->base.u2;
+    for (size_t i = 0; i < fwd.size(); i++) {
+        if (fwd[i]) out[h->keys1[i / u2] + h->keys2[i % u2]] += fwd[i];
+        if (rev[i]) out[h->keys2[i % u2] + h->keys1[i / u2]] += rev[i];
+    }
+    return SGDX_OK;
+}
+
+extern "C" int sgdx_hop_count(sgdx_handle *h, uint64_t *n_keys) {
+    if (!h || !n_keys) return fail(SGDX_EINVAL, "sgdx_hop_count: null argument");
+    std::map<std::string, uint64_t> m;
+    if (int rc = hop_entries(h, m)) return rc;
+    *n_keys = m.size();
+    return SGDX_OK;
+}
+
+extern "C" int sgdx_hop_export(sgdx_handle *h, uint8_t *keys, uint64_t *counts, uint64_t cap, uint64_t *n_written) {
+    if (!h || !n_written) return fail(SGDX_EINVAL, "sgdx_hop_export: null argument");
+    std::map<std::string, uint64_t> m;
+    if (int rc = hop_entries(h, m)) return rc;
+    if (m.size() > cap) return fail(SGDX_EINVAL, "hop export needs room for %zu keys, got %llu", m.size(), (unsigned long long)cap);
+    const uint32_t L = h->cfg.barcode_len;
+    uint64_t i = 0;
+    for (auto &kv : m) {
+        memcpy(keys + i * L, kv.first.data(), L);
+        counts[i++] = kv.second;
+    }
+    *n_written = i;
+    return SGDX_OK;
+}
+
+extern "C" int sgdx_measure_int_peak(int device, double *popc_per_s, double *lop3_per_s) {
+    if (!popc_per_s || !lop3_per_s) return fail(SGDX_EINVAL, "sgdx_measure_int_peak: null argument");
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || device < 0 || device >= ndev) return fail(SGDX_ECUDA, "no such CUDA device %d", device);
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    CU(measure_int_peak(prop.multiProcessorCount, popc_per_s, lop3_per_s));
+    return SGDX_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// batching stage
+// ------------------------------------------------------------------------------------------------
+struct Batch {
+    uint16_t *idx = nullptr;  // pinned
+    uint8_t *dist = nullptr;  // pinned
+    uint64_t n = 0;
+    uint32_t slot = 0;
+};
+
+struct sgdx_batcher {
+    sgdx_handle *h = nullptr;
+    uint64_t batch_reads = 0;
+    uint32_t L = 0;
+    std::vector<uint8_t *> in;      // one pinned input buffer per slot
+    std::vector<bool> slot_busy;    // slot has an unsynced batch
+    uint32_t cur = 0;               // slot being filled
+    uint64_t fill = 0;
+    std::deque<Batch> inflight;     // submission order
+    std::vector<Batch> free_results;
+    Batch handed{};                 // batch whose pointers the caller currently holds
+};
+
+extern "C" int sgdx_batcher_create(sgdx_handle *h, uint64_t batch_reads, sgdx_batcher **out) {
+    if (!h || !out || batch_reads == 0) return fail(SGDX_EINVAL, "sgdx_batcher_create: bad argument");
+    sgdx_batcher *b = new sgdx_batcher();
+    b->h = h;
+    b->batch_reads = batch_reads;
+    b->L = h->cfg.barcode_len;
+    b->in.resize(h->slots.size(), nullptr);
+    b->slot_busy.assign(h->slots.size(), false);
+    for (auto &p : b->in) {
+        void *q = nullptr;
+        if (int rc = sgdx_alloc_host(batch_reads * b->L, &q)) {
+            sgdx_batcher_destroy(b);
+            return rc;
+        }
+        p = static_cast<uint8_t *>(q);
+    }
+    *out = b;
+    return SGDX_OK;
+}
+
+static void release_result(sgdx_batcher *b, Batch &r) {
+    if (r.idx) b->free_results.push_back(r);
+    r = Batch{};
+}
+
+extern "C" void sgdx_batcher_destroy(sgdx_batcher *b) {
+    if (!b) return;
+    for (uint32_t s = 0; s < b->slot_busy.size(); s++)
+        if (b->slot_busy[s]) sgdx_sync(b->h, s, nullptr);
+    for (auto p : b->in) cudaFreeHost(p);
+    release_result(b, b->handed);
+    for (auto &r : b->inflight) b->free_results.push_back(r);
+    for (auto &r : b->free_results) {
+        cudaFreeHost(r.idx);
+        cudaFreeHost(r.dist);
+    }
+    delete b;
+}
+
+static int submit(sgdx_batcher *b) {
+    if (b->fill == 0) return SGDX_OK;
+    Batch r;
+    if (!b->free_results.empty()) {
+        r = b->free_results.back();
+        b->free_results.pop_back();
+    } else {
+        void *q = nullptr;
+        if (int rc = sgdx_alloc_host(b->batch_reads * sizeof(uint16_t), &q)) return rc;
+        r.idx = static_cast<uint16_t *>(q);
+        if (int rc = sgdx_alloc_host(b->batch_reads, &q)) return rc;
+        r.dist = static_cast<uint8_t *>(q);
+    }
+    r.n = b->fill;
+    r.slot = b->cur;
+    if (int rc = sgdx_match_batch(b->h, b->cur, b->in[b->cur], r.n, r.idx, r.dist)) return rc;
+    b->slot_busy[b->cur] = true;
+    b->inflight.push_back(r);
+    b->fill = 0;
+    b->cur = (b->cur + 1) % (uint32_t)b->in.size();
+    if (b->slot_busy[b->cur]) {  // about to overwrite this slot's input buffer: its batch must have left the host
+        if (int rc = sgdx_sync(b->h, b->cur, nullptr)) return rc;
+        b->slot_busy[b->cur] = false;
+    }
+    return SGDX_OK;
+}
+
+extern "C" int sgdx_batcher_push(sgdx_batcher *b, const uint8_t *ascii, uint64_t n) {
+    if (!b || (n && !ascii)) return fail(SGDX_EINVAL, "sgdx_batcher_push: null argument");
+    while (n) {
+        uint64_t take = std::min(n, b->batch_reads - b->fill);
+        memcpy(b->in[b->cur] + b->fill * b->L, ascii, take * b->L);
+        b->fill += take;
+        ascii += take * b->L;
+        n -= take;
+        if (b->fill == b->batch_reads)
+            if (int rc = submit(b)) return rc;
+    }
+    return SGDX_OK;
+}
+
+extern "C" int sgdx_batcher_flush(sgdx_batcher *b) {
+    if (!b) return fail(SGDX_EINVAL, "null batcher");
+    return submit(b);
+}
+
+extern "C" int sgdx_batcher_next(sgdx_batcher *b, const uint16_t **idx, const uint8_t **dist, uint64_t *n) {
+    if (!b || !idx || !dist || !n) return fail(SGDX_EINVAL, "sgdx_batcher_next: null argument");
+    release_result(b, b->handed);
+    *idx = nullptr;
+    *dist = nullptr;
+    *n = 0;
+    if (b->inflight.empty()) return SGDX_OK;
+    Batch r = b->inflight.front();
+    b->inflight.pop_front();
+    // a slot's stream is in-order, so syncing it covers this batch even if a newer one was queued on it
+    if (int rc = sgdx_sync(b->h, r.slot, nullptr)) return rc;
+    bool newer_on_slot = false;
+    for (auto &q : b->inflight) newer_on_slot |= (q.slot == r.slot);
+    if (!newer_on_slot) b->slot_busy[r.slot] = false;
+    b->handed = r;
+    *idx = r.idx;
+    *dist = r.dist;
+    *n = r.n;
+    return SGDX_OK;
+}

@@ -1,0 +1,208 @@
+// sgdx_device.cuh -- device-side building blocks shared by the assignment kernels (sm_100a).
+//
+// Semantics restated from /root/reference/src/lib (citations are file:line in that tree):
+//   distance            matcher.rs:335-348      selection + delta rule   matcher.rs:266-303
+//   PreCompute rule     matcher.rs:155-261      N gate + sample index    demux.rs:78-80,524-538
+//   per-sample counters metrics.rs:428-437      hop check                metrics.rs:658-676
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace sgdx {
+
+constexpr uint32_t kModeHamming = 0;     // CachedHammingDistanceMatcher rule set
+constexpr uint32_t kModePreCompute = 1;  // PreComputeMatcher rule set
+constexpr uint32_t kInfKey = 0xFFFFFFFFu;
+constexpr uint32_t kNoDist = 0xFFu;
+
+struct HopSlot {       // open-addressing slot of a barcode-half key set
+    uint64_t key;      // (hi plane << 32) | lo plane of the half, bit j = base j of the half
+    uint32_t id;       // dense id of the key, 0xFFFFFFFF = empty
+    uint32_t pad;
+};
+
+struct DevParams {
+    const uint8_t *reads_ascii;  // n * L bytes                (ASCII input)
+    const uint4 *reads_packed;   // n sgdx_read records         (packed input)
+    uint64_t n;
+    uint32_t S, L;
+    uint32_t M, delta, free_ns;  // clamped to <= 64 by the host (equivalent for L <= 32)
+    int32_t max_no_calls;        // -1 = None
+    uint32_t pc_limit;           // PreCompute: max(M, M+delta-1) (L if M+delta == 0): furthest visible competitor
+    const uint2 *table;          // S entries {lo, hi} planes of the expected barcodes
+    uint32_t table_pad;          // S rounded up to a multiple of 2
+    uint16_t *out_idx;
+    uint8_t *out_dist;           // nullable
+    unsigned long long *counters;  // [(S+1)][3] = {other, perfect, one_mismatch}; total = sum of the three
+    // hop checker
+    uint32_t hop_on, i1, i2;
+    uint32_t u1, u2;             // number of distinct index1 / index2 keys (incl. the all-N half)
+    uint32_t alln1, alln2;       // dense ids of Undetermined's all-N halves
+    const HopSlot *hash1, *hash2;
+    uint32_t hmask1, hmask2;     // capacity - 1
+    unsigned long long *hop_fwd; // [u1][u2]  barcode = I1[a] ++ I2[b]
+    unsigned long long *hop_rev; // [u1][u2]  barcode = I2[b] ++ I1[a]   (reversed-orientation rule only)
+    // bit-sliced kernel
+    const uint32_t *planes;      // [L][5][W4*4] mismatch planes, row 4 = no-call/foreign (all zero)
+    uint32_t W;                  // number of 32-sample words, multiple of 4
+    uint32_t T;                  // candidate threshold on valid-position mismatches
+};
+
+struct Rd {  // one observed barcode as bit planes; bit j = base j, bits >= L are zero
+    uint32_t lo, hi, nmask, xmask;
+};
+
+__host__ __device__ inline uint64_t mix64(uint64_t z) {
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+// 0x80 in every byte of z that is zero (exact, no cross-byte borrow)
+__device__ __forceinline__ uint32_t zero_bytes(uint32_t z) {
+    return ~(((z & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | z | 0x7F7F7F7Fu);
+}
+
+// gather bit 0 of each of the 4 bytes of x into a nibble (byte k -> bit k)
+__device__ __forceinline__ uint32_t gather4(uint32_t x) {
+    return (x * 0x01020408u) >> 24;  // (1<<24)+(1<<17)+(1<<10)+(1<<3): partial products never collide
+}
+
+// fold 4 ASCII bases (byte k = base j+k) into the planes
+__device__ __forceinline__ void fold_word(uint32_t w, uint32_t j, Rd &r) {
+    const uint32_t ones = 0x01010101u;
+    uint32_t nflag = zero_bytes(w ^ 0x4E4E4E4Eu) >> 7;                          // 'N'
+    uint32_t aceg = zero_bytes((w & 0xF9F9F9F9u) ^ 0x41414141u);                // A C E G
+    uint32_t e = zero_bytes(w ^ 0x45454545u);                                   // E
+    uint32_t t = zero_bytes(w ^ 0x54545454u);                                   // T
+    uint32_t ok = ((aceg & ~e) | t) >> 7;
+    uint32_t x = ~(ok | nflag) & ones;
+    r.lo |= gather4((w >> 1) & ones) << j;
+    r.hi |= gather4((w >> 2) & ones) << j;
+    r.nmask |= gather4(nflag) << j;
+    r.xmask |= gather4(x) << j;
+}
+
+// Load read r (L ASCII bytes) and convert. words_ok: base pointer 4-byte aligned and L % 4 == 0.
+__device__ __forceinline__ Rd load_ascii(const uint8_t *__restrict__ reads, uint64_t r, uint32_t L, bool words_ok) {
+    Rd rd = {0u, 0u, 0u, 0u};
+    const uint8_t *p = reads + r * (uint64_t)L;
+    if (words_ok) {
+        const uint32_t *pw = reinterpret_cast<const uint32_t *>(p);
+        uint32_t nw = L >> 2;
+#pragma unroll 8
+        for (uint32_t i = 0; i < 8; i++)
+            if (i < nw) fold_word(__ldg(pw + i), i * 4, rd);
+    } else {
+        for (uint32_t j = 0; j < L; j += 4) {
+            uint32_t w = 0x41414141u;  // pad with 'A': contributes zero bits to every plane
+            for (uint32_t k = 0; k < 4 && j + k < L; k++)
+                w = (w & ~(0xFFu << (8 * k))) | ((uint32_t)__ldg(p + j + k) << (8 * k));
+            fold_word(w, j, rd);
+        }
+    }
+    // planes of no-call / foreign positions are irrelevant to matching but must not leak into hop keys
+    uint32_t inv = rd.nmask | rd.xmask;
+    rd.lo &= ~inv;
+    rd.hi &= ~inv;
+    return rd;
+}
+
+__device__ __forceinline__ Rd load_packed(const uint4 *__restrict__ reads, uint64_t r, uint32_t L) {
+    uint4 v = __ldg(reads + r);  // one coalesced 128-bit load per read
+    uint32_t lm = L >= 32 ? 0xFFFFFFFFu : ((1u << L) - 1u);
+    Rd rd;
+    rd.nmask = v.z & lm;
+    rd.xmask = v.w & lm & ~rd.nmask;
+    uint32_t inv = rd.nmask | rd.xmask;
+    rd.lo = v.x & lm & ~inv;
+    rd.hi = v.y & lm & ~inv;
+    return rd;
+}
+
+struct Verdict {
+    uint32_t bin;   // sample index, S = Undetermined
+    uint32_t dist;  // reported hamming_dist, kNoDist for NoMatch
+};
+
+// best / nxt are (distance << 16 | sample) keys over the N-always-mismatch distance p' (Hamming mode) or
+// D (PreCompute mode, with invisible competitors already removed); kInfKey = none.
+template <uint32_t MODE>
+__device__ __forceinline__ Verdict apply_rules(const DevParams &p, const Rd &rd, uint32_t best, uint32_t nxt) {
+    Verdict v;
+    v.bin = p.S;
+    v.dist = kNoDist;
+    uint32_t n_no_calls = __popc(rd.nmask);
+    bool gated = p.max_no_calls >= 0 && n_no_calls > (uint32_t)p.max_no_calls;  // demux.rs:528-531
+    uint32_t bd = best >> 16, nd = nxt >> 16;  // nd = 0xFFFF when there is no competitor
+    bool ok;
+    uint32_t reported;
+    if (MODE == kModeHamming) {
+        // matcher.rs:339-341: the first free_ns no-call positions are skipped -> constant discount
+        uint32_t d = bd - min(n_no_calls, p.free_ns);
+        reported = d;
+        ok = best != kInfKey && d <= p.M && (nd - bd) > p.delta;  // matcher.rs:295-299
+    } else {
+        reported = bd;
+        bool rejected = nd <= bd + p.delta && nd <= p.pc_limit;     // visible competitor within delta
+        ok = best != kInfKey && rd.xmask == 0u && bd <= p.M && !rejected;
+    }
+    if (ok && !gated) {
+        v.bin = best & 0xFFFFu;
+        v.dist = reported;
+    }
+    return v;
+}
+
+__device__ __forceinline__ uint32_t hop_find(const HopSlot *__restrict__ tab, uint32_t mask, uint32_t alln_id,
+                                             uint32_t lo, uint32_t hi, uint32_t nm, uint32_t xm, uint32_t len) {
+    uint32_t lm = len >= 32 ? 0xFFFFFFFFu : ((1u << len) - 1u);
+    lo &= lm; hi &= lm; nm &= lm; xm &= lm;
+    if (xm) return 0xFFFFFFFFu;
+    if (nm) return nm == lm ? alln_id : 0xFFFFFFFFu;  // only Undetermined's all-N half contains Ns
+    uint64_t key = ((uint64_t)hi << 32) | lo;
+    uint32_t i = (uint32_t)mix64(key ^ ((uint64_t)len << 58)) & mask;
+    for (;;) {
+        HopSlot s = tab[i];
+        if (s.id == 0xFFFFFFFFu) return 0xFFFFFFFFu;
+        if (s.key == key) return s.id;
+        i = (i + 1) & mask;
+    }
+}
+
+// metrics.rs:658-676 for one NoMatch read (len == i1 + i2 always holds for device batches)
+__device__ __forceinline__ void hop_check(const DevParams &p, const Rd &rd) {
+    uint32_t a = hop_find(p.hash1, p.hmask1, p.alln1, rd.lo, rd.hi, rd.nmask, rd.xmask, p.i1);
+    if (a != 0xFFFFFFFFu) {
+        uint32_t b = hop_find(p.hash2, p.hmask2, p.alln2, rd.lo >> p.i1, rd.hi >> p.i1, rd.nmask >> p.i1,
+                              rd.xmask >> p.i1, p.i2);
+        if (b != 0xFFFFFFFFu) {
+            atomicAdd(&p.hop_fwd[(uint64_t)a * p.u2 + b], 1ull);
+            return;
+        }
+    }
+    // reversed orientation: index1 key in barcode[i2..], index2 key in barcode[..i2]
+    uint32_t c = hop_find(p.hash1, p.hmask1, p.alln1, rd.lo >> p.i2, rd.hi >> p.i2, rd.nmask >> p.i2,
+                          rd.xmask >> p.i2, p.i1);
+    if (c == 0xFFFFFFFFu) return;
+    uint32_t d = hop_find(p.hash2, p.hmask2, p.alln2, rd.lo, rd.hi, rd.nmask, rd.xmask, p.i2);
+    if (d == 0xFFFFFFFFu) return;
+    atomicAdd(&p.hop_rev[(uint64_t)c * p.u2 + d], 1ull);
+}
+
+// store the verdict, bump the block-private histogram (warp-aggregated), run the hop check
+__device__ __forceinline__ void emit(const DevParams &p, uint64_t r, bool active, const Rd &rd, const Verdict &v,
+                                     uint32_t *hist) {
+    uint32_t key = 0xFFFFFFFFu;
+    if (active) {
+        p.out_idx[r] = (uint16_t)v.bin;
+        if (p.out_dist) p.out_dist[r] = (uint8_t)v.dist;
+        uint32_t cls = v.dist == 0u ? 1u : (v.dist == 1u ? 2u : 0u);  // metrics.rs:428-437
+        key = v.bin * 3u + cls;
+    }
+    uint32_t peers = __match_any_sync(0xFFFFFFFFu, key);
+    if (active && (uint32_t)(__ffs(peers) - 1) == (threadIdx.x & 31u)) atomicAdd(&hist[key], (uint32_t)__popc(peers));
+    if (active && p.hop_on && v.bin == p.S) hop_check(p, rd);
+}
+
+}  // namespace sgdx

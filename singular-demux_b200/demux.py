@@ -1,0 +1,74 @@
+"""The assignment + counting step of Demultiplexer::demultiplex, batched for the GPU.
+
+Mirrors /root/reference/src/lib/demux.rs:524-556,581 (N gate -> Matcher::find -> sample index ->
+update_with_match -> hop check -> unmatched collection -> total_templates) and Demultiplexer::new's
+wiring of matcher + hop checker (demux.rs:223-270).  Segment extraction, filters, header rewriting and
+read routing stay with the host pipeline; this stage consumes the concatenated
+sample barcodes they produce and returns the sample-index array they route by.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from .matcher import GpuMatcher, SampleMetadata, as_barcode_array
+from .metrics import DemuxedGroupMetrics, SampleBarcodeHopTracker, UnmatchedCounter
+
+
+@dataclass
+class DemuxedGroup:
+    """What the host needs back per batch (demux.rs:637-645, minus the routed reads themselves)."""
+    sample_indices: np.ndarray           # uint16, undetermined_sample_index for NoMatch
+    hamming_dists: np.ndarray            # uint8, 0xFF for NoMatch
+    unmatched: Optional[np.ndarray]      # [k, L] concatenated barcodes of the NoMatch reads (collect_unmatched)
+
+
+class BarcodeAssignmentStage:
+    """samples: ALL samples, the last one must be Undetermined (demux.rs:221, 259); the matcher sees
+    samples[:-1] (run.rs:201,220).  index_lengths = (index1_length, index2_length) when exactly two
+    reads carry sample-barcode segments (metrics.rs:587-595), else None: no hop checker."""
+
+    def __init__(self, samples: Sequence[SampleMetadata], matcher_cls, max_mismatches: int, min_delta: int,
+                 free_ns: int, max_no_calls: Optional[int] = None, index_lengths: Optional[Tuple[int, int]] = None,
+                 collect_unmatched: bool = True, device: int = 0, slots: int = 2, kernel: int = 0):
+        if len(samples) < 2:
+            raise ValueError("need at least one sample plus Undetermined")
+        self.samples = list(samples)
+        self.undetermined_sample_index = len(samples) - 1
+        self.index_lengths = index_lengths
+        self.collect_unmatched = collect_unmatched
+        self.matcher: GpuMatcher = matcher_cls(self.samples[:-1], max_mismatches, min_delta, free_ns,
+                                               max_no_calls=max_no_calls, index_lengths=index_lengths,
+                                               device=device, slots=slots, kernel=kernel)
+
+    def get_undetermined_index(self) -> int:
+        return self.undetermined_sample_index
+
+    def demultiplex(self, barcodes, slot: int = 0) -> DemuxedGroup:
+        arr = as_barcode_array(barcodes, self.matcher.barcode_len)
+        idx, dist = self.matcher.find_batch(arr, slot)
+        unmatched = arr[idx == self.undetermined_sample_index] if self.collect_unmatched else None
+        return DemuxedGroup(idx, dist, unmatched)
+
+    def metrics(self) -> DemuxedGroupMetrics:
+        """Cumulative counters of every batch this stage has processed (device-resident; read on demand)."""
+        per, totals = self.matcher.counters()
+        hop = None
+        if self.index_lengths:
+            hop = SampleBarcodeHopTracker(self.index_lengths[0], self.index_lengths[1], self.matcher.hop_counts())
+        return DemuxedGroupMetrics.from_device(per, totals["total_templates"], hop)
+
+    def close(self) -> None:
+        self.matcher.close()
+
+
+def count_unmatched(unmatched: np.ndarray, counter: Optional[UnmatchedCounter] = None) -> UnmatchedCounter:
+    """Feed one batch's NoMatch barcodes to the top-N counter (the reference sends them to a counter
+    thread, demux.rs:553-555 -> metrics.rs:79-100)."""
+    counter = counter or UnmatchedCounter()
+    if unmatched is not None and unmatched.shape[0]:
+        u, c = np.unique(unmatched, axis=0, return_counts=True)
+        counter.insert_counts(u, c)
+    return counter

@@ -1,0 +1,111 @@
+"""Counters: host-side mirror of the hot-path part of /root/reference/src/lib/metrics.rs.
+
+  DemuxedGroupSampleMetrics            metrics.rs:407-437
+  DemuxedGroupMetrics.update_with      metrics.rs:315-328   (merge by summation: exact under any sharding)
+  SampleBarcodeHopTracker              metrics.rs:617-677
+  BarcodeCount / UnmatchedCounter      metrics.rs:131-206   (host-side top-N of unmatched barcodes)
+The integer columns come from device counters (sgdx_counters / sgdx_hop_export); derived float columns
+are out of scope (written by the host's unchanged TSV writer, metrics.rs:440-465).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional
+
+import numpy as np
+
+
+@dataclass
+class DemuxedGroupSampleMetrics:
+    perfect_matches: int = 0
+    one_mismatch_matches: int = 0
+    total_matches: int = 0
+
+    def update_with(self, other: "DemuxedGroupSampleMetrics") -> None:
+        self.perfect_matches += other.perfect_matches
+        self.one_mismatch_matches += other.one_mismatch_matches
+        self.total_matches += other.total_matches
+
+
+@dataclass
+class SampleBarcodeHopTracker:
+    """count_tracker: concatenated observed barcode -> count (metrics.rs:621-623)."""
+    index1_length: int
+    index2_length: int
+    count_tracker: Dict[bytes, int] = field(default_factory=dict)
+
+    def update_with_self(self, other: "SampleBarcodeHopTracker") -> None:  # metrics.rs:633-638
+        for k, v in other.count_tracker.items():
+            self.count_tracker[k] = self.count_tracker.get(k, 0) + v
+
+    def __len__(self) -> int:
+        return len(self.count_tracker)
+
+    def is_empty(self) -> bool:
+        return not self.count_tracker
+
+    def barcode_counts(self) -> List["BarcodeCount"]:
+        """Rows of sample_barcode_hop_metrics.tsv: `index1+index2`, descending count (metrics.rs:374-387)."""
+        rows = [BarcodeCount((k[:self.index1_length] + b"+" + k[self.index1_length:]).decode(), v)
+                for k, v in self.count_tracker.items()]
+        rows.sort(key=lambda r: (-r.count, r.barcode))
+        return rows
+
+
+@dataclass(frozen=True)
+class BarcodeCount:  # metrics.rs:194-206
+    barcode: str
+    count: int
+
+
+@dataclass
+class DemuxedGroupMetrics:
+    per_sample_metrics: List[DemuxedGroupSampleMetrics]
+    total_templates: int = 0
+    num_reads_failing_filters: int = 0      # filters stay on the host (demux.rs:470-480)
+    num_reads_filtered_as_control: int = 0
+    sample_barcode_hop_tracker: Optional[SampleBarcodeHopTracker] = None
+
+    @staticmethod
+    def from_device(per_sample: np.ndarray, total_templates: int, hop: Optional[SampleBarcodeHopTracker]):
+        ps = [DemuxedGroupSampleMetrics(int(r[1]), int(r[2]), int(r[0])) for r in per_sample]
+        return DemuxedGroupMetrics(ps, int(total_templates), 0, 0, hop)
+
+    def update_with(self, other: "DemuxedGroupMetrics") -> None:  # metrics.rs:315-328
+        self.num_reads_failing_filters += other.num_reads_failing_filters
+        self.num_reads_filtered_as_control += other.num_reads_filtered_as_control
+        self.total_templates += other.total_templates
+        for s, o in zip(self.per_sample_metrics, other.per_sample_metrics):
+            s.update_with(o)
+        if self.sample_barcode_hop_tracker is not None and other.sample_barcode_hop_tracker is not None:
+            self.sample_barcode_hop_tracker.update_with_self(other.sample_barcode_hop_tracker)
+
+    def per_sample_array(self) -> np.ndarray:
+        return np.array([[m.total_matches, m.perfect_matches, m.one_mismatch_matches]
+                         for m in self.per_sample_metrics], dtype=np.uint64)
+
+
+class UnmatchedCounter:
+    """metrics.rs:131-190: counts delimited unmatched barcodes; when the map exceeds max_map_size it is
+    cut down to the downsize_to most frequent keys.  Fed from the sample-index array."""
+
+    def __init__(self, max_map_size: int = 5_000_000, downsize_to: int = 5_000):
+        self.max_map_size, self.downsize_to = max_map_size, downsize_to
+        self.counts: Dict[bytes, int] = {}
+
+    def insert_counts(self, keys: np.ndarray, counts: np.ndarray) -> None:
+        for i in range(keys.shape[0]):
+            k = keys[i].tobytes()
+            self.counts[k] = self.counts.get(k, 0) + int(counts[i])
+            if len(self.counts) > self.max_map_size:
+                self.downsize()
+
+    def downsize(self) -> None:
+        top = sorted(self.counts.items(), key=lambda kv: -kv[1])[:self.downsize_to]
+        self.counts = dict(top)
+
+    def most_frequent(self, n: int, index1_length: int = 0) -> List[BarcodeCount]:
+        def delim(k: bytes) -> str:
+            return ((k[:index1_length] + b"+" + k[index1_length:]) if index1_length else k).decode()
+        rows = sorted(self.counts.items(), key=lambda kv: (-kv[1], kv[0]))[:n]
+        return [BarcodeCount(delim(k), v) for k, v in rows]

@@ -1,0 +1,348 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle, bit-exact.
+Run on a B200: python -m pytest tests -m gpu."""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+
+import sgdx_loader
+from oracle import oracle as orc
+
+sg = sgdx_loader.load()
+pytestmark = pytest.mark.gpu
+
+KERNELS = [sg.KERNEL_DIRECT, sg.KERNEL_BITSLICED]
+ORC_KIND = {sg.MatcherKind.CachedHammingDistance: orc.MATCHER_CACHED_HAMMING, sg.MatcherKind.PreCompute: orc.MATCHER_PRECOMPUTE}
+CLS = {sg.MatcherKind.CachedHammingDistance: sg.CachedHammingDistanceMatcher, sg.MatcherKind.PreCompute: sg.PreComputeMatcher}
+
+
+def _samples(table):
+    out = [sg.SampleMetadata(f"s{i}", bytes(b), i) for i, b in enumerate(table)]
+    out.append(sg.SampleMetadata(sg.UNDETERMINED_NAME, b"N" * len(out[0].barcode), len(out)))
+    return out
+
+
+def _stage(table, kind, M, D, F, mnc, il, kernel, slots=2):
+    return sg.BarcodeAssignmentStage(_samples(table), CLS[kind], M, D, F, mnc, il, kernel=kernel, slots=slots)
+
+
+def _oracle(table, kind, M, D, F, mnc, il, reads, **kw):
+    S, L = len(table), len(table[0])
+    cfg = orc.Config(S, L, M, D, F, -1 if mnc is None else mnc, ORC_KIND[kind], il[0] if il else 0, il[1] if il else 0)
+    return orc.COracle(cfg, [bytes(t) for t in table], **kw).run(reads, threads=8, use_cache=True)
+
+
+def _assert_same(stage, got, want, n):
+    assert np.array_equal(got.sample_indices, want["idx"])
+    assert np.array_equal(got.hamming_dists, want["dist"])
+    m = stage.metrics()
+    assert np.array_equal(m.per_sample_array(), want["per_sample"])
+    assert m.total_templates == want["total_templates"] == n
+    if stage.index_lengths:
+        assert m.sample_barcode_hop_tracker.count_tracker == want["hops"]
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_reference_known_answers_on_device(golden, kernel):
+    """Every demux-level known answer of the reference's own tests, through the CUDA path."""
+    for case in golden["demux_cases"]:
+        table = [s.encode() for s in case["samples"]]
+        S, L = len(table), len(table[0])
+        reads = np.frombuffer("".join(case["reads"]).encode(), dtype=np.uint8).reshape(-1, L)
+        il = (case["index1_len"], case["index2_len"]) if case["index1_len"] else None
+        for k in case["matchers"]:
+            kind = sg.MatcherKind.PreCompute if k == 1 else sg.MatcherKind.CachedHammingDistance
+            st = _stage(table, kind, case["max_mismatches"], case["min_delta"], case["free_ns"], case["max_no_calls"], il, kernel)
+            got = st.demultiplex(reads)
+            assert got.sample_indices.tolist() == case["expected_idx"], case["src"]
+            if "expected_dist" in case:
+                assert got.hamming_dists.tolist() == [0xFF if d is None else d for d in case["expected_dist"]]
+            m = st.metrics()
+            if "per_sample" in case:
+                assert m.per_sample_array().tolist() == case["per_sample"]
+            if "per_sample_totals" in case:
+                assert m.per_sample_array()[:, 0].tolist() == case["per_sample_totals"]
+            if "total_templates" in case:
+                assert m.total_templates == case["total_templates"]
+            if "hops" in case:
+                assert {k_.decode(): v for k_, v in m.sample_barcode_hop_tracker.count_tracker.items()} == case["hops"]
+                if case["hops"]:
+                    assert m.sample_barcode_hop_tracker.barcode_counts()[0] == sg.BarcodeCount("TTT+AAA", 1)
+            if "unmatched" in case:
+                c = sg.demux.count_unmatched(got.unmatched)
+                assert {k_.decode(): v for k_, v in c.counts.items()} == case["unmatched"]
+            st.close()
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_matcher_find_known_answers_on_device(golden, kernel):
+    for case in golden["matcher_cases"]:
+        table = [s.encode() for s in case["samples"]]
+        for k in case["matchers"]:
+            kind = sg.MatcherKind.PreCompute if k == 1 else sg.MatcherKind.CachedHammingDistance
+            m = CLS[kind](table, case["max_mismatches"], case["min_delta"], case["free_ns"], kernel=kernel)
+            for observed, is_match, idx, dist in case["queries"]:
+                r = m.find(observed)
+                assert r.is_match() == is_match, (case["src"], observed)
+                if is_match:
+                    assert (r.sample_index, r.hamming_dist) == (idx, dist)
+                assert r.barcode == observed.encode()
+            m.close()
+
+
+def _random_case(rng, S, L, i1, p_n=0.02, p_x=0.004, n=40000, near=0.0):
+    w = sg.synth.Workload("r", S, L, i1, 1, 2, n_reads=n, table_seed=int(rng.integers(1 << 30)),
+                          read_seed=int(rng.integers(1 << 30)), p_true=0.80, p_hop=0.08 if i1 else 0.0,
+                          p_sub=0.03, p_n=p_n, p_x=p_x, min_dist=1 if S > 4 ** min(L, 4) // 8 else 2)
+    table = w.table()
+    reads = w.reads_host(0, n, table)
+    if i1:  # exercise the reversed-orientation hop rule and Undetermined's all-N halves
+        k = n // 50
+        a, b = rng.integers(0, S, k), rng.integers(0, S, k)
+        if i1 * 2 == L:
+            reads[:k, :i1], reads[:k, i1:] = table[b, i1:], table[a, :i1]
+        reads[k:k + 20, :i1] = ord("N")
+        reads[k + 20:k + 40, i1:] = ord("N")
+        reads[k + 40:k + 50, :] = ord("N")
+    return w, table, reads
+
+
+PARAMS = [  # (M, delta, free_ns, max_no_calls)
+    (1, 2, 1, None), (0, 0, 0, None), (2, 1, 2, 1), (3, 1, 1, 0), (1, 0, 0, 2), (2, 3, 1, None), (40, 0, 3, None),
+    (1, 70, 1, None),
+]
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize("S,L,i1", [(1, 8, 0), (2, 4, 2), (7, 12, 0), (24, 16, 8), (96, 16, 8), (97, 20, 10), (384, 20, 10),
+                                    (300, 24, 12), (50, 32, 16), (33, 13, 5), (64, 6, 3), (5, 1, 0), (130, 31, 0)])
+def test_random_tables_and_reads_match_oracle(kernel, S, L, i1):
+    rng = np.random.default_rng(S * 1000 + L)
+    w, table, reads = _random_case(rng, S, L, i1)
+    il = w.index_lengths
+    for kind in (sg.MatcherKind.CachedHammingDistance, sg.MatcherKind.PreCompute):
+        for (M, D, F, mnc) in PARAMS:
+            st = _stage(table, kind, M, D, F, mnc, il, kernel)
+            got = st.demultiplex(reads)
+            want = _oracle(table, kind, M, D, F, mnc, il, reads, force_closed_form=True)
+            _assert_same(st, got, want, reads.shape[0])
+            st.close()
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_precompute_against_literal_map_oracle(kernel):
+    """Short barcodes: the oracle side uses the literally constructed PreCompute map, not the closed form."""
+    rng = np.random.default_rng(99)
+    for (S, L, i1) in [(3, 5, 0), (12, 8, 4), (1, 8, 0), (40, 10, 5)]:
+        w, table, reads = _random_case(rng, S, L, i1, p_n=0.05, p_x=0.01, n=30000)
+        for (M, D) in [(1, 2), (1, 1), (2, 1), (0, 0), (1, 3), (2, 2)]:
+            st = _stage(table, sg.MatcherKind.PreCompute, M, D, 1, None, w.index_lengths, kernel)
+            got = st.demultiplex(reads)
+            S_, L_ = len(table), len(table[0])
+            cfg = orc.Config(S_, L_, M, D, 1, -1, orc.MATCHER_PRECOMPUTE, i1, L - i1 if i1 else 0)
+            o = orc.COracle(cfg, [bytes(t) for t in table])
+            assert o.has_map
+            _assert_same(st, got, o.run(reads, threads=8), reads.shape[0])
+            st.close()
+
+
+def test_synth_device_equals_host():
+    import torch
+    w = sg.synth.Workload("t", 96, 20, 10, 1, 2, p_n=0.01, p_x=0.002)
+    table = w.table()
+    n, first = 100_003, 777
+    d_table = torch.from_numpy(table).cuda()
+    d_out = torch.empty((n, 20), dtype=torch.uint8, device="cuda")
+    w.reads_device(first, n, d_table.data_ptr(), d_out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert np.array_equal(d_out.cpu().numpy(), w.reads_host(first, n, table))
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_device_resident_and_packed_paths_equal_host_path(kernel):
+    import torch
+    rng = np.random.default_rng(5)
+    for (S, L, i1) in [(96, 16, 8), (200, 20, 10), (31, 9, 0)]:
+        w, table, reads = _random_case(rng, S, L, i1, n=50001)
+        n = reads.shape[0]
+        st = _stage(table, sg.MatcherKind.CachedHammingDistance, 1, 2, 1, None, w.index_lengths, kernel)
+        host = st.demultiplex(reads)
+        base = st.metrics().per_sample_array()
+        m = st.matcher
+        d_in = torch.from_numpy(reads).cuda()
+        d_idx = torch.empty(n, dtype=torch.int16, device="cuda")
+        d_dist = torch.empty(n, dtype=torch.uint8, device="cuda")
+        m.set_stream(0, torch.cuda.current_stream().cuda_stream)
+        m.match_device(d_in.data_ptr(), n, d_idx.data_ptr(), d_dist.data_ptr())
+        torch.cuda.synchronize()
+        assert np.array_equal(d_idx.cpu().numpy().view(np.uint16), host.sample_indices)
+        assert np.array_equal(d_dist.cpu().numpy(), host.hamming_dists)
+        d_packed = torch.empty((n, 4), dtype=torch.int32, device="cuda")
+        d_idx.zero_()
+        d_dist.zero_()
+        m.pack_device(d_in.data_ptr(), n, d_packed.data_ptr())
+        m.match_packed_device(d_packed.data_ptr(), n, d_idx.data_ptr(), d_dist.data_ptr())
+        torch.cuda.synchronize()
+        assert np.array_equal(d_idx.cpu().numpy().view(np.uint16), host.sample_indices)
+        assert np.array_equal(d_dist.cpu().numpy(), host.hamming_dists)
+        assert np.array_equal(st.metrics().per_sample_array(), base * 3)  # counters are cumulative
+        # an unaligned device pointer (odd byte offset) must still work
+        d_shift = torch.empty(n * L + 1, dtype=torch.uint8, device="cuda")
+        d_shift[1:] = d_in.view(-1)
+        m.match_device(d_shift.data_ptr() + 1, n, d_idx.data_ptr(), d_dist.data_ptr())
+        torch.cuda.synchronize()
+        assert np.array_equal(d_idx.cpu().numpy().view(np.uint16), host.sample_indices)
+        m.set_stream(0, 0)
+        st.close()
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_slots_shards_and_merge_equal_single_pass(kernel):
+    """Batches on different slots / different handles (the multi-GPU sharding model) merge to exactly the
+    single-pass counters (metrics.rs:315-328)."""
+    rng = np.random.default_rng(11)
+    w, table, reads = _random_case(rng, 96, 16, 8, n=120_000)
+    n = reads.shape[0]
+    want = _oracle(table, sg.MatcherKind.CachedHammingDistance, 1, 2, 1, None, w.index_lengths, reads)
+    st = _stage(table, sg.MatcherKind.CachedHammingDistance, 1, 2, 1, None, w.index_lengths, kernel, slots=3)
+    idx = np.empty(n, dtype=np.uint16)
+    dist = np.empty(n, dtype=np.uint8)
+    cuts = [0, 1, 40_000, 40_000, 99_999, n]
+    for i in range(len(cuts) - 1):
+        a, b = cuts[i], cuts[i + 1]
+        st.matcher.submit(reads[a:b], idx[a:b], dist[a:b], slot=i % 3)
+    for s in range(3):
+        st.matcher.sync(s)
+    assert np.array_equal(idx, want["idx"]) and np.array_equal(dist, want["dist"])
+    assert np.array_equal(st.metrics().per_sample_array(), want["per_sample"])
+    st.close()
+    merged = None
+    for part in np.array_split(np.arange(n), 4):
+        s2 = _stage(table, sg.MatcherKind.CachedHammingDistance, 1, 2, 1, None, w.index_lengths, kernel)
+        s2.demultiplex(reads[part])
+        m = s2.metrics()
+        if merged is None:
+            merged = m
+        else:
+            merged.update_with(m)
+        s2.close()
+    assert np.array_equal(merged.per_sample_array(), want["per_sample"])
+    assert merged.total_templates == n and merged.sample_barcode_hop_tracker.count_tracker == want["hops"]
+
+
+def test_batcher_returns_batches_in_order():
+    from singular_demux_b200._lib import check, lib
+    rng = np.random.default_rng(3)
+    w, table, reads = _random_case(rng, 96, 16, 8, n=100_000)
+    want = _oracle(table, sg.MatcherKind.CachedHammingDistance, 1, 2, 1, None, w.index_lengths, reads)
+    st = _stage(table, sg.MatcherKind.CachedHammingDistance, 1, 2, 1, None, w.index_lengths, sg.KERNEL_AUTO, slots=2)
+    b = C.c_void_p()
+    check(lib().sgdx_batcher_create(st.matcher.handle, 16_384, C.byref(b)))
+    got_idx, got_dist = [], []
+
+    def drain(everything):
+        while True:
+            pi, pd, n = C.c_void_p(), C.c_void_p(), C.c_uint64(0)
+            if not everything and len(got_idx) * 16_384 + 3 * 16_384 > pushed[0]:
+                return
+            check(lib().sgdx_batcher_next(b, C.byref(pi), C.byref(pd), C.byref(n)))
+            if n.value == 0:
+                return
+            got_idx.append(np.ctypeslib.as_array(C.cast(pi, C.POINTER(C.c_uint16)), (n.value,)).copy())
+            got_dist.append(np.ctypeslib.as_array(C.cast(pd, C.POINTER(C.c_uint8)), (n.value,)).copy())
+
+    pushed = [0]
+    for chunk in np.array_split(reads, 100):  # 1000-read chunks like --chunksize
+        c = np.ascontiguousarray(chunk)
+        check(lib().sgdx_batcher_push(b, c.ctypes.data, c.shape[0]))
+        pushed[0] += c.shape[0]
+        drain(False)
+    check(lib().sgdx_batcher_flush(b))
+    drain(True)
+    lib().sgdx_batcher_destroy(b)
+    assert np.array_equal(np.concatenate(got_idx), want["idx"])
+    assert np.array_equal(np.concatenate(got_dist), want["dist"])
+    assert np.array_equal(st.metrics().per_sample_array(), want["per_sample"])
+    st.close()
+
+
+def test_empty_and_tiny_batches():
+    st = _stage([b"ACGTACGTACGTACGT", b"TTTTACGTACGTAAAA"], sg.MatcherKind.CachedHammingDistance, 1, 2, 1, None, (8, 8), sg.KERNEL_AUTO)
+    got = st.demultiplex(np.zeros((0, 16), dtype=np.uint8))
+    assert got.sample_indices.shape == (0,)
+    assert st.metrics().total_templates == 0
+    got = st.demultiplex([b"ACGTACGTACGTACGT"])
+    assert got.sample_indices.tolist() == [0] and got.hamming_dists.tolist() == [0]
+    st.close()
+
+
+@pytest.mark.parametrize("cfg", ["C1", "C2", "C3", "C4"])
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_baseline_configs_parity_sample(cfg, kernel):
+    """BASELINE.json configs on a bounded sample the oracle finishes in seconds (C1 at its full 1M)."""
+    w = sg.synth.CONFIGS[cfg]
+    n = {"C1": 1_000_000, "C2": 2_000_000, "C3": 400_000, "C4": 2_000_000}[cfg]
+    table = w.table()
+    reads = w.reads_host(0, n, table)
+    kind = sg.select_matcher(w.barcode_len)
+    st = _stage(table, kind, w.max_mismatches, w.min_delta, w.free_ns, w.max_no_calls, w.index_lengths, kernel)
+    got = st.demultiplex(reads)
+    want = _oracle(table, kind, w.max_mismatches, w.min_delta, w.free_ns, w.max_no_calls, w.index_lengths, reads)
+    _assert_same(st, got, want, n)
+    if cfg == "C4":  # override: cached hamming on the short inline barcode + most_frequent_unmatched counts
+        c = sg.demux.count_unmatched(got.unmatched)
+        assert c.counts == orc.unmatched_counts(reads, want["idx"], w.num_samples)
+        for mnc in (0, 1):
+            s2 = _stage(table, sg.MatcherKind.CachedHammingDistance, 1, 2, 1, mnc, None, kernel)
+            g2 = s2.demultiplex(reads)
+            _assert_same(s2, g2, _oracle(table, sg.MatcherKind.CachedHammingDistance, 1, 2, 1, mnc, None, reads), n)
+            s2.close()
+    st.close()
+
+
+def test_full_size_properties_c2():
+    """At a large size the oracle cannot afford, check size-independent properties: conservation
+    (sum of per-sample totals == n == total_templates), shard-merge invariance, idempotence, and
+    agreement of the two kernels with each other."""
+    import torch
+    w = sg.synth.C2
+    n = 20_000_000
+    table = w.table()
+    d_table = torch.from_numpy(table).cuda()
+    d_in = torch.empty((n, w.barcode_len), dtype=torch.uint8, device="cuda")
+    w.reads_device(0, n, d_table.data_ptr(), d_in.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    outs = []
+    for kernel in KERNELS:
+        st = _stage(table, sg.MatcherKind.CachedHammingDistance, 1, 2, 1, None, w.index_lengths, kernel)
+        d_idx = torch.empty(n, dtype=torch.int16, device="cuda")
+        d_dist = torch.empty(n, dtype=torch.uint8, device="cuda")
+        st.matcher.match_device(d_in.data_ptr(), n, d_idx.data_ptr(), d_dist.data_ptr())
+        st.matcher.sync(0)
+        m1 = st.metrics()
+        per = m1.per_sample_array()
+        assert int(per[:, 0].sum()) == n == m1.total_templates
+        hist = torch.bincount(d_idx.to(torch.int64) & 0xFFFF, minlength=w.num_samples + 1).cpu().numpy()
+        assert np.array_equal(hist.astype(np.uint64), per[:, 0])
+        assert int(((d_dist == 0) & (d_idx.to(torch.int64) < w.num_samples)).sum()) == int(per[:-1, 1].sum())
+        assert 0.85 * n < int(per[:-1, 0].sum()) < 0.95 * n
+        # shards on two slots accumulate to exactly twice the single pass
+        half = n // 2
+        st.matcher.match_device(d_in.data_ptr(), half, d_idx.data_ptr(), d_dist.data_ptr(), slot=0)
+        st.matcher.match_device(d_in.data_ptr() + half * w.barcode_len, n - half, d_idx.data_ptr() + 2 * half,
+                                d_dist.data_ptr() + half, slot=1)
+        st.matcher.sync(0)
+        st.matcher.sync(1)
+        assert np.array_equal(st.metrics().per_sample_array(), per * 2)
+        hops = st.metrics().sample_barcode_hop_tracker.count_tracker
+        assert all(v % 2 == 0 for v in hops.values()) and 0.02 * n < sum(hops.values()) // 2 < 0.04 * n
+        outs.append((d_idx.cpu().numpy().copy(), d_dist.cpu().numpy().copy(), per, hops))
+        st.close()
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+    assert np.array_equal(outs[0][2], outs[1][2]) and outs[0][3] == outs[1][3]
+    # the first 1M reads against the oracle
+    k = 1_000_000
+    want = _oracle(table, sg.MatcherKind.CachedHammingDistance, 1, 2, 1, None, w.index_lengths, w.reads_host(0, k, table))
+    assert np.array_equal(outs[0][0][:k], want["idx"]) and np.array_equal(outs[0][1][:k], want["dist"])
