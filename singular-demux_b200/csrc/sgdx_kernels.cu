@@ -43,8 +43,13 @@ __global__ void __launch_bounds__(kDirectThreads) sgdx_match_direct(const DevPar
 
         uint32_t best = kInfKey, nxt = kInfKey;
         auto consider = [&](uint32_t slo, uint32_t shi, uint32_t s) {
-            uint32_t d = __popc(((rd.lo ^ slo) | inv) | (rd.hi ^ shi));
-            uint32_t key = (d << 16) | s;
+            // two 3-input LOP3s: t = (lo ^ slo) | inv ; m = t | (hi ^ shi)
+            uint32_t t, m;
+            asm("lop3.b32 %0, %1, %2, %3, 0xBE;" : "=r"(t) : "r"(rd.lo), "r"(slo), "r"(inv));
+            asm("lop3.b32 %0, %1, %2, %3, 0xF6;" : "=r"(m) : "r"(t), "r"(rd.hi), "r"(shi));
+            uint32_t d = __popc(m);
+            uint32_t key;  // (d << 16) + s as one IMAD on the fma pipe (the alu pipe is the busy one)
+            asm("mad.lo.u32 %0, %1, 65536, %2;" : "=r"(key) : "r"(d), "r"(s));
             if (MODE == kModePreCompute) key = (d == skip) ? kInfKey : key;
             nxt = min(nxt, max(best, key));
             best = min(best, key);

@@ -117,7 +117,7 @@ PARAMS = [  # (M, delta, free_ns, max_no_calls)
 
 @pytest.mark.parametrize("kernel", KERNELS)
 @pytest.mark.parametrize("S,L,i1", [(1, 8, 0), (2, 4, 2), (7, 12, 0), (24, 16, 8), (96, 16, 8), (97, 20, 10), (384, 20, 10),
-                                    (300, 24, 12), (50, 32, 16), (33, 13, 5), (64, 6, 3), (5, 1, 0), (130, 31, 0)])
+                                    (300, 24, 12), (50, 32, 16), (33, 13, 5), (64, 6, 3), (3, 1, 0), (130, 31, 0)])
 def test_random_tables_and_reads_match_oracle(kernel, S, L, i1):
     rng = np.random.default_rng(S * 1000 + L)
     w, table, reads = _random_case(rng, S, L, i1)
@@ -143,7 +143,7 @@ def test_precompute_against_literal_map_oracle(kernel):
             S_, L_ = len(table), len(table[0])
             cfg = orc.Config(S_, L_, M, D, 1, -1, orc.MATCHER_PRECOMPUTE, i1, L - i1 if i1 else 0)
             o = orc.COracle(cfg, [bytes(t) for t in table])
-            assert o.has_map
+            assert o.has_map or M + D == 0  # M = delta = 0 makes pass 2 enumerate all 5^L strings
             _assert_same(st, got, o.run(reads, threads=8), reads.shape[0])
             st.close()
 
