@@ -137,7 +137,7 @@ def main():
     ap.add_argument("--config", default="C2", choices=["C1", "C2", "C3", "C4"])
     ap.add_argument("--reads", type=int, default=0, help="reads per GPU per step (default: the config's size, capped)")
     ap.add_argument("--impl", default="sgdx", choices=["sgdx", "reference"])
-    ap.add_argument("--kernel", type=int, default=0, help="0 auto, 1 direct, 2 bit-sliced")
+    ap.add_argument("--kernel", type=int, default=0, help="0 auto, 1 direct, 2 seeded")
     ap.add_argument("--ref-sample", type=int, default=0)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -236,7 +236,7 @@ def main():
     alg_bytes = ALG_BYTES(L) * n
     achieved = alg_bytes / (avg_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "traffic": None, "peak_source": peaks_src, "kernel": "sgdx_match_direct" if m.kernel == 1 else "sgdx_match_bitsliced",
+                "traffic": None, "peak_source": peaks_src, "kernel": "sgdx_match_direct" if m.kernel == 1 else "sgdx_match_seeded",
                 "algorithmic_bytes_per_read": ALG_BYTES(L), "actual_bytes_per_read": L + 3,
                 "avg_launch_ms": avg_ms}
     if rank == 0:
@@ -309,7 +309,7 @@ def main():
             "warmup": max(args.warmup, 3), "ms_per_step": total_ms_max / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
             "config": {"workload": workload_desc(w, n), "reads_per_gpu_per_step": n, "matcher": kind.value,
-                       "kernel": "direct" if m.kernel == 1 else "bitsliced",
+                       "kernel": "direct" if m.kernel == 1 else "seeded",
                        "input": "ASCII barcodes resident in HBM", "sharding": f"{world} shard(s) by read range, host-merged counters",
                        "l2": f"inputs {n * L / 1e6:.0f} MB + outputs {n * 3 / 1e6:.0f} MB per step, larger than the 126 MB L2"},
             "roofline": roofline, "cpu_baseline": cb, "e2e": e2e, "gpu_launches": int(launches),

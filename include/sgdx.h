@@ -46,7 +46,7 @@ extern "C" {
 /* kernel variants (both are hand-written sm_100a kernels with identical results) */
 #define SGDX_KERNEL_AUTO 0u
 #define SGDX_KERNEL_DIRECT 1u     /* per (read, sample) XOR/OR/POPC scan with best/second-best keys */
-#define SGDX_KERNEL_BITSLICED 2u  /* sample-transposed mismatch planes + carry-save threshold filter */
+#define SGDX_KERNEL_SEEDED 2u     /* pigeonhole seed index -> verify only the candidate samples; falls back to DIRECT when the seed index does not apply */
 
 #define SGDX_MAX_BARCODE_LEN 32u
 #define SGDX_MAX_SAMPLES 8192u

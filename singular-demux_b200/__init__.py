@@ -4,7 +4,7 @@ Host-side mirror (Python) of the reference's interface for this one path, over t
 include/sgdx.h.  Import name: ``singular_demux_b200`` (the directory is ``singular-demux_b200``; use
 ``sgdx_loader.load()`` from the repo root, or put this directory's parent on sys.path under that name).
 """
-from ._lib import (KERNEL_AUTO, KERNEL_BITSLICED, KERNEL_DIRECT, LIB_PATH, MATCHER_AUTO, MATCHER_CACHED_HAMMING,
+from ._lib import (KERNEL_AUTO, KERNEL_SEEDED, KERNEL_DIRECT, LIB_PATH, MATCHER_AUTO, MATCHER_CACHED_HAMMING,
                    MATCHER_PRECOMPUTE, NO_DIST, SgdxError, lib)
 from .matcher import (UNDETERMINED_NAME, CachedHammingDistanceMatcher, GpuMatcher, MatcherKind, MatchResult,
                       PreComputeMatcher, SampleMetadata, select_matcher)

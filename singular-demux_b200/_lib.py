@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsgdx.so")
 
 MATCHER_AUTO, MATCHER_CACHED_HAMMING, MATCHER_PRECOMPUTE = 0, 1, 2
-KERNEL_AUTO, KERNEL_DIRECT, KERNEL_BITSLICED = 0, 1, 2
+KERNEL_AUTO, KERNEL_DIRECT, KERNEL_SEEDED = 0, 1, 2
 NO_DIST = 0xFF
 MAX_BARCODE_LEN = 32
 MAX_SAMPLES = 8192

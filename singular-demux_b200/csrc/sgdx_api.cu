@@ -52,7 +52,9 @@ struct sgdx_handle {
     int sms = 148;
     DevParams base{};  // everything but the per-batch pointers
     uint2 *d_table = nullptr;
-    uint32_t *d_planes = nullptr;
+    uint32_t *d_seed_hdr = nullptr;
+    uint16_t *d_seed_ids = nullptr;
+    bool seeded = false;  // launches use sgdx_match_seeded
     HopSlot *d_hash1 = nullptr, *d_hash2 = nullptr;
     unsigned long long *d_hop_fwd = nullptr, *d_hop_rev = nullptr;
     unsigned long long *d_counters = nullptr;
@@ -99,6 +101,66 @@ static void build_hash(const std::vector<std::string> &keys, uint32_t len, std::
     }
 }
 
+// Pigeonhole seed index (sgdx_seeded.cu): T+1 chunks, bucket headers + sample-id runs.  *have = false
+// when the configuration gives no usable index (T+1 > L, or the tables would not fit shared memory).
+static int build_seed_index(sgdx_handle *h, const std::vector<uint2> &table, bool *have, double *est_candidates) {
+    DevParams &p = h->base;
+    *have = false;
+    p.seed_C = 0;
+    const uint32_t S = p.S, L = p.L;
+    // largest number of valid-position mismatches of any sample that can be best or a delta competitor
+    const uint64_t T = h->mode == kModeHamming ? (uint64_t)p.M + p.delta : (uint64_t)p.pc_limit;
+    if (T + 1 > L) return SGDX_OK;
+    const uint32_t C = (uint32_t)T + 1u;
+    const uint32_t wmax = C <= 8 ? 5u : 4u;  // keeps the headers <= 32 KB
+    uint32_t total = 0;
+    double est = 0.0;
+    std::vector<uint32_t> pos(C), w(C), off(C);
+    for (uint32_t c = 0; c < C; c++) {
+        uint32_t a = (uint32_t)((uint64_t)c * L / C), b = (uint32_t)((uint64_t)(c + 1) * L / C);
+        pos[c] = a;
+        w[c] = std::min(b - a, wmax);
+        off[c] = total;
+        total += 1u << (2 * w[c]);
+        est += (double)S / (double)(1u << (2 * w[c]));
+        p.seed_desc[c] = pos[c] | (w[c] << 8) | (off[c] << 16);
+    }
+    std::vector<uint32_t> hdr(total, 0u);
+    std::vector<uint16_t> ids((size_t)C * S, 0);
+    for (uint32_t c = 0; c < C; c++) {
+        const uint32_t wm = (1u << w[c]) - 1u;
+        auto key_of = [&](uint32_t s) { return ((table[s].x >> pos[c]) & wm) | (((table[s].y >> pos[c]) & wm) << w[c]); };
+        std::vector<uint32_t> cnt(1u << (2 * w[c]), 0u);
+        for (uint32_t s = 0; s < S; s++) cnt[key_of(s)]++;
+        uint32_t run = c * S;
+        for (uint32_t k = 0; k < cnt.size(); k++) {
+            hdr[off[c] + k] = (run << 14) | cnt[k];
+            run += cnt[k];
+            cnt[k] = 0;
+        }
+        for (uint32_t s = 0; s < S; s++) {  // ascending sample order inside a bucket
+            uint32_t k = key_of(s);
+            ids[(hdr[off[c] + k] >> 14) + cnt[k]++] = (uint16_t)s;
+        }
+    }
+    p.seed_hdr_total = total;
+    p.seed_ids_total = C * S;
+    if (seeded_smem_bytes(p) > 100u * 1024u) {  // keep >= 2 blocks per SM; larger tables stay on the direct kernel
+        p.seed_hdr_total = p.seed_ids_total = 0;
+        return SGDX_OK;
+    }
+    CU(cudaMalloc(&h->d_seed_hdr, hdr.size() * sizeof(uint32_t)));
+    CU(cudaMalloc(&h->d_seed_ids, ids.size() * sizeof(uint16_t)));
+    CU(cudaMemcpy(h->d_seed_hdr, hdr.data(), hdr.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(h->d_seed_ids, ids.data(), ids.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    p.seed_hdr = h->d_seed_hdr;
+    p.seed_ids = h->d_seed_ids;
+    p.seed_C = C;
+    *have = true;
+    *est_candidates = est;
+    return SGDX_OK;
+}
+
 extern "C" int sgdx_create(const sgdx_config *cfg, const uint8_t *barcodes, sgdx_handle **out) {
     if (!cfg || !barcodes || !out) return fail(SGDX_EINVAL, "sgdx_create: null argument");
     *out = nullptr;
@@ -107,7 +169,7 @@ extern "C" int sgdx_create(const sgdx_config *cfg, const uint8_t *barcodes, sgdx
     if (L < 1 || L > SGDX_MAX_BARCODE_LEN)
         return fail(SGDX_EINVAL, "barcode_len %u outside 1..%u", L, SGDX_MAX_BARCODE_LEN);
     if (cfg->matcher > SGDX_MATCHER_PRECOMPUTE) return fail(SGDX_EINVAL, "unknown matcher kind %u", cfg->matcher);
-    if (cfg->kernel > SGDX_KERNEL_BITSLICED) return fail(SGDX_EINVAL, "unknown kernel kind %u", cfg->kernel);
+    if (cfg->kernel > SGDX_KERNEL_SEEDED) return fail(SGDX_EINVAL, "unknown kernel kind %u", cfg->kernel);
     if ((cfg->index1_len == 0) != (cfg->index2_len == 0) ||
         (cfg->index1_len && cfg->index1_len + cfg->index2_len != L))
         return fail(SGDX_EINVAL, "index1_len + index2_len must equal barcode_len (or both be 0)");
@@ -130,7 +192,6 @@ extern "C" int sgdx_create(const sgdx_config *cfg, const uint8_t *barcodes, sgdx
         h->cfg.matcher = L <= 12 ? SGDX_MATCHER_PRECOMPUTE : SGDX_MATCHER_CACHED_HAMMING;
     if (h->cfg.slots == 0) h->cfg.slots = 2;
     if (h->cfg.slots > 64) h->cfg.slots = 64;
-    if (h->cfg.kernel == SGDX_KERNEL_AUTO) h->cfg.kernel = SGDX_KERNEL_DIRECT;
     h->mode = h->cfg.matcher == SGDX_MATCHER_PRECOMPUTE ? kModePreCompute : kModeHamming;
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, cfg->device));
@@ -200,6 +261,22 @@ extern "C" int sgdx_create(const sgdx_config *cfg, const uint8_t *barcodes, sgdx
         p.hop_rev = h->d_hop_rev;
     }
 
+    // kernel choice: the seeded kernel needs its index to exist (T+1 <= L, shared memory fits); AUTO takes
+    // it when the expected number of candidates per read is well below a full scan of the table
+    {
+        double est = 0.0;
+        bool have = false;
+        if (h->cfg.kernel != SGDX_KERNEL_DIRECT) {
+            if (int rc = build_seed_index(h, table, &have, &est)) {
+                sgdx_destroy(h);
+                return rc;
+            }
+        }
+        if (h->cfg.kernel == SGDX_KERNEL_AUTO) h->seeded = have && 2.0 * est + 16.0 < (double)S;
+        else h->seeded = have && h->cfg.kernel == SGDX_KERNEL_SEEDED;
+        h->cfg.kernel = h->seeded ? SGDX_KERNEL_SEEDED : SGDX_KERNEL_DIRECT;
+    }
+
     h->slots.resize(h->cfg.slots);
     for (Slot &s : h->slots) {
         CU(cudaStreamCreateWithFlags(&s.own, cudaStreamNonBlocking));
@@ -224,7 +301,8 @@ extern "C" void sgdx_destroy(sgdx_handle *h) {
         if (s.own) cudaStreamDestroy(s.own);
     }
     cudaFree(h->d_table);
-    cudaFree(h->d_planes);
+    cudaFree(h->d_seed_hdr);
+    cudaFree(h->d_seed_ids);
     cudaFree(h->d_hash1);
     cudaFree(h->d_hash2);
     cudaFree(h->d_hop_fwd);
@@ -264,7 +342,8 @@ static int run_kernels(sgdx_handle *h, Slot &s, const uint8_t *d_ascii, const ui
     p.out_idx = d_idx;
     p.out_dist = d_dist;
     CU(cudaEventRecord(s.e0, s.stream));
-    CU(launch_direct(p, h->mode, d_packed != nullptr, h->sms, s.stream));
+    if (h->seeded) CU(launch_seeded(p, h->mode, d_packed != nullptr, h->sms, s.stream));
+    else CU(launch_direct(p, h->mode, d_packed != nullptr, h->sms, s.stream));
     CU(cudaEventRecord(s.e1, s.stream));
     s.timed = true;
     if (n) h->launches.fetch_add(1);

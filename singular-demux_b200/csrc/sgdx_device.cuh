@@ -42,10 +42,18 @@ struct DevParams {
     uint32_t hmask1, hmask2;     // capacity - 1
     unsigned long long *hop_fwd; // [u1][u2]  barcode = I1[a] ++ I2[b]
     unsigned long long *hop_rev; // [u1][u2]  barcode = I2[b] ++ I1[a]   (reversed-orientation rule only)
-    // bit-sliced kernel
-    const uint32_t *planes;      // [L][5][W4*4] mismatch planes, row 4 = no-call/foreign (all zero)
-    uint32_t W;                  // number of 32-sample words, multiple of 4
-    uint32_t T;                  // candidate threshold on valid-position mismatches
+    // seeded kernel: pigeonhole seed index over the expected barcodes (built by sgdx_create).
+    // The L positions are cut into seed_C = T+1 disjoint chunks, T = largest number of valid-position
+    // mismatches a sample that matters can have; chunk c is keyed by its first seed_w[c] bases
+    // (key = lo bits | hi bits << w).  seed_hdr[seed_off[c] + key] = (start << 14) | count addresses the
+    // run seed_ids[start .. start+count) of samples whose barcode has that key in chunk c.
+    const uint32_t *seed_hdr;
+    const uint16_t *seed_ids;
+    uint32_t seed_C;             // 0 = no seed index (direct kernel only)
+    uint32_t seed_hdr_total;     // entries in seed_hdr
+    uint32_t seed_ids_total;     // entries in seed_ids (= seed_C * S)
+    uint32_t seed_desc[32];      // chunk c: first base of its key window | window width (1..6) << 8 |
+                                 //          offset of its bucket headers in seed_hdr << 16
 };
 
 struct Rd {  // one observed barcode as bit planes; bit j = base j, bits >= L are zero

@@ -13,7 +13,7 @@ from oracle import oracle as orc
 sg = sgdx_loader.load()
 pytestmark = pytest.mark.gpu
 
-KERNELS = [sg.KERNEL_DIRECT, sg.KERNEL_BITSLICED]
+KERNELS = [sg.KERNEL_DIRECT, sg.KERNEL_SEEDED]
 ORC_KIND = {sg.MatcherKind.CachedHammingDistance: orc.MATCHER_CACHED_HAMMING, sg.MatcherKind.PreCompute: orc.MATCHER_PRECOMPUTE}
 CLS = {sg.MatcherKind.CachedHammingDistance: sg.CachedHammingDistanceMatcher, sg.MatcherKind.PreCompute: sg.PreComputeMatcher}
 
@@ -127,6 +127,40 @@ def test_random_tables_and_reads_match_oracle(kernel, S, L, i1):
             st = _stage(table, kind, M, D, F, mnc, il, kernel)
             got = st.demultiplex(reads)
             want = _oracle(table, kind, M, D, F, mnc, il, reads, force_closed_form=True)
+            _assert_same(st, got, want, reads.shape[0])
+            st.close()
+
+
+def test_seeded_kernel_engages_and_falls_back():
+    """AUTO picks the seeded kernel where its index pays, SEEDED is honoured whenever an index exists, and
+    configurations without one (T+1 > L) run the direct kernel."""
+    t96 = sg.synth.C1.table()
+    cases = [  # (table, M, D, requested, effective)
+        (t96, 1, 2, sg.KERNEL_AUTO, sg.KERNEL_SEEDED), (t96, 1, 2, sg.KERNEL_DIRECT, sg.KERNEL_DIRECT),
+        (t96, 1, 2, sg.KERNEL_SEEDED, sg.KERNEL_SEEDED), (t96, 9, 9, sg.KERNEL_SEEDED, sg.KERNEL_DIRECT),
+        (t96, 4, 4, sg.KERNEL_SEEDED, sg.KERNEL_SEEDED), (t96, 4, 4, sg.KERNEL_AUTO, sg.KERNEL_DIRECT),
+        (t96[:2], 1, 2, sg.KERNEL_AUTO, sg.KERNEL_DIRECT),
+    ]
+    for table, M, D, req, eff in cases:
+        m = sg.CachedHammingDistanceMatcher([bytes(t) for t in table], M, D, 1, kernel=req)
+        assert m.kernel == eff, (len(table), M, D, req, m.kernel)
+        m.close()
+
+
+@pytest.mark.parametrize("p_n,p_x", [(0.03, 0.0), (0.10, 0.01), (0.30, 0.05)])
+@pytest.mark.parametrize("S,L,i1,M,D,F", [(384, 20, 10, 1, 2, 1), (200, 24, 12, 3, 1, 2), (96, 16, 8, 2, 1, 3),
+                                            (1536, 24, 12, 3, 1, 1), (60, 32, 16, 2, 2, 4), (500, 12, 6, 1, 1, 1)])
+def test_seeded_no_call_paths(S, L, i1, M, D, F, p_n, p_x):
+    """No-call heavy reads: windows with one invalid base (4 buckets), windows with several (warp-cooperative
+    scan of the queue) and reads that cannot match at all, for both rule sets and with the N gate."""
+    rng = np.random.default_rng(S + L + int(p_n * 100))
+    w, table, reads = _random_case(rng, S, L, i1, p_n=p_n, p_x=p_x, n=60000)
+    for kind in (sg.MatcherKind.CachedHammingDistance, sg.MatcherKind.PreCompute):
+        for mnc in (None, 2):
+            st = _stage(table, kind, M, D, F, mnc, w.index_lengths, sg.KERNEL_SEEDED)
+            assert st.matcher.kernel == sg.KERNEL_SEEDED
+            got = st.demultiplex(reads)
+            want = _oracle(table, kind, M, D, F, mnc, w.index_lengths, reads, force_closed_form=True)
             _assert_same(st, got, want, reads.shape[0])
             st.close()
 
