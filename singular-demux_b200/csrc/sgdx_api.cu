@@ -54,6 +54,7 @@ struct sgdx_handle {
     uint2 *d_table = nullptr;
     uint32_t *d_seed_hdr = nullptr;
     uint16_t *d_seed_ids = nullptr;
+    uint32_t *d_ex_slots = nullptr, *d_ex_ascii = nullptr;
     bool seeded = false;  // launches use sgdx_match_seeded
     HopSlot *d_hash1 = nullptr, *d_hash2 = nullptr;
     unsigned long long *d_hop_fwd = nullptr, *d_hop_rev = nullptr;
@@ -158,6 +159,49 @@ static int build_seed_index(sgdx_handle *h, const std::vector<uint2> &table, boo
     p.seed_C = C;
     *have = true;
     *est_candidates = est;
+    return SGDX_OK;
+}
+
+// Exact-match front end of the seeded kernel (sgdx_seeded.cu): barcode rows as padded ASCII words and
+// an open-addressing table over them.  Enabled only when a byte-exact hit decides the read on its own:
+// min pairwise distance of the table > min_delta.
+static int build_exact_table(sgdx_handle *h, const uint8_t *barcodes, const std::vector<uint2> &table) {
+    DevParams &p = h->base;
+    const uint32_t S = p.S, L = p.L;
+    p.ex_on = 0;
+    p.Lw = (L + 3u) / 4u;
+    uint32_t dmin = 0xFFFFu;
+    for (uint32_t i = 0; i < S && dmin > 0; i++)
+        for (uint32_t j = i + 1; j < S; j++) {
+            uint32_t d = (uint32_t)__builtin_popcount((table[i].x ^ table[j].x) | (table[i].y ^ table[j].y));
+            if (d < dmin) dmin = d;
+        }
+    p.dmin = dmin;
+    static const uint32_t K[8] = {0x9E3779B1u, 0x85EBCA77u, 0xC2B2AE3Du, 0x27D4EB2Fu,
+                                  0x165667B1u, 0xD3A2646Du, 0xFD7046C5u, 0xB55A4F09u};
+    for (int i = 0; i < 8; i++) p.ex_k[i] = K[i];
+    uint32_t bits = 6;
+    while ((1u << bits) < 4u * S) bits++;
+    p.ex_bits = bits;
+    if (dmin <= p.delta) return SGDX_OK;                       // an exact hit could still be delta-rejected
+    if (exact_smem_bytes(p) > 100u * 1024u) return SGDX_OK;    // large tables: general path only
+    std::vector<uint32_t> rows((size_t)S * p.Lw, 0x41414141u), slots((size_t)1 << bits, 0u);
+    for (uint32_t s = 0; s < S; s++) {
+        memcpy(&rows[(size_t)s * p.Lw], barcodes + (size_t)s * L, L);  // little-endian host; tail bytes stay 'A'
+        uint32_t hsh = 0;
+        for (uint32_t i = 0; i < p.Lw; i++) hsh += rows[(size_t)s * p.Lw + i] * K[i];
+        hsh = ex_mix(hsh);
+        uint32_t slot = hsh >> (32u - bits);
+        while (slots[slot]) slot = (slot + 1u) & ((1u << bits) - 1u);
+        slots[slot] = ((hsh & 0xFFFFu) << 16) | (s + 1u);
+    }
+    CU(cudaMalloc(&h->d_ex_slots, slots.size() * sizeof(uint32_t)));
+    CU(cudaMalloc(&h->d_ex_ascii, rows.size() * sizeof(uint32_t)));
+    CU(cudaMemcpy(h->d_ex_slots, slots.data(), slots.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(h->d_ex_ascii, rows.data(), rows.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    p.ex_slots = h->d_ex_slots;
+    p.ex_ascii = h->d_ex_ascii;
+    p.ex_on = 1;
     return SGDX_OK;
 }
 
@@ -274,6 +318,11 @@ extern "C" int sgdx_create(const sgdx_config *cfg, const uint8_t *barcodes, sgdx
         }
         if (h->cfg.kernel == SGDX_KERNEL_AUTO) h->seeded = have && 2.0 * est + 16.0 < (double)S;
         else h->seeded = have && h->cfg.kernel == SGDX_KERNEL_SEEDED;
+        if (h->seeded)
+            if (int rc = build_exact_table(h, barcodes, table)) {
+                sgdx_destroy(h);
+                return rc;
+            }
         h->cfg.kernel = h->seeded ? SGDX_KERNEL_SEEDED : SGDX_KERNEL_DIRECT;
     }
 
@@ -303,6 +352,8 @@ extern "C" void sgdx_destroy(sgdx_handle *h) {
     cudaFree(h->d_table);
     cudaFree(h->d_seed_hdr);
     cudaFree(h->d_seed_ids);
+    cudaFree(h->d_ex_slots);
+    cudaFree(h->d_ex_ascii);
     cudaFree(h->d_hash1);
     cudaFree(h->d_hash2);
     cudaFree(h->d_hop_fwd);

@@ -54,6 +54,16 @@ struct DevParams {
     uint32_t seed_ids_total;     // entries in seed_ids (= seed_C * S)
     uint32_t seed_desc[32];      // chunk c: first base of its key window | window width (1..6) << 8 |
                                  //          offset of its bucket headers in seed_hdr << 16
+    // exact-match front end of the seeded kernel: an open-addressing table of the expected barcodes keyed
+    // by a multiplicative hash of their ASCII words.  A read that equals a barcode byte for byte is a
+    // Match with distance 0 without any search iff min pairwise table distance dmin > min_delta
+    // (triangle inequality: every other sample is >= dmin away) -- ex_on says so.
+    const uint32_t *ex_slots;    // [1 << ex_bits]  (tag << 16) | (sample + 1), 0 = empty
+    const uint32_t *ex_ascii;    // [S][Lw] barcode bytes as little-endian words, tail bytes 'A'
+    uint32_t ex_on, ex_bits;
+    uint32_t Lw;                 // ceil(L / 4)
+    uint32_t dmin;               // min pairwise Hamming distance of the table (0xFFFF for S == 1)
+    uint32_t ex_k[8];            // odd multipliers of the word hash
 };
 
 struct Rd {  // one observed barcode as bit planes; bit j = base j, bits >= L are zero
@@ -64,6 +74,14 @@ __host__ __device__ inline uint64_t mix64(uint64_t z) {
     z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
     z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
     return z ^ (z >> 31);
+}
+
+// finaliser of the exact-match word hash (host builds the table with the same function)
+__host__ __device__ inline uint32_t ex_mix(uint32_t h) {
+    h ^= h >> 16;
+    h *= 0x85EBCA6Bu;
+    h ^= h >> 13;
+    return h;
 }
 
 // 0x80 in every byte of z that is zero (exact, no cross-byte borrow)

@@ -1,27 +1,136 @@
-// sgdx_seeded.cu -- the seed-and-verify assignment kernel (sm_100a).
+// sgdx_seeded.cu -- the seed-and-verify assignment kernels (sm_100a).
 //
 // Same results as sgdx_match_direct (matcher.rs:273-348 / 121-262, demux.rs:524-538, metrics.rs:428-437,
-// 658-676), but instead of scoring every (read, sample) pair it enumerates only the samples that can
-// influence the verdict.  A sample matters only if its number of mismatches over the read's valid
-// (non-N, non-foreign) positions is <= T, with T = max_mismatches + min_delta for the Hamming rule set
-// and T = max(M, M+delta-1) for the PreCompute rule set ("why T is enough").  Cut the
-// barcode into T+1 disjoint chunks: by pigeonhole such a sample agrees with the read on every valid
-// position of at least one chunk, so it sits in the bucket that chunk's bases select.  Buckets come from
-// a small index built once per matcher (sgdx_create) and staged in shared memory next to the table.
+// 658-676), but instead of scoring every (read, sample) pair they enumerate only the samples that can
+// influence the verdict.
 //
+// Seed index.  A sample matters only if its number of mismatches over the read's valid (non-N,
+// non-foreign) positions is <= T, with T = max_mismatches + min_delta for the Hamming rule set and
+// T = max(M, M+delta-1) for the PreCompute rule set ("why T is enough").  Cut the barcode
+// into T+1 disjoint chunks: by pigeonhole such a sample agrees with the read on every valid position of
+// at least one chunk, so it sits in the bucket that chunk's bases select.
 //   - chunk window without invalid positions      -> one bucket
 //   - chunk window with exactly one invalid base  -> the 4 buckets of its possible values
-//   - anything worse (rare)                       -> the read is queued and scored against all samples
-//                                                    by a whole warp (per-lane best/second-best keys,
+//   - anything worse (rare), or no index at all   -> the read is scored against all samples by a whole
+//                                                    warp (per-lane best/second-best keys, then
 //                                                    __reduce_min_sync across the warp)
 // Reads that cannot match whatever the table holds (too many no-calls / foreign bytes for M, or the
 // max_no_calls gate) skip the search.  Candidates are scored exactly like the direct kernel:
 // popc(((lo^slo)|inv)|(hi^shi)), key = distance << 16 | sample; a sample reached through several
 // chunks produces the same key twice, which the `key != best` guard makes harmless.
+//
+// Exact-match front end (sgdx_match_exact_first).  Most reads of a real run equal their sample's
+// barcode byte for byte.  Such a read is Match(sample, 0) without any search whenever the table's
+// minimum pairwise distance exceeds min_delta (every other sample is then further than delta away, by
+// the triangle inequality), so the kernel first looks the raw ASCII words up in an open-addressing
+// table of the barcodes (multiplicative word hash on the fma pipe, 16-bit tag, byte-exact verify).
+// Everything else goes to a block-level queue that is drained by the full block, one thread per read,
+// through the general path above -- so the divergent work runs with full warps, not with the one or
+// two slow lanes a warp of fresh reads would have.
 #include "sgdx_kernels.h"
 
 namespace sgdx {
 
+// ------------------------------------------------------------------------------------------------
+// shared pieces
+// ------------------------------------------------------------------------------------------------
+template <uint32_t MODE>
+__device__ __forceinline__ void score(const Rd &rd, uint32_t inv, uint32_t skip, uint32_t slo, uint32_t shi, uint32_t s,
+                                      uint32_t &best, uint32_t &nxt) {
+    uint32_t t, m;
+    asm("lop3.b32 %0, %1, %2, %3, 0xBE;" : "=r"(t) : "r"(rd.lo), "r"(slo), "r"(inv));  // (lo ^ slo) | inv
+    asm("lop3.b32 %0, %1, %2, %3, 0xF6;" : "=r"(m) : "r"(t), "r"(rd.hi), "r"(shi));    // t | (hi ^ shi)
+    uint32_t d = __popc(m);
+    uint32_t key;
+    asm("mad.lo.u32 %0, %1, 65536, %2;" : "=r"(key) : "r"(d), "r"(s));
+    if (MODE == kModePreCompute) key = (d == skip) ? kInfKey : key;
+    if (key != best) {  // the same sample seen through another chunk
+        nxt = min(nxt, max(best, key));
+        best = min(best, key);
+    }
+}
+
+// reads no table can match: every sample is further than M away, or the no-call gate (demux.rs:528-531)
+template <uint32_t MODE>
+__device__ __forceinline__ bool cannot_match(const DevParams &p, const Rd &rd) {
+    const uint32_t n_nc = __popc(rd.nmask), n_x = __popc(rd.xmask);
+    bool dead = p.max_no_calls >= 0 && n_nc > (uint32_t)p.max_no_calls;
+    if (MODE == kModeHamming) dead |= n_x + (n_nc > p.free_ns ? n_nc - p.free_ns : 0u) > p.M;
+    else dead |= rd.xmask != 0u || n_nc > p.M;
+    return dead;
+}
+
+// Enumerate the seed buckets of one read. Returns false when a key window holds two or more invalid
+// bases (the caller hands the read to the all-samples scan).
+template <uint32_t MODE>
+__device__ __forceinline__ bool seed_search(const DevParams &p, const uint32_t *__restrict__ hdr,
+                                            const uint16_t *__restrict__ ids, const uint2 *__restrict__ table,
+                                            const Rd &rd, uint32_t &best, uint32_t &nxt) {
+    const uint32_t inv = rd.nmask | rd.xmask;
+    const uint32_t skip = (MODE == kModePreCompute && rd.nmask != 0u) ? p.M + 1u : 0xFFFFu;
+    for (uint32_t c = 0; c < p.seed_C; c++) {
+        const uint32_t desc = p.seed_desc[c];
+        const uint32_t pos = desc & 0xFFu, w = (desc >> 8) & 0xFFu, off = desc >> 16;
+        const uint32_t wm = (1u << w) - 1u;
+        const uint32_t iv = (inv >> pos) & wm;
+        const uint32_t key0 = ((rd.lo >> pos) & wm) | (((rd.hi >> pos) & wm) << w);
+        uint32_t nvar = 1u, j = 0u;
+        if (iv) {
+            if (iv & (iv - 1u)) return false;
+            nvar = 4u;
+            j = __ffs(iv) - 1u;
+        }
+        for (uint32_t b = 0; b < nvar; b++) {
+            const uint32_t key = key0 | ((b & 1u) << j) | ((b >> 1) << (w + j));
+            const uint32_t h = hdr[off + key];
+            const uint32_t start = h >> 14, cnt = h & 0x3FFFu;
+            for (uint32_t i = 0; i < cnt; i++) {
+                const uint32_t s = ids[start + i];
+                const uint2 t = table[s];
+                score<MODE>(rd, inv, skip, t.x, t.y, s, best, nxt);
+            }
+        }
+    }
+    return true;
+}
+
+// one warp, one read, all samples
+template <uint32_t MODE>
+__device__ __forceinline__ Verdict warp_scan(const DevParams &p, const uint2 *__restrict__ table, const Rd &rd,
+                                             uint32_t lane) {
+    const uint32_t inv = rd.nmask | rd.xmask;
+    const uint32_t skip = (MODE == kModePreCompute && rd.nmask != 0u) ? p.M + 1u : 0xFFFFu;
+    uint32_t b = kInfKey, n2 = kInfKey;
+    for (uint32_t s = lane; s < p.S; s += 32u) {
+        const uint2 t = table[s];
+        score<MODE>(rd, inv, skip, t.x, t.y, s, b, n2);
+    }
+    const uint32_t gb = __reduce_min_sync(0xFFFFFFFFu, b);
+    const uint32_t gn = __reduce_min_sync(0xFFFFFFFFu, b == gb ? n2 : b);  // keys are unique per sample
+    return apply_rules<MODE>(p, rd, gb, gn);
+}
+
+// verdict of one read written by one thread (the warp-cooperative path)
+__device__ __forceinline__ void emit_single(const DevParams &p, uint64_t r, const Rd &rd, const Verdict &v,
+                                            uint32_t *hist) {
+    p.out_idx[r] = (uint16_t)v.bin;
+    if (p.out_dist) p.out_dist[r] = (uint8_t)v.dist;
+    uint32_t cls = v.dist == 0u ? 1u : (v.dist == 1u ? 2u : 0u);
+    atomicAdd(&hist[v.bin * 3u + cls], 1u);
+    if (p.hop_on && v.bin == p.S) hop_check(p, rd);
+}
+
+static uint32_t persistent_grid(uint64_t n, uint32_t threads, int sms, int per_sm) {
+    uint64_t tiles = (n + threads - 1) / threads;
+    uint64_t cap = (uint64_t)sms * (uint64_t)per_sm;  // persistent grid: a multiple of the SM count
+    return (uint32_t)(tiles < cap ? (tiles ? tiles : 1) : cap);
+}
+
+// ------------------------------------------------------------------------------------------------
+// sgdx_match_seeded: one thread per read through the general path, tables in shared memory.
+// Used for packed input and for tables whose minimum pairwise distance does not allow the exact-match
+// shortcut.
+// ------------------------------------------------------------------------------------------------
 struct SeedSmem {
     uint4 *dq_rd;        // [threads] planes of the reads queued for the all-samples scan
     uint2 *table;        // [S]
@@ -51,32 +160,6 @@ size_t seeded_smem_bytes(const DevParams &p) {
     return seed_carve(nullptr, kSeededThreads, p.S, p.seed_hdr_total, p.seed_ids_total, nullptr);
 }
 
-template <uint32_t MODE>
-__device__ __forceinline__ void score(const Rd &rd, uint32_t inv, uint32_t skip, uint32_t slo, uint32_t shi, uint32_t s,
-                                      uint32_t &best, uint32_t &nxt) {
-    uint32_t t, m;
-    asm("lop3.b32 %0, %1, %2, %3, 0xBE;" : "=r"(t) : "r"(rd.lo), "r"(slo), "r"(inv));  // (lo ^ slo) | inv
-    asm("lop3.b32 %0, %1, %2, %3, 0xF6;" : "=r"(m) : "r"(t), "r"(rd.hi), "r"(shi));    // t | (hi ^ shi)
-    uint32_t d = __popc(m);
-    uint32_t key;
-    asm("mad.lo.u32 %0, %1, 65536, %2;" : "=r"(key) : "r"(d), "r"(s));
-    if (MODE == kModePreCompute) key = (d == skip) ? kInfKey : key;
-    if (key != best) {  // the same sample seen through another chunk
-        nxt = min(nxt, max(best, key));
-        best = min(best, key);
-    }
-}
-
-// verdict of one read written by one thread (the warp-cooperative path)
-__device__ __forceinline__ void emit_single(const DevParams &p, uint64_t r, const Rd &rd, const Verdict &v,
-                                            uint32_t *hist) {
-    p.out_idx[r] = (uint16_t)v.bin;
-    if (p.out_dist) p.out_dist[r] = (uint8_t)v.dist;
-    uint32_t cls = v.dist == 0u ? 1u : (v.dist == 1u ? 2u : 0u);
-    atomicAdd(&hist[v.bin * 3u + cls], 1u);
-    if (p.hop_on && v.bin == p.S) hop_check(p, rd);
-}
-
 template <uint32_t MODE, bool PACKED>
 __global__ void __launch_bounds__(kSeededThreads) sgdx_match_seeded(const DevParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -93,52 +176,16 @@ __global__ void __launch_bounds__(kSeededThreads) sgdx_match_seeded(const DevPar
     __syncthreads();
 
     const bool words_ok = (p.L & 3u) == 0u && (reinterpret_cast<uintptr_t>(p.reads_ascii) & 3u) == 0u;
-    const uint32_t C = p.seed_C;
 
     for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < p.n; base += (uint64_t)gridDim.x * blockDim.x) {
         const uint64_t r = base + threadIdx.x;
-        bool active = r < p.n;
+        const bool active = r < p.n;
         Rd rd = {0u, 0u, 0u, 0u};
         if (active) rd = PACKED ? load_packed(p.reads_packed, r, p.L) : load_ascii(p.reads_ascii, r, p.L, words_ok);
-        const uint32_t inv = rd.nmask | rd.xmask;
-        const uint32_t n_nc = __popc(rd.nmask), n_x = __popc(rd.xmask);
-        const uint32_t skip = (MODE == kModePreCompute && rd.nmask != 0u) ? p.M + 1u : 0xFFFFu;
-
-        // reads no table can match: every sample is further than M away / the no-call gate (demux.rs:528-531)
-        bool dead = p.max_no_calls >= 0 && n_nc > (uint32_t)p.max_no_calls;
-        if (MODE == kModeHamming) dead |= n_x + (n_nc > p.free_ns ? n_nc - p.free_ns : 0u) > p.M;
-        else dead |= rd.xmask != 0u || n_nc > p.M;
 
         uint32_t best = kInfKey, nxt = kInfKey;
         bool queued = false;
-        if (active && !dead) {
-            for (uint32_t c = 0; c < C; c++) {
-                const uint32_t desc = p.seed_desc[c];
-                const uint32_t pos = desc & 0xFFu, w = (desc >> 8) & 0xFFu, off = desc >> 16;
-                const uint32_t wm = (1u << w) - 1u;
-                const uint32_t iv = (inv >> pos) & wm;
-                const uint32_t key0 = ((rd.lo >> pos) & wm) | (((rd.hi >> pos) & wm) << w);
-                uint32_t nvar = 1u, j = 0u;
-                if (iv) {
-                    if (iv & (iv - 1u)) {  // two or more invalid bases in one window: leave it to a warp
-                        queued = true;
-                        break;
-                    }
-                    nvar = 4u;
-                    j = __ffs(iv) - 1u;
-                }
-                for (uint32_t b = 0; b < nvar; b++) {
-                    const uint32_t key = key0 | ((b & 1u) << j) | ((b >> 1) << (w + j));
-                    const uint32_t h = sm.hdr[off + key];
-                    const uint32_t start = h >> 14, cnt = h & 0x3FFFu;
-                    for (uint32_t i = 0; i < cnt; i++) {
-                        const uint32_t s = sm.ids[start + i];
-                        const uint2 t = sm.table[s];
-                        score<MODE>(rd, inv, skip, t.x, t.y, s, best, nxt);
-                    }
-                }
-            }
-        }
+        if (active && !cannot_match<MODE>(p, rd)) queued = !seed_search<MODE>(p, sm.hdr, sm.ids, sm.table, rd, best, nxt);
         if (queued) {
             uint32_t slot = atomicAdd(sm.dq_count, 1u);
             sm.dq_rd[slot] = make_uint4(rd.lo, rd.hi, rd.nmask, rd.xmask);
@@ -154,19 +201,8 @@ __global__ void __launch_bounds__(kSeededThreads) sgdx_match_seeded(const DevPar
             for (uint32_t q = warp; q < nq; q += nwarps) {
                 const uint4 qv = sm.dq_rd[q];
                 const Rd qrd = {qv.x, qv.y, qv.z, qv.w};
-                const uint32_t qinv = qrd.nmask | qrd.xmask;
-                const uint32_t qskip = (MODE == kModePreCompute && qrd.nmask != 0u) ? p.M + 1u : 0xFFFFu;
-                uint32_t b = kInfKey, n2 = kInfKey;
-                for (uint32_t s = lane; s < p.S; s += 32u) {
-                    const uint2 t = sm.table[s];
-                    score<MODE>(qrd, qinv, qskip, t.x, t.y, s, b, n2);
-                }
-                const uint32_t gb = __reduce_min_sync(0xFFFFFFFFu, b);
-                const uint32_t gn = __reduce_min_sync(0xFFFFFFFFu, b == gb ? n2 : b);  // keys are unique per sample
-                if (lane == 0) {
-                    Verdict qvd = apply_rules<MODE>(p, qrd, gb, gn);
-                    emit_single(p, base + sm.dq_tid[q], qrd, qvd, sm.hist);
-                }
+                Verdict qvd = warp_scan<MODE>(p, sm.table, qrd, lane);
+                if (lane == 0) emit_single(p, base + sm.dq_tid[q], qrd, qvd, sm.hist);
             }
             __syncthreads();  // the queue and its counter are free again before the next tile pushes
         }
@@ -179,12 +215,6 @@ __global__ void __launch_bounds__(kSeededThreads) sgdx_match_seeded(const DevPar
     }
 }
 
-static uint32_t seeded_grid(uint64_t n, int sms, int per_sm) {
-    uint64_t tiles = (n + kSeededThreads - 1) / kSeededThreads;
-    uint64_t cap = (uint64_t)sms * (uint64_t)per_sm;  // persistent grid: a multiple of the SM count
-    return (uint32_t)(tiles < cap ? (tiles ? tiles : 1) : cap);
-}
-
 template <uint32_t MODE, bool PACKED>
 static cudaError_t launch_seeded_t(const DevParams &p, int sms, cudaStream_t stream) {
     size_t smem = seeded_smem_bytes(p);
@@ -195,12 +225,238 @@ static cudaError_t launch_seeded_t(const DevParams &p, int sms, cudaStream_t str
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kSeededThreads, smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
-    kern<<<seeded_grid(p.n, sms, per_sm), kSeededThreads, smem, stream>>>(p);
+    kern<<<persistent_grid(p.n, kSeededThreads, sms, per_sm), kSeededThreads, smem, stream>>>(p);
     return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// sgdx_match_exact_first: exact-match front end + queued general path (ASCII input).
+// ------------------------------------------------------------------------------------------------
+constexpr uint32_t kExactReadsPerThread = 4;  // reads per thread between two block barriers
+
+struct ExactSmem {
+    unsigned long long *qr;  // [(R+1)*threads] read ids waiting for the general path
+    uint32_t *slots;         // [1 << ex_bits]
+    uint32_t *ascii;         // [S * Lw]
+    uint32_t *whist;         // [nwarps][S] perfect matches found by the front end, private per warp
+    uint32_t *hist;          // [(S+1)*3] general path
+    uint32_t *cq;            // [threads] queue entries that need the all-samples scan
+    uint32_t *counts;        // [0] = queue fill, [1] = cq fill
+};
+
+__host__ __device__ inline size_t exact_carve(unsigned char *base, uint32_t threads, uint32_t S, uint32_t Lw,
+                                              uint32_t ex_bits, ExactSmem *out) {
+    size_t o = 0;
+    ExactSmem s;
+    s.qr = reinterpret_cast<unsigned long long *>(base + o); o += (size_t)threads * (kExactReadsPerThread + 1) * 8;
+    s.slots = reinterpret_cast<uint32_t *>(base + o);        o += (size_t)4 << ex_bits;
+    s.ascii = reinterpret_cast<uint32_t *>(base + o);        o += (size_t)S * Lw * 4;
+    s.whist = reinterpret_cast<uint32_t *>(base + o);        o += (size_t)(threads / 32) * S * 4;
+    s.hist = reinterpret_cast<uint32_t *>(base + o);         o += (size_t)(S + 1) * 3 * 4;
+    s.cq = reinterpret_cast<uint32_t *>(base + o);           o += (size_t)threads * 4;
+    s.counts = reinterpret_cast<uint32_t *>(base + o);       o += 16;
+    if (out) *out = s;
+    return o;
+}
+
+size_t exact_smem_bytes(const DevParams &p) {
+    return exact_carve(nullptr, kSeededThreads, p.S, p.Lw, p.ex_bits, nullptr);
+}
+
+// LW little-endian words of read r; bytes past L read as 'A' (what the table's rows are padded with)
+template <uint32_t LW, bool ALIGNED>
+__device__ __forceinline__ void load_words(const uint8_t *__restrict__ reads, uint64_t r, uint32_t L,
+                                           uint32_t (&rw)[LW]) {
+    if (ALIGNED) {
+        const uint32_t *pw = reinterpret_cast<const uint32_t *>(reads + r * (uint64_t)(LW * 4u));
+#pragma unroll
+        for (uint32_t i = 0; i < LW; i++) rw[i] = __ldg(pw + i);
+    } else {
+        const uintptr_t addr = reinterpret_cast<uintptr_t>(reads) + r * (uint64_t)L;
+        const uint32_t a = (uint32_t)(addr & 3u);
+        const uint32_t *pw = reinterpret_cast<const uint32_t *>(addr - a);
+        const uint32_t k = (a + L + 3u) >> 2;  // aligned words that hold at least one byte of the read
+        uint32_t t[LW + 1];
+#pragma unroll
+        for (uint32_t i = 0; i < LW + 1; i++) t[i] = i < k ? __ldg(pw + i) : 0u;
+#pragma unroll
+        for (uint32_t i = 0; i < LW; i++) rw[i] = __funnelshift_r(t[i], t[i + 1], a * 8u);
+        const uint32_t tail = L & 3u;
+        if (tail) {
+            const uint32_t keep = (1u << (8u * tail)) - 1u;
+            rw[LW - 1] = (rw[LW - 1] & keep) | (0x41414141u & ~keep);
+        }
+    }
+}
+
+template <uint32_t MODE, uint32_t LW, bool ALIGNED>
+__global__ void __launch_bounds__(kSeededThreads) sgdx_match_exact_first(const DevParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    ExactSmem sm;
+    exact_carve(smem_raw, kSeededThreads, p.S, LW, p.ex_bits, &sm);
+    const uint32_t nbins = (p.S + 1u) * 3u;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    constexpr uint32_t nwarps = kSeededThreads / 32, T = kSeededThreads, R = kExactReadsPerThread;
+    constexpr uint32_t kNone = 0xFFFFFFFFu;
+    const uint32_t nslots = 1u << p.ex_bits;
+
+    for (uint32_t i = threadIdx.x; i < nslots; i += T) sm.slots[i] = p.ex_slots[i];
+    for (uint32_t i = threadIdx.x; i < p.S * LW; i += T) sm.ascii[i] = p.ex_ascii[i];
+    for (uint32_t i = threadIdx.x; i < nwarps * p.S; i += T) sm.whist[i] = 0u;
+    for (uint32_t i = threadIdx.x; i < nbins; i += T) sm.hist[i] = 0u;
+    if (threadIdx.x < 2) sm.counts[threadIdx.x] = 0u;
+    __syncthreads();
+
+    uint32_t *my_hist = sm.whist + warp * p.S;
+    const uint32_t shift = 32u - p.ex_bits, smask = nslots - 1u;
+    const bool words_ok = (p.L & 3u) == 0u && (reinterpret_cast<uintptr_t>(p.reads_ascii) & 3u) == 0u;
+    uint32_t qn = 0;  // queue fill, tracked identically by every thread
+
+    // general path for `count` queued reads (the newest ones), one thread per read
+    auto drain = [&](uint32_t count) {
+        const bool valid = threadIdx.x < count;
+        const uint32_t e = qn - count + threadIdx.x;
+        uint64_t r = 0;
+        Rd rd = {0u, 0u, 0u, 0u};
+        uint32_t best = kInfKey, nxt = kInfKey;
+        bool scan = false;
+        if (valid) {
+            r = sm.qr[e];
+            rd = load_ascii(p.reads_ascii, r, p.L, words_ok);
+            if (!cannot_match<MODE>(p, rd))
+                scan = p.seed_C == 0u || !seed_search<MODE>(p, p.seed_hdr, p.seed_ids, p.table, rd, best, nxt);
+        }
+        if (scan) sm.cq[atomicAdd(&sm.counts[1], 1u)] = e;
+        Verdict v = apply_rules<MODE>(p, rd, best, nxt);
+        emit(p, r, valid && !scan, rd, v, sm.hist);
+        const uint32_t nscan = __syncthreads_count(scan);
+        if (nscan) {
+            for (uint32_t q = warp; q < nscan; q += nwarps) {
+                const uint64_t qrid = sm.qr[sm.cq[q]];
+                const Rd qrd = load_ascii(p.reads_ascii, qrid, p.L, words_ok);  // same address in every lane
+                Verdict qv = warp_scan<MODE>(p, p.table, qrd, lane);
+                if (lane == 0) emit_single(p, qrid, qrd, qv, sm.hist);
+            }
+        }
+        __syncthreads();  // queue entries [qn-count, qn) are consumed
+        if (threadIdx.x == 0) {
+            sm.counts[0] = qn - count;
+            sm.counts[1] = 0u;
+        }
+        qn -= count;
+        __syncthreads();
+    };
+
+    for (uint64_t base = (uint64_t)blockIdx.x * (T * R); base < p.n; base += (uint64_t)gridDim.x * (T * R)) {
+        uint32_t rw[R][LW];
+        uint32_t hit[R];
+#pragma unroll
+        for (uint32_t k = 0; k < R; k++) {
+            const uint64_t r = base + k * T + threadIdx.x;
+            if (r < p.n) {
+                load_words<LW, ALIGNED>(p.reads_ascii, r, p.L, rw[k]);
+            } else {
+#pragma unroll
+                for (uint32_t i = 0; i < LW; i++) rw[k][i] = 0u;  // never equals a barcode row
+            }
+        }
+#pragma unroll
+        for (uint32_t k = 0; k < R; k++) {
+            const uint64_t r = base + k * T + threadIdx.x;
+            uint32_t h = 0u;
+#pragma unroll
+            for (uint32_t i = 0; i < LW; i++) h += rw[k][i] * p.ex_k[i];
+            h = ex_mix(h);
+            const uint32_t tag = h & 0xFFFFu;
+            uint32_t slot = h >> shift;
+            uint32_t ent = sm.slots[slot];
+            hit[k] = kNone;
+            // first probe, straight-line: nearly every read is decided here
+            bool tagged = ent != 0u && (ent >> 16) == tag;
+            if (tagged) {
+                const uint32_t s = (ent & 0xFFFFu) - 1u;
+                const uint32_t *row = sm.ascii + s * LW;
+                uint32_t diff = 0u;
+#pragma unroll
+                for (uint32_t i = 0; i < LW; i++) diff |= rw[k][i] ^ row[i];
+                if (diff == 0u) hit[k] = s;
+            }
+            if (hit[k] == kNone && ent != 0u) {  // occupied by another barcode: keep probing (rare)
+                for (;;) {
+                    slot = (slot + 1u) & smask;
+                    ent = sm.slots[slot];
+                    if (ent == 0u) break;
+                    if ((ent >> 16) != tag) continue;
+                    const uint32_t s = (ent & 0xFFFFu) - 1u;
+                    const uint32_t *row = sm.ascii + s * LW;
+                    uint32_t diff = 0u;
+#pragma unroll
+                    for (uint32_t i = 0; i < LW; i++) diff |= rw[k][i] ^ row[i];
+                    if (diff == 0u) {
+                        hit[k] = s;
+                        break;
+                    }
+                }
+            }
+            if (hit[k] != kNone) {
+                p.out_idx[r] = (uint16_t)hit[k];
+                if (p.out_dist) p.out_dist[r] = 0u;
+            } else if (r < p.n) {
+                sm.qr[atomicAdd(&sm.counts[0], 1u)] = r;
+            }
+            // perfect-match counters: lanes with the same sample elect a leader, which updates the warp's
+            // private histogram without an atomic
+            const uint32_t peers = __match_any_sync(0xFFFFFFFFu, hit[k]);
+            if (hit[k] != kNone && (uint32_t)(__ffs(peers) - 1) == lane) my_hist[hit[k]] += (uint32_t)__popc(peers);
+            __syncwarp();
+        }
+        __syncthreads();
+        qn = sm.counts[0];
+        __syncthreads();  // nobody pushes again before everyone has read the fill
+        while (qn >= T) drain(T);
+    }
+    if (qn) drain(qn);  // qn < T here (uniform across the block)
+
+    for (uint32_t i = threadIdx.x; i < p.S; i += T) {
+        uint32_t c = 0u;
+        for (uint32_t w = 0; w < nwarps; w++) c += sm.whist[w * p.S + i];
+        if (c) atomicAdd(&p.counters[i * 3u + 1u], (unsigned long long)c);
+    }
+    for (uint32_t i = threadIdx.x; i < nbins; i += T) {
+        uint32_t c = sm.hist[i];
+        if (c) atomicAdd(&p.counters[i], (unsigned long long)c);
+    }
+}
+
+template <uint32_t MODE, uint32_t LW, bool ALIGNED>
+static cudaError_t launch_exact_t(const DevParams &p, int sms, cudaStream_t stream) {
+    size_t smem = exact_smem_bytes(p);
+    auto kern = sgdx_match_exact_first<MODE, LW, ALIGNED>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kSeededThreads, smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+    kern<<<persistent_grid(p.n, kSeededThreads * kExactReadsPerThread, sms, per_sm), kSeededThreads, smem, stream>>>(p);
+    return cudaGetLastError();
+}
+
+template <uint32_t MODE, uint32_t LW>
+static cudaError_t launch_exact_lw(const DevParams &p, int sms, cudaStream_t stream) {
+    if (p.Lw == LW) {
+        const bool aligned = (p.L & 3u) == 0u && (reinterpret_cast<uintptr_t>(p.reads_ascii) & 3u) == 0u;
+        return aligned ? launch_exact_t<MODE, LW, true>(p, sms, stream) : launch_exact_t<MODE, LW, false>(p, sms, stream);
+    }
+    if constexpr (LW < 8) return launch_exact_lw<MODE, LW + 1>(p, sms, stream);
+    return cudaErrorInvalidValue;
 }
 
 cudaError_t launch_seeded(const DevParams &p, uint32_t mode, bool packed, int sms, cudaStream_t stream) {
     if (p.n == 0) return cudaSuccess;
+    if (!packed && p.ex_on)
+        return mode == kModeHamming ? launch_exact_lw<kModeHamming, 1>(p, sms, stream)
+                                    : launch_exact_lw<kModePreCompute, 1>(p, sms, stream);
     if (mode == kModeHamming)
         return packed ? launch_seeded_t<kModeHamming, true>(p, sms, stream)
                       : launch_seeded_t<kModeHamming, false>(p, sms, stream);
