@@ -4,6 +4,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <deque>
 #include <map>
@@ -52,9 +53,9 @@ struct sgdx_handle {
     int sms = 148;
     DevParams base{};  // everything but the per-batch pointers
     uint2 *d_table = nullptr;
-    uint32_t *d_seed_hdr = nullptr;
+    uint16_t *d_seed_hdr = nullptr;
     uint16_t *d_seed_ids = nullptr;
-    uint32_t *d_ex_slots = nullptr, *d_ex_ascii = nullptr;
+    uint32_t *d_ex_slots = nullptr, *d_ex_ascii = nullptr, *d_nb_slots = nullptr;
     bool seeded = false;  // launches use sgdx_match_seeded
     HopSlot *d_hash1 = nullptr, *d_hash2 = nullptr;
     unsigned long long *d_hop_fwd = nullptr, *d_hop_rev = nullptr;
@@ -114,6 +115,7 @@ static int build_seed_index(sgdx_handle *h, const std::vector<uint2> &table, boo
     if (T + 1 > L) return SGDX_OK;
     const uint32_t C = (uint32_t)T + 1u;
     const uint32_t wmax = C <= 8 ? 5u : 4u;  // keeps the headers <= 32 KB
+    if ((uint64_t)C * S > 0xFFFFu) return SGDX_OK;  // bucket bounds are 16-bit offsets into the id runs
     uint32_t total = 0;
     double est = 0.0;
     std::vector<uint32_t> pos(C), w(C), off(C);
@@ -122,26 +124,27 @@ static int build_seed_index(sgdx_handle *h, const std::vector<uint2> &table, boo
         pos[c] = a;
         w[c] = std::min(b - a, wmax);
         off[c] = total;
-        total += 1u << (2 * w[c]);
+        total += (1u << (2 * w[c])) + 1u;  // bucket k of chunk c is ids[hdr[off+k] .. hdr[off+k+1])
         est += (double)S / (double)(1u << (2 * w[c]));
         p.seed_desc[c] = pos[c] | (w[c] << 8) | (off[c] << 16);
     }
-    std::vector<uint32_t> hdr(total, 0u);
+    std::vector<uint16_t> hdr(total, 0);
     std::vector<uint16_t> ids((size_t)C * S, 0);
     for (uint32_t c = 0; c < C; c++) {
-        const uint32_t wm = (1u << w[c]) - 1u;
+        const uint32_t wm = (1u << w[c]) - 1u, nb = 1u << (2 * w[c]);
         auto key_of = [&](uint32_t s) { return ((table[s].x >> pos[c]) & wm) | (((table[s].y >> pos[c]) & wm) << w[c]); };
-        std::vector<uint32_t> cnt(1u << (2 * w[c]), 0u);
+        std::vector<uint32_t> cnt(nb, 0u);
         for (uint32_t s = 0; s < S; s++) cnt[key_of(s)]++;
         uint32_t run = c * S;
-        for (uint32_t k = 0; k < cnt.size(); k++) {
-            hdr[off[c] + k] = (run << 14) | cnt[k];
+        for (uint32_t k = 0; k < nb; k++) {
+            hdr[off[c] + k] = (uint16_t)run;
             run += cnt[k];
             cnt[k] = 0;
         }
+        hdr[off[c] + nb] = (uint16_t)run;
         for (uint32_t s = 0; s < S; s++) {  // ascending sample order inside a bucket
             uint32_t k = key_of(s);
-            ids[(hdr[off[c] + k] >> 14) + cnt[k]++] = (uint16_t)s;
+            ids[hdr[off[c] + k] + cnt[k]++] = (uint16_t)s;
         }
     }
     p.seed_hdr_total = total;
@@ -150,9 +153,9 @@ static int build_seed_index(sgdx_handle *h, const std::vector<uint2> &table, boo
         p.seed_hdr_total = p.seed_ids_total = 0;
         return SGDX_OK;
     }
-    CU(cudaMalloc(&h->d_seed_hdr, hdr.size() * sizeof(uint32_t)));
+    CU(cudaMalloc(&h->d_seed_hdr, hdr.size() * sizeof(uint16_t)));
     CU(cudaMalloc(&h->d_seed_ids, ids.size() * sizeof(uint16_t)));
-    CU(cudaMemcpy(h->d_seed_hdr, hdr.data(), hdr.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(h->d_seed_hdr, hdr.data(), hdr.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(h->d_seed_ids, ids.data(), ids.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
     p.seed_hdr = h->d_seed_hdr;
     p.seed_ids = h->d_seed_ids;
@@ -183,6 +186,7 @@ static int build_exact_table(sgdx_handle *h, const uint8_t *barcodes, const std:
     uint32_t bits = 6;
     while ((1u << bits) < 4u * S) bits++;
     p.ex_bits = bits;
+    if (getenv("SGDX_DISABLE_EXACT")) return SGDX_OK;          // test hook: plain seeded kernel
     if (dmin <= p.delta) return SGDX_OK;                       // an exact hit could still be delta-rejected
     if (exact_smem_bytes(p) > 100u * 1024u) return SGDX_OK;    // large tables: general path only
     std::vector<uint32_t> rows((size_t)S * p.Lw, 0x41414141u), slots((size_t)1 << bits, 0u);
@@ -202,6 +206,37 @@ static int build_exact_table(sgdx_handle *h, const uint8_t *barcodes, const std:
     p.ex_slots = h->d_ex_slots;
     p.ex_ascii = h->d_ex_ascii;
     p.ex_on = 1;
+
+    // neighbour table: a string at distance 1 from a barcode decides the read when every other barcode is
+    // then still further than min_delta away from it: (dmin - 1) - 1 > delta
+    p.nb_on = 0;
+    if (getenv("SGDX_DISABLE_NEIGHBOURS")) return SGDX_OK;  // test hook: exercise the seed search on every miss
+    if ((uint64_t)dmin <= (uint64_t)p.delta + 2u || S > 0x1FFFu) return SGDX_OK;
+    const uint64_t entries = (uint64_t)S * L * 4u;
+    uint32_t nbits = 8;
+    while ((1ull << nbits) < 4u * entries) nbits++;
+    if (nbits > 26) return SGDX_OK;
+    std::vector<uint32_t> nb((size_t)1 << nbits, 0xFFFFFFFFu);
+    static const uint8_t letters[5] = {'A', 'C', 'G', 'T', 'N'};
+    std::vector<uint32_t> row(p.Lw);
+    for (uint32_t s = 0; s < S; s++)
+        for (uint32_t pos = 0; pos < L; pos++)
+            for (uint32_t l = 0; l < 5; l++) {
+                if (letters[l] == barcodes[(size_t)s * L + pos]) continue;
+                for (uint32_t i = 0; i < p.Lw; i++) row[i] = rows[(size_t)s * p.Lw + i];
+                reinterpret_cast<uint8_t *>(row.data())[pos] = letters[l];
+                uint32_t hsh = 0;
+                for (uint32_t i = 0; i < p.Lw; i++) hsh += row[i] * K[i];
+                hsh = ex_mix(hsh);
+                uint32_t slot = hsh >> (32u - nbits);
+                while (nb[slot] != 0xFFFFFFFFu) slot = (slot + 1u) & ((1u << nbits) - 1u);
+                nb[slot] = ((hsh & 0x7FFu) << 21) | (l << 18) | (pos << 13) | s;
+            }
+    CU(cudaMalloc(&h->d_nb_slots, nb.size() * sizeof(uint32_t)));
+    CU(cudaMemcpy(h->d_nb_slots, nb.data(), nb.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    p.nb_slots = h->d_nb_slots;
+    p.nb_bits = nbits;
+    p.nb_on = 1;
     return SGDX_OK;
 }
 
@@ -354,6 +389,7 @@ extern "C" void sgdx_destroy(sgdx_handle *h) {
     cudaFree(h->d_seed_ids);
     cudaFree(h->d_ex_slots);
     cudaFree(h->d_ex_ascii);
+    cudaFree(h->d_nb_slots);
     cudaFree(h->d_hash1);
     cudaFree(h->d_hash2);
     cudaFree(h->d_hop_fwd);

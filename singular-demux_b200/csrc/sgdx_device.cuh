@@ -45,9 +45,9 @@ struct DevParams {
     // seeded kernel: pigeonhole seed index over the expected barcodes (built by sgdx_create).
     // The L positions are cut into seed_C = T+1 disjoint chunks, T = largest number of valid-position
     // mismatches a sample that matters can have; chunk c is keyed by its first seed_w[c] bases
-    // (key = lo bits | hi bits << w).  seed_hdr[seed_off[c] + key] = (start << 14) | count addresses the
-    // run seed_ids[start .. start+count) of samples whose barcode has that key in chunk c.
-    const uint32_t *seed_hdr;
+    // (key = lo bits | hi bits << w).  Bucket `key` of chunk c is the run
+    // seed_ids[seed_hdr[off_c + key] .. seed_hdr[off_c + key + 1]) of samples whose barcode has that key.
+    const uint16_t *seed_hdr;
     const uint16_t *seed_ids;
     uint32_t seed_C;             // 0 = no seed index (direct kernel only)
     uint32_t seed_hdr_total;     // entries in seed_hdr
@@ -64,6 +64,11 @@ struct DevParams {
     uint32_t Lw;                 // ceil(L / 4)
     uint32_t dmin;               // min pairwise Hamming distance of the table (0xFFFF for S == 1)
     uint32_t ex_k[8];            // odd multipliers of the word hash
+    // neighbour table (global memory): every string one substitution (A/C/G/T/N) away from a barcode, same
+    // word hash.  entry = tag(11) << 21 | letter(3: A C G T N) << 18 | position(5) << 13 | sample(13),
+    // 0xFFFFFFFF = empty.  A hit decides the read iff dmin > min_delta + 2 -- nb_on says so.
+    const uint32_t *nb_slots;
+    uint32_t nb_on, nb_bits;
 };
 
 struct Rd {  // one observed barcode as bit planes; bit j = base j, bits >= L are zero

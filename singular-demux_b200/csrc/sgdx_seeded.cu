@@ -60,38 +60,46 @@ __device__ __forceinline__ bool cannot_match(const DevParams &p, const Rd &rd) {
     return dead;
 }
 
-// Enumerate the seed buckets of one read. Returns false when a key window holds two or more invalid
-// bases (the caller hands the read to the all-samples scan).
-template <uint32_t MODE>
-__device__ __forceinline__ bool seed_search(const DevParams &p, const uint32_t *__restrict__ hdr,
+// Enumerate the seed buckets of one read.  Returns false when some key window holds two or more invalid
+// bases (best/nxt are then incomplete and the caller hands the read to the all-samples scan).  Loops are
+// kept free of early exits so that the lanes of a warp reconverge after every bucket.
+template <uint32_t MODE, bool EXPAND>
+__device__ __forceinline__ bool seed_search(const DevParams &p, const uint16_t *__restrict__ hdr,
                                             const uint16_t *__restrict__ ids, const uint2 *__restrict__ table,
                                             const Rd &rd, uint32_t &best, uint32_t &nxt) {
     const uint32_t inv = rd.nmask | rd.xmask;
     const uint32_t skip = (MODE == kModePreCompute && rd.nmask != 0u) ? p.M + 1u : 0xFFFFu;
+    bool complete = true;
     for (uint32_t c = 0; c < p.seed_C; c++) {
         const uint32_t desc = p.seed_desc[c];
         const uint32_t pos = desc & 0xFFu, w = (desc >> 8) & 0xFFu, off = desc >> 16;
         const uint32_t wm = (1u << w) - 1u;
         const uint32_t iv = (inv >> pos) & wm;
         const uint32_t key0 = ((rd.lo >> pos) & wm) | (((rd.hi >> pos) & wm) << w);
-        uint32_t nvar = 1u, j = 0u;
-        if (iv) {
-            if (iv & (iv - 1u)) return false;
-            nvar = 4u;
-            j = __ffs(iv) - 1u;
+        if (!EXPAND) {  // caller guarantees a read without invalid bases: exactly one bucket per chunk
+            const uint32_t start = hdr[off + key0], end = hdr[off + key0 + 1u];
+            for (uint32_t i = start; i < end; i++) {
+                const uint32_t s = ids[i];
+                const uint2 t = table[s];
+                score<MODE>(rd, inv, skip, t.x, t.y, s, best, nxt);
+            }
+            continue;
         }
+        const bool several = (iv & (iv - 1u)) != 0u;
+        complete = complete && !several;
+        const uint32_t nvar = several ? 0u : (iv ? 4u : 1u);
+        const uint32_t j = iv ? (uint32_t)__ffs(iv) - 1u : 0u;
         for (uint32_t b = 0; b < nvar; b++) {
             const uint32_t key = key0 | ((b & 1u) << j) | ((b >> 1) << (w + j));
-            const uint32_t h = hdr[off + key];
-            const uint32_t start = h >> 14, cnt = h & 0x3FFFu;
-            for (uint32_t i = 0; i < cnt; i++) {
-                const uint32_t s = ids[start + i];
+            const uint32_t start = hdr[off + key], end = hdr[off + key + 1u];
+            for (uint32_t i = start; i < end; i++) {
+                const uint32_t s = ids[i];
                 const uint2 t = table[s];
                 score<MODE>(rd, inv, skip, t.x, t.y, s, best, nxt);
             }
         }
     }
-    return true;
+    return complete;
 }
 
 // one warp, one read, all samples
@@ -101,9 +109,12 @@ __device__ __forceinline__ Verdict warp_scan(const DevParams &p, const uint2 *__
     const uint32_t inv = rd.nmask | rd.xmask;
     const uint32_t skip = (MODE == kModePreCompute && rd.nmask != 0u) ? p.M + 1u : 0xFFFFu;
     uint32_t b = kInfKey, n2 = kInfKey;
-    for (uint32_t s = lane; s < p.S; s += 32u) {
-        const uint2 t = table[s];
-        score<MODE>(rd, inv, skip, t.x, t.y, s, b, n2);
+    for (uint32_t s0 = 0; s0 < p.S; s0 += 32u) {  // same trip count in every lane: the warp stays converged
+        const uint32_t s = s0 + lane;
+        if (s < p.S) {
+            const uint2 t = table[s];
+            score<MODE>(rd, inv, skip, t.x, t.y, s, b, n2);
+        }
     }
     const uint32_t gb = __reduce_min_sync(0xFFFFFFFFu, b);
     const uint32_t gn = __reduce_min_sync(0xFFFFFFFFu, b == gb ? n2 : b);  // keys are unique per sample
@@ -134,10 +145,10 @@ static uint32_t persistent_grid(uint64_t n, uint32_t threads, int sms, int per_s
 struct SeedSmem {
     uint4 *dq_rd;        // [threads] planes of the reads queued for the all-samples scan
     uint2 *table;        // [S]
-    uint32_t *hdr;       // [hdr_total]
     uint32_t *hist;      // [(S+1)*3]
     uint32_t *dq_tid;    // [threads]
     uint32_t *dq_count;  // [1] (+3 pad)
+    uint16_t *hdr;       // [hdr_total]
     uint16_t *ids;       // [ids_total]
 };
 
@@ -147,10 +158,10 @@ __host__ __device__ inline size_t seed_carve(unsigned char *base, uint32_t threa
     SeedSmem s;
     s.dq_rd = reinterpret_cast<uint4 *>(base + o);      o += (size_t)threads * 16;
     s.table = reinterpret_cast<uint2 *>(base + o);      o += (size_t)S * 8;
-    s.hdr = reinterpret_cast<uint32_t *>(base + o);     o += (size_t)hdr_total * 4;
     s.hist = reinterpret_cast<uint32_t *>(base + o);    o += (size_t)(S + 1) * 3 * 4;
     s.dq_tid = reinterpret_cast<uint32_t *>(base + o);  o += (size_t)threads * 4;
     s.dq_count = reinterpret_cast<uint32_t *>(base + o); o += 16;
+    s.hdr = reinterpret_cast<uint16_t *>(base + o);     o += ((size_t)hdr_total * 2 + 15) & ~(size_t)15;
     s.ids = reinterpret_cast<uint16_t *>(base + o);     o += ((size_t)ids_total * 2 + 15) & ~(size_t)15;
     if (out) *out = s;
     return o;
@@ -185,7 +196,7 @@ __global__ void __launch_bounds__(kSeededThreads) sgdx_match_seeded(const DevPar
 
         uint32_t best = kInfKey, nxt = kInfKey;
         bool queued = false;
-        if (active && !cannot_match<MODE>(p, rd)) queued = !seed_search<MODE>(p, sm.hdr, sm.ids, sm.table, rd, best, nxt);
+        if (active && !cannot_match<MODE>(p, rd)) queued = !seed_search<MODE, true>(p, sm.hdr, sm.ids, sm.table, rd, best, nxt);
         if (queued) {
             uint32_t slot = atomicAdd(sm.dq_count, 1u);
             sm.dq_rd[slot] = make_uint4(rd.lo, rd.hi, rd.nmask, rd.xmask);
@@ -234,33 +245,50 @@ static cudaError_t launch_seeded_t(const DevParams &p, int sms, cudaStream_t str
 // ------------------------------------------------------------------------------------------------
 constexpr uint32_t kExactReadsPerThread = 4;  // reads per thread between two block barriers
 
+// Work queues of a block (shared memory).  Every stage is run by the whole block on a batch of up to
+// blockDim entries, one thread per read, so each stage executes with full warps:
+//   front end (all reads)         exact hit -> done            else -> Q1
+//   stage 1 (Q1)  neighbour table  one-substitution/one-N hit -> done   else -> Q2
+//   stage 2 (Q2)  planes + seed search on reads without invalid bases -> done; reads with invalid bases -> Q3
+//   stage 3 (Q3)  seed search with 4-way expansion of an invalid base; windows with several -> warp scan
 struct ExactSmem {
-    unsigned long long *qr;  // [(R+1)*threads] read ids waiting for the general path
+    uint2 *table;            // [S] barcode planes (stages 2, 3)
+    uint32_t *q1;            // [(R+1)*threads] block-local read numbers
+    uint32_t *q2;            // [2*threads]
+    uint32_t *q3;            // [2*threads]
     uint32_t *slots;         // [1 << ex_bits]
     uint32_t *ascii;         // [S * Lw]
     uint32_t *whist;         // [nwarps][S] perfect matches found by the front end, private per warp
-    uint32_t *hist;          // [(S+1)*3] general path
-    uint32_t *cq;            // [threads] queue entries that need the all-samples scan
-    uint32_t *counts;        // [0] = queue fill, [1] = cq fill
+    uint32_t *hist;          // [(S+1)*3] all other verdicts
+    uint32_t *cq;            // [threads] Q3 entries that need the all-samples scan
+    uint32_t *counts;        // fill of q1, q2, q3, cq
+    uint16_t *hdr;           // [seed_hdr_total] seed index
+    uint16_t *ids;           // [seed_ids_total]
 };
 
 __host__ __device__ inline size_t exact_carve(unsigned char *base, uint32_t threads, uint32_t S, uint32_t Lw,
-                                              uint32_t ex_bits, ExactSmem *out) {
+                                              uint32_t ex_bits, uint32_t hdr_total, uint32_t ids_total,
+                                              ExactSmem *out) {
     size_t o = 0;
     ExactSmem s;
-    s.qr = reinterpret_cast<unsigned long long *>(base + o); o += (size_t)threads * (kExactReadsPerThread + 1) * 8;
+    s.table = reinterpret_cast<uint2 *>(base + o);           o += (size_t)S * 8;
+    s.q1 = reinterpret_cast<uint32_t *>(base + o);           o += (size_t)threads * (kExactReadsPerThread + 1) * 4;
+    s.q2 = reinterpret_cast<uint32_t *>(base + o);           o += (size_t)threads * 2 * 4;
+    s.q3 = reinterpret_cast<uint32_t *>(base + o);           o += (size_t)threads * 2 * 4;
     s.slots = reinterpret_cast<uint32_t *>(base + o);        o += (size_t)4 << ex_bits;
     s.ascii = reinterpret_cast<uint32_t *>(base + o);        o += (size_t)S * Lw * 4;
     s.whist = reinterpret_cast<uint32_t *>(base + o);        o += (size_t)(threads / 32) * S * 4;
     s.hist = reinterpret_cast<uint32_t *>(base + o);         o += (size_t)(S + 1) * 3 * 4;
     s.cq = reinterpret_cast<uint32_t *>(base + o);           o += (size_t)threads * 4;
     s.counts = reinterpret_cast<uint32_t *>(base + o);       o += 16;
+    s.hdr = reinterpret_cast<uint16_t *>(base + o);          o += ((size_t)hdr_total * 2 + 15) & ~(size_t)15;
+    s.ids = reinterpret_cast<uint16_t *>(base + o);          o += ((size_t)ids_total * 2 + 15) & ~(size_t)15;
     if (out) *out = s;
     return o;
 }
 
 size_t exact_smem_bytes(const DevParams &p) {
-    return exact_carve(nullptr, kSeededThreads, p.S, p.Lw, p.ex_bits, nullptr);
+    return exact_carve(nullptr, kSeededThreads, p.S, p.Lw, p.ex_bits, p.seed_hdr_total, p.seed_ids_total, nullptr);
 }
 
 // LW little-endian words of read r; bytes past L read as 'A' (what the table's rows are padded with)
@@ -289,11 +317,32 @@ __device__ __forceinline__ void load_words(const uint8_t *__restrict__ reads, ui
     }
 }
 
+template <uint32_t LW>
+__device__ __forceinline__ uint32_t word_hash(const DevParams &p, const uint32_t (&rw)[LW]) {
+    uint32_t h = 0u;
+#pragma unroll
+    for (uint32_t i = 0; i < LW; i++) h += rw[i] * p.ex_k[i];
+    return ex_mix(h);
+}
+
+// planes of a read held as ASCII words (same result as load_ascii)
+template <uint32_t LW>
+__device__ __forceinline__ Rd planes_of_words(const uint32_t (&rw)[LW], uint32_t L) {
+    Rd rd = {0u, 0u, 0u, 0u};
+#pragma unroll
+    for (uint32_t i = 0; i < LW; i++) fold_word(rw[i], i * 4u, rd);  // pad bytes are 'A': zero bits in every plane
+    const uint32_t lm = L >= 32u ? 0xFFFFFFFFu : ((1u << L) - 1u);
+    const uint32_t inv = rd.nmask | rd.xmask;
+    rd.lo &= lm & ~inv;
+    rd.hi &= lm & ~inv;
+    return rd;
+}
+
 template <uint32_t MODE, uint32_t LW, bool ALIGNED>
 __global__ void __launch_bounds__(kSeededThreads) sgdx_match_exact_first(const DevParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     ExactSmem sm;
-    exact_carve(smem_raw, kSeededThreads, p.S, LW, p.ex_bits, &sm);
+    exact_carve(smem_raw, kSeededThreads, p.S, LW, p.ex_bits, p.seed_hdr_total, p.seed_ids_total, &sm);
     const uint32_t nbins = (p.S + 1u) * 3u;
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     constexpr uint32_t nwarps = kSeededThreads / 32, T = kSeededThreads, R = kExactReadsPerThread;
@@ -304,118 +353,227 @@ __global__ void __launch_bounds__(kSeededThreads) sgdx_match_exact_first(const D
     for (uint32_t i = threadIdx.x; i < p.S * LW; i += T) sm.ascii[i] = p.ex_ascii[i];
     for (uint32_t i = threadIdx.x; i < nwarps * p.S; i += T) sm.whist[i] = 0u;
     for (uint32_t i = threadIdx.x; i < nbins; i += T) sm.hist[i] = 0u;
-    if (threadIdx.x < 2) sm.counts[threadIdx.x] = 0u;
+    for (uint32_t i = threadIdx.x; i < p.S; i += T) sm.table[i] = p.table[i];
+    for (uint32_t i = threadIdx.x; i < p.seed_hdr_total; i += T) sm.hdr[i] = p.seed_hdr[i];
+    for (uint32_t i = threadIdx.x; i < p.seed_ids_total; i += T) sm.ids[i] = p.seed_ids[i];
+    if (threadIdx.x < 4) sm.counts[threadIdx.x] = 0u;
     __syncthreads();
 
     uint32_t *my_hist = sm.whist + warp * p.S;
     const uint32_t shift = 32u - p.ex_bits, smask = nslots - 1u;
-    const bool words_ok = (p.L & 3u) == 0u && (reinterpret_cast<uintptr_t>(p.reads_ascii) & 3u) == 0u;
-    uint32_t qn = 0;  // queue fill, tracked identically by every thread
+    uint32_t n1 = 0, n2 = 0, n3 = 0;  // queue fills, tracked identically by every thread
 
-    // general path for `count` queued reads (the newest ones), one thread per read
-    auto drain = [&](uint32_t count) {
+    // queue entries number the block's reads: iteration * (T*R) + offset inside the iteration's tile
+    auto read_of = [&](uint32_t e) -> uint64_t {
+        return ((uint64_t)blockIdx.x + (uint64_t)(e / (T * R)) * gridDim.x) * (T * R) + (e % (T * R));
+    };
+    auto sync_fills = [&]() {
+        __syncthreads();
+        n1 = sm.counts[0];
+        n2 = sm.counts[1];
+        n3 = sm.counts[2];
+        // nobody pushes again before everyone has read the fills; the barrier consumes the loaded values so
+        // that the loads have completed (not merely issued) when a warp arrives at it
+        __syncthreads_or((n1 & n2 & n3) == 0xFFFFFFFFu);
+    };
+
+    // ---- stage 3: reads with invalid bases, and whatever the seed index cannot enumerate
+    auto stage3 = [&](uint32_t count) {
         const bool valid = threadIdx.x < count;
-        const uint32_t e = qn - count + threadIdx.x;
         uint64_t r = 0;
         Rd rd = {0u, 0u, 0u, 0u};
-        uint32_t best = kInfKey, nxt = kInfKey;
+        uint32_t best = kInfKey, nxt = kInfKey, e = 0;
         bool scan = false;
         if (valid) {
-            r = sm.qr[e];
-            rd = load_ascii(p.reads_ascii, r, p.L, words_ok);
+            e = sm.q3[n3 - count + threadIdx.x];
+            r = read_of(e);
+            uint32_t rw[LW];
+            load_words<LW, ALIGNED>(p.reads_ascii, r, p.L, rw);
+            rd = planes_of_words<LW>(rw, p.L);
             if (!cannot_match<MODE>(p, rd))
-                scan = p.seed_C == 0u || !seed_search<MODE>(p, p.seed_hdr, p.seed_ids, p.table, rd, best, nxt);
+                scan = p.seed_C == 0u || !seed_search<MODE, true>(p, sm.hdr, sm.ids, sm.table, rd, best, nxt);
         }
-        if (scan) sm.cq[atomicAdd(&sm.counts[1], 1u)] = e;
+        if (scan) sm.cq[atomicAdd(&sm.counts[3], 1u)] = e;
         Verdict v = apply_rules<MODE>(p, rd, best, nxt);
         emit(p, r, valid && !scan, rd, v, sm.hist);
         const uint32_t nscan = __syncthreads_count(scan);
-        if (nscan) {
-            for (uint32_t q = warp; q < nscan; q += nwarps) {
-                const uint64_t qrid = sm.qr[sm.cq[q]];
-                const Rd qrd = load_ascii(p.reads_ascii, qrid, p.L, words_ok);  // same address in every lane
-                Verdict qv = warp_scan<MODE>(p, p.table, qrd, lane);
-                if (lane == 0) emit_single(p, qrid, qrd, qv, sm.hist);
-            }
+        for (uint32_t q = warp; q < nscan; q += nwarps) {  // one warp per read, all samples
+            const uint64_t qrid = read_of(sm.cq[q]);
+            uint32_t rw[LW];
+            load_words<LW, ALIGNED>(p.reads_ascii, qrid, p.L, rw);  // same address in every lane
+            const Rd qrd = planes_of_words<LW>(rw, p.L);
+            Verdict qv = warp_scan<MODE>(p, sm.table, qrd, lane);
+            if (lane == 0) emit_single(p, qrid, qrd, qv, sm.hist);
         }
-        __syncthreads();  // queue entries [qn-count, qn) are consumed
         if (threadIdx.x == 0) {
-            sm.counts[0] = qn - count;
-            sm.counts[1] = 0u;
+            sm.counts[2] = n3 - count;
+            sm.counts[3] = 0u;  // read by nobody else between the two barriers around this store
         }
-        qn -= count;
-        __syncthreads();
+        sync_fills();
     };
 
-    for (uint64_t base = (uint64_t)blockIdx.x * (T * R); base < p.n; base += (uint64_t)gridDim.x * (T * R)) {
-        uint32_t rw[R][LW];
-        uint32_t hit[R];
-#pragma unroll
-        for (uint32_t k = 0; k < R; k++) {
-            const uint64_t r = base + k * T + threadIdx.x;
-            if (r < p.n) {
-                load_words<LW, ALIGNED>(p.reads_ascii, r, p.L, rw[k]);
+    // ---- stage 2: planes + seed search for reads made of A/C/G/T only
+    auto stage2 = [&](uint32_t count) {
+        const bool valid = threadIdx.x < count;
+        uint64_t r = 0;
+        Rd rd = {0u, 0u, 0u, 0u};
+        uint32_t best = kInfKey, nxt = kInfKey;
+        bool done = false;
+        if (valid) {
+            const uint32_t e = sm.q2[n2 - count + threadIdx.x];
+            r = read_of(e);
+            uint32_t rw[LW];
+            load_words<LW, ALIGNED>(p.reads_ascii, r, p.L, rw);
+            rd = planes_of_words<LW>(rw, p.L);
+            if (cannot_match<MODE>(p, rd)) {
+                done = true;  // NoMatch without a search
+            } else if ((rd.nmask | rd.xmask) != 0u || p.seed_C == 0u) {
+                sm.q3[atomicAdd(&sm.counts[2], 1u)] = e;
             } else {
-#pragma unroll
-                for (uint32_t i = 0; i < LW; i++) rw[k][i] = 0u;  // never equals a barcode row
+                seed_search<MODE, false>(p, sm.hdr, sm.ids, sm.table, rd, best, nxt);
+                done = true;
             }
         }
-#pragma unroll
-        for (uint32_t k = 0; k < R; k++) {
-            const uint64_t r = base + k * T + threadIdx.x;
-            uint32_t h = 0u;
-#pragma unroll
-            for (uint32_t i = 0; i < LW; i++) h += rw[k][i] * p.ex_k[i];
-            h = ex_mix(h);
-            const uint32_t tag = h & 0xFFFFu;
-            uint32_t slot = h >> shift;
-            uint32_t ent = sm.slots[slot];
-            hit[k] = kNone;
-            // first probe, straight-line: nearly every read is decided here
-            bool tagged = ent != 0u && (ent >> 16) == tag;
-            if (tagged) {
-                const uint32_t s = (ent & 0xFFFFu) - 1u;
-                const uint32_t *row = sm.ascii + s * LW;
-                uint32_t diff = 0u;
-#pragma unroll
-                for (uint32_t i = 0; i < LW; i++) diff |= rw[k][i] ^ row[i];
-                if (diff == 0u) hit[k] = s;
-            }
-            if (hit[k] == kNone && ent != 0u) {  // occupied by another barcode: keep probing (rare)
+        Verdict v = apply_rules<MODE>(p, rd, best, nxt);
+        emit(p, r, done, rd, v, sm.hist);
+        if (threadIdx.x == 0) sm.counts[1] = n2 - count;
+        sync_fills();
+    };
+
+    // ---- stage 1: one-substitution / one-no-call neighbours of the barcodes (global table, L2 resident)
+    auto stage1 = [&](uint32_t count) {
+        const bool valid = threadIdx.x < count;
+        if (valid) {
+            const uint32_t e = sm.q1[n1 - count + threadIdx.x];
+            bool resolved = false;
+            if (p.nb_on) {
+                const uint64_t r = read_of(e);
+                uint32_t rw[LW];
+                load_words<LW, ALIGNED>(p.reads_ascii, r, p.L, rw);
+                const uint32_t h = word_hash<LW>(p, rw);
+                const uint32_t tag = h & 0x7FFu, nmask = (1u << p.nb_bits) - 1u;
+                uint32_t slot = h >> (32u - p.nb_bits);
                 for (;;) {
-                    slot = (slot + 1u) & smask;
-                    ent = sm.slots[slot];
-                    if (ent == 0u) break;
-                    if ((ent >> 16) != tag) continue;
+                    const uint32_t ent = __ldg(p.nb_slots + slot);
+                    if (ent == kNone) break;
+                    if ((ent >> 21) == tag) {
+                        const uint32_t s = ent & 0x1FFFu, pos = (ent >> 13) & 31u, letter = (ent >> 18) & 7u;
+                        const uint32_t *row = sm.ascii + s * LW;
+                        const uint32_t sh = (pos & 3u) * 8u, wi = pos >> 2;
+                        const uint32_t byte = letter == 4u ? 0x4Eu : ((0x54474341u >> (8u * letter)) & 0xFFu);  // ACGT, N
+                        uint32_t diff = 0u;
+#pragma unroll
+                        for (uint32_t i = 0; i < LW; i++) {
+                            uint32_t expect = row[i];
+                            if (i == wi) expect = (expect & ~(0xFFu << sh)) | (byte << sh);
+                            diff |= rw[i] ^ expect;
+                        }
+                        if (diff == 0u) {
+                            // distance 1 over all positions; every other sample is >= dmin-1 > 1+delta away
+                            const bool is_n = letter == 4u;
+                            uint32_t d = 1u;
+                            bool ok = true;
+                            if (is_n) {
+                                ok = !(p.max_no_calls >= 0 && 1u > (uint32_t)p.max_no_calls);
+                                if (MODE == kModeHamming) d = 1u - min(1u, p.free_ns);
+                            }
+                            if (ok && d <= p.M) {
+                                p.out_idx[r] = (uint16_t)s;
+                                if (p.out_dist) p.out_dist[r] = (uint8_t)d;
+                                atomicAdd(&sm.hist[s * 3u + (d == 0u ? 1u : 2u)], 1u);
+                                resolved = true;
+                            }
+                            break;
+                        }
+                    }
+                    slot = (slot + 1u) & nmask;
+                }
+            }
+            if (!resolved) sm.q2[atomicAdd(&sm.counts[1], 1u)] = e;
+        }
+        if (threadIdx.x == 0) sm.counts[0] = n1 - count;
+        sync_fills();
+    };
+
+    // One loop, one copy of every stage: the deepest non-empty queue with a full batch runs first (so no
+    // queue ever exceeds its capacity); when the input is exhausted the queues are flushed the same way.
+    uint32_t iter = 0;
+    uint64_t base = (uint64_t)blockIdx.x * (T * R);
+    for (;;) {
+        const bool more = base < p.n;
+        if (n3 >= T || (!more && n1 == 0u && n2 == 0u && n3)) {
+            stage3(min(n3, T));
+        } else if (n2 >= T || (!more && n1 == 0u && n2)) {
+            stage2(min(n2, T));
+        } else if (n1 >= T || (!more && n1)) {
+            stage1(min(n1, T));
+        } else if (more) {
+            uint32_t rw[R][LW];
+            uint32_t hit[R];
+#pragma unroll
+            for (uint32_t k = 0; k < R; k++) {
+                const uint64_t r = base + k * T + threadIdx.x;
+                if (r < p.n) {
+                    load_words<LW, ALIGNED>(p.reads_ascii, r, p.L, rw[k]);
+                } else {
+#pragma unroll
+                    for (uint32_t i = 0; i < LW; i++) rw[k][i] = 0u;  // never equals a barcode row
+                }
+            }
+#pragma unroll
+            for (uint32_t k = 0; k < R; k++) {
+                const uint64_t r = base + k * T + threadIdx.x;
+                const uint32_t h = word_hash<LW>(p, rw[k]);
+                const uint32_t tag = h & 0xFFFFu;
+                uint32_t slot = h >> shift;
+                uint32_t ent = sm.slots[slot];
+                hit[k] = kNone;
+                // first probe, straight-line: nearly every read is decided here
+                bool tagged = ent != 0u && (ent >> 16) == tag;
+                if (tagged) {
                     const uint32_t s = (ent & 0xFFFFu) - 1u;
                     const uint32_t *row = sm.ascii + s * LW;
                     uint32_t diff = 0u;
 #pragma unroll
                     for (uint32_t i = 0; i < LW; i++) diff |= rw[k][i] ^ row[i];
-                    if (diff == 0u) {
-                        hit[k] = s;
-                        break;
+                    if (diff == 0u) hit[k] = s;
+                }
+                if (hit[k] == kNone && ent != 0u) {  // occupied by another barcode: keep probing (rare)
+                    for (;;) {
+                        slot = (slot + 1u) & smask;
+                        ent = sm.slots[slot];
+                        if (ent == 0u) break;
+                        if ((ent >> 16) != tag) continue;
+                        const uint32_t s = (ent & 0xFFFFu) - 1u;
+                        const uint32_t *row = sm.ascii + s * LW;
+                        uint32_t diff = 0u;
+#pragma unroll
+                        for (uint32_t i = 0; i < LW; i++) diff |= rw[k][i] ^ row[i];
+                        if (diff == 0u) {
+                            hit[k] = s;
+                            break;
+                        }
                     }
                 }
+                if (hit[k] != kNone) {
+                    p.out_idx[r] = (uint16_t)hit[k];
+                    if (p.out_dist) p.out_dist[r] = 0u;
+                } else if (r < p.n) {
+                    sm.q1[atomicAdd(&sm.counts[0], 1u)] = iter * (T * R) + k * T + threadIdx.x;
+                }
+                // perfect-match counters: lanes with the same sample elect a leader, which updates the warp's
+                // private histogram without an atomic
+                const uint32_t peers = __match_any_sync(0xFFFFFFFFu, hit[k]);
+                if (hit[k] != kNone && (uint32_t)(__ffs(peers) - 1) == lane) my_hist[hit[k]] += (uint32_t)__popc(peers);
+                __syncwarp();
             }
-            if (hit[k] != kNone) {
-                p.out_idx[r] = (uint16_t)hit[k];
-                if (p.out_dist) p.out_dist[r] = 0u;
-            } else if (r < p.n) {
-                sm.qr[atomicAdd(&sm.counts[0], 1u)] = r;
-            }
-            // perfect-match counters: lanes with the same sample elect a leader, which updates the warp's
-            // private histogram without an atomic
-            const uint32_t peers = __match_any_sync(0xFFFFFFFFu, hit[k]);
-            if (hit[k] != kNone && (uint32_t)(__ffs(peers) - 1) == lane) my_hist[hit[k]] += (uint32_t)__popc(peers);
-            __syncwarp();
+            sync_fills();
+            base += (uint64_t)gridDim.x * (T * R);
+            iter++;
+        } else {
+            break;
         }
-        __syncthreads();
-        qn = sm.counts[0];
-        __syncthreads();  // nobody pushes again before everyone has read the fill
-        while (qn >= T) drain(T);
     }
-    if (qn) drain(qn);  // qn < T here (uniform across the block)
 
     for (uint32_t i = threadIdx.x; i < p.S; i += T) {
         uint32_t c = 0u;

@@ -165,6 +165,27 @@ def test_seeded_no_call_paths(S, L, i1, M, D, F, p_n, p_x):
             st.close()
 
 
+@pytest.mark.parametrize("cfg", ["C1", "C2"])
+def test_exact_and_neighbour_front_end_rule_grid(cfg):
+    """Well separated tables (min pairwise distance 6) take the exact-match and one-substitution shortcuts
+    of the seeded kernel; every rule parameter that touches those shortcuts is swept against the oracle."""
+    base = sg.synth.CONFIGS[cfg]
+    w = sg.synth.Workload("grid", base.num_samples, base.barcode_len, base.index1_len, 1, 2, n_reads=40_000,
+                          table_seed=base.table_seed, read_seed=77, p_true=0.85, p_hop=0.05, p_sub=0.03, p_n=0.02,
+                          p_x=0.002)
+    table = w.table()
+    reads = w.reads_host(0, w.n_reads, table)
+    for kind in (sg.MatcherKind.CachedHammingDistance, sg.MatcherKind.PreCompute):
+        for M in (0, 1, 2):
+            for D in (0, 1, 2, 3, 4):
+                for F, mnc in ((0, None), (1, None), (2, 0), (1, 1), (0, 0)):
+                    st = _stage(table, kind, M, D, F, mnc, w.index_lengths, sg.KERNEL_SEEDED)
+                    got = st.demultiplex(reads)
+                    want = _oracle(table, kind, M, D, F, mnc, w.index_lengths, reads, force_closed_form=True)
+                    _assert_same(st, got, want, reads.shape[0])
+                    st.close()
+
+
 @pytest.mark.parametrize("kernel", KERNELS)
 def test_precompute_against_literal_map_oracle(kernel):
     """Short barcodes: the oracle side uses the literally constructed PreCompute map, not the closed form."""
