@@ -368,6 +368,9 @@ extern "C" int sgdx_create(const sgdx_config *cfg, const uint8_t *barcodes, sgdx
         CU(cudaEventCreate(&s.e0));
         CU(cudaEventCreate(&s.e1));
     }
+    // table uploads and memsets above ran on the legacy default stream; the slots' streams are non-blocking and
+    // do not order against it, so make everything resident before the first batch can be queued
+    CU(cudaDeviceSynchronize());
     *out = h;
     return SGDX_OK;
 }
@@ -570,6 +573,7 @@ extern "C" int sgdx_reset_counters(sgdx_handle *h) {
         CU(cudaMemset(h->d_hop_fwd, 0, cells * sizeof(unsigned long long)));
         CU(cudaMemset(h->d_hop_rev, 0, cells * sizeof(unsigned long long)));
     }
+    CU(cudaDeviceSynchronize());  // the memsets are on the default stream, batches on non-blocking ones
     return SGDX_OK;
 }
 

@@ -258,8 +258,7 @@ struct ExactSmem {
     uint32_t *q3;            // [2*threads]
     uint32_t *slots;         // [1 << ex_bits]
     uint32_t *ascii;         // [S * Lw]
-    uint32_t *whist;         // [nwarps][S] perfect matches found by the front end, private per warp
-    uint32_t *hist;          // [(S+1)*3] all other verdicts
+    uint32_t *hist;          // [(S+1)*3] verdict counters of the block
     uint32_t *cq;            // [threads] Q3 entries that need the all-samples scan
     uint32_t *counts;        // fill of q1, q2, q3, cq
     uint16_t *hdr;           // [seed_hdr_total] seed index
@@ -277,7 +276,6 @@ __host__ __device__ inline size_t exact_carve(unsigned char *base, uint32_t thre
     s.q3 = reinterpret_cast<uint32_t *>(base + o);           o += (size_t)threads * 2 * 4;
     s.slots = reinterpret_cast<uint32_t *>(base + o);        o += (size_t)4 << ex_bits;
     s.ascii = reinterpret_cast<uint32_t *>(base + o);        o += (size_t)S * Lw * 4;
-    s.whist = reinterpret_cast<uint32_t *>(base + o);        o += (size_t)(threads / 32) * S * 4;
     s.hist = reinterpret_cast<uint32_t *>(base + o);         o += (size_t)(S + 1) * 3 * 4;
     s.cq = reinterpret_cast<uint32_t *>(base + o);           o += (size_t)threads * 4;
     s.counts = reinterpret_cast<uint32_t *>(base + o);       o += 16;
@@ -351,7 +349,6 @@ __global__ void __launch_bounds__(kSeededThreads) sgdx_match_exact_first(const D
 
     for (uint32_t i = threadIdx.x; i < nslots; i += T) sm.slots[i] = p.ex_slots[i];
     for (uint32_t i = threadIdx.x; i < p.S * LW; i += T) sm.ascii[i] = p.ex_ascii[i];
-    for (uint32_t i = threadIdx.x; i < nwarps * p.S; i += T) sm.whist[i] = 0u;
     for (uint32_t i = threadIdx.x; i < nbins; i += T) sm.hist[i] = 0u;
     for (uint32_t i = threadIdx.x; i < p.S; i += T) sm.table[i] = p.table[i];
     for (uint32_t i = threadIdx.x; i < p.seed_hdr_total; i += T) sm.hdr[i] = p.seed_hdr[i];
@@ -359,7 +356,6 @@ __global__ void __launch_bounds__(kSeededThreads) sgdx_match_exact_first(const D
     if (threadIdx.x < 4) sm.counts[threadIdx.x] = 0u;
     __syncthreads();
 
-    uint32_t *my_hist = sm.whist + warp * p.S;
     const uint32_t shift = 32u - p.ex_bits, smask = nslots - 1u;
     uint32_t n1 = 0, n2 = 0, n3 = 0;  // queue fills, tracked identically by every thread
 
@@ -372,9 +368,7 @@ __global__ void __launch_bounds__(kSeededThreads) sgdx_match_exact_first(const D
         n1 = sm.counts[0];
         n2 = sm.counts[1];
         n3 = sm.counts[2];
-        // nobody pushes again before everyone has read the fills; the barrier consumes the loaded values so
-        // that the loads have completed (not merely issued) when a warp arrives at it
-        __syncthreads_or((n1 & n2 & n3) == 0xFFFFFFFFu);
+        __syncthreads();  // nobody pushes again before everyone has read the fills
     };
 
     // ---- stage 3: reads with invalid bases, and whatever the seed index cannot enumerate
@@ -558,14 +552,10 @@ __global__ void __launch_bounds__(kSeededThreads) sgdx_match_exact_first(const D
                 if (hit[k] != kNone) {
                     p.out_idx[r] = (uint16_t)hit[k];
                     if (p.out_dist) p.out_dist[r] = 0u;
+                    atomicAdd(&sm.hist[hit[k] * 3u + 1u], 1u);  // perfect match (ATOMS.POPC.INC: aggregated in hardware)
                 } else if (r < p.n) {
                     sm.q1[atomicAdd(&sm.counts[0], 1u)] = iter * (T * R) + k * T + threadIdx.x;
                 }
-                // perfect-match counters: lanes with the same sample elect a leader, which updates the warp's
-                // private histogram without an atomic
-                const uint32_t peers = __match_any_sync(0xFFFFFFFFu, hit[k]);
-                if (hit[k] != kNone && (uint32_t)(__ffs(peers) - 1) == lane) my_hist[hit[k]] += (uint32_t)__popc(peers);
-                __syncwarp();
             }
             sync_fills();
             base += (uint64_t)gridDim.x * (T * R);
@@ -575,11 +565,7 @@ __global__ void __launch_bounds__(kSeededThreads) sgdx_match_exact_first(const D
         }
     }
 
-    for (uint32_t i = threadIdx.x; i < p.S; i += T) {
-        uint32_t c = 0u;
-        for (uint32_t w = 0; w < nwarps; w++) c += sm.whist[w * p.S + i];
-        if (c) atomicAdd(&p.counters[i * 3u + 1u], (unsigned long long)c);
-    }
+    __syncthreads();
     for (uint32_t i = threadIdx.x; i < nbins; i += T) {
         uint32_t c = sm.hist[i];
         if (c) atomicAdd(&p.counters[i], (unsigned long long)c);

@@ -287,6 +287,20 @@ def test_slots_shards_and_merge_equal_single_pass(kernel):
     assert merged.total_templates == n and merged.sample_barcode_hop_tracker.count_tracker == want["hops"]
 
 
+def test_back_to_back_create_and_first_batch():
+    """A batch queued right after sgdx_create must see fully uploaded tables and zeroed counters (the slots'
+    streams do not order against the default stream the uploads ran on): many short create -> run cycles."""
+    rng = np.random.default_rng(7)
+    w, table, reads = _random_case(rng, 96, 16, 8, n=40_000)
+    for kind, M, D, F, mnc in [(sg.MatcherKind.PreCompute, 1, 2, 1, None), (sg.MatcherKind.PreCompute, 2, 1, 2, 1),
+                               (sg.MatcherKind.CachedHammingDistance, 1, 0, 0, 2)]:
+        want = _oracle(table, kind, M, D, F, mnc, w.index_lengths, reads, force_closed_form=True)
+        for _ in range(12):
+            st = _stage(table, kind, M, D, F, mnc, w.index_lengths, sg.KERNEL_SEEDED)
+            _assert_same(st, st.demultiplex(reads), want, reads.shape[0])
+            st.close()
+
+
 def test_batcher_returns_batches_in_order():
     from singular_demux_b200._lib import check, lib
     rng = np.random.default_rng(3)
