@@ -218,13 +218,21 @@ def main():
     total_ms_max = float(t.item())
     value = world * n * args.steps / (total_ms_max * 1e-3)
 
-    # sanity on the counted work: every timed read must have been assigned (nothing skipped or cached)
+    # sanity on the counted work: every timed read must have been assigned (nothing skipped or cached);
+    # per-GPU counters are summed on the host (no device collective on this path)
     per, totals = m.counters()
     assert totals["total_templates"] == n * args.steps, (totals, n, args.steps)
     assert int(per[:, 0].sum()) == n * args.steps
-    matched_frac = totals["matched"] / max(totals["total_templates"], 1)
+    merged = sg.sharding.gather_metrics(stage.metrics(), dst=0)
+    matched_frac = None
+    if rank == 0:
+        assert merged.total_templates == world * n * args.steps
+        mp_ = merged.per_sample_array()
+        matched_frac = float(mp_[:-1, 0].sum()) / max(merged.total_templates, 1)
 
-    # ---- roofline of the dominant (only) kernel
+    # ---- roofline of the dominant (only) kernel: HBM.  achieved = SURVEY 8(d)'s algorithmic bytes per read x the
+    # reads of one launch / the launch's CUDA-event duration; the ABI takes ASCII, so the buffers actually moved
+    # are L+3 bytes per read (reported beside it); traffic = ncu dram bytes of the same launch (profiles/)
     peaks = {}
     peaks_src = "measured (MEASURED_PEAKS.json)"
     try:
@@ -233,22 +241,30 @@ def main():
         peaks_src = "fallback (B200_PROFILING.md 6.65 TB/s)"
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     avg_ms = sum(per_launch_ms) / len(per_launch_ms)
+    kname = m.kernel_name()
     alg_bytes = ALG_BYTES(L) * n
     achieved = alg_bytes / (avg_ms * 1e-3) / 1e9
+    buffers = (L + 3) * n / (avg_ms * 1e-3) / 1e9
+    traffic, traffic_src = None, None
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(kname, {}).get(args.config)
+        if t:
+            traffic, traffic_src = t["dram_bytes_per_read"] * n, t["source"]
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "traffic": None, "peak_source": peaks_src, "kernel": "sgdx_match_direct" if m.kernel == 1 else "sgdx_match_seeded",
-                "algorithmic_bytes_per_read": ALG_BYTES(L), "actual_bytes_per_read": L + 3,
-                "avg_launch_ms": avg_ms}
-    if rank == 0:
+                "traffic": traffic, "traffic_source": traffic_src, "peak_source": peaks_src, "kernel": kname,
+                "algorithmic_bytes_per_read": ALG_BYTES(L), "buffer_bytes_per_read": L + 3,
+                "achieved_buffer_gbs": buffers, "frac_buffer": buffers / hbm_peak, "avg_launch_ms": avg_ms}
+    if rank == 0 and kname == "sgdx_match_direct":
         popc, lop3 = C.c_double(0), C.c_double(0)
         sg.lib().sgdx_measure_int_peak(local, C.byref(popc), C.byref(lop3))
         pairs_per_s = n * S / (avg_ms * 1e-3)
         roofline["integer"] = {
-            "note": "for S >= 96 the path is integer-pipe bound, not HBM bound (SURVEY 8d): one mismatch popcount per "
-                    "(read, sample); peaks measured on this box by sgdx_measure_int_peak",
+            "note": "the direct kernel scores every (read, sample) pair: one POPC each, so it is bound by the POPC "
+                    "rate (measured on this box by sgdx_measure_int_peak), not by HBM",
             "pairs_per_s": pairs_per_s, "popc_peak_per_s": popc.value, "lop3_peak_per_s": lop3.value,
-            "frac_of_popc_peak": pairs_per_s / popc.value if popc.value else None,
-            "binding": "popc" if n * S / max(popc.value, 1) > alg_bytes / (hbm_peak * 1e9) else "hbm"}
+            "frac_of_popc_peak": pairs_per_s / popc.value if popc.value else None}
 
     # ---- end to end through the reference-facing C-ABI call: pinned host buffers, H2D + kernel + D2H per step
     e2e = None
@@ -309,7 +325,7 @@ def main():
             "warmup": max(args.warmup, 3), "ms_per_step": total_ms_max / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
             "config": {"workload": workload_desc(w, n), "reads_per_gpu_per_step": n, "matcher": kind.value,
-                       "kernel": "direct" if m.kernel == 1 else "seeded",
+                       "kernel": kname,
                        "input": "ASCII barcodes resident in HBM", "sharding": f"{world} shard(s) by read range, host-merged counters",
                        "l2": f"inputs {n * L / 1e6:.0f} MB + outputs {n * 3 / 1e6:.0f} MB per step, larger than the 126 MB L2"},
             "roofline": roofline, "cpu_baseline": cb, "e2e": e2e, "gpu_launches": int(launches),

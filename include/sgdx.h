@@ -117,6 +117,9 @@ int sgdx_match_packed_device(sgdx_handle *h, uint32_t slot, const sgdx_read *d_p
                              uint16_t *d_out_idx, uint8_t *d_out_dist);
 /* Run the slot on a caller-owned stream (cudaStream_t passed as void*); NULL restores the slot's own. */
 int sgdx_set_stream(sgdx_handle *h, uint32_t slot, void *cuda_stream);
+/* Name of the assignment kernel this handle launches for ASCII input ("sgdx_match_direct",
+ * "sgdx_match_seeded" or "sgdx_match_exact_first"); static storage. */
+const char *sgdx_kernel_name(const sgdx_handle *h);
 /* Number of kernel launches issued through this handle so far. */
 uint64_t sgdx_launch_count(const sgdx_handle *h);
 

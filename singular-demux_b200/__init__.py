@@ -11,6 +11,6 @@ from .matcher import (UNDETERMINED_NAME, CachedHammingDistanceMatcher, GpuMatche
 from .metrics import (BarcodeCount, DemuxedGroupMetrics, DemuxedGroupSampleMetrics, SampleBarcodeHopTracker,
                       UnmatchedCounter)
 from .demux import BarcodeAssignmentStage, DemuxedGroup
-from . import synth
+from . import sharding, synth
 
 __all__ = [n for n in dir() if not n.startswith("_")]

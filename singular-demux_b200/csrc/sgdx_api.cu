@@ -524,6 +524,12 @@ extern "C" int sgdx_set_stream(sgdx_handle *h, uint32_t slot, void *stream) {
     return SGDX_OK;
 }
 
+extern "C" const char *sgdx_kernel_name(const sgdx_handle *h) {
+    if (!h) return "";
+    if (!h->seeded) return "sgdx_match_direct";
+    return h->base.ex_on ? "sgdx_match_exact_first" : "sgdx_match_seeded";
+}
+
 extern "C" uint64_t sgdx_launch_count(const sgdx_handle *h) { return h ? h->launches.load() : 0; }
 
 static int fetch_hop(sgdx_handle *h, std::vector<unsigned long long> &fwd, std::vector<unsigned long long> &rev) {

@@ -196,6 +196,9 @@ class GpuMatcher:
     def set_stream(self, slot: int, cuda_stream: int) -> None:
         check(lib().sgdx_set_stream(self._h, slot, cuda_stream or None), "sgdx_set_stream")
 
+    def kernel_name(self) -> str:
+        return lib().sgdx_kernel_name(self._h).decode()
+
     def launch_count(self) -> int:
         return int(lib().sgdx_launch_count(self._h))
 

@@ -1,0 +1,70 @@
+"""Multi-GPU sharding of the assignment path: reads shard by contiguous range, one process per GPU, no
+data-path collective; per-GPU counters are additive and are summed on the host exactly like the reference's
+fold/reduce of per-chunk metrics (/root/reference/src/lib/run.rs:275-306, metrics.rs:315-328,633-638).
+
+``torch.distributed`` is used only as plumbing (gather of a few KB of counters to rank 0); it works the same
+over ``gloo`` on CPU (tests) and ``nccl`` on GPUs (bench.py)."""
+from __future__ import annotations
+
+from typing import Dict, Optional, Tuple
+
+import numpy as np
+
+from .metrics import DemuxedGroupMetrics, SampleBarcodeHopTracker
+
+
+def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
+    """[first, last) of rank's contiguous shard of n reads; shards differ by at most one read."""
+    if not 0 <= rank < world:
+        raise ValueError(f"rank {rank} outside 0..{world - 1}")
+    q, r = divmod(n, world)
+    first = rank * q + min(rank, r)
+    return first, first + q + (1 if rank < r else 0)
+
+
+def merge_metrics(parts) -> Optional[DemuxedGroupMetrics]:
+    """Sum the metrics of several shards (any order)."""
+    merged = None
+    for m in parts:
+        if m is None:
+            continue
+        if merged is None:
+            hop = None
+            if m.sample_barcode_hop_tracker is not None:
+                t = m.sample_barcode_hop_tracker
+                hop = SampleBarcodeHopTracker(t.index1_length, t.index2_length, dict(t.count_tracker))
+            merged = DemuxedGroupMetrics.from_device(m.per_sample_array(), m.total_templates, hop)
+            merged.num_reads_failing_filters = m.num_reads_failing_filters
+            merged.num_reads_filtered_as_control = m.num_reads_filtered_as_control
+        else:
+            merged.update_with(m)
+    return merged
+
+
+def gather_metrics(metrics: DemuxedGroupMetrics, dst: int = 0, group=None) -> Optional[DemuxedGroupMetrics]:
+    """Collect every rank's counters on rank ``dst`` and sum them there; other ranks get None.
+    Without an initialised process group this is the identity (single GPU)."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return metrics
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    payload = {
+        "per_sample": metrics.per_sample_array(),
+        "total_templates": metrics.total_templates,
+        "failing": metrics.num_reads_failing_filters,
+        "control": metrics.num_reads_filtered_as_control,
+        "hop": None if metrics.sample_barcode_hop_tracker is None else
+        (metrics.sample_barcode_hop_tracker.index1_length, metrics.sample_barcode_hop_tracker.index2_length,
+         metrics.sample_barcode_hop_tracker.count_tracker),
+    }
+    gathered = [None] * world if rank == dst else None
+    dist.gather_object(payload, gathered, dst=dst, group=group)
+    if rank != dst:
+        return None
+    parts = []
+    for g in gathered:
+        hop = None if g["hop"] is None else SampleBarcodeHopTracker(g["hop"][0], g["hop"][1], dict(g["hop"][2]))
+        m = DemuxedGroupMetrics.from_device(np.asarray(g["per_sample"], dtype=np.uint64), g["total_templates"], hop)
+        m.num_reads_failing_filters, m.num_reads_filtered_as_control = g["failing"], g["control"]
+        parts.append(m)
+    return merge_metrics(parts)
