@@ -188,7 +188,7 @@ static int build_exact_table(sgdx_handle *h, const uint8_t *barcodes, const std:
     p.ex_bits = bits;
     if (getenv("SGDX_DISABLE_EXACT")) return SGDX_OK;          // test hook: plain seeded kernel
     if (dmin <= p.delta) return SGDX_OK;                       // an exact hit could still be delta-rejected
-    if (exact_smem_bytes(p) > 100u * 1024u) return SGDX_OK;    // large tables: general path only
+    if (exact_block_threads(p) == 0u) return SGDX_OK;          // tables that do not fit one SM: general path only
     std::vector<uint32_t> rows((size_t)S * p.Lw, 0x41414141u), slots((size_t)1 << bits, 0u);
     for (uint32_t s = 0; s < S; s++) {
         memcpy(&rows[(size_t)s * p.Lw], barcodes + (size_t)s * L, L);  // little-endian host; tail bytes stay 'A'

@@ -285,8 +285,16 @@ __host__ __device__ inline size_t exact_carve(unsigned char *base, uint32_t thre
     return o;
 }
 
-size_t exact_smem_bytes(const DevParams &p) {
-    return exact_carve(nullptr, kSeededThreads, p.S, p.Lw, p.ex_bits, p.seed_hdr_total, p.seed_ids_total, nullptr);
+size_t exact_smem_bytes(const DevParams &p, uint32_t threads) {
+    return exact_carve(nullptr, threads, p.S, p.Lw, p.ex_bits, p.seed_hdr_total, p.seed_ids_total, nullptr);
+}
+
+// CTA size of sgdx_match_exact_first for this table: 256 threads while at least 3 CTAs fit an SM, one
+// 1024-thread CTA per SM for large tables (C3: 1536 x 24 bp needs 124 KB of tables), 0 = does not fit at all
+uint32_t exact_block_threads(const DevParams &p) {
+    if (exact_smem_bytes(p, 256) <= 75u * 1024u) return 256u;
+    if (exact_smem_bytes(p, 1024) <= 227u * 1024u) return 1024u;
+    return 0u;
 }
 
 // LW little-endian words of read r; bytes past L read as 'A' (what the table's rows are padded with)
@@ -336,14 +344,14 @@ __device__ __forceinline__ Rd planes_of_words(const uint32_t (&rw)[LW], uint32_t
     return rd;
 }
 
-template <uint32_t MODE, uint32_t LW, bool ALIGNED>
-__global__ void __launch_bounds__(kSeededThreads) sgdx_match_exact_first(const DevParams p) {
+template <uint32_t MODE, uint32_t LW, bool ALIGNED, uint32_t THREADS>
+__global__ void __launch_bounds__(THREADS) sgdx_match_exact_first(const DevParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     ExactSmem sm;
-    exact_carve(smem_raw, kSeededThreads, p.S, LW, p.ex_bits, p.seed_hdr_total, p.seed_ids_total, &sm);
+    exact_carve(smem_raw, THREADS, p.S, LW, p.ex_bits, p.seed_hdr_total, p.seed_ids_total, &sm);
     const uint32_t nbins = (p.S + 1u) * 3u;
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    constexpr uint32_t nwarps = kSeededThreads / 32, T = kSeededThreads, R = kExactReadsPerThread;
+    constexpr uint32_t nwarps = THREADS / 32, T = THREADS, R = kExactReadsPerThread;
     constexpr uint32_t kNone = 0xFFFFFFFFu;
     const uint32_t nslots = 1u << p.ex_bits;
 
@@ -572,17 +580,17 @@ __global__ void __launch_bounds__(kSeededThreads) sgdx_match_exact_first(const D
     }
 }
 
-template <uint32_t MODE, uint32_t LW, bool ALIGNED>
+template <uint32_t MODE, uint32_t LW, bool ALIGNED, uint32_t THREADS>
 static cudaError_t launch_exact_t(const DevParams &p, int sms, cudaStream_t stream) {
-    size_t smem = exact_smem_bytes(p);
-    auto kern = sgdx_match_exact_first<MODE, LW, ALIGNED>;
+    size_t smem = exact_smem_bytes(p, THREADS);
+    auto kern = sgdx_match_exact_first<MODE, LW, ALIGNED, THREADS>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kSeededThreads, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
-    kern<<<persistent_grid(p.n, kSeededThreads * kExactReadsPerThread, sms, per_sm), kSeededThreads, smem, stream>>>(p);
+    kern<<<persistent_grid(p.n, THREADS * kExactReadsPerThread, sms, per_sm), THREADS, smem, stream>>>(p);
     return cudaGetLastError();
 }
 
@@ -590,7 +598,11 @@ template <uint32_t MODE, uint32_t LW>
 static cudaError_t launch_exact_lw(const DevParams &p, int sms, cudaStream_t stream) {
     if (p.Lw == LW) {
         const bool aligned = (p.L & 3u) == 0u && (reinterpret_cast<uintptr_t>(p.reads_ascii) & 3u) == 0u;
-        return aligned ? launch_exact_t<MODE, LW, true>(p, sms, stream) : launch_exact_t<MODE, LW, false>(p, sms, stream);
+        if (exact_block_threads(p) == 1024u)
+            return aligned ? launch_exact_t<MODE, LW, true, 1024>(p, sms, stream)
+                           : launch_exact_t<MODE, LW, false, 1024>(p, sms, stream);
+        return aligned ? launch_exact_t<MODE, LW, true, 256>(p, sms, stream)
+                       : launch_exact_t<MODE, LW, false, 256>(p, sms, stream);
     }
     if constexpr (LW < 8) return launch_exact_lw<MODE, LW + 1>(p, sms, stream);
     return cudaErrorInvalidValue;
