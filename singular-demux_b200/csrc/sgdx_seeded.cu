@@ -260,7 +260,7 @@ struct ExactSmem {
     uint32_t *ascii;         // [S * Lw]
     uint32_t *hist;          // [(S+1)*3] verdict counters of the block
     uint32_t *cq;            // [threads] Q3 entries that need the all-samples scan
-    uint32_t *counts;        // fill of q1, q2, q3, cq
+    uint32_t *ring;          // [3] pushes of the current phase, one counter per phase modulo 3
     uint16_t *hdr;           // [seed_hdr_total] seed index
     uint16_t *ids;           // [seed_ids_total]
 };
@@ -278,7 +278,7 @@ __host__ __device__ inline size_t exact_carve(unsigned char *base, uint32_t thre
     s.ascii = reinterpret_cast<uint32_t *>(base + o);        o += (size_t)S * Lw * 4;
     s.hist = reinterpret_cast<uint32_t *>(base + o);         o += (size_t)(S + 1) * 3 * 4;
     s.cq = reinterpret_cast<uint32_t *>(base + o);           o += (size_t)threads * 4;
-    s.counts = reinterpret_cast<uint32_t *>(base + o);       o += 16;
+    s.ring = reinterpret_cast<uint32_t *>(base + o);         o += 16;
     s.hdr = reinterpret_cast<uint16_t *>(base + o);          o += ((size_t)hdr_total * 2 + 15) & ~(size_t)15;
     s.ids = reinterpret_cast<uint16_t *>(base + o);          o += ((size_t)ids_total * 2 + 15) & ~(size_t)15;
     if (out) *out = s;
@@ -361,7 +361,7 @@ __global__ void __launch_bounds__(THREADS) sgdx_match_exact_first(const DevParam
     for (uint32_t i = threadIdx.x; i < p.S; i += T) sm.table[i] = p.table[i];
     for (uint32_t i = threadIdx.x; i < p.seed_hdr_total; i += T) sm.hdr[i] = p.seed_hdr[i];
     for (uint32_t i = threadIdx.x; i < p.seed_ids_total; i += T) sm.ids[i] = p.seed_ids[i];
-    if (threadIdx.x < 4) sm.counts[threadIdx.x] = 0u;
+    if (threadIdx.x < 4) sm.ring[threadIdx.x] = 0u;
     __syncthreads();
 
     const uint32_t shift = 32u - p.ex_bits, smask = nslots - 1u;
@@ -371,12 +371,18 @@ __global__ void __launch_bounds__(THREADS) sgdx_match_exact_first(const DevParam
     auto read_of = [&](uint32_t e) -> uint64_t {
         return ((uint64_t)blockIdx.x + (uint64_t)(e / (T * R)) * gridDim.x) * (T * R) + (e % (T * R));
     };
-    auto sync_fills = [&]() {
+    // Every phase (front end or stage) pushes into exactly one queue.  Slots are handed out by an atomic on
+    // ring[phase % 3], added to the queue's fill, which every thread tracks in a register.  One barrier ends
+    // the phase: it publishes the pushed entries, after it everybody reads the phase's push count, and thread 0
+    // clears the counter that phase+2 will use (last read one barrier ago, next written one barrier ahead).
+    uint32_t phase = 0;
+    auto push_slot = [&]() -> uint32_t { return atomicAdd(&sm.ring[phase % 3u], 1u); };
+    auto end_phase = [&]() -> uint32_t {
         __syncthreads();
-        n1 = sm.counts[0];
-        n2 = sm.counts[1];
-        n3 = sm.counts[2];
-        __syncthreads();  // nobody pushes again before everyone has read the fills
+        const uint32_t pushed = sm.ring[phase % 3u];
+        if (threadIdx.x == 0) sm.ring[(phase + 2u) % 3u] = 0u;
+        phase++;
+        return pushed;
     };
 
     // ---- stage 3: reads with invalid bases, and whatever the seed index cannot enumerate
@@ -395,23 +401,22 @@ __global__ void __launch_bounds__(THREADS) sgdx_match_exact_first(const DevParam
             if (!cannot_match<MODE>(p, rd))
                 scan = p.seed_C == 0u || !seed_search<MODE, true>(p, sm.hdr, sm.ids, sm.table, rd, best, nxt);
         }
-        if (scan) sm.cq[atomicAdd(&sm.counts[3], 1u)] = e;
+        if (scan) sm.cq[push_slot()] = e;
         Verdict v = apply_rules<MODE>(p, rd, best, nxt);
         emit(p, r, valid && !scan, rd, v, sm.hist);
-        const uint32_t nscan = __syncthreads_count(scan);
-        for (uint32_t q = warp; q < nscan; q += nwarps) {  // one warp per read, all samples
-            const uint64_t qrid = read_of(sm.cq[q]);
-            uint32_t rw[LW];
-            load_words<LW, ALIGNED>(p.reads_ascii, qrid, p.L, rw);  // same address in every lane
-            const Rd qrd = planes_of_words<LW>(rw, p.L);
-            Verdict qv = warp_scan<MODE>(p, sm.table, qrd, lane);
-            if (lane == 0) emit_single(p, qrid, qrd, qv, sm.hist);
+        const uint32_t nscan = end_phase();
+        n3 -= count;
+        if (nscan) {
+            for (uint32_t q = warp; q < nscan; q += nwarps) {  // one warp per read, all samples
+                const uint64_t qrid = read_of(sm.cq[q]);
+                uint32_t rw[LW];
+                load_words<LW, ALIGNED>(p.reads_ascii, qrid, p.L, rw);  // same address in every lane
+                const Rd qrd = planes_of_words<LW>(rw, p.L);
+                Verdict qv = warp_scan<MODE>(p, sm.table, qrd, lane);
+                if (lane == 0) emit_single(p, qrid, qrd, qv, sm.hist);
+            }
+            __syncthreads();  // cq is free again before a following stage 3 pushes into it
         }
-        if (threadIdx.x == 0) {
-            sm.counts[2] = n3 - count;
-            sm.counts[3] = 0u;  // read by nobody else between the two barriers around this store
-        }
-        sync_fills();
     };
 
     // ---- stage 2: planes + seed search for reads made of A/C/G/T only
@@ -430,7 +435,7 @@ __global__ void __launch_bounds__(THREADS) sgdx_match_exact_first(const DevParam
             if (cannot_match<MODE>(p, rd)) {
                 done = true;  // NoMatch without a search
             } else if ((rd.nmask | rd.xmask) != 0u || p.seed_C == 0u) {
-                sm.q3[atomicAdd(&sm.counts[2], 1u)] = e;
+                sm.q3[n3 + push_slot()] = e;
             } else {
                 seed_search<MODE, false>(p, sm.hdr, sm.ids, sm.table, rd, best, nxt);
                 done = true;
@@ -438,8 +443,8 @@ __global__ void __launch_bounds__(THREADS) sgdx_match_exact_first(const DevParam
         }
         Verdict v = apply_rules<MODE>(p, rd, best, nxt);
         emit(p, r, done, rd, v, sm.hist);
-        if (threadIdx.x == 0) sm.counts[1] = n2 - count;
-        sync_fills();
+        n3 += end_phase();
+        n2 -= count;
     };
 
     // ---- stage 1: one-substitution / one-no-call neighbours of the barcodes (global table, L2 resident)
@@ -491,10 +496,10 @@ __global__ void __launch_bounds__(THREADS) sgdx_match_exact_first(const DevParam
                     slot = (slot + 1u) & nmask;
                 }
             }
-            if (!resolved) sm.q2[atomicAdd(&sm.counts[1], 1u)] = e;
+            if (!resolved) sm.q2[n2 + push_slot()] = e;
         }
-        if (threadIdx.x == 0) sm.counts[0] = n1 - count;
-        sync_fills();
+        n2 += end_phase();
+        n1 -= count;
     };
 
     // One loop, one copy of every stage: the deepest non-empty queue with a full batch runs first (so no
@@ -562,10 +567,10 @@ __global__ void __launch_bounds__(THREADS) sgdx_match_exact_first(const DevParam
                     if (p.out_dist) p.out_dist[r] = 0u;
                     atomicAdd(&sm.hist[hit[k] * 3u + 1u], 1u);  // perfect match (ATOMS.POPC.INC: aggregated in hardware)
                 } else if (r < p.n) {
-                    sm.q1[atomicAdd(&sm.counts[0], 1u)] = iter * (T * R) + k * T + threadIdx.x;
+                    sm.q1[n1 + push_slot()] = iter * (T * R) + k * T + threadIdx.x;
                 }
             }
-            sync_fills();
+            n1 += end_phase();
             base += (uint64_t)gridDim.x * (T * R);
             iter++;
         } else {
