@@ -58,6 +58,7 @@ struct sgdx_handle {
     uint32_t *d_ex_slots = nullptr, *d_ex_ascii = nullptr, *d_nb_slots = nullptr;
     bool seeded = false;  // launches use sgdx_match_seeded
     HopSlot *d_hash1 = nullptr, *d_hash2 = nullptr;
+    uint16_t *d_hop_lut1 = nullptr, *d_hop_lut2 = nullptr;
     unsigned long long *d_hop_fwd = nullptr, *d_hop_rev = nullptr;
     unsigned long long *d_counters = nullptr;
     std::vector<std::string> keys1, keys2;  // distinct index1 / index2 halves (ASCII), id order
@@ -165,6 +166,27 @@ static int build_seed_index(sgdx_handle *h, const std::vector<uint2> &table, boo
     return SGDX_OK;
 }
 
+// Two-choice cuckoo insertion (random walk).  owner[] remembers the hash of the entry in each slot so that an
+// evicted entry can find its other position.  false = gave up (caller grows the table).
+static bool cuckoo_insert(std::vector<uint32_t> &slots, std::vector<uint32_t> &owner, uint32_t empty, uint32_t bits,
+                          uint32_t hsh, uint32_t entry) {
+    uint32_t last = 0xFFFFFFFFu;
+    for (int kick = 0; kick < 2000; kick++) {
+        const uint32_t p1 = hsh >> (32u - bits), p2 = ex_second(hsh) >> (32u - bits);
+        for (uint32_t pos : {p1, p2})
+            if (slots[pos] == empty) {
+                slots[pos] = entry;
+                owner[pos] = hsh;
+                return true;
+            }
+        const uint32_t victim = p1 == last ? p2 : p1;
+        std::swap(entry, slots[victim]);
+        std::swap(hsh, owner[victim]);
+        last = victim;
+    }
+    return false;
+}
+
 // Exact-match front end of the seeded kernel (sgdx_seeded.cu): barcode rows as padded ASCII words and
 // an open-addressing table over them.  Enabled only when a byte-exact hit decides the read on its own:
 // min pairwise distance of the table > min_delta.
@@ -189,15 +211,14 @@ static int build_exact_table(sgdx_handle *h, const uint8_t *barcodes, const std:
     if (getenv("SGDX_DISABLE_EXACT")) return SGDX_OK;          // test hook: plain seeded kernel
     if (dmin <= p.delta) return SGDX_OK;                       // an exact hit could still be delta-rejected
     if (exact_block_threads(p) == 0u) return SGDX_OK;          // tables that do not fit one SM: general path only
-    std::vector<uint32_t> rows((size_t)S * p.Lw, 0x41414141u), slots((size_t)1 << bits, 0u);
+    std::vector<uint32_t> rows((size_t)S * p.Lw, 0x41414141u), slots((size_t)1 << bits, 0u), owner((size_t)1 << bits, 0u);
     for (uint32_t s = 0; s < S; s++) {
         memcpy(&rows[(size_t)s * p.Lw], barcodes + (size_t)s * L, L);  // little-endian host; tail bytes stay 'A'
         uint32_t hsh = 0;
         for (uint32_t i = 0; i < p.Lw; i++) hsh += rows[(size_t)s * p.Lw + i] * K[i];
         hsh = ex_mix(hsh);
-        uint32_t slot = hsh >> (32u - bits);
-        while (slots[slot]) slot = (slot + 1u) & ((1u << bits) - 1u);
-        slots[slot] = ((hsh & 0xFFFFu) << 16) | (s + 1u);
+        // load factor <= 1/4: two-choice cuckoo placement does not fail in practice; if it does, no front end
+        if (!cuckoo_insert(slots, owner, 0u, bits, hsh, ((hsh & 0xFFFFu) << 16) | (s + 1u))) return SGDX_OK;
     }
     CU(cudaMalloc(&h->d_ex_slots, slots.size() * sizeof(uint32_t)));
     CU(cudaMalloc(&h->d_ex_ascii, rows.size() * sizeof(uint32_t)));
@@ -216,7 +237,7 @@ static int build_exact_table(sgdx_handle *h, const uint8_t *barcodes, const std:
     uint32_t nbits = 8;
     while ((1ull << nbits) < 4u * entries) nbits++;
     if (nbits > 26) return SGDX_OK;
-    std::vector<uint32_t> nb((size_t)1 << nbits, 0xFFFFFFFFu);
+    std::vector<uint32_t> nb((size_t)1 << nbits, 0xFFFFFFFFu), nb_owner((size_t)1 << nbits, 0u);
     static const uint8_t letters[5] = {'A', 'C', 'G', 'T', 'N'};
     std::vector<uint32_t> row(p.Lw);
     for (uint32_t s = 0; s < S; s++)
@@ -228,9 +249,9 @@ static int build_exact_table(sgdx_handle *h, const uint8_t *barcodes, const std:
                 uint32_t hsh = 0;
                 for (uint32_t i = 0; i < p.Lw; i++) hsh += row[i] * K[i];
                 hsh = ex_mix(hsh);
-                uint32_t slot = hsh >> (32u - nbits);
-                while (nb[slot] != 0xFFFFFFFFu) slot = (slot + 1u) & ((1u << nbits) - 1u);
-                nb[slot] = ((hsh & 0x7FFu) << 21) | (l << 18) | (pos << 13) | s;
+                if (!cuckoo_insert(nb, nb_owner, 0xFFFFFFFFu, nbits, hsh,
+                                   ((hsh & 0x7FFu) << 21) | (l << 18) | (pos << 13) | s))
+                    return SGDX_OK;  // (load factor <= 1/4: not seen) stage 1 then just forwards to the seed search
             }
     CU(cudaMalloc(&h->d_nb_slots, nb.size() * sizeof(uint32_t)));
     CU(cudaMemcpy(h->d_nb_slots, nb.data(), nb.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
@@ -331,6 +352,25 @@ extern "C" int sgdx_create(const sgdx_config *cfg, const uint8_t *barcodes, sgdx
         CU(cudaMemcpy(h->d_hash2, t2.data(), t2.size() * sizeof(HopSlot), cudaMemcpyHostToDevice));
         p.hash1 = h->d_hash1;
         p.hash2 = h->d_hash2;
+        if (p.i1 <= 11u && p.i2 <= 11u && p.u1 < 0xFFFFu && p.u2 < 0xFFFFu) {  // direct-address tables, <= 8 MB each
+            auto build_lut = [&](const std::vector<std::string> &keys, uint32_t len, uint16_t **d_out) -> int {
+                std::vector<uint16_t> lut((size_t)1 << (2 * len), 0xFFFFu);
+                for (uint32_t id = 0; id < keys.size(); id++) {
+                    if (keys[id].find('N') != std::string::npos) continue;  // Undetermined's half: reads with N take the hash path
+                    uint32_t lo, hi;
+                    encode_planes(reinterpret_cast<const uint8_t *>(keys[id].data()), len, &lo, &hi);
+                    lut[lo | (hi << len)] = (uint16_t)id;
+                }
+                CU(cudaMalloc(d_out, lut.size() * sizeof(uint16_t)));
+                CU(cudaMemcpy(*d_out, lut.data(), lut.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+                return SGDX_OK;
+            };
+            if (int rc = build_lut(h->keys1, p.i1, &h->d_hop_lut1)) { sgdx_destroy(h); return rc; }
+            if (int rc = build_lut(h->keys2, p.i2, &h->d_hop_lut2)) { sgdx_destroy(h); return rc; }
+            p.hop_lut1 = h->d_hop_lut1;
+            p.hop_lut2 = h->d_hop_lut2;
+            p.hop_direct = 1;
+        }
         size_t cells = (size_t)p.u1 * p.u2;
         CU(cudaMalloc(&h->d_hop_fwd, cells * sizeof(unsigned long long)));
         CU(cudaMalloc(&h->d_hop_rev, cells * sizeof(unsigned long long)));
@@ -395,6 +435,8 @@ extern "C" void sgdx_destroy(sgdx_handle *h) {
     cudaFree(h->d_nb_slots);
     cudaFree(h->d_hash1);
     cudaFree(h->d_hash2);
+    cudaFree(h->d_hop_lut1);
+    cudaFree(h->d_hop_lut2);
     cudaFree(h->d_hop_fwd);
     cudaFree(h->d_hop_rev);
     cudaFree(h->d_counters);

@@ -40,6 +40,8 @@ struct DevParams {
     uint32_t alln1, alln2;       // dense ids of Undetermined's all-N halves
     const HopSlot *hash1, *hash2;
     uint32_t hmask1, hmask2;     // capacity - 1
+    const uint16_t *hop_lut1, *hop_lut2;  // direct-address id tables of the halves (key = lo | hi << len), 0xFFFF = absent
+    uint32_t hop_direct;         // 1 when both halves are <= 11 bases and the tables above exist
     unsigned long long *hop_fwd; // [u1][u2]  barcode = I1[a] ++ I2[b]
     unsigned long long *hop_rev; // [u1][u2]  barcode = I2[b] ++ I1[a]   (reversed-orientation rule only)
     // seeded kernel: pigeonhole seed index over the expected barcodes (built by sgdx_create).
@@ -58,7 +60,8 @@ struct DevParams {
     // by a multiplicative hash of their ASCII words.  A read that equals a barcode byte for byte is a
     // Match with distance 0 without any search iff min pairwise table distance dmin > min_delta
     // (triangle inequality: every other sample is >= dmin away) -- ex_on says so.
-    const uint32_t *ex_slots;    // [1 << ex_bits]  (tag << 16) | (sample + 1), 0 = empty
+    const uint32_t *ex_slots;    // [1 << ex_bits]  (tag << 16) | (sample + 1), 0 = empty; cuckoo: a key sits at
+                                 // h >> (32-bits) or ex_second(h) >> (32-bits), so a lookup is two independent probes
     const uint32_t *ex_ascii;    // [S][Lw] barcode bytes as little-endian words, tail bytes 'A'
     uint32_t ex_on, ex_bits;
     uint32_t Lw;                 // ceil(L / 4)
@@ -88,6 +91,9 @@ __host__ __device__ inline uint32_t ex_mix(uint32_t h) {
     h ^= h >> 13;
     return h;
 }
+
+// second cuckoo position of a key with (mixed) hash h; the first one is h >> (32 - bits)
+__host__ __device__ inline uint32_t ex_second(uint32_t h) { return h * 0x9E3779B1u + 0x7F4A7C15u; }
 
 // 0x80 in every byte of z that is zero (exact, no cross-byte borrow)
 __device__ __forceinline__ uint32_t zero_bytes(uint32_t z) {
@@ -203,6 +209,17 @@ __device__ __forceinline__ uint32_t hop_find(const HopSlot *__restrict__ tab, ui
 
 // metrics.rs:658-676 for one NoMatch read (len == i1 + i2 always holds for device batches)
 __device__ __forceinline__ void hop_check(const DevParams &p, const Rd &rd) {
+    if (p.hop_direct && (rd.nmask | rd.xmask) == 0u) {
+        // short halves without invalid bases: four independent table loads instead of up to four hash probes
+        const uint32_t m1 = (1u << p.i1) - 1u, m2 = (1u << p.i2) - 1u;
+        const uint32_t a = __ldg(p.hop_lut1 + ((rd.lo & m1) | ((rd.hi & m1) << p.i1)));
+        const uint32_t b = __ldg(p.hop_lut2 + (((rd.lo >> p.i1) & m2) | (((rd.hi >> p.i1) & m2) << p.i2)));
+        const uint32_t c = __ldg(p.hop_lut1 + (((rd.lo >> p.i2) & m1) | (((rd.hi >> p.i2) & m1) << p.i1)));
+        const uint32_t d = __ldg(p.hop_lut2 + ((rd.lo & m2) | ((rd.hi & m2) << p.i2)));
+        if (a != 0xFFFFu && b != 0xFFFFu) atomicAdd(&p.hop_fwd[(uint64_t)a * p.u2 + b], 1ull);
+        else if (c != 0xFFFFu && d != 0xFFFFu) atomicAdd(&p.hop_rev[(uint64_t)c * p.u2 + d], 1ull);
+        return;
+    }
     uint32_t a = hop_find(p.hash1, p.hmask1, p.alln1, rd.lo, rd.hi, rd.nmask, rd.xmask, p.i1);
     if (a != 0xFFFFFFFFu) {
         uint32_t b = hop_find(p.hash2, p.hmask2, p.alln2, rd.lo >> p.i1, rd.hi >> p.i1, rd.nmask >> p.i1,

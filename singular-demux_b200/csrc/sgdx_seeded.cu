@@ -364,7 +364,7 @@ __global__ void __launch_bounds__(THREADS) sgdx_match_exact_first(const DevParam
     if (threadIdx.x < 4) sm.ring[threadIdx.x] = 0u;
     __syncthreads();
 
-    const uint32_t shift = 32u - p.ex_bits, smask = nslots - 1u;
+    const uint32_t shift = 32u - p.ex_bits;
     uint32_t n1 = 0, n2 = 0, n3 = 0;  // queue fills, tracked identically by every thread
 
     // queue entries number the block's reads: iteration * (T*R) + offset inside the iteration's tile
@@ -458,42 +458,39 @@ __global__ void __launch_bounds__(THREADS) sgdx_match_exact_first(const DevParam
                 uint32_t rw[LW];
                 load_words<LW, ALIGNED>(p.reads_ascii, r, p.L, rw);
                 const uint32_t h = word_hash<LW>(p, rw);
-                const uint32_t tag = h & 0x7FFu, nmask = (1u << p.nb_bits) - 1u;
-                uint32_t slot = h >> (32u - p.nb_bits);
-                for (;;) {
-                    const uint32_t ent = __ldg(p.nb_slots + slot);
-                    if (ent == kNone) break;
-                    if ((ent >> 21) == tag) {
-                        const uint32_t s = ent & 0x1FFFu, pos = (ent >> 13) & 31u, letter = (ent >> 18) & 7u;
-                        const uint32_t *row = sm.ascii + s * LW;
-                        const uint32_t sh = (pos & 3u) * 8u, wi = pos >> 2;
-                        const uint32_t byte = letter == 4u ? 0x4Eu : ((0x54474341u >> (8u * letter)) & 0xFFu);  // ACGT, N
-                        uint32_t diff = 0u;
+                const uint32_t tag = h & 0x7FFu, nshift = 32u - p.nb_bits;
+                const uint32_t e1 = __ldg(p.nb_slots + (h >> nshift)), e2 = __ldg(p.nb_slots + (ex_second(h) >> nshift));
+                const bool m1 = e1 != kNone && (e1 >> 21) == tag, m2 = e2 != kNone && (e2 >> 21) == tag;
+                for (uint32_t t = 0; t < 2u; t++) {  // second round only if both tags matched and the first failed
+                    if (!(t == 0u ? (m1 || m2) : (m1 && m2 && !resolved))) continue;
+                    const uint32_t ent = t == 0u ? (m1 ? e1 : e2) : e2;
+                    const uint32_t s = ent & 0x1FFFu, pos = (ent >> 13) & 31u, letter = (ent >> 18) & 7u;
+                    const uint32_t *row = sm.ascii + s * LW;
+                    const uint32_t sh = (pos & 3u) * 8u, wi = pos >> 2;
+                    const uint32_t byte = letter == 4u ? 0x4Eu : ((0x54474341u >> (8u * letter)) & 0xFFu);  // ACGT, N
+                    uint32_t diff = 0u;
 #pragma unroll
-                        for (uint32_t i = 0; i < LW; i++) {
-                            uint32_t expect = row[i];
-                            if (i == wi) expect = (expect & ~(0xFFu << sh)) | (byte << sh);
-                            diff |= rw[i] ^ expect;
-                        }
-                        if (diff == 0u) {
-                            // distance 1 over all positions; every other sample is >= dmin-1 > 1+delta away
-                            const bool is_n = letter == 4u;
-                            uint32_t d = 1u;
-                            bool ok = true;
-                            if (is_n) {
-                                ok = !(p.max_no_calls >= 0 && 1u > (uint32_t)p.max_no_calls);
-                                if (MODE == kModeHamming) d = 1u - min(1u, p.free_ns);
-                            }
-                            if (ok && d <= p.M) {
-                                p.out_idx[r] = (uint16_t)s;
-                                if (p.out_dist) p.out_dist[r] = (uint8_t)d;
-                                atomicAdd(&sm.hist[s * 3u + (d == 0u ? 1u : 2u)], 1u);
-                                resolved = true;
-                            }
-                            break;
-                        }
+                    for (uint32_t i = 0; i < LW; i++) {
+                        uint32_t expect = row[i];
+                        if (i == wi) expect = (expect & ~(0xFFu << sh)) | (byte << sh);
+                        diff |= rw[i] ^ expect;
                     }
-                    slot = (slot + 1u) & nmask;
+                    if (diff != 0u) continue;
+                    // distance 1 over all positions; every other sample is >= dmin-1 > 1+delta away
+                    const bool is_n = letter == 4u;
+                    uint32_t d = 1u;
+                    bool ok = true;
+                    if (is_n) {
+                        ok = !(p.max_no_calls >= 0 && 1u > (uint32_t)p.max_no_calls);
+                        if (MODE == kModeHamming) d = 1u - min(1u, p.free_ns);
+                    }
+                    if (ok && d <= p.M) {
+                        p.out_idx[r] = (uint16_t)s;
+                        if (p.out_dist) p.out_dist[r] = (uint8_t)d;
+                        atomicAdd(&sm.hist[s * 3u + (d == 0u ? 1u : 2u)], 1u);
+                        resolved = true;
+                    }
+                    break;  // the read is this neighbour whether or not the rules accept it
                 }
             }
             if (!resolved) sm.q2[n2 + push_slot()] = e;
@@ -532,35 +529,25 @@ __global__ void __launch_bounds__(THREADS) sgdx_match_exact_first(const DevParam
                 const uint64_t r = base + k * T + threadIdx.x;
                 const uint32_t h = word_hash<LW>(p, rw[k]);
                 const uint32_t tag = h & 0xFFFFu;
-                uint32_t slot = h >> shift;
-                uint32_t ent = sm.slots[slot];
+                // cuckoo table: the barcode, if this read is one, sits in one of two slots (no probe chains)
+                const uint32_t e1 = sm.slots[h >> shift], e2 = sm.slots[ex_second(h) >> shift];
+                const bool m1 = e1 != 0u && (e1 >> 16) == tag, m2 = e2 != 0u && (e2 >> 16) == tag;
                 hit[k] = kNone;
-                // first probe, straight-line: nearly every read is decided here
-                bool tagged = ent != 0u && (ent >> 16) == tag;
-                if (tagged) {
-                    const uint32_t s = (ent & 0xFFFFu) - 1u;
+                if (m1 || m2) {
+                    const uint32_t s = ((m1 ? e1 : e2) & 0xFFFFu) - 1u;
                     const uint32_t *row = sm.ascii + s * LW;
                     uint32_t diff = 0u;
 #pragma unroll
                     for (uint32_t i = 0; i < LW; i++) diff |= rw[k][i] ^ row[i];
                     if (diff == 0u) hit[k] = s;
                 }
-                if (hit[k] == kNone && ent != 0u) {  // occupied by another barcode: keep probing (rare)
-                    for (;;) {
-                        slot = (slot + 1u) & smask;
-                        ent = sm.slots[slot];
-                        if (ent == 0u) break;
-                        if ((ent >> 16) != tag) continue;
-                        const uint32_t s = (ent & 0xFFFFu) - 1u;
-                        const uint32_t *row = sm.ascii + s * LW;
-                        uint32_t diff = 0u;
+                if (m1 && m2 && hit[k] == kNone) {  // both tags matched and the first entry was not it (~never)
+                    const uint32_t s = (e2 & 0xFFFFu) - 1u;
+                    const uint32_t *row = sm.ascii + s * LW;
+                    uint32_t diff = 0u;
 #pragma unroll
-                        for (uint32_t i = 0; i < LW; i++) diff |= rw[k][i] ^ row[i];
-                        if (diff == 0u) {
-                            hit[k] = s;
-                            break;
-                        }
-                    }
+                    for (uint32_t i = 0; i < LW; i++) diff |= rw[k][i] ^ row[i];
+                    if (diff == 0u) hit[k] = s;
                 }
                 if (hit[k] != kNone) {
                     p.out_idx[r] = (uint16_t)hit[k];
