@@ -328,7 +328,7 @@ __device__ __forceinline__ uint32_t word_hash(const DevParams &p, const uint32_t
     uint32_t h = 0u;
 #pragma unroll
     for (uint32_t i = 0; i < LW; i++) h += rw[i] * p.ex_k[i];
-    return ex_mix(h);
+    return ex_mix(h);  // (see sgdx_device.cuh)
 }
 
 // planes of a read held as ASCII words (same result as load_ascii)
@@ -342,6 +342,28 @@ __device__ __forceinline__ Rd planes_of_words(const uint32_t (&rw)[LW], uint32_t
     rd.lo &= lm & ~inv;
     rd.hi &= lm & ~inv;
     return rd;
+}
+
+// lo/hi planes of a read held as ASCII words plus a flag "some byte is not A/C/G/T" (then the planes are not
+// usable and the caller takes the full conversion).  The expected byte of each 2-bit code comes from a PRMT
+// lookup: code = (ascii >> 1) & 3 -> "ACTG"[code]; a byte is valid iff it equals its own code's letter.
+template <uint32_t LW>
+__device__ __forceinline__ bool planes_if_acgt(const uint32_t (&rw)[LW], uint32_t L, uint32_t &lo, uint32_t &hi) {
+    uint32_t l = 0u, h = 0u, bad = 0u;
+#pragma unroll
+    for (uint32_t i = 0; i < LW; i++) {
+        const uint32_t w = rw[i];
+        const uint32_t c = (w >> 1) & 0x03030303u;
+        const uint32_t y = c | (c >> 4);                               // byte 0: c0 | c1 << 4, byte 2: c2 | c3 << 4
+        const uint32_t e = __byte_perm(0x47544341u, 0u, __byte_perm(y, 0u, 0x4420));  // letters of the four codes
+        bad |= w ^ e;
+        l += (((c & 0x01010101u) * 0x01020408u) >> 24) << (4u * i);    // gather bit 0 of each byte (no carries)
+        h += (((c & 0x02020202u) * 0x00810204u) >> 24) << (4u * i);    // gather bit 1 of each byte
+    }
+    // pad bytes of the last word are 'A' (code 0, valid), so bits >= L are zero already
+    lo = l;
+    hi = h;
+    return bad == 0u;
 }
 
 template <uint32_t MODE, uint32_t LW, bool ALIGNED, uint32_t THREADS>
@@ -431,12 +453,9 @@ __global__ void __launch_bounds__(THREADS) sgdx_match_exact_first(const DevParam
             r = read_of(e);
             uint32_t rw[LW];
             load_words<LW, ALIGNED>(p.reads_ascii, r, p.L, rw);
-            rd = planes_of_words<LW>(rw, p.L);
-            if (cannot_match<MODE>(p, rd)) {
-                done = true;  // NoMatch without a search
-            } else if ((rd.nmask | rd.xmask) != 0u || p.seed_C == 0u) {
-                sm.q3[n3 + push_slot()] = e;
-            } else {
+            if (!planes_if_acgt<LW>(rw, p.L, rd.lo, rd.hi) || p.seed_C == 0u) {
+                sm.q3[n3 + push_slot()] = e;  // invalid bases (stage 3 does the full conversion), or no index
+            } else {                          // an all-A/C/G/T read passes the gate and the cannot-match test
                 seed_search<MODE, false>(p, sm.hdr, sm.ids, sm.table, rd, best, nxt);
                 done = true;
             }
@@ -553,8 +572,18 @@ __global__ void __launch_bounds__(THREADS) sgdx_match_exact_first(const DevParam
                     p.out_idx[r] = (uint16_t)hit[k];
                     if (p.out_dist) p.out_dist[r] = 0u;
                     atomicAdd(&sm.hist[hit[k] * 3u + 1u], 1u);  // perfect match (ATOMS.POPC.INC: aggregated in hardware)
-                } else if (r < p.n) {
-                    sm.q1[n1 + push_slot()] = iter * (T * R) + k * T + threadIdx.x;
+                }
+            }
+            {   // misses -> Q1, one slot reservation per thread for all of its reads
+                uint32_t nmiss = 0u;
+#pragma unroll
+                for (uint32_t k = 0; k < R; k++) nmiss += (hit[k] == kNone && base + k * T + threadIdx.x < p.n) ? 1u : 0u;
+                if (nmiss) {
+                    uint32_t slot = n1 + atomicAdd(&sm.ring[phase % 3u], nmiss);
+#pragma unroll
+                    for (uint32_t k = 0; k < R; k++)
+                        if (hit[k] == kNone && base + k * T + threadIdx.x < p.n)
+                            sm.q1[slot++] = iter * (T * R) + k * T + threadIdx.x;
                 }
             }
             n1 += end_phase();
