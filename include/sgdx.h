@@ -120,6 +120,12 @@ int sgdx_set_stream(sgdx_handle *h, uint32_t slot, void *cuda_stream);
 /* Name of the assignment kernel this handle launches for ASCII input ("sgdx_match_direct",
  * "sgdx_match_seeded" or "sgdx_match_exact_first"); static storage. */
 const char *sgdx_kernel_name(const sgdx_handle *h);
+/* Which accelerations this handle's tables allow (they never change results, only speed). */
+#define SGDX_PATH_SEED_INDEX 1u   /* pigeonhole seed index exists (T+1 <= L, fits shared memory) */
+#define SGDX_PATH_EXACT 2u        /* exact-match front end (min pairwise table distance > min_delta) */
+#define SGDX_PATH_NEIGHBOURS 4u   /* one-substitution neighbour table (min pairwise distance > min_delta + 2) */
+#define SGDX_PATH_HOP_DIRECT 8u   /* direct-address hop tables (both index halves <= 11 bases) */
+uint32_t sgdx_path_flags(const sgdx_handle *h);
 /* Number of kernel launches issued through this handle so far. */
 uint64_t sgdx_launch_count(const sgdx_handle *h);
 

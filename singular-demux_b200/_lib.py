@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libsgdx.so")
 MATCHER_AUTO, MATCHER_CACHED_HAMMING, MATCHER_PRECOMPUTE = 0, 1, 2
 KERNEL_AUTO, KERNEL_DIRECT, KERNEL_SEEDED = 0, 1, 2
 NO_DIST = 0xFF
+PATH_SEED_INDEX, PATH_EXACT, PATH_NEIGHBOURS, PATH_HOP_DIRECT = 1, 2, 4, 8
 MAX_BARCODE_LEN = 32
 MAX_SAMPLES = 8192
 
@@ -44,7 +45,7 @@ class SynthParams(C.Structure):
 SYMBOLS = [
     "sgdx_last_error", "sgdx_version", "sgdx_create", "sgdx_destroy", "sgdx_get_config", "sgdx_alloc_host",
     "sgdx_free_host", "sgdx_match_batch", "sgdx_sync", "sgdx_match_device", "sgdx_pack_device",
-    "sgdx_match_packed_device", "sgdx_set_stream", "sgdx_kernel_name", "sgdx_launch_count", "sgdx_counters", "sgdx_reset_counters",
+    "sgdx_match_packed_device", "sgdx_set_stream", "sgdx_kernel_name", "sgdx_path_flags", "sgdx_launch_count", "sgdx_counters", "sgdx_reset_counters",
     "sgdx_hop_count", "sgdx_hop_export", "sgdx_batcher_create", "sgdx_batcher_destroy", "sgdx_batcher_push",
     "sgdx_batcher_flush", "sgdx_batcher_next", "sgdx_measure_int_peak",
     "sgdx_synth_table", "sgdx_synth_reads_host", "sgdx_synth_reads_device",
@@ -78,6 +79,8 @@ def lib() -> C.CDLL:
     L.sgdx_set_stream.argtypes = [vp, u32, vp]
     L.sgdx_kernel_name.argtypes = [vp]
     L.sgdx_kernel_name.restype = C.c_char_p
+    L.sgdx_path_flags.argtypes = [vp]
+    L.sgdx_path_flags.restype = u32
     L.sgdx_launch_count.argtypes = [vp]
     L.sgdx_launch_count.restype = u64
     L.sgdx_counters.argtypes = [vp, vp, C.POINTER(Totals)]

@@ -190,7 +190,8 @@ static bool cuckoo_insert(std::vector<uint32_t> &slots, std::vector<uint32_t> &o
 // Exact-match front end of the seeded kernel (sgdx_seeded.cu): barcode rows as padded ASCII words and
 // an open-addressing table over them.  Enabled only when a byte-exact hit decides the read on its own:
 // min pairwise distance of the table > min_delta.
-static int build_exact_table(sgdx_handle *h, const uint8_t *barcodes, const std::vector<uint2> &table) {
+static int build_exact_table(sgdx_handle *h, const uint8_t *barcodes, const std::vector<uint2> &table,
+                             double est_candidates) {
     DevParams &p = h->base;
     const uint32_t S = p.S, L = p.L;
     p.ex_on = 0;
@@ -215,7 +216,7 @@ static int build_exact_table(sgdx_handle *h, const uint8_t *barcodes, const std:
     for (uint32_t s = 0; s < S; s++) {
         memcpy(&rows[(size_t)s * p.Lw], barcodes + (size_t)s * L, L);  // little-endian host; tail bytes stay 'A'
         uint32_t hsh = 0;
-        for (uint32_t i = 0; i < p.Lw; i++) hsh += rows[(size_t)s * p.Lw + i] * K[i];
+        for (uint32_t i = 0; i < p.Lw; i++) hsh = ex_word_step(hsh, rows[(size_t)s * p.Lw + i], K[i]);
         hsh = ex_mix(hsh);
         // load factor <= 1/4: two-choice cuckoo placement does not fail in practice; if it does, no front end
         if (!cuckoo_insert(slots, owner, 0u, bits, hsh, ((hsh & 0xFFFFu) << 16) | (s + 1u))) return SGDX_OK;
@@ -233,26 +234,35 @@ static int build_exact_table(sgdx_handle *h, const uint8_t *barcodes, const std:
     p.nb_on = 0;
     if (getenv("SGDX_DISABLE_NEIGHBOURS")) return SGDX_OK;  // test hook: exercise the seed search on every miss
     if ((uint64_t)dmin <= (uint64_t)p.delta + 2u || S > 0x1FFFu) return SGDX_OK;
+    // The neighbour stage costs two L2 probes per missed read; it pays when the seed search it saves is long
+    // (measured on a B200: C3, ~12 expected candidates per read: 2.11 ms with, 2.82 ms without per 100 M reads;
+    // C2, ~1.5 candidates: 1.65 ms with, 1.56 ms without)
+    if (est_candidates < 4.0 && !getenv("SGDX_FORCE_NEIGHBOURS")) return SGDX_OK;
     const uint64_t entries = (uint64_t)S * L * 4u;
     uint32_t nbits = 8;
     while ((1ull << nbits) < 4u * entries) nbits++;
     if (nbits > 26) return SGDX_OK;
-    std::vector<uint32_t> nb((size_t)1 << nbits, 0xFFFFFFFFu), nb_owner((size_t)1 << nbits, 0u);
     static const uint8_t letters[5] = {'A', 'C', 'G', 'T', 'N'};
-    std::vector<uint32_t> row(p.Lw);
-    for (uint32_t s = 0; s < S; s++)
-        for (uint32_t pos = 0; pos < L; pos++)
-            for (uint32_t l = 0; l < 5; l++) {
-                if (letters[l] == barcodes[(size_t)s * L + pos]) continue;
-                for (uint32_t i = 0; i < p.Lw; i++) row[i] = rows[(size_t)s * p.Lw + i];
-                reinterpret_cast<uint8_t *>(row.data())[pos] = letters[l];
-                uint32_t hsh = 0;
-                for (uint32_t i = 0; i < p.Lw; i++) hsh += row[i] * K[i];
-                hsh = ex_mix(hsh);
-                if (!cuckoo_insert(nb, nb_owner, 0xFFFFFFFFu, nbits, hsh,
-                                   ((hsh & 0x7FFu) << 21) | (l << 18) | (pos << 13) | s))
-                    return SGDX_OK;  // (load factor <= 1/4: not seen) stage 1 then just forwards to the seed search
-            }
+    std::vector<uint32_t> nb, nb_owner, row(p.Lw);
+    bool placed = false;
+    for (int attempt = 0; attempt < 2 && !placed && nbits <= 26; attempt++, nbits += placed ? 0 : 1) {
+        nb.assign((size_t)1 << nbits, 0xFFFFFFFFu);
+        nb_owner.assign((size_t)1 << nbits, 0u);
+        placed = true;
+        for (uint32_t s = 0; s < S && placed; s++)
+            for (uint32_t pos = 0; pos < L && placed; pos++)
+                for (uint32_t l = 0; l < 5 && placed; l++) {
+                    if (letters[l] == barcodes[(size_t)s * L + pos]) continue;
+                    for (uint32_t i = 0; i < p.Lw; i++) row[i] = rows[(size_t)s * p.Lw + i];
+                    reinterpret_cast<uint8_t *>(row.data())[pos] = letters[l];
+                    uint32_t hsh = 0;
+                    for (uint32_t i = 0; i < p.Lw; i++) hsh = ex_word_step(hsh, row[i], K[i]);
+                    hsh = ex_mix(hsh);
+                    placed = cuckoo_insert(nb, nb_owner, 0xFFFFFFFFu, nbits, hsh,
+                                           ((hsh & 0x7FFu) << 21) | (l << 18) | (pos << 13) | s);
+                }
+    }
+    if (!placed) return SGDX_OK;  // not seen with load factor <= 1/4; stage 1 then just forwards to the seed search
     CU(cudaMalloc(&h->d_nb_slots, nb.size() * sizeof(uint32_t)));
     CU(cudaMemcpy(h->d_nb_slots, nb.data(), nb.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
     p.nb_slots = h->d_nb_slots;
@@ -394,7 +404,7 @@ extern "C" int sgdx_create(const sgdx_config *cfg, const uint8_t *barcodes, sgdx
         if (h->cfg.kernel == SGDX_KERNEL_AUTO) h->seeded = have && 2.0 * est + 16.0 < (double)S;
         else h->seeded = have && h->cfg.kernel == SGDX_KERNEL_SEEDED;
         if (h->seeded)
-            if (int rc = build_exact_table(h, barcodes, table)) {
+            if (int rc = build_exact_table(h, barcodes, table, est)) {
                 sgdx_destroy(h);
                 return rc;
             }
@@ -570,6 +580,13 @@ extern "C" const char *sgdx_kernel_name(const sgdx_handle *h) {
     if (!h) return "";
     if (!h->seeded) return "sgdx_match_direct";
     return h->base.ex_on ? "sgdx_match_exact_first" : "sgdx_match_seeded";
+}
+
+extern "C" uint32_t sgdx_path_flags(const sgdx_handle *h) {
+    if (!h) return 0u;
+    const DevParams &p = h->base;
+    return (h->seeded ? SGDX_PATH_SEED_INDEX : 0u) | (h->seeded && p.ex_on ? SGDX_PATH_EXACT : 0u) |
+           (h->seeded && p.ex_on && p.nb_on ? SGDX_PATH_NEIGHBOURS : 0u) | (p.hop_direct ? SGDX_PATH_HOP_DIRECT : 0u);
 }
 
 extern "C" uint64_t sgdx_launch_count(const sgdx_handle *h) { return h ? h->launches.load() : 0; }

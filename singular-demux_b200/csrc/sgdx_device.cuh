@@ -92,6 +92,18 @@ __host__ __device__ inline uint32_t ex_mix(uint32_t h) {
     return h;
 }
 
+// Hash of a barcode held as ASCII words: sum over words of lo32(w*K) + hi32(w*K), then ex_mix.  The high half
+// matters: a substitution in the top byte of a word changes lo32(w*K) only in its top 8 bits (256 possible
+// differences, so the 4L neighbours of one barcode collide all the time); hi32 keeps the rest.
+__host__ __device__ inline uint32_t ex_word_step(uint32_t h, uint32_t w, uint32_t k) {
+#ifdef __CUDA_ARCH__
+    return __umulhi(w, k) + (w * k + h);  // IMAD + IMAD.HI on the fma pipe
+#else
+    const uint64_t pr = (uint64_t)w * k;
+    return (uint32_t)(pr >> 32) + ((uint32_t)pr + h);
+#endif
+}
+
 // second cuckoo position of a key with (mixed) hash h; the first one is h >> (32 - bits)
 __host__ __device__ inline uint32_t ex_second(uint32_t h) { return h * 0x9E3779B1u + 0x7F4A7C15u; }
 

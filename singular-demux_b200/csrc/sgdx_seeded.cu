@@ -327,8 +327,8 @@ template <uint32_t LW>
 __device__ __forceinline__ uint32_t word_hash(const DevParams &p, const uint32_t (&rw)[LW]) {
     uint32_t h = 0u;
 #pragma unroll
-    for (uint32_t i = 0; i < LW; i++) h += rw[i] * p.ex_k[i];
-    return ex_mix(h);  // (see sgdx_device.cuh)
+    for (uint32_t i = 0; i < LW; i++) h = ex_word_step(h, rw[i], p.ex_k[i]);
+    return ex_mix(h);
 }
 
 // planes of a read held as ASCII words (same result as load_ascii)
@@ -442,14 +442,14 @@ __global__ void __launch_bounds__(THREADS) sgdx_match_exact_first(const DevParam
     };
 
     // ---- stage 2: planes + seed search for reads made of A/C/G/T only
-    auto stage2 = [&](uint32_t count) {
+    auto stage2 = [&](uint32_t count, const uint32_t *q, uint32_t &nq) {  // q = Q2, or Q1 when there is no stage 1
         const bool valid = threadIdx.x < count;
         uint64_t r = 0;
         Rd rd = {0u, 0u, 0u, 0u};
         uint32_t best = kInfKey, nxt = kInfKey;
         bool done = false;
         if (valid) {
-            const uint32_t e = sm.q2[n2 - count + threadIdx.x];
+            const uint32_t e = q[nq - count + threadIdx.x];
             r = read_of(e);
             uint32_t rw[LW];
             load_words<LW, ALIGNED>(p.reads_ascii, r, p.L, rw);
@@ -463,7 +463,7 @@ __global__ void __launch_bounds__(THREADS) sgdx_match_exact_first(const DevParam
         Verdict v = apply_rules<MODE>(p, rd, best, nxt);
         emit(p, r, done, rd, v, sm.hist);
         n3 += end_phase();
-        n2 -= count;
+        nq -= count;
     };
 
     // ---- stage 1: one-substitution / one-no-call neighbours of the barcodes (global table, L2 resident)
@@ -472,7 +472,7 @@ __global__ void __launch_bounds__(THREADS) sgdx_match_exact_first(const DevParam
         if (valid) {
             const uint32_t e = sm.q1[n1 - count + threadIdx.x];
             bool resolved = false;
-            if (p.nb_on) {
+            {
                 const uint64_t r = read_of(e);
                 uint32_t rw[LW];
                 load_words<LW, ALIGNED>(p.reads_ascii, r, p.L, rw);
@@ -527,9 +527,10 @@ __global__ void __launch_bounds__(THREADS) sgdx_match_exact_first(const DevParam
         if (n3 >= T || (!more && n1 == 0u && n2 == 0u && n3)) {
             stage3(min(n3, T));
         } else if (n2 >= T || (!more && n1 == 0u && n2)) {
-            stage2(min(n2, T));
+            stage2(min(n2, T), sm.q2, n2);
         } else if (n1 >= T || (!more && n1)) {
-            stage1(min(n1, T));
+            if (p.nb_on) stage1(min(n1, T));
+            else stage2(min(n1, T), sm.q1, n1);  // no neighbour table: misses go straight to the seed search
         } else if (more) {
             uint32_t rw[R][LW];
             uint32_t hit[R];

@@ -199,6 +199,9 @@ class GpuMatcher:
     def kernel_name(self) -> str:
         return lib().sgdx_kernel_name(self._h).decode()
 
+    def path_flags(self) -> int:
+        return int(lib().sgdx_path_flags(self._h))
+
     def launch_count(self) -> int:
         return int(lib().sgdx_launch_count(self._h))
 

@@ -147,6 +147,24 @@ def test_seeded_kernel_engages_and_falls_back():
         m.close()
 
 
+@pytest.mark.parametrize("cfg", ["C1", "C2", "C3"])
+def test_baseline_tables_take_every_fast_path(cfg):
+    """The BASELINE tables (unique dual indexes, min pairwise distance 6) must run with the seed index, the
+    exact-match front end, the neighbour table and the direct hop tables all enabled; a silently disabled
+    table would only show up as a slower kernel."""
+    from singular_demux_b200 import _lib
+    w = sg.synth.CONFIGS[cfg]
+    kind = sg.select_matcher(w.barcode_len)
+    m = CLS[kind]([bytes(t) for t in w.table()], w.max_mismatches, w.min_delta, w.free_ns, index_lengths=w.index_lengths)
+    want = _lib.PATH_SEED_INDEX | _lib.PATH_EXACT
+    if cfg == "C3":  # the neighbour stage is only enabled where the seed search it saves is long (DESIGN.md)
+        want |= _lib.PATH_NEIGHBOURS
+    if max(w.index_lengths) <= 11:
+        want |= _lib.PATH_HOP_DIRECT
+    assert m.path_flags() == want and m.kernel_name() == "sgdx_match_exact_first"
+    m.close()
+
+
 @pytest.mark.parametrize("p_n,p_x", [(0.03, 0.0), (0.10, 0.01), (0.30, 0.05)])
 @pytest.mark.parametrize("S,L,i1,M,D,F", [(384, 20, 10, 1, 2, 1), (200, 24, 12, 3, 1, 2), (96, 16, 8, 2, 1, 3),
                                             (1536, 24, 12, 3, 1, 1), (60, 32, 16, 2, 2, 4), (500, 12, 6, 1, 1, 1)])
@@ -165,10 +183,15 @@ def test_seeded_no_call_paths(S, L, i1, M, D, F, p_n, p_x):
             st.close()
 
 
+@pytest.mark.parametrize("neighbours", [False, True])
 @pytest.mark.parametrize("cfg", ["C1", "C2"])
-def test_exact_and_neighbour_front_end_rule_grid(cfg):
-    """Well separated tables (min pairwise distance 6) take the exact-match and one-substitution shortcuts
-    of the seeded kernel; every rule parameter that touches those shortcuts is swept against the oracle."""
+def test_exact_and_neighbour_front_end_rule_grid(cfg, neighbours, monkeypatch):
+    """Well separated tables (min pairwise distance 6) take the exact-match and (forced here, it is a cost
+    heuristic otherwise) one-substitution shortcuts of the seeded kernel; every rule parameter that touches
+    those shortcuts is swept against the oracle."""
+    from singular_demux_b200 import _lib
+    if neighbours:
+        monkeypatch.setenv("SGDX_FORCE_NEIGHBOURS", "1")
     base = sg.synth.CONFIGS[cfg]
     w = sg.synth.Workload("grid", base.num_samples, base.barcode_len, base.index1_len, 1, 2, n_reads=40_000,
                           table_seed=base.table_seed, read_seed=77, p_true=0.85, p_hop=0.05, p_sub=0.03, p_n=0.02,
@@ -180,6 +203,8 @@ def test_exact_and_neighbour_front_end_rule_grid(cfg):
             for D in (0, 1, 2, 3, 4):
                 for F, mnc in ((0, None), (1, None), (2, 0), (1, 1), (0, 0)):
                     st = _stage(table, kind, M, D, F, mnc, w.index_lengths, sg.KERNEL_SEEDED)
+                    if neighbours and D <= 3 and st.matcher.path_flags() & _lib.PATH_EXACT:  # dmin = 6 > D + 2
+                        assert st.matcher.path_flags() & _lib.PATH_NEIGHBOURS
                     got = st.demultiplex(reads)
                     want = _oracle(table, kind, M, D, F, mnc, w.index_lengths, reads, force_closed_form=True)
                     _assert_same(st, got, want, reads.shape[0])
