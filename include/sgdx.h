@@ -107,7 +107,10 @@ int sgdx_match_batch(sgdx_handle *h, uint32_t slot, const uint8_t *barcodes_asci
                      uint16_t *out_idx, uint8_t *out_dist);
 int sgdx_sync(sgdx_handle *h, uint32_t slot, float *device_ms /* nullable: kernel time of last batch */);
 
-/* Same, buffers already resident on the handle's device (no copies). */
+/* Same, buffers already resident on the handle's device (no copies).  When barcode_len is not a multiple of 4
+ * or the pointer is not 4-byte aligned the kernels load the aligned 32-bit words that contain a read, so up to
+ * 3 bytes before the first and after the last read of the buffer are read (never used): keep the buffer inside
+ * one allocation. */
 int sgdx_match_device(sgdx_handle *h, uint32_t slot, const uint8_t *d_barcodes_ascii, uint64_t n,
                       uint16_t *d_out_idx, uint8_t *d_out_dist);
 /* Two-stage form: pack kernel (ASCII -> 16-byte records, 128-bit stores) and match on packed records. */

@@ -326,6 +326,82 @@ def test_back_to_back_create_and_first_batch():
             st.close()
 
 
+@pytest.mark.parametrize("S,L,i1,expect", [(3000, 30, 15, "sgdx_match_seeded"), (8192, 20, 10, "sgdx_match_direct"),
+                                            (1536, 24, 12, "sgdx_match_exact_first")])
+def test_large_tables_pick_a_kernel_that_fits(S, L, i1, expect):
+    """Table sizes around the shared-memory limits: 1536 x 24 runs the exact-first kernel with one 1024-thread
+    CTA per SM, 3000 x 30 only fits the plain seeded kernel, 8192 x 16 only the direct kernel."""
+    w = sg.synth.Workload("big", S, L, i1, 1, 1, n_reads=30_000, table_seed=S, read_seed=L, p_true=0.85, p_hop=0.05,
+                          p_sub=0.02, p_n=0.01, p_x=0.001, min_dist=2 if S < 8192 else 1)
+    table = w.table()
+    reads = w.reads_host(0, w.n_reads, table)
+    st = _stage(table, sg.MatcherKind.CachedHammingDistance, 1, 1, 1, None, w.index_lengths, sg.KERNEL_AUTO)
+    assert st.matcher.kernel_name() == expect
+    got = st.demultiplex(reads)
+    want = _oracle(table, sg.MatcherKind.CachedHammingDistance, 1, 1, 1, None, w.index_lengths, reads)
+    _assert_same(st, got, want, reads.shape[0])
+    st.close()
+
+
+def test_two_host_threads_on_two_slots():
+    """One handle, two host threads, each on its own slot (the `Matcher + Send + Sync` contract, demux.rs:422):
+    results and the shared device counters must equal a single-threaded pass."""
+    import threading
+    rng = np.random.default_rng(21)
+    w, table, reads = _random_case(rng, 96, 16, 8, n=200_000)
+    n = reads.shape[0]
+    want = _oracle(table, sg.MatcherKind.CachedHammingDistance, 1, 1, 1, None, w.index_lengths, reads)
+    st = _stage(table, sg.MatcherKind.CachedHammingDistance, 1, 1, 1, None, w.index_lengths, sg.KERNEL_AUTO, slots=2)
+    idx = np.empty(n, dtype=np.uint16)
+    dist = np.empty(n, dtype=np.uint8)
+    errors = []
+
+    def work(slot):
+        try:
+            lo, hi = slot * (n // 2), n if slot else n // 2
+            for a in range(lo, hi, 7_001):  # many small batches so the two threads really interleave
+                b = min(a + 7_001, hi)
+                st.matcher.submit(reads[a:b], idx[a:b], dist[a:b], slot)
+                st.matcher.sync(slot)
+        except Exception as e:  # pragma: no cover
+            errors.append(e)
+
+    ts = [threading.Thread(target=work, args=(s_,)) for s_ in (0, 1)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errors
+    assert np.array_equal(idx, want["idx"]) and np.array_equal(dist, want["dist"])
+    m = st.metrics()
+    assert np.array_equal(m.per_sample_array(), want["per_sample"]) and m.total_templates == n
+    assert m.sample_barcode_hop_tracker.count_tracker == want["hops"]
+    st.close()
+
+
+def test_two_devices_merge_to_single_pass():
+    """Sharding across GPUs: one handle per device, counters summed on the host (needs >= 2 GPUs)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    rng = np.random.default_rng(22)
+    w, table, reads = _random_case(rng, 96, 16, 8, n=100_000)
+    n = reads.shape[0]
+    want = _oracle(table, sg.MatcherKind.CachedHammingDistance, 1, 2, 1, None, w.index_lengths, reads)
+    parts, idx = [], np.empty(n, dtype=np.uint16)
+    for dev in (0, 1):
+        a, b = sg.sharding.shard_range(n, dev, 2)
+        st = sg.BarcodeAssignmentStage(_samples(table), sg.CachedHammingDistanceMatcher, 1, 2, 1, None, w.index_lengths,
+                                       device=dev)
+        idx[a:b] = st.demultiplex(reads[a:b]).sample_indices
+        parts.append(st.metrics())
+        st.close()
+    merged = sg.sharding.merge_metrics(parts)
+    assert np.array_equal(idx, want["idx"])
+    assert np.array_equal(merged.per_sample_array(), want["per_sample"]) and merged.total_templates == n
+    assert merged.sample_barcode_hop_tracker.count_tracker == want["hops"]
+
+
 def test_batcher_returns_batches_in_order():
     from singular_demux_b200._lib import check, lib
     rng = np.random.default_rng(3)
