@@ -289,10 +289,12 @@ size_t exact_smem_bytes(const DevParams &p, uint32_t threads) {
     return exact_carve(nullptr, threads, p.S, p.Lw, p.ex_bits, p.seed_hdr_total, p.seed_ids_total, nullptr);
 }
 
-// CTA size of sgdx_match_exact_first for this table: 256 threads while at least 3 CTAs fit an SM, one
-// 1024-thread CTA per SM for large tables (C3: 1536 x 24 bp needs 124 KB of tables), 0 = does not fit at all
+// CTA size of sgdx_match_exact_first for this table: 512 threads while at least two CTAs fit an SM (measured on
+// C2, ms per 100 M reads: 256 threads 1.51, 512 threads 1.34, 1024 threads 1.48 -- the per-CTA copies of the
+// tables are shared by more threads), one 1024-thread CTA per SM for large tables (C3: 1536 x 24 bp needs
+// 124 KB of tables), 0 = does not fit at all
 uint32_t exact_block_threads(const DevParams &p) {
-    if (exact_smem_bytes(p, 256) <= 75u * 1024u) return 256u;
+    if (exact_smem_bytes(p, 512) <= 113u * 1024u) return 512u;
     if (exact_smem_bytes(p, 1024) <= 227u * 1024u) return 1024u;
     return 0u;
 }
@@ -623,8 +625,8 @@ static cudaError_t launch_exact_lw(const DevParams &p, int sms, cudaStream_t str
         if (exact_block_threads(p) == 1024u)
             return aligned ? launch_exact_t<MODE, LW, true, 1024>(p, sms, stream)
                            : launch_exact_t<MODE, LW, false, 1024>(p, sms, stream);
-        return aligned ? launch_exact_t<MODE, LW, true, 256>(p, sms, stream)
-                       : launch_exact_t<MODE, LW, false, 256>(p, sms, stream);
+        return aligned ? launch_exact_t<MODE, LW, true, 512>(p, sms, stream)
+                       : launch_exact_t<MODE, LW, false, 512>(p, sms, stream);
     }
     if constexpr (LW < 8) return launch_exact_lw<MODE, LW + 1>(p, sms, stream);
     return cudaErrorInvalidValue;
