@@ -78,6 +78,7 @@ __device__ __forceinline__ bool seed_search(const DevParams &p, const uint16_t *
         const uint32_t key0 = ((rd.lo >> pos) & wm) | (((rd.hi >> pos) & wm) << w);
         if (!EXPAND) {  // caller guarantees a read without invalid bases: exactly one bucket per chunk
             const uint32_t start = hdr[off + key0], end = hdr[off + key0 + 1u];
+#pragma unroll 1  // buckets hold 0-2 samples: an unrolled loop only adds its trip-count dispatch ladder
             for (uint32_t i = start; i < end; i++) {
                 const uint32_t s = ids[i];
                 const uint2 t = table[s];
@@ -92,6 +93,7 @@ __device__ __forceinline__ bool seed_search(const DevParams &p, const uint16_t *
         for (uint32_t b = 0; b < nvar; b++) {
             const uint32_t key = key0 | ((b & 1u) << j) | ((b >> 1) << (w + j));
             const uint32_t start = hdr[off + key], end = hdr[off + key + 1u];
+#pragma unroll 1
             for (uint32_t i = start; i < end; i++) {
                 const uint32_t s = ids[i];
                 const uint2 t = table[s];
