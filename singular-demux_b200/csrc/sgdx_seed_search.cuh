@@ -1,0 +1,116 @@
+// sgdx_seed_search.cuh -- device pieces shared by the seeded kernels: candidate scoring, the pigeonhole seed
+// search, the one-warp-per-read scan and the single-thread emit (see sgdx_seeded.cu for the description).
+#pragma once
+#include "sgdx_kernels.h"
+
+namespace sgdx {
+
+// ------------------------------------------------------------------------------------------------
+// shared pieces
+// ------------------------------------------------------------------------------------------------
+template <uint32_t MODE>
+__device__ __forceinline__ void score(const Rd &rd, uint32_t inv, uint32_t skip, uint32_t slo, uint32_t shi, uint32_t s,
+                                      uint32_t &best, uint32_t &nxt) {
+    uint32_t t, m;
+    asm("lop3.b32 %0, %1, %2, %3, 0xBE;" : "=r"(t) : "r"(rd.lo), "r"(slo), "r"(inv));  // (lo ^ slo) | inv
+    asm("lop3.b32 %0, %1, %2, %3, 0xF6;" : "=r"(m) : "r"(t), "r"(rd.hi), "r"(shi));    // t | (hi ^ shi)
+    uint32_t d = __popc(m);
+    uint32_t key;
+    asm("mad.lo.u32 %0, %1, 65536, %2;" : "=r"(key) : "r"(d), "r"(s));
+    if (MODE == kModePreCompute) key = (d == skip) ? kInfKey : key;
+    if (key != best) {  // the same sample seen through another chunk
+        nxt = min(nxt, max(best, key));
+        best = min(best, key);
+    }
+}
+
+// reads no table can match: every sample is further than M away, or the no-call gate (demux.rs:528-531)
+template <uint32_t MODE>
+__device__ __forceinline__ bool cannot_match(const DevParams &p, const Rd &rd) {
+    const uint32_t n_nc = __popc(rd.nmask), n_x = __popc(rd.xmask);
+    bool dead = p.max_no_calls >= 0 && n_nc > (uint32_t)p.max_no_calls;
+    if (MODE == kModeHamming) dead |= n_x + (n_nc > p.free_ns ? n_nc - p.free_ns : 0u) > p.M;
+    else dead |= rd.xmask != 0u || n_nc > p.M;
+    return dead;
+}
+
+// Enumerate the seed buckets of one read.  Returns false when some key window holds two or more invalid
+// bases (best/nxt are then incomplete and the caller hands the read to the all-samples scan).  Loops are
+// kept free of early exits so that the lanes of a warp reconverge after every bucket.
+template <uint32_t MODE, bool EXPAND>
+__device__ __forceinline__ bool seed_search(const DevParams &p, const uint16_t *__restrict__ hdr,
+                                            const uint16_t *__restrict__ ids, const uint2 *__restrict__ table,
+                                            const Rd &rd, uint32_t &best, uint32_t &nxt) {
+    const uint32_t inv = rd.nmask | rd.xmask;
+    const uint32_t skip = (MODE == kModePreCompute && rd.nmask != 0u) ? p.M + 1u : 0xFFFFu;
+    bool complete = true;
+    for (uint32_t c = 0; c < p.seed_C; c++) {
+        const uint32_t desc = p.seed_desc[c];
+        const uint32_t pos = desc & 0xFFu, w = (desc >> 8) & 0xFFu, off = desc >> 16;
+        const uint32_t wm = (1u << w) - 1u;
+        const uint32_t iv = (inv >> pos) & wm;
+        const uint32_t key0 = ((rd.lo >> pos) & wm) | (((rd.hi >> pos) & wm) << w);
+        if (!EXPAND) {  // caller guarantees a read without invalid bases: exactly one bucket per chunk
+            const uint32_t start = hdr[off + key0], end = hdr[off + key0 + 1u];
+#pragma unroll 1  // buckets hold 0-2 samples: an unrolled loop only adds its trip-count dispatch ladder
+            for (uint32_t i = start; i < end; i++) {
+                const uint32_t s = ids[i];
+                const uint2 t = table[s];
+                score<MODE>(rd, inv, skip, t.x, t.y, s, best, nxt);
+            }
+            continue;
+        }
+        const bool several = (iv & (iv - 1u)) != 0u;
+        complete = complete && !several;
+        const uint32_t nvar = several ? 0u : (iv ? 4u : 1u);
+        const uint32_t j = iv ? (uint32_t)__ffs(iv) - 1u : 0u;
+        for (uint32_t b = 0; b < nvar; b++) {
+            const uint32_t key = key0 | ((b & 1u) << j) | ((b >> 1) << (w + j));
+            const uint32_t start = hdr[off + key], end = hdr[off + key + 1u];
+#pragma unroll 1
+            for (uint32_t i = start; i < end; i++) {
+                const uint32_t s = ids[i];
+                const uint2 t = table[s];
+                score<MODE>(rd, inv, skip, t.x, t.y, s, best, nxt);
+            }
+        }
+    }
+    return complete;
+}
+
+// one warp, one read, all samples
+template <uint32_t MODE>
+__device__ __forceinline__ Verdict warp_scan(const DevParams &p, const uint2 *__restrict__ table, const Rd &rd,
+                                             uint32_t lane) {
+    const uint32_t inv = rd.nmask | rd.xmask;
+    const uint32_t skip = (MODE == kModePreCompute && rd.nmask != 0u) ? p.M + 1u : 0xFFFFu;
+    uint32_t b = kInfKey, n2 = kInfKey;
+    for (uint32_t s0 = 0; s0 < p.S; s0 += 32u) {  // same trip count in every lane: the warp stays converged
+        const uint32_t s = s0 + lane;
+        if (s < p.S) {
+            const uint2 t = table[s];
+            score<MODE>(rd, inv, skip, t.x, t.y, s, b, n2);
+        }
+    }
+    const uint32_t gb = __reduce_min_sync(0xFFFFFFFFu, b);
+    const uint32_t gn = __reduce_min_sync(0xFFFFFFFFu, b == gb ? n2 : b);  // keys are unique per sample
+    return apply_rules<MODE>(p, rd, gb, gn);
+}
+
+// verdict of one read written by one thread (the warp-cooperative path)
+__device__ __forceinline__ void emit_single(const DevParams &p, uint64_t r, const Rd &rd, const Verdict &v,
+                                            uint32_t *hist) {
+    p.out_idx[r] = (uint16_t)v.bin;
+    if (p.out_dist) p.out_dist[r] = (uint8_t)v.dist;
+    uint32_t cls = v.dist == 0u ? 1u : (v.dist == 1u ? 2u : 0u);
+    atomicAdd(&hist[v.bin * 3u + cls], 1u);
+    if (p.hop_on && v.bin == p.S) hop_check(p, rd);
+}
+
+inline uint32_t persistent_grid(uint64_t n, uint32_t threads, int sms, int per_sm) {
+    uint64_t tiles = (n + threads - 1) / threads;
+    uint64_t cap = (uint64_t)sms * (uint64_t)per_sm;  // persistent grid: a multiple of the SM count
+    return (uint32_t)(tiles < cap ? (tiles ? tiles : 1) : cap);
+}
+
+}  // namespace sgdx
