@@ -1,0 +1,243 @@
+// sgdx_host.hpp -- C++ host-side mirror of the reference's interface for the assignment path, over the C ABI
+// (include/sgdx.h).  The reference is Rust; this image has no cargo/rustc, so the compiled-language host side is
+// C++17, header only.  Names, argument meaning and error behaviour follow /root/reference/src/lib:
+//
+//   MatchResult                       matcher.rs:27-47      MatcherKind, select_matcher      matcher.rs:49-72, run.rs:196-198
+//   trait Matcher::find               matcher.rs:75-77      CachedHammingDistanceMatcher     matcher.rs:80-109
+//   PreComputeMatcher                 matcher.rs:121-262    DemuxedGroupSampleMetrics        metrics.rs:407-437
+//   SampleBarcodeHopTracker           metrics.rs:617-677    DemuxedGroupMetrics::update_with metrics.rs:315-328
+//   Demultiplexer's assignment step   demux.rs:524-556,581  (BarcodeAssignmentStage: the batched form a GPU needs)
+//
+// Errors: the reference returns anyhow::Result from everything around the matcher and find() itself cannot fail;
+// here every failed C-ABI call throws sgdx::Error carrying sgdx_last_error().  There is no CPU fallback: without
+// libsgdx.so / a CUDA device construction throws.
+#pragma once
+#include <cstdint>
+#include <map>
+#include <optional>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../../include/sgdx.h"
+
+namespace sgdx {
+
+struct Error : std::runtime_error {
+    int code;
+    Error(int c, const std::string &what) : std::runtime_error(what + ": " + sgdx_last_error()), code(c) {}
+};
+inline void check(int rc, const char *what) {
+    if (rc != SGDX_OK) throw Error(rc, what);
+}
+
+inline const char *const UNDETERMINED_NAME = "Undetermined";  // matcher.rs:19
+
+struct SampleMetadata {  // the fields of sample_metadata.rs::SampleMetadata this path reads
+    std::string sample_id;
+    std::string barcode;
+    size_t ordinal = 0;
+};
+
+struct MatchResult {  // matcher.rs:27-47
+    bool matched = false;
+    size_t sample_index = 0;
+    size_t hamming_dist = 0;
+    std::string barcode;
+    static MatchResult Match(size_t sample_index, size_t hamming_dist, std::string barcode) {
+        return {true, sample_index, hamming_dist, std::move(barcode)};
+    }
+    static MatchResult NoMatch(std::string barcode) { return {false, 0, 0, std::move(barcode)}; }
+    bool is_match() const { return matched; }
+    bool is_no_match() const { return !matched; }
+};
+
+enum class MatcherKind { CachedHammingDistance, PreCompute };  // matcher.rs:49-53
+
+inline MatcherKind select_matcher(size_t first_barcode_len, std::optional<MatcherKind> override_matcher = {}) {
+    // run.rs:196-198
+    if (first_barcode_len <= 12 || override_matcher == MatcherKind::PreCompute) return MatcherKind::PreCompute;
+    return MatcherKind::CachedHammingDistance;
+}
+
+struct Matcher {  // matcher.rs:75-77
+    virtual ~Matcher() = default;
+    virtual MatchResult find(std::string barcode) = 0;
+};
+
+// A matcher bound to one CUDA device (owns an sgdx handle).
+class GpuMatcher : public Matcher {
+  public:
+    GpuMatcher(const std::vector<SampleMetadata> &samples, MatcherKind kind, size_t max_mismatches, size_t min_delta,
+               size_t free_ns, std::optional<size_t> max_no_calls = {},
+               std::optional<std::pair<size_t, size_t>> index_lengths = {}, int device = 0, unsigned slots = 2)
+        : kind_(kind) {
+        if (samples.empty()) throw std::invalid_argument("a GPU matcher needs at least one sample");
+        L_ = samples[0].barcode.size();
+        std::string table;
+        for (const auto &s : samples) {
+            if (s.barcode.size() != L_) throw std::invalid_argument("all sample barcodes must have the same length");
+            table += s.barcode;
+        }
+        S_ = samples.size();
+        auto clamp = [](size_t v) { return (uint32_t)(v > 0xFFFFFFFFull ? 0xFFFFFFFFull : v); };
+        sgdx_config cfg{};
+        cfg.num_samples = (uint32_t)S_;
+        cfg.barcode_len = (uint32_t)L_;
+        cfg.max_mismatches = clamp(max_mismatches);
+        cfg.min_delta = clamp(min_delta);
+        cfg.free_ns = clamp(free_ns);
+        cfg.max_no_calls = max_no_calls ? (int32_t)(*max_no_calls > 0x7FFFFFFF ? 0x7FFFFFFF : *max_no_calls) : -1;
+        cfg.matcher = kind == MatcherKind::PreCompute ? SGDX_MATCHER_PRECOMPUTE : SGDX_MATCHER_CACHED_HAMMING;
+        cfg.index1_len = index_lengths ? (uint32_t)index_lengths->first : 0;
+        cfg.index2_len = index_lengths ? (uint32_t)index_lengths->second : 0;
+        cfg.device = device;
+        cfg.slots = slots;
+        cfg.kernel = SGDX_KERNEL_AUTO;
+        check(sgdx_create(&cfg, reinterpret_cast<const uint8_t *>(table.data()), &h_), "sgdx_create");
+    }
+    GpuMatcher(const GpuMatcher &) = delete;
+    GpuMatcher &operator=(const GpuMatcher &) = delete;
+    ~GpuMatcher() override { sgdx_destroy(h_); }
+
+    MatcherKind kind() const { return kind_; }
+    size_t num_samples() const { return S_; }
+    size_t barcode_len() const { return L_; }
+    sgdx_handle *handle() const { return h_; }
+
+    // trait Matcher: one barcode = one tiny device batch; use find_batch for throughput
+    MatchResult find(std::string barcode) override {
+        if (barcode.size() != L_) {
+            // only reachable with --sample-barcode-in-fastq-header: every PreCompute key has length L (NoMatch);
+            // the zip()-truncating Hamming case stays with the host's scalar code
+            if (kind_ == MatcherKind::PreCompute) return MatchResult::NoMatch(std::move(barcode));
+            throw std::invalid_argument("barcode length differs from the matcher's");
+        }
+        uint16_t idx = 0;
+        uint8_t dist = 0;
+        find_batch(reinterpret_cast<const uint8_t *>(barcode.data()), 1, &idx, &dist);
+        if (idx == S_) return MatchResult::NoMatch(std::move(barcode));
+        return MatchResult::Match(idx, dist, std::move(barcode));
+    }
+    // n barcodes of barcode_len() bytes each -> sample index (num_samples() = no match) and hamming distance
+    void find_batch(const uint8_t *barcodes, uint64_t n, uint16_t *idx, uint8_t *dist, unsigned slot = 0) {
+        check(sgdx_match_batch(h_, slot, barcodes, n, idx, dist), "sgdx_match_batch");
+        check(sgdx_sync(h_, slot, nullptr), "sgdx_sync");
+    }
+
+  private:
+    sgdx_handle *h_ = nullptr;
+    MatcherKind kind_;
+    size_t S_ = 0, L_ = 0;
+};
+
+struct CachedHammingDistanceMatcher : GpuMatcher {  // matcher.rs:80-109 (the LRU memo is a CPU detail)
+    CachedHammingDistanceMatcher(const std::vector<SampleMetadata> &samples, size_t max_mismatches, size_t min_delta,
+                                 size_t free_ns, std::optional<size_t> max_no_calls = {},
+                                 std::optional<std::pair<size_t, size_t>> index_lengths = {}, int device = 0)
+        : GpuMatcher(samples, MatcherKind::CachedHammingDistance, max_mismatches, min_delta, free_ns, max_no_calls,
+                     index_lengths, device) {}
+};
+struct PreComputeMatcher : GpuMatcher {  // matcher.rs:121-262; free_ns is accepted and ignored, as in the reference
+    PreComputeMatcher(const std::vector<SampleMetadata> &samples, size_t max_mismatches, size_t min_delta, size_t free_ns,
+                      std::optional<size_t> max_no_calls = {},
+                      std::optional<std::pair<size_t, size_t>> index_lengths = {}, int device = 0)
+        : GpuMatcher(samples, MatcherKind::PreCompute, max_mismatches, min_delta, free_ns, max_no_calls, index_lengths,
+                     device) {}
+};
+
+struct DemuxedGroupSampleMetrics {  // metrics.rs:407-437
+    size_t perfect_matches = 0, one_mismatch_matches = 0, total_matches = 0;
+    void update_with(const DemuxedGroupSampleMetrics &o) {
+        perfect_matches += o.perfect_matches;
+        one_mismatch_matches += o.one_mismatch_matches;
+        total_matches += o.total_matches;
+    }
+};
+
+struct SampleBarcodeHopTracker {  // metrics.rs:617-677
+    size_t index1_length = 0, index2_length = 0;
+    std::map<std::string, size_t> count_tracker;  // concatenated observed barcode -> count
+    void update_with_self(const SampleBarcodeHopTracker &o) {
+        for (const auto &kv : o.count_tracker) count_tracker[kv.first] += kv.second;
+    }
+};
+
+struct DemuxedGroupMetrics {  // metrics.rs:297-328 (the fields this path fills)
+    std::vector<DemuxedGroupSampleMetrics> per_sample_metrics;
+    size_t total_templates = 0;
+    std::optional<SampleBarcodeHopTracker> sample_barcode_hop_tracker;
+    void update_with(const DemuxedGroupMetrics &o) {
+        total_templates += o.total_templates;
+        for (size_t i = 0; i < per_sample_metrics.size() && i < o.per_sample_metrics.size(); i++)
+            per_sample_metrics[i].update_with(o.per_sample_metrics[i]);
+        if (sample_barcode_hop_tracker && o.sample_barcode_hop_tracker)
+            sample_barcode_hop_tracker->update_with_self(*o.sample_barcode_hop_tracker);
+    }
+};
+
+struct DemuxedGroup {  // demux.rs:637-645, minus the routed reads
+    std::vector<uint16_t> sample_indices;  // undetermined index for NoMatch
+    std::vector<uint8_t> hamming_dists;    // SGDX_NO_DIST for NoMatch
+};
+
+// The assignment + counting step of Demultiplexer::demultiplex, batched.  `samples` holds ALL samples, the last one
+// is Undetermined (demux.rs:221,259); the matcher sees samples[..n-1] (run.rs:201,220).
+class BarcodeAssignmentStage {
+  public:
+    BarcodeAssignmentStage(const std::vector<SampleMetadata> &samples, MatcherKind kind, size_t max_mismatches,
+                           size_t min_delta, size_t free_ns, std::optional<size_t> max_no_calls = {},
+                           std::optional<std::pair<size_t, size_t>> index_lengths = {}, int device = 0)
+        : undetermined_(samples.size() - 1), index_lengths_(index_lengths),
+          matcher_(std::vector<SampleMetadata>(samples.begin(), samples.end() - 1), kind, max_mismatches, min_delta,
+                   free_ns, max_no_calls, index_lengths, device) {}
+
+    size_t get_undetermined_index() const { return undetermined_; }
+    GpuMatcher &matcher() { return matcher_; }
+
+    DemuxedGroup demultiplex(const std::vector<std::string> &barcodes) {
+        std::string flat;
+        for (const auto &b : barcodes) {
+            if (b.size() != matcher_.barcode_len()) throw std::invalid_argument("device batches need barcodes of length L");
+            flat += b;
+        }
+        DemuxedGroup g;
+        g.sample_indices.resize(barcodes.size());
+        g.hamming_dists.resize(barcodes.size());
+        matcher_.find_batch(reinterpret_cast<const uint8_t *>(flat.data()), barcodes.size(), g.sample_indices.data(),
+                            g.hamming_dists.data());
+        return g;
+    }
+
+    // cumulative counters of every batch this stage has processed (device resident, read on demand)
+    DemuxedGroupMetrics metrics() {
+        const size_t S = matcher_.num_samples();
+        std::vector<uint64_t> per((S + 1) * 3);
+        sgdx_totals t{};
+        check(sgdx_counters(matcher_.handle(), per.data(), &t), "sgdx_counters");
+        DemuxedGroupMetrics m;
+        m.total_templates = t.total_templates;
+        for (size_t s = 0; s <= S; s++) m.per_sample_metrics.push_back({per[s * 3 + 1], per[s * 3 + 2], per[s * 3]});
+        if (index_lengths_) {
+            SampleBarcodeHopTracker tr{index_lengths_->first, index_lengths_->second, {}};
+            uint64_t n = 0, w = 0;
+            check(sgdx_hop_count(matcher_.handle(), &n), "sgdx_hop_count");
+            const size_t L = matcher_.barcode_len();
+            std::vector<uint8_t> keys((n ? n : 1) * L);
+            std::vector<uint64_t> counts(n ? n : 1);
+            check(sgdx_hop_export(matcher_.handle(), keys.data(), counts.data(), n ? n : 1, &w), "sgdx_hop_export");
+            for (uint64_t i = 0; i < w; i++)
+                tr.count_tracker[std::string(reinterpret_cast<const char *>(keys.data()) + i * L, L)] = counts[i];
+            m.sample_barcode_hop_tracker = std::move(tr);
+        }
+        return m;
+    }
+
+  private:
+    size_t undetermined_;
+    std::optional<std::pair<size_t, size_t>> index_lengths_;
+    GpuMatcher matcher_;
+};
+
+}  // namespace sgdx

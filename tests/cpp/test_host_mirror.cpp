@@ -1,0 +1,180 @@
+// test_host_mirror.cpp -- the reference's own known-answer tests for the assignment path, written against the
+// C++ host mirror (singular-demux_b200/host/sgdx_host.hpp) so that they read like the originals.  Needs a CUDA
+// device (run by tests/test_gpu_parity.py::test_cpp_host_mirror_known_answers on a B200).
+//   matcher.rs:550-622   test_find_two_samples / matcher.rs:682-727 readme examples
+//   demux.rs:1181-1267   delta too small, too many mismatches, too many Ns
+//   run.rs:593-690       test_end_to_end_simple (assignment + per-sample metrics + total_templates)
+//   run.rs:1184-1238     test_end_to_end_with_all_matchers
+//   run.rs:1382-1535     dual-index hop metrics / sample metrics, run.rs:1539-1605 single index no match
+#include <cstdio>
+#include <cstdlib>
+#include <string>
+#include <vector>
+
+#include "../../singular-demux_b200/host/sgdx_host.hpp"
+
+using namespace sgdx;
+
+static int failures = 0;
+#define EXPECT(cond)                                                                   \
+    do {                                                                               \
+        if (!(cond)) {                                                                 \
+            std::fprintf(stderr, "FAILED %s:%d: %s\n", __FILE__, __LINE__, #cond);     \
+            failures++;                                                                \
+        }                                                                              \
+    } while (0)
+
+static std::vector<SampleMetadata> samples_of(const std::vector<std::string> &barcodes, bool with_undetermined) {
+    std::vector<SampleMetadata> v;
+    for (size_t i = 0; i < barcodes.size(); i++) v.push_back({"Sample" + std::to_string(i + 1), barcodes[i], i});
+    if (with_undetermined) v.push_back({UNDETERMINED_NAME, std::string(barcodes[0].size(), 'N'), barcodes.size()});
+    return v;
+}
+static const MatcherKind kBoth[] = {MatcherKind::CachedHammingDistance, MatcherKind::PreCompute};
+
+// utils.rs:338-341
+static const std::vector<std::string> kFour = {"AAAAAAAAGATTACAGA", "CCCCCCCCGATTACAGA", "GGGGGGGGGATTACAGA",
+                                               "GGGGGGTTGATTACAGA"};
+
+static void test_find_two_samples() {  // matcher.rs:550-622
+    for (MatcherKind k : kBoth) {
+        GpuMatcher m(samples_of({"AAAA", "AACC"}, false), k, 2, 1, 0);
+        MatchResult r = m.find("AAAA");
+        EXPECT(r.is_match() && r.sample_index == 0 && r.hamming_dist == 0 && r.barcode == "AAAA");
+        EXPECT(m.find("AAAG").is_no_match());  // distances 1 and 2: delta 1 <= min_delta 1
+    }
+}
+
+static void test_readme_examples() {  // matcher.rs:682-727: max_mismatches 3, min_delta 1
+    struct Case { std::vector<std::string> samples; std::string observed; bool match; size_t dist; };
+    const Case cases[] = {
+        {{"AAA", "TTT"}, "GGA", false, 0},        // best 2, next 3
+        {{"AAA", "TTT"}, "GAA", true, 1},         // best 1, next 3
+        {{"AA", "TT"}, "AA", true, 0},            // best 0, next 2
+        {{"A", "T"}, "A", false, 0},              // best 0, next 1
+        {{"AAAAAA", "TTTTTT"}, "GGGAAA", true, 3},   // best 3, next 6
+        {{"AAAAAA", "TTTTTT"}, "GGGGAA", false, 0},  // best 4 > 3
+        {{"AA", "TT"}, "GG", false, 0},           // best 2, next 2
+    };
+    for (MatcherKind k : kBoth)
+        for (const Case &c : cases) {
+            GpuMatcher m(samples_of(c.samples, false), k, 3, 1, 0);
+            MatchResult r = m.find(c.observed);
+            EXPECT(r.is_match() == c.match);
+            if (c.match) EXPECT(r.sample_index == 0 && r.hamming_dist == c.dist);
+        }
+}
+
+static void test_demux_known_answers() {
+    {   // demux.rs:1181-1204: exact SAMPLE_BARCODE_4, min_delta 3 -> Undetermined (delta to sample 3 is 2)
+        BarcodeAssignmentStage st(samples_of(kFour, true), MatcherKind::CachedHammingDistance, 2, 3, 2, 1);
+        EXPECT(st.demultiplex({"GGGGGGTTGATTACAGA"}).sample_indices[0] == st.get_undetermined_index());
+    }
+    for (MatcherKind k : kBoth) {  // demux.rs:1208-1235: one mismatch, allowed 0
+        BarcodeAssignmentStage st(samples_of(kFour, true), k, 0, 1, 2, 1);
+        EXPECT(st.demultiplex({"AAAAAAAAGATTACAGT"}).sample_indices[0] == 4);
+    }
+    for (MatcherKind k : kBoth) {  // demux.rs:1239-1267: one N, max_no_calls 0
+        BarcodeAssignmentStage st(samples_of(kFour, true), k, 1, 1, 2, 0);
+        EXPECT(st.demultiplex({"NAAAAAAAGATTACAGA"}).sample_indices[0] == 4);
+    }
+}
+
+static void test_end_to_end_simple() {  // run.rs:593-690 with the defaults of opts.rs:535-560
+    BarcodeAssignmentStage st(samples_of(kFour, true), MatcherKind::CachedHammingDistance, 2, 1, 1, 1);
+    DemuxedGroup g = st.demultiplex({"AAAAAAAAGATTACAGA", "AAAAAAAAGATTACAGT", "AAAAAAAAGATTACTTT", "GGGGGGTCGATTACAGA",
+                                     "AAAAAAAAGANNNNNNN"});
+    const uint16_t want_idx[] = {0, 0, 4, 4, 4};
+    for (int i = 0; i < 5; i++) EXPECT(g.sample_indices[i] == want_idx[i]);
+    EXPECT(g.hamming_dists[0] == 0 && g.hamming_dists[1] == 1 && g.hamming_dists[2] == SGDX_NO_DIST);
+    DemuxedGroupMetrics m = st.metrics();
+    EXPECT(m.total_templates == 5);
+    EXPECT(m.per_sample_metrics[0].total_matches == 2 && m.per_sample_metrics[0].perfect_matches == 1 &&
+           m.per_sample_metrics[0].one_mismatch_matches == 1);
+    EXPECT(m.per_sample_metrics[4].total_matches == 3 && m.per_sample_metrics[4].perfect_matches == 0);
+    EXPECT(m.per_sample_metrics[1].total_matches == 0 && m.per_sample_metrics[2].total_matches == 0 &&
+           m.per_sample_metrics[3].total_matches == 0);
+}
+
+static void test_end_to_end_with_all_matchers() {  // run.rs:1184-1238: 8 bp, M=1, delta=1
+    for (MatcherKind k : kBoth) {
+        BarcodeAssignmentStage st(samples_of({"AAAAAAAA", "ACGTACGT"}, true), k, 1, 1, 1, 1);
+        DemuxedGroup g = st.demultiplex({"AAAAAAAA", "AAAATAAA", "ACAAATAA"});
+        EXPECT(g.sample_indices[0] == 0 && g.sample_indices[1] == 0 && g.sample_indices[2] == 2);
+        DemuxedGroupMetrics m = st.metrics();
+        EXPECT(m.per_sample_metrics[0].total_matches == 2 && m.per_sample_metrics[1].total_matches == 0 &&
+               m.per_sample_metrics[2].total_matches == 1);
+    }
+    EXPECT(select_matcher(8) == MatcherKind::PreCompute && select_matcher(17) == MatcherKind::CachedHammingDistance);
+    EXPECT(select_matcher(17, MatcherKind::PreCompute) == MatcherKind::PreCompute);
+    EXPECT(select_matcher(8, MatcherKind::CachedHammingDistance) == MatcherKind::PreCompute);  // run.rs:196
+}
+
+static void test_dual_index_metrics() {
+    {   // run.rs:1382-1451: TTT+GGG, CCC+AAA; observed TTT+AAA hops
+        BarcodeAssignmentStage st(samples_of({"TTTGGG", "CCCAAA"}, true), select_matcher(6), 2, 1, 1, 1,
+                                  std::make_pair<size_t, size_t>(3, 3));
+        EXPECT(st.demultiplex({"TTTAAA"}).sample_indices[0] == 2);
+        DemuxedGroupMetrics m = st.metrics();
+        EXPECT(m.sample_barcode_hop_tracker && m.sample_barcode_hop_tracker->count_tracker.size() == 1 &&
+               m.sample_barcode_hop_tracker->count_tracker["TTTAAA"] == 1);
+    }
+    {   // run.rs:1455-1535: TTT+AAA is a sample
+        BarcodeAssignmentStage st(samples_of({"TTTAAA", "CCCGGG"}, true), select_matcher(6), 2, 1, 1, 1,
+                                  std::make_pair<size_t, size_t>(3, 3));
+        EXPECT(st.demultiplex({"TTTAAA"}).sample_indices[0] == 0);
+        DemuxedGroupMetrics m = st.metrics();
+        EXPECT(m.per_sample_metrics[0].total_matches == 1 && m.sample_barcode_hop_tracker->count_tracker.empty());
+    }
+    {   // run.rs:1539-1605: single index, no match, no hop tracker
+        BarcodeAssignmentStage st(samples_of({"CCC"}, true), select_matcher(3), 2, 1, 1, 1);
+        EXPECT(st.demultiplex({"TTT"}).sample_indices[0] == 1);
+        DemuxedGroupMetrics m = st.metrics();
+        EXPECT(m.per_sample_metrics[1].total_matches == 1 && !m.sample_barcode_hop_tracker);
+    }
+}
+
+static void test_metrics_merge_and_errors() {
+    // metrics.rs:315-328: merging is a plain sum -> two stages over halves equal one stage over everything
+    std::vector<std::string> reads = {"AAAAAAAAGATTACAGA", "AAAAAAAAGATTACAGT", "CCCCCCCCGATTACAGA", "GGGGGGTCGATTACAGA"};
+    BarcodeAssignmentStage whole(samples_of(kFour, true), MatcherKind::CachedHammingDistance, 2, 1, 1, 1);
+    whole.demultiplex(reads);
+    BarcodeAssignmentStage a(samples_of(kFour, true), MatcherKind::CachedHammingDistance, 2, 1, 1, 1);
+    BarcodeAssignmentStage b(samples_of(kFour, true), MatcherKind::CachedHammingDistance, 2, 1, 1, 1);
+    a.demultiplex({reads[0], reads[1]});
+    b.demultiplex({reads[2], reads[3]});
+    DemuxedGroupMetrics m = a.metrics(), w = whole.metrics();
+    m.update_with(b.metrics());
+    EXPECT(m.total_templates == w.total_templates);
+    for (size_t i = 0; i < w.per_sample_metrics.size(); i++)
+        EXPECT(m.per_sample_metrics[i].total_matches == w.per_sample_metrics[i].total_matches &&
+               m.per_sample_metrics[i].perfect_matches == w.per_sample_metrics[i].perfect_matches);
+    bool threw = false;
+    try {
+        GpuMatcher bad(samples_of({"ACGN"}, false), MatcherKind::CachedHammingDistance, 1, 1, 1);  // N in a sample barcode
+    } catch (const Error &e) {
+        threw = e.code == SGDX_EINVAL;
+    }
+    EXPECT(threw);
+}
+
+int main() {
+    try {
+        test_find_two_samples();
+        test_readme_examples();
+        test_demux_known_answers();
+        test_end_to_end_simple();
+        test_end_to_end_with_all_matchers();
+        test_dual_index_metrics();
+        test_metrics_merge_and_errors();
+    } catch (const Error &e) {  // e.g. no CUDA device: there is no CPU fallback to run these on
+        std::fprintf(stderr, "sgdx::Error (code %d): %s\n", e.code, e.what());
+        return 2;
+    }
+    if (failures) {
+        std::fprintf(stderr, "%d expectation(s) failed\n", failures);
+        return 1;
+    }
+    std::puts("host mirror: all reference known answers reproduced");
+    return 0;
+}

@@ -120,3 +120,18 @@ def test_unmatched_counter_downsizes_like_the_reference():
     c.insert_counts(keys, np.array([5, 1, 4, 1, 1]))
     assert len(c.counts) <= 4 and c.counts[b"AAA"] == 5 and c.counts[b"GGG"] == 4
     assert c.most_frequent(1)[0] == sg.BarcodeCount("AAA", 5)
+
+
+def test_cpp_host_mirror_builds_and_refuses_to_run_without_a_gpu():
+    """The compiled-language host side (C++ mirror of the reference's interface) builds against the C ABI; on a
+    box without a CUDA device it must fail loudly (there is no CPU fallback), not pretend to pass."""
+    import subprocess
+    import torch
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.run(["make", "-C", os.path.join(root, "tests", "cpp")], check=True, capture_output=True)
+    exe = os.path.join(root, "tests", "cpp", "test_host_mirror")
+    assert os.path.exists(exe)
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: the gpu-marked test runs the program")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 2 and "no CPU fallback" in r.stderr

@@ -402,6 +402,19 @@ def test_two_devices_merge_to_single_pass():
     assert merged.sample_barcode_hop_tracker.count_tracker == want["hops"]
 
 
+def test_cpp_host_mirror_known_answers():
+    """The reference's known-answer tests written against the C++ host mirror (tests/cpp/test_host_mirror.cpp,
+    singular-demux_b200/host/sgdx_host.hpp), run as a compiled program against libsgdx.so."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "tests", "cpp", "test_host_mirror")
+    if not os.path.exists(exe):
+        subprocess.run(["make", "-C", os.path.join(root, "tests", "cpp")], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "all reference known answers reproduced" in r.stdout
+
+
 def test_batcher_returns_batches_in_order():
     from singular_demux_b200._lib import check, lib
     rng = np.random.default_rng(3)
