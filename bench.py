@@ -146,7 +146,7 @@ def main():
     if args.impl == "reference":
         return reference_arm(args)
 
-    os.environ["NCCL_DEBUG"] = os.environ.get("SGDX_NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # NCCL's version/debug lines must not share stdout with the JSON line
     import numpy as np
     import torch
     import torch.distributed as dist
