@@ -146,7 +146,10 @@ def main():
     if args.impl == "reference":
         return reference_arm(args)
 
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # NCCL's version/debug lines must not share stdout with the JSON line
+    # rank 0 prints exactly one line on stdout; whatever libraries print (NCCL's version banner, ...) goes to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -332,7 +335,7 @@ def main():
             "roofline": roofline, "cpu_baseline": cb, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": clocks, "matched_fraction": matched_frac,
         }
-        print(json.dumps(out))
+        os.write(json_fd, (json.dumps(out) + "\n").encode())
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
