@@ -271,32 +271,9 @@ static int build_exact_table(sgdx_handle *h, const uint8_t *barcodes, const std:
     return SGDX_OK;
 }
 
-extern "C" int sgdx_create(const sgdx_config *cfg, const uint8_t *barcodes, sgdx_handle **out) {
-    if (!cfg || !barcodes || !out) return fail(SGDX_EINVAL, "sgdx_create: null argument");
-    *out = nullptr;
+// everything sgdx_create does once the arguments are validated; on failure the caller destroys the handle
+static int fill_handle(sgdx_handle *h, const sgdx_config *cfg, const uint8_t *barcodes) {
     const uint32_t S = cfg->num_samples, L = cfg->barcode_len;
-    if (S < 1 || S > SGDX_MAX_SAMPLES) return fail(SGDX_EINVAL, "num_samples %u outside 1..%u", S, SGDX_MAX_SAMPLES);
-    if (L < 1 || L > SGDX_MAX_BARCODE_LEN)
-        return fail(SGDX_EINVAL, "barcode_len %u outside 1..%u", L, SGDX_MAX_BARCODE_LEN);
-    if (cfg->matcher > SGDX_MATCHER_PRECOMPUTE) return fail(SGDX_EINVAL, "unknown matcher kind %u", cfg->matcher);
-    if (cfg->kernel > SGDX_KERNEL_SEEDED) return fail(SGDX_EINVAL, "unknown kernel kind %u", cfg->kernel);
-    if ((cfg->index1_len == 0) != (cfg->index2_len == 0) ||
-        (cfg->index1_len && cfg->index1_len + cfg->index2_len != L))
-        return fail(SGDX_EINVAL, "index1_len + index2_len must equal barcode_len (or both be 0)");
-    for (uint64_t i = 0; i < (uint64_t)S * L; i++) {
-        uint8_t c = barcodes[i];
-        if (c != 'A' && c != 'C' && c != 'G' && c != 'T')
-            return fail(SGDX_EINVAL, "expected barcode %llu has byte 0x%02x at %llu (must be upper-case ACGT)",
-                        (unsigned long long)(i / L), c, (unsigned long long)(i % L));
-    }
-    int ndev = 0;
-    cudaError_t ce = cudaGetDeviceCount(&ndev);
-    if (ce != cudaSuccess || ndev == 0)
-        return fail(SGDX_ECUDA, "no CUDA device available (%s); sgdx has no CPU fallback", cudaGetErrorString(ce));
-    if (cfg->device < 0 || cfg->device >= ndev) return fail(SGDX_EINVAL, "device %d not in 0..%d", cfg->device, ndev - 1);
-    CU(cudaSetDevice(cfg->device));
-
-    sgdx_handle *h = new sgdx_handle();
     h->cfg = *cfg;
     if (h->cfg.matcher == SGDX_MATCHER_AUTO)  // run.rs:196-198
         h->cfg.matcher = L <= 12 ? SGDX_MATCHER_PRECOMPUTE : SGDX_MATCHER_CACHED_HAMMING;
@@ -375,8 +352,8 @@ extern "C" int sgdx_create(const sgdx_config *cfg, const uint8_t *barcodes, sgdx
                 CU(cudaMemcpy(*d_out, lut.data(), lut.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
                 return SGDX_OK;
             };
-            if (int rc = build_lut(h->keys1, p.i1, &h->d_hop_lut1)) { sgdx_destroy(h); return rc; }
-            if (int rc = build_lut(h->keys2, p.i2, &h->d_hop_lut2)) { sgdx_destroy(h); return rc; }
+            if (int rc = build_lut(h->keys1, p.i1, &h->d_hop_lut1)) return rc;
+            if (int rc = build_lut(h->keys2, p.i2, &h->d_hop_lut2)) return rc;
             p.hop_lut1 = h->d_hop_lut1;
             p.hop_lut2 = h->d_hop_lut2;
             p.hop_direct = 1;
@@ -397,7 +374,6 @@ extern "C" int sgdx_create(const sgdx_config *cfg, const uint8_t *barcodes, sgdx
         bool have = false;
         if (h->cfg.kernel != SGDX_KERNEL_DIRECT) {
             if (int rc = build_seed_index(h, table, &have, &est)) {
-                sgdx_destroy(h);
                 return rc;
             }
         }
@@ -405,7 +381,6 @@ extern "C" int sgdx_create(const sgdx_config *cfg, const uint8_t *barcodes, sgdx
         else h->seeded = have && h->cfg.kernel == SGDX_KERNEL_SEEDED;
         if (h->seeded)
             if (int rc = build_exact_table(h, barcodes, table, est)) {
-                sgdx_destroy(h);
                 return rc;
             }
         h->cfg.kernel = h->seeded ? SGDX_KERNEL_SEEDED : SGDX_KERNEL_DIRECT;
@@ -421,6 +396,42 @@ extern "C" int sgdx_create(const sgdx_config *cfg, const uint8_t *barcodes, sgdx
     // table uploads and memsets above ran on the legacy default stream; the slots' streams are non-blocking and
     // do not order against it, so make everything resident before the first batch can be queued
     CU(cudaDeviceSynchronize());
+    return SGDX_OK;
+}
+
+
+extern "C" int sgdx_create(const sgdx_config *cfg, const uint8_t *barcodes, sgdx_handle **out) {
+    if (!cfg || !barcodes || !out) return fail(SGDX_EINVAL, "sgdx_create: null argument");
+    *out = nullptr;
+    const uint32_t S = cfg->num_samples, L = cfg->barcode_len;
+    if (S < 1 || S > SGDX_MAX_SAMPLES) return fail(SGDX_EINVAL, "num_samples %u outside 1..%u", S, SGDX_MAX_SAMPLES);
+    if (L < 1 || L > SGDX_MAX_BARCODE_LEN)
+        return fail(SGDX_EINVAL, "barcode_len %u outside 1..%u", L, SGDX_MAX_BARCODE_LEN);
+    if (cfg->matcher > SGDX_MATCHER_PRECOMPUTE) return fail(SGDX_EINVAL, "unknown matcher kind %u", cfg->matcher);
+    if (cfg->kernel > SGDX_KERNEL_SEEDED) return fail(SGDX_EINVAL, "unknown kernel kind %u", cfg->kernel);
+    if ((cfg->index1_len == 0) != (cfg->index2_len == 0) ||
+        (cfg->index1_len && cfg->index1_len + cfg->index2_len != L))
+        return fail(SGDX_EINVAL, "index1_len + index2_len must equal barcode_len (or both be 0)");
+    for (uint64_t i = 0; i < (uint64_t)S * L; i++) {
+        uint8_t c = barcodes[i];
+        if (c != 'A' && c != 'C' && c != 'G' && c != 'T')
+            return fail(SGDX_EINVAL, "expected barcode %llu has byte 0x%02x at %llu (must be upper-case ACGT)",
+                        (unsigned long long)(i / L), c, (unsigned long long)(i % L));
+    }
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0)
+        return fail(SGDX_ECUDA, "no CUDA device available (%s); sgdx has no CPU fallback", cudaGetErrorString(ce));
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(SGDX_EINVAL, "device %d not in 0..%d", cfg->device, ndev - 1);
+    CU(cudaSetDevice(cfg->device));
+
+    sgdx_handle *h = new sgdx_handle();
+    if (int rc = fill_handle(h, cfg, barcodes)) {
+        std::string msg = g_err;  // sgdx_destroy makes CUDA calls of its own
+        sgdx_destroy(h);
+        g_err = msg;
+        return rc;
+    }
     *out = h;
     return SGDX_OK;
 }
