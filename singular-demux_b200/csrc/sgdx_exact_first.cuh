@@ -344,16 +344,23 @@ __global__ void __launch_bounds__(THREADS, THREADS == 512u ? 3 : 1) sgdx_match_e
                     atomicAdd(&sm.hist[hit[k] * 3u + 1u], 1u);  // perfect match (ATOMS.POPC.INC: aggregated in hardware)
                 }
             }
-            {   // misses -> Q1, one slot reservation per thread for all of its reads
-                uint32_t nmiss = 0u;
+            {   // misses -> Q1: one reservation per warp (every lane adding to the same shared counter costs one
+                // wavefront per lane); the lanes take their slots from the ballots
+                uint32_t votes[R], total = 0u;
 #pragma unroll
-                for (uint32_t k = 0; k < R; k++) nmiss += (hit[k] == kNone && k * T + threadIdx.x < nvalid) ? 1u : 0u;
-                if (nmiss) {
-                    uint32_t slot = n1 + atomicAdd(&sm.ring[phase % 3u], nmiss);
+                for (uint32_t k = 0; k < R; k++) {
+                    votes[k] = __ballot_sync(0xFFFFFFFFu, hit[k] == kNone && k * T + threadIdx.x < nvalid);
+                    total += (uint32_t)__popc(votes[k]);
+                }
+                uint32_t slot = 0u;
+                if (lane == 0u && total) slot = atomicAdd(&sm.ring[phase % 3u], total);
+                slot = __shfl_sync(0xFFFFFFFFu, slot, 0) + n1;
+                const uint32_t below = (1u << lane) - 1u;
 #pragma unroll
-                    for (uint32_t k = 0; k < R; k++)
-                        if (hit[k] == kNone && k * T + threadIdx.x < nvalid)
-                            sm.q1[slot++] = iter * (T * R) + k * T + threadIdx.x;
+                for (uint32_t k = 0; k < R; k++) {
+                    if ((votes[k] >> lane) & 1u)
+                        sm.q1[slot + (uint32_t)__popc(votes[k] & below)] = iter * (T * R) + k * T + threadIdx.x;
+                    slot += (uint32_t)__popc(votes[k]);
                 }
             }
             n1 += end_phase();
