@@ -117,19 +117,19 @@ __device__ __forceinline__ uint32_t gather4(uint32_t x) {
     return (x * 0x01020408u) >> 24;  // (1<<24)+(1<<17)+(1<<10)+(1<<3): partial products never collide
 }
 
-// fold 4 ASCII bases (byte k = base j+k) into the planes
+// fold 4 ASCII bases (byte k = base j+k) into the planes.  code = (ascii >> 1) & 3; a byte is a valid base iff it
+// equals "ACTG"[code] (PRMT lookup of the four codes of the word); no-calls are found by an exact byte compare.
 __device__ __forceinline__ void fold_word(uint32_t w, uint32_t j, Rd &r) {
-    const uint32_t ones = 0x01010101u;
-    uint32_t nflag = zero_bytes(w ^ 0x4E4E4E4Eu) >> 7;                          // 'N'
-    uint32_t aceg = zero_bytes((w & 0xF9F9F9F9u) ^ 0x41414141u);                // A C E G
-    uint32_t e = zero_bytes(w ^ 0x45454545u);                                   // E
-    uint32_t t = zero_bytes(w ^ 0x54545454u);                                   // T
-    uint32_t ok = ((aceg & ~e) | t) >> 7;
-    uint32_t x = ~(ok | nflag) & ones;
-    r.lo |= gather4((w >> 1) & ones) << j;
-    r.hi |= gather4((w >> 2) & ones) << j;
-    r.nmask |= gather4(nflag) << j;
-    r.xmask |= gather4(x) << j;
+    const uint32_t c = (w >> 1) & 0x03030303u;
+    const uint32_t y = c | (c >> 4);                                     // byte 0: c0 | c1 << 4, byte 2: c2 | c3 << 4
+    const uint32_t x = w ^ __byte_perm(0x47544341u, 0u, __byte_perm(y, 0u, 0x4420));  // non-zero byte <=> not A/C/G/T
+    const uint32_t bad = ((((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x) >> 7) & 0x01010101u;
+    const uint32_t nflag = zero_bytes(w ^ 0x4E4E4E4Eu) >> 7;             // 'N'
+    const uint32_t nn = gather4(nflag);
+    r.lo |= (((c & 0x01010101u) * 0x01020408u) >> 24) << j;
+    r.hi |= (((c & 0x02020202u) * 0x00810204u) >> 24) << j;
+    r.nmask |= nn << j;
+    r.xmask |= (gather4(bad) & ~nn) << j;
 }
 
 // Load read r (L ASCII bytes) and convert. words_ok: base pointer 4-byte aligned and L % 4 == 0.
@@ -250,19 +250,17 @@ __device__ __forceinline__ void hop_check(const DevParams &p, const Rd &rd) {
     atomicAdd(&p.hop_rev[(uint64_t)c * p.u2 + d], 1ull);
 }
 
-// store the verdict, bump the block-private histogram (warp-aggregated), run the hop check
+// store the verdict, bump the block-private histogram, run the hop check.  A plain shared-memory atomicAdd of 1
+// compiles to ATOMS.POPC.INC, which combines the lanes that hit the same bin in hardware.
 __device__ __forceinline__ void emit(const DevParams &p, uint64_t r, bool active, const Rd &rd, const Verdict &v,
                                      uint32_t *hist) {
-    uint32_t key = 0xFFFFFFFFu;
     if (active) {
         p.out_idx[r] = (uint16_t)v.bin;
         if (p.out_dist) p.out_dist[r] = (uint8_t)v.dist;
-        uint32_t cls = v.dist == 0u ? 1u : (v.dist == 1u ? 2u : 0u);  // metrics.rs:428-437
-        key = v.bin * 3u + cls;
+        const uint32_t cls = v.dist == 0u ? 1u : (v.dist == 1u ? 2u : 0u);  // metrics.rs:428-437
+        atomicAdd(&hist[v.bin * 3u + cls], 1u);
+        if (p.hop_on && v.bin == p.S) hop_check(p, rd);
     }
-    uint32_t peers = __match_any_sync(0xFFFFFFFFu, key);
-    if (active && (uint32_t)(__ffs(peers) - 1) == (threadIdx.x & 31u)) atomicAdd(&hist[key], (uint32_t)__popc(peers));
-    if (active && p.hop_on && v.bin == p.S) hop_check(p, rd);
 }
 
 }  // namespace sgdx
