@@ -529,3 +529,35 @@ def test_full_size_properties_c2():
     k = 1_000_000
     want = _oracle(table, sg.MatcherKind.CachedHammingDistance, 1, 2, 1, None, w.index_lengths, w.reads_host(0, k, table))
     assert np.array_equal(outs[0][0][:k], want["idx"]) and np.array_equal(outs[0][1][:k], want["dist"])
+
+
+def test_batch_larger_than_4_gib_of_barcodes():
+    """One 250 M-read C2 batch = 5 GB of ASCII barcodes: byte offsets need 64 bits.  Conservation, bincount of
+    the index array == counters, and the first and the last million reads against the oracle."""
+    import torch
+    w = sg.synth.C2
+    n = 250_000_000
+    table = w.table()
+    d_table = torch.from_numpy(table).cuda()
+    d_in = torch.empty((n, w.barcode_len), dtype=torch.uint8, device="cuda")
+    w.reads_device(0, n, d_table.data_ptr(), d_in.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    st = _stage(table, sg.MatcherKind.CachedHammingDistance, 1, 2, 1, None, w.index_lengths, sg.KERNEL_AUTO)
+    d_idx = torch.empty(n, dtype=torch.int16, device="cuda")
+    d_dist = torch.empty(n, dtype=torch.uint8, device="cuda")
+    st.matcher.match_device(d_in.data_ptr(), n, d_idx.data_ptr(), d_dist.data_ptr())
+    st.matcher.sync(0)
+    m = st.metrics()
+    per = m.per_sample_array()
+    assert m.total_templates == n == int(per[:, 0].sum())
+    hist = torch.zeros(w.num_samples + 1, dtype=torch.int64, device="cuda")
+    for a in range(0, n, 50_000_000):  # bincount in slices: the int64 copy of the whole array would be 2 GB
+        hist += torch.bincount(d_idx[a:a + 50_000_000].to(torch.int64) & 0xFFFF, minlength=w.num_samples + 1)
+    assert np.array_equal(hist.cpu().numpy().astype(np.uint64), per[:, 0])
+    k = 1_000_000
+    for first in (0, n - k):
+        want = _oracle(table, sg.MatcherKind.CachedHammingDistance, 1, 2, 1, None, w.index_lengths,
+                       w.reads_host(first, k, table))
+        assert np.array_equal(d_idx[first:first + k].cpu().numpy().view(np.uint16), want["idx"])
+        assert np.array_equal(d_dist[first:first + k].cpu().numpy(), want["dist"])
+    st.close()
