@@ -156,6 +156,85 @@ int sgdx_batcher_flush(sgdx_batcher *b);
  * sgdx_batcher_next/destroy.  *n == 0 when nothing is pending. */
 int sgdx_batcher_next(sgdx_batcher *b, const uint16_t **idx, const uint8_t **dist, uint64_t *n);
 
+/* ==== the stages either side of the assignment; all device work, no CPU fallback ==== */
+
+/* ---- 1. most-frequent unmatched barcodes on the device.
+ * Replaces UnmatchedCounter (metrics.rs:131-190) and the counter thread it is fed through
+ * (metrics.rs:79-100, demux.rs:553-555, run.rs:185-190,262-268): after sgdx_unmatched_enable every batch
+ * also counts the concatenated barcode of each NoMatch read in a device hash table (3 bits per base, 128-bit
+ * compare-and-swap; barcodes with a byte outside ACGTN go to a side list and are counted on the host).
+ * Keys are the concatenated observed barcodes; the host writes them in their delimited form
+ * (demux.rs:504-522).  Down-sizing follows the reference's heuristic (metrics.rs:151-175) at batch
+ * granularity: when the number of distinct keys has reached max_map_size at a sgdx_sync, the table is cut to
+ * its downsize_to most frequent keys.  Below max_map_size distinct keys the counts are exact.  Needs ASCII input. */
+typedef struct sgdx_unmatched_info {
+    uint64_t distinct_keys;     /* keys in the table now (incl. foreign-byte barcodes) */
+    uint64_t unmatched_reads;   /* NoMatch reads seen since enable/reset */
+    uint64_t dropped_reads;     /* reads not counted because the table (or the foreign-byte list) was full */
+    uint64_t downsizes;         /* how many times the table was cut down */
+} sgdx_unmatched_info;
+int sgdx_unmatched_enable(sgdx_handle *h, uint64_t max_map_size /* 0 -> 5,000,000 (opts.rs:185) */,
+                          uint64_t downsize_to /* 0 -> 5,000 (opts.rs:189) */);
+int sgdx_unmatched_info_get(sgdx_handle *h, sgdx_unmatched_info *out);
+/* every (key, count) pair, unspecified order; keys = cap*L bytes.  For merging shards on the host. */
+int sgdx_unmatched_export(sgdx_handle *h, uint8_t *keys, uint64_t *counts, uint64_t cap, uint64_t *n_written);
+/* the n most frequent keys, descending count (to_file, metrics.rs:177-190; ties in byte order here, hash
+ * order in the reference).  The count threshold is found from a device-side histogram, so only the selected
+ * keys cross PCIe. */
+int sgdx_unmatched_top(sgdx_handle *h, uint64_t n, uint8_t *keys /* n*L */, uint64_t *counts /* n */,
+                       uint64_t *n_written);
+int sgdx_unmatched_downsize(sgdx_handle *h);   /* UnmatchedCounter::downsize now (metrics.rs:166-175) */
+
+/* ---- 2. sample-barcode extraction on the device.
+ * Replaces the sample-barcode part of Demultiplexer::process_segments / demultiplex (demux.rs:360-417,
+ * 504-522): the B segments of each FASTQ's read, in FASTQ order then segment order, concatenated into the
+ * L-byte barcode.  Sources are fixed-stride matrices of bases, one per FASTQ (row r = read r). */
+#define SGDX_SEG_TEMPLATE 'T'
+#define SGDX_SEG_SAMPLE_BARCODE 'B'
+#define SGDX_SEG_MOLECULAR_BARCODE 'M'
+#define SGDX_SEG_SKIP 'S'
+#define SGDX_SEG_TO_END 0xFFFFFFFFu
+typedef struct sgdx_segment {      /* read_structure::ReadSegment as used at demux.rs:380-387 */
+    uint32_t source;               /* which FASTQ (index into the source arrays); ignored by single-source calls */
+    uint32_t offset;               /* first base of the segment in the read */
+    uint32_t length;               /* bases, or SGDX_SEG_TO_END for the trailing `+` segment */
+    uint32_t kind;                 /* SGDX_SEG_* */
+} sgdx_segment;
+#define SGDX_MAX_SOURCES 8u
+#define SGDX_MAX_SEGMENTS 32u
+int sgdx_extract_device(sgdx_handle *h, uint32_t slot, uint32_t num_sources, const uint8_t *const *d_bases,
+                        const uint32_t *strides, const sgdx_segment *segments, uint32_t num_segments, uint64_t n,
+                        uint8_t *d_barcodes_out /* n*L */);
+/* extraction into the slot's scratch + sgdx_match_device in one call */
+int sgdx_match_segments_device(sgdx_handle *h, uint32_t slot, uint32_t num_sources, const uint8_t *const *d_bases,
+                               const uint32_t *strides, const sgdx_segment *segments, uint32_t num_segments,
+                               uint64_t n, uint16_t *d_out_idx, uint8_t *d_out_dist);
+
+/* ---- 3. base-quality counters per assigned sample.
+ * Replaces BaseQualCounter::update (metrics.rs:499-518) over every segment of one FASTQ and the per-sample
+ * merge at demux.rs:582-583: for read r with sample index d_idx[r], template (T) bases add to bases / q20 /
+ * q30, sample-barcode (B) bases add to index_bases_total_seen / index_bases_qual_sum.  q = byte - 33 in u8
+ * arithmetic (a byte below 33 wraps, as in a release build of the reference).  d_quals is a fixed-stride
+ * matrix (row r = quality string of read r, 16-byte aligned base); d_lens (nullable) gives each read's
+ * length <= stride, which a trailing SGDX_SEG_TO_END segment follows.  A read shorter than its fixed
+ * segments (the reference fails on it, demux.rs:380-387) adds nothing and is counted in short_reads.
+ * Call once per FASTQ of the batch. */
+typedef struct sgdx_base_qual {    /* BaseQualCounter, metrics.rs:468-481 */
+    uint64_t q20_bases, q30_bases, index_bases_qual_sum, index_bases_total_seen, bases;
+} sgdx_base_qual;
+int sgdx_qual_counts_device(sgdx_handle *h, uint32_t slot, const uint8_t *d_quals, uint64_t n, uint32_t stride,
+                            const uint32_t *d_lens, const sgdx_segment *segments, uint32_t num_segments,
+                            const uint16_t *d_idx);
+int sgdx_base_qual_counters(sgdx_handle *h, sgdx_base_qual *per_sample /* S+1, Undetermined last */,
+                            uint64_t *short_reads /* nullable */);
+
+/* ---- 4. read routing: a stable partition of the read ids by sample index, so that the host writer
+ * (run.rs:254-261, pooled_sample_writer.rs:25-40) receives one contiguous, input-ordered run per sample
+ * (what DemuxedGroup::per_sample_reads holds, demux.rs:637-645).  d_order[offsets[s] .. offsets[s+1]) are the
+ * ids of sample s's reads in input order; offsets has S+2 entries, offsets[S+1] = n.  n < 2^32. */
+int sgdx_route_device(sgdx_handle *h, uint32_t slot, const uint16_t *d_idx, uint64_t n, uint32_t *d_order,
+                      uint64_t *d_offsets /* S+2 */);
+
 /* ---- measurement support */
 /* Integer-pipe micro-benchmark on `device`: sustained 32-bit POPC and LOP3 results per second. */
 int sgdx_measure_int_peak(int device, double *popc_per_s, double *lop3_per_s);

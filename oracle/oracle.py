@@ -345,3 +345,78 @@ def unmatched_counts(reads: np.ndarray, idx: np.ndarray, undetermined: int) -> D
         return {}
     u, c = np.unique(sel, axis=0, return_counts=True)
     return {u[i].tobytes(): int(c[i]) for i in range(u.shape[0])}
+
+
+# ------------------------------------------------------------------------------------------------
+# The stages either side of the assignment, restated with numpy / plain Python.
+# TEST INFRASTRUCTURE ONLY, like the rest of this file.
+# ------------------------------------------------------------------------------------------------
+class UnmatchedCounterLiteral:
+    """metrics.rs:131-190, literally: insert() down-sizes when the map already holds max_counter_size keys
+    (metrics.rs:151-160), downsize() keeps the downsize_to most frequent (166-175; ties in hash order in the
+    reference, in byte order here), to_file() writes the n most frequent in descending count (177-190)."""
+
+    def __init__(self, max_counter_size: int = 5_000_000, downsize_to: int = 5_000):
+        self.unmatched_counter: Dict[bytes, int] = {}
+        self.max_counter_size, self.downsize_to = max_counter_size, downsize_to
+
+    def insert(self, barcode: bytes) -> None:
+        if len(self.unmatched_counter) == self.max_counter_size:
+            self.downsize()
+        self.unmatched_counter[barcode] = self.unmatched_counter.get(barcode, 0) + 1
+
+    def downsize(self) -> None:
+        top = sorted(self.unmatched_counter.items(), key=lambda kv: (-kv[1], kv[0]))[:self.downsize_to]
+        self.unmatched_counter = dict(top)
+
+    def top(self, n: int):
+        return sorted(self.unmatched_counter.items(), key=lambda kv: (-kv[1], kv[0]))[:n]
+
+
+def extract_sample_barcodes(sources: Sequence[np.ndarray], structures) -> np.ndarray:
+    """demux.rs:360-417 + 504-522: the B segments of every FASTQ's read, FASTQ order then segment order,
+    concatenated.  sources[f] = [n, stride_f] bases; structures[f] = list of (offset, length|None, kind)."""
+    parts = []
+    for bases, segs in zip(sources, structures):
+        for (off, length, kind) in segs:
+            if kind == "B":
+                parts.append(bases[:, off:(bases.shape[1] if length is None else off + length)])
+    return np.ascontiguousarray(np.concatenate(parts, axis=1))
+
+
+def base_qual_counts(quals: np.ndarray, lens: Optional[np.ndarray], segments, idx: np.ndarray,
+                     num_samples: int) -> Tuple[np.ndarray, int]:
+    """BaseQualCounter::update (metrics.rs:499-518) for every segment of one FASTQ's reads, summed per assigned
+    sample (demux.rs:582-583).  q = byte - 33 in u8 arithmetic (wraps below 33, as `q - 33` on a u8 does in a
+    release build).  Returns ([(S+1), 5] = q20, q30, index_bases_qual_sum, index_bases_total_seen, bases; number
+    of reads too short for their fixed segments, which add nothing -- the reference fails on those)."""
+    n, stride = quals.shape
+    out = np.zeros((num_samples + 1, 5), dtype=np.uint64)
+    lens = np.full(n, stride, dtype=np.int64) if lens is None else np.minimum(lens.astype(np.int64), stride)
+    need = max([off + (length or 0) for (off, length, kind) in segments] + [0])
+    ok = lens >= need
+    q = (quals.astype(np.uint8) - np.uint8(33)).astype(np.uint8)  # wrapping
+    pos = np.arange(stride)[None, :]
+    bins = idx.astype(np.int64)
+    for (off, length, kind) in segments:
+        end = lens if length is None else np.full(n, off + length, dtype=np.int64)
+        inside = (pos >= off) & (pos < end[:, None]) & ok[:, None]
+        cnt = inside.sum(axis=1)
+        if kind == "B":
+            np.add.at(out[:, 3], bins, cnt.astype(np.uint64))
+            np.add.at(out[:, 2], bins, (q * inside).sum(axis=1, dtype=np.uint64))
+        elif kind == "T":
+            np.add.at(out[:, 4], bins, cnt.astype(np.uint64))
+            np.add.at(out[:, 0], bins, ((q >= 20) & inside).sum(axis=1).astype(np.uint64))
+            np.add.at(out[:, 1], bins, ((q >= 30) & inside).sum(axis=1).astype(np.uint64))
+    return out, int((~ok).sum())
+
+
+def route_reads(idx: np.ndarray, num_samples: int) -> Tuple[np.ndarray, np.ndarray]:
+    """What DemuxedGroup::per_sample_reads holds (demux.rs:578,637-645): the reads of each sample in input
+    order.  Returns (order, offsets): order[offsets[s]:offsets[s+1]] = read ids of sample s; S+2 offsets."""
+    order = np.argsort(idx, kind="stable").astype(np.uint32)
+    counts = np.bincount(idx.astype(np.int64), minlength=num_samples + 1)
+    offsets = np.zeros(num_samples + 2, dtype=np.uint64)
+    offsets[1:] = np.cumsum(counts)
+    return order, offsets

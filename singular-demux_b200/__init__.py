@@ -8,9 +8,10 @@ from ._lib import (KERNEL_AUTO, KERNEL_SEEDED, KERNEL_DIRECT, LIB_PATH, MATCHER_
                    MATCHER_PRECOMPUTE, NO_DIST, SgdxError, lib)
 from .matcher import (UNDETERMINED_NAME, CachedHammingDistanceMatcher, GpuMatcher, MatcherKind, MatchResult,
                       PreComputeMatcher, SampleMetadata, select_matcher)
-from .metrics import (BarcodeCount, DemuxedGroupMetrics, DemuxedGroupSampleMetrics, SampleBarcodeHopTracker,
-                      UnmatchedCounter)
+from .metrics import (BarcodeCount, BaseQualCounter, DemuxedGroupMetrics, DemuxedGroupSampleMetrics,
+                      SampleBarcodeHopTracker, UnmatchedCounter)
+from .read_structure import ReadSegment, ReadStructure
 from .demux import BarcodeAssignmentStage, DemuxedGroup
-from . import sharding, synth
+from . import read_structure, sharding, synth
 
 __all__ = [n for n in dir() if not n.startswith("_")]

@@ -35,6 +35,25 @@ class Totals(C.Structure):
                 ("hop_reads", C.c_uint64)]
 
 
+class UnmatchedInfo(C.Structure):
+    _fields_ = [("distinct_keys", C.c_uint64), ("unmatched_reads", C.c_uint64), ("dropped_reads", C.c_uint64),
+                ("downsizes", C.c_uint64)]
+
+
+class Segment(C.Structure):
+    """sgdx_segment: one read-structure segment of one FASTQ."""
+    _fields_ = [("source", C.c_uint32), ("offset", C.c_uint32), ("length", C.c_uint32), ("kind", C.c_uint32)]
+
+
+class BaseQual(C.Structure):
+    _fields_ = [("q20_bases", C.c_uint64), ("q30_bases", C.c_uint64), ("index_bases_qual_sum", C.c_uint64),
+                ("index_bases_total_seen", C.c_uint64), ("bases", C.c_uint64)]
+
+
+SEG_TO_END = 0xFFFFFFFF
+MAX_SOURCES, MAX_SEGMENTS = 8, 32
+
+
 class SynthParams(C.Structure):
     _fields_ = [("seed", C.c_uint64), ("num_samples", C.c_uint32), ("barcode_len", C.c_uint32),
                 ("index1_len", C.c_uint32), ("zipf", C.c_uint32), ("p_true", C.c_uint32), ("p_hop", C.c_uint32),
@@ -48,6 +67,9 @@ SYMBOLS = [
     "sgdx_match_packed_device", "sgdx_set_stream", "sgdx_kernel_name", "sgdx_path_flags", "sgdx_launch_count", "sgdx_counters", "sgdx_reset_counters",
     "sgdx_hop_count", "sgdx_hop_export", "sgdx_batcher_create", "sgdx_batcher_destroy", "sgdx_batcher_push",
     "sgdx_batcher_flush", "sgdx_batcher_next", "sgdx_measure_int_peak",
+    "sgdx_unmatched_enable", "sgdx_unmatched_info_get", "sgdx_unmatched_export", "sgdx_unmatched_top",
+    "sgdx_unmatched_downsize", "sgdx_extract_device", "sgdx_match_segments_device", "sgdx_qual_counts_device",
+    "sgdx_base_qual_counters", "sgdx_route_device",
     "sgdx_synth_table", "sgdx_synth_reads_host", "sgdx_synth_reads_device",
 ]
 
@@ -93,6 +115,17 @@ def lib() -> C.CDLL:
     L.sgdx_batcher_push.argtypes = [vp, vp, u64]
     L.sgdx_batcher_flush.argtypes = [vp]
     L.sgdx_batcher_next.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(u64)]
+    L.sgdx_unmatched_enable.argtypes = [vp, u64, u64]
+    L.sgdx_unmatched_info_get.argtypes = [vp, C.POINTER(UnmatchedInfo)]
+    L.sgdx_unmatched_export.argtypes = [vp, vp, vp, u64, C.POINTER(u64)]
+    L.sgdx_unmatched_top.argtypes = [vp, u64, vp, vp, C.POINTER(u64)]
+    L.sgdx_unmatched_downsize.argtypes = [vp]
+    L.sgdx_extract_device.argtypes = [vp, u32, u32, C.POINTER(vp), C.POINTER(u32), C.POINTER(Segment), u32, u64, vp]
+    L.sgdx_match_segments_device.argtypes = [vp, u32, u32, C.POINTER(vp), C.POINTER(u32), C.POINTER(Segment), u32,
+                                             u64, vp, vp]
+    L.sgdx_qual_counts_device.argtypes = [vp, u32, vp, u64, u32, vp, C.POINTER(Segment), u32, vp]
+    L.sgdx_base_qual_counters.argtypes = [vp, C.POINTER(BaseQual), C.POINTER(u64)]
+    L.sgdx_route_device.argtypes = [vp, u32, vp, u64, vp, vp]
     L.sgdx_measure_int_peak.argtypes = [i32, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.sgdx_synth_table.argtypes = [u64, u32, u32, u32, u32, vp]
     L.sgdx_synth_reads_host.argtypes = [C.POINTER(SynthParams), vp, u64, u64, vp, i32]

@@ -12,14 +12,13 @@
 #include <string>
 #include <vector>
 
-#include "../../include/sgdx.h"
-#include "sgdx_kernels.h"
+#include "sgdx_handle.h"
 
 using namespace sgdx;
 
-static thread_local std::string g_err;
+thread_local std::string sgdx::g_err;
 
-static int fail(int code, const char *fmt, ...) {
+int sgdx::fail(int code, const char *fmt, ...) {
     char buf[512];
     va_list ap;
     va_start(ap, fmt);
@@ -28,43 +27,6 @@ static int fail(int code, const char *fmt, ...) {
     g_err = buf;
     return code;
 }
-
-#define CU(call)                                                                                           \
-    do {                                                                                                   \
-        cudaError_t e__ = (call);                                                                          \
-        if (e__ != cudaSuccess)                                                                            \
-            return fail(SGDX_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
-    } while (0)
-
-struct Slot {
-    cudaStream_t own = nullptr;
-    cudaStream_t stream = nullptr;  // own or caller-provided
-    cudaEvent_t e0 = nullptr, e1 = nullptr;
-    uint8_t *d_in = nullptr;
-    uint16_t *d_idx = nullptr;
-    uint8_t *d_dist = nullptr;
-    uint64_t cap = 0;  // reads
-    bool timed = false;
-};
-
-struct sgdx_handle {
-    sgdx_config cfg;  // effective (AUTO resolved)
-    uint32_t mode = kModeHamming;
-    int sms = 148;
-    DevParams base{};  // everything but the per-batch pointers
-    uint2 *d_table = nullptr;
-    uint16_t *d_seed_hdr = nullptr;
-    uint16_t *d_seed_ids = nullptr;
-    uint32_t *d_ex_slots = nullptr, *d_ex_ascii = nullptr, *d_nb_slots = nullptr;
-    bool seeded = false;  // launches use sgdx_match_seeded
-    HopSlot *d_hash1 = nullptr, *d_hash2 = nullptr;
-    uint16_t *d_hop_lut1 = nullptr, *d_hop_lut2 = nullptr;
-    unsigned long long *d_hop_fwd = nullptr, *d_hop_rev = nullptr;
-    unsigned long long *d_counters = nullptr;
-    std::vector<std::string> keys1, keys2;  // distinct index1 / index2 halves (ASCII), id order
-    std::vector<Slot> slots;
-    std::atomic<uint64_t> launches{0};
-};
 
 extern "C" const char *sgdx_last_error(void) { return g_err.c_str(); }
 extern "C" const char *sgdx_version(void) { return "sgdx 0.1.0 (sm_100a)"; }
@@ -444,6 +406,9 @@ extern "C" void sgdx_destroy(sgdx_handle *h) {
         cudaFree(s.d_in);
         cudaFree(s.d_idx);
         cudaFree(s.d_dist);
+        cudaFree(s.d_extract);
+        cudaFree(s.d_route);
+        if (s.h_unm_stats) cudaFreeHost(s.h_unm_stats);
         if (s.e0) cudaEventDestroy(s.e0);
         if (s.e1) cudaEventDestroy(s.e1);
         if (s.own) cudaStreamDestroy(s.own);
@@ -461,6 +426,7 @@ extern "C" void sgdx_destroy(sgdx_handle *h) {
     cudaFree(h->d_hop_fwd);
     cudaFree(h->d_hop_rev);
     cudaFree(h->d_counters);
+    post_destroy(h);
     delete h;
 }
 
@@ -494,12 +460,18 @@ static int run_kernels(sgdx_handle *h, Slot &s, const uint8_t *d_ascii, const ui
     p.n = n;
     p.out_idx = d_idx;
     p.out_dist = d_dist;
+    if (h->unm.on && !d_ascii && n)
+        return fail(SGDX_ESTATE, "unmatched collection needs ASCII input (packed records do not keep foreign bytes)");
+    std::unique_lock<std::mutex> lk(h->post_mu, std::defer_lock);
+    if (h->unm.on) lk.lock();  // a downsize of the unmatched table must not overlap a batch
     CU(cudaEventRecord(s.e0, s.stream));
     if (h->seeded) CU(launch_seeded(p, h->mode, d_packed != nullptr, h->sms, s.stream));
     else CU(launch_direct(p, h->mode, d_packed != nullptr, h->sms, s.stream));
+    if (n) h->launches.fetch_add(1);
+    if (h->unm.on && n)
+        if (int rc = post_after_match(h, s, d_ascii, d_idx, n)) return rc;
     CU(cudaEventRecord(s.e1, s.stream));
     s.timed = true;
-    if (n) h->launches.fetch_add(1);
     return SGDX_OK;
 }
 
@@ -575,7 +547,7 @@ extern "C" int sgdx_sync(sgdx_handle *h, uint32_t slot, float *device_ms) {
         *device_ms = 0.f;
         if (s.timed) CU(cudaEventElapsedTime(device_ms, s.e0, s.e1));
     }
-    return SGDX_OK;
+    return post_on_sync(h, s);
 }
 
 extern "C" int sgdx_set_stream(sgdx_handle *h, uint32_t slot, void *stream) {
@@ -649,6 +621,7 @@ extern "C" int sgdx_reset_counters(sgdx_handle *h) {
         CU(cudaMemset(h->d_hop_fwd, 0, cells * sizeof(unsigned long long)));
         CU(cudaMemset(h->d_hop_rev, 0, cells * sizeof(unsigned long long)));
     }
+    if (int rc = post_reset(h)) return rc;
     CU(cudaDeviceSynchronize());  // the memsets are on the default stream, batches on non-blocking ones
     return SGDX_OK;
 }

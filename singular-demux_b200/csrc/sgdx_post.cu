@@ -1,0 +1,1118 @@
+// sgdx_post.cu -- the stages either side of the assignment kernels, hand-written for sm_100a:
+//
+//   unmatched table   UnmatchedCounter (metrics.rs:131-190) as a device hash table: 3 bits per base, 128-bit
+//                     compare-and-swap claims (ATOMG.CAS.128), threshold selection of the top-N from a
+//                     device-side histogram of the counts.
+//   sgdx_extract      sample-barcode segments of every FASTQ's read concatenated into the L-byte barcode
+//                     (demux.rs:360-417,504-522).
+//   sgdx_qual_counts  BaseQualCounter::update (metrics.rs:499-518) keyed by the sample-index array
+//                     (demux.rs:582-583).  HBM-bound: tiles of 128 quality strings arrive in shared memory
+//                     through 1-D bulk copies (cp.async.bulk + mbarrier, two stages per CTA), one thread per
+//                     read counts with byte-lane SWAR arithmetic.
+//   sgdx_route        stable partition of the read ids by sample index (what DemuxedGroup::per_sample_reads
+//                     holds, demux.rs:637-645): per-warp histograms, bin-major scan, per-warp ranked scatter.
+#include <algorithm>
+#include <cstring>
+
+#include "sgdx_handle.h"
+
+using namespace sgdx;
+
+namespace sgdx {
+
+static uint32_t grid_cap(uint64_t items, uint32_t per_block, int sms, int blocks_per_sm) {
+    uint64_t tiles = (items + per_block - 1) / per_block;
+    uint64_t cap = (uint64_t)sms * (uint64_t)blocks_per_sm;
+    return (uint32_t)(tiles < cap ? (tiles ? tiles : 1) : cap);
+}
+
+// ================================================================================================
+// 1. unmatched barcodes
+// ================================================================================================
+constexpr int kUnmStats = 8;  // [0] distinct keys in the table  [1] NoMatch reads seen  [2] dropped reads
+                              // [3] entries appended to the foreign-byte list  [4] selected entries  [5] tie tickets
+constexpr unsigned long long kEmptyWord = ~0ull;
+constexpr int kUnmHistBins = 4096;
+
+struct UnmTable {
+    ulonglong2 *keys;  // {bases 0..20, bases 21..31 | 1 << 63}; {~0, ~0} = empty
+    unsigned long long *counts;
+    unsigned long long *stats;
+    uint64_t mask;       // slots - 1
+    uint64_t key_limit;  // no new keys once stats[0] reaches this
+    uint8_t *odd;        // 32-byte records
+    uint64_t odd_cap;
+};
+
+__device__ __forceinline__ ulonglong2 cas128(ulonglong2 *addr, ulonglong2 cmp, ulonglong2 val) {
+    ulonglong2 old;
+    asm volatile(
+        "{\n\t.reg .b128 c, v, o;\n\tmov.b128 c, {%2, %3};\n\tmov.b128 v, {%4, %5};\n\t"
+        "atom.global.relaxed.gpu.cas.b128 o, [%6], c, v;\n\tmov.b128 {%0, %1}, o;\n\t}"
+        : "=l"(old.x), "=l"(old.y)
+        : "l"(cmp.x), "l"(cmp.y), "l"(val.x), "l"(val.y), "l"(addr)
+        : "memory");
+    return old;
+}
+
+__device__ __forceinline__ uint64_t unm_hash(uint64_t k0, uint64_t k1) { return mix64(k0 ^ mix64(k1 + 0x9E3779B97F4A7C15ull)); }
+
+// count[key] += add; a new key claims the first empty slot of its probe sequence with one 128-bit CAS (the CAS is
+// also the read: a plain 128-bit load may be torn against a concurrent claim).  false = table full, not counted.
+__device__ __forceinline__ bool unm_add(const UnmTable &t, uint64_t k0, uint64_t k1, unsigned long long add) {
+    const ulonglong2 empty = make_ulonglong2(kEmptyWord, kEmptyWord), key = make_ulonglong2(k0, k1);
+    uint64_t i = unm_hash(k0, k1) & t.mask;
+    for (uint64_t probe = 0; probe <= t.mask; probe++) {
+        const bool full = *reinterpret_cast<volatile unsigned long long *>(t.stats) >= t.key_limit;
+        const ulonglong2 old = cas128(t.keys + i, empty, full ? empty : key);
+        if (old.x == kEmptyWord && old.y == kEmptyWord) {
+            if (full) return false;  // the key is not in the table (no deletions) and may not enter it
+            atomicAdd(t.stats + 0, 1ull);
+            atomicAdd(t.counts + i, add);
+            return true;
+        }
+        if (old.x == k0 && old.y == k1) {
+            atomicAdd(t.counts + i, add);
+            return true;
+        }
+        i = (i + 1) & t.mask;
+    }
+    return false;
+}
+
+// one thread per read: NoMatch reads (idx == S) are keyed and counted (demux.rs:553-555)
+__global__ void __launch_bounds__(256) sgdx_unmatched_count(const uint8_t *__restrict__ reads,
+                                                            const uint16_t *__restrict__ idx, uint64_t n, uint32_t S,
+                                                            uint32_t L, const UnmTable t) {
+    __shared__ unsigned int s_seen, s_drop;
+    if (threadIdx.x == 0) s_seen = s_drop = 0u;
+    __syncthreads();
+    for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (uint64_t)gridDim.x * blockDim.x) {
+        if (idx[r] != S) continue;
+        const uint8_t *p = reads + r * (uint64_t)L;
+        uint64_t k0 = 0, k1 = 1ull << 63;
+        bool odd = false;
+        for (uint32_t j = 0; j < L; j++) {
+            const uint32_t c = __ldg(p + j);
+            const uint32_t code = c == 'N' ? 4u : ((c >> 1) & 3u);       // A0 C1 T2 G3 N4
+            odd |= c != ((0x4E47544341ull >> (8u * code)) & 0xFFu);      // "ACTGN"[code]
+            if (j < 21u) k0 |= (uint64_t)code << (3u * j);
+            else k1 |= (uint64_t)code << (3u * (j - 21u));
+        }
+        atomicAdd(&s_seen, 1u);
+        bool ok;
+        if (!odd) {
+            ok = unm_add(t, k0, k1, 1ull);
+        } else {  // a byte outside ACGTN: keep the bytes themselves, the host counts these
+            const unsigned long long at = atomicAdd(t.stats + 3, 1ull);
+            ok = at < t.odd_cap;
+            if (ok)
+                for (uint32_t j = 0; j < 32u; j++) t.odd[at * 32u + j] = j < L ? __ldg(p + j) : (uint8_t)0;
+        }
+        if (!ok) atomicAdd(&s_drop, 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (s_seen) atomicAdd(t.stats + 1, (unsigned long long)s_seen);
+        if (s_drop) atomicAdd(t.stats + 2, (unsigned long long)s_drop);
+    }
+}
+
+// histogram of min(count, kUnmHistBins-1) over the occupied slots
+__global__ void __launch_bounds__(256) sgdx_unmatched_hist(const ulonglong2 *__restrict__ keys,
+                                                           const unsigned long long *__restrict__ counts, uint64_t slots,
+                                                           unsigned long long *__restrict__ hist) {
+    __shared__ unsigned int sh[kUnmHistBins];
+    for (uint32_t i = threadIdx.x; i < kUnmHistBins; i += blockDim.x) sh[i] = 0u;
+    __syncthreads();
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < slots; i += (uint64_t)gridDim.x * blockDim.x) {
+        if (keys[i].x == kEmptyWord) continue;
+        const unsigned long long c = counts[i];
+        atomicAdd(&sh[c < (unsigned long long)(kUnmHistBins - 1) ? (uint32_t)c : (uint32_t)(kUnmHistBins - 1)], 1u);
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < kUnmHistBins; i += blockDim.x)
+        if (sh[i]) atomicAdd(hist + i, (unsigned long long)sh[i]);
+}
+
+// entries with count > t, plus up to `quota` entries with count == t, compacted into out_*
+__global__ void __launch_bounds__(256) sgdx_unmatched_select(const ulonglong2 *__restrict__ keys,
+                                                             const unsigned long long *__restrict__ counts,
+                                                             uint64_t slots, unsigned long long t,
+                                                             unsigned long long quota, ulonglong2 *__restrict__ out_keys,
+                                                             unsigned long long *__restrict__ out_counts,
+                                                             uint64_t out_cap, unsigned long long *__restrict__ stats) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < slots; i += (uint64_t)gridDim.x * blockDim.x) {
+        const ulonglong2 k = keys[i];
+        if (k.x == kEmptyWord) continue;
+        const unsigned long long c = counts[i];
+        bool take = c > t;
+        if (c == t && quota) take = atomicAdd(stats + 5, 1ull) < quota;
+        if (!take) continue;
+        const unsigned long long j = atomicAdd(stats + 4, 1ull);
+        if (j < out_cap) {
+            out_keys[j] = k;
+            out_counts[j] = c;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) sgdx_unmatched_reinsert(const ulonglong2 *__restrict__ sel_keys,
+                                                               const unsigned long long *__restrict__ sel_counts,
+                                                               uint64_t n, const UnmTable t) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+        unm_add(t, sel_keys[i].x, sel_keys[i].y, sel_counts[i]);
+}
+
+// ================================================================================================
+// 2. segment extraction
+// ================================================================================================
+struct ExtractParams {
+    const uint8_t *src[SGDX_MAX_SOURCES];
+    uint32_t stride[SGDX_MAX_SOURCES];
+    uint8_t pos_src[SGDX_MAX_BARCODE_LEN];   // barcode position j comes from source pos_src[j] ...
+    uint16_t pos_off[SGDX_MAX_BARCODE_LEN];  // ... at read offset pos_off[j]
+    uint32_t L, magic;                       // magic = ceil(2^32 / L)
+    uint64_t n;
+    uint8_t *out;
+    uint32_t words_ok;                       // out is 4-byte aligned
+};
+constexpr uint32_t kExtractTileReads = 1024;
+
+// One thread per output word: four gathered bytes, one coalesced 32-bit store.
+__global__ void __launch_bounds__(256) sgdx_extract(const ExtractParams p) {
+    __shared__ uint32_t s_src[SGDX_MAX_BARCODE_LEN], s_off[SGDX_MAX_BARCODE_LEN];
+    if (threadIdx.x < p.L) {
+        s_src[threadIdx.x] = p.pos_src[threadIdx.x];
+        s_off[threadIdx.x] = p.pos_off[threadIdx.x];
+    }
+    __syncthreads();
+    const uint64_t ntiles = (p.n + kExtractTileReads - 1) / kExtractTileReads;
+    for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const uint64_t first = tile * kExtractTileReads;
+        const uint32_t cnt = (uint32_t)min((uint64_t)kExtractTileReads, p.n - first);
+        const uint32_t bytes = cnt * p.L;
+        uint8_t *out = p.out + first * p.L;  // first*L is a multiple of 4
+        for (uint32_t o = threadIdx.x * 4u; o < bytes; o += blockDim.x * 4u) {
+            uint32_t w = 0;
+            const uint32_t nb = min(4u, bytes - o);
+            for (uint32_t b = 0; b < nb; b++) {
+                const uint32_t ob = o + b;
+                const uint32_t rl = __umulhi(ob, p.magic);  // ob / L: exact for ob * L < 2^32
+                const uint32_t j = ob - rl * p.L;
+                const uint32_t s = s_src[j];
+                const uint32_t c = __ldg(p.src[s] + (first + rl) * (uint64_t)p.stride[s] + s_off[j]);
+                w |= c << (8u * b);
+            }
+            if (nb == 4u && p.words_ok) *reinterpret_cast<uint32_t *>(out + o) = w;
+            else
+                for (uint32_t b = 0; b < nb; b++) out[o + b] = (uint8_t)(w >> (8u * b));
+        }
+    }
+}
+
+// ================================================================================================
+// 3. base-quality counters
+// ================================================================================================
+constexpr int kQualThreads = 128;
+constexpr int kQualCounters = 5;  // q20, q30, index_bases_qual_sum, index_bases_total_seen, bases (metrics.rs:468-481)
+
+struct QualParams {
+    const uint8_t *quals;
+    const uint32_t *lens;  // nullable
+    const uint16_t *idx;
+    uint64_t n;
+    uint32_t stride, S;
+    uint32_t reads_per_tile;  // multiple of 16, <= kQualThreads
+    uint32_t stage_bytes;     // shared-memory bytes of one stage (multiple of 128)
+    uint32_t stages;
+    uint32_t nwords;          // words per shifted mask
+    uint32_t min_len;         // a shorter read cannot be cut into the fixed segments
+    uint32_t smem_hist;       // per-CTA histogram in shared memory (else global atomics)
+    const uint32_t *masks;    // [2][16][nwords]: template / sample-barcode position bits, shifted left by 0..15
+    unsigned long long *counters;  // [(S+1)][5], then 1 word: short reads
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@!p bra WAIT_%=;\n\t}" ::"r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+}
+// 1-D bulk copy global -> shared, completion counted in bytes on the mbarrier (both addresses and the size are
+// multiples of 16)
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+__device__ __forceinline__ uint32_t lanes8_sum(uint32_t acc) {  // sum of the four byte lanes
+    const uint32_t t = (acc & 0x00FF00FFu) + ((acc >> 8) & 0x00FF00FFu);
+    return (t & 0xFFFFu) + (t >> 16);
+}
+
+template <bool HAS_B>
+__global__ void __launch_bounds__(kQualThreads) sgdx_qual_counts(const QualParams p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    unsigned char *stage0 = smem;
+    uint32_t *s_masks = reinterpret_cast<uint32_t *>(smem + (size_t)p.stages * p.stage_bytes);
+    uint32_t *hist = s_masks + 32u * p.nwords;
+    const uint32_t nbins = p.smem_hist ? (p.S + 1u) * kQualCounters : 0u;
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(hist + ((nbins + 1u) & ~1u));
+    const uint32_t tid = threadIdx.x;
+
+    if (tid == 0) {
+        for (uint32_t s = 0; s < p.stages; s++) mbar_init(mbar + s, 1u);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (uint32_t i = tid; i < 32u * p.nwords; i += kQualThreads) s_masks[i] = p.masks[i];
+    for (uint32_t i = tid; i < nbins; i += kQualThreads) hist[i] = 0u;
+    __syncthreads();
+
+    const uint32_t R = p.reads_per_tile;
+    const uint64_t ntiles = (p.n + R - 1) / R;
+    auto issue = [&](uint64_t tile, uint32_t s) {  // thread 0 only
+        const uint64_t first = tile * R;
+        const uint32_t cnt = (uint32_t)min((uint64_t)R, p.n - first);
+        const uint32_t bulk = (cnt * p.stride) & ~15u;
+        mbar_expect_tx(mbar + s, bulk);
+        if (bulk) bulk_g2s(stage0 + (size_t)s * p.stage_bytes, p.quals + first * p.stride, bulk, mbar + s);
+    };
+    if (tid == 0)
+        for (uint32_t s = 0; s < p.stages; s++) {
+            const uint64_t tile = (uint64_t)blockIdx.x + (uint64_t)s * gridDim.x;
+            if (tile < ntiles) issue(tile, s);
+        }
+
+    unsigned long long *gcnt = p.counters;
+    auto bump = [&](uint32_t slot, uint32_t v) {
+        if (p.smem_hist) atomicAdd(hist + slot, v);
+        else atomicAdd(gcnt + slot, (unsigned long long)v);
+    };
+    auto flush = [&]() {
+        __syncthreads();
+        for (uint32_t i = tid; i < nbins; i += kQualThreads) {
+            const uint32_t c = hist[i];
+            if (c) {
+                atomicAdd(gcnt + i, (unsigned long long)c);
+                hist[i] = 0u;
+            }
+        }
+        __syncthreads();
+    };
+
+    uint32_t it = 0, shorts = 0;
+    for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
+        const uint32_t s = it % p.stages, parity = (it / p.stages) & 1u;
+        unsigned char *stage = stage0 + (size_t)s * p.stage_bytes;
+        const uint64_t first = tile * R;
+        const uint32_t cnt = (uint32_t)min((uint64_t)R, p.n - first);
+        const uint32_t bytes = cnt * p.stride, bulk = bytes & ~15u;
+        mbar_wait(mbar + s, parity);
+        if (bytes != bulk) {  // last tile only: the < 16 bytes a bulk copy cannot carry
+            if (tid < bytes - bulk) stage[bulk + tid] = p.quals[first * p.stride + bulk + tid];
+            __syncthreads();
+        }
+        if (tid < cnt) {
+            const uint32_t start = tid * p.stride, a = start & 15u;
+            const uint4 *chunks = reinterpret_cast<const uint4 *>(stage + (start & ~15u));
+            uint32_t len = p.stride;
+            if (p.lens) len = min(__ldg(p.lens + first + tid), p.stride);
+            const uint32_t bin = __ldg(p.idx + first + tid);
+            if (len < p.min_len) {
+                shorts++;
+            } else if (bin <= p.S) {
+                const uint32_t *tm = s_masks + a * p.nwords, *bm = s_masks + (16u + a) * p.nwords;
+                const uint32_t end = a + len, nchunks = (end + 15u) >> 4;
+                uint32_t acc20 = 0, acc30 = 0, c20 = 0, c30 = 0, nT = 0;   // template bases
+                uint32_t bacc = 0, bsum = 0, nB = 0, nBfast = 0;            // sample-barcode bases
+                for (uint32_t k = 0; k < nchunks; k++) {
+                    const uint32_t sh = (k & 1u) * 16u;
+                    uint32_t m = (tm[k >> 1] >> sh) & 0xFFFFu;
+                    uint32_t mb = HAS_B ? (bm[k >> 1] >> sh) & 0xFFFFu : 0u;
+                    const uint32_t rem = end - 16u * k;
+                    if (rem < 16u) {  // bytes past the read's own length
+                        const uint32_t lm = (1u << rem) - 1u;
+                        m &= lm;
+                        mb &= lm;
+                    }
+                    if ((m | mb) != 0u) {
+                        const uint4 v = chunks[k];
+                        const uint32_t x[4] = {v.x, v.y, v.z, v.w};
+                        // every byte in 33..127 <=> no 0x80 bit in (x - 0x21..) | x (a borrow only starts at an
+                        // offending byte, which flags itself)
+                        uint32_t flag = 0;
+#pragma unroll
+                        for (int w = 0; w < 4; w++) flag |= (x[w] - 0x21212121u) | x[w];
+                        if ((flag & 0x80808080u) == 0u) {
+                            // q >= 20 <=> byte + (128 - 53) carries into bit 7; no carry leaves a byte
+                            if (m == 0xFFFFu) {
+#pragma unroll
+                                for (int w = 0; w < 4; w++) {
+                                    acc20 += ((x[w] + 0x4B4B4B4Bu) & 0x80808080u) >> 7;
+                                    acc30 += ((x[w] + 0x41414141u) & 0x80808080u) >> 7;
+                                }
+                                nT += 16u;
+                            } else if (m) {
+#pragma unroll
+                                for (int w = 0; w < 4; w++) {
+                                    const uint32_t t80 = (((m >> (4 * w)) & 15u) * 0x10204080u) & 0x80808080u;
+                                    acc20 += ((x[w] + 0x4B4B4B4Bu) & t80) >> 7;
+                                    acc30 += ((x[w] + 0x41414141u) & t80) >> 7;
+                                }
+                                nT += __popc(m);
+                            }
+                            if (HAS_B && mb) {
+#pragma unroll
+                                for (int w = 0; w < 4; w++) {
+                                    const uint32_t ff = ((((mb >> (4 * w)) & 15u) * 0x00204081u) & 0x01010101u) * 0xFFu;
+                                    const uint32_t xb = x[w] & ff;
+                                    bacc += (xb & 0x00FF00FFu) + ((xb >> 8) & 0x00FF00FFu);
+                                }
+                                nBfast += __popc(mb);
+                            }
+                        } else {  // a byte outside 33..127 in the chunk: exact u8 arithmetic, byte by byte
+                            for (uint32_t j = 0; j < 16u; j++) {
+                                const uint32_t q = (((x[j >> 2] >> (8u * (j & 3u))) & 0xFFu) - 33u) & 0xFFu;
+                                if ((m >> j) & 1u) {
+                                    c20 += q >= 20u;
+                                    c30 += q >= 30u;
+                                    nT++;
+                                }
+                                if ((mb >> j) & 1u) {
+                                    bsum += q;
+                                    nB++;
+                                }
+                            }
+                        }
+                    }
+                    if ((k & 15u) == 15u) {  // byte lanes hold <= 64, 16-bit lanes <= 16 256
+                        c20 += lanes8_sum(acc20);
+                        c30 += lanes8_sum(acc30);
+                        bsum += (bacc & 0xFFFFu) + (bacc >> 16);
+                        acc20 = acc30 = bacc = 0u;
+                    }
+                }
+                c20 += lanes8_sum(acc20);
+                c30 += lanes8_sum(acc30);
+                if (nT) {
+                    if (c20) bump(bin * kQualCounters + 0u, c20);
+                    if (c30) bump(bin * kQualCounters + 1u, c30);
+                    bump(bin * kQualCounters + 4u, nT);
+                }
+                if (HAS_B) {
+                    bsum += (bacc & 0xFFFFu) + (bacc >> 16) - 33u * nBfast;
+                    nB += nBfast;
+                    if (nB) {
+                        if (bsum) bump(bin * kQualCounters + 2u, bsum);
+                        bump(bin * kQualCounters + 3u, nB);
+                    }
+                }
+            }
+        }
+        __syncthreads();  // every thread is done with this stage before it is refilled
+        if (tid == 0) {
+            const uint64_t next = tile + (uint64_t)p.stages * gridDim.x;
+            if (next < ntiles) issue(next, s);
+        }
+        if (p.smem_hist && (it & 1023u) == 1023u) flush();  // 32-bit bins: 1024 tiles of <= 128 * 4096 bytes
+    }
+    if (p.smem_hist) flush();
+    if (shorts) atomicAdd(gcnt + (size_t)(p.S + 1u) * kQualCounters, (unsigned long long)shorts);
+}
+
+// ================================================================================================
+// 4. routing: stable partition of read ids by sample index
+// ================================================================================================
+struct RouteParams {
+    const uint16_t *idx;
+    uint64_t n;
+    uint32_t bins;       // S + 1
+    uint32_t ranges;     // one warp per range
+    uint32_t chunk;      // reads per range (multiple of 32)
+    uint32_t warps;      // per CTA
+    uint32_t *matrix;    // [ranges][bins]
+    unsigned long long *totals;  // [bins], then the exclusive scan in place
+    uint32_t *order;
+    unsigned long long *offsets;  // [bins + 1]
+};
+
+__global__ void sgdx_route_hist(const RouteParams p) {
+    extern __shared__ uint32_t s_route[];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    const uint32_t range = blockIdx.x * p.warps + warp;
+    if (range >= p.ranges) return;
+    uint32_t *h = s_route + (size_t)warp * p.bins;
+    for (uint32_t b = lane; b < p.bins; b += 32u) h[b] = 0u;
+    __syncwarp();
+    const uint64_t lo = (uint64_t)range * p.chunk, hi = min(p.n, lo + p.chunk);
+    for (uint64_t r = lo + lane; r < hi; r += 32u) {
+        const uint32_t b = min((uint32_t)__ldg(p.idx + r), p.bins - 1u);
+        atomicAdd(h + b, 1u);
+    }
+    __syncwarp();
+    uint32_t *row = p.matrix + (size_t)range * p.bins;
+    for (uint32_t b = lane; b < p.bins; b += 32u) row[b] = h[b];
+}
+
+// column b of the matrix becomes its exclusive prefix over the ranges; totals[b] = column sum
+__global__ void __launch_bounds__(128) sgdx_route_scan_ranges(const RouteParams p) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= p.bins) return;
+    uint32_t run = 0;
+#pragma unroll 8
+    for (uint32_t t = 0; t < p.ranges; t++) {
+        const uint32_t c = p.matrix[(size_t)t * p.bins + b];
+        p.matrix[(size_t)t * p.bins + b] = run;
+        run += c;
+    }
+    p.totals[b] = run;
+}
+
+// one CTA: exclusive scan of the bin totals -> offsets[0..bins], totals[] := bin bases
+__global__ void __launch_bounds__(1024) sgdx_route_scan_bins(const RouteParams p) {
+    __shared__ unsigned long long s_part[1024];
+    const uint32_t per = (p.bins + 1023u) / 1024u;
+    const uint32_t lo = threadIdx.x * per, hi = min(p.bins, lo + per);
+    unsigned long long sum = 0;
+    for (uint32_t b = lo; b < hi; b++) sum += p.totals[b];
+    s_part[threadIdx.x] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long run = 0;
+        for (uint32_t i = 0; i < 1024u; i++) {
+            const unsigned long long c = s_part[i];
+            s_part[i] = run;
+            run += c;
+        }
+    }
+    __syncthreads();
+    unsigned long long run = s_part[threadIdx.x];
+    for (uint32_t b = lo; b < hi; b++) {
+        const unsigned long long c = p.totals[b];
+        p.totals[b] = run;
+        p.offsets[b] = run;
+        run += c;
+    }
+    if (threadIdx.x == 1023u) p.offsets[p.bins] = p.n;
+}
+
+__global__ void sgdx_route_scatter(const RouteParams p) {
+    extern __shared__ uint32_t s_route[];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    const uint32_t range = blockIdx.x * p.warps + warp;
+    if (range >= p.ranges) return;
+    uint32_t *cur = s_route + (size_t)warp * p.bins;
+    const uint32_t *row = p.matrix + (size_t)range * p.bins;
+    for (uint32_t b = lane; b < p.bins; b += 32u) cur[b] = row[b] + (uint32_t)p.totals[b];
+    __syncwarp();
+    const uint64_t lo = (uint64_t)range * p.chunk, hi = min(p.n, lo + p.chunk);
+    const uint32_t lt = (1u << lane) - 1u;
+    for (uint64_t base = lo; base < hi; base += 32u) {
+        const uint64_t r = base + lane;
+        const bool active = r < hi;
+        const uint32_t b = active ? min((uint32_t)__ldg(p.idx + r), p.bins - 1u) : 0xFFFFFFFFu;
+        const uint32_t peers = __match_any_sync(0xFFFFFFFFu, b);
+        const uint32_t rank = __popc(peers & lt);
+        uint32_t at = 0;
+        if (active && rank == 0u) {  // lowest lane of each bin group advances the bin's cursor
+            at = cur[b];
+            cur[b] = at + __popc(peers);
+        }
+        at = __shfl_sync(0xFFFFFFFFu, at, __ffs(peers) - 1);
+        if (active) p.order[at + rank] = (uint32_t)r;
+        __syncwarp();
+    }
+}
+
+// ================================================================================================
+// host side
+// ================================================================================================
+static UnmTable unm_table(const UnmatchedState &u) {
+    UnmTable t;
+    t.keys = u.d_keys;
+    t.counts = u.d_counts;
+    t.stats = u.d_stats;
+    t.mask = u.cap_slots - 1;
+    t.key_limit = u.key_limit;
+    t.odd = u.d_odd;
+    t.odd_cap = u.odd_cap;
+    return t;
+}
+
+int post_after_match(sgdx_handle *h, Slot &s, const uint8_t *d_ascii, const uint16_t *d_idx, uint64_t n) {
+    UnmatchedState &u = h->unm;
+    const uint32_t grid = grid_cap(n, 256, h->sms, 8);
+    sgdx_unmatched_count<<<grid, 256, 0, s.stream>>>(d_ascii, d_idx, n, h->cfg.num_samples, h->cfg.barcode_len,
+                                                     unm_table(u));
+    CU(cudaGetLastError());
+    h->launches.fetch_add(1);
+    if (!s.h_unm_stats) CU(cudaMallocHost(&s.h_unm_stats, kUnmStats * sizeof(unsigned long long)));
+    CU(cudaMemcpyAsync(s.h_unm_stats, u.d_stats, kUnmStats * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                       s.stream));
+    s.unm_pending = true;
+    return SGDX_OK;
+}
+
+static void decode_key(ulonglong2 k, uint32_t L, char *out) {
+    static const char letters[8] = {'A', 'C', 'T', 'G', 'N', '?', '?', '?'};
+    for (uint32_t j = 0; j < L; j++) {
+        const uint64_t w = j < 21 ? k.x >> (3 * j) : k.y >> (3 * (j - 21));
+        out[j] = letters[w & 7u];
+    }
+}
+
+// device idle, post_mu held: fold the foreign-byte list into the host map and empty it
+static int unm_drain_odd(sgdx_handle *h) {
+    UnmatchedState &u = h->unm;
+    unsigned long long st[kUnmStats];
+    CU(cudaMemcpy(st, u.d_stats, sizeof st, cudaMemcpyDeviceToHost));
+    const uint64_t have = std::min<uint64_t>(st[3], u.odd_cap);
+    if (have) {
+        std::vector<uint8_t> buf(have * 32u);
+        CU(cudaMemcpy(buf.data(), u.d_odd, buf.size(), cudaMemcpyDeviceToHost));
+        const uint32_t L = h->cfg.barcode_len;
+        for (uint64_t i = 0; i < have; i++) u.odd[std::string(reinterpret_cast<const char *>(&buf[i * 32u]), L)]++;
+    }
+    CU(cudaMemset(u.d_stats + 3, 0, sizeof(unsigned long long)));
+    return SGDX_OK;
+}
+
+struct UnmEntry {
+    std::string key;
+    uint64_t count;
+};
+
+// device idle, post_mu held.  The `want` most frequent device-table entries (all of them when want is huge), found
+// by a count threshold from the device histogram; only those are copied to the host.  keep_on_device: leave the
+// compacted (key, count) list in d_sel_* and report its length.
+static int unm_select_top(sgdx_handle *h, uint64_t want, std::vector<ulonglong2> &keys, std::vector<unsigned long long> &counts) {
+    UnmatchedState &u = h->unm;
+    unsigned long long st[kUnmStats];
+    CU(cudaMemcpy(st, u.d_stats, sizeof st, cudaMemcpyDeviceToHost));
+    const uint64_t distinct = st[0];
+    keys.clear();
+    counts.clear();
+    if (distinct == 0 || want == 0) return SGDX_OK;
+    unsigned long long t = 0, quota = 0;
+    uint64_t need = distinct;
+    if (want < distinct) {
+        CU(cudaMemset(u.d_hist, 0, kUnmHistBins * sizeof(unsigned long long)));
+        sgdx_unmatched_hist<<<grid_cap(u.cap_slots, 256, h->sms, 8), 256>>>(u.d_keys, u.d_counts, u.cap_slots, u.d_hist);
+        CU(cudaGetLastError());
+        std::vector<unsigned long long> hist(kUnmHistBins);
+        CU(cudaMemcpy(hist.data(), u.d_hist, hist.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        // largest t with #(count >= t) >= want; counts above the last bin are not resolved: take them all
+        uint64_t above = 0;  // #(count > t) while walking down
+        t = kUnmHistBins - 1;
+        for (;;) {
+            if (above + hist[t] >= want || t == 1) break;
+            above += hist[t];
+            t--;
+        }
+        if (t == (unsigned long long)(kUnmHistBins - 1)) {
+            t = kUnmHistBins - 2;  // everything with count >= last bin
+            quota = 0;
+            need = hist[kUnmHistBins - 1];
+        } else {
+            quota = want > above ? want - above : 0;
+            need = above + std::min<uint64_t>(quota, hist[t]);
+        }
+    }
+    if (need > u.sel_cap) {
+        cudaFree(u.d_sel_keys);
+        cudaFree(u.d_sel_counts);
+        u.d_sel_keys = nullptr;
+        u.d_sel_counts = nullptr;
+        u.sel_cap = 0;
+        CU(cudaMalloc(&u.d_sel_keys, need * sizeof(ulonglong2)));
+        CU(cudaMalloc(&u.d_sel_counts, need * sizeof(unsigned long long)));
+        u.sel_cap = need;
+    }
+    CU(cudaMemset(u.d_stats + 4, 0, 2 * sizeof(unsigned long long)));
+    sgdx_unmatched_select<<<grid_cap(u.cap_slots, 256, h->sms, 8), 256>>>(u.d_keys, u.d_counts, u.cap_slots, t, quota,
+                                                                          u.d_sel_keys, u.d_sel_counts, u.sel_cap,
+                                                                          u.d_stats);
+    CU(cudaGetLastError());
+    CU(cudaMemcpy(st, u.d_stats, sizeof st, cudaMemcpyDeviceToHost));
+    const uint64_t got = std::min<uint64_t>(st[4], u.sel_cap);
+    keys.resize(got);
+    counts.resize(got);
+    if (got) {
+        CU(cudaMemcpy(keys.data(), u.d_sel_keys, got * sizeof(ulonglong2), cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(counts.data(), u.d_sel_counts, got * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    }
+    return SGDX_OK;
+}
+
+// the `want` most frequent keys of table + foreign-byte map, sorted by (count desc, key asc)
+static int unm_top_entries(sgdx_handle *h, uint64_t want, std::vector<UnmEntry> &out) {
+    if (int rc = unm_drain_odd(h)) return rc;
+    std::vector<ulonglong2> keys;
+    std::vector<unsigned long long> counts;
+    if (int rc = unm_select_top(h, want, keys, counts)) return rc;
+    const uint32_t L = h->cfg.barcode_len;
+    out.clear();
+    out.reserve(keys.size() + h->unm.odd.size());
+    std::string k(L, 'A');
+    for (size_t i = 0; i < keys.size(); i++) {
+        decode_key(keys[i], L, &k[0]);
+        out.push_back(UnmEntry{k, counts[i]});
+    }
+    for (auto &kv : h->unm.odd) out.push_back(UnmEntry{kv.first, kv.second});
+    std::sort(out.begin(), out.end(), [](const UnmEntry &a, const UnmEntry &b) {
+        return a.count != b.count ? a.count > b.count : a.key < b.key;
+    });
+    if (out.size() > want) out.resize(want);
+    return SGDX_OK;
+}
+
+// UnmatchedCounter::downsize (metrics.rs:166-175); device idle, post_mu held
+static int unm_downsize_locked(sgdx_handle *h) {
+    UnmatchedState &u = h->unm;
+    std::vector<UnmEntry> top;
+    if (int rc = unm_top_entries(h, u.downsize_to, top)) return rc;
+    std::vector<ulonglong2> keys;
+    std::vector<unsigned long long> counts;
+    std::map<std::string, uint64_t> odd;
+    const uint32_t L = h->cfg.barcode_len;
+    for (const UnmEntry &e : top) {
+        uint64_t k0 = 0, k1 = 1ull << 63;
+        bool foreign = false;
+        for (uint32_t j = 0; j < L; j++) {
+            const char c = e.key[j];
+            uint64_t code = c == 'A' ? 0 : c == 'C' ? 1 : c == 'T' ? 2 : c == 'G' ? 3 : c == 'N' ? 4 : 7;
+            foreign |= code == 7;
+            if (j < 21) k0 |= code << (3 * j);
+            else k1 |= code << (3 * (j - 21));
+        }
+        if (foreign) odd[e.key] = e.count;
+        else {
+            keys.push_back(make_ulonglong2(k0, k1));
+            counts.push_back(e.count);
+        }
+    }
+    u.odd.swap(odd);
+    CU(cudaMemset(u.d_keys, 0xFF, u.cap_slots * sizeof(ulonglong2)));
+    CU(cudaMemset(u.d_counts, 0, u.cap_slots * sizeof(unsigned long long)));
+    CU(cudaMemset(u.d_stats, 0, sizeof(unsigned long long)));  // distinct; the read totals stay
+    if (!keys.empty()) {
+        if (keys.size() > u.sel_cap) return fail(SGDX_ESTATE, "unmatched downsize: selection scratch too small");
+        CU(cudaMemcpy(u.d_sel_keys, keys.data(), keys.size() * sizeof(ulonglong2), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(u.d_sel_counts, counts.data(), counts.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice));
+        sgdx_unmatched_reinsert<<<grid_cap(keys.size(), 256, h->sms, 8), 256>>>(u.d_sel_keys, u.d_sel_counts, keys.size(),
+                                                                               unm_table(u));
+        CU(cudaGetLastError());
+    }
+    CU(cudaDeviceSynchronize());
+    u.downsizes++;
+    return SGDX_OK;
+}
+
+int post_on_sync(sgdx_handle *h, Slot &s) {
+    if (!s.unm_pending) return SGDX_OK;
+    s.unm_pending = false;
+    UnmatchedState &u = h->unm;
+    const unsigned long long *st = s.h_unm_stats;
+    std::lock_guard<std::mutex> lk(h->post_mu);
+    const bool too_many = st[0] + u.odd.size() >= u.max_map_size;
+    const bool odd_filling = st[3] > u.odd_cap / 2;
+    if (!too_many && !odd_filling) return SGDX_OK;
+    CU(cudaSetDevice(h->cfg.device));
+    CU(cudaDeviceSynchronize());
+    if (too_many) return unm_downsize_locked(h);
+    return unm_drain_odd(h);
+}
+
+int post_reset(sgdx_handle *h) {
+    const uint32_t S = h->cfg.num_samples;
+    if (h->qual.d_counters) CU(cudaMemset(h->qual.d_counters, 0, ((size_t)(S + 1) * kQualCounters + 1) * sizeof(unsigned long long)));
+    UnmatchedState &u = h->unm;
+    if (u.on) {
+        CU(cudaMemset(u.d_keys, 0xFF, u.cap_slots * sizeof(ulonglong2)));
+        CU(cudaMemset(u.d_counts, 0, u.cap_slots * sizeof(unsigned long long)));
+        CU(cudaMemset(u.d_stats, 0, kUnmStats * sizeof(unsigned long long)));
+        u.odd.clear();
+        u.downsizes = 0;
+    }
+    return SGDX_OK;
+}
+
+void post_destroy(sgdx_handle *h) {
+    UnmatchedState &u = h->unm;
+    cudaFree(u.d_keys);
+    cudaFree(u.d_counts);
+    cudaFree(u.d_stats);
+    cudaFree(u.d_odd);
+    cudaFree(u.d_sel_keys);
+    cudaFree(u.d_sel_counts);
+    cudaFree(u.d_hist);
+    cudaFree(h->qual.d_counters);
+    for (Slot &s : h->slots) cudaFree(s.d_qmasks);
+}
+
+}  // namespace sgdx
+
+// ------------------------------------------------------------------------------------------------
+// C ABI: unmatched
+// ------------------------------------------------------------------------------------------------
+extern "C" int sgdx_unmatched_enable(sgdx_handle *h, uint64_t max_map_size, uint64_t downsize_to) {
+    if (!h) return fail(SGDX_EINVAL, "null handle");
+    if (h->unm.on) return fail(SGDX_ESTATE, "unmatched collection is already enabled");
+    if (max_map_size == 0) max_map_size = 5000000ull;  // opts.rs:185
+    if (downsize_to == 0) downsize_to = 5000ull;       // opts.rs:189
+    if (downsize_to > max_map_size) downsize_to = max_map_size;
+    if (max_map_size > (1ull << 30)) return fail(SGDX_EINVAL, "max_map_size %llu too large", (unsigned long long)max_map_size);
+    std::lock_guard<std::mutex> lk(h->post_mu);
+    CU(cudaSetDevice(h->cfg.device));
+    CU(cudaDeviceSynchronize());
+    UnmatchedState &u = h->unm;
+    u.max_map_size = max_map_size;
+    u.downsize_to = downsize_to;
+    // room for a batch's worth of new keys between two syncs: 4x the limit, at least 2^16 slots
+    uint64_t cap = 1ull << 16;
+    while (cap < 4 * max_map_size) cap <<= 1;
+    u.cap_slots = cap;
+    u.key_limit = cap / 4 * 3;
+    u.odd_cap = 1ull << 20;
+    CU(cudaMalloc(&u.d_keys, cap * sizeof(ulonglong2)));
+    CU(cudaMalloc(&u.d_counts, cap * sizeof(unsigned long long)));
+    CU(cudaMalloc(&u.d_stats, kUnmStats * sizeof(unsigned long long)));
+    CU(cudaMalloc(&u.d_odd, u.odd_cap * 32u));
+    CU(cudaMalloc(&u.d_hist, kUnmHistBins * sizeof(unsigned long long)));
+    CU(cudaMemset(u.d_keys, 0xFF, cap * sizeof(ulonglong2)));
+    CU(cudaMemset(u.d_counts, 0, cap * sizeof(unsigned long long)));
+    CU(cudaMemset(u.d_stats, 0, kUnmStats * sizeof(unsigned long long)));
+    CU(cudaDeviceSynchronize());
+    u.on = true;
+    return SGDX_OK;
+}
+
+#define UNM_ENTER(h)                                                                       \
+    if (!(h)) return fail(SGDX_EINVAL, "null handle");                                     \
+    if (!(h)->unm.on) return fail(SGDX_ESTATE, "call sgdx_unmatched_enable first");        \
+    std::lock_guard<std::mutex> lk((h)->post_mu);                                          \
+    CU(cudaSetDevice((h)->cfg.device));                                                    \
+    CU(cudaDeviceSynchronize())
+
+extern "C" int sgdx_unmatched_info_get(sgdx_handle *h, sgdx_unmatched_info *out) {
+    if (!out) return fail(SGDX_EINVAL, "sgdx_unmatched_info_get: null out");
+    UNM_ENTER(h);
+    if (int rc = unm_drain_odd(h)) return rc;
+    unsigned long long st[kUnmStats];
+    CU(cudaMemcpy(st, h->unm.d_stats, sizeof st, cudaMemcpyDeviceToHost));
+    out->distinct_keys = st[0] + h->unm.odd.size();
+    out->unmatched_reads = st[1];
+    out->dropped_reads = st[2];
+    out->downsizes = h->unm.downsizes;
+    return SGDX_OK;
+}
+
+static int unm_write(sgdx_handle *h, const std::vector<UnmEntry> &v, uint8_t *keys, uint64_t *counts, uint64_t cap,
+                     uint64_t *n_written) {
+    if (v.size() > cap) return fail(SGDX_EINVAL, "unmatched export needs room for %zu keys, got %llu", v.size(), (unsigned long long)cap);
+    const uint32_t L = h->cfg.barcode_len;
+    for (size_t i = 0; i < v.size(); i++) {
+        memcpy(keys + i * L, v[i].key.data(), L);
+        counts[i] = v[i].count;
+    }
+    *n_written = v.size();
+    return SGDX_OK;
+}
+
+extern "C" int sgdx_unmatched_export(sgdx_handle *h, uint8_t *keys, uint64_t *counts, uint64_t cap, uint64_t *n_written) {
+    if (!n_written || (cap && (!keys || !counts))) return fail(SGDX_EINVAL, "sgdx_unmatched_export: null argument");
+    UNM_ENTER(h);
+    std::vector<UnmEntry> v;
+    if (int rc = unm_top_entries(h, ~0ull, v)) return rc;
+    return unm_write(h, v, keys, counts, cap, n_written);
+}
+
+extern "C" int sgdx_unmatched_top(sgdx_handle *h, uint64_t n, uint8_t *keys, uint64_t *counts, uint64_t *n_written) {
+    if (!n_written || (n && (!keys || !counts))) return fail(SGDX_EINVAL, "sgdx_unmatched_top: null argument");
+    UNM_ENTER(h);
+    std::vector<UnmEntry> v;
+    if (int rc = unm_top_entries(h, n, v)) return rc;
+    return unm_write(h, v, keys, counts, n, n_written);
+}
+
+extern "C" int sgdx_unmatched_downsize(sgdx_handle *h) {
+    UNM_ENTER(h);
+    return unm_downsize_locked(h);
+}
+
+// ------------------------------------------------------------------------------------------------
+// C ABI: extraction
+// ------------------------------------------------------------------------------------------------
+static int fill_extract(sgdx_handle *h, uint32_t num_sources, const uint8_t *const *d_bases, const uint32_t *strides,
+                        const sgdx_segment *segs, uint32_t nsegs, ExtractParams *p) {
+    if (!d_bases || !strides || !segs) return fail(SGDX_EINVAL, "segment extraction: null argument");
+    if (num_sources < 1 || num_sources > SGDX_MAX_SOURCES) return fail(SGDX_EINVAL, "1..%u sources", SGDX_MAX_SOURCES);
+    if (nsegs < 1 || nsegs > SGDX_MAX_SEGMENTS) return fail(SGDX_EINVAL, "1..%u segments", SGDX_MAX_SEGMENTS);
+    const uint32_t L = h->cfg.barcode_len;
+    memset(p, 0, sizeof *p);
+    for (uint32_t s = 0; s < num_sources; s++) {
+        if (!d_bases[s] || strides[s] == 0 || strides[s] > 0xFFFFu) return fail(SGDX_EINVAL, "source %u: null or stride outside 1..65535", s);
+        p->src[s] = d_bases[s];
+        p->stride[s] = strides[s];
+    }
+    // sample-barcode segments in FASTQ order, then segment order (demux.rs:504-522)
+    uint32_t pos = 0;
+    for (uint32_t s = 0; s < num_sources; s++)
+        for (uint32_t i = 0; i < nsegs; i++) {
+            const sgdx_segment &g = segs[i];
+            if (g.source >= num_sources) return fail(SGDX_EINVAL, "segment %u: source %u of %u", i, g.source, num_sources);
+            if (g.source != s || g.kind != SGDX_SEG_SAMPLE_BARCODE) continue;
+            uint32_t len = g.length == SGDX_SEG_TO_END ? (g.offset < strides[s] ? strides[s] - g.offset : 0u) : g.length;
+            if ((uint64_t)g.offset + len > strides[s]) return fail(SGDX_EINVAL, "segment %u runs past the stride of source %u", i, s);
+            for (uint32_t j = 0; j < len; j++, pos++) {
+                if (pos >= L) return fail(SGDX_EINVAL, "sample-barcode segments are longer than barcode_len %u", L);
+                p->pos_src[pos] = (uint8_t)s;
+                p->pos_off[pos] = (uint16_t)(g.offset + j);
+            }
+        }
+    if (pos != L) return fail(SGDX_EINVAL, "sample-barcode segments sum to %u bases, barcode_len is %u (run.rs:109-119)", pos, L);
+    p->L = L;
+    p->magic = (uint32_t)(((1ull << 32) + L - 1) / L);
+    return SGDX_OK;
+}
+
+static int check_slot_post(sgdx_handle *h, uint32_t slot) {
+    if (!h) return fail(SGDX_EINVAL, "null handle");
+    if (slot >= h->slots.size()) return fail(SGDX_EINVAL, "slot %u >= %zu", slot, h->slots.size());
+    return SGDX_OK;
+}
+
+extern "C" int sgdx_extract_device(sgdx_handle *h, uint32_t slot, uint32_t num_sources, const uint8_t *const *d_bases,
+                                   const uint32_t *strides, const sgdx_segment *segs, uint32_t nsegs, uint64_t n,
+                                   uint8_t *d_out) {
+    if (int rc = check_slot_post(h, slot)) return rc;
+    ExtractParams p;
+    if (int rc = fill_extract(h, num_sources, d_bases, strides, segs, nsegs, &p)) return rc;
+    if (n == 0) return SGDX_OK;
+    if (!d_out) return fail(SGDX_EINVAL, "sgdx_extract_device: null output");
+    CU(cudaSetDevice(h->cfg.device));
+    p.n = n;
+    p.out = d_out;
+    p.words_ok = (reinterpret_cast<uintptr_t>(d_out) & 3u) == 0u;
+    sgdx_extract<<<grid_cap(n, kExtractTileReads, h->sms, 8), 256, 0, h->slots[slot].stream>>>(p);
+    CU(cudaGetLastError());
+    h->launches.fetch_add(1);
+    return SGDX_OK;
+}
+
+extern "C" int sgdx_match_segments_device(sgdx_handle *h, uint32_t slot, uint32_t num_sources,
+                                          const uint8_t *const *d_bases, const uint32_t *strides,
+                                          const sgdx_segment *segs, uint32_t nsegs, uint64_t n, uint16_t *d_idx,
+                                          uint8_t *d_dist) {
+    if (int rc = check_slot_post(h, slot)) return rc;
+    Slot &s = h->slots[slot];
+    CU(cudaSetDevice(h->cfg.device));
+    if (n > s.extract_cap) {
+        CU(cudaStreamSynchronize(s.stream));
+        cudaFree(s.d_extract);
+        s.d_extract = nullptr;
+        s.extract_cap = 0;
+        const uint64_t cap = n + n / 8 + 1024;
+        CU(cudaMalloc(&s.d_extract, cap * h->cfg.barcode_len));
+        s.extract_cap = cap;
+    }
+    if (int rc = sgdx_extract_device(h, slot, num_sources, d_bases, strides, segs, nsegs, n, s.d_extract)) return rc;
+    return sgdx_match_device(h, slot, s.d_extract, n, d_idx, d_dist);
+}
+
+// ------------------------------------------------------------------------------------------------
+// C ABI: base-quality counters
+// ------------------------------------------------------------------------------------------------
+static int ensure_qual_counters(sgdx_handle *h) {
+    if (h->qual.d_counters) return SGDX_OK;
+    std::lock_guard<std::mutex> lk(h->post_mu);
+    if (h->qual.d_counters) return SGDX_OK;
+    const size_t words = (size_t)(h->cfg.num_samples + 1) * kQualCounters + 1;
+    unsigned long long *d = nullptr;
+    CU(cudaMalloc(&d, words * sizeof(unsigned long long)));
+    CU(cudaMemset(d, 0, words * sizeof(unsigned long long)));
+    CU(cudaDeviceSynchronize());
+    h->qual.d_counters = d;
+    return SGDX_OK;
+}
+
+extern "C" int sgdx_qual_counts_device(sgdx_handle *h, uint32_t slot, const uint8_t *d_quals, uint64_t n,
+                                       uint32_t stride, const uint32_t *d_lens, const sgdx_segment *segs,
+                                       uint32_t nsegs, const uint16_t *d_idx) {
+    if (int rc = check_slot_post(h, slot)) return rc;
+    if (!segs || nsegs < 1 || nsegs > SGDX_MAX_SEGMENTS) return fail(SGDX_EINVAL, "sgdx_qual_counts_device: 1..%u segments", SGDX_MAX_SEGMENTS);
+    if (stride < 1 || stride > 3072u) return fail(SGDX_EINVAL, "stride %u outside 1..3072", stride);
+    if (n && (!d_quals || !d_idx)) return fail(SGDX_EINVAL, "sgdx_qual_counts_device: null buffer");
+    if (reinterpret_cast<uintptr_t>(d_quals) & 15u) return fail(SGDX_EINVAL, "quality matrix must be 16-byte aligned");
+    CU(cudaSetDevice(h->cfg.device));
+    if (int rc = ensure_qual_counters(h)) return rc;
+    Slot &s = h->slots[slot];
+
+    // position masks of the structure: bit p of tbits / bbits = position p is a template / sample-barcode base
+    const uint32_t nwords = (stride + 15u + 31u) / 32u + 1u;
+    std::vector<uint32_t> key;
+    key.push_back(stride);
+    uint32_t min_len = 0, has_b = 0;
+    std::vector<uint8_t> kind(stride, 0);
+    for (uint32_t i = 0; i < nsegs; i++) {
+        const sgdx_segment &g = segs[i];
+        key.insert(key.end(), {g.offset, g.length, g.kind});
+        if (g.kind != SGDX_SEG_TEMPLATE && g.kind != SGDX_SEG_SAMPLE_BARCODE && g.kind != SGDX_SEG_MOLECULAR_BARCODE &&
+            g.kind != SGDX_SEG_SKIP)
+            return fail(SGDX_EINVAL, "segment %u: unknown kind %u", i, g.kind);
+        uint32_t end;
+        if (g.length == SGDX_SEG_TO_END) {
+            if (g.offset > stride) return fail(SGDX_EINVAL, "segment %u starts past the stride", i);
+            end = stride;
+            min_len = std::max(min_len, g.offset);
+        } else {
+            if ((uint64_t)g.offset + g.length > stride) return fail(SGDX_EINVAL, "segment %u runs past the stride", i);
+            end = g.offset + g.length;
+            min_len = std::max(min_len, end);
+        }
+        for (uint32_t q = g.offset; q < end; q++) {
+            if (kind[q]) return fail(SGDX_EINVAL, "segments overlap at position %u", q);
+            kind[q] = (uint8_t)g.kind;
+        }
+        if (g.kind == SGDX_SEG_SAMPLE_BARCODE && end > g.offset) has_b = 1;
+    }
+    if (key != s.qmasks_key) {
+        std::vector<uint32_t> masks((size_t)32 * nwords, 0u);
+        for (uint32_t a = 0; a < 16; a++)
+            for (uint32_t q = 0; q < stride; q++) {
+                const uint32_t bit = q + a;
+                if (kind[q] == SGDX_SEG_TEMPLATE) masks[(size_t)a * nwords + (bit >> 5)] |= 1u << (bit & 31u);
+                if (kind[q] == SGDX_SEG_SAMPLE_BARCODE) masks[(size_t)(16 + a) * nwords + (bit >> 5)] |= 1u << (bit & 31u);
+            }
+        CU(cudaStreamSynchronize(s.stream));  // a kernel still reading the old masks
+        if (masks.size() > s.qmasks_cap) {
+            cudaFree(s.d_qmasks);
+            s.d_qmasks = nullptr;
+            s.qmasks_cap = 0;
+            CU(cudaMalloc(&s.d_qmasks, masks.size() * sizeof(uint32_t)));
+            s.qmasks_cap = masks.size();
+        }
+        CU(cudaMemcpy(s.d_qmasks, masks.data(), masks.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        s.qmasks_key = key;
+    }
+    if (n == 0) return SGDX_OK;
+
+    QualParams p{};
+    p.quals = d_quals;
+    p.lens = d_lens;
+    p.idx = d_idx;
+    p.n = n;
+    p.stride = stride;
+    p.S = h->cfg.num_samples;
+    p.nwords = nwords;
+    p.min_len = min_len;
+    p.masks = s.d_qmasks;
+    p.counters = h->qual.d_counters;
+    // tile = reads_per_tile quality strings, a multiple of 16 reads so that every tile starts 16-byte aligned
+    uint32_t R = kQualThreads;
+    while (R > 16u && (uint64_t)R * stride > 48u * 1024u) R >>= 1;
+    p.reads_per_tile = R;
+    p.stage_bytes = (R * stride + 16u + 127u) & ~127u;
+    p.stages = 2;
+    const size_t hist_bytes = (size_t)(p.S + 1) * kQualCounters * sizeof(uint32_t);
+    p.smem_hist = hist_bytes <= 48u * 1024u ? 1u : 0u;
+    const size_t nbins = p.smem_hist ? (size_t)(p.S + 1) * kQualCounters : 0;
+    const size_t smem = (size_t)p.stages * p.stage_bytes + (size_t)32 * nwords * 4 + ((nbins + 1) & ~(size_t)1) * 4 + p.stages * 8;
+    auto kern = has_b ? sgdx_qual_counts<true> : sgdx_qual_counts<false>;
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kQualThreads, smem));
+    if (per_sm < 1) return fail(SGDX_EINVAL, "quality-counter kernel does not fit (stride %u, %u samples)", stride, p.S);
+    const uint32_t grid = grid_cap(n, R, h->sms, per_sm);
+    kern<<<grid, kQualThreads, smem, s.stream>>>(p);
+    CU(cudaGetLastError());
+    h->launches.fetch_add(1);
+    return SGDX_OK;
+}
+
+extern "C" int sgdx_base_qual_counters(sgdx_handle *h, sgdx_base_qual *per_sample, uint64_t *short_reads) {
+    if (!h || !per_sample) return fail(SGDX_EINVAL, "sgdx_base_qual_counters: null argument");
+    CU(cudaSetDevice(h->cfg.device));
+    CU(cudaDeviceSynchronize());
+    const uint32_t S = h->cfg.num_samples;
+    std::vector<unsigned long long> raw((size_t)(S + 1) * kQualCounters + 1, 0ull);
+    if (h->qual.d_counters) CU(cudaMemcpy(raw.data(), h->qual.d_counters, raw.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    for (uint32_t b = 0; b <= S; b++) {
+        per_sample[b].q20_bases = raw[(size_t)b * kQualCounters + 0];
+        per_sample[b].q30_bases = raw[(size_t)b * kQualCounters + 1];
+        per_sample[b].index_bases_qual_sum = raw[(size_t)b * kQualCounters + 2];
+        per_sample[b].index_bases_total_seen = raw[(size_t)b * kQualCounters + 3];
+        per_sample[b].bases = raw[(size_t)b * kQualCounters + 4];
+    }
+    if (short_reads) *short_reads = raw.back();
+    return SGDX_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// C ABI: routing
+// ------------------------------------------------------------------------------------------------
+extern "C" int sgdx_route_device(sgdx_handle *h, uint32_t slot, const uint16_t *d_idx, uint64_t n, uint32_t *d_order,
+                                 uint64_t *d_offsets) {
+    if (int rc = check_slot_post(h, slot)) return rc;
+    if (!d_offsets || (n && (!d_idx || !d_order))) return fail(SGDX_EINVAL, "sgdx_route_device: null buffer");
+    if (n >> 32) return fail(SGDX_EINVAL, "sgdx_route_device: %llu reads, at most 2^32 - 1 per call", (unsigned long long)n);
+    CU(cudaSetDevice(h->cfg.device));
+    Slot &s = h->slots[slot];
+    RouteParams p{};
+    p.idx = d_idx;
+    p.n = n;
+    p.bins = h->cfg.num_samples + 1;
+    // one warp per contiguous range of reads; each warp keeps a private row of `bins` counters in shared memory
+    const size_t row_bytes = (size_t)p.bins * sizeof(uint32_t);
+    p.warps = (uint32_t)std::max<size_t>(1, std::min<size_t>(8, (96u * 1024u) / row_bytes));
+    const uint64_t max_ranges = (uint64_t)h->sms * 64u;
+    uint64_t ranges = std::min<uint64_t>(max_ranges, (n + 1023) / 1024);
+    if (ranges == 0) ranges = 1;
+    uint64_t chunk = (n + ranges - 1) / ranges;
+    chunk = (chunk + 31) & ~31ull;
+    if (chunk == 0) chunk = 32;
+    ranges = n ? (n + chunk - 1) / chunk : 1;
+    p.ranges = (uint32_t)ranges;
+    p.chunk = (uint32_t)chunk;
+    const size_t need = ranges * row_bytes + (size_t)p.bins * sizeof(unsigned long long);
+    if (need > s.route_cap) {
+        CU(cudaStreamSynchronize(s.stream));
+        cudaFree(s.d_route);
+        s.d_route = nullptr;
+        s.route_cap = 0;
+        CU(cudaMalloc(&s.d_route, need + need / 4));
+        s.route_cap = need + need / 4;
+    }
+    p.totals = static_cast<unsigned long long *>(s.d_route);  // 8-byte aligned part first
+    p.matrix = reinterpret_cast<uint32_t *>(p.totals + p.bins);
+    p.order = d_order;
+    p.offsets = reinterpret_cast<unsigned long long *>(d_offsets);
+    const size_t smem = (size_t)p.warps * row_bytes;
+    CU(cudaFuncSetAttribute(sgdx_route_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU(cudaFuncSetAttribute(sgdx_route_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const uint32_t grid = (p.ranges + p.warps - 1) / p.warps;
+    sgdx_route_hist<<<grid, p.warps * 32u, smem, s.stream>>>(p);
+    CU(cudaGetLastError());
+    sgdx_route_scan_ranges<<<(p.bins + 127u) / 128u, 128, 0, s.stream>>>(p);
+    CU(cudaGetLastError());
+    sgdx_route_scan_bins<<<1, 1024, 0, s.stream>>>(p);
+    CU(cudaGetLastError());
+    if (n) {
+        sgdx_route_scatter<<<grid, p.warps * 32u, smem, s.stream>>>(p);
+        CU(cudaGetLastError());
+    }
+    h->launches.fetch_add(n ? 4 : 3);
+    return SGDX_OK;
+}

@@ -32,16 +32,29 @@ class BarcodeAssignmentStage:
 
     def __init__(self, samples: Sequence[SampleMetadata], matcher_cls, max_mismatches: int, min_delta: int,
                  free_ns: int, max_no_calls: Optional[int] = None, index_lengths: Optional[Tuple[int, int]] = None,
-                 collect_unmatched: bool = True, device: int = 0, slots: int = 2, kernel: int = 0):
+                 collect_unmatched: bool = True, device: int = 0, slots: int = 2, kernel: int = 0,
+                 unmatched_on_device: bool = False, most_unmatched_max_map_size: int = 5_000_000,
+                 most_unmatched_downsize_to: int = 5_000):
         if len(samples) < 2:
             raise ValueError("need at least one sample plus Undetermined")
         self.samples = list(samples)
         self.undetermined_sample_index = len(samples) - 1
         self.index_lengths = index_lengths
-        self.collect_unmatched = collect_unmatched
+        self.collect_unmatched = collect_unmatched and not unmatched_on_device
+        self.unmatched_on_device = unmatched_on_device
         self.matcher: GpuMatcher = matcher_cls(self.samples[:-1], max_mismatches, min_delta, free_ns,
                                                max_no_calls=max_no_calls, index_lengths=index_lengths,
                                                device=device, slots=slots, kernel=kernel)
+        if unmatched_on_device:  # run.rs:185-190: UnmatchedCounterThread::new(channel, max_map_size, downsize_to)
+            self.matcher.unmatched_enable(most_unmatched_max_map_size, most_unmatched_downsize_to)
+
+    def most_frequent_unmatched(self, n: int = 1000) -> List["BarcodeCount"]:
+        """Rows of most_frequent_unmatched.tsv (metrics.rs:177-190) from the device table; keys in their
+        delimited form (demux.rs:504-522: index segments joined by `+`)."""
+        from .metrics import BarcodeCount
+        i1 = self.index_lengths[0] if self.index_lengths else 0
+        return [BarcodeCount(((k[:i1] + b"+" + k[i1:]) if i1 else k).decode(errors="replace"), c)
+                for k, c in self.matcher.unmatched_top(n)]
 
     def get_undetermined_index(self) -> int:
         return self.undetermined_sample_index

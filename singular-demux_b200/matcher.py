@@ -20,7 +20,7 @@ from typing import Dict, Optional, Sequence, Tuple, Union
 import numpy as np
 
 from . import _lib
-from ._lib import Config, SgdxError, Totals, check, lib
+from ._lib import BaseQual, Config, SgdxError, Totals, UnmatchedInfo, check, lib
 
 UNDETERMINED_NAME = "Undetermined"  # matcher.rs:19
 
@@ -225,6 +225,83 @@ class GpuMatcher:
         w = C.c_uint64(0)
         check(lib().sgdx_hop_export(self._h, keys.ctypes.data, cnt.ctypes.data, max(k, 1), C.byref(w)), "sgdx_hop_export")
         return {keys[i].tobytes(): int(cnt[i]) for i in range(int(w.value))}
+
+
+    # -- most-frequent unmatched barcodes (UnmatchedCounter, metrics.rs:131-190), counted on the device ----
+    def unmatched_enable(self, max_map_size: int = 5_000_000, downsize_to: int = 5_000) -> None:
+        check(lib().sgdx_unmatched_enable(self._h, max_map_size, downsize_to), "sgdx_unmatched_enable")
+
+    def unmatched_info(self) -> Dict[str, int]:
+        i = UnmatchedInfo()
+        check(lib().sgdx_unmatched_info_get(self._h, C.byref(i)), "sgdx_unmatched_info_get")
+        return {"distinct_keys": i.distinct_keys, "unmatched_reads": i.unmatched_reads,
+                "dropped_reads": i.dropped_reads, "downsizes": i.downsizes}
+
+    def _unmatched_pairs(self, fn, what: str, k: int):
+        keys = np.zeros((max(k, 1), self.barcode_len), dtype=np.uint8)
+        cnt = np.zeros(max(k, 1), dtype=np.uint64)
+        w = C.c_uint64(0)
+        check(fn(keys, cnt, w), what)
+        return [(keys[i].tobytes(), int(cnt[i])) for i in range(int(w.value))]
+
+    def unmatched_counts(self) -> Dict[bytes, int]:
+        """Every concatenated unmatched barcode and its count (for merging shards)."""
+        k = self.unmatched_info()["distinct_keys"]
+        return dict(self._unmatched_pairs(
+            lambda keys, cnt, w: lib().sgdx_unmatched_export(self._h, keys.ctypes.data, cnt.ctypes.data, max(k, 1),
+                                                             C.byref(w)), "sgdx_unmatched_export", k))
+
+    def unmatched_top(self, n: int):
+        """The n most frequent (barcode, count) pairs, descending count (to_file, metrics.rs:177-190)."""
+        return self._unmatched_pairs(
+            lambda keys, cnt, w: lib().sgdx_unmatched_top(self._h, n, keys.ctypes.data, cnt.ctypes.data, C.byref(w)),
+            "sgdx_unmatched_top", n)
+
+    def unmatched_downsize(self) -> None:
+        check(lib().sgdx_unmatched_downsize(self._h), "sgdx_unmatched_downsize")
+
+    # -- segment extraction (demux.rs:360-417,504-522) ---------------------------------------------------------
+    def _sources(self, d_base_ptrs: Sequence[int], strides: Sequence[int]):
+        k = len(d_base_ptrs)
+        ptrs = (C.c_void_p * k)(*[C.c_void_p(int(p)) for p in d_base_ptrs])
+        st = (C.c_uint32 * k)(*[int(x) for x in strides])
+        return k, ptrs, st
+
+    def extract_device(self, d_base_ptrs: Sequence[int], strides: Sequence[int], structures, n: int,
+                       d_out_ptr: int, slot: int = 0) -> None:
+        from .read_structure import c_segments
+        k, ptrs, st = self._sources(d_base_ptrs, strides)
+        segs, ns = c_segments(structures)
+        check(lib().sgdx_extract_device(self._h, slot, k, ptrs, st, segs, ns, n, d_out_ptr), "sgdx_extract_device")
+
+    def match_segments_device(self, d_base_ptrs: Sequence[int], strides: Sequence[int], structures, n: int,
+                              d_idx_ptr: int, d_dist_ptr: int = 0, slot: int = 0) -> None:
+        from .read_structure import c_segments
+        k, ptrs, st = self._sources(d_base_ptrs, strides)
+        segs, ns = c_segments(structures)
+        check(lib().sgdx_match_segments_device(self._h, slot, k, ptrs, st, segs, ns, n, d_idx_ptr,
+                                               d_dist_ptr or None), "sgdx_match_segments_device")
+
+    # -- base-quality counters (metrics.rs:499-518, demux.rs:582-583) -------------------------------------------
+    def qual_counts_device(self, d_quals_ptr: int, n: int, stride: int, structure, d_idx_ptr: int,
+                           d_lens_ptr: int = 0, slot: int = 0) -> None:
+        from .read_structure import c_segments
+        segs, ns = c_segments([structure])
+        check(lib().sgdx_qual_counts_device(self._h, slot, d_quals_ptr, n, stride, d_lens_ptr or None, segs, ns,
+                                            d_idx_ptr), "sgdx_qual_counts_device")
+
+    def base_qual_counters(self) -> Tuple[np.ndarray, int]:
+        """[(S+1), 5] = q20_bases, q30_bases, index_bases_qual_sum, index_bases_total_seen, bases; short reads."""
+        arr = (BaseQual * (self.num_samples + 1))()
+        short = C.c_uint64(0)
+        check(lib().sgdx_base_qual_counters(self._h, arr, C.byref(short)), "sgdx_base_qual_counters")
+        out = np.array([[a.q20_bases, a.q30_bases, a.index_bases_qual_sum, a.index_bases_total_seen, a.bases]
+                        for a in arr], dtype=np.uint64)
+        return out, int(short.value)
+
+    # -- read routing (demux.rs:637-645: per_sample_reads) -------------------------------------------------------
+    def route_device(self, d_idx_ptr: int, n: int, d_order_ptr: int, d_offsets_ptr: int, slot: int = 0) -> None:
+        check(lib().sgdx_route_device(self._h, slot, d_idx_ptr, n, d_order_ptr, d_offsets_ptr), "sgdx_route_device")
 
 
 class CachedHammingDistanceMatcher(GpuMatcher):

@@ -3,7 +3,8 @@
   DemuxedGroupSampleMetrics            metrics.rs:407-437
   DemuxedGroupMetrics.update_with      metrics.rs:315-328   (merge by summation: exact under any sharding)
   SampleBarcodeHopTracker              metrics.rs:617-677
-  BarcodeCount / UnmatchedCounter      metrics.rs:131-206   (host-side top-N of unmatched barcodes)
+  BarcodeCount / UnmatchedCounter      metrics.rs:131-206   (host-side merge of the device tables' exports)
+  BaseQualCounter                      metrics.rs:468-497   (filled from sgdx_base_qual_counters)
 The integer columns come from device counters (sgdx_counters / sgdx_hop_export); derived float columns
 are out of scope (written by the host's unchanged TSV writer, metrics.rs:440-465).
 """
@@ -25,6 +26,28 @@ class DemuxedGroupSampleMetrics:
         self.perfect_matches += other.perfect_matches
         self.one_mismatch_matches += other.one_mismatch_matches
         self.total_matches += other.total_matches
+
+
+@dataclass
+class BaseQualCounter:
+    """metrics.rs:468-481; update_with_self = metrics.rs:489-496.  The per-base update (metrics.rs:499-518)
+    runs on the device (sgdx_qual_counts_device)."""
+    q20_bases: int = 0
+    q30_bases: int = 0
+    index_bases_qual_sum: int = 0
+    index_bases_total_seen: int = 0
+    bases: int = 0
+
+    def update_with_self(self, other: "BaseQualCounter") -> None:
+        self.q20_bases += other.q20_bases
+        self.q30_bases += other.q30_bases
+        self.index_bases_qual_sum += other.index_bases_qual_sum
+        self.index_bases_total_seen += other.index_bases_total_seen
+        self.bases += other.bases
+
+    @staticmethod
+    def from_row(row) -> "BaseQualCounter":
+        return BaseQualCounter(*[int(x) for x in row])
 
 
 @dataclass

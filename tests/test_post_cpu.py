@@ -1,0 +1,110 @@
+"""CPU checks of the stages either side of the assignment: the oracle restatements against the reference's own
+known answers, the read-structure mirror, struct layouts of the new C-ABI types."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import sgdx_loader
+from oracle import oracle as orc
+
+sg = sgdx_loader.load()
+RS = sg.ReadStructure.from_str
+
+
+def _segs(rs):
+    return [(g.offset, g.length, g.kind) for g in rs.segments]
+
+
+def test_base_qual_oracle_reproduces_reference_test():
+    """run.rs:1040-1157 (test_demux_filtering...): read structure 17B39T, qualities '?'*17 + bytes 35..73.
+    Expected per read: 39 template bases, 11 with q >= 30, 21 with q >= 20; 4 / 2 / 1 reads kept."""
+    one = [63] * 17 + list(range(35, 74))
+    for reads, (bases, q30, q20) in ((4, (156, 44, 84)), (2, (78, 22, 42)), (1, (39, 11, 21))):
+        q = np.array([one] * reads, dtype=np.uint8)
+        out, short = orc.base_qual_counts(q, None, _segs(RS("17B39T")), np.zeros(reads, dtype=np.uint16), 4)
+        assert (int(out[0, 4]), int(out[0, 1]), int(out[0, 0])) == (bases, q30, q20) and short == 0
+        assert (int(out[0, 2]), int(out[0, 3])) == (30 * 17 * reads, 17 * reads)  # metrics.rs:500-505
+        assert int(out[1:].sum()) == 0
+
+
+def test_base_qual_oracle_segment_kinds_and_wrap():
+    """metrics.rs:499-518: only T adds to bases/q20/q30, only B to the index sums; M and S add nothing.
+    `q - 33` on a u8 wraps for bytes below '!' (release build): 32 -> 255 counts as >= Q30."""
+    q = np.array([[33 + 19, 33 + 20, 33 + 29, 33 + 30, 32, 33 + 40, 33 + 2, 33 + 3]], dtype=np.uint8)
+    out, _ = orc.base_qual_counts(q, None, _segs(RS("5T1M1S1B")), np.array([1], dtype=np.uint16), 2)
+    assert out[1].tolist() == [4, 2, 3, 1, 5]
+    out, short = orc.base_qual_counts(q, np.array([6], dtype=np.uint32), _segs(RS("5T1M+T")), np.array([0], dtype=np.uint16), 2)
+    assert out[0].tolist() == [4, 2, 0, 0, 5] and short == 0        # `+T` is empty at length 6
+    out, short = orc.base_qual_counts(q, np.array([5], dtype=np.uint32), _segs(RS("5T1M+T")), np.array([0], dtype=np.uint16), 2)
+    assert int(out.sum()) == 0 and short == 1                        # shorter than the fixed segments
+
+
+def test_unmatched_literal_reproduces_reference_tests(golden):
+    """run.rs:652-689: three unmatched barcodes, each once; run.rs:1444-1451: the hopped barcode once."""
+    for case in golden["demux_cases"]:
+        if "unmatched" not in case:
+            continue
+        table = [s.encode() for s in case["samples"]]
+        L = len(table[0])
+        il = (case["index1_len"], case["index2_len"]) if case["index1_len"] else (0, 0)
+        for k in case["matchers"]:
+            cfg = orc.Config(len(table), L, case["max_mismatches"], case["min_delta"], case["free_ns"],
+                             -1 if case["max_no_calls"] is None else case["max_no_calls"],
+                             orc.MATCHER_PRECOMPUTE if k == 1 else orc.MATCHER_CACHED_HAMMING, il[0], il[1])
+            res = orc.LiteralDemux(cfg, table).run([r.encode() for r in case["reads"]])
+            c = orc.UnmatchedCounterLiteral()
+            for r, i in zip(case["reads"], res["idx"]):
+                if i == len(table):
+                    c.insert(r.encode())
+            assert {k_.decode(): v for k_, v in c.unmatched_counter.items()} == case["unmatched"]
+            assert len(c.top(1000)) == len(case["unmatched"])
+
+
+def test_unmatched_literal_downsizes_like_the_reference():
+    """metrics.rs:151-175: the map is cut when it already holds max_counter_size keys and one more arrives."""
+    c = orc.UnmatchedCounterLiteral(max_counter_size=4, downsize_to=2)
+    for k in [b"A", b"A", b"A", b"C", b"C", b"G", b"T"]:
+        c.insert(k)
+    assert len(c.unmatched_counter) == 4
+    c.insert(b"A")                      # present already, but the map is full: cut first (reference behaviour)
+    assert c.unmatched_counter == {b"A": 4, b"C": 2}
+    assert c.top(1) == [(b"A", 4)]
+
+
+def test_extract_and_route_oracles():
+    i1 = np.frombuffer(b"AAAACCCC" b"GGGGTTTT", dtype=np.uint8).reshape(2, 8)
+    r1 = np.frombuffer(b"NNACGTxx" b"NNTGCAyy", dtype=np.uint8).reshape(2, 8)
+    got = orc.extract_sample_barcodes([r1, i1], [_segs(RS("2S4B+T")), _segs(RS("8B"))])
+    assert [bytes(r) for r in got] == [b"ACGTAAAACCCC", b"TGCAGGGGTTTT"]  # FASTQ order, then segment order
+    idx = np.array([2, 0, 2, 1, 0, 2], dtype=np.uint16)
+    order, off = orc.route_reads(idx, 2)
+    assert order.tolist() == [1, 4, 3, 0, 2, 5] and off.tolist() == [0, 2, 3, 6]
+
+
+def test_read_structure_mirror():
+    rs = RS("8B+T")
+    assert [(g.offset, g.length, g.kind) for g in rs.segments] == [(0, 8, "B"), (8, None, "T")]
+    assert rs.sample_barcode_length() == 8 and rs.min_length() == 8
+    assert RS("6M+T").sample_barcode_length() == 0
+    assert RS("3b2s4B").sample_barcode_length() == 7
+    for bad in ("", "8", "B8", "+T8B", "0T", "8Q", "8B +T x"):
+        with pytest.raises(ValueError):
+            RS(bad)
+    arr, n = sg.read_structure.c_segments([RS("10B"), RS("4S+T")])
+    assert n == 3 and (arr[2].source, arr[2].offset, arr[2].length, arr[2].kind) == (1, 4, 0xFFFFFFFF, ord("T"))
+
+
+def test_new_struct_layouts_match_header():
+    from singular_demux_b200 import _lib
+    assert C.sizeof(_lib.UnmatchedInfo) == 4 * 8
+    assert C.sizeof(_lib.Segment) == 4 * 4
+    assert C.sizeof(_lib.BaseQual) == 5 * 8
+
+
+def test_post_calls_validate_before_touching_cuda():
+    L = sg.lib()
+    assert L.sgdx_unmatched_enable(None, 0, 0) == -1
+    assert L.sgdx_route_device(None, 0, None, 0, None, None) == -1
+    assert L.sgdx_base_qual_counters(None, None, None) == -1
+    assert L.sgdx_qual_counts_device(None, 0, None, 0, 150, None, None, 0, None) == -1
