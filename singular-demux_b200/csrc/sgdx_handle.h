@@ -43,14 +43,15 @@ struct Slot {
     std::vector<uint32_t> qmasks_key;
 };
 
+struct UnmSlot;
+
 // most-frequent-unmatched collection (sgdx_post.cu); the table lives on the device
 struct UnmatchedState {
     bool on = false;
     uint64_t max_map_size = 0, downsize_to = 0;
     uint64_t cap_slots = 0;   // power of two
     uint64_t key_limit = 0;   // new keys are refused (and counted as dropped) beyond this many
-    ulonglong2 *d_keys = nullptr;
-    unsigned long long *d_counts = nullptr;
+    UnmSlot *d_slots = nullptr;             // 32-byte slots: key + count (sgdx_post.cu)
     unsigned long long *d_stats = nullptr;  // kUnmStats words, see sgdx_post.cu
     uint8_t *d_odd = nullptr;               // barcodes with a byte outside ACGTN, 32 bytes each
     uint64_t odd_cap = 0;

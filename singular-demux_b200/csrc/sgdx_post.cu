@@ -33,10 +33,16 @@ constexpr int kUnmStats = 8;  // [0] distinct keys in the table  [1] NoMatch rea
                               // [3] entries appended to the foreign-byte list  [4] selected entries  [5] tie tickets
 constexpr unsigned long long kEmptyWord = ~0ull;
 constexpr int kUnmHistBins = 4096;
+constexpr unsigned int kUnmPublish = 256;
+
+struct __align__(32) UnmSlot {
+    ulonglong2 key;            // {bases 0..20, bases 21..31 | 1 << 63}; {~0, ~0} = empty
+    unsigned long long count;  // same 32-byte sector as the key: the add after a claim is an L2 hit
+    unsigned long long pad;    // 0xFF.. (never read)
+};
 
 struct UnmTable {
-    ulonglong2 *keys;  // {bases 0..20, bases 21..31 | 1 << 63}; {~0, ~0} = empty
-    unsigned long long *counts;
+    UnmSlot *slots;
     unsigned long long *stats;
     uint64_t mask;       // slots - 1
     uint64_t key_limit;  // no new keys once stats[0] reaches this
@@ -58,34 +64,37 @@ __device__ __forceinline__ ulonglong2 cas128(ulonglong2 *addr, ulonglong2 cmp, u
 __device__ __forceinline__ uint64_t unm_hash(uint64_t k0, uint64_t k1) { return mix64(k0 ^ mix64(k1 + 0x9E3779B97F4A7C15ull)); }
 
 // count[key] += add; a new key claims the first empty slot of its probe sequence with one 128-bit CAS (the CAS is
-// also the read: a plain 128-bit load may be torn against a concurrent claim).  false = table full, not counted.
-__device__ __forceinline__ bool unm_add(const UnmTable &t, uint64_t k0, uint64_t k1, unsigned long long add) {
+// also the read: a plain 128-bit load may be torn against a concurrent claim).  `full`: the table may not take new
+// keys (then the CAS compares and swaps empty for empty: an atomic read).  0 = not counted (table full),
+// 1 = counted, 2 = counted and the key is new.
+__device__ __forceinline__ uint32_t unm_add(const UnmTable &t, uint64_t k0, uint64_t k1, unsigned long long add,
+                                            bool full) {
     const ulonglong2 empty = make_ulonglong2(kEmptyWord, kEmptyWord), key = make_ulonglong2(k0, k1);
     uint64_t i = unm_hash(k0, k1) & t.mask;
     for (uint64_t probe = 0; probe <= t.mask; probe++) {
-        const bool full = *reinterpret_cast<volatile unsigned long long *>(t.stats) >= t.key_limit;
-        const ulonglong2 old = cas128(t.keys + i, empty, full ? empty : key);
+        const ulonglong2 old = cas128(&t.slots[i].key, empty, full ? empty : key);
         if (old.x == kEmptyWord && old.y == kEmptyWord) {
-            if (full) return false;  // the key is not in the table (no deletions) and may not enter it
-            atomicAdd(t.stats + 0, 1ull);
-            atomicAdd(t.counts + i, add);
-            return true;
+            if (full) return 0u;  // the key is not in the table (no deletions) and may not enter it
+            atomicAdd(&t.slots[i].count, add + 1ull);  // an empty slot's count is ~0 (memset 0xFF)
+            return 2u;
         }
         if (old.x == k0 && old.y == k1) {
-            atomicAdd(t.counts + i, add);
-            return true;
+            atomicAdd(&t.slots[i].count, add);
+            return 1u;
         }
         i = (i + 1) & t.mask;
     }
-    return false;
+    return 0u;
 }
 
 // one thread per read: NoMatch reads (idx == S) are keyed and counted (demux.rs:553-555)
 __global__ void __launch_bounds__(256) sgdx_unmatched_count(const uint8_t *__restrict__ reads,
                                                             const uint16_t *__restrict__ idx, uint64_t n, uint32_t S,
                                                             uint32_t L, const UnmTable t) {
-    __shared__ unsigned int s_seen, s_drop;
-    if (threadIdx.x == 0) s_seen = s_drop = 0u;
+    // the number of distinct keys is published in steps of kUnmPublish per CTA (one global atomic per step instead
+    // of one per key on a single word); the key limit is therefore enforced to within gridDim.x * kUnmPublish keys
+    __shared__ unsigned int s_seen, s_drop, s_new;
+    if (threadIdx.x == 0) s_seen = s_drop = s_new = 0u;
     __syncthreads();
     for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (uint64_t)gridDim.x * blockDim.x) {
         if (idx[r] != S) continue;
@@ -102,7 +111,10 @@ __global__ void __launch_bounds__(256) sgdx_unmatched_count(const uint8_t *__res
         atomicAdd(&s_seen, 1u);
         bool ok;
         if (!odd) {
-            ok = unm_add(t, k0, k1, 1ull);
+            const bool full = *reinterpret_cast<volatile unsigned long long *>(t.stats) >= t.key_limit;
+            const uint32_t how = unm_add(t, k0, k1, 1ull, full);
+            ok = how != 0u;
+            if (how == 2u && (atomicAdd(&s_new, 1u) + 1u) % kUnmPublish == 0u) atomicAdd(t.stats + 0, (unsigned long long)kUnmPublish);
         } else {  // a byte outside ACGTN: keep the bytes themselves, the host counts these
             const unsigned long long at = atomicAdd(t.stats + 3, 1ull);
             ok = at < t.odd_cap;
@@ -115,19 +127,19 @@ __global__ void __launch_bounds__(256) sgdx_unmatched_count(const uint8_t *__res
     if (threadIdx.x == 0) {
         if (s_seen) atomicAdd(t.stats + 1, (unsigned long long)s_seen);
         if (s_drop) atomicAdd(t.stats + 2, (unsigned long long)s_drop);
+        if (s_new % kUnmPublish) atomicAdd(t.stats + 0, (unsigned long long)(s_new % kUnmPublish));
     }
 }
 
 // histogram of min(count, kUnmHistBins-1) over the occupied slots
-__global__ void __launch_bounds__(256) sgdx_unmatched_hist(const ulonglong2 *__restrict__ keys,
-                                                           const unsigned long long *__restrict__ counts, uint64_t slots,
+__global__ void __launch_bounds__(256) sgdx_unmatched_hist(const UnmSlot *__restrict__ tab, uint64_t slots,
                                                            unsigned long long *__restrict__ hist) {
     __shared__ unsigned int sh[kUnmHistBins];
     for (uint32_t i = threadIdx.x; i < kUnmHistBins; i += blockDim.x) sh[i] = 0u;
     __syncthreads();
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < slots; i += (uint64_t)gridDim.x * blockDim.x) {
-        if (keys[i].x == kEmptyWord) continue;
-        const unsigned long long c = counts[i];
+        if (tab[i].key.x == kEmptyWord) continue;
+        const unsigned long long c = tab[i].count;
         atomicAdd(&sh[c < (unsigned long long)(kUnmHistBins - 1) ? (uint32_t)c : (uint32_t)(kUnmHistBins - 1)], 1u);
     }
     __syncthreads();
@@ -136,16 +148,15 @@ __global__ void __launch_bounds__(256) sgdx_unmatched_hist(const ulonglong2 *__r
 }
 
 // entries with count > t, plus up to `quota` entries with count == t, compacted into out_*
-__global__ void __launch_bounds__(256) sgdx_unmatched_select(const ulonglong2 *__restrict__ keys,
-                                                             const unsigned long long *__restrict__ counts,
+__global__ void __launch_bounds__(256) sgdx_unmatched_select(const UnmSlot *__restrict__ tab,
                                                              uint64_t slots, unsigned long long t,
                                                              unsigned long long quota, ulonglong2 *__restrict__ out_keys,
                                                              unsigned long long *__restrict__ out_counts,
                                                              uint64_t out_cap, unsigned long long *__restrict__ stats) {
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < slots; i += (uint64_t)gridDim.x * blockDim.x) {
-        const ulonglong2 k = keys[i];
+        const ulonglong2 k = tab[i].key;
         if (k.x == kEmptyWord) continue;
-        const unsigned long long c = counts[i];
+        const unsigned long long c = tab[i].count;
         bool take = c > t;
         if (c == t && quota) take = atomicAdd(stats + 5, 1ull) < quota;
         if (!take) continue;
@@ -160,8 +171,10 @@ __global__ void __launch_bounds__(256) sgdx_unmatched_select(const ulonglong2 *_
 __global__ void __launch_bounds__(256) sgdx_unmatched_reinsert(const ulonglong2 *__restrict__ sel_keys,
                                                                const unsigned long long *__restrict__ sel_counts,
                                                                uint64_t n, const UnmTable t) {
+    unsigned int fresh = 0;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
-        unm_add(t, sel_keys[i].x, sel_keys[i].y, sel_counts[i]);
+        fresh += unm_add(t, sel_keys[i].x, sel_keys[i].y, sel_counts[i], false) == 2u;
+    if (fresh) atomicAdd(t.stats + 0, (unsigned long long)fresh);
 }
 
 // ================================================================================================
@@ -181,10 +194,14 @@ constexpr uint32_t kExtractTileReads = 1024;
 
 // One thread per output word: four gathered bytes, one coalesced 32-bit store.
 __global__ void __launch_bounds__(256) sgdx_extract(const ExtractParams p) {
-    __shared__ uint32_t s_src[SGDX_MAX_BARCODE_LEN], s_off[SGDX_MAX_BARCODE_LEN];
+    // per barcode position: where its byte lives in read 0 of its source, and that source's stride (an indexed
+    // kernel parameter would go through the address-divergence unit on every byte)
+    __shared__ const uint8_t *s_ptr[SGDX_MAX_BARCODE_LEN];
+    __shared__ uint32_t s_stride[SGDX_MAX_BARCODE_LEN];
     if (threadIdx.x < p.L) {
-        s_src[threadIdx.x] = p.pos_src[threadIdx.x];
-        s_off[threadIdx.x] = p.pos_off[threadIdx.x];
+        const uint32_t src = p.pos_src[threadIdx.x];
+        s_ptr[threadIdx.x] = p.src[src] + p.pos_off[threadIdx.x];
+        s_stride[threadIdx.x] = p.stride[src];
     }
     __syncthreads();
     const uint64_t ntiles = (p.n + kExtractTileReads - 1) / kExtractTileReads;
@@ -200,8 +217,7 @@ __global__ void __launch_bounds__(256) sgdx_extract(const ExtractParams p) {
                 const uint32_t ob = o + b;
                 const uint32_t rl = __umulhi(ob, p.magic);  // ob / L: exact for ob * L < 2^32
                 const uint32_t j = ob - rl * p.L;
-                const uint32_t s = s_src[j];
-                const uint32_t c = __ldg(p.src[s] + (first + rl) * (uint64_t)p.stride[s] + s_off[j]);
+                const uint32_t c = __ldg(s_ptr[j] + (first + rl) * (uint64_t)s_stride[j]);
                 w |= c << (8u * b);
             }
             if (nb == 4u && p.words_ok) *reinterpret_cast<uint32_t *>(out + o) = w;
@@ -228,6 +244,8 @@ struct QualParams {
     uint32_t stages;
     uint32_t nwords;          // words per shifted mask
     uint32_t min_len;         // a shorter read cannot be cut into the fixed segments
+    uint32_t one;             // 1 (see add_fma)
+    uint32_t t_tail;          // positions t_tail .. stride-1 are all template bases (stride if the last one is not)
     uint32_t smem_hist;       // per-CTA histogram in shared memory (else global atomics)
     const uint32_t *masks;    // [2][16][nwords]: template / sample-barcode position bits, shifted left by 0..15
     unsigned long long *counters;  // [(S+1)][5], then 1 word: short reads
@@ -255,6 +273,21 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
                      smem_u32(dst)),
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
+}
+
+// a + k on the fma pipe (IMAD): the alu pipe carries the LOP3 / LEA.HI of the counting loop
+// (`one` is a kernel parameter holding 1: a literal multiplier would be folded back into an alu-pipe add)
+__device__ __forceinline__ uint32_t add_fma(uint32_t a, uint32_t one, uint32_t k) {
+    uint32_t r;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(one), "r"(k));
+    return r;
+}
+
+// x & 0x80808080, opaque to the optimiser so that `acc += top_bits(..) >> 7` stays one LEA.HI
+__device__ __forceinline__ uint32_t top_bits(uint32_t x) {
+    uint32_t r;
+    asm("and.b32 %0, %1, 0x80808080;" : "=r"(r) : "r"(x));
+    return r;
 }
 
 __device__ __forceinline__ uint32_t lanes8_sum(uint32_t acc) {  // sum of the four byte lanes
@@ -337,72 +370,104 @@ __global__ void __launch_bounds__(kQualThreads) sgdx_qual_counts(const QualParam
                 const uint32_t end = a + len, nchunks = (end + 15u) >> 4;
                 uint32_t acc20 = 0, acc30 = 0, c20 = 0, c30 = 0, nT = 0;   // template bases
                 uint32_t bacc = 0, bsum = 0, nB = 0, nBfast = 0;            // sample-barcode bases
-                for (uint32_t k = 0; k < nchunks; k++) {
+                auto drain = [&]() {  // byte lanes hold <= 64, 16-bit lanes <= 16 256 after 16 chunks
+                    c20 += lanes8_sum(acc20);
+                    c30 += lanes8_sum(acc30);
+                    bsum += (bacc & 0xFFFFu) + (bacc >> 16);
+                    acc20 = acc30 = bacc = 0u;
+                };
+                // a byte outside 33..127 in the chunk: exact u8 arithmetic, byte by byte
+                auto slow_chunk = [&](const uint32_t (&x)[4], uint32_t m, uint32_t mb) {
+#pragma unroll 1
+                    for (uint32_t j = 0; j < 16u; j++) {
+                        const uint32_t xw = j < 8u ? (j < 4u ? x[0] : x[1]) : (j < 12u ? x[2] : x[3]);
+                        const uint32_t q = (((xw >> (8u * (j & 3u))) & 0xFFu) - 33u) & 0xFFu;
+                        if ((m >> j) & 1u) {
+                            c20 += q >= 20u;
+                            c30 += q >= 30u;
+                            nT++;
+                        }
+                        if ((mb >> j) & 1u) {
+                            bsum += q;
+                            nB++;
+                        }
+                    }
+                };
+                // any chunk: position masks from the read structure, trimmed to the read's own length
+                auto general_chunk = [&](uint32_t k) {
                     const uint32_t sh = (k & 1u) * 16u;
                     uint32_t m = (tm[k >> 1] >> sh) & 0xFFFFu;
                     uint32_t mb = HAS_B ? (bm[k >> 1] >> sh) & 0xFFFFu : 0u;
                     const uint32_t rem = end - 16u * k;
-                    if (rem < 16u) {  // bytes past the read's own length
+                    if (rem < 16u) {
                         const uint32_t lm = (1u << rem) - 1u;
                         m &= lm;
                         mb &= lm;
                     }
-                    if ((m | mb) != 0u) {
+                    if ((m | mb) == 0u) return;
+                    const uint4 v = chunks[k];
+                    const uint32_t x[4] = {v.x, v.y, v.z, v.w};
+                    // every byte in 33..127 <=> no 0x80 bit in (x - 0x21..) | x (a borrow only starts at an
+                    // offending byte, which flags itself)
+                    uint32_t flag = 0;
+#pragma unroll
+                    for (int w = 0; w < 4; w++) flag |= (x[w] - 0x21212121u) | x[w];
+                    if (flag & 0x80808080u) {
+                        slow_chunk(x, m, mb);
+                        return;
+                    }
+                    if (m) {  // q >= 20 <=> byte + (128 - 53) carries into bit 7; no carry leaves a byte
+#pragma unroll
+                        for (int w = 0; w < 4; w++) {
+                            const uint32_t t80 = (((m >> (4 * w)) & 15u) * 0x10204080u) & 0x80808080u;
+                            acc20 += ((x[w] + 0x4B4B4B4Bu) & t80) >> 7;
+                            acc30 += ((x[w] + 0x41414141u) & t80) >> 7;
+                        }
+                        nT += __popc(m);
+                    }
+                    if (HAS_B && mb) {
+#pragma unroll
+                        for (int w = 0; w < 4; w++) {
+                            const uint32_t ff = ((((mb >> (4 * w)) & 15u) * 0x00204081u) & 0x01010101u) * 0xFFu;
+                            const uint32_t xb = x[w] & ff;
+                            bacc += (xb & 0x00FF00FFu) + ((xb >> 8) & 0x00FF00FFu);
+                        }
+                        nBfast += __popc(mb);
+                    }
+                };
+                // chunks [k_lo, k_hi) hold template bases only (the structure ends in a run of T from position
+                // t_tail on, and the chunk lies inside the read): no masks
+                const uint32_t k_lo = min((p.t_tail + a + 15u) >> 4, nchunks), k_hi = max(end >> 4, k_lo);
+                for (uint32_t k = 0; k < k_lo; k++) {
+                    general_chunk(k);
+                    if ((k & 15u) == 15u) drain();
+                }
+                drain();
+                for (uint32_t k0 = k_lo; k0 < k_hi; k0 += 16u) {
+                    const uint32_t k1 = min(k0 + 16u, k_hi);
+#pragma unroll 2
+                    for (uint32_t k = k0; k < k1; k++) {
                         const uint4 v = chunks[k];
                         const uint32_t x[4] = {v.x, v.y, v.z, v.w};
-                        // every byte in 33..127 <=> no 0x80 bit in (x - 0x21..) | x (a borrow only starts at an
-                        // offending byte, which flags itself)
                         uint32_t flag = 0;
 #pragma unroll
                         for (int w = 0; w < 4; w++) flag |= (x[w] - 0x21212121u) | x[w];
-                        if ((flag & 0x80808080u) == 0u) {
-                            // q >= 20 <=> byte + (128 - 53) carries into bit 7; no carry leaves a byte
-                            if (m == 0xFFFFu) {
+                        if (flag & 0x80808080u) {
+                            slow_chunk(x, 0xFFFFu, 0u);
+                        } else {
 #pragma unroll
-                                for (int w = 0; w < 4; w++) {
-                                    acc20 += ((x[w] + 0x4B4B4B4Bu) & 0x80808080u) >> 7;
-                                    acc30 += ((x[w] + 0x41414141u) & 0x80808080u) >> 7;
-                                }
-                                nT += 16u;
-                            } else if (m) {
-#pragma unroll
-                                for (int w = 0; w < 4; w++) {
-                                    const uint32_t t80 = (((m >> (4 * w)) & 15u) * 0x10204080u) & 0x80808080u;
-                                    acc20 += ((x[w] + 0x4B4B4B4Bu) & t80) >> 7;
-                                    acc30 += ((x[w] + 0x41414141u) & t80) >> 7;
-                                }
-                                nT += __popc(m);
+                            for (int w = 0; w < 4; w++) {
+                                acc20 += top_bits(add_fma(x[w], p.one, 0x4B4B4B4Bu)) >> 7;  // IMAD, LOP3, LEA.HI
+                                acc30 += top_bits(add_fma(x[w], p.one, 0x41414141u)) >> 7;
                             }
-                            if (HAS_B && mb) {
-#pragma unroll
-                                for (int w = 0; w < 4; w++) {
-                                    const uint32_t ff = ((((mb >> (4 * w)) & 15u) * 0x00204081u) & 0x01010101u) * 0xFFu;
-                                    const uint32_t xb = x[w] & ff;
-                                    bacc += (xb & 0x00FF00FFu) + ((xb >> 8) & 0x00FF00FFu);
-                                }
-                                nBfast += __popc(mb);
-                            }
-                        } else {  // a byte outside 33..127 in the chunk: exact u8 arithmetic, byte by byte
-                            for (uint32_t j = 0; j < 16u; j++) {
-                                const uint32_t q = (((x[j >> 2] >> (8u * (j & 3u))) & 0xFFu) - 33u) & 0xFFu;
-                                if ((m >> j) & 1u) {
-                                    c20 += q >= 20u;
-                                    c30 += q >= 30u;
-                                    nT++;
-                                }
-                                if ((mb >> j) & 1u) {
-                                    bsum += q;
-                                    nB++;
-                                }
-                            }
+                            nT += 16u;
                         }
                     }
-                    if ((k & 15u) == 15u) {  // byte lanes hold <= 64, 16-bit lanes <= 16 256
-                        c20 += lanes8_sum(acc20);
-                        c30 += lanes8_sum(acc30);
-                        bsum += (bacc & 0xFFFFu) + (bacc >> 16);
-                        acc20 = acc30 = bacc = 0u;
-                    }
+                    drain();
+                }
+                for (uint32_t k = k_hi; k < nchunks; k++) {
+                    general_chunk(k);
+                    if ((k & 15u) == 15u) drain();
                 }
                 c20 += lanes8_sum(acc20);
                 c30 += lanes8_sum(acc30);
@@ -457,6 +522,7 @@ __global__ void sgdx_route_hist(const RouteParams p) {
     for (uint32_t b = lane; b < p.bins; b += 32u) h[b] = 0u;
     __syncwarp();
     const uint64_t lo = (uint64_t)range * p.chunk, hi = min(p.n, lo + p.chunk);
+#pragma unroll 4
     for (uint64_t r = lo + lane; r < hi; r += 32u) {
         const uint32_t b = min((uint32_t)__ldg(p.idx + r), p.bins - 1u);
         atomicAdd(h + b, 1u);
@@ -466,18 +532,33 @@ __global__ void sgdx_route_hist(const RouteParams p) {
     for (uint32_t b = lane; b < p.bins; b += 32u) row[b] = h[b];
 }
 
-// column b of the matrix becomes its exclusive prefix over the ranges; totals[b] = column sum
-__global__ void __launch_bounds__(128) sgdx_route_scan_ranges(const RouteParams p) {
-    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+// column b of the matrix becomes its exclusive prefix over the ranges; totals[b] = column sum.  One warp per bin,
+// lanes stride over the ranges, shuffle scan with a running carry.
+__global__ void __launch_bounds__(256) sgdx_route_scan_ranges(const RouteParams p) {
+    const uint32_t b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
     if (b >= p.bins) return;
-    uint32_t run = 0;
-#pragma unroll 8
-    for (uint32_t t = 0; t < p.ranges; t++) {
-        const uint32_t c = p.matrix[(size_t)t * p.bins + b];
-        p.matrix[(size_t)t * p.bins + b] = run;
-        run += c;
+    uint32_t carry = 0;
+    for (uint32_t t0 = 0; t0 < p.ranges; t0 += 128u) {
+        uint32_t c[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {  // independent strided loads first, then the four shuffle scans
+            const uint32_t t = t0 + 32u * j + lane;
+            c[j] = t < p.ranges ? p.matrix[(size_t)t * p.bins + b] : 0u;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const uint32_t t = t0 + 32u * j + lane;
+            uint32_t incl = c[j];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t up = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+                if (lane >= (uint32_t)d) incl += up;
+            }
+            if (t < p.ranges) p.matrix[(size_t)t * p.bins + b] = carry + incl - c[j];
+            carry += __shfl_sync(0xFFFFFFFFu, incl, 31);
+        }
     }
-    p.totals[b] = run;
+    if (lane == 0) p.totals[b] = carry;
 }
 
 // one CTA: exclusive scan of the bin totals -> offsets[0..bins], totals[] := bin bases
@@ -519,20 +600,29 @@ __global__ void sgdx_route_scatter(const RouteParams p) {
     __syncwarp();
     const uint64_t lo = (uint64_t)range * p.chunk, hi = min(p.n, lo + p.chunk);
     const uint32_t lt = (1u << lane) - 1u;
-    for (uint64_t base = lo; base < hi; base += 32u) {
-        const uint64_t r = base + lane;
-        const bool active = r < hi;
-        const uint32_t b = active ? min((uint32_t)__ldg(p.idx + r), p.bins - 1u) : 0xFFFFFFFFu;
-        const uint32_t peers = __match_any_sync(0xFFFFFFFFu, b);
-        const uint32_t rank = __popc(peers & lt);
-        uint32_t at = 0;
-        if (active && rank == 0u) {  // lowest lane of each bin group advances the bin's cursor
-            at = cur[b];
-            cur[b] = at + __popc(peers);
+    for (uint64_t base = lo; base < hi; base += 128u) {
+        uint32_t bb[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {  // four independent loads in flight per lane
+            const uint64_t r = base + 32u * j + lane;
+            bb[j] = r < hi ? min((uint32_t)__ldg(p.idx + r), p.bins - 1u) : 0xFFFFFFFFu;
         }
-        at = __shfl_sync(0xFFFFFFFFu, at, __ffs(peers) - 1);
-        if (active) p.order[at + rank] = (uint32_t)r;
-        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const uint64_t r = base + 32u * j + lane;
+            const uint32_t b = bb[j];
+            const bool active = b != 0xFFFFFFFFu;
+            const uint32_t peers = __match_any_sync(0xFFFFFFFFu, b);
+            const uint32_t rank = __popc(peers & lt);
+            uint32_t at = 0;
+            if (active && rank == 0u) {  // lowest lane of each bin group advances the bin's cursor
+                at = cur[b];
+                cur[b] = at + __popc(peers);
+            }
+            at = __shfl_sync(0xFFFFFFFFu, at, __ffs(peers) - 1);
+            if (active) p.order[at + rank] = (uint32_t)r;
+            __syncwarp();
+        }
     }
 }
 
@@ -541,8 +631,7 @@ __global__ void sgdx_route_scatter(const RouteParams p) {
 // ================================================================================================
 static UnmTable unm_table(const UnmatchedState &u) {
     UnmTable t;
-    t.keys = u.d_keys;
-    t.counts = u.d_counts;
+    t.slots = u.d_slots;
     t.stats = u.d_stats;
     t.mask = u.cap_slots - 1;
     t.key_limit = u.key_limit;
@@ -609,7 +698,7 @@ static int unm_select_top(sgdx_handle *h, uint64_t want, std::vector<ulonglong2>
     uint64_t need = distinct;
     if (want < distinct) {
         CU(cudaMemset(u.d_hist, 0, kUnmHistBins * sizeof(unsigned long long)));
-        sgdx_unmatched_hist<<<grid_cap(u.cap_slots, 256, h->sms, 8), 256>>>(u.d_keys, u.d_counts, u.cap_slots, u.d_hist);
+        sgdx_unmatched_hist<<<grid_cap(u.cap_slots, 256, h->sms, 8), 256>>>(u.d_slots, u.cap_slots, u.d_hist);
         CU(cudaGetLastError());
         std::vector<unsigned long long> hist(kUnmHistBins);
         CU(cudaMemcpy(hist.data(), u.d_hist, hist.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
@@ -641,7 +730,7 @@ static int unm_select_top(sgdx_handle *h, uint64_t want, std::vector<ulonglong2>
         u.sel_cap = need;
     }
     CU(cudaMemset(u.d_stats + 4, 0, 2 * sizeof(unsigned long long)));
-    sgdx_unmatched_select<<<grid_cap(u.cap_slots, 256, h->sms, 8), 256>>>(u.d_keys, u.d_counts, u.cap_slots, t, quota,
+    sgdx_unmatched_select<<<grid_cap(u.cap_slots, 256, h->sms, 8), 256>>>(u.d_slots, u.cap_slots, t, quota,
                                                                           u.d_sel_keys, u.d_sel_counts, u.sel_cap,
                                                                           u.d_stats);
     CU(cudaGetLastError());
@@ -704,8 +793,7 @@ static int unm_downsize_locked(sgdx_handle *h) {
         }
     }
     u.odd.swap(odd);
-    CU(cudaMemset(u.d_keys, 0xFF, u.cap_slots * sizeof(ulonglong2)));
-    CU(cudaMemset(u.d_counts, 0, u.cap_slots * sizeof(unsigned long long)));
+    CU(cudaMemset(u.d_slots, 0xFF, u.cap_slots * sizeof(UnmSlot)));
     CU(cudaMemset(u.d_stats, 0, sizeof(unsigned long long)));  // distinct; the read totals stay
     if (!keys.empty()) {
         if (keys.size() > u.sel_cap) return fail(SGDX_ESTATE, "unmatched downsize: selection scratch too small");
@@ -740,8 +828,7 @@ int post_reset(sgdx_handle *h) {
     if (h->qual.d_counters) CU(cudaMemset(h->qual.d_counters, 0, ((size_t)(S + 1) * kQualCounters + 1) * sizeof(unsigned long long)));
     UnmatchedState &u = h->unm;
     if (u.on) {
-        CU(cudaMemset(u.d_keys, 0xFF, u.cap_slots * sizeof(ulonglong2)));
-        CU(cudaMemset(u.d_counts, 0, u.cap_slots * sizeof(unsigned long long)));
+        CU(cudaMemset(u.d_slots, 0xFF, u.cap_slots * sizeof(UnmSlot)));
         CU(cudaMemset(u.d_stats, 0, kUnmStats * sizeof(unsigned long long)));
         u.odd.clear();
         u.downsizes = 0;
@@ -751,8 +838,7 @@ int post_reset(sgdx_handle *h) {
 
 void post_destroy(sgdx_handle *h) {
     UnmatchedState &u = h->unm;
-    cudaFree(u.d_keys);
-    cudaFree(u.d_counts);
+    cudaFree(u.d_slots);
     cudaFree(u.d_stats);
     cudaFree(u.d_odd);
     cudaFree(u.d_sel_keys);
@@ -780,19 +866,17 @@ extern "C" int sgdx_unmatched_enable(sgdx_handle *h, uint64_t max_map_size, uint
     UnmatchedState &u = h->unm;
     u.max_map_size = max_map_size;
     u.downsize_to = downsize_to;
-    // room for a batch's worth of new keys between two syncs: 4x the limit, at least 2^16 slots
-    uint64_t cap = 1ull << 16;
+    // room for a batch's worth of new keys between two syncs: 4x the limit, at least 2^21 slots (64 MB)
+    uint64_t cap = 1ull << 21;  // key_limit must stay above the publishing lag of the distinct-key count
     while (cap < 4 * max_map_size) cap <<= 1;
     u.cap_slots = cap;
     u.key_limit = cap / 4 * 3;
     u.odd_cap = 1ull << 20;
-    CU(cudaMalloc(&u.d_keys, cap * sizeof(ulonglong2)));
-    CU(cudaMalloc(&u.d_counts, cap * sizeof(unsigned long long)));
+    CU(cudaMalloc(&u.d_slots, cap * sizeof(UnmSlot)));
     CU(cudaMalloc(&u.d_stats, kUnmStats * sizeof(unsigned long long)));
     CU(cudaMalloc(&u.d_odd, u.odd_cap * 32u));
     CU(cudaMalloc(&u.d_hist, kUnmHistBins * sizeof(unsigned long long)));
-    CU(cudaMemset(u.d_keys, 0xFF, cap * sizeof(ulonglong2)));
-    CU(cudaMemset(u.d_counts, 0, cap * sizeof(unsigned long long)));
+    CU(cudaMemset(u.d_slots, 0xFF, cap * sizeof(UnmSlot)));
     CU(cudaMemset(u.d_stats, 0, kUnmStats * sizeof(unsigned long long)));
     CU(cudaDeviceSynchronize());
     u.on = true;
@@ -1018,6 +1102,9 @@ extern "C" int sgdx_qual_counts_device(sgdx_handle *h, uint32_t slot, const uint
     p.S = h->cfg.num_samples;
     p.nwords = nwords;
     p.min_len = min_len;
+    p.one = 1u;
+    p.t_tail = stride;
+    while (p.t_tail > 0 && kind[p.t_tail - 1] == SGDX_SEG_TEMPLATE) p.t_tail--;
     p.masks = s.d_qmasks;
     p.counters = h->qual.d_counters;
     // tile = reads_per_tile quality strings, a multiple of 16 reads so that every tile starts 16-byte aligned
@@ -1077,7 +1164,8 @@ extern "C" int sgdx_route_device(sgdx_handle *h, uint32_t slot, const uint16_t *
     // one warp per contiguous range of reads; each warp keeps a private row of `bins` counters in shared memory
     const size_t row_bytes = (size_t)p.bins * sizeof(uint32_t);
     p.warps = (uint32_t)std::max<size_t>(1, std::min<size_t>(8, (96u * 1024u) / row_bytes));
-    const uint64_t max_ranges = (uint64_t)h->sms * 64u;
+    // few enough ranges that the (ranges x bins) offset matrix stays small next to the index array itself
+    const uint64_t max_ranges = (uint64_t)h->sms * 16u;
     uint64_t ranges = std::min<uint64_t>(max_ranges, (n + 1023) / 1024);
     if (ranges == 0) ranges = 1;
     uint64_t chunk = (n + ranges - 1) / ranges;
@@ -1105,7 +1193,7 @@ extern "C" int sgdx_route_device(sgdx_handle *h, uint32_t slot, const uint16_t *
     const uint32_t grid = (p.ranges + p.warps - 1) / p.warps;
     sgdx_route_hist<<<grid, p.warps * 32u, smem, s.stream>>>(p);
     CU(cudaGetLastError());
-    sgdx_route_scan_ranges<<<(p.bins + 127u) / 128u, 128, 0, s.stream>>>(p);
+    sgdx_route_scan_ranges<<<(p.bins + 7u) / 8u, 256, 0, s.stream>>>(p);
     CU(cudaGetLastError());
     sgdx_route_scan_bins<<<1, 1024, 0, s.stream>>>(p);
     CU(cudaGetLastError());
