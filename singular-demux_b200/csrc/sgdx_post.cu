@@ -36,7 +36,8 @@ constexpr int kUnmHistBins = 4096;
 constexpr unsigned int kUnmPublish = 256;
 
 struct __align__(32) UnmSlot {
-    ulonglong2 key;            // {bases 0..20, bases 21..31 | 1 << 63}; {~0, ~0} = empty
+    ulonglong2 key;            // 96-bit string, base j = 3 bits at 3j (A0 C1 T2 G3 N7): {bits 0..63, bits 64..95 | 1 << 63};
+                               // {~0, ~0} = empty
     unsigned long long count;  // same 32-byte sector as the key: the add after a claim is an L2 hit
     unsigned long long pad;    // 0xFF.. (never read)
 };
@@ -87,43 +88,91 @@ __device__ __forceinline__ uint32_t unm_add(const UnmTable &t, uint64_t k0, uint
     return 0u;
 }
 
-// one thread per read: NoMatch reads (idx == S) are keyed and counted (demux.rs:553-555)
+// four ASCII bases -> four 3-bit codes packed into 12 bits (A0 C1 T2 G3 N7, base k at bit 3k); odd |= a byte that
+// is none of ACGTN
+__device__ __forceinline__ uint32_t key_word(uint32_t w, uint32_t &odd) {
+    const uint32_t c = (w >> 1) & 0x03030303u;
+    const uint32_t y = c | (c >> 4);
+    const uint32_t x = w ^ __byte_perm(0x47544341u, 0u, __byte_perm(y, 0u, 0x4420));  // zero byte <=> "ACTG"[code]
+    const uint32_t bad = (((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x) & 0x80808080u;
+    const uint32_t nfl = zero_bytes(w ^ 0x4E4E4E4Eu);                                  // 0x80 where the byte is 'N'
+    odd |= bad & ~nfl;
+    const uint32_t c3 = c | (nfl >> 5);
+    const uint32_t t = c3 | (c3 >> 5);
+    return (t & 0x3Fu) | ((t >> 10) & 0xFC0u);
+}
+
+constexpr uint32_t kUnmTile = 2048;  // reads per CTA step
+
+// NoMatch reads (idx == S) are keyed and counted (demux.rs:553-555).  Two phases per tile so that the rare work
+// runs in full warps: every thread tests eight index entries and queues the NoMatch ones in shared memory; then
+// the CTA walks the queue, one thread per queued read (word loads, SWAR key, one 128-bit CAS + one add).
 __global__ void __launch_bounds__(256) sgdx_unmatched_count(const uint8_t *__restrict__ reads,
                                                             const uint16_t *__restrict__ idx, uint64_t n, uint32_t S,
                                                             uint32_t L, const UnmTable t) {
     // the number of distinct keys is published in steps of kUnmPublish per CTA (one global atomic per step instead
     // of one per key on a single word); the key limit is therefore enforced to within gridDim.x * kUnmPublish keys
-    __shared__ unsigned int s_seen, s_drop, s_new;
-    if (threadIdx.x == 0) s_seen = s_drop = s_new = 0u;
+    __shared__ unsigned int s_seen, s_drop, s_new, s_qn;
+    __shared__ uint16_t s_queue[kUnmTile];
+    if (threadIdx.x == 0) s_seen = s_drop = s_new = s_qn = 0u;
     __syncthreads();
-    for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (uint64_t)gridDim.x * blockDim.x) {
-        if (idx[r] != S) continue;
-        const uint8_t *p = reads + r * (uint64_t)L;
-        uint64_t k0 = 0, k1 = 1ull << 63;
-        bool odd = false;
-        for (uint32_t j = 0; j < L; j++) {
-            const uint32_t c = __ldg(p + j);
-            const uint32_t code = c == 'N' ? 4u : ((c >> 1) & 3u);       // A0 C1 T2 G3 N4
-            odd |= c != ((0x4E47544341ull >> (8u * code)) & 0xFFu);      // "ACTGN"[code]
-            if (j < 21u) k0 |= (uint64_t)code << (3u * j);
-            else k1 |= (uint64_t)code << (3u * (j - 21u));
+    const bool words_ok = (L & 3u) == 0u && (reinterpret_cast<uintptr_t>(reads) & 3u) == 0u;
+    const uint32_t nw = (L + 3u) >> 2;
+    const uint64_t ntiles = (n + kUnmTile - 1) / kUnmTile;
+    for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const uint64_t first = tile * kUnmTile;
+        const uint32_t cnt = (uint32_t)min((uint64_t)kUnmTile, n - first);
+#pragma unroll
+        for (uint32_t i = 0; i < kUnmTile / 256u; i++) {
+            const uint32_t rl = threadIdx.x + 256u * i;
+            if (rl < cnt && __ldg(idx + first + rl) == S) s_queue[atomicAdd(&s_qn, 1u)] = (uint16_t)rl;
         }
-        atomicAdd(&s_seen, 1u);
-        bool ok;
-        if (!odd) {
-            const bool full = *reinterpret_cast<volatile unsigned long long *>(t.stats) >= t.key_limit;
-            const uint32_t how = unm_add(t, k0, k1, 1ull, full);
-            ok = how != 0u;
-            if (how == 2u && (atomicAdd(&s_new, 1u) + 1u) % kUnmPublish == 0u) atomicAdd(t.stats + 0, (unsigned long long)kUnmPublish);
-        } else {  // a byte outside ACGTN: keep the bytes themselves, the host counts these
-            const unsigned long long at = atomicAdd(t.stats + 3, 1ull);
-            ok = at < t.odd_cap;
-            if (ok)
-                for (uint32_t j = 0; j < 32u; j++) t.odd[at * 32u + j] = j < L ? __ldg(p + j) : (uint8_t)0;
+        __syncthreads();
+        const uint32_t qn = s_qn;
+        for (uint32_t q = threadIdx.x; q < qn; q += 256u) {
+            const uint8_t *p = reads + (first + s_queue[q]) * (uint64_t)L;
+            unsigned long long k0 = 0ull;
+            uint32_t k1 = 0u, odd = 0u;
+#pragma unroll
+            for (uint32_t i = 0; i < 8u; i++) {
+                if (i >= nw) break;
+                uint32_t w;
+                if (words_ok) {
+                    w = __ldg(reinterpret_cast<const uint32_t *>(p) + i);
+                } else {
+                    w = 0x41414141u;  // pad with 'A' (code 0)
+                    for (uint32_t k = 0; k < 4u && 4u * i + k < L; k++)
+                        w = (w & ~(0xFFu << (8u * k))) | ((uint32_t)__ldg(p + 4u * i + k) << (8u * k));
+                }
+                const uint32_t u = key_word(w, odd);  // bases 4i .. 4i+3 at bits 12i .. 12i+11 of a 96-bit string
+                if (i < 5u) k0 |= (unsigned long long)u << (12u * i);
+                else if (i == 5u) {
+                    k0 |= (unsigned long long)u << 60;
+                    k1 |= u >> 4;
+                } else k1 |= u << (12u * i - 64u);
+            }
+            bool ok;
+            if (!odd) {
+                const bool full = *reinterpret_cast<volatile unsigned long long *>(t.stats) >= t.key_limit;
+                const uint32_t how = unm_add(t, k0, (1ull << 63) | k1, 1ull, full);
+                ok = how != 0u;
+                if (how == 2u && (atomicAdd(&s_new, 1u) + 1u) % kUnmPublish == 0u)
+                    atomicAdd(t.stats + 0, (unsigned long long)kUnmPublish);
+            } else {  // a byte outside ACGTN: keep the bytes themselves, the host counts these
+                const unsigned long long at = atomicAdd(t.stats + 3, 1ull);
+                ok = at < t.odd_cap;
+                if (ok)
+                    for (uint32_t j = 0; j < 32u; j++) t.odd[at * 32u + j] = j < L ? __ldg(p + j) : (uint8_t)0;
+            }
+            if (!ok) atomicAdd(&s_drop, 1u);
         }
-        if (!ok) atomicAdd(&s_drop, 1u);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            s_seen += qn;
+            s_qn = 0u;
+        }
+        __syncthreads();
     }
-    __syncthreads();
     if (threadIdx.x == 0) {
         if (s_seen) atomicAdd(t.stats + 1, (unsigned long long)s_seen);
         if (s_drop) atomicAdd(t.stats + 2, (unsigned long long)s_drop);
@@ -138,7 +187,7 @@ __global__ void __launch_bounds__(256) sgdx_unmatched_hist(const UnmSlot *__rest
     for (uint32_t i = threadIdx.x; i < kUnmHistBins; i += blockDim.x) sh[i] = 0u;
     __syncthreads();
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < slots; i += (uint64_t)gridDim.x * blockDim.x) {
-        if (tab[i].key.x == kEmptyWord) continue;
+        if (tab[i].key.y == kEmptyWord) continue;  // occupied slots carry bit 63 only in the top half of .y
         const unsigned long long c = tab[i].count;
         atomicAdd(&sh[c < (unsigned long long)(kUnmHistBins - 1) ? (uint32_t)c : (uint32_t)(kUnmHistBins - 1)], 1u);
     }
@@ -155,7 +204,7 @@ __global__ void __launch_bounds__(256) sgdx_unmatched_select(const UnmSlot *__re
                                                              uint64_t out_cap, unsigned long long *__restrict__ stats) {
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < slots; i += (uint64_t)gridDim.x * blockDim.x) {
         const ulonglong2 k = tab[i].key;
-        if (k.x == kEmptyWord) continue;
+        if (k.y == kEmptyWord) continue;
         const unsigned long long c = tab[i].count;
         bool take = c > t;
         if (c == t && quota) take = atomicAdd(stats + 5, 1ull) < quota;
@@ -210,12 +259,23 @@ __global__ void __launch_bounds__(256) sgdx_extract(const ExtractParams p) {
         const uint32_t cnt = (uint32_t)min((uint64_t)kExtractTileReads, p.n - first);
         const uint32_t bytes = cnt * p.L;
         uint8_t *out = p.out + first * p.L;  // first*L is a multiple of 4
+        if ((p.L & 3u) == 0u && p.words_ok) {  // a word never straddles two reads: one division per word
+            for (uint32_t o = threadIdx.x * 4u; o < bytes; o += blockDim.x * 4u) {
+                const uint32_t rl = __umulhi(o, p.magic);  // o / L: exact for o * L < 2^32
+                const uint32_t j = o - rl * p.L;
+                const uint64_t r = first + rl;
+                const uint32_t b0 = __ldg(s_ptr[j] + r * s_stride[j]), b1 = __ldg(s_ptr[j + 1] + r * s_stride[j + 1]);
+                const uint32_t b2 = __ldg(s_ptr[j + 2] + r * s_stride[j + 2]), b3 = __ldg(s_ptr[j + 3] + r * s_stride[j + 3]);
+                *reinterpret_cast<uint32_t *>(out + o) = b0 | (b1 << 8) | (b2 << 16) | (b3 << 24);
+            }
+            continue;
+        }
         for (uint32_t o = threadIdx.x * 4u; o < bytes; o += blockDim.x * 4u) {
             uint32_t w = 0;
             const uint32_t nb = min(4u, bytes - o);
             for (uint32_t b = 0; b < nb; b++) {
                 const uint32_t ob = o + b;
-                const uint32_t rl = __umulhi(ob, p.magic);  // ob / L: exact for ob * L < 2^32
+                const uint32_t rl = __umulhi(ob, p.magic);
                 const uint32_t j = ob - rl * p.L;
                 const uint32_t c = __ldg(s_ptr[j] + (first + rl) * (uint64_t)s_stride[j]);
                 w |= c << (8u * b);
@@ -239,7 +299,7 @@ struct QualParams {
     const uint16_t *idx;
     uint64_t n;
     uint32_t stride, S;
-    uint32_t reads_per_tile;  // multiple of 16, <= kQualThreads
+    uint32_t reads_per_tile;  // multiple of 16
     uint32_t stage_bytes;     // shared-memory bytes of one stage (multiple of 128)
     uint32_t stages;
     uint32_t nwords;          // words per shifted mask
@@ -357,12 +417,12 @@ __global__ void __launch_bounds__(kQualThreads) sgdx_qual_counts(const QualParam
             if (tid < bytes - bulk) stage[bulk + tid] = p.quals[first * p.stride + bulk + tid];
             __syncthreads();
         }
-        if (tid < cnt) {
-            const uint32_t start = tid * p.stride, a = start & 15u;
+        for (uint32_t rl = tid; rl < cnt; rl += kQualThreads) {  // several reads per thread when they are short
+            const uint32_t start = rl * p.stride, a = start & 15u;
             const uint4 *chunks = reinterpret_cast<const uint4 *>(stage + (start & ~15u));
             uint32_t len = p.stride;
-            if (p.lens) len = min(__ldg(p.lens + first + tid), p.stride);
-            const uint32_t bin = __ldg(p.idx + first + tid);
+            if (p.lens) len = min(__ldg(p.lens + first + rl), p.stride);
+            const uint32_t bin = __ldg(p.idx + first + rl);
             if (len < p.min_len) {
                 shorts++;
             } else if (bin <= p.S) {
@@ -491,7 +551,7 @@ __global__ void __launch_bounds__(kQualThreads) sgdx_qual_counts(const QualParam
             const uint64_t next = tile + (uint64_t)p.stages * gridDim.x;
             if (next < ntiles) issue(next, s);
         }
-        if (p.smem_hist && (it & 1023u) == 1023u) flush();  // 32-bit bins: 1024 tiles of <= 128 * 4096 bytes
+        if (p.smem_hist && (it & 63u) == 63u) flush();  // 32-bit bins: 64 tiles of <= 48 KB, each byte adds <= 255
     }
     if (p.smem_hist) flush();
     if (shorts) atomicAdd(gcnt + (size_t)(p.S + 1u) * kQualCounters, (unsigned long long)shorts);
@@ -655,11 +715,9 @@ int post_after_match(sgdx_handle *h, Slot &s, const uint8_t *d_ascii, const uint
 }
 
 static void decode_key(ulonglong2 k, uint32_t L, char *out) {
-    static const char letters[8] = {'A', 'C', 'T', 'G', 'N', '?', '?', '?'};
-    for (uint32_t j = 0; j < L; j++) {
-        const uint64_t w = j < 21 ? k.x >> (3 * j) : k.y >> (3 * (j - 21));
-        out[j] = letters[w & 7u];
-    }
+    static const char letters[8] = {'A', 'C', 'T', 'G', '?', '?', '?', 'N'};
+    const unsigned __int128 bits = ((unsigned __int128)(k.y & 0xFFFFFFFFull) << 64) | k.x;
+    for (uint32_t j = 0; j < L; j++) out[j] = letters[(unsigned)(bits >> (3 * j)) & 7u];
 }
 
 // device idle, post_mu held: fold the foreign-byte list into the host map and empty it
@@ -777,18 +835,17 @@ static int unm_downsize_locked(sgdx_handle *h) {
     std::map<std::string, uint64_t> odd;
     const uint32_t L = h->cfg.barcode_len;
     for (const UnmEntry &e : top) {
-        uint64_t k0 = 0, k1 = 1ull << 63;
+        unsigned __int128 bits = 0;
         bool foreign = false;
         for (uint32_t j = 0; j < L; j++) {
             const char c = e.key[j];
-            uint64_t code = c == 'A' ? 0 : c == 'C' ? 1 : c == 'T' ? 2 : c == 'G' ? 3 : c == 'N' ? 4 : 7;
-            foreign |= code == 7;
-            if (j < 21) k0 |= code << (3 * j);
-            else k1 |= code << (3 * (j - 21));
+            const unsigned code = c == 'A' ? 0 : c == 'C' ? 1 : c == 'T' ? 2 : c == 'G' ? 3 : c == 'N' ? 7 : 4;
+            foreign |= code == 4;
+            bits |= (unsigned __int128)code << (3 * j);
         }
         if (foreign) odd[e.key] = e.count;
         else {
-            keys.push_back(make_ulonglong2(k0, k1));
+            keys.push_back(make_ulonglong2((unsigned long long)bits, (1ull << 63) | (unsigned long long)(bits >> 64)));
             counts.push_back(e.count);
         }
     }
@@ -1110,6 +1167,7 @@ extern "C" int sgdx_qual_counts_device(sgdx_handle *h, uint32_t slot, const uint
     // tile = reads_per_tile quality strings, a multiple of 16 reads so that every tile starts 16-byte aligned
     uint32_t R = kQualThreads;
     while (R > 16u && (uint64_t)R * stride > 48u * 1024u) R >>= 1;
+    if ((uint64_t)R * stride < 8u * 1024u) R = kQualThreads * std::min<uint32_t>(32u, 16u * 1024u / (kQualThreads * stride));  // short reads: ~16 KB tiles
     p.reads_per_tile = R;
     p.stage_bytes = (R * stride + 16u + 127u) & ~127u;
     p.stages = 2;
