@@ -103,48 +103,49 @@ __device__ __forceinline__ uint32_t key_word(uint32_t w, uint32_t &odd) {
 }
 
 constexpr uint32_t kUnmTile = 2048;  // reads per CTA step
+constexpr uint32_t kUnmThreads = 256;
 
-// NoMatch reads (idx == S) are keyed and counted (demux.rs:553-555).  Two phases per tile so that the rare work
-// runs in full warps: every thread tests eight index entries and queues the NoMatch ones in shared memory; then
-// the CTA walks the queue, one thread per queued read (word loads, SWAR key, one 128-bit CAS + one add).
-__global__ void __launch_bounds__(256) sgdx_unmatched_count(const uint8_t *__restrict__ reads,
-                                                            const uint16_t *__restrict__ idx, uint64_t n, uint32_t S,
-                                                            uint32_t L, const UnmTable t) {
+// NoMatch reads (idx == S) are keyed and counted (demux.rs:553-555).  The rare work runs in full warps: every
+// thread tests eight index entries of a tile (eight independent loads) and queues the NoMatch ones in shared
+// memory; whenever the queue holds a full batch of 256 the CTA drains it, one thread per queued read (word loads,
+// SWAR key, one 128-bit CAS + one add).
+__global__ void __launch_bounds__(kUnmThreads) sgdx_unmatched_count(const uint8_t *__restrict__ reads,
+                                                                    const uint16_t *__restrict__ idx, uint64_t n,
+                                                                    uint32_t S, uint32_t L, const UnmTable t) {
     // the number of distinct keys is published in steps of kUnmPublish per CTA (one global atomic per step instead
     // of one per key on a single word); the key limit is therefore enforced to within gridDim.x * kUnmPublish keys
-    __shared__ unsigned int s_seen, s_drop, s_new, s_qn;
-    __shared__ uint16_t s_queue[kUnmTile];
-    if (threadIdx.x == 0) s_seen = s_drop = s_new = s_qn = 0u;
+    __shared__ unsigned int s_drop, s_new, s_qn;
+    __shared__ uint32_t s_queue[kUnmTile + kUnmThreads];  // entry = tile ordinal of this CTA << 11 | read in tile
+    if (threadIdx.x == 0) s_drop = s_new = s_qn = 0u;
     __syncthreads();
     const bool words_ok = (L & 3u) == 0u && (reinterpret_cast<uintptr_t>(reads) & 3u) == 0u;
     const uint32_t nw = (L + 3u) >> 2;
     const uint64_t ntiles = (n + kUnmTile - 1) / kUnmTile;
-    for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const uint64_t first = tile * kUnmTile;
-        const uint32_t cnt = (uint32_t)min((uint64_t)kUnmTile, n - first);
+    uint32_t seen = 0;  // thread 0 only
+
+    auto drain = [&](uint32_t from, uint32_t count) {  // queue entries [from, from + count), count <= 256
+        if (threadIdx.x < count) {
+            const uint32_t e = s_queue[from + threadIdx.x];
+            const uint64_t r = ((uint64_t)blockIdx.x + (uint64_t)(e >> 11) * gridDim.x) * kUnmTile + (e & 2047u);
+            const uint8_t *p = reads + r * (uint64_t)L;
+            const unsigned long long distinct = *reinterpret_cast<volatile unsigned long long *>(t.stats);
+            uint32_t w[8];
 #pragma unroll
-        for (uint32_t i = 0; i < kUnmTile / 256u; i++) {
-            const uint32_t rl = threadIdx.x + 256u * i;
-            if (rl < cnt && __ldg(idx + first + rl) == S) s_queue[atomicAdd(&s_qn, 1u)] = (uint16_t)rl;
-        }
-        __syncthreads();
-        const uint32_t qn = s_qn;
-        for (uint32_t q = threadIdx.x; q < qn; q += 256u) {
-            const uint8_t *p = reads + (first + s_queue[q]) * (uint64_t)L;
+            for (uint32_t i = 0; i < 8u; i++) {
+                w[i] = 0x41414141u;  // pad with 'A' (code 0)
+                if (i < nw) {
+                    if (words_ok) w[i] = __ldg(reinterpret_cast<const uint32_t *>(p) + i);
+                    else
+                        for (uint32_t k = 0; k < 4u && 4u * i + k < L; k++)
+                            w[i] = (w[i] & ~(0xFFu << (8u * k))) | ((uint32_t)__ldg(p + 4u * i + k) << (8u * k));
+                }
+            }
             unsigned long long k0 = 0ull;
             uint32_t k1 = 0u, odd = 0u;
 #pragma unroll
             for (uint32_t i = 0; i < 8u; i++) {
                 if (i >= nw) break;
-                uint32_t w;
-                if (words_ok) {
-                    w = __ldg(reinterpret_cast<const uint32_t *>(p) + i);
-                } else {
-                    w = 0x41414141u;  // pad with 'A' (code 0)
-                    for (uint32_t k = 0; k < 4u && 4u * i + k < L; k++)
-                        w = (w & ~(0xFFu << (8u * k))) | ((uint32_t)__ldg(p + 4u * i + k) << (8u * k));
-                }
-                const uint32_t u = key_word(w, odd);  // bases 4i .. 4i+3 at bits 12i .. 12i+11 of a 96-bit string
+                const uint32_t u = key_word(w[i], odd);  // bases 4i .. 4i+3 at bits 12i .. 12i+11 of a 96-bit string
                 if (i < 5u) k0 |= (unsigned long long)u << (12u * i);
                 else if (i == 5u) {
                     k0 |= (unsigned long long)u << 60;
@@ -153,8 +154,7 @@ __global__ void __launch_bounds__(256) sgdx_unmatched_count(const uint8_t *__res
             }
             bool ok;
             if (!odd) {
-                const bool full = *reinterpret_cast<volatile unsigned long long *>(t.stats) >= t.key_limit;
-                const uint32_t how = unm_add(t, k0, (1ull << 63) | k1, 1ull, full);
+                const uint32_t how = unm_add(t, k0, (1ull << 63) | k1, 1ull, distinct >= t.key_limit);
                 ok = how != 0u;
                 if (how == 2u && (atomicAdd(&s_new, 1u) + 1u) % kUnmPublish == 0u)
                     atomicAdd(t.stats + 0, (unsigned long long)kUnmPublish);
@@ -166,15 +166,41 @@ __global__ void __launch_bounds__(256) sgdx_unmatched_count(const uint8_t *__res
             }
             if (!ok) atomicAdd(&s_drop, 1u);
         }
+    };
+
+    uint32_t it = 0;
+    for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
+        const uint64_t first = tile * kUnmTile;
+        const uint32_t cnt = (uint32_t)min((uint64_t)kUnmTile, n - first);
+        uint32_t v[kUnmTile / kUnmThreads];
+#pragma unroll
+        for (uint32_t i = 0; i < kUnmTile / kUnmThreads; i++) {
+            const uint32_t rl = threadIdx.x + kUnmThreads * i;
+            v[i] = rl < cnt ? (uint32_t)__ldg(idx + first + rl) : 0xFFFFFFFFu;
+        }
+#pragma unroll
+        for (uint32_t i = 0; i < kUnmTile / kUnmThreads; i++)
+            if (v[i] == S) s_queue[atomicAdd(&s_qn, 1u)] = (it << 11) | (threadIdx.x + kUnmThreads * i);
+        __syncthreads();
+        uint32_t qn = s_qn;
+        const uint32_t pushed = qn;
+        while (qn >= kUnmThreads) {  // full batches from the top of the queue
+            qn -= kUnmThreads;
+            drain(qn, kUnmThreads);
+        }
         __syncthreads();
         if (threadIdx.x == 0) {
-            s_seen += qn;
-            s_qn = 0u;
+            seen += pushed - qn;
+            s_qn = qn;
         }
         __syncthreads();
     }
+    const uint32_t rest = s_qn;
+    drain(0u, rest);
+    __syncthreads();
     if (threadIdx.x == 0) {
-        if (s_seen) atomicAdd(t.stats + 1, (unsigned long long)s_seen);
+        seen += rest;
+        if (seen) atomicAdd(t.stats + 1, (unsigned long long)seen);
         if (s_drop) atomicAdd(t.stats + 2, (unsigned long long)s_drop);
         if (s_new % kUnmPublish) atomicAdd(t.stats + 0, (unsigned long long)(s_new % kUnmPublish));
     }
@@ -412,6 +438,13 @@ __global__ void __launch_bounds__(kQualThreads) sgdx_qual_counts(const QualParam
         const uint64_t first = tile * R;
         const uint32_t cnt = (uint32_t)min((uint64_t)R, p.n - first);
         const uint32_t bytes = cnt * p.stride, bulk = bytes & ~15u;
+        // this thread's first read of the tile: its sample index and length do not depend on the tile's bytes, so
+        // their latency is spent while the bulk copy is still in flight
+        uint32_t bin0 = 0, len0 = p.stride;
+        if (tid < cnt) {
+            bin0 = __ldg(p.idx + first + tid);
+            if (p.lens) len0 = min(__ldg(p.lens + first + tid), p.stride);
+        }
         mbar_wait(mbar + s, parity);
         if (bytes != bulk) {  // last tile only: the < 16 bytes a bulk copy cannot carry
             if (tid < bytes - bulk) stage[bulk + tid] = p.quals[first * p.stride + bulk + tid];
@@ -420,9 +453,11 @@ __global__ void __launch_bounds__(kQualThreads) sgdx_qual_counts(const QualParam
         for (uint32_t rl = tid; rl < cnt; rl += kQualThreads) {  // several reads per thread when they are short
             const uint32_t start = rl * p.stride, a = start & 15u;
             const uint4 *chunks = reinterpret_cast<const uint4 *>(stage + (start & ~15u));
-            uint32_t len = p.stride;
-            if (p.lens) len = min(__ldg(p.lens + first + rl), p.stride);
-            const uint32_t bin = __ldg(p.idx + first + rl);
+            uint32_t len = len0, bin = bin0;
+            if (rl != tid) {
+                bin = __ldg(p.idx + first + rl);
+                len = p.lens ? min(__ldg(p.lens + first + rl), p.stride) : p.stride;
+            }
             if (len < p.min_len) {
                 shorts++;
             } else if (bin <= p.S) {
@@ -430,7 +465,9 @@ __global__ void __launch_bounds__(kQualThreads) sgdx_qual_counts(const QualParam
                 const uint32_t end = a + len, nchunks = (end + 15u) >> 4;
                 uint32_t acc20 = 0, acc30 = 0, c20 = 0, c30 = 0, nT = 0;   // template bases
                 uint32_t bacc = 0, bsum = 0, nB = 0, nBfast = 0;            // sample-barcode bases
-                auto drain = [&]() {  // byte lanes hold <= 64, 16-bit lanes <= 16 256 after 16 chunks
+                // byte lanes gain <= 4 per chunk, the 16-bit lanes of bacc <= 1016 per (general) chunk: at most 15 + 32
+                // + 15 chunks pass between two drains below
+                auto drain = [&]() {
                     c20 += lanes8_sum(acc20);
                     c30 += lanes8_sum(acc30);
                     bsum += (bacc & 0xFFFFu) + (bacc >> 16);
@@ -502,9 +539,8 @@ __global__ void __launch_bounds__(kQualThreads) sgdx_qual_counts(const QualParam
                     general_chunk(k);
                     if ((k & 15u) == 15u) drain();
                 }
-                drain();
-                for (uint32_t k0 = k_lo; k0 < k_hi; k0 += 16u) {
-                    const uint32_t k1 = min(k0 + 16u, k_hi);
+                for (uint32_t k0 = k_lo; k0 < k_hi; k0 += 32u) {
+                    const uint32_t k1 = min(k0 + 32u, k_hi);
 #pragma unroll 2
                     for (uint32_t k = k0; k < k1; k++) {
                         const uint4 v = chunks[k];
@@ -523,11 +559,11 @@ __global__ void __launch_bounds__(kQualThreads) sgdx_qual_counts(const QualParam
                             nT += 16u;
                         }
                     }
-                    drain();
+                    if (k1 < k_hi) drain();
                 }
                 for (uint32_t k = k_hi; k < nchunks; k++) {
                     general_chunk(k);
-                    if ((k & 15u) == 15u) drain();
+                    if (((k - k_hi) & 15u) == 15u) drain();
                 }
                 c20 += lanes8_sum(acc20);
                 c30 += lanes8_sum(acc30);
@@ -702,9 +738,15 @@ static UnmTable unm_table(const UnmatchedState &u) {
 
 int post_after_match(sgdx_handle *h, Slot &s, const uint8_t *d_ascii, const uint16_t *d_idx, uint64_t n) {
     UnmatchedState &u = h->unm;
-    const uint32_t grid = grid_cap(n, 256, h->sms, 8);
-    sgdx_unmatched_count<<<grid, 256, 0, s.stream>>>(d_ascii, d_idx, n, h->cfg.num_samples, h->cfg.barcode_len,
-                                                     unm_table(u));
+    static int per_sm = 0;  // resident CTAs per SM: the grid is exactly one wave
+    if (per_sm == 0) {
+        int v = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, sgdx_unmatched_count, (int)kUnmThreads, 0));
+        per_sm = v < 1 ? 1 : v;
+    }
+    const uint32_t grid = grid_cap(n, kUnmTile, h->sms, per_sm);
+    sgdx_unmatched_count<<<grid, kUnmThreads, 0, s.stream>>>(d_ascii, d_idx, n, h->cfg.num_samples,
+                                                             h->cfg.barcode_len, unm_table(u));
     CU(cudaGetLastError());
     h->launches.fetch_add(1);
     if (!s.h_unm_stats) CU(cudaMallocHost(&s.h_unm_stats, kUnmStats * sizeof(unsigned long long)));
