@@ -317,6 +317,8 @@ __global__ void __launch_bounds__(256) sgdx_extract(const ExtractParams p) {
 // 3. base-quality counters
 // ================================================================================================
 constexpr int kQualThreads = 128;
+constexpr int kQualSplit = 1;                            // threads per read: each takes half of the read's chunks
+constexpr int kQualLanes = kQualThreads / kQualSplit;  // reads in flight per CTA
 constexpr int kQualCounters = 5;  // q20, q30, index_bases_qual_sum, index_bases_total_seen, bases (metrics.rs:468-481)
 
 struct QualParams {
@@ -440,26 +442,27 @@ __global__ void __launch_bounds__(kQualThreads) sgdx_qual_counts(const QualParam
         const uint32_t bytes = cnt * p.stride, bulk = bytes & ~15u;
         // this thread's first read of the tile: its sample index and length do not depend on the tile's bytes, so
         // their latency is spent while the bulk copy is still in flight
+        const uint32_t lane_read = tid / kQualSplit, part = tid % kQualSplit;
         uint32_t bin0 = 0, len0 = p.stride;
-        if (tid < cnt) {
-            bin0 = __ldg(p.idx + first + tid);
-            if (p.lens) len0 = min(__ldg(p.lens + first + tid), p.stride);
+        if (lane_read < cnt) {
+            bin0 = __ldg(p.idx + first + lane_read);
+            if (p.lens) len0 = min(__ldg(p.lens + first + lane_read), p.stride);
         }
         mbar_wait(mbar + s, parity);
         if (bytes != bulk) {  // last tile only: the < 16 bytes a bulk copy cannot carry
             if (tid < bytes - bulk) stage[bulk + tid] = p.quals[first * p.stride + bulk + tid];
             __syncthreads();
         }
-        for (uint32_t rl = tid; rl < cnt; rl += kQualThreads) {  // several reads per thread when they are short
+        for (uint32_t rl = lane_read; rl < cnt; rl += kQualLanes) {  // several reads per thread when they are short
             const uint32_t start = rl * p.stride, a = start & 15u;
             const uint4 *chunks = reinterpret_cast<const uint4 *>(stage + (start & ~15u));
             uint32_t len = len0, bin = bin0;
-            if (rl != tid) {
+            if (rl != lane_read) {
                 bin = __ldg(p.idx + first + rl);
                 len = p.lens ? min(__ldg(p.lens + first + rl), p.stride) : p.stride;
             }
             if (len < p.min_len) {
-                shorts++;
+                shorts += part == 0u;
             } else if (bin <= p.S) {
                 const uint32_t *tm = s_masks + a * p.nwords, *bm = s_masks + (16u + a) * p.nwords;
                 const uint32_t end = a + len, nchunks = (end + 15u) >> 4;
@@ -535,35 +538,46 @@ __global__ void __launch_bounds__(kQualThreads) sgdx_qual_counts(const QualParam
                 // chunks [k_lo, k_hi) hold template bases only (the structure ends in a run of T from position
                 // t_tail on, and the chunk lies inside the read): no masks
                 const uint32_t k_lo = min((p.t_tail + a + 15u) >> 4, nchunks), k_hi = max(end >> 4, k_lo);
-                for (uint32_t k = 0; k < k_lo; k++) {
+                // this thread's share of the read: chunks [kb, ke)
+                const uint32_t kb = (nchunks * part) / kQualSplit, ke = (nchunks * (part + 1u)) / kQualSplit;
+                const uint32_t g0 = min(k_lo, ke), f0 = max(k_lo, kb), f1 = max(min(k_hi, ke), f0), g1 = max(k_hi, kb);
+                for (uint32_t k = kb; k < g0; k++) {
                     general_chunk(k);
-                    if ((k & 15u) == 15u) drain();
+                    if (((k - kb) & 15u) == 15u) drain();
                 }
-                for (uint32_t k0 = k_lo; k0 < k_hi; k0 += 32u) {
-                    const uint32_t k1 = min(k0 + 32u, k_hi);
-#pragma unroll 2
+                for (uint32_t k0 = f0; k0 < f1; k0 += 32u) {
+                    // branch-free over the block; a byte outside 33..127 anywhere in it (never in a valid FASTQ)
+                    // discards the block's sums and redoes it chunk by chunk
+                    const uint32_t k1 = min(k0 + 32u, f1);
+                    const uint32_t save20 = acc20, save30 = acc30;
+                    uint32_t flag = 0;
+#pragma unroll 4
                     for (uint32_t k = k0; k < k1; k++) {
                         const uint4 v = chunks[k];
                         const uint32_t x[4] = {v.x, v.y, v.z, v.w};
-                        uint32_t flag = 0;
 #pragma unroll
-                        for (int w = 0; w < 4; w++) flag |= (x[w] - 0x21212121u) | x[w];
-                        if (flag & 0x80808080u) {
-                            slow_chunk(x, 0xFFFFu, 0u);
-                        } else {
-#pragma unroll
-                            for (int w = 0; w < 4; w++) {
-                                acc20 += top_bits(add_fma(x[w], p.one, 0x4B4B4B4Bu)) >> 7;  // IMAD, LOP3, LEA.HI
-                                acc30 += top_bits(add_fma(x[w], p.one, 0x41414141u)) >> 7;
-                            }
-                            nT += 16u;
+                        for (int w = 0; w < 4; w++) {
+                            flag |= (x[w] - 0x21212121u) | x[w];
+                            acc20 += top_bits(add_fma(x[w], p.one, 0x4B4B4B4Bu)) >> 7;  // IMAD, LOP3, LEA.HI
+                            acc30 += top_bits(add_fma(x[w], p.one, 0x41414141u)) >> 7;
                         }
                     }
-                    if (k1 < k_hi) drain();
+                    if (flag & 0x80808080u) {
+                        acc20 = save20;
+                        acc30 = save30;
+                        for (uint32_t k = k0; k < k1; k++) {
+                            general_chunk(k);
+                            if (((k - k0) & 15u) == 15u) drain();
+                        }
+                        drain();
+                    } else {
+                        nT += 16u * (k1 - k0);
+                        if (k1 < f1) drain();
+                    }
                 }
-                for (uint32_t k = k_hi; k < nchunks; k++) {
+                for (uint32_t k = g1; k < ke; k++) {
                     general_chunk(k);
-                    if (((k - k_hi) & 15u) == 15u) drain();
+                    if (((k - g1) & 15u) == 15u) drain();
                 }
                 c20 += lanes8_sum(acc20);
                 c30 += lanes8_sum(acc30);
@@ -1207,9 +1221,9 @@ extern "C" int sgdx_qual_counts_device(sgdx_handle *h, uint32_t slot, const uint
     p.masks = s.d_qmasks;
     p.counters = h->qual.d_counters;
     // tile = reads_per_tile quality strings, a multiple of 16 reads so that every tile starts 16-byte aligned
-    uint32_t R = kQualThreads;
+    uint32_t R = kQualLanes;
     while (R > 16u && (uint64_t)R * stride > 48u * 1024u) R >>= 1;
-    if ((uint64_t)R * stride < 8u * 1024u) R = kQualThreads * std::min<uint32_t>(32u, 16u * 1024u / (kQualThreads * stride));  // short reads: ~16 KB tiles
+    if ((uint64_t)R * stride < 8u * 1024u) R = kQualLanes * std::min<uint32_t>(32u, 16u * 1024u / (kQualLanes * stride));  // short reads: ~16 KB tiles
     p.reads_per_tile = R;
     p.stage_bytes = (R * stride + 16u + 127u) & ~127u;
     p.stages = 2;
