@@ -141,6 +141,7 @@ def main():
     ap.add_argument("--ref-sample", type=int, default=0)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-post", action="store_true", help="skip the stages either side of the assignment")
     ap.add_argument("--e2e-chunk", type=int, default=4_000_000)
     args = ap.parse_args()
     if args.impl == "reference":
@@ -323,6 +324,16 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu:
         cb = cpu_baseline(sg, w, table)
 
+    # ---- the stages either side of the assignment, device-timed on the same C2-shaped reads: not part
+    # of `value`; their kernels are not counted in gpu_launches
+    post = None
+    if rank == 0 and world == 1 and not args.no_post and args.config == "C2":
+        del d_in, d_idx, d_dist
+        torch.cuda.empty_cache()
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import bench_post
+        post = bench_post.measure(reads=min(n, 50_000_000), steps=min(args.steps, 10), warmup=max(args.warmup, 3))
+
     if rank == 0:
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -333,7 +344,7 @@ def main():
                        "input": "ASCII barcodes resident in HBM", "sharding": f"{world} shard(s) by read range, host-merged counters",
                        "l2": f"inputs {n * L / 1e6:.0f} MB + outputs {n * 3 / 1e6:.0f} MB per step, larger than the 126 MB L2"},
             "roofline": roofline, "cpu_baseline": cb, "e2e": e2e, "gpu_launches": int(launches),
-            "clocks": clocks, "matched_fraction": matched_frac,
+            "clocks": clocks, "matched_fraction": matched_frac, "post": post,
         }
         os.write(json_fd, (json.dumps(out) + "\n").encode())
     if world > 1:

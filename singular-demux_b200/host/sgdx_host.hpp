@@ -7,6 +7,8 @@
 //   PreComputeMatcher                 matcher.rs:121-262    DemuxedGroupSampleMetrics        metrics.rs:407-437
 //   SampleBarcodeHopTracker           metrics.rs:617-677    DemuxedGroupMetrics::update_with metrics.rs:315-328
 //   Demultiplexer's assignment step   demux.rs:524-556,581  (BarcodeAssignmentStage: the batched form a GPU needs)
+//   ReadStructure / ReadSegment       opts.rs:84-92 (crate read-structure 0.1.0, used at demux.rs:380-387)
+//   BaseQualCounter                   metrics.rs:468-518    UnmatchedCounter / BarcodeCount  metrics.rs:131-206
 //
 // Errors: the reference returns anyhow::Result from everything around the matcher and find() itself cannot fail;
 // here every failed C-ABI call throws sgdx::Error carrying sgdx_last_error().  There is no CPU fallback: without
@@ -177,6 +179,54 @@ struct DemuxedGroupMetrics {  // metrics.rs:297-328 (the fields this path fills)
     }
 };
 
+struct BarcodeCount {  // metrics.rs:194-206
+    std::string barcode;
+    uint64_t count = 0;
+};
+
+struct BaseQualCounter {  // metrics.rs:468-497; the per-base update (499-518) runs on the device
+    uint64_t q20_bases = 0, q30_bases = 0, index_bases_qual_sum = 0, index_bases_total_seen = 0, bases = 0;
+    void update_with_self(const BaseQualCounter &o) {
+        q20_bases += o.q20_bases;
+        q30_bases += o.q30_bases;
+        index_bases_qual_sum += o.index_bases_qual_sum;
+        index_bases_total_seen += o.index_bases_total_seen;
+        bases += o.bases;
+    }
+};
+
+// `--read-structures` strings (opts.rs:84-92): <length><kind> segments, kinds T B M S, `+` only on the last one
+struct ReadStructure {
+    std::vector<sgdx_segment> segments;  // source is filled in by the calls that take several structures
+    static ReadStructure from_str(const std::string &text) {
+        ReadStructure rs;
+        uint32_t off = 0;
+        size_t i = 0;
+        while (i < text.size()) {
+            uint32_t len = 0;
+            bool plus = false;
+            if (text[i] == '+') {
+                plus = true;
+                i++;
+            } else {
+                size_t j = i;
+                while (j < text.size() && text[j] >= '0' && text[j] <= '9') len = len * 10 + (uint32_t)(text[j++] - '0');
+                if (j == i || len == 0) throw std::invalid_argument("read structure: expected a positive length in " + text);
+                i = j;
+            }
+            if (i >= text.size()) throw std::invalid_argument("read structure: missing segment kind in " + text);
+            const char k = (char)(text[i] >= 'a' ? text[i] - 32 : text[i]);
+            i++;
+            if (k != 'T' && k != 'B' && k != 'M' && k != 'S') throw std::invalid_argument("read structure: unknown kind in " + text);
+            if (plus && i != text.size()) throw std::invalid_argument("read structure: only the last segment may be `+`: " + text);
+            rs.segments.push_back(sgdx_segment{0u, off, plus ? SGDX_SEG_TO_END : len, (uint32_t)k});
+            off += len;
+        }
+        if (rs.segments.empty()) throw std::invalid_argument("empty read structure");
+        return rs;
+    }
+};
+
 struct DemuxedGroup {  // demux.rs:637-645, minus the routed reads
     std::vector<uint16_t> sample_indices;  // undetermined index for NoMatch
     std::vector<uint8_t> hamming_dists;    // SGDX_NO_DIST for NoMatch
@@ -208,6 +258,42 @@ class BarcodeAssignmentStage {
         matcher_.find_batch(reinterpret_cast<const uint8_t *>(flat.data()), barcodes.size(), g.sample_indices.data(),
                             g.hamming_dists.data());
         return g;
+    }
+
+    // UnmatchedCounterThread::new (run.rs:185-190): from now on every batch also counts its NoMatch barcodes on the device
+    void collect_unmatched(uint64_t max_map_size = 5000000, uint64_t downsize_to = 5000) {
+        check(sgdx_unmatched_enable(matcher_.handle(), max_map_size, downsize_to), "sgdx_unmatched_enable");
+    }
+    // rows of most_frequent_unmatched.tsv (metrics.rs:177-190): delimited barcode (demux.rs:504-522), descending count
+    std::vector<BarcodeCount> most_frequent_unmatched(uint64_t n) {
+        const size_t L = matcher_.barcode_len();
+        std::vector<uint8_t> keys((n ? n : 1) * L);
+        std::vector<uint64_t> counts(n ? n : 1);
+        uint64_t w = 0;
+        check(sgdx_unmatched_top(matcher_.handle(), n, keys.data(), counts.data(), &w), "sgdx_unmatched_top");
+        std::vector<BarcodeCount> rows;
+        for (uint64_t i = 0; i < w; i++) {
+            std::string k(reinterpret_cast<const char *>(keys.data()) + i * L, L);
+            if (index_lengths_) k.insert(index_lengths_->first, "+");
+            rows.push_back({std::move(k), counts[i]});
+        }
+        return rows;
+    }
+
+    // BaseQualCounter::update over one FASTQ's quality strings of a batch that is resident on the device, keyed
+    // by the batch's sample-index array (demux.rs:582-583); d_lens may be null (all reads `stride` long)
+    void count_base_qualities(const uint8_t *d_quals, uint64_t n, uint32_t stride, const ReadStructure &rs,
+                              const uint16_t *d_sample_indices, const uint32_t *d_lens = nullptr, unsigned slot = 0) {
+        check(sgdx_qual_counts_device(matcher_.handle(), slot, d_quals, n, stride, d_lens, rs.segments.data(),
+                                      (uint32_t)rs.segments.size(), d_sample_indices), "sgdx_qual_counts_device");
+    }
+    std::vector<BaseQualCounter> base_qual_counters() {  // one per sample, Undetermined last
+        std::vector<sgdx_base_qual> raw(matcher_.num_samples() + 1);
+        check(sgdx_base_qual_counters(matcher_.handle(), raw.data(), nullptr), "sgdx_base_qual_counters");
+        std::vector<BaseQualCounter> out;
+        for (const auto &r : raw)
+            out.push_back({r.q20_bases, r.q30_bases, r.index_bases_qual_sum, r.index_bases_total_seen, r.bases});
+        return out;
     }
 
     // cumulative counters of every batch this stage has processed (device resident, read on demand)

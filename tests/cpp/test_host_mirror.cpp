@@ -158,6 +158,41 @@ static void test_metrics_merge_and_errors() {
     EXPECT(threw);
 }
 
+static void test_unmatched_and_read_structures() {
+    // run.rs:652-689: the three unmatched barcodes of the simple end-to-end run, once each
+    BarcodeAssignmentStage st(samples_of(kFour, true),
+                              MatcherKind::CachedHammingDistance, 2, 1, 1, 1);
+    st.collect_unmatched();
+    st.demultiplex({"AAAAAAAAGATTACAGA", "AAAAAAAAGATTACAGT", "AAAAAAAAGATTACTTT", "GGGGGGTCGATTACAGA", "AAAAAAAAGANNNNNNN"});
+    auto rows = st.most_frequent_unmatched(1000);
+    EXPECT(rows.size() == 3);
+    for (const auto &r : rows) EXPECT(r.count == 1);
+    EXPECT(rows[0].barcode == "AAAAAAAAGANNNNNNN" && rows[1].barcode == "AAAAAAAAGATTACTTT" && rows[2].barcode == "GGGGGGTCGATTACAGA");
+    // run.rs:1444-1451: the hopped barcode, delimited
+    BarcodeAssignmentStage dual(samples_of({"TTTGGG", "CCCAAA"}, true), MatcherKind::PreCompute, 2, 1, 1, 1,
+                                std::make_pair<size_t, size_t>(3, 3));
+    dual.collect_unmatched();
+    dual.demultiplex({"TTTAAA"});
+    auto hop = dual.most_frequent_unmatched(10);
+    EXPECT(hop.size() == 1 && hop[0].barcode == "TTT+AAA" && hop[0].count == 1);
+    // read structures (opts.rs:84-92)
+    auto rs = ReadStructure::from_str("8B+T");
+    EXPECT(rs.segments.size() == 2 && rs.segments[0].length == 8 && rs.segments[0].kind == 'B');
+    EXPECT(rs.segments[1].offset == 8 && rs.segments[1].length == SGDX_SEG_TO_END && rs.segments[1].kind == 'T');
+    bool threw = false;
+    try {
+        ReadStructure::from_str("+T8B");
+    } catch (const std::invalid_argument &) {
+        threw = true;
+    }
+    EXPECT(threw);
+    BaseQualCounter a{1, 2, 3, 4, 5}, b{10, 20, 30, 40, 50};
+    a.update_with_self(b);  // metrics.rs:489-496
+    EXPECT(a.q20_bases == 11 && a.q30_bases == 22 && a.index_bases_qual_sum == 33 && a.index_bases_total_seen == 44 && a.bases == 55);
+    auto q = st.base_qual_counters();
+    EXPECT(q.size() == 5 && q[0].bases == 0);
+}
+
 int main() {
     try {
         test_find_two_samples();
@@ -167,6 +202,7 @@ int main() {
         test_end_to_end_with_all_matchers();
         test_dual_index_metrics();
         test_metrics_merge_and_errors();
+        test_unmatched_and_read_structures();
     } catch (const Error &e) {  // e.g. no CUDA device: there is no CPU fallback to run these on
         std::fprintf(stderr, "sgdx::Error (code %d): %s\n", e.code, e.what());
         return 2;

@@ -16,15 +16,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--reads", type=int, default=50_000_000)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--only", default="qual,qual_index,unmatched,extract,route")
-    ap.add_argument("--stride", type=int, default=150)
-    args = ap.parse_args()
-    only = set(args.only.split(","))
+def measure(reads=50_000_000, steps=10, warmup=3, only="qual,qual_index,unmatched,extract,route", stride=150):
+    """Returns {stage: numbers}; used by this script and by bench.py's "post" key."""
+    import argparse as _a
+    args = _a.Namespace(reads=reads, steps=steps, warmup=warmup, stride=stride)
+    only = set(only.split(","))
 
     import numpy as np
     import torch
@@ -38,6 +34,7 @@ def main():
     table = w.table()
     samples = [sg.SampleMetadata(f"s{i}", bytes(table[i]), i) for i in range(S)]
     samples.append(sg.SampleMetadata(sg.UNDETERMINED_NAME, b"N" * L, S))
+    prev_stream = torch.cuda.current_stream()
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     d_table = torch.from_numpy(table).cuda()
@@ -137,7 +134,20 @@ def main():
         out["unmatched_top1000_ms"] = 1e3 * (time.perf_counter() - t0)
         out["unmatched_top_first"] = [top[0][0].decode(), top[0][1]] if top else None
         st2.close()
-    print(json.dumps(out))
+    torch.cuda.synchronize()
+    torch.cuda.set_stream(prev_stream)
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--reads", type=int, default=50_000_000)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--only", default="qual,qual_index,unmatched,extract,route")
+    ap.add_argument("--stride", type=int, default=150)
+    a = ap.parse_args()
+    print(json.dumps(measure(a.reads, a.steps, a.warmup, a.only, a.stride)))
 
 
 if __name__ == "__main__":
