@@ -68,3 +68,41 @@ def gather_metrics(metrics: DemuxedGroupMetrics, dst: int = 0, group=None) -> Op
         m.num_reads_failing_filters, m.num_reads_filtered_as_control = g["failing"], g["control"]
         parts.append(m)
     return merge_metrics(parts)
+
+
+def merge_unmatched(parts, n: int = 1000, index1_length: int = 0, max_map_size: int = 5_000_000,
+                    downsize_to: int = 5_000):
+    """Sum the unmatched-barcode maps of several shards (each one GpuMatcher.unmatched_counts()) and return the
+    rows of most_frequent_unmatched.tsv (metrics.rs:177-190).  The reference has one counter for the whole run
+    (metrics.rs:79-100); per-GPU tables are additive, so below max_map_size distinct keys the merge is exact."""
+    from .metrics import UnmatchedCounter
+    c = UnmatchedCounter(max_map_size, downsize_to)
+    for p in parts:
+        for k, v in p.items():
+            c.counts[k] = c.counts.get(k, 0) + int(v)
+        if len(c.counts) > max_map_size:
+            c.downsize()
+    return c.most_frequent(n, index1_length)
+
+
+def _gather_to(obj, dst: int, group):
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return [obj]
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    gathered = [None] * world if rank == dst else None
+    dist.gather_object(obj, gathered, dst=dst, group=group)
+    return gathered
+
+
+def gather_unmatched(counts: Dict[bytes, int], n: int = 1000, index1_length: int = 0, dst: int = 0, group=None):
+    """Every rank's unmatched map to rank ``dst`` -> merged top-n rows there, None elsewhere."""
+    parts = _gather_to(counts, dst, group)
+    return None if parts is None else merge_unmatched(parts, n, index1_length)
+
+
+def gather_base_qual(counters: np.ndarray, dst: int = 0, group=None) -> Optional[np.ndarray]:
+    """Sum of every rank's [(S+1), 5] base-quality counters (BaseQualCounter::update_with_self, metrics.rs:489-496)
+    on rank ``dst``; None elsewhere."""
+    parts = _gather_to(np.asarray(counters, dtype=np.uint64), dst, group)
+    return None if parts is None else np.sum(np.stack(parts), axis=0, dtype=np.uint64)

@@ -35,6 +35,17 @@ def _oracle_metrics(sg, w, table, reads):
     return sg.DemuxedGroupMetrics.from_device(res["per_sample"], res["total_templates"], hop)
 
 
+def _oracle_idx(w, table, reads):
+    from oracle import oracle as orc
+    cfg = orc.Config(w.num_samples, w.barcode_len, w.max_mismatches, w.min_delta, w.free_ns, -1,
+                     orc.MATCHER_CACHED_HAMMING, w.index1_len, w.barcode_len - w.index1_len)
+    return orc.COracle(cfg, table).run(reads, threads=2)["idx"]
+
+
+def _quals(n):
+    return np.random.default_rng(3).integers(33, 75, (n, 40), dtype=np.uint8)
+
+
 def _worker(rank, world, port, out_path):
     sys.path.insert(0, ROOT)
     import torch.distributed as dist
@@ -46,6 +57,19 @@ def _worker(rank, world, port, out_path):
         mine = _oracle_metrics(sg, w, table, reads[first:last])
         merged = sg.sharding.gather_metrics(mine, dst=0)
         assert (merged is None) == (rank != 0)
+        # the stages either side of the assignment: unmatched maps and base-quality counters merge by sum as well
+        from oracle import oracle as orc
+        res_idx = _oracle_idx(w, table, reads[first:last])
+        um = orc.unmatched_counts(reads[first:last], res_idx, w.num_samples)
+        rows = sg.sharding.gather_unmatched(um, n=50, index1_length=w.index1_len, dst=0)
+        quals = _quals(reads.shape[0])[first:last]
+        bq, _ = orc.base_qual_counts(quals, None, [(0, 40, "T")], res_idx, w.num_samples)
+        bq_all = sg.sharding.gather_base_qual(bq, dst=0)
+        assert (rows is None) == (bq_all is None) == (rank != 0)
+        if rank == 0:
+            with open(out_path + ".unmatched", "w") as f:
+                f.write(repr([(r.barcode, r.count) for r in rows]))
+            np.save(out_path + ".bq.npy", bq_all)
         if rank == 0:
             np.save(out_path, merged.per_sample_array())
             with open(out_path + ".hops", "w") as f:
@@ -91,3 +115,10 @@ def test_two_gloo_ranks_merge_to_single_pass(tmp_path):
     assert np.array_equal(np.load(out), whole.per_sample_array())
     assert open(out + ".total").read() == str(reads.shape[0])
     assert open(out + ".hops").read() == repr(sorted(whole.sample_barcode_hop_tracker.count_tracker.items()))
+    from oracle import oracle as orc
+    idx = _oracle_idx(w, table, reads)
+    want_rows = sg.sharding.merge_unmatched([orc.unmatched_counts(reads, idx, w.num_samples)], 50, w.index1_len)
+    assert open(out + ".unmatched").read() == repr([(r.barcode, r.count) for r in want_rows])
+    assert "+" in want_rows[0].barcode
+    want_bq, _ = orc.base_qual_counts(_quals(reads.shape[0]), None, [(0, 40, "T")], idx, w.num_samples)
+    assert np.array_equal(np.load(out + ".bq.npy"), want_bq)
