@@ -65,6 +65,43 @@ inline uint32_t exact_block_threads_impl(const DevParams &p) {
     return 0u;
 }
 
+// The same words with the widest loads the row stride allows (base pointer 16-byte aligned, L == 4 * LW): a warp's
+// 32 rows span 128 * LW bytes whatever the load width, so every request costs about LW wavefronts in the L1 data
+// pipe -- fewer, wider requests mean fewer wavefronts.  Rows of an odd number of words are 8-byte aligned for even
+// reads only: odd reads take their first word alone and pair the rest, even reads pair from the start.
+template <uint32_t LW>
+__device__ __forceinline__ void load_words_wide(const uint8_t *__restrict__ reads, uint64_t r, uint32_t (&rw)[LW]) {
+    const uint32_t *pw = reinterpret_cast<const uint32_t *>(reads) + r * LW;
+    if constexpr (LW % 4u == 0u) {
+#pragma unroll
+        for (uint32_t i = 0; i < LW / 4u; i++) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4 *>(pw) + i);
+            rw[4 * i] = v.x, rw[4 * i + 1] = v.y, rw[4 * i + 2] = v.z, rw[4 * i + 3] = v.w;
+        }
+    } else if constexpr (LW % 2u == 0u) {
+#pragma unroll
+        for (uint32_t i = 0; i < LW / 2u; i++) {
+            const uint2 v = __ldg(reinterpret_cast<const uint2 *>(pw) + i);
+            rw[2 * i] = v.x, rw[2 * i + 1] = v.y;
+        }
+    } else if constexpr (LW == 1u) {
+        rw[0] = __ldg(pw);
+    } else {
+        constexpr uint32_t NP = (LW - 1u) / 2u;
+        const uint32_t odd = (uint32_t)r & 1u;
+        uint2 v[NP];
+#pragma unroll
+        for (uint32_t i = 0; i < NP; i++) v[i] = __ldg(reinterpret_cast<const uint2 *>(pw + odd) + i);
+        const uint32_t single = __ldg(pw + (odd ? 0u : LW - 1u));
+#pragma unroll
+        for (uint32_t i = 0; i < NP; i++) {
+            rw[2 * i] = odd ? (i == 0u ? single : v[i == 0u ? 0u : i - 1u].y) : v[i].x;
+            rw[2 * i + 1] = odd ? v[i].x : v[i].y;
+        }
+        rw[LW - 1] = odd ? v[NP - 1].y : single;
+    }
+}
+
 // LW little-endian words of read r; bytes past L read as 'A' (what the table's rows are padded with)
 template <uint32_t LW, bool ALIGNED>
 __device__ __forceinline__ void load_words(const uint8_t *__restrict__ reads, uint64_t r, uint32_t L,
@@ -155,6 +192,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == 512u ? 3 : 1) sgdx_match_e
     __syncthreads();
 
     const uint32_t shift = 32u - p.ex_bits;
+    const bool wide = (reinterpret_cast<uintptr_t>(p.reads_ascii) & 15u) == 0u;  // front end: 64/128-bit loads
     uint32_t n1 = 0, n2 = 0, n3 = 0;  // queue fills, tracked identically by every thread
 
     // queue entries number the block's reads: iteration * (T*R) + offset inside the iteration's tile
@@ -307,7 +345,10 @@ __global__ void __launch_bounds__(THREADS, THREADS == 512u ? 3 : 1) sgdx_match_e
             for (uint32_t k = 0; k < R; k++) {
                 const uint64_t r = base + k * T + threadIdx.x;
                 if (k * T + threadIdx.x < nvalid) {
-                    load_words<LW, ALIGNED>(p.reads_ascii, r, p.L, rw[k]);
+                    // measured on a B200: 24-byte rows (C3) 2.01 -> 1.92 ms per 100 M reads with 64-bit loads; rows of
+                    // an odd number of words (C2, 20 bytes) lose to the lane-parity selects: 1.24 -> 1.35 ms
+                    if (ALIGNED && wide && LW % 2u == 0u) load_words_wide<LW>(p.reads_ascii, r, rw[k]);
+                    else load_words<LW, ALIGNED>(p.reads_ascii, r, p.L, rw[k]);
                 } else {
 #pragma unroll
                     for (uint32_t i = 0; i < LW; i++) rw[k][i] = 0u;  // never equals a barcode row
