@@ -397,3 +397,59 @@ def test_routing_after_assignment_c2():
     per = st.metrics().per_sample_array()
     assert np.array_equal(np.diff(want_off.astype(np.int64)), per[:, 0].astype(np.int64))
     st.close()
+
+
+# ------------------------------------------------------------------------------------------------
+# host threads, slots and streams
+# ------------------------------------------------------------------------------------------------
+def test_two_host_threads_share_one_handle_with_every_stage_on():
+    """`M: Matcher + Send + Sync` (demux.rs:422): two host threads, one slot each, assignment + unmatched table +
+    quality counters + routing on their own shards; the totals must equal the single-pass oracle."""
+    import threading
+    import torch
+    w = sg.synth.C1
+    n = 600_000
+    table = w.table()
+    reads = w.reads_host(0, n, table)
+    rng = np.random.default_rng(3)
+    quals = rng.integers(33, 75, (n, 48), dtype=np.uint8)
+    rs = RS("8B+T")
+    st = _stage(w, table, unmatched_on_device=True, slots=2)
+    want_idx = _oracle_idx(w, table, reads)
+    d_reads, d_quals = _cuda(reads), _cuda(quals)
+    d_idx = torch.empty(n, dtype=torch.int16, device="cuda")
+    d_order = torch.empty(n, dtype=torch.int32, device="cuda")
+    d_off = torch.zeros((2, w.num_samples + 2), dtype=torch.int64, device="cuda")
+    half = (n // 2) & ~15
+    errors = []
+
+    def work(slot, a, b):
+        try:
+            step = 37_504  # multiple of 16: quality tiles stay 16-byte aligned
+            for lo in range(a, b, step):
+                hi = min(lo + step, b)
+                m = st.matcher
+                m.match_device(d_reads.data_ptr() + lo * w.barcode_len, hi - lo, d_idx.data_ptr() + 2 * lo, 0, slot)
+                m.qual_counts_device(d_quals.data_ptr() + lo * 48, hi - lo, 48, rs, d_idx.data_ptr() + 2 * lo, 0, slot)
+                m.sync(slot)
+            st.matcher.route_device(d_idx.data_ptr() + 2 * a, b - a, d_order.data_ptr() + 4 * a,
+                                    d_off[slot].data_ptr(), slot)
+            st.matcher.sync(slot)
+        except Exception as e:  # noqa: BLE001
+            errors.append(e)
+
+    ts = [threading.Thread(target=work, args=(0, 0, half)), threading.Thread(target=work, args=(1, half, n))]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert not errors, errors
+    idx = d_idx.cpu().numpy().view(np.uint16)
+    assert np.array_equal(idx, want_idx)
+    assert st.matcher.unmatched_counts() == orc.unmatched_counts(reads, want_idx, w.num_samples)
+    got_q, _ = st.matcher.base_qual_counters()
+    want_q, _ = orc.base_qual_counts(quals, None, _segs(rs), want_idx, w.num_samples)
+    assert np.array_equal(got_q, want_q)
+    for slot, (a, b) in enumerate(((0, half), (half, n))):
+        o, off = orc.route_reads(want_idx[a:b], w.num_samples)
+        assert np.array_equal(d_order[a:b].cpu().numpy().view(np.uint32), o)
+        assert np.array_equal(d_off[slot].cpu().numpy().astype(np.uint64), off)
+    st.close()
