@@ -62,6 +62,7 @@ struct UnmatchedState {
     uint64_t sel_cap = 0;
     unsigned long long *d_hist = nullptr;
     uint64_t downsizes = 0;
+    int ctas_per_sm = 1;                    // resident CTAs of sgdx_unmatched_count per SM
 };
 
 struct QualState {

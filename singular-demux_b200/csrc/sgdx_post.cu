@@ -752,13 +752,7 @@ static UnmTable unm_table(const UnmatchedState &u) {
 
 int post_after_match(sgdx_handle *h, Slot &s, const uint8_t *d_ascii, const uint16_t *d_idx, uint64_t n) {
     UnmatchedState &u = h->unm;
-    static int per_sm = 0;  // resident CTAs per SM: the grid is exactly one wave
-    if (per_sm == 0) {
-        int v = 0;
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, sgdx_unmatched_count, (int)kUnmThreads, 0));
-        per_sm = v < 1 ? 1 : v;
-    }
-    const uint32_t grid = grid_cap(n, kUnmTile, h->sms, per_sm);
+    const uint32_t grid = grid_cap(n, kUnmTile, h->sms, u.ctas_per_sm);  // exactly one wave of resident CTAs
     sgdx_unmatched_count<<<grid, kUnmThreads, 0, s.stream>>>(d_ascii, d_idx, n, h->cfg.num_samples,
                                                              h->cfg.barcode_len, unm_table(u));
     CU(cudaGetLastError());
@@ -979,6 +973,9 @@ extern "C" int sgdx_unmatched_enable(sgdx_handle *h, uint64_t max_map_size, uint
     UnmatchedState &u = h->unm;
     u.max_map_size = max_map_size;
     u.downsize_to = downsize_to;
+    int per_sm = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sgdx_unmatched_count, (int)kUnmThreads, 0));
+    u.ctas_per_sm = per_sm < 1 ? 1 : per_sm;
     // room for a batch's worth of new keys between two syncs: 4x the limit, at least 2^21 slots (64 MB)
     uint64_t cap = 1ull << 21;  // key_limit must stay above the publishing lag of the distinct-key count
     while (cap < 4 * max_map_size) cap <<= 1;
