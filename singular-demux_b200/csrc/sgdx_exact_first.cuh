@@ -2,6 +2,8 @@
 // description at the top of sgdx_seeded.cu).  The kernel is a template over the number of 32-bit words per
 // read; sgdx_exact_words.cu instantiates it once per word count (compiled as eight objects, in parallel).
 #pragma once
+#include <cstdlib>
+
 #include "sgdx_seed_search.cuh"
 
 namespace sgdx {
@@ -27,17 +29,22 @@ struct ExactSmem {
     uint32_t *hist;          // [(S+1)*3] verdict counters of the block
     uint32_t *cq;            // [threads] Q3 entries that need the all-samples scan
     uint32_t *ring;          // [3] pushes of the current phase, one counter per phase modulo 3
+    uint32_t *stage;         // staged front end: the tile of T*R reads a bulk copy delivers (else empty)
+    uint64_t *bar;           // ... and its mbarrier
     uint16_t *hdr;           // [seed_hdr_total] seed index
     uint16_t *ids;           // [seed_ids_total]
 };
 
 __host__ __device__ inline size_t exact_carve(unsigned char *base, uint32_t threads, uint32_t S, uint32_t Lw,
                                               uint32_t ex_bits, uint32_t hdr_total, uint32_t ids_total,
-                                              ExactSmem *out) {
+                                              ExactSmem *out, uint32_t rpt = kExactReadsPerThread,
+                                              uint32_t stage_bytes = 0) {
     size_t o = 0;
     ExactSmem s;
+    s.bar = reinterpret_cast<uint64_t *>(base + o);          o += stage_bytes ? 128 : 0;                // 8-byte aligned
+    s.stage = reinterpret_cast<uint32_t *>(base + o);        o += (stage_bytes + 127u) & ~(size_t)127;  // 16-byte aligned
     s.table = reinterpret_cast<uint2 *>(base + o);           o += (size_t)S * 8;
-    s.q1 = reinterpret_cast<uint32_t *>(base + o);           o += (size_t)threads * (kExactReadsPerThread + 1) * 4;
+    s.q1 = reinterpret_cast<uint32_t *>(base + o);           o += (size_t)threads * (rpt + 1) * 4;
     s.q2 = reinterpret_cast<uint32_t *>(base + o);           o += (size_t)threads * 2 * 4;
     s.q3 = reinterpret_cast<uint32_t *>(base + o);           o += (size_t)threads * 2 * 4;
     s.slots = reinterpret_cast<uint32_t *>(base + o);        o += (size_t)4 << ex_bits;
@@ -51,8 +58,30 @@ __host__ __device__ inline size_t exact_carve(unsigned char *base, uint32_t thre
     return o;
 }
 
-inline size_t exact_smem_bytes_impl(const DevParams &p, uint32_t threads) {
-    return exact_carve(nullptr, threads, p.S, p.Lw, p.ex_bits, p.seed_hdr_total, p.seed_ids_total, nullptr);
+inline size_t exact_smem_bytes_impl(const DevParams &p, uint32_t threads, uint32_t rpt = kExactReadsPerThread,
+                                    uint32_t stage_bytes = 0) {
+    return exact_carve(nullptr, threads, p.S, p.Lw, p.ex_bits, p.seed_hdr_total, p.seed_ids_total, nullptr, rpt, stage_bytes);
+}
+
+// Staged front end (sgdx_match_exact_first<..., STAGED = true>): the tile of reads arrives in shared memory through
+// one 1-D bulk copy (cp.async.bulk + mbarrier) instead of 32-bit loads at the row stride; two reads per thread so
+// that three CTAs still fit an SM.
+constexpr uint32_t kStagedReadsPerThread = 4;
+
+__device__ __forceinline__ uint32_t xf_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void xf_stage_issue(uint64_t *bar, void *dst, const void *src, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(xf_smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     xf_smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(xf_smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void xf_stage_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tXFWAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@!p bra XFWAIT_%=;\n\t}" ::"r"(xf_smem_u32(bar)), "r"(parity)
+        : "memory");
 }
 
 // CTA size of sgdx_match_exact_first for this table: 512 threads while at least two CTAs fit an SM (measured on
@@ -171,14 +200,15 @@ __device__ __forceinline__ bool planes_if_acgt(const uint32_t (&rw)[LW], uint32_
     return bad == 0u;
 }
 
-template <uint32_t MODE, uint32_t LW, bool ALIGNED, uint32_t THREADS>
+template <uint32_t MODE, uint32_t LW, bool ALIGNED, uint32_t THREADS, bool STAGED = false>
 __global__ void __launch_bounds__(THREADS, THREADS == 512u ? 3 : 1) sgdx_match_exact_first(const DevParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr uint32_t nwarps = THREADS / 32, T = THREADS, R = STAGED ? kStagedReadsPerThread : kExactReadsPerThread;
+    constexpr uint32_t kStageBytes = STAGED ? T * R * LW * 4u : 0u;
     ExactSmem sm;
-    exact_carve(smem_raw, THREADS, p.S, LW, p.ex_bits, p.seed_hdr_total, p.seed_ids_total, &sm);
+    exact_carve(smem_raw, THREADS, p.S, LW, p.ex_bits, p.seed_hdr_total, p.seed_ids_total, &sm, R, kStageBytes);
     const uint32_t nbins = (p.S + 1u) * 3u;
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    constexpr uint32_t nwarps = THREADS / 32, T = THREADS, R = kExactReadsPerThread;
     constexpr uint32_t kNone = 0xFFFFFFFFu;
     const uint32_t nslots = 1u << p.ex_bits;
 
@@ -189,7 +219,19 @@ __global__ void __launch_bounds__(THREADS, THREADS == 512u ? 3 : 1) sgdx_match_e
     for (uint32_t i = threadIdx.x; i < p.seed_hdr_total; i += T) sm.hdr[i] = p.seed_hdr[i];
     for (uint32_t i = threadIdx.x; i < p.seed_ids_total; i += T) sm.ids[i] = p.seed_ids[i];
     if (threadIdx.x < 4) sm.ring[threadIdx.x] = 0u;
+    if (STAGED && threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(xf_smem_u32(sm.bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     __syncthreads();
+    // staged tiles: full tiles only (their byte count and start are multiples of 16); thread 0 issues the copy of
+    // the CTA's next tile as soon as the barrier that ends a front-end pass has freed the stage
+    auto stage_next = [&](uint64_t tile_base) {
+        if (STAGED && threadIdx.x == 0 && tile_base < p.n && p.n - tile_base >= (uint64_t)(T * R))
+            xf_stage_issue(sm.bar, sm.stage, p.reads_ascii + tile_base * (uint64_t)(LW * 4u), kStageBytes);
+    };
+    stage_next((uint64_t)blockIdx.x * (T * R));
+    uint32_t staged_done = 0;
 
     const uint32_t shift = 32u - p.ex_bits;
     const bool wide = (reinterpret_cast<uintptr_t>(p.reads_ascii) & 15u) == 0u;  // front end: 64/128-bit loads
@@ -341,6 +383,14 @@ __global__ void __launch_bounds__(THREADS, THREADS == 512u ? 3 : 1) sgdx_match_e
             uint32_t rw[R][LW];
             uint32_t hit[R];
             const uint32_t nvalid = (uint32_t)min((uint64_t)(T * R), p.n - base);  // reads of this tile (32-bit tests below)
+            if (STAGED && nvalid == T * R) {  // the tile is (being) delivered to shared memory
+                xf_stage_wait(sm.bar, staged_done & 1u);
+                staged_done++;
+#pragma unroll
+                for (uint32_t k = 0; k < R; k++)
+#pragma unroll
+                    for (uint32_t i = 0; i < LW; i++) rw[k][i] = sm.stage[(k * T + threadIdx.x) * LW + i];
+            } else
 #pragma unroll
             for (uint32_t k = 0; k < R; k++) {
                 const uint64_t r = base + k * T + threadIdx.x;
@@ -407,6 +457,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == 512u ? 3 : 1) sgdx_match_e
             n1 += end_phase();
             base += (uint64_t)gridDim.x * (T * R);
             iter++;
+            stage_next(base);  // every thread has its words in registers (barrier above)
         } else {
             break;
         }
@@ -419,17 +470,18 @@ __global__ void __launch_bounds__(THREADS, THREADS == 512u ? 3 : 1) sgdx_match_e
     }
 }
 
-template <uint32_t MODE, uint32_t LW, bool ALIGNED, uint32_t THREADS>
+template <uint32_t MODE, uint32_t LW, bool ALIGNED, uint32_t THREADS, bool STAGED = false>
 static cudaError_t launch_exact_t(const DevParams &p, int sms, cudaStream_t stream) {
-    size_t smem = exact_smem_bytes_impl(p, THREADS);
-    auto kern = sgdx_match_exact_first<MODE, LW, ALIGNED, THREADS>;
+    constexpr uint32_t R = STAGED ? kStagedReadsPerThread : kExactReadsPerThread;
+    size_t smem = exact_smem_bytes_impl(p, THREADS, R, STAGED ? THREADS * R * LW * 4u : 0u);
+    auto kern = sgdx_match_exact_first<MODE, LW, ALIGNED, THREADS, STAGED>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int per_sm = 0;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
-    kern<<<persistent_grid(p.n, THREADS * kExactReadsPerThread, sms, per_sm), THREADS, smem, stream>>>(p);
+    kern<<<persistent_grid(p.n, THREADS * R, sms, per_sm), THREADS, smem, stream>>>(p);
     return cudaGetLastError();
 }
 
@@ -438,6 +490,13 @@ template <uint32_t LW>
 cudaError_t launch_exact_words(const DevParams &p, uint32_t mode, int sms, cudaStream_t stream) {
     const bool aligned = (p.L & 3u) == 0u && (reinterpret_cast<uintptr_t>(p.reads_ascii) & 3u) == 0u;
     const bool big = exact_block_threads_impl(p) == 1024u;
+    // staged front end: 512-thread CTAs, rows of whole words, 16-byte aligned input, and the table + stage must
+    // still leave room for three CTAs per SM
+    const bool staged = getenv("SGDX_STAGED") && aligned && !big && (reinterpret_cast<uintptr_t>(p.reads_ascii) & 15u) == 0u &&
+                        exact_smem_bytes_impl(p, 512, kStagedReadsPerThread, 512u * kStagedReadsPerThread * LW * 4u) <= 113u * 1024u;
+    if (staged)
+        return mode == kModeHamming ? launch_exact_t<kModeHamming, LW, true, 512, true>(p, sms, stream)
+                                    : launch_exact_t<kModePreCompute, LW, true, 512, true>(p, sms, stream);
     if (mode == kModeHamming) {
         if (big) return aligned ? launch_exact_t<kModeHamming, LW, true, 1024>(p, sms, stream)
                                 : launch_exact_t<kModeHamming, LW, false, 1024>(p, sms, stream);

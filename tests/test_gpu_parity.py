@@ -561,3 +561,30 @@ def test_batch_larger_than_4_gib_of_barcodes():
         assert np.array_equal(d_idx[first:first + k].cpu().numpy().view(np.uint16), want["idx"])
         assert np.array_equal(d_dist[first:first + k].cpu().numpy(), want["dist"])
     st.close()
+
+
+def test_staged_front_end_is_bit_exact(monkeypatch):
+    """SGDX_STAGED=1 selects the bulk-copy (cp.async.bulk + mbarrier) front end of sgdx_match_exact_first, an
+    experiment that is not the default: full tiles come through shared memory, the ragged
+    last tile through ordinary loads.  Same verdicts and counters as the oracle."""
+    import torch
+    monkeypatch.setenv("SGDX_STAGED", "1")
+    w = sg.synth.C2
+    n = 1_000_003
+    table = w.table()
+    reads = w.reads_host(0, n, table)
+    st = _stage(table, sg.MatcherKind.CachedHammingDistance, w.max_mismatches, w.min_delta, w.free_ns, None,
+                w.index_lengths, sg.KERNEL_AUTO)
+    d_in = torch.from_numpy(reads).cuda()
+    d_idx = torch.empty(n, dtype=torch.int16, device="cuda")
+    d_dist = torch.empty(n, dtype=torch.uint8, device="cuda")
+    st.matcher.match_device(d_in.data_ptr(), n, d_idx.data_ptr(), d_dist.data_ptr())
+    st.matcher.sync(0)
+    want = _oracle(table, sg.MatcherKind.CachedHammingDistance, w.max_mismatches, w.min_delta, w.free_ns, None,
+                   w.index_lengths, reads)
+    assert np.array_equal(d_idx.cpu().numpy().view(np.uint16), want["idx"])
+    assert np.array_equal(d_dist.cpu().numpy(), want["dist"])
+    m = st.metrics()
+    assert np.array_equal(m.per_sample_array(), want["per_sample"]) and m.total_templates == n
+    assert m.sample_barcode_hop_tracker.count_tracker == want["hops"]
+    st.close()

@@ -453,3 +453,41 @@ def test_two_host_threads_share_one_handle_with_every_stage_on():
         assert np.array_equal(d_order[a:b].cpu().numpy().view(np.uint32), o)
         assert np.array_equal(d_off[slot].cpu().numpy().astype(np.uint64), off)
     st.close()
+
+
+def test_empty_batches_and_tiny_inputs_on_every_stage():
+    """n = 0 and n = 1 through every entry point (ragged ends of a run; demux.rs handles empty chunks too)."""
+    import torch
+    w = sg.synth.C1
+    table = w.table()
+    st = _stage(w, table, unmatched_on_device=True)
+    m = st.matcher
+    d = torch.zeros(4096, dtype=torch.uint8, device="cuda")
+    i16 = torch.zeros(64, dtype=torch.int16, device="cuda")
+    i32 = torch.zeros(64, dtype=torch.int32, device="cuda")
+    off = torch.full((w.num_samples + 2,), -1, dtype=torch.int64, device="cuda")
+    rs = RS("16B")
+    m.match_device(d.data_ptr(), 0, i16.data_ptr())
+    m.extract_device([d.data_ptr()], [16], [rs], 0, d.data_ptr() + 2048)
+    m.match_segments_device([d.data_ptr()], [16], [rs], 0, i16.data_ptr())
+    m.qual_counts_device(d.data_ptr(), 0, 16, rs, i16.data_ptr())
+    m.route_device(i16.data_ptr(), 0, i32.data_ptr(), off.data_ptr())
+    m.sync(0)
+    assert off.cpu().numpy().tolist() == [0] * (w.num_samples + 2)
+    assert m.unmatched_counts() == {} and m.unmatched_top(5) == []
+    assert int(m.base_qual_counters()[0].sum()) == 0
+    one = np.frombuffer(b"N" * 16, dtype=np.uint8).reshape(1, 16)
+    q1 = np.full((1, 16), ord("I"), dtype=np.uint8)
+    d_one, d_q1 = _cuda(one), _cuda(q1)
+    m.match_segments_device([d_one.data_ptr()], [16], [rs], 1, i16.data_ptr())
+    m.qual_counts_device(d_q1.data_ptr(), 1, 16, rs, i16.data_ptr())
+    m.route_device(i16.data_ptr(), 1, i32.data_ptr(), off.data_ptr())
+    m.sync(0)
+    assert int(i16[0]) == w.num_samples and int(i32[0]) == 0
+    assert off.cpu().numpy().tolist() == [0] * (w.num_samples + 1) + [1]
+    assert m.unmatched_top(5) == [(b"N" * 16, 1)]
+    got, short = m.base_qual_counters()
+    assert got[w.num_samples].tolist() == [0, 0, 16 * 40, 16, 0] and short == 0
+    info = m.unmatched_info()
+    assert info["unmatched_reads"] == 1 and info["distinct_keys"] == 1
+    st.close()
