@@ -134,7 +134,8 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--config", default="C2", choices=["C1", "C2", "C3", "C4"])
+    ap.add_argument("--config", default="C2", choices=["C1", "C2", "C3", "C4", "C5"],
+                    help="BASELINE.json configs; C5 = C2's table, 2 G reads split over the ranks (40 GB on one GPU)")
     ap.add_argument("--reads", type=int, default=0, help="reads per GPU per step (default: the config's size, capped)")
     ap.add_argument("--impl", default="sgdx", choices=["sgdx", "reference"])
     ap.add_argument("--kernel", type=int, default=0, help="0 auto, 1 direct, 2 seeded")
@@ -167,7 +168,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     w = sg.synth.CONFIGS[args.config]
-    n = args.reads or min(w.n_reads, 100_000_000)
+    n = args.reads or (w.n_reads // world if args.config == "C5" else min(w.n_reads, 100_000_000))
     L, S = w.barcode_len, w.num_samples
     table = w.table()
     kind = sg.select_matcher(L)
