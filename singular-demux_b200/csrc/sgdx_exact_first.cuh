@@ -64,8 +64,9 @@ inline size_t exact_smem_bytes_impl(const DevParams &p, uint32_t threads, uint32
 }
 
 // Staged front end (sgdx_match_exact_first<..., STAGED = true>): the tile of reads arrives in shared memory through
-// one 1-D bulk copy (cp.async.bulk + mbarrier) instead of 32-bit loads at the row stride; two reads per thread so
-// that three CTAs still fit an SM.
+// one 1-D bulk copy (cp.async.bulk + mbarrier) instead of 32-bit loads at the row stride.  Opt-in (SGDX_STAGED=1):
+// measured on C2 it does not beat the plain loads yet -- 4 reads per thread need a 40 KB stage (2 CTAs per SM,
+// 1.26 ms per 100 M reads against 1.23 ms), 2 reads per thread keep 3 CTAs but double the barriers (1.42 ms).
 constexpr uint32_t kStagedReadsPerThread = 4;
 
 __device__ __forceinline__ uint32_t xf_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -383,6 +384,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == 512u ? 3 : 1) sgdx_match_e
             uint32_t rw[R][LW];
             uint32_t hit[R];
             const uint32_t nvalid = (uint32_t)min((uint64_t)(T * R), p.n - base);  // reads of this tile (32-bit tests below)
+            bool staged_issued = false;
             if (STAGED && nvalid == T * R) {  // the tile is (being) delivered to shared memory
                 xf_stage_wait(sm.bar, staged_done & 1u);
                 staged_done++;
@@ -390,6 +392,11 @@ __global__ void __launch_bounds__(THREADS, THREADS == 512u ? 3 : 1) sgdx_match_e
                 for (uint32_t k = 0; k < R; k++)
 #pragma unroll
                     for (uint32_t i = 0; i < LW; i++) rw[k][i] = sm.stage[(k * T + threadIdx.x) * LW + i];
+                // every thread has its words in registers: refill the stage now, so that the copy of the CTA's
+                // next tile runs under this pass's hashing and probing
+                __syncthreads();
+                stage_next(base + (uint64_t)gridDim.x * (T * R));
+                staged_issued = true;
             } else
 #pragma unroll
             for (uint32_t k = 0; k < R; k++) {
@@ -457,7 +464,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == 512u ? 3 : 1) sgdx_match_e
             n1 += end_phase();
             base += (uint64_t)gridDim.x * (T * R);
             iter++;
-            stage_next(base);  // every thread has its words in registers (barrier above)
+            if (!staged_issued) stage_next(base);  // a pass that took ordinary loads leaves the stage free
         } else {
             break;
         }
