@@ -588,3 +588,59 @@ def test_staged_front_end_is_bit_exact(monkeypatch):
     assert np.array_equal(m.per_sample_array(), want["per_sample"]) and m.total_templates == n
     assert m.sample_barcode_hop_tracker.count_tracker == want["hops"]
     st.close()
+
+
+def test_full_size_properties_c3_with_unmatched_and_routing():
+    """BASELINE config C3 at its full size (1536 x (12+12), M=3, delta=1, 500 M reads = 12 GB of barcodes) in one
+    launch, with the unmatched table on and the routing after it: conservation, bincount of the index array ==
+    counters == run lengths of the routing, every routed run sorted (stable) and holding only its sample, the
+    unmatched totals == Undetermined's count, and the first / last half million reads against the oracle."""
+    import torch
+    w = sg.synth.C3
+    n = w.n_reads
+    assert n == 500_000_000
+    table = w.table()
+    d_table = torch.from_numpy(table).cuda()
+    d_in = torch.empty((n, w.barcode_len), dtype=torch.uint8, device="cuda")
+    w.reads_device(0, n, d_table.data_ptr(), d_in.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    st = sg.BarcodeAssignmentStage(_samples(table), sg.CachedHammingDistanceMatcher, w.max_mismatches, w.min_delta,
+                                   w.free_ns, None, w.index_lengths, unmatched_on_device=True,
+                                   most_unmatched_max_map_size=60_000_000)
+    S = w.num_samples
+    d_idx = torch.empty(n, dtype=torch.int16, device="cuda")
+    d_dist = torch.empty(n, dtype=torch.uint8, device="cuda")
+    d_order = torch.empty(n, dtype=torch.int32, device="cuda")
+    d_off = torch.zeros(S + 2, dtype=torch.int64, device="cuda")
+    st.matcher.match_device(d_in.data_ptr(), n, d_idx.data_ptr(), d_dist.data_ptr())
+    st.matcher.route_device(d_idx.data_ptr(), n, d_order.data_ptr(), d_off.data_ptr())
+    st.matcher.sync(0)
+    per = st.metrics().per_sample_array()
+    assert int(per[:, 0].sum()) == n == st.metrics().total_templates
+    hist = torch.zeros(S + 1, dtype=torch.int64, device="cuda")
+    for a in range(0, n, 50_000_000):
+        hist += torch.bincount(d_idx[a:a + 50_000_000].to(torch.int64) & 0xFFFF, minlength=S + 1)
+    assert np.array_equal(hist.cpu().numpy().astype(np.uint64), per[:, 0])
+    off = d_off.cpu().numpy()
+    assert off[0] == 0 and off[-1] == n and np.array_equal(np.diff(off).astype(np.uint64), per[:, 0])
+    for s in (0, 1, S // 2, S - 1, S):  # a few runs: ascending read ids (stable), all of that sample
+        run = d_order[int(off[s]):int(off[s + 1])].to(torch.int64)
+        if run.numel() > 1:
+            assert bool((run[1:] > run[:-1]).all())
+        assert bool(((d_idx[run].to(torch.int64) & 0xFFFF) == s).all())
+    info = st.matcher.unmatched_info()
+    assert info["unmatched_reads"] == int(per[S, 0]) and info["dropped_reads"] == 0 and info["downsizes"] == 0
+    top = st.matcher.unmatched_top(100)
+    assert len(top) == 100 and all(top[i][1] >= top[i + 1][1] for i in range(99))
+    k = 500_000
+    for first in (0, n - k):
+        reads = w.reads_host(first, k, table)
+        want = _oracle(table, sg.MatcherKind.CachedHammingDistance, w.max_mismatches, w.min_delta, w.free_ns, None,
+                       w.index_lengths, reads)
+        assert np.array_equal(d_idx[first:first + k].cpu().numpy().view(np.uint16), want["idx"])
+        assert np.array_equal(d_dist[first:first + k].cpu().numpy(), want["dist"])
+    um = orc.unmatched_counts(reads, want["idx"], S)  # the last slice's own unmatched keys are in the table
+    full = dict(top)
+    heavy = max(um.items(), key=lambda kv: kv[1])
+    assert heavy[1] <= full.get(heavy[0], 10 ** 18)
+    st.close()
