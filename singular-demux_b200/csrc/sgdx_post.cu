@@ -256,60 +256,52 @@ __global__ void __launch_bounds__(256) sgdx_unmatched_reinsert(const ulonglong2 
 // 2. segment extraction
 // ================================================================================================
 struct ExtractParams {
-    const uint8_t *src[SGDX_MAX_SOURCES];
-    uint32_t stride[SGDX_MAX_SOURCES];
-    uint8_t pos_src[SGDX_MAX_BARCODE_LEN];   // barcode position j comes from source pos_src[j] ...
-    uint16_t pos_off[SGDX_MAX_BARCODE_LEN];  // ... at read offset pos_off[j]
-    uint32_t L, magic;                       // magic = ceil(2^32 / L)
+    // the sample-barcode segments in concatenation order: segment i copies run_len[i] bytes from
+    // run_ptr[i] + read * run_stride[i] (its FASTQ's matrix + the segment's offset in the read)
+    const uint8_t *run_ptr[SGDX_MAX_SEGMENTS];
+    uint32_t run_stride[SGDX_MAX_SEGMENTS];
+    uint32_t run_len[SGDX_MAX_SEGMENTS];
+    uint32_t runs, L;
     uint64_t n;
     uint8_t *out;
     uint32_t words_ok;                       // out is 4-byte aligned
 };
-constexpr uint32_t kExtractTileReads = 1024;
+constexpr uint32_t kExtractThreads = 256;  // = reads per tile
 
-// One thread per output word: four gathered bytes, one coalesced 32-bit store.
-__global__ void __launch_bounds__(256) sgdx_extract(const ExtractParams p) {
-    // per barcode position: where its byte lives in read 0 of its source, and that source's stride (an indexed
-    // kernel parameter would go through the address-divergence unit on every byte)
-    __shared__ const uint8_t *s_ptr[SGDX_MAX_BARCODE_LEN];
-    __shared__ uint32_t s_stride[SGDX_MAX_BARCODE_LEN];
-    if (threadIdx.x < p.L) {
-        const uint32_t src = p.pos_src[threadIdx.x];
-        s_ptr[threadIdx.x] = p.src[src] + p.pos_off[threadIdx.x];
-        s_stride[threadIdx.x] = p.stride[src];
-    }
-    __syncthreads();
-    const uint64_t ntiles = (p.n + kExtractTileReads - 1) / kExtractTileReads;
+// One thread per read copies the byte runs of its sample-barcode segments (the segment list is indexed by the loop
+// counter, so it comes through the uniform datapath; inside a run the addresses are consecutive) into a
+// shared-memory tile; the CTA then writes the tile with coalesced 32-bit stores.  A 20-byte row stride is
+// conflict-free for the byte stores (bank = 5 * lane + pos / 4).
+__global__ void __launch_bounds__(kExtractThreads) sgdx_extract(const ExtractParams p) {
+    __shared__ __align__(16) uint8_t s_tile[kExtractThreads * SGDX_MAX_BARCODE_LEN];
+    const uint32_t L = p.L;
+    const uint64_t ntiles = (p.n + kExtractThreads - 1) / kExtractThreads;
     for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const uint64_t first = tile * kExtractTileReads;
-        const uint32_t cnt = (uint32_t)min((uint64_t)kExtractTileReads, p.n - first);
-        const uint32_t bytes = cnt * p.L;
-        uint8_t *out = p.out + first * p.L;  // first*L is a multiple of 4
-        if ((p.L & 3u) == 0u && p.words_ok) {  // a word never straddles two reads: one division per word
-            for (uint32_t o = threadIdx.x * 4u; o < bytes; o += blockDim.x * 4u) {
-                const uint32_t rl = __umulhi(o, p.magic);  // o / L: exact for o * L < 2^32
-                const uint32_t j = o - rl * p.L;
-                const uint64_t r = first + rl;
-                const uint32_t b0 = __ldg(s_ptr[j] + r * s_stride[j]), b1 = __ldg(s_ptr[j + 1] + r * s_stride[j + 1]);
-                const uint32_t b2 = __ldg(s_ptr[j + 2] + r * s_stride[j + 2]), b3 = __ldg(s_ptr[j + 3] + r * s_stride[j + 3]);
-                *reinterpret_cast<uint32_t *>(out + o) = b0 | (b1 << 8) | (b2 << 16) | (b3 << 24);
+        const uint64_t first = tile * kExtractThreads;
+        const uint32_t cnt = (uint32_t)min((uint64_t)kExtractThreads, p.n - first);
+        if (threadIdx.x < cnt) {
+            const uint64_t r = first + threadIdx.x;
+            uint8_t *row = s_tile + threadIdx.x * L;
+            for (uint32_t g = 0; g < p.runs; g++) {
+                const uint8_t *from = p.run_ptr[g] + r * p.run_stride[g];
+                const uint32_t len = p.run_len[g];
+#pragma unroll 4
+                for (uint32_t k = 0; k < len; k++) row[k] = __ldg(from + k);
+                row += len;
             }
-            continue;
         }
-        for (uint32_t o = threadIdx.x * 4u; o < bytes; o += blockDim.x * 4u) {
-            uint32_t w = 0;
-            const uint32_t nb = min(4u, bytes - o);
-            for (uint32_t b = 0; b < nb; b++) {
-                const uint32_t ob = o + b;
-                const uint32_t rl = __umulhi(ob, p.magic);
-                const uint32_t j = ob - rl * p.L;
-                const uint32_t c = __ldg(s_ptr[j] + (first + rl) * (uint64_t)s_stride[j]);
-                w |= c << (8u * b);
-            }
-            if (nb == 4u && p.words_ok) *reinterpret_cast<uint32_t *>(out + o) = w;
-            else
-                for (uint32_t b = 0; b < nb; b++) out[o + b] = (uint8_t)(w >> (8u * b));
+        __syncthreads();
+        const uint32_t bytes = cnt * L;
+        uint8_t *out = p.out + first * L;  // first * L is a multiple of 4
+        if (p.words_ok) {
+            const uint32_t words = bytes >> 2;
+            for (uint32_t i = threadIdx.x; i < words; i += kExtractThreads)
+                reinterpret_cast<uint32_t *>(out)[i] = reinterpret_cast<const uint32_t *>(s_tile)[i];
+            for (uint32_t i = (words << 2) + threadIdx.x; i < bytes; i += kExtractThreads) out[i] = s_tile[i];
+        } else {
+            for (uint32_t i = threadIdx.x; i < bytes; i += kExtractThreads) out[i] = s_tile[i];
         }
+        __syncthreads();
     }
 }
 
@@ -1056,11 +1048,8 @@ static int fill_extract(sgdx_handle *h, uint32_t num_sources, const uint8_t *con
     if (nsegs < 1 || nsegs > SGDX_MAX_SEGMENTS) return fail(SGDX_EINVAL, "1..%u segments", SGDX_MAX_SEGMENTS);
     const uint32_t L = h->cfg.barcode_len;
     memset(p, 0, sizeof *p);
-    for (uint32_t s = 0; s < num_sources; s++) {
+    for (uint32_t s = 0; s < num_sources; s++)
         if (!d_bases[s] || strides[s] == 0 || strides[s] > 0xFFFFu) return fail(SGDX_EINVAL, "source %u: null or stride outside 1..65535", s);
-        p->src[s] = d_bases[s];
-        p->stride[s] = strides[s];
-    }
     // sample-barcode segments in FASTQ order, then segment order (demux.rs:504-522)
     uint32_t pos = 0;
     for (uint32_t s = 0; s < num_sources; s++)
@@ -1070,15 +1059,16 @@ static int fill_extract(sgdx_handle *h, uint32_t num_sources, const uint8_t *con
             if (g.source != s || g.kind != SGDX_SEG_SAMPLE_BARCODE) continue;
             uint32_t len = g.length == SGDX_SEG_TO_END ? (g.offset < strides[s] ? strides[s] - g.offset : 0u) : g.length;
             if ((uint64_t)g.offset + len > strides[s]) return fail(SGDX_EINVAL, "segment %u runs past the stride of source %u", i, s);
-            for (uint32_t j = 0; j < len; j++, pos++) {
-                if (pos >= L) return fail(SGDX_EINVAL, "sample-barcode segments are longer than barcode_len %u", L);
-                p->pos_src[pos] = (uint8_t)s;
-                p->pos_off[pos] = (uint16_t)(g.offset + j);
-            }
+            if (pos + len > L) return fail(SGDX_EINVAL, "sample-barcode segments are longer than barcode_len %u", L);
+            if (len == 0) continue;
+            p->run_ptr[p->runs] = d_bases[s] + g.offset;
+            p->run_stride[p->runs] = strides[s];
+            p->run_len[p->runs] = len;
+            p->runs++;
+            pos += len;
         }
     if (pos != L) return fail(SGDX_EINVAL, "sample-barcode segments sum to %u bases, barcode_len is %u (run.rs:109-119)", pos, L);
     p->L = L;
-    p->magic = (uint32_t)(((1ull << 32) + L - 1) / L);
     return SGDX_OK;
 }
 
@@ -1100,7 +1090,7 @@ extern "C" int sgdx_extract_device(sgdx_handle *h, uint32_t slot, uint32_t num_s
     p.n = n;
     p.out = d_out;
     p.words_ok = (reinterpret_cast<uintptr_t>(d_out) & 3u) == 0u;
-    sgdx_extract<<<grid_cap(n, kExtractTileReads, h->sms, 8), 256, 0, h->slots[slot].stream>>>(p);
+    sgdx_extract<<<grid_cap(n, kExtractThreads, h->sms, 8), kExtractThreads, 0, h->slots[slot].stream>>>(p);
     CU(cudaGetLastError());
     h->launches.fetch_add(1);
     return SGDX_OK;
