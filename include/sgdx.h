@@ -235,6 +235,27 @@ int sgdx_base_qual_counters(sgdx_handle *h, sgdx_base_qual *per_sample /* S+1, U
 int sgdx_route_device(sgdx_handle *h, uint32_t slot, const uint16_t *d_idx, uint64_t n, uint32_t *d_order,
                       uint64_t *d_offsets /* S+2 */);
 
+/* ---- 5. one call per batch: the device-resident form of Demultiplex::demultiplex(&PerFastqRecordSet) ->
+ * DemuxedGroup (demux.rs:164-173,445-584) after the header filters: sample-barcode extraction from every FASTQ's
+ * reads, assignment with its counters (and the unmatched table when enabled), base-quality counters of every
+ * FASTQ that brings qualities, and -- when d_order is given -- the routing of the reads to their samples, all
+ * queued on the slot's stream.  Header rewriting, quality masking and the writers stay on the host. */
+typedef struct sgdx_fastq_view {   /* the records of one FASTQ of the batch as fixed-stride matrices on the device */
+    const uint8_t *d_bases;        /* n * stride */
+    const uint8_t *d_quals;        /* n * stride, 16-byte aligned; NULL = no quality counters from this FASTQ */
+    const uint32_t *d_lens;        /* per-read length <= stride; NULL = every read is `stride` long */
+    uint32_t stride;
+} sgdx_fastq_view;
+typedef struct sgdx_demux_out {
+    uint16_t *d_sample_idx;        /* n; S = Undetermined (demux.rs:535-538) */
+    uint8_t *d_hamming_dist;       /* n, nullable */
+    uint32_t *d_order;             /* n, nullable: per_sample_reads as one stable permutation ... */
+    uint64_t *d_offsets;           /* ... and its S+2 run bounds (required with d_order) */
+} sgdx_demux_out;
+int sgdx_demultiplex_device(sgdx_handle *h, uint32_t slot, const sgdx_fastq_view *fastqs, uint32_t num_fastqs,
+                            const sgdx_segment *segments /* .source = index into fastqs */, uint32_t num_segments,
+                            uint64_t n, const sgdx_demux_out *out);
+
 /* ---- measurement support */
 /* Integer-pipe micro-benchmark on `device`: sustained 32-bit POPC and LOP3 results per second. */
 int sgdx_measure_int_peak(int device, double *popc_per_s, double *lop3_per_s);

@@ -420,3 +420,71 @@ def route_reads(idx: np.ndarray, num_samples: int) -> Tuple[np.ndarray, np.ndarr
     offsets = np.zeros(num_samples + 2, dtype=np.uint64)
     offsets[1:] = np.cumsum(counts)
     return order, offsets
+
+
+class LiteralDemultiplexer:
+    """Demultiplexer::demultiplex (demux.rs:445-584) for templates that passed the header filters, read by read in
+    plain Python (small inputs): process_segments over every FASTQ (360-417: extraction, BaseQualCounter), the
+    concatenated sample barcode (504-522), the N gate and the matcher (524-538), update_with_match, hop check and
+    unmatched collection (541-556), routing (578), total_templates and the quality counters of the template's
+    sample (581-583).  fastqs = [(bases [n, stride], quals [n, stride], lens [n] or None)], structures[f] = list
+    of (offset, length | None, kind)."""
+
+    def __init__(self, cfg: Config, samples: Sequence[bytes]):
+        self.demux = LiteralDemux(cfg, samples)
+        self.cfg = cfg
+
+    def run(self, fastqs, structures):
+        S = self.cfg.num_samples
+        n = fastqs[0][0].shape[0]
+        qual = np.zeros((S + 1, 5), dtype=np.uint64)
+        per_sample_reads = [[] for _ in range(S + 1)]
+        barcodes, counters = [], []
+        for r in range(n):
+            bc = b""
+            counter = [0, 0, 0, 0, 0]  # q20, q30, index sum, index seen, bases
+            for (bases, quals, lens), segs in zip(fastqs, structures):
+                ln = bases.shape[1] if lens is None else int(lens[r])
+                for (off, length, kind) in segs:
+                    end = ln if length is None else off + length
+                    sb, sq = bases[r, off:end], quals[r, off:end]
+                    if kind == "B":
+                        bc += sb.tobytes()
+                        counter[3] += len(sq)
+                        counter[2] += int(sum((int(q) - 33) & 0xFF for q in sq))
+                    elif kind == "T":
+                        counter[4] += len(sq)
+                        for q in sq:
+                            q = (int(q) - 33) & 0xFF
+                            if q >= 30:
+                                counter[1] += 1
+                                counter[0] += 1
+                            elif q >= 20:
+                                counter[0] += 1
+            barcodes.append(bc)
+            counters.append(counter)
+        res = self.demux.run(barcodes)
+        for r in range(n):  # routing (578) and the template's quality counters added to its sample (582-583)
+            b = int(res["idx"][r])
+            per_sample_reads[b].append(r)
+            qual[b] += np.array(counters[r], dtype=np.uint64)
+        res["per_sample_reads"] = per_sample_reads
+        res["base_qual"] = qual
+        res["barcodes"] = barcodes
+        return res
+
+
+def demultiplex_batch(cfg: Config, samples: Sequence[bytes], fastqs, structures):
+    """The same stage composed from the vectorised restatements above (any size): returns idx, dist, per_sample,
+    hops, unmatched, base_qual [(S+1), 5], order, offsets."""
+    S = cfg.num_samples
+    barcodes = extract_sample_barcodes([f[0] for f in fastqs], structures)
+    res = COracle(cfg, [bytes(s) for s in samples]).run(barcodes, threads=4)
+    qual = np.zeros((S + 1, 5), dtype=np.uint64)
+    for (bases, quals, lens), segs in zip(fastqs, structures):
+        qual += base_qual_counts(quals, lens, segs, res["idx"], S)[0]
+    res["base_qual"] = qual
+    res["unmatched"] = unmatched_counts(barcodes, res["idx"], S)
+    res["order"], res["offsets"] = route_reads(res["idx"], S)
+    res["barcodes"] = barcodes
+    return res

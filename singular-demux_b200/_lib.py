@@ -50,6 +50,15 @@ class BaseQual(C.Structure):
                 ("index_bases_total_seen", C.c_uint64), ("bases", C.c_uint64)]
 
 
+class FastqView(C.Structure):
+    _fields_ = [("d_bases", C.c_void_p), ("d_quals", C.c_void_p), ("d_lens", C.c_void_p), ("stride", C.c_uint32)]
+
+
+class DemuxOut(C.Structure):
+    _fields_ = [("d_sample_idx", C.c_void_p), ("d_hamming_dist", C.c_void_p), ("d_order", C.c_void_p),
+                ("d_offsets", C.c_void_p)]
+
+
 SEG_TO_END = 0xFFFFFFFF
 MAX_SOURCES, MAX_SEGMENTS = 8, 32
 
@@ -69,7 +78,7 @@ SYMBOLS = [
     "sgdx_batcher_flush", "sgdx_batcher_next", "sgdx_measure_int_peak",
     "sgdx_unmatched_enable", "sgdx_unmatched_info_get", "sgdx_unmatched_export", "sgdx_unmatched_top",
     "sgdx_unmatched_downsize", "sgdx_extract_device", "sgdx_match_segments_device", "sgdx_qual_counts_device",
-    "sgdx_base_qual_counters", "sgdx_route_device",
+    "sgdx_base_qual_counters", "sgdx_route_device", "sgdx_demultiplex_device",
     "sgdx_synth_table", "sgdx_synth_reads_host", "sgdx_synth_reads_device",
 ]
 
@@ -126,6 +135,8 @@ def lib() -> C.CDLL:
     L.sgdx_qual_counts_device.argtypes = [vp, u32, vp, u64, u32, vp, C.POINTER(Segment), u32, vp]
     L.sgdx_base_qual_counters.argtypes = [vp, C.POINTER(BaseQual), C.POINTER(u64)]
     L.sgdx_route_device.argtypes = [vp, u32, vp, u64, vp, vp]
+    L.sgdx_demultiplex_device.argtypes = [vp, u32, C.POINTER(FastqView), u32, C.POINTER(Segment), u32, u64,
+                                          C.POINTER(DemuxOut)]
     L.sgdx_measure_int_peak.argtypes = [i32, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.sgdx_synth_table.argtypes = [u64, u32, u32, u32, u32, vp]
     L.sgdx_synth_reads_host.argtypes = [C.POINTER(SynthParams), vp, u64, u64, vp, i32]

@@ -1305,3 +1305,44 @@ extern "C" int sgdx_route_device(sgdx_handle *h, uint32_t slot, const uint16_t *
     h->launches.fetch_add(n ? 4 : 3);
     return SGDX_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// C ABI: one call per batch
+// ------------------------------------------------------------------------------------------------
+extern "C" int sgdx_demultiplex_device(sgdx_handle *h, uint32_t slot, const sgdx_fastq_view *fastqs, uint32_t num_fastqs,
+                                       const sgdx_segment *segs, uint32_t nsegs, uint64_t n, const sgdx_demux_out *out) {
+    if (int rc = check_slot_post(h, slot)) return rc;
+    if (!fastqs || !segs || !out) return fail(SGDX_EINVAL, "sgdx_demultiplex_device: null argument");
+    if (num_fastqs < 1 || num_fastqs > SGDX_MAX_SOURCES) return fail(SGDX_EINVAL, "1..%u FASTQs", SGDX_MAX_SOURCES);
+    if (nsegs < 1 || nsegs > SGDX_MAX_SEGMENTS) return fail(SGDX_EINVAL, "1..%u segments", SGDX_MAX_SEGMENTS);
+    if (n && !out->d_sample_idx) return fail(SGDX_EINVAL, "sgdx_demultiplex_device: null sample index output");
+    if (out->d_order && !out->d_offsets) return fail(SGDX_EINVAL, "sgdx_demultiplex_device: d_order needs d_offsets");
+    const uint8_t *bases[SGDX_MAX_SOURCES];
+    uint32_t strides[SGDX_MAX_SOURCES];
+    for (uint32_t f = 0; f < num_fastqs; f++) {
+        bases[f] = fastqs[f].d_bases;
+        strides[f] = fastqs[f].stride;
+    }
+    // demux.rs:504-522 (barcode of the template) + 524-556 (assignment, counters, hop check, unmatched)
+    if (int rc = sgdx_match_segments_device(h, slot, num_fastqs, bases, strides, segs, nsegs, n, out->d_sample_idx,
+                                            out->d_hamming_dist))
+        return rc;
+    // demux.rs:360-417 (per-segment quality counters) + 582-583 (added to the template's sample)
+    for (uint32_t f = 0; f < num_fastqs; f++) {
+        if (!fastqs[f].d_quals) continue;
+        sgdx_segment own[SGDX_MAX_SEGMENTS];
+        uint32_t k = 0;
+        for (uint32_t i = 0; i < nsegs; i++)
+            if (segs[i].source == f) {
+                own[k] = segs[i];
+                own[k++].source = 0;
+            }
+        if (k == 0) continue;
+        if (int rc = sgdx_qual_counts_device(h, slot, fastqs[f].d_quals, n, fastqs[f].stride, fastqs[f].d_lens, own, k,
+                                             out->d_sample_idx))
+            return rc;
+    }
+    // demux.rs:578: per_sample_reads[sample_idx].push(read), as a permutation
+    if (out->d_order) return sgdx_route_device(h, slot, out->d_sample_idx, n, out->d_order, out->d_offsets);
+    return SGDX_OK;
+}

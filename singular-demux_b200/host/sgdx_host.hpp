@@ -287,6 +287,21 @@ class BarcodeAssignmentStage {
         check(sgdx_qual_counts_device(matcher_.handle(), slot, d_quals, n, stride, d_lens, rs.segments.data(),
                                       (uint32_t)rs.segments.size(), d_sample_indices), "sgdx_qual_counts_device");
     }
+    // Demultiplex::demultiplex (demux.rs:164-173,445-584) for a device-resident batch: extraction, assignment with
+    // its counters (and the unmatched table when collect_unmatched() was called), quality counters of every FASTQ
+    // that brings qualities, routing when out.d_order is set -- all queued on the slot's stream
+    void demultiplex_device(const std::vector<sgdx_fastq_view> &fastqs, const std::vector<ReadStructure> &structures,
+                            uint64_t n, const sgdx_demux_out &out, unsigned slot = 0) {
+        if (fastqs.size() != structures.size()) throw std::invalid_argument("one read structure per FASTQ (run.rs:109-119)");
+        std::vector<sgdx_segment> segs;
+        for (size_t f = 0; f < structures.size(); f++)
+            for (sgdx_segment g : structures[f].segments) {
+                g.source = (uint32_t)f;
+                segs.push_back(g);
+            }
+        check(sgdx_demultiplex_device(matcher_.handle(), slot, fastqs.data(), (uint32_t)fastqs.size(), segs.data(),
+                                      (uint32_t)segs.size(), n, &out), "sgdx_demultiplex_device");
+    }
     std::vector<BaseQualCounter> base_qual_counters() {  // one per sample, Undetermined last
         std::vector<sgdx_base_qual> raw(matcher_.num_samples() + 1);
         check(sgdx_base_qual_counters(matcher_.handle(), raw.data(), nullptr), "sgdx_base_qual_counters");

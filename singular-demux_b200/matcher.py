@@ -304,6 +304,22 @@ class GpuMatcher:
         check(lib().sgdx_route_device(self._h, slot, d_idx_ptr, n, d_order_ptr, d_offsets_ptr), "sgdx_route_device")
 
 
+    # -- Demultiplex::demultiplex for a device-resident batch (demux.rs:445-584) -----------------------------------
+    def demultiplex_device(self, fastqs, structures, n: int, d_idx_ptr: int, d_dist_ptr: int = 0, d_order_ptr: int = 0,
+                           d_offsets_ptr: int = 0, slot: int = 0) -> None:
+        """fastqs: one (d_bases_ptr, d_quals_ptr or 0, d_lens_ptr or 0, stride) per FASTQ; structures: their
+        ReadStructures.  Extraction + assignment (+ unmatched table) + quality counters (+ routing) on one stream."""
+        from ._lib import DemuxOut, FastqView
+        from .read_structure import c_segments
+        views = (FastqView * len(fastqs))()
+        for i, (b, q, ln, stride) in enumerate(fastqs):
+            views[i] = FastqView(int(b), int(q) or None, int(ln) or None, int(stride))
+        segs, ns = c_segments(structures)
+        out = DemuxOut(int(d_idx_ptr), int(d_dist_ptr) or None, int(d_order_ptr) or None, int(d_offsets_ptr) or None)
+        check(lib().sgdx_demultiplex_device(self._h, slot, views, len(fastqs), segs, ns, n, C.byref(out)),
+              "sgdx_demultiplex_device")
+
+
 class CachedHammingDistanceMatcher(GpuMatcher):
     """matcher.rs:80-109. The reference's per-thread LRU memo is an implementation detail of its CPU
     scan (semantically transparent); the kernel re-evaluates every read instead."""

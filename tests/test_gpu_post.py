@@ -491,3 +491,70 @@ def test_empty_batches_and_tiny_inputs_on_every_stage():
     info = m.unmatched_info()
     assert info["unmatched_reads"] == 1 and info["distinct_keys"] == 1
     st.close()
+
+
+# ------------------------------------------------------------------------------------------------
+# 5. one call per batch
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("layout", ["dual_index_paired_end", "inline_single_end"])
+def test_demultiplex_device_equals_the_per_batch_oracle(layout):
+    """sgdx_demultiplex_device = Demultiplex::demultiplex for a device-resident batch (demux.rs:445-584): index,
+    distance, per-sample counters, hop map, unmatched map, quality counters and per-sample read lists, all against
+    oracle.demultiplex_batch (itself checked against the read-by-read restatement on CPU)."""
+    import torch
+    rng = np.random.default_rng(21)
+    letters = np.frombuffer(b"ACGTN", dtype=np.uint8)
+    if layout == "dual_index_paired_end":
+        w = sg.synth.C2
+        n = 150_000
+        table = w.table()
+        bc = w.reads_host(0, n, table)
+        i1 = bc[:, :10].copy()
+        i2 = letters[rng.integers(0, 4, (n, 12))].copy()
+        i2[:, 2:12] = bc[:, 10:]
+        r1 = letters[rng.integers(0, 5, (n, 151))].copy()
+        r2 = letters[rng.integers(0, 5, (n, 100))].copy()
+        arrays, structs = [i1, i2, r1, r2], ["10B", "2S10B", "+T", "8M92T"]
+        ragged = {2: rng.integers(0, 152, n).astype(np.uint32)}
+    else:
+        w = sg.synth.C4
+        n = 200_000
+        table = w.table()
+        bc = w.reads_host(0, n, table)
+        r1 = letters[rng.integers(0, 5, (n, 158))].copy()
+        r1[:, :8] = bc
+        arrays, structs = [r1], ["8B+T"]
+        ragged = {0: rng.integers(8, 159, n).astype(np.uint32)}
+    rss = [RS(s) for s in structs]
+    quals = [rng.integers(33, 75, a.shape, dtype=np.uint8) for a in arrays]
+    kind = sg.select_matcher(w.barcode_len)
+    il = w.index_lengths
+    cfg = orc.Config(w.num_samples, w.barcode_len, w.max_mismatches, w.min_delta, w.free_ns, -1, ORC_KIND[kind],
+                     il[0] if il else 0, il[1] if il else 0)
+    want = orc.demultiplex_batch(cfg, [bytes(t) for t in table],
+                                 [(a, q, ragged.get(i)) for i, (a, q) in enumerate(zip(arrays, quals))],
+                                 [_segs(rs) for rs in rss])
+    st = _stage(w, table, unmatched_on_device=True)
+    m = st.matcher
+    d_a, d_q = [_cuda(a) for a in arrays], [_cuda(q) for q in quals]
+    d_l = {i: _cuda(v) for i, v in ragged.items()}
+    d_idx = torch.empty(n, dtype=torch.int16, device="cuda")
+    d_dist = torch.empty(n, dtype=torch.uint8, device="cuda")
+    d_order = torch.empty(n, dtype=torch.int32, device="cuda")
+    d_off = torch.zeros(w.num_samples + 2, dtype=torch.int64, device="cuda")
+    fastqs = [(d_a[i].data_ptr(), d_q[i].data_ptr(), d_l[i].data_ptr() if i in d_l else 0, arrays[i].shape[1])
+              for i in range(len(arrays))]
+    m.demultiplex_device(fastqs, rss, n, d_idx.data_ptr(), d_dist.data_ptr(), d_order.data_ptr(), d_off.data_ptr())
+    m.sync(0)
+    assert np.array_equal(d_idx.cpu().numpy().view(np.uint16), want["idx"])
+    assert np.array_equal(d_dist.cpu().numpy(), want["dist"])
+    met = st.metrics()
+    assert np.array_equal(met.per_sample_array(), want["per_sample"]) and met.total_templates == n
+    if il:
+        assert met.sample_barcode_hop_tracker.count_tracker == want["hops"]
+    assert m.unmatched_counts() == want["unmatched"]
+    got_q, short = m.base_qual_counters()
+    assert np.array_equal(got_q, want["base_qual"]) and short == 0
+    assert np.array_equal(d_order.cpu().numpy().view(np.uint32), want["order"])
+    assert np.array_equal(d_off.cpu().numpy().astype(np.uint64), want["offsets"])
+    st.close()

@@ -108,3 +108,48 @@ def test_post_calls_validate_before_touching_cuda():
     assert L.sgdx_route_device(None, 0, None, 0, None, None) == -1
     assert L.sgdx_base_qual_counters(None, None, None) == -1
     assert L.sgdx_qual_counts_device(None, 0, None, 0, 150, None, None, 0, None) == -1
+
+
+def test_literal_demultiplexer_reproduces_reference_run():
+    """run.rs:1040-1157 through the read-by-read restatement of demux.rs:445-584: four 17B39T reads of sample 1
+    -> 4 templates, 156 bases, 44 >= Q30, 84 >= Q20 on sample 1, nothing anywhere else."""
+    table = [b"AAAAAAAAGATTACAGA", b"CCCCCCCCGATTACAGA", b"GGGGGGGGGATTACAGA", b"GGGGGGTTGATTACAGA"]
+    cfg = orc.Config(4, 17, 2, 1, 1, 1, orc.MATCHER_CACHED_HAMMING, 0, 0)
+    bases = np.frombuffer((table[0] + b"A" * 39) * 4, dtype=np.uint8).reshape(4, 56)
+    quals = np.array([[63] * 17 + list(range(35, 74))] * 4, dtype=np.uint8)
+    res = orc.LiteralDemultiplexer(cfg, table).run([(bases, quals, None)], [_segs(RS("17B39T"))])
+    assert res["idx"].tolist() == [0, 0, 0, 0] and res["total_templates"] == 4
+    assert res["per_sample"][0].tolist() == [4, 4, 0]
+    assert res["base_qual"][0].tolist() == [84, 44, 17 * 30 * 4, 17 * 4, 156] and int(res["base_qual"][1:].sum()) == 0
+    assert res["per_sample_reads"][0] == [0, 1, 2, 3] and res["unmatched"] == {}
+
+
+def test_vectorised_demultiplex_equals_the_literal_one():
+    """The composed numpy/C oracle against the read-by-read one on a small ragged dual-index paired-end batch."""
+    rng = np.random.default_rng(12)
+    w = sg.synth.Workload("lit", 12, 12, 6, 1, 1, n_reads=600, table_seed=5, read_seed=6, p_true=0.7, p_hop=0.1, p_n=0.02)
+    table = w.table()
+    bc = w.reads_host(0, 600, table, threads=1)
+    n = 600
+    letters = np.frombuffer(b"ACGTN", dtype=np.uint8)
+    r1 = letters[rng.integers(0, 5, (n, 30))].copy()
+    r2 = letters[rng.integers(0, 5, (n, 25))].copy()
+    i1, i2 = bc[:, :6].copy(), letters[rng.integers(0, 5, (n, 9))].copy()
+    i2[:, 3:9] = bc[:, 6:]
+    fq = []
+    for a in (i1, i2, r1, r2):
+        q = rng.integers(33, 75, a.shape, dtype=np.uint8)
+        q[rng.random(a.shape) < 0.01] = 20  # below '!': wraps
+        fq.append([a, q, None])
+    fq[2][2] = rng.integers(4, 31, n).astype(np.uint32)   # R1 ragged: 4M+T needs >= 4
+    structures = [_segs(RS(s)) for s in ("6B", "3S6B", "4M+T", "25T")]
+    cfg = orc.Config(12, 12, 1, 1, 1, -1, orc.MATCHER_CACHED_HAMMING, 6, 6)
+    lit = orc.LiteralDemultiplexer(cfg, [bytes(t) for t in table]).run([tuple(f) for f in fq], structures)
+    vec = orc.demultiplex_batch(cfg, [bytes(t) for t in table], [tuple(f) for f in fq], structures)
+    assert np.array_equal(lit["idx"], vec["idx"]) and np.array_equal(lit["dist"], vec["dist"])
+    assert np.array_equal(lit["per_sample"], vec["per_sample"]) and lit["hops"] == vec["hops"]
+    assert lit["unmatched"] == vec["unmatched"] and len(lit["unmatched"]) > 10
+    assert np.array_equal(lit["base_qual"], vec["base_qual"])
+    for s in range(13):
+        assert lit["per_sample_reads"][s] == vec["order"][int(vec["offsets"][s]):int(vec["offsets"][s + 1])].tolist()
+    assert [bytes(b) for b in vec["barcodes"]] == lit["barcodes"]
