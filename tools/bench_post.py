@@ -16,7 +16,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def measure(reads=50_000_000, steps=10, warmup=3, only="qual,qual_index,unmatched,extract,route", stride=150):
+def measure(reads=50_000_000, steps=10, warmup=3, only="qual,qual_index,unmatched,extract,route,demultiplex", stride=150):
     """Returns {stage: numbers}; used by this script and by bench.py's "post" key."""
     import argparse as _a
     args = _a.Namespace(reads=reads, steps=steps, warmup=warmup, stride=stride)
@@ -112,6 +112,31 @@ def measure(reads=50_000_000, steps=10, warmup=3, only="qual,qual_index,unmatche
         line("route", ms, best, n * (2 + 2 + 4), "sgdx_route_hist + scan + sgdx_route_scatter",
              {"bytes_per_read": 8, "note": "index array read twice (histogram, scatter), 4-byte read id written once"})
         del d_order
+    if "demultiplex" in only:
+        # Demultiplex::demultiplex for a whole paired-end dual-index batch resident on the device: I1 10B, I2 10B,
+        # R1 150T, R2 150T with qualities -> extraction, assignment, four quality passes, routing (one call)
+        nd = min(n, 20_000_000)
+        g = torch.Generator(device="cuda")
+        g.manual_seed(3)
+        d_i1 = d_in[:nd, :10].contiguous()
+        d_i2 = d_in[:nd, 10:].contiguous()
+        d_qi = torch.randint(33, 75, (nd, 10), dtype=torch.uint8, device="cuda", generator=g)
+        d_r = torch.randint(33, 75, (nd, 150), dtype=torch.uint8, device="cuda", generator=g)  # stands for bases and quals
+        d_order = torch.empty(nd, dtype=torch.int32, device="cuda")
+        d_off = torch.zeros(S + 2, dtype=torch.int64, device="cuda")
+        d_dist = torch.empty(nd, dtype=torch.uint8, device="cuda")
+        fastqs = [(d_i1.data_ptr(), d_qi.data_ptr(), 0, 10), (d_i2.data_ptr(), d_qi.data_ptr(), 0, 10),
+                  (d_r.data_ptr(), d_r.data_ptr(), 0, 150), (d_r.data_ptr(), d_r.data_ptr(), 0, 150)]
+        rss = [RS("10B"), RS("10B"), RS("150T"), RS("150T")]
+        ms, best = timed(lambda: m.demultiplex_device(fastqs, rss, nd, d_idx.data_ptr(), d_dist.data_ptr(),
+                                                      d_order.data_ptr(), d_off.data_ptr()))
+        nbytes = nd * (20 + 20 + 300 + 20 + 3 + 8)
+        out["demultiplex_device"] = {
+            "kernel": "sgdx_extract + sgdx_match_exact_first + 4 x sgdx_qual_counts + sgdx_route_*", "templates": nd,
+            "avg_ms": ms, "best_ms": best, "templates_per_s": nd / (ms * 1e-3), "bytes": nbytes,
+            "achieved_gbs": nbytes / (ms * 1e-3) / 1e9, "frac_of_hbm_peak": nbytes / (ms * 1e-3) / 1e9 / peak,
+            "layout": "I1 10B + I2 10B + R1 150T + R2 150T, qualities of all four FASTQs counted, routing on"}
+        del d_i1, d_i2, d_qi, d_r, d_order, d_dist
     stage.close()
     if "unmatched" in only:
         st2 = sg.BarcodeAssignmentStage(samples, sg.CachedHammingDistanceMatcher, w.max_mismatches, w.min_delta,
@@ -144,7 +169,7 @@ def main():
     ap.add_argument("--reads", type=int, default=50_000_000)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--only", default="qual,qual_index,unmatched,extract,route")
+    ap.add_argument("--only", default="qual,qual_index,unmatched,extract,route,demultiplex")
     ap.add_argument("--stride", type=int, default=150)
     a = ap.parse_args()
     print(json.dumps(measure(a.reads, a.steps, a.warmup, a.only, a.stride)))
