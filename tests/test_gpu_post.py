@@ -558,3 +558,44 @@ def test_demultiplex_device_equals_the_per_batch_oracle(layout):
     assert np.array_equal(d_order.cpu().numpy().view(np.uint32), want["order"])
     assert np.array_equal(d_off.cpu().numpy().astype(np.uint64), want["offsets"])
     st.close()
+
+
+def test_unmatched_table_under_heavy_contention():
+    """Ten million reads, almost all of them unmatched: 40 % one key (all N), 30 % sixteen hot keys, the rest
+    distinct random 24-mers -- same-slot claims and same-address adds from every CTA at once.  Exact counts."""
+    rng = np.random.default_rng(99)
+    w = sg.synth.Workload("h", 32, 24, 12, 1, 2, n_reads=0, table_seed=41, read_seed=42)
+    table = w.table()
+    n = 10_000_000
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    reads = acgt[rng.integers(0, 4, (n, 24), dtype=np.uint8)]
+    kind = rng.random(n)
+    reads[kind < 0.4] = ord("N")
+    hot = acgt[rng.integers(0, 4, (16, 24))]
+    sel = np.flatnonzero((kind >= 0.4) & (kind < 0.7))
+    reads[sel] = hot[rng.integers(0, 16, sel.size)]
+    st = _stage(w, table, unmatched_on_device=True, slots=2, most_unmatched_max_map_size=8_000_000)
+    half = n // 2
+    import torch
+    d_reads = _cuda(reads)
+    d_idx = torch.empty(n, dtype=torch.int16, device="cuda")
+    st.matcher.match_device(d_reads.data_ptr(), half, d_idx.data_ptr(), 0, 0)
+    st.matcher.match_device(d_reads.data_ptr() + half * 24, n - half, d_idx.data_ptr() + 2 * half, 0, 1)
+    st.matcher.sync(0)
+    st.matcher.sync(1)
+    idx = d_idx.cpu().numpy().view(np.uint16)
+    um = reads[idx == w.num_samples]
+    packed = np.ascontiguousarray(um).view(np.dtype((np.void, 24))).ravel()
+    keys, counts = np.unique(packed, return_counts=True)
+    info = st.matcher.unmatched_info()
+    assert info["unmatched_reads"] == um.shape[0] and info["dropped_reads"] == 0 and info["downsizes"] == 0
+    assert info["distinct_keys"] == keys.shape[0]
+    top = st.matcher.unmatched_top(17)
+    want_top = sorted(((k.tobytes(), int(c)) for k, c in zip(keys, counts) if c > 1), key=lambda kv: (-kv[1], kv[0]))[:17]
+    assert top == want_top and top[0] == (b"N" * 24, int((kind < 0.4).sum()))
+    got = st.matcher.unmatched_counts()
+    assert len(got) == keys.shape[0]
+    assert sum(got.values()) == um.shape[0]
+    for k, c in zip(keys[::997], counts[::997]):
+        assert got[k.tobytes()] == int(c)
+    st.close()
