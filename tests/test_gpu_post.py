@@ -599,3 +599,43 @@ def test_unmatched_table_under_heavy_contention():
     for k, c in zip(keys[::997], counts[::997]):
         assert got[k.tobytes()] == int(c)
     st.close()
+
+
+def test_reference_extraction_tests_on_device():
+    """demux.rs:867-1043 through sgdx_demultiplex_device, both matchers: every layout's template lands in sample 1,
+    the extracted barcode is SAMPLE_BARCODE_1, `bases` = the template length, 17 index bases of quality 0."""
+    import json
+    import os
+    import torch
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    g = json.load(open(os.path.join(root, "tests", "golden", "reference_extraction_cases.json")))
+    table = [s.encode() for s in g["samples"]]
+    for case in g["cases"]:
+        rss = [RS(s) for s in case["structures"]]
+        for cls in (sg.CachedHammingDistanceMatcher, sg.PreComputeMatcher):
+            st = sg.BarcodeAssignmentStage(_samples(table), cls, g["max_mismatches"], g["min_delta"], g["free_ns"],
+                                           g["max_no_calls"], None, unmatched_on_device=True)
+            m = st.matcher
+            keep, fastqs = [], []
+            for b in case["bases"]:
+                a = torch.zeros(len(b) + 32, dtype=torch.uint8, device="cuda")  # 16-byte aligned, padded
+                a[:len(b)] = torch.frombuffer(bytearray(b.encode()), dtype=torch.uint8).cuda()
+                q = torch.full((len(b) + 32,), g["qual_byte"], dtype=torch.uint8, device="cuda")
+                keep += [a, q]
+                fastqs.append((a.data_ptr(), q.data_ptr(), 0, len(b)))
+            d_bc = torch.zeros(32, dtype=torch.uint8, device="cuda")
+            m.extract_device([f[0] for f in fastqs], [f[3] for f in fastqs], rss, 1, d_bc.data_ptr())
+            d_idx = torch.full((4,), -1, dtype=torch.int16, device="cuda")
+            d_dist = torch.full((4,), 77, dtype=torch.uint8, device="cuda")
+            d_order = torch.full((4,), -1, dtype=torch.int32, device="cuda")
+            d_off = torch.zeros(6, dtype=torch.int64, device="cuda")
+            m.demultiplex_device(fastqs, rss, 1, d_idx.data_ptr(), d_dist.data_ptr(), d_order.data_ptr(), d_off.data_ptr())
+            m.sync(0)
+            assert bytes(d_bc[:17].cpu().numpy()) == table[0], case["src"]
+            assert int(d_idx[0]) == g["expected_sample_index"] and int(d_dist[0]) == 0, case["src"]
+            assert d_off.cpu().numpy().tolist() == [0, 1, 1, 1, 1, 1] and int(d_order[0]) == 0
+            got_q, short = m.base_qual_counters()
+            assert got_q[0].tolist() == [0, 0, 0, 17, case["template_bases"]] and short == 0, case["src"]
+            assert int(got_q[1:].sum()) == 0 and m.unmatched_counts() == {}
+            assert st.metrics().per_sample_array()[0].tolist() == [1, 1, 0]
+            st.close()
