@@ -325,6 +325,8 @@ struct QualParams {
     uint32_t nwords;          // words per shifted mask
     uint32_t min_len;         // a shorter read cannot be cut into the fixed segments
     uint32_t one;             // 1 (see add_fma)
+    uint32_t short_rows;      // stride <= 32: one SWAR pass per row instead of 16-byte chunks
+    uint32_t tmask32, bmask32;  // ... with the template / sample-barcode position bits of the structure
     uint32_t t_tail;          // positions t_tail .. stride-1 are all template bases (stride if the last one is not)
     uint32_t smem_hist;       // per-CTA histogram in shared memory (else global atomics)
     const uint32_t *masks;    // [2][16][nwords]: template / sample-barcode position bits, shifted left by 0..15
@@ -375,7 +377,7 @@ __device__ __forceinline__ uint32_t lanes8_sum(uint32_t acc) {  // sum of the fo
     return (t & 0xFFFFu) + (t >> 16);
 }
 
-template <bool HAS_B>
+template <bool HAS_B, bool SHORT_ROWS>
 __global__ void __launch_bounds__(kQualThreads) sgdx_qual_counts(const QualParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char *stage0 = smem;
@@ -455,7 +457,56 @@ __global__ void __launch_bounds__(kQualThreads) sgdx_qual_counts(const QualParam
             }
             if (len < p.min_len) {
                 shorts += part == 0u;
-            } else if (bin <= p.S) {
+            } else if (SHORT_ROWS && bin <= p.S) {
+                // rows of at most 32 bytes (index reads): the chunk machinery costs more than the bytes.  The row's
+                // words come from aligned 32-bit loads and a funnel shift, the position masks are two 32-bit
+                // kernel parameters, the sums are byte-lane SWAR; a word with a byte outside 33..127 (also a
+                // neighbour's or a stale one: only ever a false alarm) sends the row to the exact byte loop.
+                const uint32_t vm = len >= 32u ? 0xFFFFFFFFu : ((1u << len) - 1u);
+                const uint32_t tmb = p.tmask32 & vm, bmb = HAS_B ? (p.bmask32 & vm) : 0u;
+                const uint32_t *wp = reinterpret_cast<const uint32_t *>(stage + (start & ~3u));
+                const uint32_t sh = (start & 3u) * 8u, nrw = (p.stride + 3u) >> 2;
+                uint32_t a20 = 0, a30 = 0, bacc = 0, flag = 0;
+                for (uint32_t i = 0; i < nrw; i++) {
+                    const uint32_t x = __funnelshift_r(wp[i], wp[i + 1], sh);  // bytes 4i .. 4i+3 of the row
+                    flag |= (x - 0x21212121u) | x;
+                    const uint32_t t80 = (((tmb >> (4u * i)) & 15u) * 0x10204080u) & 0x80808080u;
+                    a20 += ((x + 0x4B4B4B4Bu) & t80) >> 7;
+                    a30 += ((x + 0x41414141u) & t80) >> 7;
+                    if (HAS_B) {
+                        const uint32_t ff = ((((bmb >> (4u * i)) & 15u) * 0x00204081u) & 0x01010101u) * 0xFFu;
+                        const uint32_t xb = x & ff;
+                        bacc += (xb & 0x00FF00FFu) + ((xb >> 8) & 0x00FF00FFu);
+                    }
+                }
+                uint32_t c20, c30, bsum;
+                const uint32_t nT = __popc(tmb), nB = __popc(bmb);
+                if ((flag & 0x80808080u) == 0u) {
+                    c20 = lanes8_sum(a20);
+                    c30 = lanes8_sum(a30);
+                    bsum = (bacc & 0xFFFFu) + (bacc >> 16) - 33u * nB;
+                } else {
+                    c20 = c30 = bsum = 0u;
+                    const unsigned char *row = stage + start;
+                    for (uint32_t j = 0; j < len; j++) {
+                        const uint32_t q = ((uint32_t)row[j] - 33u) & 0xFFu;
+                        if ((tmb >> j) & 1u) {
+                            c20 += q >= 20u;
+                            c30 += q >= 30u;
+                        }
+                        if ((bmb >> j) & 1u) bsum += q;
+                    }
+                }
+                if (nT) {
+                    if (c20) bump(bin * kQualCounters + 0u, c20);
+                    if (c30) bump(bin * kQualCounters + 1u, c30);
+                    bump(bin * kQualCounters + 4u, nT);
+                }
+                if (HAS_B && nB) {
+                    if (bsum) bump(bin * kQualCounters + 2u, bsum);
+                    bump(bin * kQualCounters + 3u, nB);
+                }
+            } else if (!SHORT_ROWS && bin <= p.S) {
                 const uint32_t *tm = s_masks + a * p.nwords, *bm = s_masks + (16u + a) * p.nwords;
                 const uint32_t end = a + len, nchunks = (end + 15u) >> 4;
                 uint32_t acc20 = 0, acc30 = 0, c20 = 0, c30 = 0, nT = 0;   // template bases
@@ -1203,6 +1254,12 @@ extern "C" int sgdx_qual_counts_device(sgdx_handle *h, uint32_t slot, const uint
     p.nwords = nwords;
     p.min_len = min_len;
     p.one = 1u;
+    p.short_rows = stride <= 32u ? 1u : 0u;
+    if (p.short_rows)
+        for (uint32_t q = 0; q < stride; q++) {
+            if (kind[q] == SGDX_SEG_TEMPLATE) p.tmask32 |= 1u << q;
+            if (kind[q] == SGDX_SEG_SAMPLE_BARCODE) p.bmask32 |= 1u << q;
+        }
     p.t_tail = stride;
     while (p.t_tail > 0 && kind[p.t_tail - 1] == SGDX_SEG_TEMPLATE) p.t_tail--;
     p.masks = s.d_qmasks;
@@ -1218,7 +1275,8 @@ extern "C" int sgdx_qual_counts_device(sgdx_handle *h, uint32_t slot, const uint
     p.smem_hist = hist_bytes <= 48u * 1024u ? 1u : 0u;
     const size_t nbins = p.smem_hist ? (size_t)(p.S + 1) * kQualCounters : 0;
     const size_t smem = (size_t)p.stages * p.stage_bytes + (size_t)32 * nwords * 4 + ((nbins + 1) & ~(size_t)1) * 4 + p.stages * 8;
-    auto kern = has_b ? sgdx_qual_counts<true> : sgdx_qual_counts<false>;
+    auto kern = p.short_rows ? (has_b ? sgdx_qual_counts<true, true> : sgdx_qual_counts<false, true>)
+                             : (has_b ? sgdx_qual_counts<true, false> : sgdx_qual_counts<false, false>);
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kQualThreads, smem));

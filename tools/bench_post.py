@@ -85,7 +85,7 @@ def measure(reads=50_000_000, steps=10, warmup=3, only="qual,qual_index,unmatche
         d_q = torch.randint(33, 75, (n, stride), dtype=torch.uint8, device="cuda", generator=g)
         rs = RS(f"{stride}T")
         ms, best = timed(lambda: m.qual_counts_device(d_q.data_ptr(), n, stride, rs, d_idx.data_ptr()))
-        line("qual_counts_template", ms, best, n * (stride + 2), "sgdx_qual_counts<false>",
+        line("qual_counts_template", ms, best, n * (stride + 2), "sgdx_qual_counts<false, false>",
              {"read_structure": f"{stride}T", "bytes_per_read": stride + 2})
         del d_q
     if "qual_index" in only:
@@ -94,7 +94,7 @@ def measure(reads=50_000_000, steps=10, warmup=3, only="qual,qual_index,unmatche
         d_q = torch.randint(33, 75, (n, 10), dtype=torch.uint8, device="cuda", generator=g)
         rs = RS("10B")
         ms, best = timed(lambda: m.qual_counts_device(d_q.data_ptr(), n, 10, rs, d_idx.data_ptr()))
-        line("qual_counts_index", ms, best, n * 12, "sgdx_qual_counts<true>", {"read_structure": "10B", "bytes_per_read": 12})
+        line("qual_counts_index", ms, best, n * 12, "sgdx_qual_counts<true, true> (rows <= 32 bytes)", {"read_structure": "10B", "bytes_per_read": 12})
         del d_q
     if "extract" in only:
         d_i1 = d_in[:, :10].contiguous()
