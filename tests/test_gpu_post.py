@@ -639,3 +639,48 @@ def test_reference_extraction_tests_on_device():
             assert int(got_q[1:].sum()) == 0 and m.unmatched_counts() == {}
             assert st.metrics().per_sample_array()[0].tolist() == [1, 1, 0]
             st.close()
+
+
+def test_downsizing_while_another_thread_submits():
+    """The table is cut down inside sgdx_sync of one thread while the other keeps launching batches on its own
+    slot (post_mu orders them).  No drops, at least one cut, and the heavy keys keep their exact counts."""
+    import threading
+    rng = np.random.default_rng(17)
+    w = sg.synth.Workload("dz", 16, 16, 8, 1, 2, n_reads=0, table_seed=3, read_seed=4)
+    table = w.table()
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    heavy = acgt[rng.integers(0, 4, (8, 16))]
+    st = _stage(w, table, unmatched_on_device=True, slots=2, most_unmatched_max_map_size=20_000,
+                most_unmatched_downsize_to=64)
+    batches = []
+    for t in range(2):
+        per_thread = []
+        for b in range(12):
+            noise = acgt[rng.integers(0, 4, (6_000, 16))]
+            reps = np.repeat(heavy, 300, axis=0)
+            x = np.concatenate([noise, reps])
+            rng.shuffle(x)
+            per_thread.append(np.ascontiguousarray(x))
+        batches.append(per_thread)
+    errors, undetermined = [], [0, 0]
+
+    def work(slot):
+        try:
+            for x in batches[slot]:
+                idx = st.demultiplex(x, slot=slot).sample_indices
+                undetermined[slot] += int((idx == w.num_samples).sum())
+        except Exception as e:  # noqa: BLE001
+            errors.append(e)
+
+    ts = [threading.Thread(target=work, args=(s,)) for s in range(2)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert not errors, errors
+    info = st.matcher.unmatched_info()
+    assert info["downsizes"] >= 1 and info["dropped_reads"] == 0
+    assert info["unmatched_reads"] == sum(undetermined)
+    top = dict(st.matcher.unmatched_top(8))
+    # every heavy key is unmatched for this table (random 16-mers against 16 samples) and was seen 2 * 12 * 300 times
+    for h in heavy:
+        assert top.get(h.tobytes()) == 2 * 12 * 300
+    st.close()
