@@ -684,3 +684,36 @@ def test_downsizing_while_another_thread_submits():
     for h in heavy:
         assert top.get(h.tobytes()) == 2 * 12 * 300
     st.close()
+
+
+def test_batcher_feeds_the_unmatched_table():
+    """The host batching stage (1000-read chunks -> pinned super-batches -> sgdx_match_batch) with the unmatched
+    table on: the host path counts the same keys as the oracle, chunk boundaries do not matter."""
+    import ctypes as C
+    from singular_demux_b200._lib import check, lib
+    w = sg.synth.C1
+    n = 200_000
+    table = w.table()
+    reads = w.reads_host(0, n, table)
+    st = _stage(w, table, unmatched_on_device=True, slots=2)
+    b = C.c_void_p()
+    check(lib().sgdx_batcher_create(st.matcher.handle, 32_768, C.byref(b)))
+    got = []
+    for chunk in np.array_split(reads, 200):
+        c = np.ascontiguousarray(chunk)
+        check(lib().sgdx_batcher_push(b, c.ctypes.data, c.shape[0]))
+    check(lib().sgdx_batcher_flush(b))
+    while True:
+        pi, pd, k = C.c_void_p(), C.c_void_p(), C.c_uint64(0)
+        check(lib().sgdx_batcher_next(b, C.byref(pi), C.byref(pd), C.byref(k)))
+        if k.value == 0:
+            break
+        got.append(np.ctypeslib.as_array(C.cast(pi, C.POINTER(C.c_uint16)), (k.value,)).copy())
+    lib().sgdx_batcher_destroy(b)
+    idx = np.concatenate(got)
+    want_idx = _oracle_idx(w, table, reads)
+    assert np.array_equal(idx, want_idx)
+    assert st.matcher.unmatched_counts() == orc.unmatched_counts(reads, want_idx, w.num_samples)
+    rows = st.most_frequent_unmatched(5)
+    assert len(rows) == 5 and all("+" in r.barcode for r in rows)
+    st.close()
