@@ -55,7 +55,6 @@ struct UnmatchedState {
     unsigned long long *d_stats = nullptr;  // kUnmStats words, see sgdx_post.cu
     uint8_t *d_odd = nullptr;               // barcodes with a byte outside ACGTN, 32 bytes each
     uint64_t odd_cap = 0;
-    uint64_t odd_drained = 0;               // entries of d_odd already folded into `odd`
     std::map<std::string, uint64_t> odd;    // host-side counts of those
     ulonglong2 *d_sel_keys = nullptr;       // selection scratch
     unsigned long long *d_sel_counts = nullptr;

@@ -309,7 +309,7 @@ __global__ void __launch_bounds__(kExtractThreads) sgdx_extract(const ExtractPar
 // 3. base-quality counters
 // ================================================================================================
 constexpr int kQualThreads = 128;
-constexpr int kQualSplit = 1;                            // threads per read: each takes half of the read's chunks
+constexpr int kQualSplit = 1;                            // threads per read (2 was measured: slower)
 constexpr int kQualLanes = kQualThreads / kQualSplit;  // reads in flight per CTA
 constexpr int kQualCounters = 5;  // q20, q30, index_bases_qual_sum, index_bases_total_seen, bases (metrics.rs:468-481)
 
