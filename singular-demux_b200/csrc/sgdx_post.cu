@@ -310,7 +310,6 @@ __global__ void __launch_bounds__(kExtractThreads) sgdx_extract(const ExtractPar
 // ================================================================================================
 constexpr int kQualThreads = 128;
 constexpr int kQualSplit = 1;                            // threads per read (2 was measured: slower)
-constexpr int kQualLanes = kQualThreads / kQualSplit;  // reads in flight per CTA
 constexpr int kQualCounters = 5;  // q20, q30, index_bases_qual_sum, index_bases_total_seen, bases (metrics.rs:468-481)
 
 struct QualParams {
@@ -377,8 +376,11 @@ __device__ __forceinline__ uint32_t lanes8_sum(uint32_t acc) {  // sum of the fo
     return (t & 0xFFFFu) + (t >> 16);
 }
 
+constexpr int kQualShortThreads = 256;  // rows of <= 32 bytes: 32 registers, so twice the warps fit
+
 template <bool HAS_B, bool SHORT_ROWS>
-__global__ void __launch_bounds__(kQualThreads) sgdx_qual_counts(const QualParams p) {
+__global__ void __launch_bounds__(SHORT_ROWS ? kQualShortThreads : kQualThreads) sgdx_qual_counts(const QualParams p) {
+    constexpr uint32_t kThreads = SHORT_ROWS ? kQualShortThreads : kQualThreads, kLanes = kThreads / kQualSplit;
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char *stage0 = smem;
     uint32_t *s_masks = reinterpret_cast<uint32_t *>(smem + (size_t)p.stages * p.stage_bytes);
@@ -391,8 +393,8 @@ __global__ void __launch_bounds__(kQualThreads) sgdx_qual_counts(const QualParam
         for (uint32_t s = 0; s < p.stages; s++) mbar_init(mbar + s, 1u);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (uint32_t i = tid; i < 32u * p.nwords; i += kQualThreads) s_masks[i] = p.masks[i];
-    for (uint32_t i = tid; i < nbins; i += kQualThreads) hist[i] = 0u;
+    for (uint32_t i = tid; i < 32u * p.nwords; i += kThreads) s_masks[i] = p.masks[i];
+    for (uint32_t i = tid; i < nbins; i += kThreads) hist[i] = 0u;
     __syncthreads();
 
     const uint32_t R = p.reads_per_tile;
@@ -417,7 +419,7 @@ __global__ void __launch_bounds__(kQualThreads) sgdx_qual_counts(const QualParam
     };
     auto flush = [&]() {
         __syncthreads();
-        for (uint32_t i = tid; i < nbins; i += kQualThreads) {
+        for (uint32_t i = tid; i < nbins; i += kThreads) {
             const uint32_t c = hist[i];
             if (c) {
                 atomicAdd(gcnt + i, (unsigned long long)c);
@@ -447,7 +449,7 @@ __global__ void __launch_bounds__(kQualThreads) sgdx_qual_counts(const QualParam
             if (tid < bytes - bulk) stage[bulk + tid] = p.quals[first * p.stride + bulk + tid];
             __syncthreads();
         }
-        for (uint32_t rl = lane_read; rl < cnt; rl += kQualLanes) {  // several reads per thread when they are short
+        for (uint32_t rl = lane_read; rl < cnt; rl += kLanes) {  // several reads per thread when they are short
             const uint32_t start = rl * p.stride, a = start & 15u;
             const uint4 *chunks = reinterpret_cast<const uint4 *>(stage + (start & ~15u));
             uint32_t len = len0, bin = bin0;
@@ -1265,9 +1267,10 @@ extern "C" int sgdx_qual_counts_device(sgdx_handle *h, uint32_t slot, const uint
     p.masks = s.d_qmasks;
     p.counters = h->qual.d_counters;
     // tile = reads_per_tile quality strings, a multiple of 16 reads so that every tile starts 16-byte aligned
-    uint32_t R = kQualLanes;
+    const uint32_t threads = p.short_rows ? kQualShortThreads : kQualThreads, lanes = threads / kQualSplit;
+    uint32_t R = lanes;
     while (R > 16u && (uint64_t)R * stride > 48u * 1024u) R >>= 1;
-    if ((uint64_t)R * stride < 8u * 1024u) R = kQualLanes * std::min<uint32_t>(32u, 16u * 1024u / (kQualLanes * stride));  // short reads: ~16 KB tiles
+    if ((uint64_t)R * stride < 8u * 1024u) R = lanes * std::max<uint32_t>(1u, std::min<uint32_t>(32u, 16u * 1024u / (lanes * stride)));  // short reads: ~16 KB tiles
     p.reads_per_tile = R;
     p.stage_bytes = (R * stride + 16u + 127u) & ~127u;
     p.stages = 2;
@@ -1279,10 +1282,10 @@ extern "C" int sgdx_qual_counts_device(sgdx_handle *h, uint32_t slot, const uint
                              : (has_b ? sgdx_qual_counts<true, false> : sgdx_qual_counts<false, false>);
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kQualThreads, smem));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, (int)threads, smem));
     if (per_sm < 1) return fail(SGDX_EINVAL, "quality-counter kernel does not fit (stride %u, %u samples)", stride, p.S);
     const uint32_t grid = grid_cap(n, R, h->sms, per_sm);
-    kern<<<grid, kQualThreads, smem, s.stream>>>(p);
+    kern<<<grid, threads, smem, s.stream>>>(p);
     CU(cudaGetLastError());
     h->launches.fetch_add(1);
     return SGDX_OK;
