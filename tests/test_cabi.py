@@ -135,3 +135,19 @@ def test_cpp_host_mirror_builds_and_refuses_to_run_without_a_gpu():
         pytest.skip("GPU present: the gpu-marked test runs the program")
     r = subprocess.run([exe], capture_output=True, text=True, timeout=60)
     assert r.returncode == 2 and "no CPU fallback" in r.stderr
+
+
+def test_headers_are_plain_c(tmp_path):
+    """The boundary is a C ABI: include/*.h must compile as C99 (no C++ types, no torch types in the signatures)."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if not gcc:
+        pytest.skip("no gcc")
+    src = tmp_path / "hdr.c"
+    src.write_text('#include "sgdx.h"\n#include "sgdx_synth.h"\n'
+                   "int main(void) { sgdx_config c; sgdx_segment s = {0, 0, SGDX_SEG_TO_END, SGDX_SEG_TEMPLATE};\n"
+                   "  sgdx_demux_out o = {0}; sgdx_fastq_view v = {0}; (void)c; (void)s; (void)o; (void)v; return 0; }\n")
+    r = subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+                        "-fsyntax-only", str(src)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
