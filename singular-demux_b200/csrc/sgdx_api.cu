@@ -655,6 +655,7 @@ extern "C" int sgdx_hop_export(sgdx_handle *h, uint8_t *keys, uint64_t *counts, 
     std::map<std::string, uint64_t> m;
     if (int rc = hop_entries(h, m)) return rc;
     if (m.size() > cap) return fail(SGDX_EINVAL, "hop export needs room for %zu keys, got %llu", m.size(), (unsigned long long)cap);
+    if (!m.empty() && (!keys || !counts)) return fail(SGDX_EINVAL, "sgdx_hop_export: null output buffer");
     const uint32_t L = h->cfg.barcode_len;
     uint64_t i = 0;
     for (auto &kv : m) {
@@ -749,12 +750,18 @@ static int submit(sgdx_batcher *b) {
         void *q = nullptr;
         if (int rc = sgdx_alloc_host(b->batch_reads * sizeof(uint16_t), &q)) return rc;
         r.idx = static_cast<uint16_t *>(q);
-        if (int rc = sgdx_alloc_host(b->batch_reads, &q)) return rc;
+        if (int rc = sgdx_alloc_host(b->batch_reads, &q)) {
+            cudaFreeHost(r.idx);
+            return rc;
+        }
         r.dist = static_cast<uint8_t *>(q);
     }
     r.n = b->fill;
     r.slot = b->cur;
-    if (int rc = sgdx_match_batch(b->h, b->cur, b->in[b->cur], r.n, r.idx, r.dist)) return rc;
+    if (int rc = sgdx_match_batch(b->h, b->cur, b->in[b->cur], r.n, r.idx, r.dist)) {
+        b->free_results.push_back(r);  // the reads stay in the slot's input buffer; a retry re-submits them
+        return rc;
+    }
     b->slot_busy[b->cur] = true;
     b->inflight.push_back(r);
     b->fill = 0;

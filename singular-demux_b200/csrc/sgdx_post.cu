@@ -828,6 +828,8 @@ static int unm_drain_odd(sgdx_handle *h) {
         for (uint64_t i = 0; i < have; i++) u.odd[std::string(reinterpret_cast<const char *>(&buf[i * 32u]), L)]++;
     }
     CU(cudaMemset(u.d_stats + 3, 0, sizeof(unsigned long long)));
+    // the memset is on the default stream; the next batch runs on a non-blocking one and appends to this counter
+    CU(cudaDeviceSynchronize());
     return SGDX_OK;
 }
 
@@ -1233,15 +1235,18 @@ extern "C" int sgdx_qual_counts_device(sgdx_handle *h, uint32_t slot, const uint
                 if (kind[q] == SGDX_SEG_TEMPLATE) masks[(size_t)a * nwords + (bit >> 5)] |= 1u << (bit & 31u);
                 if (kind[q] == SGDX_SEG_SAMPLE_BARCODE) masks[(size_t)(16 + a) * nwords + (bit >> 5)] |= 1u << (bit & 31u);
             }
-        CU(cudaStreamSynchronize(s.stream));  // a kernel still reading the old masks
         if (masks.size() > s.qmasks_cap) {
+            CU(cudaStreamSynchronize(s.stream));  // a kernel still reading the old masks
             cudaFree(s.d_qmasks);
             s.d_qmasks = nullptr;
             s.qmasks_cap = 0;
+            s.qmasks_key.clear();
             CU(cudaMalloc(&s.d_qmasks, masks.size() * sizeof(uint32_t)));
             s.qmasks_cap = masks.size();
         }
-        CU(cudaMemcpy(s.d_qmasks, masks.data(), masks.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        // on the slot's stream: ordered after the kernels that read the old masks and before the one queued
+        // below (a copy on the default stream orders against neither); pageable source, staged before return
+        CU(cudaMemcpyAsync(s.d_qmasks, masks.data(), masks.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, s.stream));
         s.qmasks_key = key;
     }
     if (n == 0) return SGDX_OK;
