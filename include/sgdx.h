@@ -118,6 +118,28 @@ int sgdx_pack_device(sgdx_handle *h, uint32_t slot, const uint8_t *d_barcodes_as
                      sgdx_read *d_packed);
 int sgdx_match_packed_device(sgdx_handle *h, uint32_t slot, const sgdx_read *d_packed, uint64_t n,
                              uint16_t *d_out_idx, uint8_t *d_out_dist);
+/* Compact records: one 64-bit word per read, for barcode_len <= SGDX_COMPACT_MAX_LEN -- BASELINE.json's
+ * "2-bit base planes plus an N mask", SURVEY 8(d)'s algorithmic input of ceil(3L/8) bytes per read:
+ *   bits  0..20  lo plane: bit j = bit 0 of base j's code, code = (ascii >> 1) & 3 (A0 C1 T2 G3)
+ *   bits 21..41  hi plane: bit j = bit 1 of the code
+ *   bits 42..62  invalid plane: base j is not A/C/G/T; there lo = 0 means 'N' (a no-call, demux.rs:78-80),
+ *                lo = 1 any other byte (mismatches every sample, as in matcher.rs:335-348); hi = 0
+ *   bit  63      zero; planes are zero at positions >= barcode_len
+ * The batching stage (demux.rs:522 -> :528) writes this instead of ASCII into its pinned buffer:
+ * sgdx_pack_compact_host is that pass (host code, `threads` workers, AVX2 when the CPU has it), and
+ * sgdx_match_compact_batch is sgdx_match_batch for such a buffer: 8 instead of barcode_len bytes per read
+ * cross PCIe, and the kernel reads them with one coalesced 64-bit load.  Results are identical to the ASCII
+ * entry points for every configuration; tables without the exact-match shortcut (see SGDX_PATH_COMPACT)
+ * are served through the 16-byte packed form of the general kernels.  Unmatched collection needs ASCII. */
+#define SGDX_COMPACT_MAX_LEN 21u
+int sgdx_pack_compact_host(const uint8_t *barcodes_ascii, uint64_t n, uint32_t barcode_len, uint64_t *out_records,
+                           uint32_t threads /* 0 -> 1 */);
+int sgdx_pack_compact_device(sgdx_handle *h, uint32_t slot, const uint8_t *d_barcodes_ascii, uint64_t n,
+                             uint64_t *d_records);
+int sgdx_match_compact_batch(sgdx_handle *h, uint32_t slot, const uint64_t *records, uint64_t n,
+                             uint16_t *out_idx, uint8_t *out_dist);
+int sgdx_match_compact_device(sgdx_handle *h, uint32_t slot, const uint64_t *d_records, uint64_t n,
+                              uint16_t *d_out_idx, uint8_t *d_out_dist);
 /* Run the slot on a caller-owned stream (cudaStream_t passed as void*); NULL restores the slot's own. */
 int sgdx_set_stream(sgdx_handle *h, uint32_t slot, void *cuda_stream);
 /* Name of the assignment kernel this handle launches for ASCII input ("sgdx_match_direct",
@@ -128,6 +150,7 @@ const char *sgdx_kernel_name(const sgdx_handle *h);
 #define SGDX_PATH_EXACT 2u        /* exact-match front end (min pairwise table distance > min_delta) */
 #define SGDX_PATH_NEIGHBOURS 4u   /* one-substitution neighbour table (min pairwise distance > min_delta + 2) */
 #define SGDX_PATH_HOP_DIRECT 8u   /* direct-address hop tables (both index halves <= 11 bases) */
+#define SGDX_PATH_COMPACT 16u     /* sgdx_match_compact serves compact records (exact shortcut valid, barcode_len <= 21) */
 uint32_t sgdx_path_flags(const sgdx_handle *h);
 /* Number of kernel launches issued through this handle so far. */
 uint64_t sgdx_launch_count(const sgdx_handle *h);

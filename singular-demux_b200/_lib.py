@@ -14,7 +14,8 @@ LIB_PATH = os.path.join(_HERE, "libsgdx.so")
 MATCHER_AUTO, MATCHER_CACHED_HAMMING, MATCHER_PRECOMPUTE = 0, 1, 2
 KERNEL_AUTO, KERNEL_DIRECT, KERNEL_SEEDED = 0, 1, 2
 NO_DIST = 0xFF
-PATH_SEED_INDEX, PATH_EXACT, PATH_NEIGHBOURS, PATH_HOP_DIRECT = 1, 2, 4, 8
+PATH_SEED_INDEX, PATH_EXACT, PATH_NEIGHBOURS, PATH_HOP_DIRECT, PATH_COMPACT = 1, 2, 4, 8, 16
+COMPACT_MAX_LEN = 21
 MAX_BARCODE_LEN = 32
 MAX_SAMPLES = 8192
 
@@ -73,7 +74,8 @@ class SynthParams(C.Structure):
 SYMBOLS = [
     "sgdx_last_error", "sgdx_version", "sgdx_create", "sgdx_destroy", "sgdx_get_config", "sgdx_alloc_host",
     "sgdx_free_host", "sgdx_match_batch", "sgdx_sync", "sgdx_match_device", "sgdx_pack_device",
-    "sgdx_match_packed_device", "sgdx_set_stream", "sgdx_kernel_name", "sgdx_path_flags", "sgdx_launch_count", "sgdx_counters", "sgdx_reset_counters",
+    "sgdx_match_packed_device", "sgdx_pack_compact_host", "sgdx_pack_compact_device", "sgdx_match_compact_batch",
+    "sgdx_match_compact_device", "sgdx_set_stream", "sgdx_kernel_name", "sgdx_path_flags", "sgdx_launch_count", "sgdx_counters", "sgdx_reset_counters",
     "sgdx_hop_count", "sgdx_hop_export", "sgdx_batcher_create", "sgdx_batcher_destroy", "sgdx_batcher_push",
     "sgdx_batcher_flush", "sgdx_batcher_next", "sgdx_measure_int_peak",
     "sgdx_unmatched_enable", "sgdx_unmatched_info_get", "sgdx_unmatched_export", "sgdx_unmatched_top",
@@ -107,6 +109,10 @@ def lib() -> C.CDLL:
     L.sgdx_match_device.argtypes = [vp, u32, vp, u64, vp, vp]
     L.sgdx_pack_device.argtypes = [vp, u32, vp, u64, vp]
     L.sgdx_match_packed_device.argtypes = [vp, u32, vp, u64, vp, vp]
+    L.sgdx_pack_compact_host.argtypes = [vp, u64, u32, vp, u32]
+    L.sgdx_pack_compact_device.argtypes = [vp, u32, vp, u64, vp]
+    L.sgdx_match_compact_batch.argtypes = [vp, u32, vp, u64, vp, vp]
+    L.sgdx_match_compact_device.argtypes = [vp, u32, vp, u64, vp, vp]
     L.sgdx_set_stream.argtypes = [vp, u32, vp]
     L.sgdx_kernel_name.argtypes = [vp]
     L.sgdx_kernel_name.restype = C.c_char_p

@@ -233,6 +233,34 @@ static int build_exact_table(sgdx_handle *h, const uint8_t *barcodes, const std:
     return SGDX_OK;
 }
 
+// Front end of sgdx_match_compact (sgdx_compact.cu): the same cuckoo placement over a hash of each barcode's
+// compact record.  Exists when the exact-match shortcut is valid (ex_on) and a read fits one 64-bit record.
+static int build_compact_table(sgdx_handle *h, const std::vector<uint2> &table) {
+    const DevParams &p = h->base;
+    h->cx = CompactParams{};
+    if (!h->seeded || !p.ex_on || p.L > kCompactMaxLen) return SGDX_OK;
+    const uint32_t k0 = 0x9E3779B1u, k1 = 0x85EBCA77u;
+    for (uint32_t bits = std::max(p.ex_bits, 6u); bits <= p.ex_bits + 2u; bits++) {
+        if (compact_smem_bytes(p, bits) > 200u * 1024u) return SGDX_OK;
+        std::vector<uint32_t> slots((size_t)1 << bits, 0u), owner((size_t)1 << bits, 0u);
+        bool placed = true;
+        for (uint32_t s = 0; s < p.S && placed; s++) {
+            const uint64_t rec = compact_record(table[s].x, table[s].y);
+            const uint32_t hsh = ex_mix(ex_word_step(ex_word_step(0u, (uint32_t)rec, k0), (uint32_t)(rec >> 32), k1));
+            placed = cuckoo_insert(slots, owner, 0u, bits, hsh, ((hsh & 0xFFFFu) << 16) | (s + 1u));
+        }
+        if (!placed) continue;  // not seen at load factor <= 1/4; a larger table is tried twice
+        CU(cudaMalloc(&h->d_cx_slots, slots.size() * sizeof(uint32_t)));
+        CU(cudaMemcpy(h->d_cx_slots, slots.data(), slots.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        h->cx.slots = h->d_cx_slots;
+        h->cx.bits = bits;
+        h->cx.k0 = k0;
+        h->cx.k1 = k1;
+        return SGDX_OK;
+    }
+    return SGDX_OK;
+}
+
 // everything sgdx_create does once the arguments are validated; on failure the caller destroys the handle
 static int fill_handle(sgdx_handle *h, const sgdx_config *cfg, const uint8_t *barcodes) {
     const uint32_t S = cfg->num_samples, L = cfg->barcode_len;
@@ -346,6 +374,7 @@ static int fill_handle(sgdx_handle *h, const sgdx_config *cfg, const uint8_t *ba
                 return rc;
             }
         h->cfg.kernel = h->seeded ? SGDX_KERNEL_SEEDED : SGDX_KERNEL_DIRECT;
+        if (int rc = build_compact_table(h, table)) return rc;
     }
 
     h->slots.resize(h->cfg.slots);
@@ -408,6 +437,7 @@ extern "C" void sgdx_destroy(sgdx_handle *h) {
         cudaFree(s.d_dist);
         cudaFree(s.d_extract);
         cudaFree(s.d_route);
+        cudaFree(s.d_cexp);
         if (s.h_unm_stats) cudaFreeHost(s.h_unm_stats);
         if (s.e0) cudaEventDestroy(s.e0);
         if (s.e1) cudaEventDestroy(s.e1);
@@ -419,6 +449,7 @@ extern "C" void sgdx_destroy(sgdx_handle *h) {
     cudaFree(h->d_ex_slots);
     cudaFree(h->d_ex_ascii);
     cudaFree(h->d_nb_slots);
+    cudaFree(h->d_cx_slots);
     cudaFree(h->d_hash1);
     cudaFree(h->d_hash2);
     cudaFree(h->d_hop_lut1);
@@ -514,7 +545,7 @@ static int ensure_capacity(Slot &s, uint64_t n, uint32_t L) {
     s.d_dist = nullptr;
     s.cap = 0;
     uint64_t cap = n + n / 8 + 1024;
-    CU(cudaMalloc(&s.d_in, cap * L));
+    CU(cudaMalloc(&s.d_in, cap * std::max<uint32_t>(L, 8u)));  // L ASCII bytes or one 64-bit compact record per read
     CU(cudaMalloc(&s.d_idx, cap * sizeof(uint16_t)));
     CU(cudaMalloc(&s.d_dist, cap));
     s.cap = cap;
@@ -532,6 +563,83 @@ extern "C" int sgdx_match_batch(sgdx_handle *h, uint32_t slot, const uint8_t *as
     if (int rc = ensure_capacity(s, n, L)) return rc;
     if (n) CU(cudaMemcpyAsync(s.d_in, ascii, n * L, cudaMemcpyHostToDevice, s.stream));
     if (int rc = run_kernels(h, s, s.d_in, nullptr, n, s.d_idx, s.d_dist)) return rc;
+    if (n) {
+        CU(cudaMemcpyAsync(out_idx, s.d_idx, n * sizeof(uint16_t), cudaMemcpyDeviceToHost, s.stream));
+        if (out_dist) CU(cudaMemcpyAsync(out_dist, s.d_dist, n, cudaMemcpyDeviceToHost, s.stream));
+    }
+    return SGDX_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// compact records (one 64-bit word per read, barcode_len <= 21)
+// ------------------------------------------------------------------------------------------------
+static int run_compact(sgdx_handle *h, Slot &s, const uint64_t *d_records, uint64_t n, uint16_t *d_idx, uint8_t *d_dist) {
+    if (h->cfg.barcode_len > kCompactMaxLen)
+        return fail(SGDX_EINVAL, "compact records hold at most %u bases, barcode_len is %u", kCompactMaxLen, h->cfg.barcode_len);
+    if (reinterpret_cast<uintptr_t>(d_records) & 7u) return fail(SGDX_EINVAL, "compact records must be 8-byte aligned");
+    if (h->unm.on && n)
+        return fail(SGDX_ESTATE, "unmatched collection needs ASCII input (compact records do not keep foreign bytes)");
+    if (!h->cx.slots) {  // table without the exact-match shortcut: expand to 16-byte records, general kernels
+        if (n > s.cexp_cap) {
+            CU(cudaStreamSynchronize(s.stream));
+            cudaFree(s.d_cexp);
+            s.d_cexp = nullptr;
+            s.cexp_cap = 0;
+            const uint64_t cap = n + n / 8 + 1024;
+            CU(cudaMalloc(&s.d_cexp, cap * sizeof(uint4)));
+            s.cexp_cap = cap;
+        }
+        CU(launch_expand_compact(d_records, n, s.d_cexp, h->sms, s.stream));
+        if (n) h->launches.fetch_add(1);
+        return run_kernels(h, s, nullptr, s.d_cexp, n, d_idx, d_dist);
+    }
+    DevParams p = h->base;
+    p.n = n;
+    p.out_idx = d_idx;
+    p.out_dist = d_dist;
+    CompactParams c = h->cx;
+    c.reads = d_records;
+    CU(cudaEventRecord(s.e0, s.stream));
+    CU(launch_compact(p, c, h->mode, h->sms, s.stream));
+    if (n) h->launches.fetch_add(1);
+    CU(cudaEventRecord(s.e1, s.stream));
+    s.timed = true;
+    return SGDX_OK;
+}
+
+extern "C" int sgdx_match_compact_device(sgdx_handle *h, uint32_t slot, const uint64_t *d_records, uint64_t n,
+                                         uint16_t *d_idx, uint8_t *d_dist) {
+    if (int rc = check_slot(h, slot)) return rc;
+    if (n && (!d_records || !d_idx)) return fail(SGDX_EINVAL, "sgdx_match_compact_device: null buffer");
+    if (n >> 40) return fail(SGDX_EINVAL, "batch too large");
+    CU(cudaSetDevice(h->cfg.device));
+    return run_compact(h, h->slots[slot], d_records, n, d_idx, d_dist);
+}
+
+extern "C" int sgdx_pack_compact_device(sgdx_handle *h, uint32_t slot, const uint8_t *d_ascii, uint64_t n,
+                                        uint64_t *d_records) {
+    if (int rc = check_slot(h, slot)) return rc;
+    if (n && (!d_ascii || !d_records)) return fail(SGDX_EINVAL, "sgdx_pack_compact_device: null buffer");
+    if (h->cfg.barcode_len > kCompactMaxLen)
+        return fail(SGDX_EINVAL, "compact records hold at most %u bases, barcode_len is %u", kCompactMaxLen, h->cfg.barcode_len);
+    if (reinterpret_cast<uintptr_t>(d_records) & 7u) return fail(SGDX_EINVAL, "compact records must be 8-byte aligned");
+    CU(cudaSetDevice(h->cfg.device));
+    CU(launch_pack_compact(d_ascii, n, h->cfg.barcode_len, d_records, h->sms, h->slots[slot].stream));
+    if (n) h->launches.fetch_add(1);
+    return SGDX_OK;
+}
+
+extern "C" int sgdx_match_compact_batch(sgdx_handle *h, uint32_t slot, const uint64_t *records, uint64_t n,
+                                        uint16_t *out_idx, uint8_t *out_dist) {
+    if (int rc = check_slot(h, slot)) return rc;
+    if (n && (!records || !out_idx)) return fail(SGDX_EINVAL, "sgdx_match_compact_batch: null buffer");
+    if (n >> 34) return fail(SGDX_EINVAL, "batch of %llu reads too large; split it", (unsigned long long)n);
+    CU(cudaSetDevice(h->cfg.device));
+    Slot &s = h->slots[slot];
+    if (int rc = ensure_capacity(s, n, h->cfg.barcode_len)) return rc;
+    uint64_t *d_rec = reinterpret_cast<uint64_t *>(s.d_in);
+    if (n) CU(cudaMemcpyAsync(d_rec, records, n * sizeof(uint64_t), cudaMemcpyHostToDevice, s.stream));
+    if (int rc = run_compact(h, s, d_rec, n, s.d_idx, s.d_dist)) return rc;
     if (n) {
         CU(cudaMemcpyAsync(out_idx, s.d_idx, n * sizeof(uint16_t), cudaMemcpyDeviceToHost, s.stream));
         if (out_dist) CU(cudaMemcpyAsync(out_dist, s.d_dist, n, cudaMemcpyDeviceToHost, s.stream));
@@ -569,7 +677,8 @@ extern "C" uint32_t sgdx_path_flags(const sgdx_handle *h) {
     if (!h) return 0u;
     const DevParams &p = h->base;
     return (h->seeded ? SGDX_PATH_SEED_INDEX : 0u) | (h->seeded && p.ex_on ? SGDX_PATH_EXACT : 0u) |
-           (h->seeded && p.ex_on && p.nb_on ? SGDX_PATH_NEIGHBOURS : 0u) | (p.hop_direct ? SGDX_PATH_HOP_DIRECT : 0u);
+           (h->seeded && p.ex_on && p.nb_on ? SGDX_PATH_NEIGHBOURS : 0u) | (p.hop_direct ? SGDX_PATH_HOP_DIRECT : 0u) |
+           (h->cx.slots ? SGDX_PATH_COMPACT : 0u);
 }
 
 extern "C" uint64_t sgdx_launch_count(const sgdx_handle *h) { return h ? h->launches.load() : 0; }

@@ -41,6 +41,8 @@ struct Slot {
     uint32_t *d_qmasks = nullptr;               // shifted segment masks of the last read structure this slot
     uint64_t qmasks_cap = 0;                    //   counted qualities for (words), and that structure
     std::vector<uint32_t> qmasks_key;
+    uint4 *d_cexp = nullptr;                    // scratch of the compact-input general path (16-byte records)
+    uint64_t cexp_cap = 0;
 };
 
 struct UnmSlot;
@@ -80,6 +82,8 @@ struct sgdx_handle {
     uint16_t *d_seed_ids = nullptr;
     uint32_t *d_ex_slots = nullptr, *d_ex_ascii = nullptr, *d_nb_slots = nullptr;
     bool seeded = false;  // launches use sgdx_match_seeded
+    uint32_t *d_cx_slots = nullptr;  // compact-record front end (sgdx_compact.cu); cx.slots == nullptr: not available
+    sgdx::CompactParams cx{};
     sgdx::HopSlot *d_hash1 = nullptr, *d_hash2 = nullptr;
     uint16_t *d_hop_lut1 = nullptr, *d_hop_lut2 = nullptr;
     unsigned long long *d_hop_fwd = nullptr, *d_hop_rev = nullptr;

@@ -1,0 +1,109 @@
+// sgdx_hostpack.cpp -- host side of the compact read format (include/sgdx.h, sgdx_pack_compact_host).
+//
+// The batching stage between the segment extractor (demux.rs:504-522) and the matcher writes every observed
+// barcode into a pinned buffer anyway; writing it as one 64-bit compact record (sgdx_compact.cu: lo plane |
+// hi plane << 21 | invalid plane << 42) instead of L ASCII bytes is the same pass over the bytes and cuts the
+// PCIe traffic of a 20-base read from 20 to 8 bytes.  Pure host code: this is a data-format conversion, not a
+// matcher -- assignment itself has no CPU path.
+#include <algorithm>
+#include <cstdint>
+#include <cstring>
+#include <thread>
+#include <vector>
+
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
+
+#include "../../include/sgdx.h"
+
+namespace sgdx {
+int fail(int code, const char *fmt, ...);  // sgdx_api.cu: sets the thread's sgdx_last_error text
+}
+
+namespace {
+
+constexpr uint32_t kField = 21;
+
+inline uint64_t pack_scalar(const uint8_t *p, uint32_t L) {
+    uint32_t lo = 0, hi = 0, inv = 0;
+    for (uint32_t j = 0; j < L; j++) {
+        const uint8_t c = p[j];
+        if (c == 'A' || c == 'C' || c == 'G' || c == 'T') {
+            lo |= (uint32_t)((c >> 1) & 1u) << j;
+            hi |= (uint32_t)((c >> 2) & 1u) << j;
+        } else {
+            inv |= 1u << j;
+            if (c != 'N') lo |= 1u << j;  // foreign byte: mismatches every sample, is not a no-call
+        }
+    }
+    return (uint64_t)lo | ((uint64_t)hi << kField) | ((uint64_t)inv << (2 * kField));
+}
+
+void pack_range_scalar(const uint8_t *ascii, uint64_t begin, uint64_t end, uint32_t L, uint64_t *out) {
+    for (uint64_t r = begin; r < end; r++) out[r] = pack_scalar(ascii + r * L, L);
+}
+
+#if defined(__x86_64__)
+// 32 bytes per load, one read per iteration: bit 1 / bit 2 of every byte through a shift + movemask, validity
+// through a nibble-indexed table of the four letters (a byte is A/C/G/T iff table[byte & 15] == byte)
+__attribute__((target("avx2"))) void pack_range_avx2(const uint8_t *ascii, uint64_t begin, uint64_t end, uint32_t L,
+                                                     uint64_t total, uint64_t *out) {
+    // reads whose 32-byte load would run past the end of the buffer take the scalar path
+    const uint64_t bytes = total * L;
+    uint64_t safe_end = end;
+    while (safe_end > begin && (safe_end - 1) * L + 32 > bytes) safe_end--;
+    // unused nibbles hold 0x01, whose own nibble (1) is taken by 'A': no byte equals its entry by accident
+    const __m256i lut = _mm256_setr_epi8(1, 'A', 1, 'C', 'T', 1, 1, 'G', 1, 1, 1, 1, 1, 1, 1, 1,
+                                         1, 'A', 1, 'C', 'T', 1, 1, 'G', 1, 1, 1, 1, 1, 1, 1, 1);
+    const __m256i nib = _mm256_set1_epi8(0x0F), enn = _mm256_set1_epi8('N');
+    const uint32_t m = (1u << L) - 1u;  // L <= 21
+    for (uint64_t r = begin; r < safe_end; r++) {
+        const __m256i x = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(ascii + r * L));
+        const uint32_t b1 = (uint32_t)_mm256_movemask_epi8(_mm256_slli_epi16(x, 6));
+        const uint32_t b2 = (uint32_t)_mm256_movemask_epi8(_mm256_slli_epi16(x, 5));
+        const uint32_t ok = (uint32_t)_mm256_movemask_epi8(_mm256_cmpeq_epi8(_mm256_shuffle_epi8(lut, _mm256_and_si256(x, nib)), x));
+        const uint32_t isn = (uint32_t)_mm256_movemask_epi8(_mm256_cmpeq_epi8(x, enn));
+        const uint32_t inv = ~ok & m;
+        const uint32_t lo = (b1 & ok & m) | (inv & ~isn);
+        const uint32_t hi = b2 & ok & m;
+        out[r] = (uint64_t)lo | ((uint64_t)hi << kField) | ((uint64_t)inv << (2 * kField));
+    }
+    pack_range_scalar(ascii, safe_end, end, L, out);
+}
+#endif
+
+void pack_range(const uint8_t *ascii, uint64_t begin, uint64_t end, uint32_t L, uint64_t total, uint64_t *out) {
+#if defined(__x86_64__)
+    static const bool have_avx2 = __builtin_cpu_supports("avx2");
+    if (have_avx2) return pack_range_avx2(ascii, begin, end, L, total, out);
+#endif
+    (void)total;
+    pack_range_scalar(ascii, begin, end, L, out);
+}
+
+}  // namespace
+
+extern "C" int sgdx_pack_compact_host(const uint8_t *ascii, uint64_t n, uint32_t barcode_len, uint64_t *out,
+                                      uint32_t threads) {
+    if (barcode_len < 1 || barcode_len > SGDX_COMPACT_MAX_LEN)
+        return sgdx::fail(SGDX_EINVAL, "compact records hold 1..%u bases, barcode_len is %u", SGDX_COMPACT_MAX_LEN, barcode_len);
+    if (n && (!ascii || !out)) return sgdx::fail(SGDX_EINVAL, "sgdx_pack_compact_host: null buffer");
+    if (threads == 0) threads = 1;
+    const uint64_t min_per_thread = 1u << 16;  // below this a thread costs more than it saves
+    uint64_t nt = std::min<uint64_t>(threads, (n + min_per_thread - 1) / min_per_thread);
+    if (nt <= 1) {
+        pack_range(ascii, 0, n, barcode_len, n, out);
+        return SGDX_OK;
+    }
+    std::vector<std::thread> pool;
+    pool.reserve(nt - 1);
+    const uint64_t per = (n + nt - 1) / nt;
+    for (uint64_t t = 1; t < nt; t++) {
+        const uint64_t b = std::min(n, t * per), e = std::min(n, (t + 1) * per);
+        pool.emplace_back(pack_range, ascii, b, e, barcode_len, n, out);
+    }
+    pack_range(ascii, 0, std::min(n, per), barcode_len, n, out);
+    for (auto &th : pool) th.join();
+    return SGDX_OK;
+}

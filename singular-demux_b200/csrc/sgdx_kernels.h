@@ -15,6 +15,21 @@ uint32_t exact_block_threads(const DevParams &p);
 cudaError_t launch_seeded(const DevParams &p, uint32_t mode, bool packed, int sms, cudaStream_t stream);
 cudaError_t launch_pack(const uint8_t *reads, uint64_t n, uint32_t L, uint4 *out, int sms, cudaStream_t stream);
 
+// compact records (sgdx_compact.cu): one 64-bit word per read of at most kCompactMaxLen bases --
+// lo plane | hi plane << 21 | invalid plane << 42 (at an invalid position lo = 0: 'N', lo = 1: any other byte)
+constexpr uint32_t kCompactMaxLen = 21;
+struct CompactParams {
+    const uint64_t *reads;  // n records
+    const uint32_t *slots;  // [1 << bits] cuckoo table of the expected barcodes: (tag16 << 16) | (sample + 1), 0 = empty
+    uint32_t bits;
+    uint32_t k0, k1;        // multipliers of the hash over the record's two 32-bit words
+};
+inline uint64_t compact_record(uint32_t lo, uint32_t hi) { return (uint64_t)lo | ((uint64_t)hi << 21); }
+size_t compact_smem_bytes(const DevParams &p, uint32_t bits);
+cudaError_t launch_compact(const DevParams &p, const CompactParams &c, uint32_t mode, int sms, cudaStream_t stream);
+cudaError_t launch_pack_compact(const uint8_t *reads, uint64_t n, uint32_t L, uint64_t *out, int sms, cudaStream_t stream);
+cudaError_t launch_expand_compact(const uint64_t *in, uint64_t n, uint4 *out, int sms, cudaStream_t stream);
+
 // integer-pipe micro-benchmark (sgdx_microbench.cu)
 cudaError_t measure_int_peak(int sms, double *popc_per_s, double *lop3_per_s);
 

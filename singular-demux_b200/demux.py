@@ -59,9 +59,11 @@ class BarcodeAssignmentStage:
     def get_undetermined_index(self) -> int:
         return self.undetermined_sample_index
 
-    def demultiplex(self, barcodes, slot: int = 0) -> DemuxedGroup:
+    def demultiplex(self, barcodes, slot: int = 0, compact: bool = False, pack_threads: int = 1) -> DemuxedGroup:
+        """compact=True: the batch crosses PCIe as one 64-bit record per read (barcode_len <= 21), packed here
+        by sgdx_pack_compact_host; same results."""
         arr = as_barcode_array(barcodes, self.matcher.barcode_len)
-        idx, dist = self.matcher.find_batch(arr, slot)
+        idx, dist = self.matcher.find_batch_compact(arr, slot, pack_threads) if compact else self.matcher.find_batch(arr, slot)
         unmatched = arr[idx == self.undetermined_sample_index] if self.collect_unmatched else None
         return DemuxedGroup(idx, dist, unmatched)
 

@@ -127,6 +127,14 @@ class GpuMatcher : public Matcher {
         check(sgdx_match_batch(h_, slot, barcodes, n, idx, dist), "sgdx_match_batch");
         check(sgdx_sync(h_, slot, nullptr), "sgdx_sync");
     }
+    // the same through compact records (barcode_len() <= SGDX_COMPACT_MAX_LEN): packed on the host, 8 bytes per
+    // read over PCIe; `records` is the caller's (ideally pinned) buffer of n words
+    void find_batch_compact(const uint8_t *barcodes, uint64_t n, uint64_t *records, uint16_t *idx, uint8_t *dist,
+                            unsigned slot = 0, unsigned pack_threads = 1) {
+        check(sgdx_pack_compact_host(barcodes, n, (uint32_t)L_, records, pack_threads), "sgdx_pack_compact_host");
+        check(sgdx_match_compact_batch(h_, slot, records, n, idx, dist), "sgdx_match_compact_batch");
+        check(sgdx_sync(h_, slot, nullptr), "sgdx_sync");
+    }
 
   private:
     sgdx_handle *h_ = nullptr;

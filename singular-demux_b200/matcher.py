@@ -100,6 +100,15 @@ def as_barcode_array(barcodes, L: int) -> np.ndarray:
     return np.frombuffer(b"".join(rows), dtype=np.uint8).reshape(len(rows), L)
 
 
+def pack_compact_host(barcodes: np.ndarray, threads: int = 1, out: Optional[np.ndarray] = None) -> np.ndarray:
+    """sgdx_pack_compact_host: (n, L) ASCII barcodes -> n compact 64-bit records (format: include/sgdx.h)."""
+    arr = np.ascontiguousarray(barcodes, dtype=np.uint8)
+    n, L = arr.shape
+    rec = np.empty(n, dtype=np.uint64) if out is None else out
+    check(lib().sgdx_pack_compact_host(arr.ctypes.data, n, L, rec.ctypes.data, threads), "sgdx_pack_compact_host")
+    return rec
+
+
 class GpuMatcher:
     """A matcher bound to one CUDA device through sgdx_create (owns an sgdx handle)."""
 
@@ -192,6 +201,27 @@ class GpuMatcher:
     def match_packed_device(self, d_packed_ptr: int, n: int, d_idx_ptr: int, d_dist_ptr: int = 0, slot: int = 0) -> None:
         check(lib().sgdx_match_packed_device(self._h, slot, d_packed_ptr, n, d_idx_ptr, d_dist_ptr or None),
               "sgdx_match_packed_device")
+
+    # -- compact records: one 64-bit word per read (barcode_len <= 21), include/sgdx.h ------------
+    def find_batch_compact(self, barcodes, slot: int = 0, threads: int = 1) -> Tuple[np.ndarray, np.ndarray]:
+        """find_batch through the compact path: host pack -> 8 bytes per read over PCIe -> sgdx_match_compact."""
+        rec = pack_compact_host(as_barcode_array(barcodes, self.barcode_len), threads)
+        idx = np.empty(rec.size, dtype=np.uint16)
+        dist = np.empty(rec.size, dtype=np.uint8)
+        self.submit_compact_ptr(rec.ctypes.data, rec.size, idx.ctypes.data, dist.ctypes.data, slot)
+        self.sync(slot)
+        return idx, dist
+
+    def submit_compact_ptr(self, rec_ptr: int, n: int, idx_ptr: int, dist_ptr: int, slot: int = 0) -> None:
+        check(lib().sgdx_match_compact_batch(self._h, slot, rec_ptr, n, idx_ptr, dist_ptr or None),
+              "sgdx_match_compact_batch")
+
+    def pack_compact_device(self, d_ascii_ptr: int, n: int, d_records_ptr: int, slot: int = 0) -> None:
+        check(lib().sgdx_pack_compact_device(self._h, slot, d_ascii_ptr, n, d_records_ptr), "sgdx_pack_compact_device")
+
+    def match_compact_device(self, d_records_ptr: int, n: int, d_idx_ptr: int, d_dist_ptr: int = 0, slot: int = 0) -> None:
+        check(lib().sgdx_match_compact_device(self._h, slot, d_records_ptr, n, d_idx_ptr, d_dist_ptr or None),
+              "sgdx_match_compact_device")
 
     def set_stream(self, slot: int, cuda_stream: int) -> None:
         check(lib().sgdx_set_stream(self._h, slot, cuda_stream or None), "sgdx_set_stream")
