@@ -175,6 +175,10 @@ void sgdx_batcher_destroy(sgdx_batcher *b);
 int sgdx_batcher_push(sgdx_batcher *b, const uint8_t *barcodes_ascii, uint64_t n);
 /* launch the partially filled batch, if any */
 int sgdx_batcher_flush(sgdx_batcher *b);
+/* on != 0: sgdx_batcher_push packs each barcode into a compact record as it copies it into the pinned buffer, and
+ * batches go up as 8 bytes per read (barcode_len <= SGDX_COMPACT_MAX_LEN, no unmatched collection).  Call before
+ * the first push or after the last result was taken. */
+int sgdx_batcher_set_compact(sgdx_batcher *b, int on);
 /* Oldest unconsumed batch: blocks until it is done; pointers stay valid until the next call of
  * sgdx_batcher_next/destroy.  *n == 0 when nothing is pending. */
 int sgdx_batcher_next(sgdx_batcher *b, const uint16_t **idx, const uint8_t **dist, uint64_t *n);

@@ -77,7 +77,7 @@ SYMBOLS = [
     "sgdx_match_packed_device", "sgdx_pack_compact_host", "sgdx_pack_compact_device", "sgdx_match_compact_batch",
     "sgdx_match_compact_device", "sgdx_set_stream", "sgdx_kernel_name", "sgdx_path_flags", "sgdx_launch_count", "sgdx_counters", "sgdx_reset_counters",
     "sgdx_hop_count", "sgdx_hop_export", "sgdx_batcher_create", "sgdx_batcher_destroy", "sgdx_batcher_push",
-    "sgdx_batcher_flush", "sgdx_batcher_next", "sgdx_measure_int_peak",
+    "sgdx_batcher_flush", "sgdx_batcher_set_compact", "sgdx_batcher_next", "sgdx_measure_int_peak",
     "sgdx_unmatched_enable", "sgdx_unmatched_info_get", "sgdx_unmatched_export", "sgdx_unmatched_top",
     "sgdx_unmatched_downsize", "sgdx_extract_device", "sgdx_match_segments_device", "sgdx_qual_counts_device",
     "sgdx_base_qual_counters", "sgdx_route_device", "sgdx_demultiplex_device",
@@ -129,6 +129,7 @@ def lib() -> C.CDLL:
     L.sgdx_batcher_destroy.restype = None
     L.sgdx_batcher_push.argtypes = [vp, vp, u64]
     L.sgdx_batcher_flush.argtypes = [vp]
+    L.sgdx_batcher_set_compact.argtypes = [vp, i32]
     L.sgdx_batcher_next.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(u64)]
     L.sgdx_unmatched_enable.argtypes = [vp, u64, u64]
     L.sgdx_unmatched_info_get.argtypes = [vp, C.POINTER(UnmatchedInfo)]

@@ -801,6 +801,7 @@ struct sgdx_batcher {
     sgdx_handle *h = nullptr;
     uint64_t batch_reads = 0;
     uint32_t L = 0;
+    bool compact = false;           // the pinned buffers hold 64-bit compact records instead of L ASCII bytes
     std::vector<uint8_t *> in;      // one pinned input buffer per slot
     std::vector<bool> slot_busy;    // slot has an unsynced batch
     uint32_t cur = 0;               // slot being filled
@@ -820,13 +821,23 @@ extern "C" int sgdx_batcher_create(sgdx_handle *h, uint64_t batch_reads, sgdx_ba
     b->slot_busy.assign(h->slots.size(), false);
     for (auto &p : b->in) {
         void *q = nullptr;
-        if (int rc = sgdx_alloc_host(batch_reads * b->L, &q)) {
+        if (int rc = sgdx_alloc_host(batch_reads * std::max<uint32_t>(b->L, 8u), &q)) {
             sgdx_batcher_destroy(b);
             return rc;
         }
         p = static_cast<uint8_t *>(q);
     }
     *out = b;
+    return SGDX_OK;
+}
+
+extern "C" int sgdx_batcher_set_compact(sgdx_batcher *b, int on) {
+    if (!b) return fail(SGDX_EINVAL, "null batcher");
+    if (b->fill || !b->inflight.empty()) return fail(SGDX_ESTATE, "sgdx_batcher_set_compact: batches are in flight");
+    if (on && b->L > kCompactMaxLen)
+        return fail(SGDX_EINVAL, "compact records hold at most %u bases, barcode_len is %u", kCompactMaxLen, b->L);
+    if (on && b->h->unm.on) return fail(SGDX_ESTATE, "unmatched collection needs ASCII input");
+    b->compact = on != 0;
     return SGDX_OK;
 }
 
@@ -867,7 +878,10 @@ static int submit(sgdx_batcher *b) {
     }
     r.n = b->fill;
     r.slot = b->cur;
-    if (int rc = sgdx_match_batch(b->h, b->cur, b->in[b->cur], r.n, r.idx, r.dist)) {
+    const int rc_submit = b->compact ? sgdx_match_compact_batch(b->h, b->cur, reinterpret_cast<const uint64_t *>(b->in[b->cur]),
+                                                                r.n, r.idx, r.dist)
+                                     : sgdx_match_batch(b->h, b->cur, b->in[b->cur], r.n, r.idx, r.dist);
+    if (int rc = rc_submit) {
         b->free_results.push_back(r);  // the reads stay in the slot's input buffer; a retry re-submits them
         return rc;
     }
@@ -886,7 +900,12 @@ extern "C" int sgdx_batcher_push(sgdx_batcher *b, const uint8_t *ascii, uint64_t
     if (!b || (n && !ascii)) return fail(SGDX_EINVAL, "sgdx_batcher_push: null argument");
     while (n) {
         uint64_t take = std::min(n, b->batch_reads - b->fill);
-        memcpy(b->in[b->cur] + b->fill * b->L, ascii, take * b->L);
+        if (b->compact) {  // the copy into the pinned buffer is the packing pass
+            if (int rc = sgdx_pack_compact_host(ascii, take, b->L, reinterpret_cast<uint64_t *>(b->in[b->cur]) + b->fill, 1))
+                return rc;
+        } else {
+            memcpy(b->in[b->cur] + b->fill * b->L, ascii, take * b->L);
+        }
         b->fill += take;
         ascii += take * b->L;
         n -= take;

@@ -161,3 +161,33 @@ def test_compact_empty_tiny_and_refused_inputs():
     with pytest.raises(sg.SgdxError, match="at most 21"):
         long.submit_compact_ptr(rec.ctypes.data, 4, idx.ctypes.data, 0)
     long.close()
+
+
+def test_batcher_in_compact_mode_returns_the_same_batches():
+    """sgdx_batcher_set_compact: push packs into the pinned buffer, batches go up as 8 bytes per read."""
+    from singular_demux_b200._lib import check, lib
+    rng = np.random.default_rng(3)
+    w, table, reads = _random_case(rng, 96, 16, 8, n=100_000)
+    want = _oracle(table, sg.MatcherKind.CachedHammingDistance, 1, 2, 1, None, w.index_lengths, reads)
+    st = _stage(table, sg.MatcherKind.CachedHammingDistance, 1, 2, 1, None, w.index_lengths, slots=2)
+    b = C.c_void_p()
+    check(lib().sgdx_batcher_create(st.matcher.handle, 16_384, C.byref(b)))
+    check(lib().sgdx_batcher_set_compact(b, 1))
+    got_idx, got_dist = [], []
+    for chunk in np.array_split(reads, 100):  # 1000-read chunks like --chunksize
+        c = np.ascontiguousarray(chunk)
+        check(lib().sgdx_batcher_push(b, c.ctypes.data, c.shape[0]))
+    assert lib().sgdx_batcher_set_compact(b, 0) != 0  # refused while batches are in flight
+    check(lib().sgdx_batcher_flush(b))
+    while True:
+        pi, pd, n = C.c_void_p(), C.c_void_p(), C.c_uint64(0)
+        check(lib().sgdx_batcher_next(b, C.byref(pi), C.byref(pd), C.byref(n)))
+        if n.value == 0:
+            break
+        got_idx.append(np.ctypeslib.as_array(C.cast(pi, C.POINTER(C.c_uint16)), (n.value,)).copy())
+        got_dist.append(np.ctypeslib.as_array(C.cast(pd, C.POINTER(C.c_uint8)), (n.value,)).copy())
+    lib().sgdx_batcher_destroy(b)
+    assert np.array_equal(np.concatenate(got_idx), want["idx"])
+    assert np.array_equal(np.concatenate(got_dist), want["dist"])
+    assert np.array_equal(st.metrics().per_sample_array(), want["per_sample"])
+    st.close()

@@ -102,6 +102,8 @@ def main():
         pageable = np.array(h_in)  # the extractor's output: ordinary host memory
         ref_idx = d_idx.cpu().numpy().view(np.uint16)
         chunk, nslots = min(args.chunk, n), m.slots
+        from concurrent.futures import ThreadPoolExecutor
+        pool = ThreadPoolExecutor(args.pack_threads)  # ctypes calls release the GIL
 
         def run(mode):
             off, i = 0, 0
@@ -113,9 +115,13 @@ def main():
                 if mode == "ascii":
                     m.submit_ptr(hin.value + off * L, c, hidx.value + off * 2, hdist.value + off, slot)
                 else:
-                    if mode == "pack":
-                        sg._lib.check(lib.sgdx_pack_compact_host(pageable.ctypes.data + off * L, c, L, hrec.value + off * 8,
-                                                                 args.pack_threads))
+                    if mode == "pack":  # a persistent pool of host threads, each packing its share of the chunk
+                        per = (c + args.pack_threads - 1) // args.pack_threads
+                        futs = [pool.submit(lib.sgdx_pack_compact_host, pageable.ctypes.data + (off + b) * L,
+                                            min(per, c - b), L, hrec.value + (off + b) * 8, 1)
+                                for b in range(0, c, per)]
+                        for f in futs:
+                            sg._lib.check(f.result())
                     m.submit_compact_ptr(hrec.value + off * 8, c, hidx.value + off * 2, hdist.value + off, slot)
                 off += c
                 i += 1
