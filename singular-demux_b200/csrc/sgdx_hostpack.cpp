@@ -7,6 +7,7 @@
 // matcher -- assignment itself has no CPU path.
 #include <algorithm>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <thread>
 #include <vector>
@@ -46,7 +47,9 @@ void pack_range_scalar(const uint8_t *ascii, uint64_t begin, uint64_t end, uint3
 
 #if defined(__x86_64__)
 // 32 bytes per load, one read per iteration: bit 1 / bit 2 of every byte through a shift + movemask, validity
-// through a nibble-indexed table of the four letters (a byte is A/C/G/T iff table[byte & 15] == byte)
+// through a nibble-indexed table of the four letters (a byte is A/C/G/T iff table[byte & 15] == byte).
+// Measured and not kept: 64-byte AVX-512 loads (three reads per load, masks cut with PEXT) and non-temporal
+// stores of the records -- neither was faster; the pass runs at the speed of a memcpy of the same bytes.
 __attribute__((target("avx2"))) void pack_range_avx2(const uint8_t *ascii, uint64_t begin, uint64_t end, uint32_t L,
                                                      uint64_t total, uint64_t *out) {
     // reads whose 32-byte load would run past the end of the buffer take the scalar path
@@ -75,7 +78,7 @@ __attribute__((target("avx2"))) void pack_range_avx2(const uint8_t *ascii, uint6
 
 void pack_range(const uint8_t *ascii, uint64_t begin, uint64_t end, uint32_t L, uint64_t total, uint64_t *out) {
 #if defined(__x86_64__)
-    static const bool have_avx2 = __builtin_cpu_supports("avx2");
+    static const bool have_avx2 = __builtin_cpu_supports("avx2") && !getenv("SGDX_PACK_NO_AVX2");
     if (have_avx2) return pack_range_avx2(ascii, begin, end, L, total, out);
 #endif
     (void)total;

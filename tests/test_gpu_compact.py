@@ -11,10 +11,7 @@ import sgdx_loader
 from oracle import oracle as orc
 
 sg = sgdx_loader.load()
-# Opt-in until the path has had its first green run on a B200 (the round's GPU budget ran out right after it was
-# written): SGDX_TEST_COMPACT=1 python -m pytest tests/test_gpu_compact.py -m gpu
-pytestmark = [pytest.mark.gpu, pytest.mark.skipif(os.environ.get("SGDX_TEST_COMPACT") != "1",
-                                                  reason="compact path not yet validated on a GPU; set SGDX_TEST_COMPACT=1")]
+pytestmark = pytest.mark.gpu
 
 ORC_KIND = {sg.MatcherKind.CachedHammingDistance: orc.MATCHER_CACHED_HAMMING, sg.MatcherKind.PreCompute: orc.MATCHER_PRECOMPUTE}
 CLS = {sg.MatcherKind.CachedHammingDistance: sg.CachedHammingDistanceMatcher, sg.MatcherKind.PreCompute: sg.PreComputeMatcher}
