@@ -335,6 +335,22 @@ def main():
         import bench_post
         post = bench_post.measure(reads=min(n, 50_000_000), steps=min(args.steps, 10), warmup=max(args.warmup, 3))
 
+    # ---- the compact-record input format next to the ASCII path, same workload: kernel time on
+    # resident records and the end-to-end call from host records; reported beside `value` / `e2e`, not instead
+    compact = None
+    if rank == 0 and world == 1 and not args.no_post and L <= 21:
+        try:
+            d_in = d_idx = d_dist = None
+            torch.cuda.empty_cache()
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import bench_compact
+            compact = bench_compact.measure(config=args.config, reads=n, steps=min(args.steps, 10),
+                                            warmup=max(args.warmup, 3), no_e2e=args.no_e2e)
+        except Exception as ex:  # never lose the bench line to the side measurement
+            import traceback
+            traceback.print_exc()
+            compact = {"error": repr(ex)}
+
     if rank == 0:
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -345,7 +361,7 @@ def main():
                        "input": "ASCII barcodes resident in HBM", "sharding": f"{world} shard(s) by read range, host-merged counters",
                        "l2": f"inputs {n * L / 1e6:.0f} MB + outputs {n * 3 / 1e6:.0f} MB per step, larger than the 126 MB L2"},
             "roofline": roofline, "cpu_baseline": cb, "e2e": e2e, "gpu_launches": int(launches),
-            "clocks": clocks, "matched_fraction": matched_frac, "post": post,
+            "clocks": clocks, "matched_fraction": matched_frac, "post": post, "compact": compact,
         }
         os.write(json_fd, (json.dumps(out) + "\n").encode())
     if world > 1:

@@ -26,7 +26,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def main():
+def parse_args(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--config", default="C2")
     ap.add_argument("--reads", type=int, default=100_000_000)
@@ -35,7 +35,14 @@ def main():
     ap.add_argument("--chunk", type=int, default=4_000_000)
     ap.add_argument("--pack-threads", type=int, default=os.cpu_count() or 1)
     ap.add_argument("--no-e2e", action="store_true")
-    args = ap.parse_args()
+    return ap.parse_args(argv)
+
+
+def measure(**kw):
+    """Returns the numbers as a dict; used by this script and by bench.py's "compact" key."""
+    args = parse_args([])
+    for k, v in kw.items():
+        setattr(args, k, v)
 
     import numpy as np
     import torch
@@ -149,7 +156,11 @@ def main():
         for p in (hin, hrec, hidx, hdist):
             lib.sgdx_free_host(p)
     m.close()
-    print(json.dumps(out))
+    return out
+
+
+def main():
+    print(json.dumps(measure(**vars(parse_args()))))
 
 
 if __name__ == "__main__":
