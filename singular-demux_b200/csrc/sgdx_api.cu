@@ -256,8 +256,48 @@ static int build_compact_table(sgdx_handle *h, const std::vector<uint2> &table) 
         h->cx.bits = bits;
         h->cx.k0 = k0;
         h->cx.k1 = k1;
-        return SGDX_OK;
+        break;
     }
+    if (!h->cx.slots) return SGDX_OK;
+
+    // short seed index for stage 2 (see CompactParams): same construction as build_seed_index with M + 1 chunks
+    const uint32_t C = p.M + 1u;
+    if (!getenv("SGDX_SHORT_SEED") || (uint64_t)p.dmin <= 2ull * p.M + p.delta || C > p.L || C > 8u) return SGDX_OK;
+    std::vector<uint16_t> hdr, ids((size_t)C * p.S, 0);
+    uint32_t total = 0;
+    for (uint32_t c = 0; c < C; c++) {
+        const uint32_t a = (uint32_t)((uint64_t)c * p.L / C), b = (uint32_t)((uint64_t)(c + 1) * p.L / C);
+        const uint32_t w = std::min(b - a, 5u), nb = 1u << (2 * w), wm = (1u << w) - 1u;
+        h->cx.short_desc[c] = a | (w << 8) | (total << 16);
+        hdr.resize(total + nb + 1u, 0);
+        auto key_of = [&](uint32_t s) { return ((table[s].x >> a) & wm) | (((table[s].y >> a) & wm) << w); };
+        std::vector<uint32_t> cnt(nb, 0u);
+        for (uint32_t s = 0; s < p.S; s++) cnt[key_of(s)]++;
+        uint32_t run = c * p.S;
+        for (uint32_t k = 0; k < nb; k++) {
+            hdr[total + k] = (uint16_t)run;
+            run += cnt[k];
+            cnt[k] = 0;
+        }
+        hdr[total + nb] = (uint16_t)run;
+        for (uint32_t s = 0; s < p.S; s++) {
+            const uint32_t k = key_of(s);
+            ids[hdr[total + k] + cnt[k]++] = (uint16_t)s;
+        }
+        total += nb + 1u;
+    }
+    if ((uint64_t)C * p.S > 0xFFFFu || total > 0xFFFFu ||
+        compact_smem_bytes(p, h->cx.bits, total, C * p.S) > 72u * 1024u)  // keep three CTAs per SM
+        return SGDX_OK;
+    CU(cudaMalloc(&h->d_cx_short_hdr, hdr.size() * sizeof(uint16_t)));
+    CU(cudaMalloc(&h->d_cx_short_ids, ids.size() * sizeof(uint16_t)));
+    CU(cudaMemcpy(h->d_cx_short_hdr, hdr.data(), hdr.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(h->d_cx_short_ids, ids.data(), ids.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    h->cx.short_hdr = h->d_cx_short_hdr;
+    h->cx.short_ids = h->d_cx_short_ids;
+    h->cx.short_hdr_total = total;
+    h->cx.short_ids_total = C * p.S;
+    h->cx.short_C = C;
     return SGDX_OK;
 }
 
@@ -450,6 +490,8 @@ extern "C" void sgdx_destroy(sgdx_handle *h) {
     cudaFree(h->d_ex_ascii);
     cudaFree(h->d_nb_slots);
     cudaFree(h->d_cx_slots);
+    cudaFree(h->d_cx_short_hdr);
+    cudaFree(h->d_cx_short_ids);
     cudaFree(h->d_hash1);
     cudaFree(h->d_hash2);
     cudaFree(h->d_hop_lut1);
@@ -678,7 +720,7 @@ extern "C" uint32_t sgdx_path_flags(const sgdx_handle *h) {
     const DevParams &p = h->base;
     return (h->seeded ? SGDX_PATH_SEED_INDEX : 0u) | (h->seeded && p.ex_on ? SGDX_PATH_EXACT : 0u) |
            (h->seeded && p.ex_on && p.nb_on ? SGDX_PATH_NEIGHBOURS : 0u) | (p.hop_direct ? SGDX_PATH_HOP_DIRECT : 0u) |
-           (h->cx.slots ? SGDX_PATH_COMPACT : 0u);
+           (h->cx.slots ? SGDX_PATH_COMPACT : 0u) | (h->cx.short_C ? SGDX_PATH_SHORT_SEED : 0u);
 }
 
 extern "C" uint64_t sgdx_launch_count(const sgdx_handle *h) { return h ? h->launches.load() : 0; }

@@ -40,10 +40,13 @@ struct CompactSmem {
     uint32_t *ring;   // [3] pushes of the current phase
     uint16_t *hdr;    // seed index
     uint16_t *ids;
+    uint16_t *shdr;   // short seed index (stage 2), may be empty
+    uint16_t *sids;
 };
 
 __host__ __device__ inline size_t compact_carve(unsigned char *base, uint32_t threads, uint32_t S, uint32_t bits,
-                                                uint32_t hdr_total, uint32_t ids_total, CompactSmem *out) {
+                                                uint32_t hdr_total, uint32_t ids_total, uint32_t shdr_total,
+                                                uint32_t sids_total, CompactSmem *out) {
     size_t o = 0;
     CompactSmem s;
     s.table = reinterpret_cast<uint2 *>(base + o);      o += ((size_t)S * 8 + 15) & ~(size_t)15;
@@ -55,12 +58,15 @@ __host__ __device__ inline size_t compact_carve(unsigned char *base, uint32_t th
     s.ring = reinterpret_cast<uint32_t *>(base + o);    o += 16;
     s.hdr = reinterpret_cast<uint16_t *>(base + o);     o += ((size_t)hdr_total * 2 + 15) & ~(size_t)15;
     s.ids = reinterpret_cast<uint16_t *>(base + o);     o += ((size_t)ids_total * 2 + 15) & ~(size_t)15;
+    s.shdr = reinterpret_cast<uint16_t *>(base + o);    o += ((size_t)shdr_total * 2 + 15) & ~(size_t)15;
+    s.sids = reinterpret_cast<uint16_t *>(base + o);    o += ((size_t)sids_total * 2 + 15) & ~(size_t)15;
     if (out) *out = s;
     return o;
 }
 
-size_t compact_smem_bytes(const DevParams &p, uint32_t bits) {
-    return compact_carve(nullptr, kCompactThreads, p.S, bits, p.seed_hdr_total, p.seed_ids_total, nullptr);
+size_t compact_smem_bytes(const DevParams &p, uint32_t bits, uint32_t shdr_total, uint32_t sids_total) {
+    return compact_carve(nullptr, kCompactThreads, p.S, bits, p.seed_hdr_total, p.seed_ids_total, shdr_total, sids_total,
+                         nullptr);
 }
 
 __device__ __forceinline__ Rd rd_of_compact(uint64_t rec) {
@@ -87,7 +93,7 @@ __global__ void __launch_bounds__(kCompactThreads, 3) sgdx_match_compact(const D
     constexpr uint32_t T = kCompactThreads, R = kCompactReadsPerThread, nwarps = T / 32;
     constexpr uint32_t kNone = 0xFFFFFFFFu;
     CompactSmem sm;
-    compact_carve(smem_raw, T, p.S, c.bits, p.seed_hdr_total, p.seed_ids_total, &sm);
+    compact_carve(smem_raw, T, p.S, c.bits, p.seed_hdr_total, p.seed_ids_total, c.short_hdr_total, c.short_ids_total, &sm);
     const uint32_t nbins = (p.S + 1u) * 3u;
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const uint32_t nslots = 1u << c.bits;
@@ -97,6 +103,8 @@ __global__ void __launch_bounds__(kCompactThreads, 3) sgdx_match_compact(const D
     for (uint32_t i = threadIdx.x; i < p.S; i += T) sm.table[i] = p.table[i];
     for (uint32_t i = threadIdx.x; i < p.seed_hdr_total; i += T) sm.hdr[i] = p.seed_hdr[i];
     for (uint32_t i = threadIdx.x; i < p.seed_ids_total; i += T) sm.ids[i] = p.seed_ids[i];
+    for (uint32_t i = threadIdx.x; i < c.short_hdr_total; i += T) sm.shdr[i] = c.short_hdr[i];
+    for (uint32_t i = threadIdx.x; i < c.short_ids_total; i += T) sm.sids[i] = c.short_ids[i];
     if (threadIdx.x < 4) sm.ring[threadIdx.x] = 0u;
     __syncthreads();
 
@@ -162,6 +170,25 @@ __global__ void __launch_bounds__(kCompactThreads, 3) sgdx_match_compact(const D
             const uint64_t rec = __ldg(c.reads + r);
             if ((rec >> (2u * kCompactField)) != 0ull) {
                 sm.q3[n3 + push_slot()] = e;
+            } else if (c.short_C) {
+                // dmin > 2M + delta: at most one sample is within M of this read, and then every other one is
+                // further than M + delta away -- the first candidate with d <= M is the verdict, nxt stays "none"
+                rd = rd_of_compact(rec);
+                for (uint32_t ch = 0; ch < c.short_C; ch++) {
+                    const uint32_t desc = c.short_desc[ch];
+                    const uint32_t pos = desc & 0xFFu, w = (desc >> 8) & 0xFFu, off = desc >> 16;
+                    const uint32_t wm = (1u << w) - 1u;
+                    const uint32_t key = ((rd.lo >> pos) & wm) | (((rd.hi >> pos) & wm) << w);
+                    const uint32_t start = sm.shdr[off + key], end = sm.shdr[off + key + 1u];
+#pragma unroll 1
+                    for (uint32_t i = start; i < end; i++) {
+                        const uint32_t s = sm.sids[i];
+                        const uint2 t = sm.table[s];
+                        const uint32_t d = __popc((rd.lo ^ t.x) | (rd.hi ^ t.y));
+                        if (d <= p.M) best = (d << 16) | s;
+                    }
+                }
+                done = true;
             } else {  // an all-A/C/G/T read passes the gate and the cannot-match test
                 rd = rd_of_compact(rec);
                 seed_search<MODE, false>(p, sm.hdr, sm.ids, sm.table, rd, best, nxt);
@@ -270,7 +297,7 @@ __global__ void __launch_bounds__(256) sgdx_expand_compact(const uint64_t *__res
 
 cudaError_t launch_compact(const DevParams &p, const CompactParams &c, uint32_t mode, int sms, cudaStream_t stream) {
     if (p.n == 0) return cudaSuccess;
-    const size_t smem = compact_smem_bytes(p, c.bits);
+    const size_t smem = compact_smem_bytes(p, c.bits, c.short_hdr_total, c.short_ids_total);
     auto kern = mode == kModeHamming ? sgdx_match_compact<kModeHamming> : sgdx_match_compact<kModePreCompute>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;

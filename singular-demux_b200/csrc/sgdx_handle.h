@@ -84,6 +84,7 @@ struct sgdx_handle {
     bool seeded = false;  // launches use sgdx_match_seeded
     uint32_t *d_cx_slots = nullptr;  // compact-record front end (sgdx_compact.cu); cx.slots == nullptr: not available
     sgdx::CompactParams cx{};
+    uint16_t *d_cx_short_hdr = nullptr, *d_cx_short_ids = nullptr;
     sgdx::HopSlot *d_hash1 = nullptr, *d_hash2 = nullptr;
     uint16_t *d_hop_lut1 = nullptr, *d_hop_lut2 = nullptr;
     unsigned long long *d_hop_fwd = nullptr, *d_hop_rev = nullptr;

@@ -23,9 +23,18 @@ struct CompactParams {
     const uint32_t *slots;  // [1 << bits] cuckoo table of the expected barcodes: (tag16 << 16) | (sample + 1), 0 = empty
     uint32_t bits;
     uint32_t k0, k1;        // multipliers of the hash over the record's two 32-bit words
+    // Short seed index (optional): when min pairwise table distance > 2 * max_mismatches + min_delta, a read without
+    // invalid positions that is within max_mismatches of a sample has every other sample further than
+    // max_mismatches + min_delta away, so only samples within max_mismatches matter and the delta test cannot
+    // fail: max_mismatches + 1 chunks instead of max_mismatches + min_delta + 1.  Same bucket layout as the seed
+    // index of DevParams; short_C == 0: not available.
+    const uint16_t *short_hdr;
+    const uint16_t *short_ids;
+    uint32_t short_C, short_hdr_total, short_ids_total;
+    uint32_t short_desc[8];
 };
 inline uint64_t compact_record(uint32_t lo, uint32_t hi) { return (uint64_t)lo | ((uint64_t)hi << 21); }
-size_t compact_smem_bytes(const DevParams &p, uint32_t bits);
+size_t compact_smem_bytes(const DevParams &p, uint32_t bits, uint32_t short_hdr_total = 0, uint32_t short_ids_total = 0);
 cudaError_t launch_compact(const DevParams &p, const CompactParams &c, uint32_t mode, int sms, cudaStream_t stream);
 cudaError_t launch_pack_compact(const uint8_t *reads, uint64_t n, uint32_t L, uint64_t *out, int sms, cudaStream_t stream);
 cudaError_t launch_expand_compact(const uint64_t *in, uint64_t n, uint4 *out, int sms, cudaStream_t stream);
