@@ -74,3 +74,36 @@ def test_packer_rejects_barcodes_longer_than_a_record():
     assert b"compact records" in L.sgdx_last_error()
     assert L.sgdx_pack_compact_host(None, 4, 20, out, 1) == -1
     assert L.sgdx_pack_compact_host(None, 0, 20, None, 1) == 0
+
+
+@pytest.mark.parametrize("cfg_name,M,D", [("C1", 1, 2), ("C2", 1, 2), ("C1", 2, 1), ("C2", 0, 5), ("C2", 2, 1)])
+def test_short_seed_rule_holds_in_the_oracle(cfg_name, M, D):
+    """The claim behind CompactParams.short_*: when the table's minimum pairwise distance exceeds 2M + delta, a read
+    made of A/C/G/T only is Match(s, d) iff exactly one sample s is within d <= M of it (then the delta test cannot
+    fail), else NoMatch -- in both rule sets.  Checked against the oracle (the restated reference rules)."""
+    from oracle import oracle as orc
+    w = sg.synth.CONFIGS[cfg_name]
+    table = w.table()
+    S, L = table.shape
+    pair = (table[:, None, :] != table[None, :, :]).sum(-1)
+    np.fill_diagonal(pair, 99)
+    assert pair.min() > 2 * M + D, "pick parameters the synthetic table satisfies"
+    rng = np.random.default_rng(S + 10 * M + D)
+    n = 6000
+    reads = table[rng.integers(0, S, n)].copy()
+    nsub = rng.integers(0, 5, n)  # 0..4 substitutions, the rest random reads
+    letters = np.frombuffer(b"ACGT", dtype=np.uint8)
+    for r in range(n):
+        pos = rng.choice(L, nsub[r], replace=False)
+        reads[r, pos] = letters[rng.integers(0, 4, nsub[r])]
+    reads[-500:] = letters[rng.integers(0, 4, (500, L))]
+    dist = (reads[:, None, :] != table[None, :, :]).sum(-1)
+    best, arg = dist.min(1), dist.argmin(1)
+    want_idx = np.where(best <= M, arg, S).astype(np.uint16)
+    want_dist = np.where(best <= M, best, 0xFF).astype(np.uint8)
+    assert ((dist <= M).sum(1) <= 1).all()
+    for kind in (orc.MATCHER_CACHED_HAMMING, orc.MATCHER_PRECOMPUTE):
+        cfg = orc.Config(S, L, M, D, 1, -1, kind, 0, 0)
+        got = orc.COracle(cfg, [bytes(t) for t in table], force_closed_form=True).run(reads, threads=2, use_cache=False)
+        assert np.array_equal(got["idx"], want_idx)
+        assert np.array_equal(got["dist"], want_dist)
