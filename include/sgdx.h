@@ -152,7 +152,7 @@ const char *sgdx_kernel_name(const sgdx_handle *h);
 #define SGDX_PATH_HOP_DIRECT 8u   /* direct-address hop tables (both index halves <= 11 bases) */
 #define SGDX_PATH_COMPACT 16u     /* sgdx_match_compact serves compact records (exact shortcut valid, barcode_len <= 21) */
 #define SGDX_PATH_SHORT_SEED 32u  /* ... and its seed search uses max_mismatches + 1 chunks (min pairwise distance >
-                                     2 * max_mismatches + min_delta; opt-in: SGDX_SHORT_SEED=1 at sgdx_create) */
+                                     2 * max_mismatches + min_delta; SGDX_NO_SHORT_SEED=1 at sgdx_create turns it off) */
 uint32_t sgdx_path_flags(const sgdx_handle *h);
 /* Number of kernel launches issued through this handle so far. */
 uint64_t sgdx_launch_count(const sgdx_handle *h);

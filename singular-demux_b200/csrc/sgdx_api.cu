@@ -239,30 +239,58 @@ static int build_compact_table(sgdx_handle *h, const std::vector<uint2> &table) 
     const DevParams &p = h->base;
     h->cx = CompactParams{};
     if (!h->seeded || !p.ex_on || p.L > kCompactMaxLen) return SGDX_OK;
-    const uint32_t k0 = 0x9E3779B1u, k1 = 0x85EBCA77u;
-    for (uint32_t bits = std::max(p.ex_bits, 6u); bits <= p.ex_bits + 2u; bits++) {
+    // two-choice cuckoo placement of 64-bit entries (record | (sample + 1) << 42); an entry's positions follow
+    // from its own record, so an evicted entry needs no side table.  Load factor <= 1/4; if a random walk gives
+    // up, other multipliers and then a larger table are tried.
+    static const uint32_t KS[4][4] = {{0x9E3779B1u, 0x85EBCA77u, 0xC2B2AE3Du, 0x27D4EB2Fu},
+                                      {0x165667B1u, 0xD3A2646Du, 0xFD7046C5u, 0xB55A4F09u},
+                                      {0x2545F491u, 0x9E6C63D1u, 0x7FEB352Du, 0x846CA68Bu},
+                                      {0xCC9E2D51u, 0x1B873593u, 0xE6546B65u, 0x85EBCA6Bu}};
+    const uint64_t rec_mask = (1ull << 42) - 1ull;
+    for (uint32_t attempt = 0; attempt < 12 && !h->cx.slots; attempt++) {
+        const uint32_t bits = std::max(p.ex_bits, 6u) + attempt / 4u;
+        const uint32_t *K = KS[attempt % 4u];
         if (compact_smem_bytes(p, bits) > 200u * 1024u) return SGDX_OK;
-        std::vector<uint32_t> slots((size_t)1 << bits, 0u), owner((size_t)1 << bits, 0u);
+        std::vector<uint64_t> slots((size_t)1 << bits, 0ull);
+        auto pos = [&](uint64_t entry, int which) {
+            const uint32_t w0 = (uint32_t)(entry & rec_mask), w1 = (uint32_t)((entry & rec_mask) >> 32);
+            return ((w0 * K[2 * which]) ^ (w1 * K[2 * which + 1])) >> (32u - bits);
+        };
         bool placed = true;
         for (uint32_t s = 0; s < p.S && placed; s++) {
-            const uint64_t rec = compact_record(table[s].x, table[s].y);
-            const uint32_t hsh = ex_mix(ex_word_step(ex_word_step(0u, (uint32_t)rec, k0), (uint32_t)(rec >> 32), k1));
-            placed = cuckoo_insert(slots, owner, 0u, bits, hsh, ((hsh & 0xFFFFu) << 16) | (s + 1u));
+            uint64_t entry = compact_record(table[s].x, table[s].y) | ((uint64_t)(s + 1u) << 42);
+            uint32_t last = 0xFFFFFFFFu;
+            placed = false;
+            for (int kick = 0; kick < 2000 && !placed; kick++) {
+                const uint32_t p1 = pos(entry, 0), p2 = pos(entry, 1);
+                if (slots[p1] == 0ull) {
+                    slots[p1] = entry;
+                    placed = true;
+                } else if (slots[p2] == 0ull) {
+                    slots[p2] = entry;
+                    placed = true;
+                } else {
+                    const uint32_t victim = p1 == last ? p2 : p1;
+                    std::swap(entry, slots[victim]);
+                    last = victim;
+                }
+            }
         }
-        if (!placed) continue;  // not seen at load factor <= 1/4; a larger table is tried twice
-        CU(cudaMalloc(&h->d_cx_slots, slots.size() * sizeof(uint32_t)));
-        CU(cudaMemcpy(h->d_cx_slots, slots.data(), slots.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        if (!placed) continue;
+        CU(cudaMalloc(&h->d_cx_slots, slots.size() * sizeof(uint64_t)));
+        CU(cudaMemcpy(h->d_cx_slots, slots.data(), slots.size() * sizeof(uint64_t), cudaMemcpyHostToDevice));
         h->cx.slots = h->d_cx_slots;
         h->cx.bits = bits;
-        h->cx.k0 = k0;
-        h->cx.k1 = k1;
-        break;
+        h->cx.k0 = K[0];
+        h->cx.k1 = K[1];
+        h->cx.k2 = K[2];
+        h->cx.k3 = K[3];
     }
     if (!h->cx.slots) return SGDX_OK;
 
     // short seed index for stage 2 (see CompactParams): same construction as build_seed_index with M + 1 chunks
     const uint32_t C = p.M + 1u;
-    if (!getenv("SGDX_SHORT_SEED") || (uint64_t)p.dmin <= 2ull * p.M + p.delta || C > p.L || C > 8u) return SGDX_OK;
+    if (getenv("SGDX_NO_SHORT_SEED") || (uint64_t)p.dmin <= 2ull * p.M + p.delta || C > p.L || C > 8u) return SGDX_OK;
     std::vector<uint16_t> hdr, ids((size_t)C * p.S, 0);
     uint32_t total = 0;
     for (uint32_t c = 0; c < C; c++) {

@@ -14,9 +14,9 @@
 //
 // sgdx_match_compact has the shape of sgdx_match_exact_first (sgdx_exact_first.cuh) without its ASCII work:
 //   front end (all reads)  a read without invalid positions is looked up in a cuckoo table of the expected
-//                          barcodes keyed by a hash of the record's two words; a hit whose planes equal the
-//                          barcode's is Match(sample, 0) (valid because min pairwise table distance > min_delta)
-//                          -> done; everything else -> Q1
+//                          barcodes (two positions from two multiply-xor hashes of the record's words, 64-bit
+//                          entries = record | sample << 42); an equal entry is Match(sample, 0) (valid because
+//                          min pairwise table distance > min_delta) -> done; everything else -> Q1
 //   stage 2 (Q1)           reads without invalid positions: pigeonhole seed search -> done; others -> Q3
 //   stage 3 (Q3)           seed search with 4-way expansion of an invalid base; windows with several -> one warp
 //                          per read over all samples
@@ -34,10 +34,12 @@ struct CompactSmem {
     uint2 *table;     // [S] barcode planes
     uint32_t *q1;     // [(R+1)*threads] block-local read numbers
     uint32_t *q3;     // [2*threads]
-    uint32_t *slots;  // [1 << bits]
+    uint2 *slots;     // [1 << bits] 64-bit cuckoo entries
     uint32_t *hist;   // [(S+1)*3]
     uint32_t *cq;     // [threads] Q3 entries that need the all-samples scan
     uint32_t *ring;   // [3] pushes of the current phase
+    uint32_t *sdesc;  // [8] chunk descriptors of the short seed index (a run-time index into the kernel
+                      //     parameter would put the whole struct on the local stack)
     uint16_t *hdr;    // seed index
     uint16_t *ids;
     uint16_t *shdr;   // short seed index (stage 2), may be empty
@@ -50,12 +52,13 @@ __host__ __device__ inline size_t compact_carve(unsigned char *base, uint32_t th
     size_t o = 0;
     CompactSmem s;
     s.table = reinterpret_cast<uint2 *>(base + o);      o += ((size_t)S * 8 + 15) & ~(size_t)15;
+    s.slots = reinterpret_cast<uint2 *>(base + o);      o += (size_t)8 << bits;
     s.q1 = reinterpret_cast<uint32_t *>(base + o);      o += (size_t)threads * (kCompactReadsPerThread + 1) * 4;
     s.q3 = reinterpret_cast<uint32_t *>(base + o);      o += (size_t)threads * 2 * 4;
-    s.slots = reinterpret_cast<uint32_t *>(base + o);   o += (size_t)4 << bits;
     s.hist = reinterpret_cast<uint32_t *>(base + o);    o += (((size_t)(S + 1) * 3 * 4) + 15) & ~(size_t)15;
     s.cq = reinterpret_cast<uint32_t *>(base + o);      o += (size_t)threads * 4;
     s.ring = reinterpret_cast<uint32_t *>(base + o);    o += 16;
+    s.sdesc = reinterpret_cast<uint32_t *>(base + o);   o += 32;
     s.hdr = reinterpret_cast<uint16_t *>(base + o);     o += ((size_t)hdr_total * 2 + 15) & ~(size_t)15;
     s.ids = reinterpret_cast<uint16_t *>(base + o);     o += ((size_t)ids_total * 2 + 15) & ~(size_t)15;
     s.shdr = reinterpret_cast<uint16_t *>(base + o);    o += ((size_t)shdr_total * 2 + 15) & ~(size_t)15;
@@ -98,7 +101,7 @@ __global__ void __launch_bounds__(kCompactThreads, 3) sgdx_match_compact(const D
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const uint32_t nslots = 1u << c.bits;
 
-    for (uint32_t i = threadIdx.x; i < nslots; i += T) sm.slots[i] = c.slots[i];
+    for (uint32_t i = threadIdx.x; i < nslots; i += T) sm.slots[i] = reinterpret_cast<const uint2 *>(c.slots)[i];
     for (uint32_t i = threadIdx.x; i < nbins; i += T) sm.hist[i] = 0u;
     for (uint32_t i = threadIdx.x; i < p.S; i += T) sm.table[i] = p.table[i];
     for (uint32_t i = threadIdx.x; i < p.seed_hdr_total; i += T) sm.hdr[i] = p.seed_hdr[i];
@@ -106,6 +109,9 @@ __global__ void __launch_bounds__(kCompactThreads, 3) sgdx_match_compact(const D
     for (uint32_t i = threadIdx.x; i < c.short_hdr_total; i += T) sm.shdr[i] = c.short_hdr[i];
     for (uint32_t i = threadIdx.x; i < c.short_ids_total; i += T) sm.sids[i] = c.short_ids[i];
     if (threadIdx.x < 4) sm.ring[threadIdx.x] = 0u;
+#pragma unroll
+    for (uint32_t i = 0; i < 8; i++)
+        if (threadIdx.x == i) sm.sdesc[i] = c.short_desc[i];
     __syncthreads();
 
     const uint32_t shift = 32u - c.bits;
@@ -175,7 +181,7 @@ __global__ void __launch_bounds__(kCompactThreads, 3) sgdx_match_compact(const D
                 // further than M + delta away -- the first candidate with d <= M is the verdict, nxt stays "none"
                 rd = rd_of_compact(rec);
                 for (uint32_t ch = 0; ch < c.short_C; ch++) {
-                    const uint32_t desc = c.short_desc[ch];
+                    const uint32_t desc = sm.sdesc[ch];
                     const uint32_t pos = desc & 0xFFu, w = (desc >> 8) & 0xFFu, off = desc >> 16;
                     const uint32_t wm = (1u << w) - 1u;
                     const uint32_t key = ((rd.lo >> pos) & wm) | (((rd.hi >> pos) & wm) << w);
@@ -222,21 +228,15 @@ __global__ void __launch_bounds__(kCompactThreads, 3) sgdx_match_compact(const D
                 const uint32_t w0 = (uint32_t)rec[k], w1 = (uint32_t)(rec[k] >> 32);
                 hit[k] = kNone;
                 if ((w1 >> (2u * kCompactField - 32u)) == 0u) {  // no invalid position (and not a padding lane)
-                    const uint32_t h = ex_mix(ex_word_step(ex_word_step(0u, w0, c.k0), w1, c.k1));
-                    const uint32_t tag = h & 0xFFFFu;
-                    const uint32_t e1 = sm.slots[h >> shift], e2 = sm.slots[ex_second(h) >> shift];
-                    const bool m1 = e1 != 0u && (e1 >> 16) == tag, m2 = e2 != 0u && (e2 >> 16) == tag;
-                    const uint32_t lo = w0 & kCompactMask, hi = __funnelshift_r(w0, w1, kCompactField) & kCompactMask;
-                    if (m1 || m2) {
-                        const uint32_t s = ((m1 ? e1 : e2) & 0xFFFFu) - 1u;
-                        const uint2 t = sm.table[s];
-                        if (t.x == lo && t.y == hi) hit[k] = s;
-                    }
-                    if (m1 && m2 && hit[k] == kNone) {  // both tags matched and the first entry was not it (~never)
-                        const uint32_t s = (e2 & 0xFFFFu) - 1u;
-                        const uint2 t = sm.table[s];
-                        if (t.x == lo && t.y == hi) hit[k] = s;
-                    }
+                    // two multiply-xor hashes of the record's words pick the two cuckoo positions; an entry is
+                    // record | (sample + 1) << 42, so one 64-bit compare both verifies the barcode and yields
+                    // the sample (an empty slot is 0: its sample field fails the test even for an all-A read)
+                    const uint32_t a = ((w0 * c.k0) ^ (w1 * c.k1)) >> shift, b = ((w0 * c.k2) ^ (w1 * c.k3)) >> shift;
+                    const uint2 e1 = sm.slots[a], e2 = sm.slots[b];
+                    const uint32_t x1 = e1.y ^ w1, x2 = e2.y ^ w1;
+                    const bool h1 = ((e1.x ^ w0) | (x1 & 0x3FFu)) == 0u && x1 != 0u;
+                    const bool h2 = ((e2.x ^ w0) | (x2 & 0x3FFu)) == 0u && x2 != 0u;
+                    if (h1 || h2) hit[k] = ((h1 ? x1 : x2) >> 10) - 1u;
                 }
                 if (hit[k] != kNone) {
                     p.out_idx[r] = (uint16_t)hit[k];

@@ -20,9 +20,10 @@ cudaError_t launch_pack(const uint8_t *reads, uint64_t n, uint32_t L, uint4 *out
 constexpr uint32_t kCompactMaxLen = 21;
 struct CompactParams {
     const uint64_t *reads;  // n records
-    const uint32_t *slots;  // [1 << bits] cuckoo table of the expected barcodes: (tag16 << 16) | (sample + 1), 0 = empty
+    const uint64_t *slots;  // [1 << bits] cuckoo table of the expected barcodes: record | (sample + 1) << 42, 0 = empty
     uint32_t bits;
-    uint32_t k0, k1;        // multipliers of the hash over the record's two 32-bit words
+    uint32_t k0, k1, k2, k3;  // position 1 = ((w0 * k0) ^ (w1 * k1)) >> (32 - bits), position 2 likewise with k2, k3
+                              // (w0, w1 = the record's two 32-bit words)
     // Short seed index (optional): when min pairwise table distance > 2 * max_mismatches + min_delta, a read without
     // invalid positions that is within max_mismatches of a sample has every other sample further than
     // max_mismatches + min_delta away, so only samples within max_mismatches matter and the delta test cannot
