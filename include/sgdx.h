@@ -21,6 +21,8 @@
  * Barcodes are passed the way the reference passes them: raw ASCII bytes, all sample-barcode (B)
  * segments of a template concatenated in FASTQ order (demux.rs:404-405,504-522), exactly
  * barcode_len bytes per read (run.rs:109-119 guarantees it outside --sample-barcode-in-fastq-header).
+ * Barcodes of at most 21 bases may instead be passed as one 64-bit compact record each (2-bit base planes +
+ * invalid plane, "Compact records" below): same results, 8 instead of barcode_len bytes per read.
  */
 #ifndef SGDX_H
 #define SGDX_H
