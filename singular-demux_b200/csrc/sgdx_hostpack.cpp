@@ -66,6 +66,10 @@ __attribute__((target("avx2"))) void pack_range_avx2(const uint8_t *ascii, uint6
         const uint32_t b1 = (uint32_t)_mm256_movemask_epi8(_mm256_slli_epi16(x, 6));
         const uint32_t b2 = (uint32_t)_mm256_movemask_epi8(_mm256_slli_epi16(x, 5));
         const uint32_t ok = (uint32_t)_mm256_movemask_epi8(_mm256_cmpeq_epi8(_mm256_shuffle_epi8(lut, _mm256_and_si256(x, nib)), x));
+        if (__builtin_expect((ok & m) == m, 1)) {  // every base is A/C/G/T: no invalid plane to form
+            out[r] = (uint64_t)(b1 & m) | ((uint64_t)(b2 & m) << kField);
+            continue;
+        }
         const uint32_t isn = (uint32_t)_mm256_movemask_epi8(_mm256_cmpeq_epi8(x, enn));
         const uint32_t inv = ~ok & m;
         const uint32_t lo = (b1 & ok & m) | (inv & ~isn);
