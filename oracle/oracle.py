@@ -488,3 +488,25 @@ def demultiplex_batch(cfg: Config, samples: Sequence[bytes], fastqs, structures)
     res["order"], res["offsets"] = route_reads(res["idx"], S)
     res["barcodes"] = barcodes
     return res
+
+
+def compact_records(reads: np.ndarray) -> np.ndarray:
+    """The compact read format of include/sgdx.h ("Compact records"), stated with numpy: one 64-bit word per
+    read of at most 21 bases = lo plane | hi plane << 21 | invalid plane << 42, code = (ascii >> 1) & 3
+    (A0 C1 T2 G3); at a position that is not A/C/G/T the invalid bit is set, hi = 0, and lo = 0 for 'N'
+    (the byte demux.rs:78-80 counts as a no-call) or 1 for any other byte (which mismatches every sample,
+    matcher.rs:335-348).  Checker of sgdx_pack_compact_host / sgdx_pack_compact_device."""
+    reads = np.asarray(reads, dtype=np.uint8)
+    n, L = reads.shape
+    assert L <= 21
+    a = reads.astype(np.uint64)
+    ok = np.isin(reads, np.frombuffer(b"ACGT", dtype=np.uint8))
+    j = np.arange(L, dtype=np.uint64)
+    lo = np.where(ok, (a >> np.uint64(1)) & np.uint64(1), (reads != ord("N")).astype(np.uint64))
+    hi = np.where(ok, (a >> np.uint64(2)) & np.uint64(1), np.uint64(0))
+    inv = (~ok).astype(np.uint64)
+    if n == 0:
+        return np.empty(0, dtype=np.uint64)
+    return ((lo << j).sum(axis=1) | ((hi << j).sum(axis=1) << np.uint64(21)) |
+            ((inv << j).sum(axis=1) << np.uint64(42))).astype(np.uint64)
+

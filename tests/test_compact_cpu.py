@@ -7,23 +7,12 @@ import numpy as np
 import pytest
 
 import sgdx_loader
+from oracle import oracle as orc
 
 sg = sgdx_loader.load()
 
 
-def records_numpy(arr):
-    """lo plane | hi plane << 21 | invalid plane << 42; code = (ascii >> 1) & 3; at an invalid position
-    lo = 0 for 'N' and 1 for any other byte, hi = 0."""
-    n, L = arr.shape
-    a = arr.astype(np.uint64)
-    ok = np.isin(arr, np.frombuffer(b"ACGT", dtype=np.uint8))
-    isn = arr == ord("N")
-    j = np.arange(L, dtype=np.uint64)
-    lo = np.where(ok, (a >> np.uint64(1)) & np.uint64(1), np.where(isn, 0, 1).astype(np.uint64))
-    hi = np.where(ok, (a >> np.uint64(2)) & np.uint64(1), np.uint64(0))
-    inv = (~ok).astype(np.uint64)
-    return ((lo << j).sum(axis=1) | ((hi << j).sum(axis=1) << np.uint64(21)) |
-            ((inv << j).sum(axis=1) << np.uint64(42))).astype(np.uint64)
+records_numpy = orc.compact_records
 
 
 ALPHABET = np.frombuffer(b"ACGTACGTACGTACGTNNacgtn\x00\x01\x41\x43\x47\x54\x4e\x80\xc1\xff\x0f\x11\x31\x51\x61", dtype=np.uint8)
@@ -81,7 +70,6 @@ def test_short_seed_rule_holds_in_the_oracle(cfg_name, M, D):
     """The claim behind CompactParams.short_*: when the table's minimum pairwise distance exceeds 2M + delta, a read
     made of A/C/G/T only is Match(s, d) iff exactly one sample s is within d <= M of it (then the delta test cannot
     fail), else NoMatch -- in both rule sets.  Checked against the oracle (the restated reference rules)."""
-    from oracle import oracle as orc
     w = sg.synth.CONFIGS[cfg_name]
     table = w.table()
     S, L = table.shape
