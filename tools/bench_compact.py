@@ -112,26 +112,26 @@ def measure(**kw):
         from concurrent.futures import ThreadPoolExecutor
         pool = ThreadPoolExecutor(args.pack_threads)  # ctypes calls release the GIL
 
+        def pack_async(off, c):  # a persistent pool of host threads, each packing its share of the chunk
+            per = (c + args.pack_threads - 1) // args.pack_threads
+            return [pool.submit(lib.sgdx_pack_compact_host, pageable.ctypes.data + (off + b) * L, min(per, c - b), L,
+                                hrec.value + (off + b) * 8, 1) for b in range(0, c, per)]
+
         def run(mode):
-            off, i = 0, 0
-            while off < n:
-                c = min(chunk, n - off)
+            chunks = [(off, min(chunk, n - off)) for off in range(0, n, chunk)]
+            futs = pack_async(*chunks[0]) if mode == "pack" else None
+            for i, (off, c) in enumerate(chunks):
                 slot = i % nslots
+                if mode == "pack":  # chunk i + 1 is packed while chunk i is submitted and uploaded
+                    for f in futs:
+                        sg._lib.check(f.result())
+                    futs = pack_async(*chunks[i + 1]) if i + 1 < len(chunks) else None
                 if i >= nslots:
                     m.sync(slot)
                 if mode == "ascii":
                     m.submit_ptr(hin.value + off * L, c, hidx.value + off * 2, hdist.value + off, slot)
                 else:
-                    if mode == "pack":  # a persistent pool of host threads, each packing its share of the chunk
-                        per = (c + args.pack_threads - 1) // args.pack_threads
-                        futs = [pool.submit(lib.sgdx_pack_compact_host, pageable.ctypes.data + (off + b) * L,
-                                            min(per, c - b), L, hrec.value + (off + b) * 8, 1)
-                                for b in range(0, c, per)]
-                        for f in futs:
-                            sg._lib.check(f.result())
                     m.submit_compact_ptr(hrec.value + off * 8, c, hidx.value + off * 2, hdist.value + off, slot)
-                off += c
-                i += 1
             for s in range(nslots):
                 m.sync(s)
 
