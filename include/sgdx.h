@@ -120,6 +120,15 @@ int sgdx_pack_device(sgdx_handle *h, uint32_t slot, const uint8_t *d_barcodes_as
                      sgdx_read *d_packed);
 int sgdx_match_packed_device(sgdx_handle *h, uint32_t slot, const sgdx_read *d_packed, uint64_t n,
                              uint16_t *d_out_idx, uint8_t *d_out_dist);
+/* The packed form from HOST buffers (SURVEY Appendix B's `sgdx_pack` + packed `sgdx_match_batch`): sgdx_pack_host
+ * converts n ASCII barcodes of any barcode_len <= 32 into 16-byte sgdx_read records (host code, `threads` workers,
+ * AVX2 when the CPU has it; same records as sgdx_pack_device), sgdx_match_packed_batch is sgdx_match_batch for such
+ * a buffer (16 instead of barcode_len bytes per read over PCIe: worth it above 16 bases; for <= 21 bases the compact
+ * records below are smaller).  Runs the general kernels; unmatched collection needs ASCII. */
+int sgdx_pack_host(const uint8_t *barcodes_ascii, uint64_t n, uint32_t barcode_len, sgdx_read *out_records,
+                   uint32_t threads /* 0 -> 1 */);
+int sgdx_match_packed_batch(sgdx_handle *h, uint32_t slot, const sgdx_read *records, uint64_t n,
+                            uint16_t *out_idx, uint8_t *out_dist);
 /* Compact records: one 64-bit word per read, for barcode_len <= SGDX_COMPACT_MAX_LEN -- BASELINE.json's
  * "2-bit base planes plus an N mask", SURVEY 8(d)'s algorithmic input of ceil(3L/8) bytes per read:
  *   bits  0..20  lo plane: bit j = bit 0 of base j's code, code = (ascii >> 1) & 3 (A0 C1 T2 G3)

@@ -510,3 +510,23 @@ def compact_records(reads: np.ndarray) -> np.ndarray:
     return ((lo << j).sum(axis=1) | ((hi << j).sum(axis=1) << np.uint64(21)) |
             ((inv << j).sum(axis=1) << np.uint64(42))).astype(np.uint64)
 
+
+def packed_records(reads: np.ndarray) -> np.ndarray:
+    """The 16-byte sgdx_read records of include/sgdx.h, stated with numpy: (n, 4) uint32 {lo, hi, nmask, xmask},
+    bit j = base j; code = (ascii >> 1) & 3 at A/C/G/T positions (planes zero elsewhere), nmask = byte == 'N',
+    xmask = any other byte.  Checker of sgdx_pack_host / sgdx_pack_device."""
+    reads = np.asarray(reads, dtype=np.uint8)
+    n, L = reads.shape
+    assert L <= 32
+    a = reads.astype(np.uint64)
+    ok = np.isin(reads, np.frombuffer(b"ACGT", dtype=np.uint8))
+    isn = reads == ord("N")
+    j = np.arange(L, dtype=np.uint64)
+    out = np.zeros((n, 4), dtype=np.uint32)
+    if n:
+        out[:, 0] = (np.where(ok, (a >> np.uint64(1)) & np.uint64(1), np.uint64(0)) << j).sum(axis=1)
+        out[:, 1] = (np.where(ok, (a >> np.uint64(2)) & np.uint64(1), np.uint64(0)) << j).sum(axis=1)
+        out[:, 2] = (isn.astype(np.uint64) << j).sum(axis=1)
+        out[:, 3] = ((~ok & ~isn).astype(np.uint64) << j).sum(axis=1)
+    return out
+

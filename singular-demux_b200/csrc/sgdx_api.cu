@@ -643,6 +643,19 @@ extern "C" int sgdx_match_batch(sgdx_handle *h, uint32_t slot, const uint8_t *as
 // ------------------------------------------------------------------------------------------------
 // compact records (one 64-bit word per read, barcode_len <= 21)
 // ------------------------------------------------------------------------------------------------
+// the slot's buffer of 16-byte sgdx_read records (expanded compact records, or a packed batch from the host)
+static int ensure_packed_scratch(Slot &s, uint64_t n) {
+    if (n <= s.cexp_cap) return SGDX_OK;
+    CU(cudaStreamSynchronize(s.stream));
+    cudaFree(s.d_cexp);
+    s.d_cexp = nullptr;
+    s.cexp_cap = 0;
+    const uint64_t cap = n + n / 8 + 1024;
+    CU(cudaMalloc(&s.d_cexp, cap * sizeof(uint4)));
+    s.cexp_cap = cap;
+    return SGDX_OK;
+}
+
 static int run_compact(sgdx_handle *h, Slot &s, const uint64_t *d_records, uint64_t n, uint16_t *d_idx, uint8_t *d_dist) {
     if (h->cfg.barcode_len > kCompactMaxLen)
         return fail(SGDX_EINVAL, "compact records hold at most %u bases, barcode_len is %u", kCompactMaxLen, h->cfg.barcode_len);
@@ -650,15 +663,7 @@ static int run_compact(sgdx_handle *h, Slot &s, const uint64_t *d_records, uint6
     if (h->unm.on && n)
         return fail(SGDX_ESTATE, "unmatched collection needs ASCII input (compact records do not keep foreign bytes)");
     if (!h->cx.slots) {  // table without the exact-match shortcut: expand to 16-byte records, general kernels
-        if (n > s.cexp_cap) {
-            CU(cudaStreamSynchronize(s.stream));
-            cudaFree(s.d_cexp);
-            s.d_cexp = nullptr;
-            s.cexp_cap = 0;
-            const uint64_t cap = n + n / 8 + 1024;
-            CU(cudaMalloc(&s.d_cexp, cap * sizeof(uint4)));
-            s.cexp_cap = cap;
-        }
+        if (int rc = ensure_packed_scratch(s, n)) return rc;
         CU(launch_expand_compact(d_records, n, s.d_cexp, h->sms, s.stream));
         if (n) h->launches.fetch_add(1);
         return run_kernels(h, s, nullptr, s.d_cexp, n, d_idx, d_dist);
@@ -710,6 +715,25 @@ extern "C" int sgdx_match_compact_batch(sgdx_handle *h, uint32_t slot, const uin
     uint64_t *d_rec = reinterpret_cast<uint64_t *>(s.d_in);
     if (n) CU(cudaMemcpyAsync(d_rec, records, n * sizeof(uint64_t), cudaMemcpyHostToDevice, s.stream));
     if (int rc = run_compact(h, s, d_rec, n, s.d_idx, s.d_dist)) return rc;
+    if (n) {
+        CU(cudaMemcpyAsync(out_idx, s.d_idx, n * sizeof(uint16_t), cudaMemcpyDeviceToHost, s.stream));
+        if (out_dist) CU(cudaMemcpyAsync(out_dist, s.d_dist, n, cudaMemcpyDeviceToHost, s.stream));
+    }
+    return SGDX_OK;
+}
+
+// sgdx_match_batch for a host buffer of 16-byte sgdx_read records (any barcode_len <= 32; sgdx_pack_host writes them)
+extern "C" int sgdx_match_packed_batch(sgdx_handle *h, uint32_t slot, const sgdx_read *records, uint64_t n,
+                                       uint16_t *out_idx, uint8_t *out_dist) {
+    if (int rc = check_slot(h, slot)) return rc;
+    if (n && (!records || !out_idx)) return fail(SGDX_EINVAL, "sgdx_match_packed_batch: null buffer");
+    if (n >> 34) return fail(SGDX_EINVAL, "batch of %llu reads too large; split it", (unsigned long long)n);
+    CU(cudaSetDevice(h->cfg.device));
+    Slot &s = h->slots[slot];
+    if (int rc = ensure_capacity(s, n, h->cfg.barcode_len)) return rc;
+    if (int rc = ensure_packed_scratch(s, n)) return rc;
+    if (n) CU(cudaMemcpyAsync(s.d_cexp, records, n * sizeof(uint4), cudaMemcpyHostToDevice, s.stream));
+    if (int rc = run_kernels(h, s, nullptr, s.d_cexp, n, s.d_idx, s.d_dist)) return rc;
     if (n) {
         CU(cudaMemcpyAsync(out_idx, s.d_idx, n * sizeof(uint16_t), cudaMemcpyDeviceToHost, s.stream));
         if (out_dist) CU(cudaMemcpyAsync(out_dist, s.d_dist, n, cudaMemcpyDeviceToHost, s.stream));

@@ -80,6 +80,76 @@ __attribute__((target("avx2"))) void pack_range_avx2(const uint8_t *ascii, uint6
 }
 #endif
 
+// ---- 16-byte sgdx_read records {lo, hi, nmask, xmask}: any barcode_len <= 32 ---------------------------------
+void planes_range_scalar(const uint8_t *ascii, uint64_t begin, uint64_t end, uint32_t L, sgdx_read *out) {
+    for (uint64_t r = begin; r < end; r++) {
+        const uint8_t *p = ascii + r * L;
+        sgdx_read v = {0u, 0u, 0u, 0u};
+        for (uint32_t j = 0; j < L; j++) {
+            const uint8_t c = p[j];
+            if (c == 'A' || c == 'C' || c == 'G' || c == 'T') {
+                v.lo |= (uint32_t)((c >> 1) & 1u) << j;
+                v.hi |= (uint32_t)((c >> 2) & 1u) << j;
+            } else if (c == 'N') {
+                v.nmask |= 1u << j;
+            } else {
+                v.xmask |= 1u << j;
+            }
+        }
+        out[r] = v;
+    }
+}
+
+#if defined(__x86_64__)
+__attribute__((target("avx2"))) void planes_range_avx2(const uint8_t *ascii, uint64_t begin, uint64_t end, uint32_t L,
+                                                       uint64_t total, sgdx_read *out) {
+    const uint64_t bytes = total * L;
+    uint64_t safe_end = end;
+    while (safe_end > begin && (safe_end - 1) * L + 32 > bytes) safe_end--;
+    const __m256i lut = _mm256_setr_epi8(1, 'A', 1, 'C', 'T', 1, 1, 'G', 1, 1, 1, 1, 1, 1, 1, 1,
+                                         1, 'A', 1, 'C', 'T', 1, 1, 'G', 1, 1, 1, 1, 1, 1, 1, 1);
+    const __m256i nib = _mm256_set1_epi8(0x0F), enn = _mm256_set1_epi8('N');
+    const uint32_t m = L >= 32 ? 0xFFFFFFFFu : (1u << L) - 1u;
+    for (uint64_t r = begin; r < safe_end; r++) {
+        const __m256i x = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(ascii + r * L));
+        const uint32_t b1 = (uint32_t)_mm256_movemask_epi8(_mm256_slli_epi16(x, 6));
+        const uint32_t b2 = (uint32_t)_mm256_movemask_epi8(_mm256_slli_epi16(x, 5));
+        const uint32_t ok = (uint32_t)_mm256_movemask_epi8(_mm256_cmpeq_epi8(_mm256_shuffle_epi8(lut, _mm256_and_si256(x, nib)), x));
+        const uint32_t isn = (uint32_t)_mm256_movemask_epi8(_mm256_cmpeq_epi8(x, enn));
+        sgdx_read v;
+        v.lo = b1 & ok & m;
+        v.hi = b2 & ok & m;
+        v.nmask = isn & m;
+        v.xmask = ~ok & ~isn & m;
+        out[r] = v;
+    }
+    planes_range_scalar(ascii, safe_end, end, L, out);
+}
+#endif
+
+void planes_range(const uint8_t *ascii, uint64_t begin, uint64_t end, uint32_t L, uint64_t total, sgdx_read *out) {
+#if defined(__x86_64__)
+    static const bool have_avx2 = __builtin_cpu_supports("avx2") && !getenv("SGDX_PACK_NO_AVX2");
+    if (have_avx2) return planes_range_avx2(ascii, begin, end, L, total, out);
+#endif
+    (void)total;
+    planes_range_scalar(ascii, begin, end, L, out);
+}
+
+template <typename Out, typename Fn>
+void run_threads(Fn fn, const uint8_t *ascii, uint64_t n, uint32_t L, Out *out, uint32_t threads) {
+    if (threads == 0) threads = 1;
+    const uint64_t min_per_thread = 1u << 16;  // below this a thread costs more than it saves
+    const uint64_t nt = std::min<uint64_t>(threads, (n + min_per_thread - 1) / min_per_thread);
+    if (nt <= 1) return fn(ascii, 0, n, L, n, out);
+    std::vector<std::thread> pool;
+    pool.reserve(nt - 1);
+    const uint64_t per = (n + nt - 1) / nt;
+    for (uint64_t t = 1; t < nt; t++) pool.emplace_back(fn, ascii, std::min(n, t * per), std::min(n, (t + 1) * per), L, n, out);
+    fn(ascii, 0, std::min(n, per), L, n, out);
+    for (auto &th : pool) th.join();
+}
+
 void pack_range(const uint8_t *ascii, uint64_t begin, uint64_t end, uint32_t L, uint64_t total, uint64_t *out) {
 #if defined(__x86_64__)
     static const bool have_avx2 = __builtin_cpu_supports("avx2") && !getenv("SGDX_PACK_NO_AVX2");
@@ -96,21 +166,14 @@ extern "C" int sgdx_pack_compact_host(const uint8_t *ascii, uint64_t n, uint32_t
     if (barcode_len < 1 || barcode_len > SGDX_COMPACT_MAX_LEN)
         return sgdx::fail(SGDX_EINVAL, "compact records hold 1..%u bases, barcode_len is %u", SGDX_COMPACT_MAX_LEN, barcode_len);
     if (n && (!ascii || !out)) return sgdx::fail(SGDX_EINVAL, "sgdx_pack_compact_host: null buffer");
-    if (threads == 0) threads = 1;
-    const uint64_t min_per_thread = 1u << 16;  // below this a thread costs more than it saves
-    uint64_t nt = std::min<uint64_t>(threads, (n + min_per_thread - 1) / min_per_thread);
-    if (nt <= 1) {
-        pack_range(ascii, 0, n, barcode_len, n, out);
-        return SGDX_OK;
-    }
-    std::vector<std::thread> pool;
-    pool.reserve(nt - 1);
-    const uint64_t per = (n + nt - 1) / nt;
-    for (uint64_t t = 1; t < nt; t++) {
-        const uint64_t b = std::min(n, t * per), e = std::min(n, (t + 1) * per);
-        pool.emplace_back(pack_range, ascii, b, e, barcode_len, n, out);
-    }
-    pack_range(ascii, 0, std::min(n, per), barcode_len, n, out);
-    for (auto &th : pool) th.join();
+    run_threads(pack_range, ascii, n, barcode_len, out, threads);
+    return SGDX_OK;
+}
+
+extern "C" int sgdx_pack_host(const uint8_t *ascii, uint64_t n, uint32_t barcode_len, sgdx_read *out, uint32_t threads) {
+    if (barcode_len < 1 || barcode_len > SGDX_MAX_BARCODE_LEN)
+        return sgdx::fail(SGDX_EINVAL, "barcode_len %u outside 1..%u", barcode_len, SGDX_MAX_BARCODE_LEN);
+    if (n && (!ascii || !out)) return sgdx::fail(SGDX_EINVAL, "sgdx_pack_host: null buffer");
+    run_threads(planes_range, ascii, n, barcode_len, out, threads);
     return SGDX_OK;
 }

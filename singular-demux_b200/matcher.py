@@ -109,6 +109,15 @@ def pack_compact_host(barcodes: np.ndarray, threads: int = 1, out: Optional[np.n
     return rec
 
 
+def pack_host(barcodes: np.ndarray, threads: int = 1) -> np.ndarray:
+    """sgdx_pack_host: (n, L) ASCII barcodes, L <= 32 -> (n, 4) uint32 sgdx_read records {lo, hi, nmask, xmask}."""
+    arr = np.ascontiguousarray(barcodes, dtype=np.uint8)
+    n, L = arr.shape
+    rec = np.empty((n, 4), dtype=np.uint32)
+    check(lib().sgdx_pack_host(arr.ctypes.data, n, L, rec.ctypes.data, threads), "sgdx_pack_host")
+    return rec
+
+
 class GpuMatcher:
     """A matcher bound to one CUDA device through sgdx_create (owns an sgdx handle)."""
 
@@ -209,6 +218,17 @@ class GpuMatcher:
         idx = np.empty(rec.size, dtype=np.uint16)
         dist = np.empty(rec.size, dtype=np.uint8)
         self.submit_compact_ptr(rec.ctypes.data, rec.size, idx.ctypes.data, dist.ctypes.data, slot)
+        self.sync(slot)
+        return idx, dist
+
+    def find_batch_packed(self, barcodes, slot: int = 0, threads: int = 1) -> Tuple[np.ndarray, np.ndarray]:
+        """find_batch through 16-byte records packed on the host (any barcode_len): sgdx_match_packed_batch."""
+        rec = pack_host(as_barcode_array(barcodes, self.barcode_len), threads)
+        n = rec.shape[0]
+        idx = np.empty(n, dtype=np.uint16)
+        dist = np.empty(n, dtype=np.uint8)
+        check(lib().sgdx_match_packed_batch(self._h, slot, rec.ctypes.data, n, idx.ctypes.data, dist.ctypes.data),
+              "sgdx_match_packed_batch")
         self.sync(slot)
         return idx, dist
 

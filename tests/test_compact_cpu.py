@@ -95,3 +95,28 @@ def test_short_seed_rule_holds_in_the_oracle(cfg_name, M, D):
         got = orc.COracle(cfg, [bytes(t) for t in table], force_closed_form=True).run(reads, threads=2, use_cache=False)
         assert np.array_equal(got["idx"], want_idx)
         assert np.array_equal(got["dist"], want_dist)
+
+
+@pytest.mark.parametrize("L", [1, 5, 8, 16, 20, 21, 24, 31, 32])
+def test_host_packer_of_16_byte_records_equals_the_format_definition(L):
+    """sgdx_pack_host (SURVEY Appendix B's `sgdx_pack`): {lo, hi, nmask, xmask} per read, any length up to 32."""
+    rng = np.random.default_rng(2000 + L)
+    n = 70_001
+    arr = ALPHABET[rng.integers(0, ALPHABET.size, size=(n, L))]
+    want = orc.packed_records(arr)
+    assert np.array_equal(sg.pack_host(arr), want)
+    assert np.array_equal(sg.pack_host(arr, threads=3), want)
+    assert sg.pack_host(arr[:0]).shape == (0, 4)
+
+
+def test_16_byte_packer_every_byte_value_and_argument_checks():
+    L = 32
+    arr = np.full((256 * L, L), ord("C"), dtype=np.uint8)
+    for pos in range(L):
+        arr[pos * 256:(pos + 1) * 256, pos] = np.arange(256, dtype=np.uint8)
+    assert np.array_equal(sg.pack_host(arr), orc.packed_records(arr))
+    lib = sg.lib()
+    out = (C.c_uint32 * 16)()
+    assert lib.sgdx_pack_host(b"A" * 132, 4, 33, out, 1) == -1 and b"barcode_len" in lib.sgdx_last_error()
+    assert lib.sgdx_pack_host(None, 4, 20, out, 1) == -1
+
