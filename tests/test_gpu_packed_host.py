@@ -1,8 +1,6 @@
 """GPU parity of the host-packed 16-byte record path (sgdx_pack_host + sgdx_match_packed_batch: SURVEY Appendix B's
-`sgdx_pack` / packed `sgdx_match_batch`) against the CPU oracle.  Written after the round's GPU budget was spent:
-this file has not had a B200 run yet, which is why it sorts after the validated suites (`pytest -x` reaches it last).
-Its parts are validated separately: the packer on CPU (tests/test_compact_cpu.py), the packed kernels through
-sgdx_match_packed_device (tests/test_gpu_parity.py::test_device_resident_and_packed_paths_equal_host_path)."""
+`sgdx_pack` / packed `sgdx_match_batch`) against the CPU oracle: index, distance, per-sample counters, hop map, for six
+table shapes (8 to 32 bases) x both rule sets x three rule settings."""
 import numpy as np
 import pytest
 
