@@ -1,0 +1,36 @@
+// Host packers (csrc/sgdx_hostpack.cpp) under AddressSanitizer + UBSan: exact-size heap buffers for every barcode
+// length and a range of batch sizes, so any byte the 32-byte vector loads read past the end of the input is flagged;
+// also checks that the 8-byte and the 16-byte record of every read agree.  Built and run by
+// tests/test_compact_cpu.py::test_host_packers_are_clean_under_asan (no GPU, no libsgdx.so: the source is compiled in).
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+#include "../../include/sgdx.h"
+namespace sgdx { int fail(int code, const char *, ...) { return code; } }
+int main() {
+    const char letters[] = "ACGTNacx";
+    for (uint32_t L = 1; L <= 32; L++)
+        for (uint64_t n : {0ull, 1ull, 2ull, 3ull, 7ull, 64ull, 1000ull, 70000ull, 200001ull}) {
+            // exact-size heap buffers: ASAN flags any byte read past the end
+            uint8_t *in = (uint8_t *)malloc(n * L ? n * L : 1);
+            for (uint64_t i = 0; i < n * L; i++) in[i] = letters[(i * 2654435761u >> 7) % 8];
+            sgdx_read *o16 = (sgdx_read *)malloc(n ? n * sizeof(sgdx_read) : 1);
+            if (sgdx_pack_host(in, n, L, o16, 3)) return 1;
+            if (L <= 21) {
+                uint64_t *o8 = (uint64_t *)malloc(n ? n * 8 : 1);
+                if (sgdx_pack_compact_host(in, n, L, o8, 3)) return 2;
+                for (uint64_t r = 0; r < n; r++) {  // the two formats agree
+                    uint64_t rec = o8[r];
+                    uint32_t lo = rec & 0x1FFFFF, hi = (rec >> 21) & 0x1FFFFF, inv = (rec >> 42) & 0x1FFFFF;
+                    if ((lo & ~inv) != o16[r].lo || hi != o16[r].hi || (inv & ~lo) != o16[r].nmask || (inv & lo) != o16[r].xmask) return 3;
+                }
+                free(o8);
+            }
+            free(o16);
+            free(in);
+        }
+    puts("ok");
+    return 0;
+}

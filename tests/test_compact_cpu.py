@@ -120,3 +120,25 @@ def test_16_byte_packer_every_byte_value_and_argument_checks():
     assert lib.sgdx_pack_host(b"A" * 132, 4, 33, out, 1) == -1 and b"barcode_len" in lib.sgdx_last_error()
     assert lib.sgdx_pack_host(None, 4, 20, out, 1) == -1
 
+
+def test_host_packers_are_clean_under_asan(tmp_path):
+    """tests/cpp/test_hostpack_asan.cpp: both packers, AVX2 and scalar, every length, exact-size buffers."""
+    import os
+    import shutil
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cxx = shutil.which("g++")
+    if not cxx:
+        pytest.skip("no g++")
+    exe = str(tmp_path / "hostpack_asan")
+    build = subprocess.run([cxx, "-O1", "-g", "-std=c++17", "-fsanitize=address,undefined", "-fno-omit-frame-pointer", "-o", exe,
+                            os.path.join(root, "tests", "cpp", "test_hostpack_asan.cpp"),
+                            os.path.join(root, "singular-demux_b200", "csrc", "sgdx_hostpack.cpp"), "-lpthread"],
+                           capture_output=True, text=True)
+    if build.returncode != 0 and "sanitize" in build.stderr + build.stdout:
+        pytest.skip("this g++ has no sanitizer runtime")
+    assert build.returncode == 0, build.stderr
+    for env in ({}, {"SGDX_PACK_NO_AVX2": "1"}):
+        r = subprocess.run([exe], capture_output=True, text=True, env={**os.environ, **env}, timeout=300)
+        assert r.returncode == 0 and r.stdout.strip() == "ok", r.stdout + r.stderr
+
