@@ -164,6 +164,9 @@ const char *sgdx_kernel_name(const sgdx_handle *h);
 #define SGDX_PATH_COMPACT 16u     /* sgdx_match_compact serves compact records (exact shortcut valid, barcode_len <= 21) */
 #define SGDX_PATH_SHORT_SEED 32u  /* ... and its seed search uses max_mismatches + 1 chunks (min pairwise distance >
                                      2 * max_mismatches + min_delta; SGDX_NO_SHORT_SEED=1 at sgdx_create turns it off) */
+#define SGDX_PATH_PERFECT_HASH 64u /* compact records run sgdx_match_ph: every A/C/G/T string within max_mismatches of a
+                                     barcode sits in a perfect hash with its precomputed verdict (barcode_len <= 21 and at
+                                     most ~28 000 such strings; SGDX_DISABLE_PH=1 at sgdx_create turns it off) */
 uint32_t sgdx_path_flags(const sgdx_handle *h);
 /* Number of kernel launches issued through this handle so far. */
 uint64_t sgdx_launch_count(const sgdx_handle *h);

@@ -35,6 +35,17 @@ int sgdx_synth_reads_host(const sgdx_synth_params *p, const uint8_t *table, uint
 int sgdx_synth_reads_device(const sgdx_synth_params *p, const uint8_t *d_table, uint64_t first, uint64_t n,
                             uint8_t *d_out, void *cuda_stream);
 
+
+/* Test support for the perfect-hash kernel (SGDX_PATH_PERFECT_HASH): builds that kernel's tables for `cfg` on the
+ * host -- the same code sgdx_create runs -- and answers n compact records with the kernel's fast-path arithmetic,
+ * so CPU tests can hold the tables against the oracle.  Records with invalid positions (general path on the
+ * device) come back as idx 0xFFFF / dist 0xFE.  info[6] (nullable) = {tables exist, number of keys, bucket bits,
+ * slot bits, single-invalid-base shortcut valid, min pairwise table distance}.  It is not an assignment path: it
+ * ignores no-calls, the hop checker and the counters. */
+struct sgdx_config;
+int sgdx_ph_probe_host(const struct sgdx_config *cfg, const uint8_t *barcodes_ascii, const uint64_t *records,
+                       uint64_t n, uint16_t *out_idx, uint8_t *out_dist, uint32_t *info);
+
 #ifdef __cplusplus
 }
 #endif

@@ -9,12 +9,13 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsgdx.so")
+LIB_PATH = os.environ.get("SGDX_LIB") or os.path.join(_HERE, "libsgdx.so")  # SGDX_LIB: experiment builds (tools/)
 
 MATCHER_AUTO, MATCHER_CACHED_HAMMING, MATCHER_PRECOMPUTE = 0, 1, 2
 KERNEL_AUTO, KERNEL_DIRECT, KERNEL_SEEDED = 0, 1, 2
 NO_DIST = 0xFF
 PATH_SEED_INDEX, PATH_EXACT, PATH_NEIGHBOURS, PATH_HOP_DIRECT, PATH_COMPACT, PATH_SHORT_SEED = 1, 2, 4, 8, 16, 32
+PATH_PERFECT_HASH = 64
 COMPACT_MAX_LEN = 21
 MAX_BARCODE_LEN = 32
 MAX_SAMPLES = 8192
@@ -81,7 +82,7 @@ SYMBOLS = [
     "sgdx_unmatched_enable", "sgdx_unmatched_info_get", "sgdx_unmatched_export", "sgdx_unmatched_top",
     "sgdx_unmatched_downsize", "sgdx_extract_device", "sgdx_match_segments_device", "sgdx_qual_counts_device",
     "sgdx_base_qual_counters", "sgdx_route_device", "sgdx_demultiplex_device",
-    "sgdx_synth_table", "sgdx_synth_reads_host", "sgdx_synth_reads_device",
+    "sgdx_synth_table", "sgdx_synth_reads_host", "sgdx_synth_reads_device", "sgdx_ph_probe_host",
 ]
 
 _lib = None
@@ -150,6 +151,7 @@ def lib() -> C.CDLL:
     L.sgdx_synth_table.argtypes = [u64, u32, u32, u32, u32, vp]
     L.sgdx_synth_reads_host.argtypes = [C.POINTER(SynthParams), vp, u64, u64, vp, i32]
     L.sgdx_synth_reads_device.argtypes = [C.POINTER(SynthParams), vp, u64, u64, vp, vp]
+    L.sgdx_ph_probe_host.argtypes = [C.POINTER(Config), vp, vp, u64, vp, vp, vp]
     for name in SYMBOLS:
         fn = getattr(L, name)
         if fn.restype is C.c_int and name not in ("sgdx_last_error", "sgdx_version"):

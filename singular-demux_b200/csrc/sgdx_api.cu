@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "sgdx_handle.h"
+#include "sgdx_phbuild.h"
 
 using namespace sgdx;
 
@@ -329,6 +330,36 @@ static int build_compact_table(sgdx_handle *h, const std::vector<uint2> &table) 
     return SGDX_OK;
 }
 
+
+// Perfect hash of the match neighbourhood for sgdx_match_ph (sgdx_ph.cu): built on the host by sgdx_phbuild.cpp
+static int build_ph_table(sgdx_handle *h, const std::vector<uint2> &table) {
+    const DevParams &p = h->base;
+    h->ph = PhParams{};
+    if (getenv("SGDX_DISABLE_PH")) return SGDX_OK;  // test hook: the older compact kernels
+    std::vector<PhPlanes> planes(p.S);
+    for (uint32_t s = 0; s < p.S; s++) planes[s] = PhPlanes{table[s].x, table[s].y};
+    const PhRules rules{p.S, p.L, p.M, p.delta, p.pc_limit, h->mode};
+    PhTables t;
+    if (!ph_build(rules, planes, 227u * 1024u, ph_smem_bytes, &t)) return SGDX_OK;
+    CU(cudaMalloc(&h->d_ph_disp, t.disp.size() * sizeof(uint16_t)));
+    CU(cudaMalloc(&h->d_ph_slots, t.slots.size() * sizeof(uint16_t)));
+    CU(cudaMemcpy(h->d_ph_disp, t.disp.data(), t.disp.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(h->d_ph_slots, t.slots.data(), t.slots.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    h->ph.disp = h->d_ph_disp;
+    h->ph.slots = h->d_ph_slots;
+    h->ph.bshift = t.bshift;
+    h->ph.sshift = t.sshift;
+    h->ph.k0 = t.k0;
+    h->ph.k1 = t.k1;
+    h->ph.k2 = t.k2;
+    h->ph.nm0 = t.nm0;
+    h->ph.nm1 = t.nm1;
+    h->ph.lmask = t.lmask;
+    h->ph.single_ok = t.single_ok;
+    h->ph_keys = t.nkeys;
+    return SGDX_OK;
+}
+
 // everything sgdx_create does once the arguments are validated; on failure the caller destroys the handle
 static int fill_handle(sgdx_handle *h, const sgdx_config *cfg, const uint8_t *barcodes) {
     const uint32_t S = cfg->num_samples, L = cfg->barcode_len;
@@ -443,6 +474,7 @@ static int fill_handle(sgdx_handle *h, const sgdx_config *cfg, const uint8_t *ba
             }
         h->cfg.kernel = h->seeded ? SGDX_KERNEL_SEEDED : SGDX_KERNEL_DIRECT;
         if (int rc = build_compact_table(h, table)) return rc;
+        if (int rc = build_ph_table(h, table)) return rc;
     }
 
     h->slots.resize(h->cfg.slots);
@@ -520,6 +552,8 @@ extern "C" void sgdx_destroy(sgdx_handle *h) {
     cudaFree(h->d_cx_slots);
     cudaFree(h->d_cx_short_hdr);
     cudaFree(h->d_cx_short_ids);
+    cudaFree(h->d_ph_disp);
+    cudaFree(h->d_ph_slots);
     cudaFree(h->d_hash1);
     cudaFree(h->d_hash2);
     cudaFree(h->d_hop_lut1);
@@ -662,9 +696,25 @@ static int run_compact(sgdx_handle *h, Slot &s, const uint64_t *d_records, uint6
     if (reinterpret_cast<uintptr_t>(d_records) & 7u) return fail(SGDX_EINVAL, "compact records must be 8-byte aligned");
     if (h->unm.on && n)
         return fail(SGDX_ESTATE, "unmatched collection needs ASCII input (compact records do not keep foreign bytes)");
+    if (h->ph.slots) {  // perfect hash of the match neighbourhood: sgdx_match_ph
+        DevParams p = h->base;
+        p.n = n;
+        p.out_idx = d_idx;
+        p.out_dist = d_dist;
+        PhParams c = h->ph;
+        c.reads = d_records;
+        c.vec = ((reinterpret_cast<uintptr_t>(d_records) & 31u) == 0u && (reinterpret_cast<uintptr_t>(d_idx) & 7u) == 0u &&
+                 (reinterpret_cast<uintptr_t>(d_dist) & 3u) == 0u) ? 1u : 0u;
+        CU(cudaEventRecord(s.e0, s.stream));
+        CU(launch_ph(p, c, h->mode, h->sms, s.stream));
+        if (n) h->launches.fetch_add(1);
+        CU(cudaEventRecord(s.e1, s.stream));
+        s.timed = true;
+        return SGDX_OK;
+    }
     if (!h->cx.slots) {  // table without the exact-match shortcut: expand to 16-byte records, general kernels
         if (int rc = ensure_packed_scratch(s, n)) return rc;
-        CU(launch_expand_compact(d_records, n, s.d_cexp, h->sms, s.stream));
+        CU(launch_expand_compact(d_records, n, h->cfg.barcode_len, s.d_cexp, h->sms, s.stream));
         if (n) h->launches.fetch_add(1);
         return run_kernels(h, s, nullptr, s.d_cexp, n, d_idx, d_dist);
     }
@@ -772,7 +822,8 @@ extern "C" uint32_t sgdx_path_flags(const sgdx_handle *h) {
     const DevParams &p = h->base;
     return (h->seeded ? SGDX_PATH_SEED_INDEX : 0u) | (h->seeded && p.ex_on ? SGDX_PATH_EXACT : 0u) |
            (h->seeded && p.ex_on && p.nb_on ? SGDX_PATH_NEIGHBOURS : 0u) | (p.hop_direct ? SGDX_PATH_HOP_DIRECT : 0u) |
-           (h->cx.slots ? SGDX_PATH_COMPACT : 0u) | (h->cx.short_C ? SGDX_PATH_SHORT_SEED : 0u);
+           (h->cx.slots ? SGDX_PATH_COMPACT : 0u) | (h->cx.short_C ? SGDX_PATH_SHORT_SEED : 0u) |
+           (h->ph.slots ? SGDX_PATH_PERFECT_HASH : 0u);
 }
 
 extern "C" uint64_t sgdx_launch_count(const sgdx_handle *h) { return h ? h->launches.load() : 0; }

@@ -27,8 +27,6 @@ namespace sgdx {
 
 constexpr uint32_t kCompactThreads = 512;
 constexpr uint32_t kCompactReadsPerThread = 4;
-constexpr uint32_t kCompactField = 21;
-constexpr uint32_t kCompactMask = (1u << kCompactField) - 1u;
 
 struct CompactSmem {
     uint2 *table;     // [S] barcode planes
@@ -72,24 +70,6 @@ size_t compact_smem_bytes(const DevParams &p, uint32_t bits, uint32_t shdr_total
                          nullptr);
 }
 
-__device__ __forceinline__ Rd rd_of_compact(uint64_t rec) {
-    const uint32_t lo = (uint32_t)rec & kCompactMask;
-    const uint32_t hi = (uint32_t)(rec >> kCompactField) & kCompactMask;
-    const uint32_t inv = (uint32_t)(rec >> (2u * kCompactField)) & kCompactMask;
-    Rd rd;
-    rd.nmask = inv & ~lo;
-    rd.xmask = inv & lo;
-    rd.lo = lo & ~inv;
-    rd.hi = hi & ~inv;
-    return rd;
-}
-
-__device__ __forceinline__ uint64_t compact_of_rd(const Rd &rd) {
-    const uint32_t inv = rd.nmask | rd.xmask;
-    return (uint64_t)((rd.lo & ~inv) | rd.xmask) | ((uint64_t)(rd.hi & ~inv) << kCompactField) |
-           ((uint64_t)inv << (2u * kCompactField));
-}
-
 template <uint32_t MODE>
 __global__ void __launch_bounds__(kCompactThreads, 3) sgdx_match_compact(const DevParams p, const CompactParams c) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -115,6 +95,7 @@ __global__ void __launch_bounds__(kCompactThreads, 3) sgdx_match_compact(const D
     __syncthreads();
 
     const uint32_t shift = 32u - c.bits;
+    const uint32_t lmask = (1u << p.L) - 1u;  // barcode_len <= 21; stray bits above it are ignored
     uint32_t n1 = 0, n3 = 0;  // queue fills, tracked identically by every thread
 
     // queue entries number the block's reads: iteration * (T*R) + offset inside the iteration's tile
@@ -143,7 +124,7 @@ __global__ void __launch_bounds__(kCompactThreads, 3) sgdx_match_compact(const D
         if (valid) {
             e = sm.q3[n3 - count + threadIdx.x];
             r = read_of(e);
-            rd = rd_of_compact(__ldg(c.reads + r));
+            rd = rd_of_compact(__ldg(c.reads + r), lmask);
             if (!cannot_match<MODE>(p, rd))
                 scan = !seed_search<MODE, true>(p, sm.hdr, sm.ids, sm.table, rd, best, nxt);
         }
@@ -155,7 +136,7 @@ __global__ void __launch_bounds__(kCompactThreads, 3) sgdx_match_compact(const D
         if (nscan) {
             for (uint32_t q = warp; q < nscan; q += nwarps) {  // one warp per read, all samples
                 const uint64_t qrid = read_of(sm.cq[q]);
-                const Rd qrd = rd_of_compact(__ldg(c.reads + qrid));  // same address in every lane
+                const Rd qrd = rd_of_compact(__ldg(c.reads + qrid), lmask);  // same address in every lane
                 Verdict qv = warp_scan<MODE>(p, sm.table, qrd, lane);
                 if (lane == 0) emit_single(p, qrid, qrd, qv, sm.hist);
             }
@@ -174,12 +155,12 @@ __global__ void __launch_bounds__(kCompactThreads, 3) sgdx_match_compact(const D
             const uint32_t e = sm.q1[n1 - count + threadIdx.x];
             r = read_of(e);
             const uint64_t rec = __ldg(c.reads + r);
-            if ((rec >> (2u * kCompactField)) != 0ull) {
+            if (((rec >> (2u * kCompactField)) & lmask) != 0ull) {
                 sm.q3[n3 + push_slot()] = e;
             } else if (c.short_C) {
                 // dmin > 2M + delta: at most one sample is within M of this read, and then every other one is
                 // further than M + delta away -- the first candidate with d <= M is the verdict, nxt stays "none"
-                rd = rd_of_compact(rec);
+                rd = rd_of_compact(rec, lmask);
                 for (uint32_t ch = 0; ch < c.short_C; ch++) {
                     const uint32_t desc = sm.sdesc[ch];
                     const uint32_t pos = desc & 0xFFu, w = (desc >> 8) & 0xFFu, off = desc >> 16;
@@ -196,7 +177,7 @@ __global__ void __launch_bounds__(kCompactThreads, 3) sgdx_match_compact(const D
                 }
                 done = true;
             } else {  // an all-A/C/G/T read passes the gate and the cannot-match test
-                rd = rd_of_compact(rec);
+                rd = rd_of_compact(rec, lmask);
                 seed_search<MODE, false>(p, sm.hdr, sm.ids, sm.table, rd, best, nxt);
                 done = true;
             }
@@ -287,10 +268,10 @@ __global__ void __launch_bounds__(256) sgdx_pack_compact(const uint8_t *__restri
 
 // compact -> 16-byte sgdx_read records, for tables the fast kernel does not cover (no seed index, or
 // min pairwise distance <= min_delta): those go through the packed form of the general kernels
-__global__ void __launch_bounds__(256) sgdx_expand_compact(const uint64_t *__restrict__ in, uint64_t n,
+__global__ void __launch_bounds__(256) sgdx_expand_compact(const uint64_t *__restrict__ in, uint64_t n, uint32_t lmask,
                                                            uint4 *__restrict__ out) {
     for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (uint64_t)gridDim.x * blockDim.x) {
-        const Rd rd = rd_of_compact(__ldg(in + r));
+        const Rd rd = rd_of_compact(__ldg(in + r), lmask);
         out[r] = make_uint4(rd.lo, rd.hi, rd.nmask, rd.xmask);
     }
 }
@@ -315,9 +296,9 @@ cudaError_t launch_pack_compact(const uint8_t *reads, uint64_t n, uint32_t L, ui
     return cudaGetLastError();
 }
 
-cudaError_t launch_expand_compact(const uint64_t *in, uint64_t n, uint4 *out, int sms, cudaStream_t stream) {
+cudaError_t launch_expand_compact(const uint64_t *in, uint64_t n, uint32_t L, uint4 *out, int sms, cudaStream_t stream) {
     if (n == 0) return cudaSuccess;
-    sgdx_expand_compact<<<persistent_grid(n, 256, sms, 8), 256, 0, stream>>>(in, n, out);
+    sgdx_expand_compact<<<persistent_grid(n, 256, sms, 8), 256, 0, stream>>>(in, n, (1u << L) - 1u, out);
     return cudaGetLastError();
 }
 

@@ -85,6 +85,9 @@ struct sgdx_handle {
     uint64_t *d_cx_slots = nullptr;  // compact-record front end (sgdx_compact.cu); cx.slots == nullptr: not available
     sgdx::CompactParams cx{};
     uint16_t *d_cx_short_hdr = nullptr, *d_cx_short_ids = nullptr;
+    uint16_t *d_ph_disp = nullptr, *d_ph_slots = nullptr;  // perfect-hash kernel (sgdx_ph.cu); ph.slots == nullptr: not available
+    sgdx::PhParams ph{};
+    uint32_t ph_keys = 0;
     sgdx::HopSlot *d_hash1 = nullptr, *d_hash2 = nullptr;
     uint16_t *d_hop_lut1 = nullptr, *d_hop_lut2 = nullptr;
     unsigned long long *d_hop_fwd = nullptr, *d_hop_rev = nullptr;

@@ -18,6 +18,8 @@ cudaError_t launch_pack(const uint8_t *reads, uint64_t n, uint32_t L, uint4 *out
 // compact records (sgdx_compact.cu): one 64-bit word per read of at most kCompactMaxLen bases --
 // lo plane | hi plane << 21 | invalid plane << 42 (at an invalid position lo = 0: 'N', lo = 1: any other byte)
 constexpr uint32_t kCompactMaxLen = 21;
+constexpr uint32_t kCompactField = 21;  // bits per plane
+constexpr uint32_t kCompactMask = (1u << kCompactField) - 1u;
 struct CompactParams {
     const uint64_t *reads;  // n records
     const uint64_t *slots;  // [1 << bits] cuckoo table of the expected barcodes: record | (sample + 1) << 42, 0 = empty
@@ -38,7 +40,33 @@ inline uint64_t compact_record(uint32_t lo, uint32_t hi) { return (uint64_t)lo |
 size_t compact_smem_bytes(const DevParams &p, uint32_t bits, uint32_t short_hdr_total = 0, uint32_t short_ids_total = 0);
 cudaError_t launch_compact(const DevParams &p, const CompactParams &c, uint32_t mode, int sms, cudaStream_t stream);
 cudaError_t launch_pack_compact(const uint8_t *reads, uint64_t n, uint32_t L, uint64_t *out, int sms, cudaStream_t stream);
-cudaError_t launch_expand_compact(const uint64_t *in, uint64_t n, uint4 *out, int sms, cudaStream_t stream);
+cudaError_t launch_expand_compact(const uint64_t *in, uint64_t n, uint32_t L, uint4 *out, int sms, cudaStream_t stream);
+
+// Perfect-hash kernel for compact records (sgdx_ph.cu).  Key set K = every A/C/G/T string within max_mismatches
+// substitutions of an expected barcode.  For a read without invalid positions the verdict is a function of the
+// string alone, so sgdx_create computes it once per key (full scan, both rule sets) and stores the winning sample
+// (or "none") in a two-level perfect hash over K:
+//     h    = hi32(w0 * k0) + w0 * k1 + w1 * k2          (w0, w1 = the record's 32-bit words)
+//     slot = (h * disp[h >> bshift]) >> sshift           (disp: one odd 16-bit multiplier per bucket)
+//     e    = slots[slot]                                 (sample index; S = none)
+// The entry carries no tag: the kernel verifies by distance.  A read inside K finds its own entry, whose sample is
+// its best sample at distance <= max_mismatches (or S: planes[S] is a dummy that is > 10 away from everything); a
+// read outside K finds some other key's entry, and its distance to that sample is > max_mismatches because it is
+// further than that from every sample.  Reads with invalid positions (or stray bits) take the general path.
+struct PhParams {
+    const uint64_t *reads;
+    const uint16_t *disp;   // [1 << (32 - bshift)]
+    const uint16_t *slots;  // [1 << (32 - sshift)]
+    uint32_t bshift, sshift;
+    uint32_t k0, k1, k2;
+    uint32_t nm0, nm1;      // bits of w0 / w1 that a record made of barcode_len A/C/G/T bases never has set
+    uint32_t lmask;         // (1 << barcode_len) - 1
+    uint32_t single_ok;     // min pairwise table distance > 2M + delta + 1: a read with ONE invalid base is decided by
+                            // the unique sample within M over its valid positions, found by probing its 4 completions
+    uint32_t vec;           // per launch: 256-bit record loads / packed result stores (all three buffers aligned)
+};
+size_t ph_smem_bytes(uint32_t S, uint32_t bbits, uint32_t sbits);
+cudaError_t launch_ph(const DevParams &p, const PhParams &c, uint32_t mode, int sms, cudaStream_t stream);
 
 // integer-pipe micro-benchmark (sgdx_microbench.cu)
 cudaError_t measure_int_peak(int sms, double *popc_per_s, double *lop3_per_s);

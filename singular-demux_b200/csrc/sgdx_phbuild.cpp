@@ -1,0 +1,213 @@
+// sgdx_phbuild.cpp -- see sgdx_phbuild.h.  Key set: every A/C/G/T string within max_mismatches substitutions of an
+// expected barcode.  Each key's verdict is computed here exactly as the kernels compute it per read (score +
+// apply_rules of sgdx_device.cuh for a read without invalid positions): best / second-best (distance << 16 | sample)
+// keys over the whole table, then matcher.rs:295-299 or the PreCompute visibility rule.
+#include "sgdx_phbuild.h"
+
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+
+#include "../../include/sgdx.h"
+#include "../../include/sgdx_synth.h"
+
+namespace sgdx {
+
+namespace {
+constexpr uint32_t kField = 21, kFieldMask = (1u << kField) - 1u, kMaxSlotBits = 15, kInf = 0xFFFFFFFFu;
+
+inline uint64_t record_of(uint32_t lo, uint32_t hi) { return (uint64_t)lo | ((uint64_t)hi << kField); }
+
+uint32_t verdict(const PhRules &r, const std::vector<PhPlanes> &table, uint32_t lo, uint32_t hi) {
+    uint32_t best = kInf, nxt = kInf;
+    for (uint32_t s = 0; s < r.S; s++) {
+        const uint32_t d = (uint32_t)__builtin_popcount((lo ^ table[s].lo) | (hi ^ table[s].hi));
+        const uint32_t key = (d << 16) | s;
+        nxt = std::min(nxt, std::max(best, key));
+        best = std::min(best, key);
+    }
+    const uint32_t bd = best >> 16, nd = nxt >> 16;  // nd = 0xFFFF without a competitor
+    bool ok;
+    if (r.mode == 0u) ok = best != kInf && bd <= r.M && (nd - bd) > r.delta;
+    else ok = best != kInf && bd <= r.M && !(nd <= bd + r.delta && nd <= r.pc_limit);
+    return ok ? (best & 0xFFFFu) : r.S;
+}
+}  // namespace
+
+bool ph_build(const PhRules &r, const std::vector<PhPlanes> &table, size_t smem_limit,
+              size_t (*smem_bytes)(uint32_t, uint32_t, uint32_t), PhTables *out) {
+    const uint32_t S = r.S, L = r.L, M = r.M;
+    if (L > kField || M > 10u || S >= 0xFFFFu) return false;
+    {   // S * sum_k C(L,k) 3^k keys before deduplication
+        double per = 0.0, term = 1.0;
+        for (uint32_t k = 0; k <= M && k <= L; k++) {
+            per += term;
+            term = term * 3.0 * (double)(L - k) / (double)(k + 1u);
+        }
+        if (per * S > 3.0 * (double)(1u << kMaxSlotBits)) return false;
+    }
+    // strings at exact distance k from sample s, each once (substituted positions ascending)
+    struct Node {
+        uint32_t lo, hi, next_pos;
+    };
+    std::vector<uint64_t> keys;
+    std::vector<Node> frontier, grown;
+    for (uint32_t s = 0; s < S; s++) {
+        frontier.assign(1, Node{table[s].lo, table[s].hi, 0u});
+        keys.push_back(record_of(table[s].lo, table[s].hi));
+        for (uint32_t k = 1; k <= M && k <= L; k++) {
+            grown.clear();
+            for (const Node &nd : frontier)
+                for (uint32_t j = nd.next_pos; j < L; j++) {
+                    const uint32_t cur = ((nd.lo >> j) & 1u) | (((nd.hi >> j) & 1u) << 1);
+                    for (uint32_t b = 0; b < 4; b++) {
+                        if (b == cur) continue;
+                        const uint32_t lo = (nd.lo & ~(1u << j)) | ((b & 1u) << j);
+                        const uint32_t hi = (nd.hi & ~(1u << j)) | ((b >> 1) << j);
+                        grown.push_back(Node{lo, hi, j + 1u});
+                        keys.push_back(record_of(lo, hi));
+                    }
+                }
+            frontier.swap(grown);
+        }
+    }
+    std::sort(keys.begin(), keys.end());
+    keys.erase(std::unique(keys.begin(), keys.end()), keys.end());
+    const size_t nk = keys.size();
+    uint32_t sbits = 6;
+    while ((double)nk > 0.86 * (double)(1u << sbits)) sbits++;
+    if (sbits > kMaxSlotBits) return false;
+    uint32_t bbits = 4;
+    while (((size_t)3 << bbits) < nk) bbits++;  // <= 3 keys per bucket on average
+    std::vector<uint16_t> entry(nk);
+    for (size_t i = 0; i < nk; i++)
+        entry[i] = (uint16_t)verdict(r, table, (uint32_t)keys[i] & kFieldMask, (uint32_t)(keys[i] >> kField) & kFieldMask);
+
+    static const uint32_t KS[6][3] = {{0x9E3779B1u, 0x85EBCA77u, 0xC2B2AE3Du}, {0x27D4EB2Fu, 0x165667B1u, 0xD3A2646Du},
+                                      {0xFD7046C5u, 0xB55A4F09u, 0x2545F491u}, {0x9E6C63D1u, 0x7FEB352Du, 0x846CA68Bu},
+                                      {0xCC9E2D51u, 0x1B873593u, 0xE6546B65u}, {0x85EBCA6Bu, 0xC2B2AE35u, 0x9E3779B9u}};
+    PhTables t;
+    bool built = false;
+    for (uint32_t attempt = 0; attempt < 12 && !built; attempt++) {
+        const uint32_t *K = KS[attempt % 6u];
+        if (attempt == 6u && ++sbits > kMaxSlotBits) break;  // second round: a larger table
+        if (smem_bytes && smem_bytes(S, bbits, sbits) > smem_limit) return false;
+        const uint32_t nb = 1u << bbits, nslots = 1u << sbits, bshift = 32u - bbits, sshift = 32u - sbits;
+        std::vector<uint32_t> hv(nk);
+        std::vector<std::vector<uint32_t>> buckets(nb);
+        for (size_t i = 0; i < nk; i++) {
+            const uint32_t w0 = (uint32_t)keys[i], w1 = (uint32_t)(keys[i] >> 32);
+            hv[i] = (uint32_t)(((uint64_t)w0 * K[0]) >> 32) + w0 * K[1] + w1 * K[2];
+            buckets[hv[i] >> bshift].push_back((uint32_t)i);
+        }
+        std::vector<uint32_t> order(nb);
+        for (uint32_t b = 0; b < nb; b++) order[b] = b;
+        std::stable_sort(order.begin(), order.end(),
+                         [&](uint32_t a, uint32_t b) { return buckets[a].size() > buckets[b].size(); });
+        t.disp.assign(nb, 1u);
+        t.slots.assign(nslots, (uint16_t)S);
+        std::vector<uint8_t> used(nslots, 0u);
+        std::vector<uint32_t> pos;
+        bool ok = true;
+        for (uint32_t oi = 0; oi < nb && ok; oi++) {  // largest buckets first, while the table is still empty
+            const std::vector<uint32_t> &bk = buckets[order[oi]];
+            if (bk.empty()) break;
+            bool placed = false;
+            for (uint32_t mul = 1u; mul < 65536u && !placed; mul += 2u) {
+                pos.clear();
+                bool clash = false;
+                for (uint32_t i : bk) {
+                    const uint32_t q = (hv[i] * mul) >> sshift;
+                    if (used[q] || std::find(pos.begin(), pos.end(), q) != pos.end()) {
+                        clash = true;
+                        break;
+                    }
+                    pos.push_back(q);
+                }
+                if (clash) continue;
+                for (size_t k = 0; k < bk.size(); k++) {
+                    used[pos[k]] = 1u;
+                    t.slots[pos[k]] = entry[bk[k]];
+                }
+                t.disp[order[oi]] = (uint16_t)mul;
+                placed = true;
+            }
+            ok = placed;
+        }
+        if (!ok) continue;
+        t.bshift = bshift;
+        t.sshift = sshift;
+        t.k0 = K[0];
+        t.k1 = K[1];
+        t.k2 = K[2];
+        for (size_t i = 0; i < nk && ok; i++) ok = ph_lookup(t, keys[i]) == entry[i];  // every key reaches its own entry
+        built = ok;
+    }
+    if (!built) return false;
+    const uint32_t lmask = (1u << L) - 1u;
+    t.lmask = lmask;
+    t.nm0 = ~(lmask | (lmask << kField));
+    t.nm1 = ~(lmask >> (32u - kField));
+    uint32_t dmin = 0xFFFFu;
+    for (uint32_t i = 0; i < S && dmin > 0; i++)
+        for (uint32_t j = i + 1; j < S; j++)
+            dmin = std::min(dmin, (uint32_t)__builtin_popcount((table[i].lo ^ table[j].lo) | (table[i].hi ^ table[j].hi)));
+    t.dmin = dmin;
+    t.single_ok = (uint64_t)dmin > 2ull * M + r.delta + 1ull ? 1u : 0u;
+    t.nkeys = (uint32_t)nk;
+    *out = std::move(t);
+    return true;
+}
+
+}  // namespace sgdx
+
+// Test support (include/sgdx_synth.h): build the tables for a configuration on the host and answer records the way the
+// kernel's fast path does.  No device, no matcher: records with invalid positions are reported as deferred.
+extern "C" int sgdx_ph_probe_host(const sgdx_config *cfg, const uint8_t *barcodes, const uint64_t *records, uint64_t n,
+                                  uint16_t *out_idx, uint8_t *out_dist, uint32_t *info) {
+    using namespace sgdx;
+    if (!cfg || !barcodes || (n && (!records || !out_idx || !out_dist))) return SGDX_EINVAL;
+    const uint32_t S = cfg->num_samples, L = cfg->barcode_len;
+    if (S < 1 || S > SGDX_MAX_SAMPLES || L < 1 || L > SGDX_COMPACT_MAX_LEN) return SGDX_EINVAL;
+    std::vector<PhPlanes> table(S);
+    for (uint32_t s = 0; s < S; s++) {
+        uint32_t lo = 0, hi = 0;
+        for (uint32_t j = 0; j < L; j++) {
+            const uint32_t c = (barcodes[(size_t)s * L + j] >> 1) & 3u;
+            lo |= (c & 1u) << j;
+            hi |= (c >> 1) << j;
+        }
+        table[s] = PhPlanes{lo, hi};
+    }
+    uint32_t matcher = cfg->matcher;
+    if (matcher == SGDX_MATCHER_AUTO) matcher = L <= 12 ? SGDX_MATCHER_PRECOMPUTE : SGDX_MATCHER_CACHED_HAMMING;
+    PhRules r{S, L, std::min<uint32_t>(cfg->max_mismatches, 64u), std::min<uint32_t>(cfg->min_delta, 64u),
+              ph_pc_limit(cfg->max_mismatches, cfg->min_delta, L), matcher == SGDX_MATCHER_PRECOMPUTE ? 1u : 0u};
+    PhTables t;
+    const bool have = ph_build(r, table, 0, nullptr, &t);
+    if (info) {
+        info[0] = have ? 1u : 0u;
+        info[1] = t.nkeys;
+        info[2] = have ? 32u - t.bshift : 0u;
+        info[3] = have ? 32u - t.sshift : 0u;
+        info[4] = t.single_ok;
+        info[5] = t.dmin;
+    }
+    if (!have) return SGDX_OK;
+    for (uint64_t i = 0; i < n; i++) {
+        const uint32_t w0 = (uint32_t)records[i], w1 = (uint32_t)(records[i] >> 32);
+        if (((w0 & t.nm0) | (w1 & t.nm1)) != 0u) {  // general path on the device
+            out_idx[i] = 0xFFFFu;
+            out_dist[i] = 0xFEu;
+            continue;
+        }
+        const uint32_t e = ph_lookup(t, records[i]);
+        const uint32_t lo = w0 & kFieldMask, hi = (uint32_t)(records[i] >> kField) & kFieldMask;
+        const uint32_t tlo = e < S ? table[e].lo : 0u, thi = e < S ? table[e].hi : 0xFFFFFFFFu;
+        const uint32_t d = (uint32_t)__builtin_popcount((lo ^ tlo) | (hi ^ thi));
+        const bool ok = d <= r.M;
+        out_idx[i] = (uint16_t)(ok ? e : S);
+        out_dist[i] = (uint8_t)(ok ? d : SGDX_NO_DIST);
+    }
+    return SGDX_OK;
+}

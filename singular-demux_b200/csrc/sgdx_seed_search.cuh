@@ -107,6 +107,26 @@ __device__ __forceinline__ void emit_single(const DevParams &p, uint64_t r, cons
     if (p.hop_on && v.bin == p.S) hop_check(p, rd);
 }
 
+// compact record (include/sgdx.h) <-> planes.  lmask = (1 << barcode_len) - 1: bits a caller left above the
+// barcode's length in any plane, and bit 63, are ignored.
+__device__ __forceinline__ Rd rd_of_compact(uint64_t rec, uint32_t lmask) {
+    const uint32_t lo = (uint32_t)rec & lmask;
+    const uint32_t hi = (uint32_t)(rec >> kCompactField) & lmask;
+    const uint32_t inv = (uint32_t)(rec >> (2u * kCompactField)) & lmask;
+    Rd rd;
+    rd.nmask = inv & ~lo;
+    rd.xmask = inv & lo;
+    rd.lo = lo & ~inv;
+    rd.hi = hi & ~inv;
+    return rd;
+}
+
+__device__ __forceinline__ uint64_t compact_of_rd(const Rd &rd) {
+    const uint32_t inv = rd.nmask | rd.xmask;
+    return (uint64_t)((rd.lo & ~inv) | rd.xmask) | ((uint64_t)(rd.hi & ~inv) << kCompactField) |
+           ((uint64_t)inv << (2u * kCompactField));
+}
+
 inline uint32_t persistent_grid(uint64_t n, uint32_t threads, int sms, int per_sm) {
     uint64_t tiles = (n + threads - 1) / threads;
     uint64_t cap = (uint64_t)sms * (uint64_t)per_sm;  // persistent grid: a multiple of the SM count

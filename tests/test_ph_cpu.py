@@ -1,0 +1,126 @@
+"""Tables of the perfect-hash kernel (sgdx_match_ph, csrc/sgdx_ph.cu) against the oracle, without a GPU.
+
+sgdx_ph_probe_host (include/sgdx_synth.h) runs the same host code sgdx_create runs to build the two-level perfect
+hash of the match neighbourhood, then answers compact records with the kernel's fast-path arithmetic (hash ->
+bucket multiplier -> untagged entry -> distance test).  For every read made of A/C/G/T only that answer must be
+Matcher::find's (matcher.rs:273-303 / 121-262) -- including tables whose barcodes are so close that ties and the
+delta rule reject reads near them, which is where the precomputed verdict (not the distance test) decides."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import sgdx_loader
+from oracle import oracle as orc
+
+sg = sgdx_loader.load()
+LETTERS = np.frombuffer(b"ACGT", dtype=np.uint8)
+
+
+def probe(table, M, D, matcher, reads):
+    S, L = table.shape
+    cfg = sg._lib.Config(S, L, M, D, 1, -1, matcher, 0, 0, 0, 1, 0)
+    rec = sg.pack_compact_host(reads)
+    idx = np.empty(len(reads), dtype=np.uint16)
+    dist = np.empty(len(reads), dtype=np.uint8)
+    info = (C.c_uint32 * 6)()
+    tb = np.ascontiguousarray(table)
+    rc = sg.lib().sgdx_ph_probe_host(C.byref(cfg), tb.ctypes.data, rec.ctypes.data, len(reads), idx.ctypes.data,
+                                     dist.ctypes.data, info)
+    assert rc == 0
+    return idx, dist, list(info)
+
+
+def reads_near(table, rng, n, max_subs):
+    """Reads at 0..max_subs substitutions from random barcodes, plus uniform random reads."""
+    S, L = table.shape
+    reads = table[rng.integers(0, S, n)].copy()
+    nsub = rng.integers(0, max_subs + 1, n)
+    for r in range(n):
+        pos = rng.choice(L, min(nsub[r], L), replace=False)
+        reads[r, pos] = LETTERS[rng.integers(0, 4, len(pos))]
+    reads[-n // 10:] = LETTERS[rng.integers(0, 4, (n // 10, L))]
+    return reads
+
+
+def oracle_run(table, M, D, kind, reads):
+    S, L = table.shape
+    cfg = orc.Config(S, L, M, D, 1, -1, kind, 0, 0)
+    got = orc.COracle(cfg, [bytes(t) for t in table], force_closed_form=True).run(reads, threads=2, use_cache=False)
+    return got["idx"], got["dist"]
+
+
+@pytest.mark.parametrize("cfg_name,M,D", [("C1", 1, 2), ("C2", 1, 2), ("C2", 0, 5), ("C1", 0, 0), ("C4", 1, 2),
+                                          ("C4", 2, 0)])
+def test_baseline_tables_equal_the_oracle(cfg_name, M, D):
+    w = sg.synth.CONFIGS[cfg_name]
+    table = w.table()
+    S, L = table.shape
+    rng = np.random.default_rng(S * 31 + M * 7 + D)
+    reads = reads_near(table, rng, 20000, M + 3)
+    for kind, matcher in ((orc.MATCHER_CACHED_HAMMING, 1), (orc.MATCHER_PRECOMPUTE, 2)):
+        idx, dist, info = probe(table, M, D, matcher, reads)
+        assert info[0] == 1, info
+        want_idx, want_dist = oracle_run(table, M, D, kind, reads)
+        assert np.array_equal(idx, want_idx)
+        assert np.array_equal(dist, want_dist)
+    if cfg_name == "C2" and M == 1:
+        assert info[1] == 384 * 61 and info[3] == 15  # 23 424 keys in 32 768 slots
+
+
+@pytest.mark.parametrize("seed,S,L,M,D", [(1, 40, 6, 1, 1), (2, 40, 6, 2, 1), (3, 64, 8, 1, 2), (4, 64, 8, 2, 0), (5, 12, 5, 1, 0),
+                                          (6, 30, 7, 3, 1), (7, 200, 10, 1, 3), (8, 16, 4, 4, 1), (9, 100, 12, 1, 1),
+                                          (10, 3, 21, 1, 2), (11, 500, 16, 1, 1)])
+def test_close_tables_where_ties_and_delta_decide(seed, S, L, M, D):
+    """Random distinct barcodes with no distance guarantee: many keys are within M of two samples, or have a
+    competitor within delta, so their precomputed verdict is NoMatch although the distance test alone would pass."""
+    rng = np.random.default_rng(seed)
+    table = np.unique(LETTERS[rng.integers(0, 4, (S * 2, L))], axis=0)
+    rng.shuffle(table)
+    table = np.ascontiguousarray(table[:S])
+    S = len(table)
+    reads = reads_near(table, rng, 12000, M + 2)
+    saw_rejected_near = False
+    for kind, matcher in ((orc.MATCHER_CACHED_HAMMING, 1), (orc.MATCHER_PRECOMPUTE, 2)):
+        idx, dist, info = probe(table, M, D, matcher, reads)
+        if not info[0]:
+            pytest.skip("configuration has too many keys for a perfect hash")
+        want_idx, want_dist = oracle_run(table, M, D, kind, reads)
+        assert np.array_equal(idx, want_idx)
+        assert np.array_equal(dist, want_dist)
+        near = (reads[:, None, :] != table[None, :, :]).sum(-1).min(1) <= M
+        saw_rejected_near |= bool((near & (want_idx == S)).any())
+    if L <= 8:
+        assert saw_rejected_near, "the case this test exists for did not occur"
+
+
+def test_exhaustive_short_barcodes_both_rule_sets():
+    """Every one of the 4^6 strings, 9 rule settings, both rule sets."""
+    rng = np.random.default_rng(99)
+    L = 6
+    table = np.unique(LETTERS[rng.integers(0, 4, (24, L))], axis=0)[:20]
+    allreads = LETTERS[(np.arange(4 ** L)[:, None] >> (2 * np.arange(L))) & 3]
+    for M in (0, 1, 2):
+        for D in (0, 1, 3):
+            for kind, matcher in ((orc.MATCHER_CACHED_HAMMING, 1), (orc.MATCHER_PRECOMPUTE, 2)):
+                idx, dist, info = probe(table, M, D, matcher, allreads)
+                assert info[0] == 1
+                want_idx, want_dist = oracle_run(table, M, D, kind, allreads)
+                assert np.array_equal(idx, want_idx), (M, D, kind)
+                assert np.array_equal(dist, want_dist), (M, D, kind)
+
+
+def test_reads_with_invalid_positions_are_deferred_and_big_key_sets_refused():
+    w = sg.synth.CONFIGS["C2"]
+    table = w.table()
+    reads = table[:64].copy()
+    reads[::2, 3] = ord("N")
+    reads[1::4, 7] = ord("R")
+    idx, dist, info = probe(table, 1, 2, 1, reads)
+    bad = (reads == ord("N")).any(1) | (reads == ord("R")).any(1)
+    assert (idx[bad] == 0xFFFF).all() and (dist[bad] == 0xFE).all()
+    assert np.array_equal(idx[~bad], np.arange(64)[~bad])
+    # 384 x 20 bases at two mismatches: 384 * 1771 keys -- no tables, the older kernels serve it
+    _, _, info2 = probe(table, 2, 1, 1, reads[:1])
+    assert info2[0] == 0
+    assert info[4] == 1 and info[5] >= 6  # min pairwise distance 6 > 2*1 + 2 + 1: single-N shortcut valid

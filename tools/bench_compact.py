@@ -91,7 +91,7 @@ def measure(**kw):
     out["device"] = {
         "ascii": {"kernel": m.kernel_name(), "avg_ms": a_avg, "best_ms": a_best, "reads_per_s": n / a_avg * 1e3,
                   "buffer_bytes_per_read": L + 3, "buffer_gbs": n * (L + 3) / a_avg / 1e6},
-        "compact": {"kernel": "sgdx_match_compact", "avg_ms": c_avg, "best_ms": c_best, "reads_per_s": n / c_avg * 1e3,
+        "compact": {"kernel": "sgdx_match_ph" if m.path_flags() & 64 else "sgdx_match_compact", "avg_ms": c_avg, "best_ms": c_best, "reads_per_s": n / c_avg * 1e3,
                     "algorithmic_bytes_per_read": 11, "achieved_gbs": n * 11 / c_avg / 1e6,
                     "frac_of_hbm_peak": n * 11 / c_avg / 1e6 / peak, "equals_ascii_kernel": same},
     }
