@@ -139,9 +139,10 @@ int sgdx_match_packed_batch(sgdx_handle *h, uint32_t slot, const sgdx_read *reco
  * The batching stage (demux.rs:522 -> :528) writes this instead of ASCII into its pinned buffer:
  * sgdx_pack_compact_host is that pass (host code, `threads` workers, AVX2 when the CPU has it), and
  * sgdx_match_compact_batch is sgdx_match_batch for such a buffer: 8 instead of barcode_len bytes per read
- * cross PCIe, and the kernel reads them with one coalesced 64-bit load.  Results are identical to the ASCII
- * entry points for every configuration; tables without the exact-match shortcut (see SGDX_PATH_COMPACT)
- * are served through the 16-byte packed form of the general kernels.  Unmatched collection needs ASCII. */
+ * cross PCIe, and the kernel (sgdx_match_ph, see SGDX_PATH_PERFECT_HASH) reads four of them with one 256-bit load.
+ * Results are identical to the ASCII entry points for every configuration; tables too large for the perfect hash
+ * are served through the 16-byte packed form of the general kernels.  Bits above barcode_len in any plane, and
+ * bit 63, are ignored.  Unmatched collection needs ASCII. */
 #define SGDX_COMPACT_MAX_LEN 21u
 int sgdx_pack_compact_host(const uint8_t *barcodes_ascii, uint64_t n, uint32_t barcode_len, uint64_t *out_records,
                            uint32_t threads /* 0 -> 1 */);
@@ -161,9 +162,7 @@ const char *sgdx_kernel_name(const sgdx_handle *h);
 #define SGDX_PATH_EXACT 2u        /* exact-match front end (min pairwise table distance > min_delta) */
 #define SGDX_PATH_NEIGHBOURS 4u   /* one-substitution neighbour table (min pairwise distance > min_delta + 2) */
 #define SGDX_PATH_HOP_DIRECT 8u   /* direct-address hop tables (both index halves <= 11 bases) */
-#define SGDX_PATH_COMPACT 16u     /* sgdx_match_compact serves compact records (exact shortcut valid, barcode_len <= 21) */
-#define SGDX_PATH_SHORT_SEED 32u  /* ... and its seed search uses max_mismatches + 1 chunks (min pairwise distance >
-                                     2 * max_mismatches + min_delta; SGDX_NO_SHORT_SEED=1 at sgdx_create turns it off) */
+/* 16u, 32u: flags of the round-1 compact kernel, retired (never set) */
 #define SGDX_PATH_PERFECT_HASH 64u /* compact records run sgdx_match_ph: every A/C/G/T string within max_mismatches of a
                                      barcode sits in a perfect hash with its precomputed verdict (barcode_len <= 21 and at
                                      most ~28 000 such strings; SGDX_DISABLE_PH=1 at sgdx_create turns it off) */

@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get("SGDX_LIB") or os.path.join(_HERE, "libsgdx.so")  # SG
 MATCHER_AUTO, MATCHER_CACHED_HAMMING, MATCHER_PRECOMPUTE = 0, 1, 2
 KERNEL_AUTO, KERNEL_DIRECT, KERNEL_SEEDED = 0, 1, 2
 NO_DIST = 0xFF
-PATH_SEED_INDEX, PATH_EXACT, PATH_NEIGHBOURS, PATH_HOP_DIRECT, PATH_COMPACT, PATH_SHORT_SEED = 1, 2, 4, 8, 16, 32
+PATH_SEED_INDEX, PATH_EXACT, PATH_NEIGHBOURS, PATH_HOP_DIRECT = 1, 2, 4, 8
 PATH_PERFECT_HASH = 64
 COMPACT_MAX_LEN = 21
 MAX_BARCODE_LEN = 32

@@ -234,103 +234,6 @@ static int build_exact_table(sgdx_handle *h, const uint8_t *barcodes, const std:
     return SGDX_OK;
 }
 
-// Front end of sgdx_match_compact (sgdx_compact.cu): the same cuckoo placement over a hash of each barcode's
-// compact record.  Exists when the exact-match shortcut is valid (ex_on) and a read fits one 64-bit record.
-static int build_compact_table(sgdx_handle *h, const std::vector<uint2> &table) {
-    const DevParams &p = h->base;
-    h->cx = CompactParams{};
-    if (!h->seeded || !p.ex_on || p.L > kCompactMaxLen) return SGDX_OK;
-    // two-choice cuckoo placement of 64-bit entries (record | (sample + 1) << 42); an entry's positions follow
-    // from its own record, so an evicted entry needs no side table.  Load factor <= 1/4; if a random walk gives
-    // up, other multipliers and then a larger table are tried.
-    static const uint32_t KS[4][4] = {{0x9E3779B1u, 0x85EBCA77u, 0xC2B2AE3Du, 0x27D4EB2Fu},
-                                      {0x165667B1u, 0xD3A2646Du, 0xFD7046C5u, 0xB55A4F09u},
-                                      {0x2545F491u, 0x9E6C63D1u, 0x7FEB352Du, 0x846CA68Bu},
-                                      {0xCC9E2D51u, 0x1B873593u, 0xE6546B65u, 0x85EBCA6Bu}};
-    const uint64_t rec_mask = (1ull << 42) - 1ull;
-    for (uint32_t attempt = 0; attempt < 12 && !h->cx.slots; attempt++) {
-        const uint32_t bits = std::max(p.ex_bits, 6u) + attempt / 4u;
-        const uint32_t *K = KS[attempt % 4u];
-        if (compact_smem_bytes(p, bits) > 200u * 1024u) return SGDX_OK;
-        std::vector<uint64_t> slots((size_t)1 << bits, 0ull);
-        auto pos = [&](uint64_t entry, int which) {
-            const uint32_t w0 = (uint32_t)(entry & rec_mask), w1 = (uint32_t)((entry & rec_mask) >> 32);
-            return ((w0 * K[2 * which]) ^ (w1 * K[2 * which + 1])) >> (32u - bits);
-        };
-        bool placed = true;
-        for (uint32_t s = 0; s < p.S && placed; s++) {
-            uint64_t entry = compact_record(table[s].x, table[s].y) | ((uint64_t)(s + 1u) << 42);
-            uint32_t last = 0xFFFFFFFFu;
-            placed = false;
-            for (int kick = 0; kick < 2000 && !placed; kick++) {
-                const uint32_t p1 = pos(entry, 0), p2 = pos(entry, 1);
-                if (slots[p1] == 0ull) {
-                    slots[p1] = entry;
-                    placed = true;
-                } else if (slots[p2] == 0ull) {
-                    slots[p2] = entry;
-                    placed = true;
-                } else {
-                    const uint32_t victim = p1 == last ? p2 : p1;
-                    std::swap(entry, slots[victim]);
-                    last = victim;
-                }
-            }
-        }
-        if (!placed) continue;
-        CU(cudaMalloc(&h->d_cx_slots, slots.size() * sizeof(uint64_t)));
-        CU(cudaMemcpy(h->d_cx_slots, slots.data(), slots.size() * sizeof(uint64_t), cudaMemcpyHostToDevice));
-        h->cx.slots = h->d_cx_slots;
-        h->cx.bits = bits;
-        h->cx.k0 = K[0];
-        h->cx.k1 = K[1];
-        h->cx.k2 = K[2];
-        h->cx.k3 = K[3];
-    }
-    if (!h->cx.slots) return SGDX_OK;
-
-    // short seed index for stage 2 (see CompactParams): same construction as build_seed_index with M + 1 chunks
-    const uint32_t C = p.M + 1u;
-    if (getenv("SGDX_NO_SHORT_SEED") || (uint64_t)p.dmin <= 2ull * p.M + p.delta || C > p.L || C > 8u) return SGDX_OK;
-    std::vector<uint16_t> hdr, ids((size_t)C * p.S, 0);
-    uint32_t total = 0;
-    for (uint32_t c = 0; c < C; c++) {
-        const uint32_t a = (uint32_t)((uint64_t)c * p.L / C), b = (uint32_t)((uint64_t)(c + 1) * p.L / C);
-        const uint32_t w = std::min(b - a, 5u), nb = 1u << (2 * w), wm = (1u << w) - 1u;
-        h->cx.short_desc[c] = a | (w << 8) | (total << 16);
-        hdr.resize(total + nb + 1u, 0);
-        auto key_of = [&](uint32_t s) { return ((table[s].x >> a) & wm) | (((table[s].y >> a) & wm) << w); };
-        std::vector<uint32_t> cnt(nb, 0u);
-        for (uint32_t s = 0; s < p.S; s++) cnt[key_of(s)]++;
-        uint32_t run = c * p.S;
-        for (uint32_t k = 0; k < nb; k++) {
-            hdr[total + k] = (uint16_t)run;
-            run += cnt[k];
-            cnt[k] = 0;
-        }
-        hdr[total + nb] = (uint16_t)run;
-        for (uint32_t s = 0; s < p.S; s++) {
-            const uint32_t k = key_of(s);
-            ids[hdr[total + k] + cnt[k]++] = (uint16_t)s;
-        }
-        total += nb + 1u;
-    }
-    if ((uint64_t)C * p.S > 0xFFFFu || total > 0xFFFFu ||
-        compact_smem_bytes(p, h->cx.bits, total, C * p.S) > 72u * 1024u)  // keep three CTAs per SM
-        return SGDX_OK;
-    CU(cudaMalloc(&h->d_cx_short_hdr, hdr.size() * sizeof(uint16_t)));
-    CU(cudaMalloc(&h->d_cx_short_ids, ids.size() * sizeof(uint16_t)));
-    CU(cudaMemcpy(h->d_cx_short_hdr, hdr.data(), hdr.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(h->d_cx_short_ids, ids.data(), ids.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
-    h->cx.short_hdr = h->d_cx_short_hdr;
-    h->cx.short_ids = h->d_cx_short_ids;
-    h->cx.short_hdr_total = total;
-    h->cx.short_ids_total = C * p.S;
-    h->cx.short_C = C;
-    return SGDX_OK;
-}
-
-
 // Perfect hash of the match neighbourhood for sgdx_match_ph (sgdx_ph.cu): built on the host by sgdx_phbuild.cpp
 static int build_ph_table(sgdx_handle *h, const std::vector<uint2> &table) {
     const DevParams &p = h->base;
@@ -357,6 +260,33 @@ static int build_ph_table(sgdx_handle *h, const std::vector<uint2> &table) {
     h->ph.lmask = t.lmask;
     h->ph.single_ok = t.single_ok;
     h->ph_keys = t.nkeys;
+    if (p.hop_on) {
+        // hop key sets for the kernel's shared memory (PhParams::hop1/hop2): the distinct halves without the all-N
+        // ones of Undetermined (a read with a no-call takes the general path and the global tables)
+        auto build = [&](const std::vector<std::string> &keys, uint32_t len, uint64_t **d_out, uint32_t *bits_out) -> int {
+            uint32_t bits = 4;
+            while ((1u << bits) * 2u < keys.size() * 5u) bits++;  // load factor <= 0.4
+            std::vector<uint64_t> tab((size_t)1 << bits, 0ull);
+            const uint32_t mask = (1u << bits) - 1u;
+            for (uint32_t id = 0; id < keys.size(); id++) {
+                if (keys[id].find('N') != std::string::npos) continue;
+                uint32_t lo, hi;
+                encode_planes(reinterpret_cast<const uint8_t *>(keys[id].data()), len, &lo, &hi);
+                const uint64_t key = (uint64_t)lo | ((uint64_t)hi << len);
+                uint32_t i = (((uint32_t)key * 0x9E3779B1u) ^ ((uint32_t)(key >> 32) * 0x85EBCA77u)) >> (32u - bits);
+                while (tab[i]) i = (i + 1u) & mask;
+                tab[i] = key | ((uint64_t)(id + 1u) << 42);
+            }
+            CU(cudaMalloc(d_out, tab.size() * sizeof(uint64_t)));
+            CU(cudaMemcpy(*d_out, tab.data(), tab.size() * sizeof(uint64_t), cudaMemcpyHostToDevice));
+            *bits_out = bits;
+            return SGDX_OK;
+        };
+        if (int rc = build(h->keys1, p.i1, &h->d_ph_hop1, &h->ph.hbits1)) return rc;
+        if (int rc = build(h->keys2, p.i2, &h->d_ph_hop2, &h->ph.hbits2)) return rc;
+        h->ph.hop1 = h->d_ph_hop1;
+        h->ph.hop2 = h->d_ph_hop2;
+    }
     return SGDX_OK;
 }
 
@@ -473,7 +403,6 @@ static int fill_handle(sgdx_handle *h, const sgdx_config *cfg, const uint8_t *ba
                 return rc;
             }
         h->cfg.kernel = h->seeded ? SGDX_KERNEL_SEEDED : SGDX_KERNEL_DIRECT;
-        if (int rc = build_compact_table(h, table)) return rc;
         if (int rc = build_ph_table(h, table)) return rc;
     }
 
@@ -549,11 +478,10 @@ extern "C" void sgdx_destroy(sgdx_handle *h) {
     cudaFree(h->d_ex_slots);
     cudaFree(h->d_ex_ascii);
     cudaFree(h->d_nb_slots);
-    cudaFree(h->d_cx_slots);
-    cudaFree(h->d_cx_short_hdr);
-    cudaFree(h->d_cx_short_ids);
     cudaFree(h->d_ph_disp);
     cudaFree(h->d_ph_slots);
+    cudaFree(h->d_ph_hop1);
+    cudaFree(h->d_ph_hop2);
     cudaFree(h->d_hash1);
     cudaFree(h->d_hash2);
     cudaFree(h->d_hop_lut1);
@@ -703,8 +631,6 @@ static int run_compact(sgdx_handle *h, Slot &s, const uint64_t *d_records, uint6
         p.out_dist = d_dist;
         PhParams c = h->ph;
         c.reads = d_records;
-        c.vec = ((reinterpret_cast<uintptr_t>(d_records) & 31u) == 0u && (reinterpret_cast<uintptr_t>(d_idx) & 7u) == 0u &&
-                 (reinterpret_cast<uintptr_t>(d_dist) & 3u) == 0u) ? 1u : 0u;
         CU(cudaEventRecord(s.e0, s.stream));
         CU(launch_ph(p, c, h->mode, h->sms, s.stream));
         if (n) h->launches.fetch_add(1);
@@ -712,24 +638,11 @@ static int run_compact(sgdx_handle *h, Slot &s, const uint64_t *d_records, uint6
         s.timed = true;
         return SGDX_OK;
     }
-    if (!h->cx.slots) {  // table without the exact-match shortcut: expand to 16-byte records, general kernels
-        if (int rc = ensure_packed_scratch(s, n)) return rc;
-        CU(launch_expand_compact(d_records, n, h->cfg.barcode_len, s.d_cexp, h->sms, s.stream));
-        if (n) h->launches.fetch_add(1);
-        return run_kernels(h, s, nullptr, s.d_cexp, n, d_idx, d_dist);
-    }
-    DevParams p = h->base;
-    p.n = n;
-    p.out_idx = d_idx;
-    p.out_dist = d_dist;
-    CompactParams c = h->cx;
-    c.reads = d_records;
-    CU(cudaEventRecord(s.e0, s.stream));
-    CU(launch_compact(p, c, h->mode, h->sms, s.stream));
+    // no perfect hash for this table (too many strings within max_mismatches): 16-byte records, general kernels
+    if (int rc = ensure_packed_scratch(s, n)) return rc;
+    CU(launch_expand_compact(d_records, n, h->cfg.barcode_len, s.d_cexp, h->sms, s.stream));
     if (n) h->launches.fetch_add(1);
-    CU(cudaEventRecord(s.e1, s.stream));
-    s.timed = true;
-    return SGDX_OK;
+    return run_kernels(h, s, nullptr, s.d_cexp, n, d_idx, d_dist);
 }
 
 extern "C" int sgdx_match_compact_device(sgdx_handle *h, uint32_t slot, const uint64_t *d_records, uint64_t n,
@@ -822,7 +735,6 @@ extern "C" uint32_t sgdx_path_flags(const sgdx_handle *h) {
     const DevParams &p = h->base;
     return (h->seeded ? SGDX_PATH_SEED_INDEX : 0u) | (h->seeded && p.ex_on ? SGDX_PATH_EXACT : 0u) |
            (h->seeded && p.ex_on && p.nb_on ? SGDX_PATH_NEIGHBOURS : 0u) | (p.hop_direct ? SGDX_PATH_HOP_DIRECT : 0u) |
-           (h->cx.slots ? SGDX_PATH_COMPACT : 0u) | (h->cx.short_C ? SGDX_PATH_SHORT_SEED : 0u) |
            (h->ph.slots ? SGDX_PATH_PERFECT_HASH : 0u);
 }
 

@@ -15,30 +15,12 @@ uint32_t exact_block_threads(const DevParams &p);
 cudaError_t launch_seeded(const DevParams &p, uint32_t mode, bool packed, int sms, cudaStream_t stream);
 cudaError_t launch_pack(const uint8_t *reads, uint64_t n, uint32_t L, uint4 *out, int sms, cudaStream_t stream);
 
-// compact records (sgdx_compact.cu): one 64-bit word per read of at most kCompactMaxLen bases --
+// compact records (sgdx_compact.cu, sgdx_ph.cu): one 64-bit word per read of at most kCompactMaxLen bases --
 // lo plane | hi plane << 21 | invalid plane << 42 (at an invalid position lo = 0: 'N', lo = 1: any other byte)
 constexpr uint32_t kCompactMaxLen = 21;
 constexpr uint32_t kCompactField = 21;  // bits per plane
 constexpr uint32_t kCompactMask = (1u << kCompactField) - 1u;
-struct CompactParams {
-    const uint64_t *reads;  // n records
-    const uint64_t *slots;  // [1 << bits] cuckoo table of the expected barcodes: record | (sample + 1) << 42, 0 = empty
-    uint32_t bits;
-    uint32_t k0, k1, k2, k3;  // position 1 = ((w0 * k0) ^ (w1 * k1)) >> (32 - bits), position 2 likewise with k2, k3
-                              // (w0, w1 = the record's two 32-bit words)
-    // Short seed index (optional): when min pairwise table distance > 2 * max_mismatches + min_delta, a read without
-    // invalid positions that is within max_mismatches of a sample has every other sample further than
-    // max_mismatches + min_delta away, so only samples within max_mismatches matter and the delta test cannot
-    // fail: max_mismatches + 1 chunks instead of max_mismatches + min_delta + 1.  Same bucket layout as the seed
-    // index of DevParams; short_C == 0: not available.
-    const uint16_t *short_hdr;
-    const uint16_t *short_ids;
-    uint32_t short_C, short_hdr_total, short_ids_total;
-    uint32_t short_desc[8];
-};
 inline uint64_t compact_record(uint32_t lo, uint32_t hi) { return (uint64_t)lo | ((uint64_t)hi << 21); }
-size_t compact_smem_bytes(const DevParams &p, uint32_t bits, uint32_t short_hdr_total = 0, uint32_t short_ids_total = 0);
-cudaError_t launch_compact(const DevParams &p, const CompactParams &c, uint32_t mode, int sms, cudaStream_t stream);
 cudaError_t launch_pack_compact(const uint8_t *reads, uint64_t n, uint32_t L, uint64_t *out, int sms, cudaStream_t stream);
 cudaError_t launch_expand_compact(const uint64_t *in, uint64_t n, uint32_t L, uint4 *out, int sms, cudaStream_t stream);
 
@@ -63,7 +45,12 @@ struct PhParams {
     uint32_t lmask;         // (1 << barcode_len) - 1
     uint32_t single_ok;     // min pairwise table distance > 2M + delta + 1: a read with ONE invalid base is decided by
                             // the unique sample within M over its valid positions, found by probing its 4 completions
-    uint32_t vec;           // per launch: 256-bit record loads / packed result stores (all three buffers aligned)
+    // hop key sets for shared memory (optional; hbits == 0: the kernel uses the global tables of DevParams): open
+    // addressing over the distinct index1 / index2 halves without Undetermined's all-N halves,
+    // entry = key | (dense id + 1) << 42, key = lo bits | hi bits << half length, 0 = empty
+    const uint64_t *hop1, *hop2;
+    uint32_t hbits1, hbits2;
+    uint32_t clog;          // per launch: log2 of the copies of the planes table in shared memory
 };
 size_t ph_smem_bytes(uint32_t S, uint32_t bbits, uint32_t sbits);
 cudaError_t launch_ph(const DevParams &p, const PhParams &c, uint32_t mode, int sms, cudaStream_t stream);

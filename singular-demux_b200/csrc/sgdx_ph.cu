@@ -28,23 +28,34 @@ constexpr uint32_t kPhThreads = 1024;
 constexpr uint32_t kPhWarps = kPhThreads / 32;
 constexpr uint32_t kPhChunk = 128;  // reads per warp per iteration
 constexpr uint32_t kPhQueue = 160;  // <= 31 left over + <= 128 pushed by one chunk
+constexpr uint32_t kPhQueue2 = 64;  // <= 31 left over + <= 32 pushed by one drain of the first queue
 
 struct PhSmem {
+    uint64_t *qrec;   // [warps][kPhQueue] deferred reads: record ...
+    uint32_t *qoff;   // [warps][kPhQueue] ... and (warp iteration * 128 + offset in chunk)
+    uint64_t *q2rec;  // [warps][kPhQueue2] the deferred reads that need the general path ...
+    uint32_t *q2off;  // [warps][kPhQueue2] ... same numbering
+    uint64_t *hop1;   // [1 << hbits1] index1 halves of the expected barcodes (open addressing), optional
+    uint64_t *hop2;   // [1 << hbits2] index2 halves
+    uint2 *planes;    // [S + 1][copies]: barcode planes, replicated so that the lanes of a half warp read distinct banks;
+                      //                  row S = dummy that nothing matches
+    uint32_t *hist;   // [3][S + 1] perfect, one mismatch, other (metrics.rs:428-437), + 1 word nobody reads
     uint16_t *disp;   // [1 << bbits]
     uint16_t *slots;  // [1 << sbits]
-    uint2 *planes;    // [S + 1], entry S = dummy that nothing matches
-    uint32_t *hist;   // [3][S + 1]: perfect, one mismatch, other (metrics.rs:428-437)
-    uint64_t *qhop;   // [warps][kPhQueue] records of A/C/G/T-only NoMatch reads awaiting the hop check
-    uint32_t *qslow;  // [warps][kPhQueue] (warp iteration * 128 + offset in chunk) of reads for the general path
 };
 
-__host__ __device__ inline size_t ph_carve(unsigned char *base, uint32_t S, uint32_t bbits, uint32_t sbits, PhSmem *out) {
+__host__ __device__ inline size_t ph_carve(unsigned char *base, uint32_t S, uint32_t bbits, uint32_t sbits, uint32_t clog,
+                                           uint32_t hbits1, uint32_t hbits2, PhSmem *out) {
     size_t o = 0;
     PhSmem s;
-    s.qhop = reinterpret_cast<uint64_t *>(base + o);   o += (size_t)kPhWarps * kPhQueue * 8;
-    s.planes = reinterpret_cast<uint2 *>(base + o);    o += (((size_t)S + 1) * 8 + 15) & ~(size_t)15;
-    s.hist = reinterpret_cast<uint32_t *>(base + o);   o += (((size_t)S + 1) * 3 * 4 + 15) & ~(size_t)15;
-    s.qslow = reinterpret_cast<uint32_t *>(base + o);  o += (size_t)kPhWarps * kPhQueue * 4;
+    s.qrec = reinterpret_cast<uint64_t *>(base + o);   o += (size_t)kPhWarps * kPhQueue * 8;
+    s.q2rec = reinterpret_cast<uint64_t *>(base + o);  o += (size_t)kPhWarps * kPhQueue2 * 8;
+    s.hop1 = reinterpret_cast<uint64_t *>(base + o);   o += hbits1 ? (size_t)8 << hbits1 : 0;
+    s.hop2 = reinterpret_cast<uint64_t *>(base + o);   o += hbits2 ? (size_t)8 << hbits2 : 0;
+    s.planes = reinterpret_cast<uint2 *>(base + o);    o += (((size_t)S + 1) * 8) << clog;
+    s.qoff = reinterpret_cast<uint32_t *>(base + o);   o += (size_t)kPhWarps * kPhQueue * 4;
+    s.q2off = reinterpret_cast<uint32_t *>(base + o);  o += (size_t)kPhWarps * kPhQueue2 * 4;
+    s.hist = reinterpret_cast<uint32_t *>(base + o);   o += ((((size_t)S + 1) * 3 + 1) * 4 + 15) & ~(size_t)15;
     s.disp = reinterpret_cast<uint16_t *>(base + o);   o += (size_t)2 << bbits;
     s.slots = reinterpret_cast<uint16_t *>(base + o);  o += (size_t)2 << sbits;
     o = (o + 15) & ~(size_t)15;
@@ -52,15 +63,56 @@ __host__ __device__ inline size_t ph_carve(unsigned char *base, uint32_t S, uint
     return o;
 }
 
-size_t ph_smem_bytes(uint32_t S, uint32_t bbits, uint32_t sbits) { return ph_carve(nullptr, S, bbits, sbits, nullptr); }
+constexpr size_t kPhSmemLimit = 227u * 1024u;
 
-// the perfect-hash probe of one record without invalid positions: entry (sample or S) and distance to it
-__device__ __forceinline__ void ph_probe(const PhSmem &sm, const PhParams &c, uint32_t w0, uint32_t w1, uint32_t &e,
-                                         uint32_t &d) {
+size_t ph_smem_bytes(uint32_t S, uint32_t bbits, uint32_t sbits) { return ph_carve(nullptr, S, bbits, sbits, 0u, 0u, 0u, nullptr); }
+
+// What is optional goes into shared memory as far as it fits: first the hop key sets (without them every hop check
+// is a round trip to L2), then copies of the planes table (up to one per lane of a half warp).
+static void ph_fit(uint32_t S, PhParams &c) {
+    const uint32_t bbits = 32u - c.bshift, sbits = 32u - c.sshift;
+    if (ph_carve(nullptr, S, bbits, sbits, 0u, c.hbits1, c.hbits2, nullptr) > kPhSmemLimit) c.hbits1 = c.hbits2 = 0u;
+    c.clog = 4u;
+    while (c.clog && ph_carve(nullptr, S, bbits, sbits, c.clog, c.hbits1, c.hbits2, nullptr) > kPhSmemLimit) c.clog--;
+}
+
+// A half of an A/C/G/T-only barcode in the shared-memory key set: dense id of the key, or 0xFFFFFFFF.
+// Entry = key | (id + 1) << 42, key = lo bits | hi bits << len; 0 = empty; linear probing at load <= 0.4.
+__device__ __forceinline__ uint32_t ph_hop_find(const uint64_t *tab, uint32_t hbits, uint64_t key) {
+    const uint32_t mask = (1u << hbits) - 1u;
+    uint32_t i = (((uint32_t)key * 0x9E3779B1u) ^ ((uint32_t)(key >> 32) * 0x85EBCA77u)) >> (32u - hbits);
+    for (;;) {
+        const uint64_t e = tab[i];
+        if (e == 0ull) return 0xFFFFFFFFu;
+        if ((e & ((1ull << 42) - 1ull)) == key) return (uint32_t)(e >> 42) - 1u;
+        i = (i + 1u) & mask;
+    }
+}
+
+// metrics.rs:658-676 for an A/C/G/T-only NoMatch read, key sets in shared memory
+__device__ __forceinline__ void ph_hop_check(const DevParams &p, const PhParams &c, const PhSmem &sm, uint32_t lo, uint32_t hi) {
+    const uint32_t m1 = (1u << p.i1) - 1u, m2 = (1u << p.i2) - 1u;
+    const uint32_t a = ph_hop_find(sm.hop1, c.hbits1, (uint64_t)(lo & m1) | ((uint64_t)(hi & m1) << p.i1));
+    const uint32_t b = ph_hop_find(sm.hop2, c.hbits2, (uint64_t)((lo >> p.i1) & m2) | ((uint64_t)((hi >> p.i1) & m2) << p.i2));
+    if (a != 0xFFFFFFFFu && b != 0xFFFFFFFFu) {
+        atomicAdd(&p.hop_fwd[(uint64_t)a * p.u2 + b], 1ull);
+        return;
+    }
+    // reversed orientation: index1 key in barcode[i2..], index2 key in barcode[..i2]
+    const uint32_t c1 = ph_hop_find(sm.hop1, c.hbits1, (uint64_t)((lo >> p.i2) & m1) | ((uint64_t)((hi >> p.i2) & m1) << p.i1));
+    if (c1 == 0xFFFFFFFFu) return;
+    const uint32_t d2 = ph_hop_find(sm.hop2, c.hbits2, (uint64_t)(lo & m2) | ((uint64_t)(hi & m2) << p.i2));
+    if (d2 != 0xFFFFFFFFu) atomicAdd(&p.hop_rev[(uint64_t)c1 * p.u2 + d2], 1ull);
+}
+
+// the perfect-hash probe of one record without invalid positions: entry (sample or S) and distance to it.
+// prow = this lane's copy of the planes table.
+__device__ __forceinline__ void ph_probe(const PhSmem &sm, const PhParams &c, const uint2 *prow, uint32_t w0, uint32_t w1,
+                                         uint32_t &e, uint32_t &d) {
     const uint32_t h = __umulhi(w0, c.k0) + w0 * c.k1 + w1 * c.k2;
     const uint32_t mul = sm.disp[h >> c.bshift];
     e = sm.slots[(h * mul) >> c.sshift];
-    const uint2 t = sm.planes[e];
+    const uint2 t = prow[e << c.clog];
     const uint32_t lo = w0 & kCompactMask;
     const uint32_t hi = __funnelshift_r(w0, w1, kCompactField);  // bits 21..52 of the record; 42..52 are zero here
     d = (uint32_t)__popc((lo ^ t.x) | (hi ^ t.y));
@@ -75,40 +127,52 @@ __device__ __forceinline__ void ph_emit(const DevParams &p, uint32_t *hist, uint
     if (p.hop_on && v.bin == p.S) hop_check(p, rd);
 }
 
-template <uint32_t MODE>
+// VEC: every chunk is full and the three buffers are aligned for 256 / 64 / 32-bit accesses (lane i owns reads
+// 4i..4i+3 of a chunk).  !VEC: any alignment, ragged end (lane i owns reads i, i+32, i+64, i+96).
+template <uint32_t MODE, bool VEC>
 __global__ void __launch_bounds__(kPhThreads, 1) sgdx_match_ph(const DevParams p, const PhParams c) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     PhSmem sm;
     const uint32_t bbits = 32u - c.bshift, sbits = 32u - c.sshift;
-    ph_carve(smem_raw, p.S, bbits, sbits, &sm);
-    const uint32_t S1 = p.S + 1u, nbins = S1 * 3u;
+    ph_carve(smem_raw, p.S, bbits, sbits, c.clog, c.hbits1, c.hbits2, &sm);
+    const uint32_t S1 = p.S + 1u, nbins = S1 * 3u, trash = nbins;
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t ncopies = 1u << c.clog;
 
     for (uint32_t i = threadIdx.x; i < (1u << bbits); i += kPhThreads) sm.disp[i] = c.disp[i];
     for (uint32_t i = threadIdx.x; i < (1u << sbits); i += kPhThreads) sm.slots[i] = c.slots[i];
-    for (uint32_t i = threadIdx.x; i < p.S; i += kPhThreads) sm.planes[i] = p.table[i];
-    if (threadIdx.x == 0) sm.planes[p.S] = make_uint2(0u, 0xFFFFFFFFu);  // >= 11 mismatches against any valid record
-    for (uint32_t i = threadIdx.x; i < nbins; i += kPhThreads) sm.hist[i] = 0u;
+    for (uint32_t i = threadIdx.x; i < (S1 << c.clog); i += kPhThreads) {
+        const uint32_t s = i >> c.clog;  // the dummy row is >= 11 mismatches away from any valid record
+        sm.planes[i] = s < p.S ? p.table[s] : make_uint2(0u, 0xFFFFFFFFu);
+    }
+    for (uint32_t i = threadIdx.x; i <= nbins; i += kPhThreads) sm.hist[i] = 0u;
+    if (c.hbits1) {
+        for (uint32_t i = threadIdx.x; i < (1u << c.hbits1); i += kPhThreads) sm.hop1[i] = c.hop1[i];
+        for (uint32_t i = threadIdx.x; i < (1u << c.hbits2); i += kPhThreads) sm.hop2[i] = c.hop2[i];
+    }
     __syncthreads();
 
-    uint64_t *const qh = sm.qhop + warp * kPhQueue;
-    uint32_t *const qs = sm.qslow + warp * kPhQueue;
-    uint32_t nh = 0u, ns = 0u;  // queue fills, warp-uniform
+    uint64_t *const qrec = sm.qrec + warp * kPhQueue;
+    uint32_t *const qoff = sm.qoff + warp * kPhQueue;
+    uint64_t *const q2rec = sm.q2rec + warp * kPhQueue2;
+    uint32_t *const q2off = sm.q2off + warp * kPhQueue2;
+    const uint2 *const prow = sm.planes + (lane & (ncopies - 1u));
+    uint32_t n1 = 0u, n2 = 0u;  // queue fills, warp-uniform
     const uint64_t total_warps = (uint64_t)gridDim.x * kPhWarps, gwarp = (uint64_t)blockIdx.x * kPhWarps + warp;
     const uint64_t nchunks = (p.n + kPhChunk - 1u) / kPhChunk;
+    const uint32_t below = (1u << lane) - 1u;
+    const uint32_t off0 = VEC ? lane * 4u : lane, offk = VEC ? 1u : 32u;  // chunk offset of my read k = off0 + k * offk
 
-    // records of chunk `ch` into r[0..3]; out-of-range reads become all-ones records (they look invalid, so nothing
-    // counts them, and `live` keeps them out of the queues)
     auto fetch = [&](uint64_t ch, uint64_t (&r)[4]) {
         if (ch >= nchunks) return;
         const uint64_t base = ch * kPhChunk;
-        if (c.vec && base + kPhChunk <= p.n) {
-            const uint64_t *src = c.reads + base + lane * 4u;
+        if (VEC) {
+            const uint64_t *src = c.reads + base + off0;
             asm volatile("ld.global.nc.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4];"
                          : "=l"(r[0]), "=l"(r[1]), "=l"(r[2]), "=l"(r[3]) : "l"(src));
         } else {
 #pragma unroll
-            for (uint32_t k = 0; k < 4; k++) {
+            for (uint32_t k = 0; k < 4; k++) {  // out-of-range reads become all-ones records: they look invalid
                 const uint64_t i = base + k * 32u + lane;
                 r[k] = i < p.n ? __ldg(c.reads + i) : ~0ull;
             }
@@ -123,31 +187,46 @@ __global__ void __launch_bounds__(kPhThreads, 1) sgdx_match_ph(const DevParams p
         if (!final) {
             fetch(ch + total_warps, nextrec);
             const uint64_t base = ch * kPhChunk;
-            const bool packed4 = c.vec && base + kPhChunk <= p.n;  // lane owns 4 consecutive reads
-            uint32_t bin[4], dist[4], cnt = 0u, flags = 0u;
+            // four reads per lane, phase by phase, so that the four dependent shared-memory chains overlap
+            uint32_t bin[4], dist[4], h[4], e[4];
+            uint2 t[4];
+            bool stray[4], dk[4];
 #pragma unroll
             for (uint32_t k = 0; k < 4; k++) {
                 const uint32_t w0 = (uint32_t)rec[k], w1 = (uint32_t)(rec[k] >> 32);
-                const bool slow = ((w0 & c.nm0) | (w1 & c.nm1)) != 0u;
-                uint32_t e, d;
-                ph_probe(sm, c, w0, w1, e, d);
-                const bool ok = d <= p.M && !slow;
-                bin[k] = ok ? e : p.S;
-                dist[k] = ok ? d : kNoDist;
-#ifndef SGDX_PH_X_NOHIST  // (experiment builds only, tools/build_variants.sh: what the histogram costs)
-                if (!slow) atomicAdd(&sm.hist[min(dist[k], 2u) * S1 + bin[k]], 1u);
-#endif
-                const bool live = packed4 || base + k * 32u + lane < p.n;
-                const bool hopq = !slow && !ok && p.hop_on != 0u;
-                const bool slowq = slow && live;
-                cnt += (hopq ? 1u : 0u) + (slowq ? 0x10000u : 0u);
-                flags |= ((hopq ? 1u : 0u) | (slowq ? 16u : 0u)) << k;
+                stray[k] = ((w0 & c.nm0) | (w1 & c.nm1)) != 0u;  // not "barcode_len A/C/G/T bases"
+                h[k] = __umulhi(w0, c.k0) + w0 * c.k1 + w1 * c.k2;
+                e[k] = sm.disp[h[k] >> c.bshift];
             }
-            // results: a read of the general path gets "Undetermined / no distance" now and is patched by the drain
-            if (packed4) {
-                const uint64_t at = base + lane * 4u;
-                const uint2 v = make_uint2(bin[0] | (bin[1] << 16), bin[2] | (bin[3] << 16));
-                *reinterpret_cast<uint2 *>(p.out_idx + at) = v;
+#pragma unroll
+            for (uint32_t k = 0; k < 4; k++) e[k] = sm.slots[(h[k] * e[k]) >> c.sshift];
+#pragma unroll
+            for (uint32_t k = 0; k < 4; k++) t[k] = prow[e[k] << c.clog];
+#pragma unroll
+            for (uint32_t k = 0; k < 4; k++) {
+                const uint32_t w0 = (uint32_t)rec[k], w1 = (uint32_t)(rec[k] >> 32);
+                const uint32_t lo = w0 & kCompactMask;
+                const uint32_t hi = __funnelshift_r(w0, w1, kCompactField);  // bits 21..52; 42..52 are zero unless stray
+                const uint32_t d = (uint32_t)__popc((lo ^ t[k].x) | (hi ^ t[k].y));
+                const bool bad = d > p.M || stray[k];
+                bin[k] = bad ? p.S : e[k];
+                dist[k] = bad ? kNoDist : d;
+                uint32_t hidx = min(dist[k], 2u) * S1 + bin[k];
+                hidx = stray[k] ? trash : hidx;  // the general path counts its reads itself
+#ifndef SGDX_PH_X_NOHIST  // (experiment builds only, tools/build_variants.sh: what the histogram costs)
+                atomicAdd(&sm.hist[hidx], 1u);
+#endif
+                // deferred: the hop check of a NoMatch read, or the whole read if it is not plain A/C/G/T
+                dk[k] = p.hop_on ? bad : stray[k];
+                if (!VEC) dk[k] = dk[k] && base + k * 32u + lane < p.n;
+#ifdef SGDX_PH_X_NOQ  // (experiment builds only: what the deferred reads cost)
+                dk[k] = false;
+#endif
+            }
+            // results: a read of the general path gets "Undetermined / no distance" now and is patched later
+            if (VEC) {
+                const uint64_t at = base + off0;
+                *reinterpret_cast<uint2 *>(p.out_idx + at) = make_uint2(bin[0] | (bin[1] << 16), bin[2] | (bin[3] << 16));
                 if (p.out_dist)
                     *reinterpret_cast<uint32_t *>(p.out_dist + at) = dist[0] | (dist[1] << 8) | (dist[2] << 16) | (dist[3] << 24);
             } else {
@@ -160,93 +239,106 @@ __global__ void __launch_bounds__(kPhThreads, 1) sgdx_match_ph(const DevParams p
                     }
                 }
             }
-            // deferred reads -> the warp's queues: one packed inclusive scan gives both write positions
-#ifdef SGDX_PH_X_NOQ  // (experiment builds only: what the deferred reads cost)
-            cnt = 0u;
-#endif
-            if (__any_sync(0xFFFFFFFFu, cnt != 0u)) {
-                uint32_t incl = cnt;
-#pragma unroll
-                for (uint32_t o = 1; o < 32; o <<= 1) {
-                    const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-                    if (lane >= o) incl += t;
-                }
-                const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
-                uint32_t ph = nh + ((incl - cnt) & 0xFFFFu), ps = ns + ((incl - cnt) >> 16);
+            if (__any_sync(0xFFFFFFFFu, dk[0] || dk[1] || dk[2] || dk[3])) {
 #pragma unroll
                 for (uint32_t k = 0; k < 4; k++) {
-                    if ((flags >> k) & 1u) qh[ph++] = rec[k];
-                    if ((flags >> (k + 4u)) & 1u) qs[ps++] = iter * kPhChunk + (packed4 ? lane * 4u + k : k * 32u + lane);
+                    const bool mine = dk[k];
+                    const uint32_t votes = __ballot_sync(0xFFFFFFFFu, mine);
+                    if (mine) {
+                        const uint32_t at = n1 + (uint32_t)__popc(votes & below);
+                        qrec[at] = rec[k];
+                        qoff[at] = iter * kPhChunk + off0 + k * offk;
+                    }
+                    n1 += (uint32_t)__popc(votes);
                 }
-                nh += total & 0xFFFFu;
-                ns += total >> 16;
                 __syncwarp();
             }
 #pragma unroll
             for (uint32_t k = 0; k < 4; k++) rec[k] = nextrec[k];
         }
 
-        // ---- hop check of queued NoMatch reads (metrics.rs:658-676), 32 at a time
-        while (nh >= 32u || (final && nh)) {
-            const uint32_t take = min(nh, 32u);
-            nh -= take;
+        // ---- deferred reads, 32 at a time: hop check of the A/C/G/T-only NoMatch reads (metrics.rs:658-676); the
+        // others move on to the second queue
+        while (n1 >= 32u || (final && (n1 | n2))) {
+            const uint32_t take = min(n1, 32u);  // 0 when only the second queue is left to flush
+            n1 -= take;
+            bool general = false;
+            uint64_t q = 0ull;
+            uint32_t off = 0u;
             if (lane < take) {
-                const uint64_t q = qh[nh + lane];
-                Rd rd;
-                rd.lo = (uint32_t)q & kCompactMask;
-                rd.hi = (uint32_t)(q >> kCompactField) & kCompactMask;
-                rd.nmask = rd.xmask = 0u;
-                hop_check(p, rd);
-            }
-            __syncwarp();
-        }
-
-        // ---- general path: reads with invalid positions or stray bits
-        while (ns >= 32u || (final && ns)) {
-            const uint32_t take = min(ns, 32u);
-            ns -= take;
-            bool scan = false;
-            uint64_t r = 0;
-            if (lane < take) {
-                const uint32_t e = qs[ns + lane];
-                r = ((uint64_t)(e / kPhChunk) * total_warps + gwarp) * kPhChunk + (e % kPhChunk);
-                const Rd rd = rd_of_compact(__ldg(c.reads + r), c.lmask);
-                const uint32_t inv = rd.nmask | rd.xmask;
-                uint32_t best = kInfKey, nxt = kInfKey;
-                if (!cannot_match<MODE>(p, rd)) {
-                    if (inv == 0u || (c.single_ok && (inv & (inv - 1u)) == 0u)) {
-                        // no invalid base (the record only had stray bits): its own key.  One invalid base: the unique
-                        // sample within M over the valid positions, if any, is the entry of one of the 4 completions;
-                        // whatever else the probes return is a real sample scored at its real distance
-                        const uint32_t skip = (MODE == kModePreCompute && rd.nmask != 0u) ? p.M + 1u : 0xFFFFu;
-                        const uint32_t nvar = inv ? 4u : 1u;
-                        for (uint32_t b = 0; b < nvar; b++) {
-                            const uint32_t lo = rd.lo | ((b & 1u) ? inv : 0u), hi = rd.hi | ((b >> 1) ? inv : 0u);
-                            const uint64_t key = (uint64_t)lo | ((uint64_t)hi << kCompactField);
-                            uint32_t pe, pd;
-                            ph_probe(sm, c, (uint32_t)key, (uint32_t)(key >> 32), pe, pd);
-                            if (pe < p.S) {
-                                const uint2 t = sm.planes[pe];
-                                score<MODE>(rd, inv, skip, t.x, t.y, pe, best, nxt);
-                            }
-                        }
-                    } else if (p.seed_C == 0u || !seed_search<MODE, true>(p, p.seed_hdr, p.seed_ids, sm.planes, rd, best, nxt)) {
-                        scan = true;
+                q = qrec[n1 + lane];
+                off = qoff[n1 + lane];
+                const uint32_t w0 = (uint32_t)q, w1 = (uint32_t)(q >> 32);
+                general = ((w0 & c.nm0) | (w1 & c.nm1)) != 0u;
+                if (!general) {
+                    const uint32_t lo = w0 & kCompactMask, hi = __funnelshift_r(w0, w1, kCompactField) & kCompactMask;
+                    if (c.hbits1) {
+                        ph_hop_check(p, c, sm, lo, hi);
+                    } else {
+                        const Rd rd = {lo, hi, 0u, 0u};
+                        hop_check(p, rd);
                     }
                 }
-                if (!scan) ph_emit(p, sm.hist, S1, r, rd, apply_rules<MODE>(p, rd, best, nxt));
             }
-            // whatever the seed index cannot enumerate: one warp per read over all samples
-            uint32_t todo = __ballot_sync(0xFFFFFFFFu, scan);
-            while (todo) {
-                const uint32_t src = (uint32_t)__ffs(todo) - 1u;
-                todo &= todo - 1u;
-                const uint64_t qr = __shfl_sync(0xFFFFFFFFu, r, src);
-                const Rd qrd = rd_of_compact(__ldg(c.reads + qr), c.lmask);
-                const Verdict qv = warp_scan<MODE>(p, sm.planes, qrd, lane);
-                if (lane == 0u) ph_emit(p, sm.hist, S1, qr, qrd, qv);
+            const uint32_t votes = __ballot_sync(0xFFFFFFFFu, general);
+            if (general) {
+                const uint32_t at = n2 + (uint32_t)__popc(votes & below);
+                q2rec[at] = q;
+                q2off[at] = off;
             }
+            n2 += (uint32_t)__popc(votes);
             __syncwarp();
+
+            // ---- general path: reads with invalid positions or stray bits
+            while (n2 >= 32u || (final && n1 == 0u && n2)) {
+                const uint32_t take2 = min(n2, 32u);
+                n2 -= take2;
+                bool scan = false;
+                uint64_t r = 0;
+                if (lane < take2) {
+                    const uint32_t e = q2off[n2 + lane];
+                    r = ((uint64_t)(e / kPhChunk) * total_warps + gwarp) * kPhChunk + (e % kPhChunk);
+                    const Rd rd = rd_of_compact(q2rec[n2 + lane], c.lmask);
+                    const uint32_t inv = rd.nmask | rd.xmask;
+                    uint32_t best = kInfKey, nxt = kInfKey;
+                    if (!cannot_match<MODE>(p, rd)) {
+                        if (inv == 0u || (c.single_ok && (inv & (inv - 1u)) == 0u)) {
+                            // no invalid base (the record only had stray bits): its own key.  One invalid base: the
+                            // unique sample within M over the valid positions, if any, is the entry of one of the 4
+                            // completions; whatever else the probes return is a real sample scored at its real distance
+                            const uint32_t skip = (MODE == kModePreCompute && rd.nmask != 0u) ? p.M + 1u : 0xFFFFu;
+                            const uint32_t nvar = inv ? 4u : 1u;
+                            for (uint32_t b = 0; b < nvar; b++) {
+                                const uint32_t lo = rd.lo | ((b & 1u) ? inv : 0u), hi = rd.hi | ((b >> 1) ? inv : 0u);
+                                const uint64_t key = (uint64_t)lo | ((uint64_t)hi << kCompactField);
+                                uint32_t pe, pd;
+                                ph_probe(sm, c, prow, (uint32_t)key, (uint32_t)(key >> 32), pe, pd);
+                                if (pe < p.S) {
+                                    const uint2 t = prow[pe << c.clog];
+                                    score<MODE>(rd, inv, skip, t.x, t.y, pe, best, nxt);
+                                }
+                            }
+                        } else if (c.single_ok || p.seed_C == 0u ||
+                                   !seed_search<MODE, true>(p, p.seed_hdr, p.seed_ids, p.table, rd, best, nxt)) {
+                            // with the shortcut valid only reads with several invalid bases get here: too few to be
+                            // worth a chain of dependent global loads at one or two active lanes
+                            scan = true;
+                        }
+                    }
+                    if (!scan) ph_emit(p, sm.hist, S1, r, rd, apply_rules<MODE>(p, rd, best, nxt));
+                }
+                // whatever the seed index cannot enumerate: one warp per read over all samples
+                uint32_t todo = __ballot_sync(0xFFFFFFFFu, scan);
+                while (todo) {
+                    const uint32_t src = (uint32_t)__ffs(todo) - 1u;
+                    todo &= todo - 1u;
+                    const uint64_t qr = __shfl_sync(0xFFFFFFFFu, r, src);
+                    const Rd qrd = rd_of_compact(__ldg(c.reads + qr), c.lmask);
+                    const Verdict qv = warp_scan<MODE>(p, p.table, qrd, lane);
+                    if (lane == 0u) ph_emit(p, sm.hist, S1, qr, qrd, qv);
+                }
+                __syncwarp();
+            }
         }
         if (final) break;
     }
@@ -254,24 +346,47 @@ __global__ void __launch_bounds__(kPhThreads, 1) sgdx_match_ph(const DevParams p
     __syncthreads();
     for (uint32_t i = threadIdx.x; i < nbins; i += kPhThreads) {
         const uint32_t cnt = sm.hist[i];
-        if (cnt) {  // hist is [class][bin] with class 0 perfect, 1 one mismatch, 2 other; counters are [bin][other, perfect, one]
+        if (cnt) {  // hist is [class][bin], class 0 perfect, 1 one mismatch, 2 other; counters are [bin][other, perfect, one]
             const uint32_t cls = i / S1, b = i % S1;
             atomicAdd(&p.counters[b * 3u + (cls == 2u ? 0u : cls + 1u)], (unsigned long long)cnt);
         }
     }
 }
 
-cudaError_t launch_ph(const DevParams &p, const PhParams &c, uint32_t mode, int sms, cudaStream_t stream) {
+template <uint32_t MODE, bool VEC>
+static cudaError_t launch_ph_t(const DevParams &p, const PhParams &c, int sms, cudaStream_t stream) {
     if (p.n == 0) return cudaSuccess;
-    const size_t smem = ph_smem_bytes(p.S, 32u - c.bshift, 32u - c.sshift);
-    auto kern = mode == kModeHamming ? sgdx_match_ph<kModeHamming> : sgdx_match_ph<kModePreCompute>;
+    const size_t smem = ph_carve(nullptr, p.S, 32u - c.bshift, 32u - c.sshift, c.clog, c.hbits1, c.hbits2, nullptr);
+    auto kern = sgdx_match_ph<MODE, VEC>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    const uint64_t chunks = (p.n + kPhChunk - 1u) / kPhChunk, per_cta = kPhWarps;
-    uint64_t grid = (chunks + per_cta - 1u) / per_cta;
+    const uint64_t chunks = (p.n + kPhChunk - 1u) / kPhChunk;
+    uint64_t grid = (chunks + kPhWarps - 1u) / kPhWarps;
     if (grid > (uint64_t)sms) grid = (uint64_t)sms;  // one persistent CTA per SM
     kern<<<(uint32_t)grid, kPhThreads, smem, stream>>>(p, c);
     return cudaGetLastError();
+}
+
+// Aligned buffers: the full chunks go through the vector kernel and the last n % 128 reads through the general one
+// (a second, one-CTA launch); anything else through the general one.
+cudaError_t launch_ph(const DevParams &p0, const PhParams &c0, uint32_t mode, int sms, cudaStream_t stream) {
+    DevParams p = p0;
+    PhParams c = c0;
+    ph_fit(p.S, c);
+    const bool ham = mode == kModeHamming;
+    const bool aligned = (reinterpret_cast<uintptr_t>(c.reads) & 31u) == 0u && (reinterpret_cast<uintptr_t>(p.out_idx) & 7u) == 0u &&
+                         (reinterpret_cast<uintptr_t>(p.out_dist) & 3u) == 0u;
+    if (aligned) {
+        const uint64_t n_main = p.n & ~(uint64_t)(kPhChunk - 1u);
+        p.n = n_main;
+        cudaError_t e = ham ? launch_ph_t<kModeHamming, true>(p, c, sms, stream) : launch_ph_t<kModePreCompute, true>(p, c, sms, stream);
+        if (e != cudaSuccess) return e;
+        p.n = p0.n - n_main;
+        c.reads += n_main;
+        p.out_idx += n_main;
+        if (p.out_dist) p.out_dist += n_main;
+    }
+    return ham ? launch_ph_t<kModeHamming, false>(p, c, sms, stream) : launch_ph_t<kModePreCompute, false>(p, c, sms, stream);
 }
 
 }  // namespace sgdx

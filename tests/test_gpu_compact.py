@@ -1,5 +1,5 @@
 """GPU parity of the compact-record path (include/sgdx.h: sgdx_pack_compact_host / _device,
-sgdx_match_compact_batch / _device; kernel sgdx_match_compact) against the CPU oracle and against the ASCII
+sgdx_match_compact_batch / _device; kernel sgdx_match_ph, or the general kernels on expanded records) against the CPU oracle and against the ASCII
 path, bit-exact on index, distance, per-sample counters, total_templates and the hop map."""
 import ctypes as C
 import os
@@ -15,7 +15,7 @@ pytestmark = pytest.mark.gpu
 
 ORC_KIND = {sg.MatcherKind.CachedHammingDistance: orc.MATCHER_CACHED_HAMMING, sg.MatcherKind.PreCompute: orc.MATCHER_PRECOMPUTE}
 CLS = {sg.MatcherKind.CachedHammingDistance: sg.CachedHammingDistanceMatcher, sg.MatcherKind.PreCompute: sg.PreComputeMatcher}
-PATH_COMPACT = 16
+PATH_PH = 64
 
 
 def _samples(table):
@@ -67,7 +67,7 @@ PARAMS = [(1, 2, 1, None), (0, 0, 0, None), (2, 1, 2, 1), (3, 1, 1, 0), (1, 0, 0
 @pytest.mark.parametrize("S,L,i1", [(1, 8, 0), (2, 4, 2), (7, 12, 0), (96, 16, 8), (97, 20, 10), (384, 20, 10),
                                     (200, 21, 10), (33, 13, 5), (64, 6, 3), (3, 1, 0)])
 def test_compact_path_matches_oracle_on_random_tables(S, L, i1):
-    """Fast kernel where the table allows the exact-match shortcut, 16-byte general path elsewhere: both through
+    """Perfect-hash kernel where the table's match neighbourhood is small enough, 16-byte general path elsewhere: both through
     sgdx_match_compact_batch, both rule sets, N-heavy and foreign bytes included."""
     rng = np.random.default_rng(S * 977 + L)
     w, table, reads = _random_case(rng, S, L, i1)
@@ -76,13 +76,13 @@ def test_compact_path_matches_oracle_on_random_tables(S, L, i1):
     for kind in (sg.MatcherKind.CachedHammingDistance, sg.MatcherKind.PreCompute):
         for (M, D, F, mnc) in PARAMS:
             st = _stage(table, kind, M, D, F, mnc, il)
-            fast += bool(st.matcher.path_flags() & PATH_COMPACT)
+            fast += bool(st.matcher.path_flags() & PATH_PH)
             got = st.demultiplex(reads, compact=True, pack_threads=2)
             want = _oracle(table, kind, M, D, F, mnc, il, reads)
             _assert_same(st, got, want, reads.shape[0])
             st.close()
     if (S, L) in ((96, 16), (384, 20), (200, 21)):
-        assert fast > 0, "the compact fast kernel never engaged on a well separated table"
+        assert fast > 0, "the perfect-hash kernel never engaged on a table it should serve"
 
 
 @pytest.mark.parametrize("L", [1, 7, 8, 16, 19, 20, 21])
@@ -115,7 +115,7 @@ def test_baseline_tables_take_the_compact_kernel_and_equal_the_ascii_path(cfg):
     for mode in ("ascii", "compact"):
         st = _stage(table, sg.MatcherKind.CachedHammingDistance, w.max_mismatches, w.min_delta, w.free_ns, None, w.index_lengths)
         m = st.matcher
-        assert m.path_flags() & PATH_COMPACT
+        assert m.path_flags() & PATH_PH
         d_in = torch.from_numpy(reads).cuda()
         d_idx = torch.empty(n, dtype=torch.int16, device="cuda")
         d_dist = torch.empty(n, dtype=torch.uint8, device="cuda")

@@ -161,8 +161,8 @@ def test_baseline_tables_take_every_fast_path(cfg):
         want |= _lib.PATH_NEIGHBOURS
     if max(w.index_lengths) <= 11:
         want |= _lib.PATH_HOP_DIRECT
-    if w.barcode_len <= _lib.COMPACT_MAX_LEN:  # compact records, and dmin = 6 > 2 * 1 + 2: the short seed index too
-        want |= _lib.PATH_COMPACT | _lib.PATH_SHORT_SEED
+    if w.barcode_len <= _lib.COMPACT_MAX_LEN:  # compact records: the perfect hash of the match neighbourhood
+        want |= _lib.PATH_PERFECT_HASH
     assert m.path_flags() == want and m.kernel_name() == "sgdx_match_exact_first"
     m.close()
 

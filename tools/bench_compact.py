@@ -83,7 +83,7 @@ def measure(**kw):
         return sum(ms) / len(ms), min(ms)
 
     out = {"workload": f"{args.config} {S}x{L}, {n} reads, 1 B200", "hbm_peak_gbs": peak, "steps": args.steps,
-           "path_flags": m.path_flags(), "compact_fast_kernel": bool(m.path_flags() & 16)}
+           "path_flags": m.path_flags(), "perfect_hash_kernel": bool(m.path_flags() & 64)}
     a_avg, a_best = timed(lambda: m.match_device(d_in.data_ptr(), n, d_idx.data_ptr(), d_dist.data_ptr()))
     c_avg, c_best = timed(lambda: m.match_compact_device(d_rec.data_ptr(), n, d_idx_c.data_ptr(), d_dist_c.data_ptr()))
     torch.cuda.synchronize()
