@@ -261,31 +261,35 @@ static int build_ph_table(sgdx_handle *h, const std::vector<uint2> &table) {
     h->ph.single_ok = t.single_ok;
     h->ph_keys = t.nkeys;
     if (p.hop_on) {
-        // hop key sets for the kernel's shared memory (PhParams::hop1/hop2): the distinct halves without the all-N
-        // ones of Undetermined (a read with a no-call takes the general path and the global tables)
-        auto build = [&](const std::vector<std::string> &keys, uint32_t len, uint64_t **d_out, uint32_t *bits_out) -> int {
-            uint32_t bits = 4;
-            while ((1u << bits) * 2u < keys.size() * 5u) bits++;  // load factor <= 0.4
-            std::vector<uint64_t> tab((size_t)1 << bits, 0ull);
-            const uint32_t mask = (1u << bits) - 1u;
-            for (uint32_t id = 0; id < keys.size(); id++) {
-                if (keys[id].find('N') != std::string::npos) continue;
+        // hop key sets for the kernel's shared memory (PhParams::hop_*): the distinct halves without the all-N ones of
+        // Undetermined (a read with a no-call takes the general path and the global tables)
+        std::vector<uint64_t> k1, k2;
+        std::vector<uint32_t> id1, id2;
+        auto collect = [](const std::vector<std::string> &keys, uint32_t len, std::vector<uint64_t> &k, std::vector<uint32_t> &id) {
+            for (uint32_t i = 0; i < keys.size(); i++) {
+                if (keys[i].find('N') != std::string::npos) continue;
                 uint32_t lo, hi;
-                encode_planes(reinterpret_cast<const uint8_t *>(keys[id].data()), len, &lo, &hi);
-                const uint64_t key = (uint64_t)lo | ((uint64_t)hi << len);
-                uint32_t i = (((uint32_t)key * 0x9E3779B1u) ^ ((uint32_t)(key >> 32) * 0x85EBCA77u)) >> (32u - bits);
-                while (tab[i]) i = (i + 1u) & mask;
-                tab[i] = key | ((uint64_t)(id + 1u) << 42);
+                encode_planes(reinterpret_cast<const uint8_t *>(keys[i].data()), len, &lo, &hi);
+                k.push_back((uint64_t)lo | ((uint64_t)hi << len));
+                id.push_back(i);
             }
-            CU(cudaMalloc(d_out, tab.size() * sizeof(uint64_t)));
-            CU(cudaMemcpy(*d_out, tab.data(), tab.size() * sizeof(uint64_t), cudaMemcpyHostToDevice));
-            *bits_out = bits;
-            return SGDX_OK;
         };
-        if (int rc = build(h->keys1, p.i1, &h->d_ph_hop1, &h->ph.hbits1)) return rc;
-        if (int rc = build(h->keys2, p.i2, &h->d_ph_hop2, &h->ph.hbits2)) return rc;
-        h->ph.hop1 = h->d_ph_hop1;
-        h->ph.hop2 = h->d_ph_hop2;
+        collect(h->keys1, p.i1, k1, id1);
+        collect(h->keys2, p.i2, k2, id2);
+        PhHopTables ht;
+        if (ph_build_hop(k1, id1, k2, id2, &ht)) {
+            CU(cudaMalloc(&h->d_ph_hop_slots, ht.slots.size() * sizeof(uint64_t)));
+            CU(cudaMalloc(&h->d_ph_hop_disp, ht.disp.size() * sizeof(uint16_t)));
+            CU(cudaMemcpy(h->d_ph_hop_slots, ht.slots.data(), ht.slots.size() * sizeof(uint64_t), cudaMemcpyHostToDevice));
+            CU(cudaMemcpy(h->d_ph_hop_disp, ht.disp.data(), ht.disp.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+            h->ph.hop_slots = h->d_ph_hop_slots;
+            h->ph.hop_disp = h->d_ph_hop_disp;
+            h->ph.hop_bshift = ht.bshift;
+            h->ph.hop_sshift = ht.sshift;
+            h->ph.hop_k0 = ht.k0;
+            h->ph.hop_k1 = ht.k1;
+            h->ph.hop_k2 = ht.k2;
+        }
     }
     return SGDX_OK;
 }
@@ -480,8 +484,8 @@ extern "C" void sgdx_destroy(sgdx_handle *h) {
     cudaFree(h->d_nb_slots);
     cudaFree(h->d_ph_disp);
     cudaFree(h->d_ph_slots);
-    cudaFree(h->d_ph_hop1);
-    cudaFree(h->d_ph_hop2);
+    cudaFree(h->d_ph_hop_slots);
+    cudaFree(h->d_ph_hop_disp);
     cudaFree(h->d_hash1);
     cudaFree(h->d_hash2);
     cudaFree(h->d_hop_lut1);

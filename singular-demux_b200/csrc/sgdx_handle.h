@@ -82,7 +82,8 @@ struct sgdx_handle {
     uint16_t *d_seed_ids = nullptr;
     uint32_t *d_ex_slots = nullptr, *d_ex_ascii = nullptr, *d_nb_slots = nullptr;
     bool seeded = false;  // launches use sgdx_match_seeded
-    uint64_t *d_ph_hop1 = nullptr, *d_ph_hop2 = nullptr;
+    uint64_t *d_ph_hop_slots = nullptr;
+    uint16_t *d_ph_hop_disp = nullptr;
     uint16_t *d_ph_disp = nullptr, *d_ph_slots = nullptr;  // perfect-hash kernel (sgdx_ph.cu); ph.slots == nullptr: not available
     sgdx::PhParams ph{};
     uint32_t ph_keys = 0;

@@ -45,11 +45,14 @@ struct PhParams {
     uint32_t lmask;         // (1 << barcode_len) - 1
     uint32_t single_ok;     // min pairwise table distance > 2M + delta + 1: a read with ONE invalid base is decided by
                             // the unique sample within M over its valid positions, found by probing its 4 completions
-    // hop key sets for shared memory (optional; hbits == 0: the kernel uses the global tables of DevParams): open
-    // addressing over the distinct index1 / index2 halves without Undetermined's all-N halves,
-    // entry = key | (dense id + 1) << 42, key = lo bits | hi bits << half length, 0 = empty
-    const uint64_t *hop1, *hop2;
-    uint32_t hbits1, hbits2;
+    // hop key sets for shared memory (optional; hop_slots == nullptr: the kernel uses the global tables of DevParams):
+    // one perfect hash of the same construction over the distinct index1 / index2 halves (without Undetermined's
+    // all-N halves): key = lo bits | hi bits << half length | which << 41 (0: index1 half, 1: index2 half),
+    // slot = key | (dense id + 1) << 42, 0 = empty
+    const uint16_t *hop_disp;
+    const uint64_t *hop_slots;
+    uint32_t hop_bshift, hop_sshift, hop_k0, hop_k1, hop_k2;
+    uint32_t hop_smem;      // per launch: 1 = the hop tables are in shared memory
     uint32_t clog;          // per launch: log2 of the copies of the planes table in shared memory
 };
 size_t ph_smem_bytes(uint32_t S, uint32_t bbits, uint32_t sbits);

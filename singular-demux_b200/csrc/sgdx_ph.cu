@@ -35,8 +35,8 @@ struct PhSmem {
     uint32_t *qoff;   // [warps][kPhQueue] ... and (warp iteration * 128 + offset in chunk)
     uint64_t *q2rec;  // [warps][kPhQueue2] the deferred reads that need the general path ...
     uint32_t *q2off;  // [warps][kPhQueue2] ... same numbering
-    uint64_t *hop1;   // [1 << hbits1] index1 halves of the expected barcodes (open addressing), optional
-    uint64_t *hop2;   // [1 << hbits2] index2 halves
+    uint64_t *hslots; // hop key sets (PhParams::hop_slots), optional
+    uint16_t *hdisp;
     uint2 *planes;    // [S + 1][copies]: barcode planes, replicated so that the lanes of a half warp read distinct banks;
                       //                  row S = dummy that nothing matches
     uint32_t *hist;   // [3][S + 1] perfect, one mismatch, other (metrics.rs:428-437), + 1 word nobody reads
@@ -45,19 +45,19 @@ struct PhSmem {
 };
 
 __host__ __device__ inline size_t ph_carve(unsigned char *base, uint32_t S, uint32_t bbits, uint32_t sbits, uint32_t clog,
-                                           uint32_t hbits1, uint32_t hbits2, PhSmem *out) {
+                                           uint32_t hsbits, uint32_t hbbits, PhSmem *out) {  // hsbits == 0: no hop tables
     size_t o = 0;
     PhSmem s;
     s.qrec = reinterpret_cast<uint64_t *>(base + o);   o += (size_t)kPhWarps * kPhQueue * 8;
     s.q2rec = reinterpret_cast<uint64_t *>(base + o);  o += (size_t)kPhWarps * kPhQueue2 * 8;
-    s.hop1 = reinterpret_cast<uint64_t *>(base + o);   o += hbits1 ? (size_t)8 << hbits1 : 0;
-    s.hop2 = reinterpret_cast<uint64_t *>(base + o);   o += hbits2 ? (size_t)8 << hbits2 : 0;
+    s.hslots = reinterpret_cast<uint64_t *>(base + o); o += hsbits ? (size_t)8 << hsbits : 0;
     s.planes = reinterpret_cast<uint2 *>(base + o);    o += (((size_t)S + 1) * 8) << clog;
     s.qoff = reinterpret_cast<uint32_t *>(base + o);   o += (size_t)kPhWarps * kPhQueue * 4;
     s.q2off = reinterpret_cast<uint32_t *>(base + o);  o += (size_t)kPhWarps * kPhQueue2 * 4;
     s.hist = reinterpret_cast<uint32_t *>(base + o);   o += ((((size_t)S + 1) * 3 + 1) * 4 + 15) & ~(size_t)15;
     s.disp = reinterpret_cast<uint16_t *>(base + o);   o += (size_t)2 << bbits;
     s.slots = reinterpret_cast<uint16_t *>(base + o);  o += (size_t)2 << sbits;
+    s.hdisp = reinterpret_cast<uint16_t *>(base + o);  o += hsbits ? (size_t)2 << hbbits : 0;
     o = (o + 15) & ~(size_t)15;
     if (out) *out = s;
     return o;
@@ -71,59 +71,56 @@ size_t ph_smem_bytes(uint32_t S, uint32_t bbits, uint32_t sbits) { return ph_car
 // is a round trip to L2), then copies of the planes table (up to one per lane of a half warp).
 static void ph_fit(uint32_t S, PhParams &c) {
     const uint32_t bbits = 32u - c.bshift, sbits = 32u - c.sshift;
-    if (ph_carve(nullptr, S, bbits, sbits, 0u, c.hbits1, c.hbits2, nullptr) > kPhSmemLimit) c.hbits1 = c.hbits2 = 0u;
+    const uint32_t hs = 32u - c.hop_sshift, hb = 32u - c.hop_bshift;
+    c.hop_smem = c.hop_slots && ph_carve(nullptr, S, bbits, sbits, 0u, hs, hb, nullptr) <= kPhSmemLimit ? 1u : 0u;
     c.clog = 4u;
-    while (c.clog && ph_carve(nullptr, S, bbits, sbits, c.clog, c.hbits1, c.hbits2, nullptr) > kPhSmemLimit) c.clog--;
-}
-
-// A half of an A/C/G/T-only barcode in the shared-memory key set: dense id of the key, or 0xFFFFFFFF.
-// Entry = key | (id + 1) << 42, key = lo bits | hi bits << len; 0 = empty; linear probing at load <= 0.4.
-__device__ __forceinline__ uint32_t ph_hop_find(const uint64_t *tab, uint32_t hbits, uint64_t key) {
-    const uint32_t mask = (1u << hbits) - 1u;
-    uint32_t i = (((uint32_t)key * 0x9E3779B1u) ^ ((uint32_t)(key >> 32) * 0x85EBCA77u)) >> (32u - hbits);
-    for (;;) {
-        const uint64_t e = tab[i];
-        if (e == 0ull) return 0xFFFFFFFFu;
-        if ((e & ((1ull << 42) - 1ull)) == key) return (uint32_t)(e >> 42) - 1u;
-        i = (i + 1u) & mask;
-    }
-}
-
-// metrics.rs:658-676 for an A/C/G/T-only NoMatch read, key sets in shared memory
-__device__ __forceinline__ void ph_hop_check(const DevParams &p, const PhParams &c, const PhSmem &sm, uint32_t lo, uint32_t hi) {
-    const uint32_t m1 = (1u << p.i1) - 1u, m2 = (1u << p.i2) - 1u;
-    const uint32_t a = ph_hop_find(sm.hop1, c.hbits1, (uint64_t)(lo & m1) | ((uint64_t)(hi & m1) << p.i1));
-    const uint32_t b = ph_hop_find(sm.hop2, c.hbits2, (uint64_t)((lo >> p.i1) & m2) | ((uint64_t)((hi >> p.i1) & m2) << p.i2));
-    if (a != 0xFFFFFFFFu && b != 0xFFFFFFFFu) {
-        atomicAdd(&p.hop_fwd[(uint64_t)a * p.u2 + b], 1ull);
-        return;
-    }
-    // reversed orientation: index1 key in barcode[i2..], index2 key in barcode[..i2]
-    const uint32_t c1 = ph_hop_find(sm.hop1, c.hbits1, (uint64_t)((lo >> p.i2) & m1) | ((uint64_t)((hi >> p.i2) & m1) << p.i1));
-    if (c1 == 0xFFFFFFFFu) return;
-    const uint32_t d2 = ph_hop_find(sm.hop2, c.hbits2, (uint64_t)(lo & m2) | ((uint64_t)(hi & m2) << p.i2));
-    if (d2 != 0xFFFFFFFFu) atomicAdd(&p.hop_rev[(uint64_t)c1 * p.u2 + d2], 1ull);
+    while (c.clog && ph_carve(nullptr, S, bbits, sbits, c.clog, c.hop_smem ? hs : 0u, hb, nullptr) > kPhSmemLimit) c.clog--;
 }
 
 // the perfect-hash probe of one record without invalid positions: entry (sample or S) and distance to it.
-// prow = this lane's copy of the planes table.
-__device__ __forceinline__ void ph_probe(const PhSmem &sm, const PhParams &c, const uint2 *prow, uint32_t w0, uint32_t w1,
-                                         uint32_t &e, uint32_t &d) {
+// prow = this lane's copy of the planes table, rowbytes = bytes per row of that table.
+__device__ __forceinline__ void ph_probe(const PhSmem &sm, const PhParams &c, const unsigned char *prow, uint32_t rowbytes,
+                                         uint32_t w0, uint32_t w1, uint32_t &e, uint32_t &d) {
     const uint32_t h = __umulhi(w0, c.k0) + w0 * c.k1 + w1 * c.k2;
     const uint32_t mul = sm.disp[h >> c.bshift];
     e = sm.slots[(h * mul) >> c.sshift];
-    const uint2 t = prow[e << c.clog];
+    const uint2 t = *reinterpret_cast<const uint2 *>(prow + e * rowbytes);
     const uint32_t lo = w0 & kCompactMask;
     const uint32_t hi = __funnelshift_r(w0, w1, kCompactField);  // bits 21..52 of the record; 42..52 are zero here
     d = (uint32_t)__popc((lo ^ t.x) | (hi ^ t.y));
 }
 
-// verdict of one read of the general path: patch the placeholder the fast path stored, count, hop check
+// dense id of a barcode half in the shared-memory key sets, or 0xFFFFFFFF
+__device__ __forceinline__ uint32_t ph_hop_find(const PhSmem &sm, const PhParams &c, uint64_t key) {
+    const uint32_t w0 = (uint32_t)key, w1 = (uint32_t)(key >> 32);
+    const uint32_t h = __umulhi(w0, c.hop_k0) + w0 * c.hop_k1 + w1 * c.hop_k2;
+    const uint64_t e = sm.hslots[(h * (uint32_t)sm.hdisp[h >> c.hop_bshift]) >> c.hop_sshift];
+    return (e & ((1ull << 42) - 1ull)) == key ? (uint32_t)(e >> 42) - 1u : 0xFFFFFFFFu;
+}
+
+// metrics.rs:658-676 for an A/C/G/T-only NoMatch read, key sets in shared memory: four independent look-ups
+__device__ __forceinline__ void ph_hop_check(const DevParams &p, const PhParams &c, const PhSmem &sm, uint32_t lo, uint32_t hi) {
+    const uint32_t m1 = (1u << p.i1) - 1u, m2 = (1u << p.i2) - 1u;
+    const uint64_t second = 1ull << 41;
+    const uint32_t a = ph_hop_find(sm, c, (uint64_t)(lo & m1) | ((uint64_t)(hi & m1) << p.i1));
+    const uint32_t b = ph_hop_find(sm, c, (uint64_t)((lo >> p.i1) & m2) | ((uint64_t)((hi >> p.i1) & m2) << p.i2) | second);
+    // reversed orientation: index1 key in barcode[i2..], index2 key in barcode[..i2]
+    const uint32_t c1 = ph_hop_find(sm, c, (uint64_t)((lo >> p.i2) & m1) | ((uint64_t)((hi >> p.i2) & m1) << p.i1));
+    const uint32_t d2 = ph_hop_find(sm, c, (uint64_t)(lo & m2) | ((uint64_t)(hi & m2) << p.i2) | second);
+    if (a != 0xFFFFFFFFu && b != 0xFFFFFFFFu) atomicAdd(&p.hop_fwd[(uint64_t)a * p.u2 + b], 1ull);
+    else if (c1 != 0xFFFFFFFFu && d2 != 0xFFFFFFFFu) atomicAdd(&p.hop_rev[(uint64_t)c1 * p.u2 + d2], 1ull);
+}
+
+// verdict of one read of the general path: patch the placeholder the fast path stored and move its count from
+// "Undetermined", where the fast path booked it, to its bin; hop check
 __device__ __forceinline__ void ph_emit(const DevParams &p, uint32_t *hist, uint32_t S1, uint64_t r, const Rd &rd,
                                         const Verdict &v) {
-    p.out_idx[r] = (uint16_t)v.bin;
-    if (p.out_dist) p.out_dist[r] = (uint8_t)v.dist;
-    atomicAdd(&hist[min(v.dist, 2u) * S1 + v.bin], 1u);  // metrics.rs:428-437
+    if (v.bin != p.S) {
+        p.out_idx[r] = (uint16_t)v.bin;
+        if (p.out_dist) p.out_dist[r] = (uint8_t)v.dist;
+        atomicAdd(&hist[min(v.dist, 2u) * S1 + v.bin], 1u);  // metrics.rs:428-437
+        atomicSub(&hist[2u * S1 + p.S], 1u);
+    }
     if (p.hop_on && v.bin == p.S) hop_check(p, rd);
 }
 
@@ -134,8 +131,8 @@ __global__ void __launch_bounds__(kPhThreads, 1) sgdx_match_ph(const DevParams p
     extern __shared__ __align__(16) unsigned char smem_raw[];
     PhSmem sm;
     const uint32_t bbits = 32u - c.bshift, sbits = 32u - c.sshift;
-    ph_carve(smem_raw, p.S, bbits, sbits, c.clog, c.hbits1, c.hbits2, &sm);
-    const uint32_t S1 = p.S + 1u, nbins = S1 * 3u, trash = nbins;
+    ph_carve(smem_raw, p.S, bbits, sbits, c.clog, c.hop_smem ? 32u - c.hop_sshift : 0u, 32u - c.hop_bshift, &sm);
+    const uint32_t S1 = p.S + 1u, nbins = S1 * 3u;
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const uint32_t ncopies = 1u << c.clog;
 
@@ -146,9 +143,9 @@ __global__ void __launch_bounds__(kPhThreads, 1) sgdx_match_ph(const DevParams p
         sm.planes[i] = s < p.S ? p.table[s] : make_uint2(0u, 0xFFFFFFFFu);
     }
     for (uint32_t i = threadIdx.x; i <= nbins; i += kPhThreads) sm.hist[i] = 0u;
-    if (c.hbits1) {
-        for (uint32_t i = threadIdx.x; i < (1u << c.hbits1); i += kPhThreads) sm.hop1[i] = c.hop1[i];
-        for (uint32_t i = threadIdx.x; i < (1u << c.hbits2); i += kPhThreads) sm.hop2[i] = c.hop2[i];
+    if (c.hop_smem) {
+        for (uint32_t i = threadIdx.x; i < (1u << (32u - c.hop_sshift)); i += kPhThreads) sm.hslots[i] = c.hop_slots[i];
+        for (uint32_t i = threadIdx.x; i < (1u << (32u - c.hop_bshift)); i += kPhThreads) sm.hdisp[i] = c.hop_disp[i];
     }
     __syncthreads();
 
@@ -156,11 +153,13 @@ __global__ void __launch_bounds__(kPhThreads, 1) sgdx_match_ph(const DevParams p
     uint32_t *const qoff = sm.qoff + warp * kPhQueue;
     uint64_t *const q2rec = sm.q2rec + warp * kPhQueue2;
     uint32_t *const q2off = sm.q2off + warp * kPhQueue2;
-    const uint2 *const prow = sm.planes + (lane & (ncopies - 1u));
+    const unsigned char *const prow = reinterpret_cast<const unsigned char *>(sm.planes + (lane & (ncopies - 1u)));
+    const uint32_t rowbytes = 8u << c.clog;
     uint32_t n1 = 0u, n2 = 0u;  // queue fills, warp-uniform
     const uint64_t total_warps = (uint64_t)gridDim.x * kPhWarps, gwarp = (uint64_t)blockIdx.x * kPhWarps + warp;
     const uint64_t nchunks = (p.n + kPhChunk - 1u) / kPhChunk;
     const uint32_t below = (1u << lane) - 1u;
+    const bool hop = p.hop_on != 0u;
     const uint32_t off0 = VEC ? lane * 4u : lane, offk = VEC ? 1u : 32u;  // chunk offset of my read k = off0 + k * offk
 
     auto fetch = [&](uint64_t ch, uint64_t (&r)[4]) {
@@ -201,7 +200,7 @@ __global__ void __launch_bounds__(kPhThreads, 1) sgdx_match_ph(const DevParams p
 #pragma unroll
             for (uint32_t k = 0; k < 4; k++) e[k] = sm.slots[(h[k] * e[k]) >> c.sshift];
 #pragma unroll
-            for (uint32_t k = 0; k < 4; k++) t[k] = prow[e[k] << c.clog];
+            for (uint32_t k = 0; k < 4; k++) t[k] = *reinterpret_cast<const uint2 *>(prow + e[k] * rowbytes);
 #pragma unroll
             for (uint32_t k = 0; k < 4; k++) {
                 const uint32_t w0 = (uint32_t)rec[k], w1 = (uint32_t)(rec[k] >> 32);
@@ -211,14 +210,13 @@ __global__ void __launch_bounds__(kPhThreads, 1) sgdx_match_ph(const DevParams p
                 const bool bad = d > p.M || stray[k];
                 bin[k] = bad ? p.S : e[k];
                 dist[k] = bad ? kNoDist : d;
-                uint32_t hidx = min(dist[k], 2u) * S1 + bin[k];
-                hidx = stray[k] ? trash : hidx;  // the general path counts its reads itself
+                // a read of the general path is booked as Undetermined for now; its drain moves the count
+                const bool live = VEC || base + k * 32u + lane < p.n;
 #ifndef SGDX_PH_X_NOHIST  // (experiment builds only, tools/build_variants.sh: what the histogram costs)
-                atomicAdd(&sm.hist[hidx], 1u);
+                if (live) atomicAdd(&sm.hist[min(dist[k], 2u) * S1 + bin[k]], 1u);
 #endif
                 // deferred: the hop check of a NoMatch read, or the whole read if it is not plain A/C/G/T
-                dk[k] = p.hop_on ? bad : stray[k];
-                if (!VEC) dk[k] = dk[k] && base + k * 32u + lane < p.n;
+                dk[k] = bad && (hop || stray[k]) && live;
 #ifdef SGDX_PH_X_NOQ  // (experiment builds only: what the deferred reads cost)
                 dk[k] = false;
 #endif
@@ -272,7 +270,7 @@ __global__ void __launch_bounds__(kPhThreads, 1) sgdx_match_ph(const DevParams p
                 general = ((w0 & c.nm0) | (w1 & c.nm1)) != 0u;
                 if (!general) {
                     const uint32_t lo = w0 & kCompactMask, hi = __funnelshift_r(w0, w1, kCompactField) & kCompactMask;
-                    if (c.hbits1) {
+                    if (c.hop_smem) {
                         ph_hop_check(p, c, sm, lo, hi);
                     } else {
                         const Rd rd = {lo, hi, 0u, 0u};
@@ -312,9 +310,9 @@ __global__ void __launch_bounds__(kPhThreads, 1) sgdx_match_ph(const DevParams p
                                 const uint32_t lo = rd.lo | ((b & 1u) ? inv : 0u), hi = rd.hi | ((b >> 1) ? inv : 0u);
                                 const uint64_t key = (uint64_t)lo | ((uint64_t)hi << kCompactField);
                                 uint32_t pe, pd;
-                                ph_probe(sm, c, prow, (uint32_t)key, (uint32_t)(key >> 32), pe, pd);
+                                ph_probe(sm, c, prow, rowbytes, (uint32_t)key, (uint32_t)(key >> 32), pe, pd);
                                 if (pe < p.S) {
-                                    const uint2 t = prow[pe << c.clog];
+                                    const uint2 t = *reinterpret_cast<const uint2 *>(prow + pe * rowbytes);
                                     score<MODE>(rd, inv, skip, t.x, t.y, pe, best, nxt);
                                 }
                             }
@@ -356,7 +354,8 @@ __global__ void __launch_bounds__(kPhThreads, 1) sgdx_match_ph(const DevParams p
 template <uint32_t MODE, bool VEC>
 static cudaError_t launch_ph_t(const DevParams &p, const PhParams &c, int sms, cudaStream_t stream) {
     if (p.n == 0) return cudaSuccess;
-    const size_t smem = ph_carve(nullptr, p.S, 32u - c.bshift, 32u - c.sshift, c.clog, c.hbits1, c.hbits2, nullptr);
+    const size_t smem = ph_carve(nullptr, p.S, 32u - c.bshift, 32u - c.sshift, c.clog, c.hop_smem ? 32u - c.hop_sshift : 0u,
+                                 32u - c.hop_bshift, nullptr);
     auto kern = sgdx_match_ph<MODE, VEC>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;

@@ -34,6 +34,107 @@ uint32_t verdict(const PhRules &r, const std::vector<PhPlanes> &table, uint32_t 
 }
 }  // namespace
 
+namespace {
+const uint32_t kChdK[6][3] = {{0x9E3779B1u, 0x85EBCA77u, 0xC2B2AE3Du}, {0x27D4EB2Fu, 0x165667B1u, 0xD3A2646Du},
+                              {0xFD7046C5u, 0xB55A4F09u, 0x2545F491u}, {0x9E6C63D1u, 0x7FEB352Du, 0x846CA68Bu},
+                              {0xCC9E2D51u, 0x1B873593u, 0xE6546B65u}, {0x85EBCA6Bu, 0xC2B2AE35u, 0x9E3779B9u}};
+const uint32_t *chd_multipliers(uint32_t set) { return kChdK[set % 6u]; }
+}  // namespace
+
+// Two-level perfect hash ("hash, displace") of 64-bit keys:
+//     h = hi32(w0 * K0) + w0 * K1 + w1 * K2,   slot = (h * disp[h >> bshift]) >> sshift
+// disp holds one odd 16-bit multiplier per bucket; buckets are placed largest first while the table is still empty.
+// where[i] = slot of key i.  *kset = index of the multiplier set that worked (chd_multipliers).
+bool chd_place(const std::vector<uint64_t> &keys, uint32_t bbits, uint32_t sbits, uint32_t max_sbits, uint32_t S,
+               size_t smem_limit, size_t (*smem_bytes)(uint32_t, uint32_t, uint32_t), std::vector<uint16_t> *disp,
+               std::vector<uint32_t> *where, uint32_t *bshift_out, uint32_t *sshift_out, uint32_t *kset) {
+    const size_t nk = keys.size();
+    for (uint32_t attempt = 0; attempt < 12; attempt++) {
+        const uint32_t *K = kChdK[attempt % 6u];
+        if (attempt == 6u && ++sbits > max_sbits) return false;  // second round: a larger table
+        if (smem_bytes && smem_bytes(S, bbits, sbits) > smem_limit) return false;
+        const uint32_t nb = 1u << bbits, nslots = 1u << sbits, bshift = 32u - bbits, sshift = 32u - sbits;
+        std::vector<uint32_t> hv(nk);
+        std::vector<std::vector<uint32_t>> buckets(nb);
+        for (size_t i = 0; i < nk; i++) {
+            const uint32_t w0 = (uint32_t)keys[i], w1 = (uint32_t)(keys[i] >> 32);
+            hv[i] = (uint32_t)(((uint64_t)w0 * K[0]) >> 32) + w0 * K[1] + w1 * K[2];
+            buckets[hv[i] >> bshift].push_back((uint32_t)i);
+        }
+        std::vector<uint32_t> order(nb);
+        for (uint32_t b = 0; b < nb; b++) order[b] = b;
+        std::stable_sort(order.begin(), order.end(),
+                         [&](uint32_t a, uint32_t b) { return buckets[a].size() > buckets[b].size(); });
+        disp->assign(nb, 1u);
+        where->assign(nk, 0u);
+        std::vector<uint8_t> used(nslots, 0u);
+        std::vector<uint32_t> pos;
+        bool ok = true;
+        for (uint32_t oi = 0; oi < nb && ok; oi++) {
+            const std::vector<uint32_t> &bk = buckets[order[oi]];
+            if (bk.empty()) break;
+            bool placed = false;
+            for (uint32_t mul = 1u; mul < 65536u && !placed; mul += 2u) {
+                pos.clear();
+                bool clash = false;
+                for (uint32_t i : bk) {
+                    const uint32_t q = (hv[i] * mul) >> sshift;
+                    if (used[q] || std::find(pos.begin(), pos.end(), q) != pos.end()) {
+                        clash = true;
+                        break;
+                    }
+                    pos.push_back(q);
+                }
+                if (clash) continue;
+                for (size_t k = 0; k < bk.size(); k++) {
+                    used[pos[k]] = 1u;
+                    (*where)[bk[k]] = pos[k];
+                }
+                (*disp)[order[oi]] = (uint16_t)mul;
+                placed = true;
+            }
+            ok = placed;
+        }
+        if (!ok) continue;
+        *bshift_out = bshift;
+        *sshift_out = sshift;
+        *kset = attempt % 6u;
+        return true;
+    }
+    return false;
+}
+
+// Hop key sets (metrics.rs:575-614) as one perfect hash: key = half (lo bits | hi bits << length) | which << 41,
+// which = 0 for an index1 half, 1 for an index2 half; slots[] = key | (dense id + 1) << 42, 0 = empty.
+bool ph_build_hop(const std::vector<uint64_t> &keys1, const std::vector<uint32_t> &ids1, const std::vector<uint64_t> &keys2,
+                  const std::vector<uint32_t> &ids2, PhHopTables *out) {
+    std::vector<uint64_t> keys;
+    std::vector<uint64_t> vals;
+    for (size_t i = 0; i < keys1.size(); i++) {
+        keys.push_back(keys1[i]);
+        vals.push_back(keys1[i] | ((uint64_t)(ids1[i] + 1u) << 42));
+    }
+    for (size_t i = 0; i < keys2.size(); i++) {
+        const uint64_t k = keys2[i] | (1ull << 41);
+        keys.push_back(k);
+        vals.push_back(k | ((uint64_t)(ids2[i] + 1u) << 42));
+    }
+    if (keys.empty() || keys.size() > 3000u) return false;  // 32 KB of slots at most
+    uint32_t sbits = 4, bbits = 2;
+    while ((double)keys.size() > 0.7 * (double)(1u << sbits)) sbits++;
+    while (((size_t)3 << bbits) < keys.size()) bbits++;
+    std::vector<uint32_t> where;
+    uint32_t kset = 0;
+    if (!chd_place(keys, bbits, sbits, 13u, 0u, 0, nullptr, &out->disp, &where, &out->bshift, &out->sshift, &kset)) return false;
+    const uint32_t *K = chd_multipliers(kset);
+    out->k0 = K[0];
+    out->k1 = K[1];
+    out->k2 = K[2];
+    out->slots.assign((size_t)1 << (32u - out->sshift), 0ull);
+    for (size_t i = 0; i < keys.size(); i++) out->slots[where[i]] = vals[i];
+    return true;
+}
+
 bool ph_build(const PhRules &r, const std::vector<PhPlanes> &table, size_t smem_limit,
               size_t (*smem_bytes)(uint32_t, uint32_t, uint32_t), PhTables *out) {
     const uint32_t S = r.S, L = r.L, M = r.M;
@@ -83,67 +184,19 @@ bool ph_build(const PhRules &r, const std::vector<PhPlanes> &table, size_t smem_
     for (size_t i = 0; i < nk; i++)
         entry[i] = (uint16_t)verdict(r, table, (uint32_t)keys[i] & kFieldMask, (uint32_t)(keys[i] >> kField) & kFieldMask);
 
-    static const uint32_t KS[6][3] = {{0x9E3779B1u, 0x85EBCA77u, 0xC2B2AE3Du}, {0x27D4EB2Fu, 0x165667B1u, 0xD3A2646Du},
-                                      {0xFD7046C5u, 0xB55A4F09u, 0x2545F491u}, {0x9E6C63D1u, 0x7FEB352Du, 0x846CA68Bu},
-                                      {0xCC9E2D51u, 0x1B873593u, 0xE6546B65u}, {0x85EBCA6Bu, 0xC2B2AE35u, 0x9E3779B9u}};
     PhTables t;
-    bool built = false;
-    for (uint32_t attempt = 0; attempt < 12 && !built; attempt++) {
-        const uint32_t *K = KS[attempt % 6u];
-        if (attempt == 6u && ++sbits > kMaxSlotBits) break;  // second round: a larger table
-        if (smem_bytes && smem_bytes(S, bbits, sbits) > smem_limit) return false;
-        const uint32_t nb = 1u << bbits, nslots = 1u << sbits, bshift = 32u - bbits, sshift = 32u - sbits;
-        std::vector<uint32_t> hv(nk);
-        std::vector<std::vector<uint32_t>> buckets(nb);
-        for (size_t i = 0; i < nk; i++) {
-            const uint32_t w0 = (uint32_t)keys[i], w1 = (uint32_t)(keys[i] >> 32);
-            hv[i] = (uint32_t)(((uint64_t)w0 * K[0]) >> 32) + w0 * K[1] + w1 * K[2];
-            buckets[hv[i] >> bshift].push_back((uint32_t)i);
-        }
-        std::vector<uint32_t> order(nb);
-        for (uint32_t b = 0; b < nb; b++) order[b] = b;
-        std::stable_sort(order.begin(), order.end(),
-                         [&](uint32_t a, uint32_t b) { return buckets[a].size() > buckets[b].size(); });
-        t.disp.assign(nb, 1u);
-        t.slots.assign(nslots, (uint16_t)S);
-        std::vector<uint8_t> used(nslots, 0u);
-        std::vector<uint32_t> pos;
-        bool ok = true;
-        for (uint32_t oi = 0; oi < nb && ok; oi++) {  // largest buckets first, while the table is still empty
-            const std::vector<uint32_t> &bk = buckets[order[oi]];
-            if (bk.empty()) break;
-            bool placed = false;
-            for (uint32_t mul = 1u; mul < 65536u && !placed; mul += 2u) {
-                pos.clear();
-                bool clash = false;
-                for (uint32_t i : bk) {
-                    const uint32_t q = (hv[i] * mul) >> sshift;
-                    if (used[q] || std::find(pos.begin(), pos.end(), q) != pos.end()) {
-                        clash = true;
-                        break;
-                    }
-                    pos.push_back(q);
-                }
-                if (clash) continue;
-                for (size_t k = 0; k < bk.size(); k++) {
-                    used[pos[k]] = 1u;
-                    t.slots[pos[k]] = entry[bk[k]];
-                }
-                t.disp[order[oi]] = (uint16_t)mul;
-                placed = true;
-            }
-            ok = placed;
-        }
-        if (!ok) continue;
-        t.bshift = bshift;
-        t.sshift = sshift;
+    std::vector<uint32_t> where;
+    if (!chd_place(keys, bbits, sbits, kMaxSlotBits, S, smem_limit, smem_bytes, &t.disp, &where, &t.bshift, &t.sshift, &t.k0)) return false;
+    {
+        const uint32_t *K = chd_multipliers(t.k0);
         t.k0 = K[0];
         t.k1 = K[1];
         t.k2 = K[2];
-        for (size_t i = 0; i < nk && ok; i++) ok = ph_lookup(t, keys[i]) == entry[i];  // every key reaches its own entry
-        built = ok;
     }
-    if (!built) return false;
+    t.slots.assign((size_t)1 << (32u - t.sshift), (uint16_t)S);
+    for (size_t i = 0; i < nk; i++) t.slots[where[i]] = entry[i];
+    for (size_t i = 0; i < nk; i++)  // every key reaches its own entry through the kernel's arithmetic
+        if (ph_lookup(t, keys[i]) != entry[i]) return false;
     const uint32_t lmask = (1u << L) - 1u;
     t.lmask = lmask;
     t.nm0 = ~(lmask | (lmask << kField));

@@ -24,6 +24,19 @@ struct PhTables {
     uint32_t nm0 = 0, nm1 = 0, lmask = 0, single_ok = 0, dmin = 0, nkeys = 0;
 };
 
+struct PhHopTables {
+    std::vector<uint16_t> disp;
+    std::vector<uint64_t> slots;
+    uint32_t bshift = 0, sshift = 0, k0 = 0, k1 = 0, k2 = 0;
+};
+
+bool chd_place(const std::vector<uint64_t> &keys, uint32_t bbits, uint32_t sbits, uint32_t max_sbits, uint32_t S,
+               size_t smem_limit, size_t (*smem_bytes)(uint32_t, uint32_t, uint32_t), std::vector<uint16_t> *disp,
+               std::vector<uint32_t> *where, uint32_t *bshift_out, uint32_t *sshift_out, uint32_t *kset);
+// keys = halves as lo bits | hi bits << length (A/C/G/T only), ids = their dense ids; false = not built
+bool ph_build_hop(const std::vector<uint64_t> &keys1, const std::vector<uint32_t> &ids1, const std::vector<uint64_t> &keys2,
+                  const std::vector<uint32_t> &ids2, PhHopTables *out);
+
 // matcher.rs:175,201: max_mismatches + min_delta - 1 wraps when both are 0 and is then clamped to L
 inline uint32_t ph_pc_limit(uint32_t max_mismatches, uint32_t min_delta, uint32_t L) {
     const uint64_t md = (uint64_t)max_mismatches + min_delta;
