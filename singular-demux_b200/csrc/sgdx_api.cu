@@ -277,7 +277,7 @@ static int build_ph_table(sgdx_handle *h, const std::vector<uint2> &table) {
         collect(h->keys1, p.i1, k1, id1);
         collect(h->keys2, p.i2, k2, id2);
         PhHopTables ht;
-        if (ph_build_hop(k1, id1, k2, id2, &ht)) {
+        if (ph_build_hop(k1, id1, k2, id2, p.i1 == p.i2, &ht)) {
             CU(cudaMalloc(&h->d_ph_hop_slots, ht.slots.size() * sizeof(uint64_t)));
             CU(cudaMalloc(&h->d_ph_hop_disp, ht.disp.size() * sizeof(uint16_t)));
             CU(cudaMemcpy(h->d_ph_hop_slots, ht.slots.data(), ht.slots.size() * sizeof(uint64_t), cudaMemcpyHostToDevice));

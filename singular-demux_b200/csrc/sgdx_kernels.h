@@ -47,8 +47,8 @@ struct PhParams {
                             // the unique sample within M over its valid positions, found by probing its 4 completions
     // hop key sets for shared memory (optional; hop_slots == nullptr: the kernel uses the global tables of DevParams):
     // one perfect hash of the same construction over the distinct index1 / index2 halves (without Undetermined's
-    // all-N halves): key = lo bits | hi bits << half length | which << 41 (0: index1 half, 1: index2 half),
-    // slot = key | (dense id + 1) << 42, 0 = empty
+    // all-N halves): key = lo bits | hi bits << half length | tag << 40 (tag = 1: an index2 half, only when the two
+    // halves differ in length), slot = key | (index1 id + 1) << 41 | (index2 id + 1) << 52, 0 = empty
     const uint16_t *hop_disp;
     const uint64_t *hop_slots;
     uint32_t hop_bshift, hop_sshift, hop_k0, hop_k1, hop_k2;

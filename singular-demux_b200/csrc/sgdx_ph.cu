@@ -90,25 +90,34 @@ __device__ __forceinline__ void ph_probe(const PhSmem &sm, const PhParams &c, co
     d = (uint32_t)__popc((lo ^ t.x) | (hi ^ t.y));
 }
 
-// dense id of a barcode half in the shared-memory key sets, or 0xFFFFFFFF
+// A barcode half in the shared-memory key sets: (index1 id + 1) | (index2 id + 1) << 16, 0 in a field = not such a key.
+// key = lo bits | hi bits << length | tag << 40 (PhParams::hop_*)
 __device__ __forceinline__ uint32_t ph_hop_find(const PhSmem &sm, const PhParams &c, uint64_t key) {
     const uint32_t w0 = (uint32_t)key, w1 = (uint32_t)(key >> 32);
     const uint32_t h = __umulhi(w0, c.hop_k0) + w0 * c.hop_k1 + w1 * c.hop_k2;
     const uint64_t e = sm.hslots[(h * (uint32_t)sm.hdisp[h >> c.hop_bshift]) >> c.hop_sshift];
-    return (e & ((1ull << 42) - 1ull)) == key ? (uint32_t)(e >> 42) - 1u : 0xFFFFFFFFu;
+    const uint32_t ids = (uint32_t)(e >> 41);  // 11 + 11 bits
+    return (e & ((1ull << 41) - 1ull)) == key ? (ids & 0x7FFu) | ((ids >> 11) << 16) : 0u;
 }
 
-// metrics.rs:658-676 for an A/C/G/T-only NoMatch read, key sets in shared memory: four independent look-ups
+// metrics.rs:658-676 for an A/C/G/T-only NoMatch read, key sets in shared memory.  Halves of equal length share
+// their keys: two look-ups give all four memberships; otherwise four.
 __device__ __forceinline__ void ph_hop_check(const DevParams &p, const PhParams &c, const PhSmem &sm, uint32_t lo, uint32_t hi) {
     const uint32_t m1 = (1u << p.i1) - 1u, m2 = (1u << p.i2) - 1u;
-    const uint64_t second = 1ull << 41;
-    const uint32_t a = ph_hop_find(sm, c, (uint64_t)(lo & m1) | ((uint64_t)(hi & m1) << p.i1));
-    const uint32_t b = ph_hop_find(sm, c, (uint64_t)((lo >> p.i1) & m2) | ((uint64_t)((hi >> p.i1) & m2) << p.i2) | second);
-    // reversed orientation: index1 key in barcode[i2..], index2 key in barcode[..i2]
-    const uint32_t c1 = ph_hop_find(sm, c, (uint64_t)((lo >> p.i2) & m1) | ((uint64_t)((hi >> p.i2) & m1) << p.i1));
-    const uint32_t d2 = ph_hop_find(sm, c, (uint64_t)(lo & m2) | ((uint64_t)(hi & m2) << p.i2) | second);
-    if (a != 0xFFFFFFFFu && b != 0xFFFFFFFFu) atomicAdd(&p.hop_fwd[(uint64_t)a * p.u2 + b], 1ull);
-    else if (c1 != 0xFFFFFFFFu && d2 != 0xFFFFFFFFu) atomicAdd(&p.hop_rev[(uint64_t)c1 * p.u2 + d2], 1ull);
+    uint32_t a, b, c1, d2;  // ids + 1 of: index1 key in bc[..i1], index2 key in bc[i1..], index1 key in bc[i2..], index2 key in bc[..i2]
+    if (p.i1 == p.i2) {
+        const uint32_t x = ph_hop_find(sm, c, (uint64_t)(lo & m1) | ((uint64_t)(hi & m1) << p.i1));
+        const uint32_t y = ph_hop_find(sm, c, (uint64_t)((lo >> p.i1) & m1) | ((uint64_t)((hi >> p.i1) & m1) << p.i1));
+        a = x & 0xFFFFu, b = y >> 16, c1 = y & 0xFFFFu, d2 = x >> 16;
+    } else {
+        const uint64_t tag = 1ull << 40;  // keys of length i2
+        a = ph_hop_find(sm, c, (uint64_t)(lo & m1) | ((uint64_t)(hi & m1) << p.i1)) & 0xFFFFu;
+        b = ph_hop_find(sm, c, (uint64_t)((lo >> p.i1) & m2) | ((uint64_t)((hi >> p.i1) & m2) << p.i2) | tag) >> 16;
+        c1 = ph_hop_find(sm, c, (uint64_t)((lo >> p.i2) & m1) | ((uint64_t)((hi >> p.i2) & m1) << p.i1)) & 0xFFFFu;
+        d2 = ph_hop_find(sm, c, (uint64_t)(lo & m2) | ((uint64_t)(hi & m2) << p.i2) | tag) >> 16;
+    }
+    if (a && b) atomicAdd(&p.hop_fwd[(uint64_t)(a - 1u) * p.u2 + (b - 1u)], 1ull);
+    else if (c1 && d2) atomicAdd(&p.hop_rev[(uint64_t)(c1 - 1u) * p.u2 + (d2 - 1u)], 1ull);
 }
 
 // verdict of one read of the general path: patch the placeholder the fast path stored and move its count from
@@ -155,6 +164,7 @@ __global__ void __launch_bounds__(kPhThreads, 1) sgdx_match_ph(const DevParams p
     uint32_t *const q2off = sm.q2off + warp * kPhQueue2;
     const unsigned char *const prow = reinterpret_cast<const unsigned char *>(sm.planes + (lane & (ncopies - 1u)));
     const uint32_t rowbytes = 8u << c.clog;
+    const uint32_t qrec_s = (uint32_t)__cvta_generic_to_shared(qrec), qoff_s = (uint32_t)__cvta_generic_to_shared(qoff);
     uint32_t n1 = 0u, n2 = 0u;  // queue fills, warp-uniform
     const uint64_t total_warps = (uint64_t)gridDim.x * kPhWarps, gwarp = (uint64_t)blockIdx.x * kPhWarps + warp;
     const uint64_t nchunks = (p.n + kPhChunk - 1u) / kPhChunk;
@@ -187,13 +197,11 @@ __global__ void __launch_bounds__(kPhThreads, 1) sgdx_match_ph(const DevParams p
             fetch(ch + total_warps, nextrec);
             const uint64_t base = ch * kPhChunk;
             // four reads per lane, phase by phase, so that the four dependent shared-memory chains overlap
-            uint32_t bin[4], dist[4], h[4], e[4];
+            uint32_t bin[4], dist[4], h[4], e[4], defer = 0u;
             uint2 t[4];
-            bool stray[4], dk[4];
 #pragma unroll
             for (uint32_t k = 0; k < 4; k++) {
                 const uint32_t w0 = (uint32_t)rec[k], w1 = (uint32_t)(rec[k] >> 32);
-                stray[k] = ((w0 & c.nm0) | (w1 & c.nm1)) != 0u;  // not "barcode_len A/C/G/T bases"
                 h[k] = __umulhi(w0, c.k0) + w0 * c.k1 + w1 * c.k2;
                 e[k] = sm.disp[h[k] >> c.bshift];
             }
@@ -207,7 +215,8 @@ __global__ void __launch_bounds__(kPhThreads, 1) sgdx_match_ph(const DevParams p
                 const uint32_t lo = w0 & kCompactMask;
                 const uint32_t hi = __funnelshift_r(w0, w1, kCompactField);  // bits 21..52; 42..52 are zero unless stray
                 const uint32_t d = (uint32_t)__popc((lo ^ t[k].x) | (hi ^ t[k].y));
-                const bool bad = d > p.M || stray[k];
+                const bool stray = ((w0 & c.nm0) | (w1 & c.nm1)) != 0u;  // not "barcode_len A/C/G/T bases"
+                const bool bad = d > p.M || stray;
                 bin[k] = bad ? p.S : e[k];
                 dist[k] = bad ? kNoDist : d;
                 // a read of the general path is booked as Undetermined for now; its drain moves the count
@@ -216,9 +225,9 @@ __global__ void __launch_bounds__(kPhThreads, 1) sgdx_match_ph(const DevParams p
                 if (live) atomicAdd(&sm.hist[min(dist[k], 2u) * S1 + bin[k]], 1u);
 #endif
                 // deferred: the hop check of a NoMatch read, or the whole read if it is not plain A/C/G/T
-                dk[k] = bad && (hop || stray[k]) && live;
+                if (bad && (hop || stray) && live) defer |= 1u << k;
 #ifdef SGDX_PH_X_NOQ  // (experiment builds only: what the deferred reads cost)
-                dk[k] = false;
+                defer = 0u;
 #endif
             }
             // results: a read of the general path gets "Undetermined / no distance" now and is patched later
@@ -237,15 +246,15 @@ __global__ void __launch_bounds__(kPhThreads, 1) sgdx_match_ph(const DevParams p
                     }
                 }
             }
-            if (__any_sync(0xFFFFFFFFu, dk[0] || dk[1] || dk[2] || dk[3])) {
+            if (__any_sync(0xFFFFFFFFu, defer != 0u)) {
 #pragma unroll
                 for (uint32_t k = 0; k < 4; k++) {
-                    const bool mine = dk[k];
+                    const bool mine = (defer >> k) & 1u;
                     const uint32_t votes = __ballot_sync(0xFFFFFFFFu, mine);
                     if (mine) {
                         const uint32_t at = n1 + (uint32_t)__popc(votes & below);
-                        qrec[at] = rec[k];
-                        qoff[at] = iter * kPhChunk + off0 + k * offk;
+                        asm volatile("st.shared.u64 [%0], %1;" ::"r"(qrec_s + at * 8u), "l"(rec[k]) : "memory");
+                        asm volatile("st.shared.u32 [%0], %1;" ::"r"(qoff_s + at * 4u), "r"(iter * kPhChunk + off0 + k * offk) : "memory");
                     }
                     n1 += (uint32_t)__popc(votes);
                 }

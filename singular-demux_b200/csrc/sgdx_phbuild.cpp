@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <utility>
 
 #include "../../include/sgdx.h"
 #include "../../include/sgdx_synth.h"
@@ -104,20 +105,28 @@ bool chd_place(const std::vector<uint64_t> &keys, uint32_t bbits, uint32_t sbits
     return false;
 }
 
-// Hop key sets (metrics.rs:575-614) as one perfect hash: key = half (lo bits | hi bits << length) | which << 41,
-// which = 0 for an index1 half, 1 for an index2 half; slots[] = key | (dense id + 1) << 42, 0 = empty.
+// Hop key sets (metrics.rs:575-614) as one perfect hash.  key = half (lo bits | hi bits << length) | tag << 40, tag = 1
+// for an index2 half when the two halves differ in length (with equal lengths a string may be both, and one look-up
+// answers both questions); slots[] = key | (index1 id + 1) << 41 | (index2 id + 1) << 52, 0 = empty.
 bool ph_build_hop(const std::vector<uint64_t> &keys1, const std::vector<uint32_t> &ids1, const std::vector<uint64_t> &keys2,
-                  const std::vector<uint32_t> &ids2, PhHopTables *out) {
-    std::vector<uint64_t> keys;
-    std::vector<uint64_t> vals;
+                  const std::vector<uint32_t> &ids2, bool same_length, PhHopTables *out) {
+    std::vector<std::pair<uint64_t, uint64_t>> kv;  // key -> id fields
     for (size_t i = 0; i < keys1.size(); i++) {
-        keys.push_back(keys1[i]);
-        vals.push_back(keys1[i] | ((uint64_t)(ids1[i] + 1u) << 42));
+        if (ids1[i] + 1u > 0x7FFu) return false;
+        kv.emplace_back(keys1[i], (uint64_t)(ids1[i] + 1u) << 41);
     }
     for (size_t i = 0; i < keys2.size(); i++) {
-        const uint64_t k = keys2[i] | (1ull << 41);
-        keys.push_back(k);
-        vals.push_back(k | ((uint64_t)(ids2[i] + 1u) << 42));
+        if (ids2[i] + 1u > 0x7FFu) return false;
+        kv.emplace_back(keys2[i] | (same_length ? 0ull : 1ull << 40), (uint64_t)(ids2[i] + 1u) << 52);
+    }
+    std::sort(kv.begin(), kv.end());
+    std::vector<uint64_t> keys, vals;
+    for (const auto &e : kv) {
+        if (!keys.empty() && keys.back() == e.first) vals.back() |= e.second;
+        else {
+            keys.push_back(e.first);
+            vals.push_back(e.first | e.second);
+        }
     }
     if (keys.empty() || keys.size() > 3000u) return false;  // 32 KB of slots at most
     uint32_t sbits = 4, bbits = 2;

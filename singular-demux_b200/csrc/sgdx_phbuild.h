@@ -35,7 +35,7 @@ bool chd_place(const std::vector<uint64_t> &keys, uint32_t bbits, uint32_t sbits
                std::vector<uint32_t> *where, uint32_t *bshift_out, uint32_t *sshift_out, uint32_t *kset);
 // keys = halves as lo bits | hi bits << length (A/C/G/T only), ids = their dense ids; false = not built
 bool ph_build_hop(const std::vector<uint64_t> &keys1, const std::vector<uint32_t> &ids1, const std::vector<uint64_t> &keys2,
-                  const std::vector<uint32_t> &ids2, PhHopTables *out);
+                  const std::vector<uint32_t> &ids2, bool same_length, PhHopTables *out);
 
 // matcher.rs:175,201: max_mismatches + min_delta - 1 wraps when both are 0 and is then clamped to L
 inline uint32_t ph_pc_limit(uint32_t max_mismatches, uint32_t min_delta, uint32_t L) {
