@@ -530,3 +530,42 @@ def packed_records(reads: np.ndarray) -> np.ndarray:
         out[:, 3] = ((~ok & ~isn).astype(np.uint64) << j).sum(axis=1)
     return out
 
+
+# ------------------------------------------------------------------------------------------------
+# seeded synthetic workloads without the product library: oracle/liboracle_synth.so is built
+# from the generator's shared source (singular-demux_b200/csrc/sgdx_synth_core.h) by oracle/Makefile
+# ------------------------------------------------------------------------------------------------
+_SYNTH = None
+
+
+def synth_lib() -> C.CDLL:
+    global _SYNTH
+    if _SYNTH is None:
+        out = os.path.join(_HERE, "liboracle_synth.so")
+        src = os.path.join(_HERE, "synth_host.cpp")
+        core = os.path.join(os.path.dirname(_HERE), "singular-demux_b200", "csrc", "sgdx_synth_core.h")
+        if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(src), os.path.getmtime(core)):
+            subprocess.run(["g++", "-O3", "-std=c++17", "-fPIC", "-shared", "-o", out, src, "-lpthread"], check=True, cwd=_HERE)
+        L = C.CDLL(out)
+        L.orc_synth_table.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]
+        L.orc_synth_reads_host.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_int]
+        _SYNTH = L
+    return _SYNTH
+
+
+def synth_table(w) -> np.ndarray:
+    """Expected-barcode table of a Workload (singular_demux_b200.synth), drawn by the oracle-side generator."""
+    out = np.zeros((w.num_samples, w.barcode_len), dtype=np.uint8)
+    if synth_lib().orc_synth_table(w.table_seed, w.num_samples, w.barcode_len, w.index1_len, w.min_dist, out.ctypes.data):
+        raise RuntimeError("could not draw the table")
+    return out
+
+
+def synth_reads(w, first: int, n: int, table: np.ndarray, threads: int = 8) -> np.ndarray:
+    out = np.empty((n, w.barcode_len), dtype=np.uint8)
+    p = w.params()
+    tb = np.ascontiguousarray(table, dtype=np.uint8)
+    if synth_lib().orc_synth_reads_host(C.byref(p), tb.ctypes.data, first, n, out.ctypes.data, threads):
+        raise RuntimeError("synthetic read generation failed")
+    return out
+

@@ -734,6 +734,11 @@ extern "C" const char *sgdx_kernel_name(const sgdx_handle *h) {
     return h->base.ex_on ? "sgdx_match_exact_first" : "sgdx_match_seeded";
 }
 
+extern "C" const char *sgdx_compact_kernel_name(const sgdx_handle *h) {
+    if (!h || h->cfg.barcode_len > kCompactMaxLen) return "";
+    return h->ph.slots ? "sgdx_match_ph" : sgdx_kernel_name(h);  // without a perfect hash: expanded records, general kernels
+}
+
 extern "C" uint32_t sgdx_path_flags(const sgdx_handle *h) {
     if (!h) return 0u;
     const DevParams &p = h->base;

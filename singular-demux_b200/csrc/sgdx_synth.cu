@@ -1,97 +1,18 @@
 // sgdx_synth.cu -- seeded synthetic barcode generator, identical on host and device.
-#include <cstring>
-#include <string>
-#include <thread>
-#include <vector>
-
+// The generator itself is sgdx_synth_core.h; this file adds the CUDA kernel and the C entry points.
 #include "../../include/sgdx.h"
 #include "../../include/sgdx_synth.h"
-#include "sgdx_device.cuh"
+#include "sgdx_synth_core.h"
 
 namespace sgdx {
-
-struct Rng {
-    uint64_t s;
-    __host__ __device__ explicit Rng(uint64_t seed, uint64_t id) : s(mix64(seed ^ mix64(id + 0x632BE59BD9B4E019ull))) {}
-    __host__ __device__ uint64_t next() {
-        s += 0x9E3779B97F4A7C15ull;
-        return mix64(s);
-    }
-};
-
-__host__ __device__ inline uint32_t pick_sample(Rng &g, uint32_t S, uint32_t zipf) {
-    uint64_t v = g.next() >> 32;
-    if (zipf) v = (v * v) >> 32;  // density ~ 1/sqrt(k): a few popular samples, a long tail
-    return (uint32_t)((v * S) >> 32);
-}
-
-__host__ __device__ inline void synth_one(const sgdx_synth_params &p, const uint8_t *table, uint64_t id, uint8_t *out) {
-    const char bases[4] = {'A', 'C', 'G', 'T'};
-    const uint32_t L = p.barcode_len, S = p.num_samples;
-    Rng g(p.seed, id);
-    uint32_t kind = (uint32_t)(g.next() >> 32);
-    bool templated = true;
-    uint64_t t_hop = (uint64_t)p.p_true + (p.index1_len ? p.p_hop : 0u);
-    if (kind < p.p_true) {
-        uint32_t k = pick_sample(g, S, p.zipf);
-        for (uint32_t j = 0; j < L; j++) out[j] = table[(uint64_t)k * L + j];
-    } else if ((uint64_t)kind < t_hop) {
-        uint32_t a = pick_sample(g, S, p.zipf), b = pick_sample(g, S, p.zipf);
-        if (b == a) b = (a + 1) % S;
-        for (uint32_t j = 0; j < L; j++) out[j] = table[(uint64_t)(j < p.index1_len ? a : b) * L + j];
-    } else {
-        templated = false;
-        uint64_t bits = g.next();
-        for (uint32_t j = 0; j < L; j++) out[j] = (uint8_t)bases[(bits >> (2 * j)) & 3u];
-    }
-    for (uint32_t j = 0; j < L; j++) {
-        uint64_t u = g.next();
-        uint32_t lo = (uint32_t)u, hi = (uint32_t)(u >> 32);
-        if (templated && lo < p.p_sub) {
-            uint32_t cur = out[j] == 'A' ? 0u : out[j] == 'C' ? 1u : out[j] == 'G' ? 2u : 3u;
-            out[j] = (uint8_t)bases[(cur + 1u + (uint32_t)(g.next() % 3u)) & 3u];
-        }
-        if (hi < p.p_n) out[j] = 'N';
-        else if ((uint64_t)hi < (uint64_t)p.p_n + p.p_x) out[j] = 'R';
-    }
-}
 
 __global__ void __launch_bounds__(256) synth_kernel(sgdx_synth_params p, const uint8_t *__restrict__ table,
                                                     uint64_t first, uint64_t n, uint8_t *__restrict__ out) {
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-        uint8_t tmp[SGDX_MAX_BARCODE_LEN];
+        uint8_t tmp[kSynthMaxLen];
         synth_one(p, table, first + i, tmp);
         for (uint32_t j = 0; j < p.barcode_len; j++) out[i * p.barcode_len + j] = tmp[j];
     }
-}
-
-static uint32_t hamming(const uint8_t *a, const uint8_t *b, uint32_t n) {
-    uint32_t d = 0;
-    for (uint32_t i = 0; i < n; i++) d += a[i] != b[i];
-    return d;
-}
-
-// greedy: accept a random string iff its distance to every accepted one is >= min_dist
-static bool draw_set(uint64_t seed, uint32_t count, uint32_t len, uint32_t min_dist, std::vector<std::string> &out) {
-    const char bases[4] = {'A', 'C', 'G', 'T'};
-    Rng g(seed, len * 1315423911ull + count);
-    out.clear();
-    for (uint64_t tries = 0; out.size() < count; tries++) {
-        if (tries > 4000000ull + 4000ull * count) return false;
-        std::string s(len, 'A');
-        for (uint32_t j = 0; j < len; j += 32) {
-            uint64_t bits = g.next();
-            for (uint32_t k = 0; k < 32 && j + k < len; k++) s[j + k] = bases[(bits >> (2 * k)) & 3u];
-        }
-        bool ok = true;
-        for (auto &t : out)
-            if (hamming((const uint8_t *)s.data(), (const uint8_t *)t.data(), len) < min_dist) {
-                ok = false;
-                break;
-            }
-        if (ok) out.push_back(s);
-    }
-    return true;
 }
 
 }  // namespace sgdx
@@ -99,37 +20,12 @@ static bool draw_set(uint64_t seed, uint32_t count, uint32_t len, uint32_t min_d
 using namespace sgdx;
 
 extern "C" int sgdx_synth_table(uint64_t seed, uint32_t S, uint32_t L, uint32_t i1, uint32_t min_dist, uint8_t *out) {
-    if (!out || S == 0 || L == 0 || L > SGDX_MAX_BARCODE_LEN || i1 >= L) return SGDX_EINVAL;
-    std::vector<std::string> a, b;
-    if (i1 == 0) {
-        if (!draw_set(seed, S, L, min_dist, a)) return SGDX_EINVAL;
-        for (uint32_t s = 0; s < S; s++) memcpy(out + (uint64_t)s * L, a[s].data(), L);
-        return SGDX_OK;
-    }
-    if (!draw_set(seed, S, i1, min_dist, a) || !draw_set(seed ^ 0xA5A5A5A5DEADBEEFull, S, L - i1, min_dist, b))
-        return SGDX_EINVAL;
-    for (uint32_t s = 0; s < S; s++) {
-        memcpy(out + (uint64_t)s * L, a[s].data(), i1);
-        memcpy(out + (uint64_t)s * L + i1, b[s].data(), L - i1);
-    }
-    return SGDX_OK;
+    return synth_table_impl(seed, S, L, i1, min_dist, out) ? SGDX_EINVAL : SGDX_OK;
 }
 
 extern "C" int sgdx_synth_reads_host(const sgdx_synth_params *p, const uint8_t *table, uint64_t first, uint64_t n,
                                      uint8_t *out, int threads) {
-    if (!p || !table || (n && !out) || p->barcode_len == 0 || p->barcode_len > SGDX_MAX_BARCODE_LEN) return SGDX_EINVAL;
-    if (threads < 1) threads = 1;
-    auto work = [&](uint64_t b, uint64_t e) {
-        for (uint64_t i = b; i < e; i++) synth_one(*p, table, first + i, out + i * p->barcode_len);
-    };
-    if (threads == 1 || n < 4096) {
-        work(0, n);
-    } else {
-        std::vector<std::thread> ts;
-        for (int t = 0; t < threads; t++) ts.emplace_back(work, n * t / threads, n * (t + 1) / threads);
-        for (auto &t : ts) t.join();
-    }
-    return SGDX_OK;
+    return synth_reads_host_impl(p, table, first, n, out, threads) ? SGDX_EINVAL : SGDX_OK;
 }
 
 extern "C" int sgdx_synth_reads_device(const sgdx_synth_params *p, const uint8_t *d_table, uint64_t first, uint64_t n,

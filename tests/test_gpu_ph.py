@@ -245,3 +245,25 @@ def test_full_size_properties_and_agreement_with_the_older_kernels():
     want = _oracle(table, HAM, 1, 2, 1, None, w.index_lengths, reads)
     assert np.array_equal(res["ph"][0][:k].numpy().view(np.uint16), want["idx"])
     assert np.array_equal(res["ph"][1][:k].numpy(), want["dist"])
+
+
+def test_stress_streams_equal_the_oracle():
+    """bench.py's "stress" streams on C2's table: 5 % substitutions per base (a third of the reads end up one
+    mismatch away, a third unmatched) and exactly one substituted base in every read."""
+    import dataclasses
+    w = sg.synth.C2
+    table = w.table()
+    n = 400_003
+    rng = np.random.default_rng(11)
+    a = dataclasses.replace(w, p_sub=0.05).reads_host(0, n, table)
+    b = dataclasses.replace(w, p_true=1.0, p_hop=0.0, p_sub=0.0, p_n=0.0).reads_host(0, n, table)
+    pos = rng.integers(0, 20, n)
+    code = {65: 0, 67: 1, 71: 2, 84: 3}
+    cur = np.vectorize(code.get)(b[np.arange(n), pos])
+    b[np.arange(n), pos] = LETTERS[(cur + rng.integers(1, 4, n)) & 3]
+    for reads in (a, b):
+        st = _stage(table, HAM, 1, 2, 1, None, w.index_lengths)
+        got = st.demultiplex(reads, compact=True, pack_threads=2)
+        _assert_same(st, got, _oracle(table, HAM, 1, 2, 1, None, w.index_lengths, reads), n)
+        st.close()
+    assert (got.hamming_dists == 1).all() and (got.sample_indices < len(table)).all()
