@@ -9,8 +9,8 @@ from ._lib import (KERNEL_AUTO, KERNEL_SEEDED, KERNEL_DIRECT, LIB_PATH, MATCHER_
 from .matcher import (UNDETERMINED_NAME, CachedHammingDistanceMatcher, GpuMatcher, MatcherKind, MatchResult,
                       PreComputeMatcher, SampleMetadata, pack_compact_host, pack_host, select_matcher)
 from .metrics import (BarcodeCount, BaseQualCounter, DemuxedGroupMetrics, DemuxedGroupSampleMetrics,
-                      SampleBarcodeHopTracker, UnmatchedCounter)
-from .read_structure import ReadSegment, ReadStructure
+                      SampleBarcodeHopTracker, UnmatchedCounter, delimit_barcode)
+from .read_structure import ReadSegment, ReadStructure, barcode_segment_lengths
 from .demux import BarcodeAssignmentStage, DemuxedGroup
 from . import read_structure, sharding, synth
 

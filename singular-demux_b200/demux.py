@@ -34,12 +34,19 @@ class BarcodeAssignmentStage:
                  free_ns: int, max_no_calls: Optional[int] = None, index_lengths: Optional[Tuple[int, int]] = None,
                  collect_unmatched: bool = True, device: int = 0, slots: int = 2, kernel: int = 0,
                  unmatched_on_device: bool = False, most_unmatched_max_map_size: int = 5_000_000,
-                 most_unmatched_downsize_to: int = 5_000):
+                 most_unmatched_downsize_to: int = 5_000, barcode_segment_lengths: Optional[Sequence[int]] = None):
         if len(samples) < 2:
             raise ValueError("need at least one sample plus Undetermined")
         self.samples = list(samples)
         self.undetermined_sample_index = len(samples) - 1
         self.index_lengths = index_lengths
+        # lengths of the B segments (FASTQ order, then segment order): where the delimited barcode gets its `+`
+        # (demux.rs:56-62).  Default: one segment per barcode read, i.e. index_lengths, or a single segment.
+        if barcode_segment_lengths is None:
+            barcode_segment_lengths = list(index_lengths) if index_lengths else [len(samples[0].barcode)]
+        if sum(barcode_segment_lengths) != len(samples[0].barcode):
+            raise ValueError("barcode_segment_lengths must add up to the barcode length (run.rs:109-119)")
+        self.barcode_segment_lengths = list(barcode_segment_lengths)
         self.collect_unmatched = collect_unmatched and not unmatched_on_device
         self.unmatched_on_device = unmatched_on_device
         self.matcher: GpuMatcher = matcher_cls(self.samples[:-1], max_mismatches, min_delta, free_ns,
@@ -50,10 +57,9 @@ class BarcodeAssignmentStage:
 
     def most_frequent_unmatched(self, n: int = 1000) -> List["BarcodeCount"]:
         """Rows of most_frequent_unmatched.tsv (metrics.rs:177-190) from the device table; keys in their
-        delimited form (demux.rs:504-522: index segments joined by `+`)."""
-        from .metrics import BarcodeCount
-        i1 = self.index_lengths[0] if self.index_lengths else 0
-        return [BarcodeCount(((k[:i1] + b"+" + k[i1:]) if i1 else k).decode(errors="replace"), c)
+        delimited form (demux.rs:56-62, 504-522: every sample-barcode segment joined to the next by `+`)."""
+        from .metrics import BarcodeCount, delimit_barcode
+        return [BarcodeCount(delimit_barcode(k, self.barcode_segment_lengths).decode(errors="replace"), c)
                 for k, c in self.matcher.unmatched_top(n)]
 
     def get_undetermined_index(self) -> int:

@@ -272,7 +272,27 @@ class BarcodeAssignmentStage {
     void collect_unmatched(uint64_t max_map_size = 5000000, uint64_t downsize_to = 5000) {
         check(sgdx_unmatched_enable(matcher_.handle(), max_map_size, downsize_to), "sgdx_unmatched_enable");
     }
-    // rows of most_frequent_unmatched.tsv (metrics.rs:177-190): delimited barcode (demux.rs:504-522), descending count
+    // Lengths of the sample-barcode (B) segments in FASTQ order, then segment order: the delimited barcode has a `+`
+    // between every two of them (ExtractedBarcode::add_bases, demux.rs:56-62).  Default: one segment per barcode read.
+    void set_barcode_segment_lengths(std::vector<size_t> lengths) { segment_lengths_ = std::move(lengths); }
+    std::string delimit(const std::string &concatenated) const {
+        std::vector<size_t> cuts = segment_lengths_;
+        if (cuts.empty() && index_lengths_) cuts = {index_lengths_->first};
+        std::string out;
+        size_t pos = 0;
+        for (size_t ln : cuts) {
+            if (pos >= concatenated.size()) break;
+            if (pos) out += '+';
+            out += concatenated.substr(pos, ln);
+            pos += ln;
+        }
+        if (pos < concatenated.size()) {
+            if (pos) out += '+';
+            out += concatenated.substr(pos);
+        }
+        return out;
+    }
+    // rows of most_frequent_unmatched.tsv (metrics.rs:177-190): delimited barcode (demux.rs:56-62,504-522), descending count
     std::vector<BarcodeCount> most_frequent_unmatched(uint64_t n) {
         const size_t L = matcher_.barcode_len();
         std::vector<uint8_t> keys((n ? n : 1) * L);
@@ -282,8 +302,7 @@ class BarcodeAssignmentStage {
         std::vector<BarcodeCount> rows;
         for (uint64_t i = 0; i < w; i++) {
             std::string k(reinterpret_cast<const char *>(keys.data()) + i * L, L);
-            if (index_lengths_) k.insert(index_lengths_->first, "+");
-            rows.push_back({std::move(k), counts[i]});
+            rows.push_back({delimit(k), counts[i]});
         }
         return rows;
     }
@@ -346,6 +365,7 @@ class BarcodeAssignmentStage {
   private:
     size_t undetermined_;
     std::optional<std::pair<size_t, size_t>> index_lengths_;
+    std::vector<size_t> segment_lengths_;  // B segments, FASTQ order then segment order; empty = one per barcode read
     GpuMatcher matcher_;
 };
 

@@ -11,7 +11,7 @@ are out of scope (written by the host's unchanged TSV writer, metrics.rs:440-465
 from __future__ import annotations
 
 from dataclasses import dataclass, field
-from typing import Dict, List, Optional
+from typing import Sequence, Dict, List, Optional
 
 import numpy as np
 
@@ -108,6 +108,22 @@ class DemuxedGroupMetrics:
                          for m in self.per_sample_metrics], dtype=np.uint64)
 
 
+def delimit_barcode(concatenated: bytes, segment_lengths: Optional[Sequence[int]]) -> bytes:
+    """ExtractedBarcode::add_bases (demux.rs:56-62): the B segments of a template joined by `+`.  Whatever the
+    lengths do not cover is the last segment (header-barcode mode has barcodes of any length)."""
+    if not segment_lengths:
+        return concatenated
+    parts, pos = [], 0
+    for ln in segment_lengths:
+        if pos >= len(concatenated):
+            break
+        parts.append(concatenated[pos:pos + ln])
+        pos += ln
+    if pos < len(concatenated):
+        parts.append(concatenated[pos:])
+    return b"+".join(parts)
+
+
 class UnmatchedCounter:
     """metrics.rs:131-190: counts delimited unmatched barcodes; when the map exceeds max_map_size it is
     cut down to the downsize_to most frequent keys.  Fed from the sample-index array."""
@@ -127,8 +143,12 @@ class UnmatchedCounter:
         top = sorted(self.counts.items(), key=lambda kv: -kv[1])[:self.downsize_to]
         self.counts = dict(top)
 
-    def most_frequent(self, n: int, index1_length: int = 0) -> List[BarcodeCount]:
-        def delim(k: bytes) -> str:
-            return ((k[:index1_length] + b"+" + k[index1_length:]) if index1_length else k).decode()
+    def most_frequent(self, n: int, index1_length: int = 0,
+                      segment_lengths: Optional[Sequence[int]] = None) -> List[BarcodeCount]:
+        """segment_lengths = lengths of the sample-barcode (B) segments in FASTQ order, then segment order: the
+        reference writes the delimited barcode, `+` between every two of them (demux.rs:56-62, pushed at :553-555).
+        index1_length is the two-segment shorthand (one B segment per index read)."""
+        if segment_lengths is None and index1_length:
+            segment_lengths = [index1_length]  # the rest of the key is the second segment
         rows = sorted(self.counts.items(), key=lambda kv: (-kv[1], kv[0]))[:n]
-        return [BarcodeCount(delim(k), v) for k, v in rows]
+        return [BarcodeCount(delimit_barcode(k, segment_lengths).decode(errors="replace"), v) for k, v in rows]

@@ -68,6 +68,22 @@ class ReadStructure:
         return max([g.offset + (g.length or 0) for g in self.segments] + [0])
 
 
+def barcode_segment_lengths(structures: Sequence[ReadStructure], read_lens: Optional[Sequence[int]] = None) -> List[int]:
+    """Lengths of the sample-barcode segments in FASTQ order, then segment order (demux.rs:504-522): the pieces the
+    delimited barcode joins with `+` (demux.rs:56-62).  read_lens[f] is needed for a trailing `+B`."""
+    out: List[int] = []
+    for f, rs in enumerate(structures):
+        for g in rs.segments:
+            if g.kind == "B":
+                if g.length is None:
+                    if read_lens is None:
+                        raise ValueError("indefinite-length sample barcode segment needs the read length")
+                    out.append(max(read_lens[f] - g.offset, 0))
+                else:
+                    out.append(g.length)
+    return out
+
+
 def c_segments(structures: Sequence[ReadStructure]):
     """sgdx_segment array of several FASTQs' structures (source = position in `structures`)."""
     rows = [(src, g) for src, rs in enumerate(structures) for g in rs.segments]

@@ -71,7 +71,7 @@ def gather_metrics(metrics: DemuxedGroupMetrics, dst: int = 0, group=None) -> Op
 
 
 def merge_unmatched(parts, n: int = 1000, index1_length: int = 0, max_map_size: int = 5_000_000,
-                    downsize_to: int = 5_000):
+                    downsize_to: int = 5_000, segment_lengths=None):
     """Sum the unmatched-barcode maps of several shards (each one GpuMatcher.unmatched_counts()) and return the
     rows of most_frequent_unmatched.tsv (metrics.rs:177-190).  The reference has one counter for the whole run
     (metrics.rs:79-100); per-GPU tables are additive, so below max_map_size distinct keys the merge is exact."""
@@ -82,7 +82,7 @@ def merge_unmatched(parts, n: int = 1000, index1_length: int = 0, max_map_size: 
             c.counts[k] = c.counts.get(k, 0) + int(v)
         if len(c.counts) > max_map_size:
             c.downsize()
-    return c.most_frequent(n, index1_length)
+    return c.most_frequent(n, index1_length, segment_lengths)
 
 
 def _gather_to(obj, dst: int, group):
@@ -95,10 +95,11 @@ def _gather_to(obj, dst: int, group):
     return gathered
 
 
-def gather_unmatched(counts: Dict[bytes, int], n: int = 1000, index1_length: int = 0, dst: int = 0, group=None):
+def gather_unmatched(counts: Dict[bytes, int], n: int = 1000, index1_length: int = 0, dst: int = 0, group=None,
+                     segment_lengths=None):
     """Every rank's unmatched map to rank ``dst`` -> merged top-n rows there, None elsewhere."""
     parts = _gather_to(counts, dst, group)
-    return None if parts is None else merge_unmatched(parts, n, index1_length)
+    return None if parts is None else merge_unmatched(parts, n, index1_length, segment_lengths=segment_lengths)
 
 
 def gather_base_qual(counters: np.ndarray, dst: int = 0, group=None) -> Optional[np.ndarray]:

@@ -175,6 +175,10 @@ static void test_unmatched_and_read_structures() {
     dual.demultiplex({"TTTAAA"});
     auto hop = dual.most_frequent_unmatched(10);
     EXPECT(hop.size() == 1 && hop[0].barcode == "TTT+AAA" && hop[0].count == 1);
+    // demux.rs:56-62: a `+` between every two sample-barcode segments -- 2B1S1B + 2B here, three pieces
+    dual.set_barcode_segment_lengths({2, 1, 3});
+    EXPECT(dual.delimit("TTTAAA") == "TT+T+AAA" && dual.most_frequent_unmatched(10)[0].barcode == "TT+T+AAA");
+    EXPECT(st.delimit("AAAAAAAAGATTACAGA") == "AAAAAAAAGATTACAGA");  // one barcode read, one segment: no delimiter
     // read structures (opts.rs:84-92)
     auto rs = ReadStructure::from_str("8B+T");
     EXPECT(rs.segments.size() == 2 && rs.segments[0].length == 8 && rs.segments[0].kind == 'B');

@@ -197,3 +197,31 @@ def test_oracle_reproduces_the_reference_extraction_tests():
             assert res["idx"].tolist() == [g["expected_sample_index"]], case["src"]
             assert res["per_sample_reads"][0] == [0] and all(not r for r in res["per_sample_reads"][1:])
             assert res["base_qual"][0].tolist() == [0, 0, 0, 17, case["template_bases"]], case["src"]
+
+
+def test_delimited_unmatched_keys_have_a_plus_between_every_barcode_segment():
+    """ExtractedBarcode::add_bases (demux.rs:56-62) pushes `+` before every B segment but the first -- several B
+    segments inside one read (4B2S4B) and three barcode reads (10B+T 8B 8B) included -- and that delimited string is
+    what the unmatched counter receives (demux.rs:553-555) and most_frequent_unmatched.tsv shows."""
+    rs = [sg.ReadStructure.from_str(s) for s in ("4B2S4B", "+T")]
+    assert sg.barcode_segment_lengths(rs, read_lens=[10, 50]) == [4, 4]
+    assert sg.delimit_barcode(b"ACGTTTGA", [4, 4]) == b"ACGT+TTGA"
+    rs3 = [sg.ReadStructure.from_str(s) for s in ("10B+T", "8B", "8B")]
+    cuts = sg.barcode_segment_lengths(rs3, read_lens=[160, 8, 8])
+    assert cuts == [10, 8, 8]
+    key = b"A" * 10 + b"C" * 8 + b"G" * 8
+    assert sg.delimit_barcode(key, cuts) == b"AAAAAAAAAA+CCCCCCCC+GGGGGGGG"
+    assert sg.delimit_barcode(b"ACGTACGT", [8]) == b"ACGTACGT" == sg.delimit_barcode(b"ACGTACGT", None)
+    assert sg.barcode_segment_lengths([sg.ReadStructure.from_str("6B2M+T"), sg.ReadStructure.from_str("+B")], [100, 9]) == [6, 9]
+    # the literal walk of demultiplex produces exactly these pieces
+    fq = [np.frombuffer(b"ACGTNNTTGA", dtype=np.uint8).reshape(1, -1)]
+    bc = orc.extract_sample_barcodes(fq, [[(0, 4, "B"), (4, 2, "S"), (6, 4, "B")]])
+    assert sg.delimit_barcode(bytes(bc[0]), [4, 4]) == b"ACGT+TTGA"
+    # the counters' rows: three segments, and the two-read shorthand
+    c = sg.UnmatchedCounter()
+    c.insert_counts(np.frombuffer(key, dtype=np.uint8).reshape(1, -1), np.array([3]))
+    assert c.most_frequent(5, segment_lengths=cuts) == [sg.BarcodeCount("AAAAAAAAAA+CCCCCCCC+GGGGGGGG", 3)]
+    assert c.most_frequent(5, index1_length=10) == [sg.BarcodeCount("AAAAAAAAAA+CCCCCCCCGGGGGGGG", 3)]
+    assert c.most_frequent(5) == [sg.BarcodeCount(key.decode(), 3)]
+    rows = sg.sharding.merge_unmatched([{key: 2}, {key: 5}], n=3, segment_lengths=cuts)
+    assert rows == [sg.BarcodeCount("AAAAAAAAAA+CCCCCCCC+GGGGGGGG", 7)]
