@@ -11,7 +11,7 @@ from .matcher import (UNDETERMINED_NAME, CachedHammingDistanceMatcher, GpuMatche
 from .metrics import (BarcodeCount, BaseQualCounter, DemuxedGroupMetrics, DemuxedGroupSampleMetrics,
                       SampleBarcodeHopTracker, UnmatchedCounter, delimit_barcode)
 from .read_structure import ReadSegment, ReadStructure, barcode_segment_lengths
-from .demux import BarcodeAssignmentStage, DemuxedGroup
+from .demux import BarcodeAssignmentStage, DemuxedGroup, from_delimited
 from . import read_structure, sharding, synth
 
 __all__ = [n for n in dir() if not n.startswith("_")]

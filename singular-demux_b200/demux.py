@@ -25,6 +25,13 @@ class DemuxedGroup:
     unmatched: Optional[np.ndarray]      # [k, L] concatenated barcodes of the NoMatch reads (collect_unmatched)
 
 
+def from_delimited(delimited: bytes) -> bytes:
+    """ExtractedBarcode::from_delimited (demux.rs:42-53), the --sample-barcode-in-fastq-header path: the concatenated
+    barcode the matcher sees is the header's barcode without its FIRST `+` (later ones stay)."""
+    i = delimited.find(b"+")
+    return delimited if i < 0 else delimited[:i] + delimited[i + 1:]
+
+
 class BarcodeAssignmentStage:
     """samples: ALL samples, the last one must be Undetermined (demux.rs:221, 259); the matcher sees
     samples[:-1] (run.rs:201,220).  index_lengths = (index1_length, index2_length) when exactly two

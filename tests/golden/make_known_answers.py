@@ -88,6 +88,27 @@ golden = {
          "max_mismatches": 2, "min_delta": 1, "free_ns": 1, "max_no_calls": 1, "matchers": [1],
          "index1_len": 0, "index2_len": 0, "reads": ["TTT"], "expected_idx": [1],
          "per_sample_totals": [0, 1], "unmatched": {"TTT": 1}},
+        # 1000 + 1000 exact reads of two samples through `+T +T 8B` (one barcode read: no hop checker).  The test
+        # builds its PreComputeMatcher over all three metadata entries, Undetermined's all-N barcode included
+        # (demux.rs:1684); production hands the matcher samples[0..n-1] (run.rs:201,220) and so does this case --
+        # an exact read is Match(sample, 0) either way.
+        {"src": "demux.rs:1583-1730 test_demux_simple_multi_read", "samples": ["ACTGACTG", "GTCAGTCA"],
+         "max_mismatches": 1, "min_delta": 0, "free_ns": 2, "max_no_calls": -1, "matchers": [1],
+         "index1_len": 0, "index2_len": 0, "reads": ["ACTGACTG"] * 1000 + ["GTCAGTCA"] * 1000,
+         "expected_idx": [0] * 1000 + [1] * 1000, "expected_dist": [0] * 2000,
+         "per_sample": [[1000, 1000, 0], [1000, 1000, 0], [0, 0, 0]], "total_templates": 2000, "unmatched": {}},
+        # --sample-barcode-in-fastq-header: the barcode comes from the header, single index (no delimiter) ...
+        {"src": "demux.rs:1758-1777 test_demux_fragment_reads_sample_barcode_from_fastq_header_single_index "
+                "(DemuxTestContext::demux_structures: M=2 d=1 max_no_calls=1, matcher free_ns=2)",
+         "samples": PRESET, "max_mismatches": 2, "min_delta": 1, "free_ns": 2, "max_no_calls": 1, "matchers": [0],
+         "index1_len": 0, "index2_len": 0, "reads": [S1], "expected_idx": [0], "expected_dist": [0],
+         "per_sample_totals": [1, 0, 0, 0, 0]},
+        # ... and dual index: `AAAAAAAAGA+TTACAGA` in the header; ExtractedBarcode::from_delimited (demux.rs:42-53)
+        # drops the first `+` for the matcher and keeps the delimited form for the output header
+        {"src": "demux.rs:1779-1799 test_demux_fragment_reads_sample_barcode_from_fastq_header_dual_index",
+         "samples": PRESET, "max_mismatches": 2, "min_delta": 1, "free_ns": 2, "max_no_calls": 1, "matchers": [0],
+         "index1_len": 0, "index2_len": 0, "header_barcodes": [S1[:10] + "+" + S1[10:]], "reads": [S1],
+         "expected_idx": [0], "expected_dist": [0], "per_sample_totals": [1, 0, 0, 0, 0]},
     ],
 }
 

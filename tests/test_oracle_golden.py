@@ -77,6 +77,19 @@ def test_matcher_known_answers(golden):
                 _check_find(c_closed.find, q)
 
 
+def test_header_barcodes_lose_their_first_delimiter(golden):
+    """demux.rs:42-53 / 1779-1799: `index1+index2` in the FASTQ header -> the concatenated barcode of the case."""
+    import sgdx_loader
+    sg = sgdx_loader.load()
+    seen = 0
+    for case in golden["demux_cases"]:
+        for hb, read in zip(case.get("header_barcodes", []), case["reads"]):
+            assert sg.from_delimited(hb.encode()) == read.encode(), case["src"]
+            seen += 1
+    assert seen >= 1
+    assert sg.from_delimited(b"ACGT") == b"ACGT" and sg.from_delimited(b"AC+GT+TT") == b"ACGT+TT"
+
+
 def test_demux_known_answers(golden):
     for case in golden["demux_cases"]:
         samples = [s.encode() for s in case["samples"]]
