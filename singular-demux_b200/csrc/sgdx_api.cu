@@ -408,6 +408,9 @@ static int fill_handle(sgdx_handle *h, const sgdx_config *cfg, const uint8_t *ba
             }
         h->cfg.kernel = h->seeded ? SGDX_KERNEL_SEEDED : SGDX_KERNEL_DIRECT;
         if (int rc = build_ph_table(h, table)) return rc;
+        // one expected barcode and no hop checker: compact records need no table at all (sgdx_single.cu);
+        // SGDX_DISABLE_SINGLE is a test hook (the perfect-hash kernel serves the same records)
+        h->single = S == 1 && !p.hop_on && L <= kCompactMaxLen && !getenv("SGDX_DISABLE_SINGLE");
     }
 
     h->slots.resize(h->cfg.slots);
@@ -628,6 +631,18 @@ static int run_compact(sgdx_handle *h, Slot &s, const uint64_t *d_records, uint6
     if (reinterpret_cast<uintptr_t>(d_records) & 7u) return fail(SGDX_EINVAL, "compact records must be 8-byte aligned");
     if (h->unm.on && n)
         return fail(SGDX_ESTATE, "unmatched collection needs ASCII input (compact records do not keep foreign bytes)");
+    if (h->single) {  // one barcode: sgdx_match_single
+        DevParams p = h->base;
+        p.n = n;
+        p.out_idx = d_idx;
+        p.out_dist = d_dist;
+        CU(cudaEventRecord(s.e0, s.stream));
+        CU(launch_single(p, d_records, h->mode, h->sms, s.stream));
+        if (n) h->launches.fetch_add(1);
+        CU(cudaEventRecord(s.e1, s.stream));
+        s.timed = true;
+        return SGDX_OK;
+    }
     if (h->ph.slots) {  // perfect hash of the match neighbourhood: sgdx_match_ph
         DevParams p = h->base;
         p.n = n;
@@ -736,6 +751,7 @@ extern "C" const char *sgdx_kernel_name(const sgdx_handle *h) {
 
 extern "C" const char *sgdx_compact_kernel_name(const sgdx_handle *h) {
     if (!h || h->cfg.barcode_len > kCompactMaxLen) return "";
+    if (h->single) return "sgdx_match_single";
     return h->ph.slots ? "sgdx_match_ph" : sgdx_kernel_name(h);  // without a perfect hash: expanded records, general kernels
 }
 

@@ -87,6 +87,7 @@ struct sgdx_handle {
     uint16_t *d_ph_disp = nullptr, *d_ph_slots = nullptr;  // perfect-hash kernel (sgdx_ph.cu); ph.slots == nullptr: not available
     sgdx::PhParams ph{};
     uint32_t ph_keys = 0;
+    bool single = false;  // compact records run sgdx_match_single
     sgdx::HopSlot *d_hash1 = nullptr, *d_hash2 = nullptr;
     uint16_t *d_hop_lut1 = nullptr, *d_hop_lut2 = nullptr;
     unsigned long long *d_hop_fwd = nullptr, *d_hop_rev = nullptr;

@@ -58,6 +58,9 @@ struct PhParams {
 size_t ph_smem_bytes(uint32_t S, uint32_t bbits, uint32_t sbits);
 cudaError_t launch_ph(const DevParams &p, const PhParams &c, uint32_t mode, int sms, cudaStream_t stream);
 
+// one expected barcode, no hop checker (sgdx_single.cu): compact records against a single pair of planes
+cudaError_t launch_single(const DevParams &p, const uint64_t *reads, uint32_t mode, int sms, cudaStream_t stream);
+
 // integer-pipe micro-benchmark (sgdx_microbench.cu)
 cudaError_t measure_int_peak(int sms, double *popc_per_s, double *lop3_per_s);
 

@@ -267,3 +267,58 @@ def test_stress_streams_equal_the_oracle():
         _assert_same(st, got, _oracle(table, HAM, 1, 2, 1, None, w.index_lengths, reads), n)
         st.close()
     assert (got.hamming_dists == 1).all() and (got.sample_indices < len(table)).all()
+
+
+@pytest.mark.parametrize("n,shift", [(0, 0), (1, 0), (3, 1), (4, 0), (5, 0), (1027, 1), (400_001, 0), (400_001, 1)])
+def test_single_sample_kernel_sizes_alignment_and_agreement_with_the_perfect_hash(n, shift):
+    """BASELINE config 4 (one 8-base inline barcode, 2 % no-calls per base, PreCompute by run.rs:196): compact records
+    run sgdx_match_single; ragged sizes, unaligned buffers, both rule sets with and without the no-call gate, against
+    the oracle and against sgdx_match_ph on the same records (SGDX_DISABLE_SINGLE=1)."""
+    import torch
+    w = sg.synth.C4
+    table = w.table()
+    rng = np.random.default_rng(n + shift)
+    reads = dataclass_reads(w, table, n, rng)
+    rec = sg.pack_compact_host(reads) if n else np.zeros(0, dtype=np.uint64)
+    for kind in (PRE, HAM):
+        for (M, D, F, mnc) in ((1, 2, 1, None), (2, 0, 0, 1), (0, 3, 2, 0)):
+            want = _oracle(table, kind, M, D, F, mnc, None, reads) if n else None
+            outs = []
+            for disable in ("", "1"):
+                os.environ["SGDX_DISABLE_SINGLE"] = disable
+                if not disable:
+                    del os.environ["SGDX_DISABLE_SINGLE"]
+                try:
+                    st = _stage(table, kind, M, D, F, mnc, None)
+                    assert st.matcher.compact_kernel_name() == ("sgdx_match_single" if not disable else "sgdx_match_ph")
+                    d_rec = torch.zeros(n + 8, dtype=torch.int64, device="cuda")
+                    d_idx = torch.full((n + 8,), -1, dtype=torch.int16, device="cuda")
+                    d_dist = torch.full((n + 8,), 0x77, dtype=torch.uint8, device="cuda")
+                    d_rec[shift:shift + n] = torch.from_numpy(rec.view(np.int64)).cuda()
+                    st.matcher.match_compact_device(d_rec.data_ptr() + 8 * shift, n, d_idx.data_ptr() + 2 * shift, d_dist.data_ptr() + shift)
+                    st.matcher.sync()
+                    torch.cuda.synchronize()
+                finally:
+                    os.environ.pop("SGDX_DISABLE_SINGLE", None)
+                idx, dist = d_idx.cpu().numpy().view(np.uint16), d_dist.cpu().numpy()
+                assert (idx[:shift] == 0xFFFF).all() and (idx[shift + n:] == 0xFFFF).all()
+                assert (dist[:shift] == 0x77).all() and (dist[shift + n:] == 0x77).all()
+                m = st.metrics()
+                outs.append((idx[shift:shift + n].copy(), dist[shift:shift + n].copy(), m.per_sample_array(), m.total_templates))
+                st.close()
+            a, b = outs
+            assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2]) and a[3] == b[3] == n
+            if n:
+                assert np.array_equal(a[0], want["idx"]) and np.array_equal(a[1], want["dist"])
+                assert np.array_equal(a[2], want["per_sample"])
+
+
+def dataclass_reads(w, table, n, rng):
+    """C4-shaped reads with some foreign bytes and a few all-N / heavily masked reads."""
+    if n == 0:
+        return np.zeros((0, w.barcode_len), dtype=np.uint8)
+    import dataclasses
+    reads = dataclasses.replace(w, p_x=0.003).reads_host(3, n, table)
+    k = min(n, 50)
+    reads[:k][rng.random((k, w.barcode_len)) < 0.5] = ord("N")
+    return reads
