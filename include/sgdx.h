@@ -160,15 +160,19 @@ const char *sgdx_kernel_name(const sgdx_handle *h);
 /* ... and for compact records ("sgdx_match_ph", "sgdx_match_single" for one sample without hop checker, or the ASCII name when the records are expanded for the general
  * kernels; "" when barcode_len > SGDX_COMPACT_MAX_LEN). */
 const char *sgdx_compact_kernel_name(const sgdx_handle *h);
+/* ... and for 16-byte sgdx_read records ("sgdx_match_ph" for barcodes of 22..32 bases whose tables allow it, else
+ * "sgdx_match_seeded" / "sgdx_match_direct"). */
+const char *sgdx_packed_kernel_name(const sgdx_handle *h);
 /* Which accelerations this handle's tables allow (they never change results, only speed). */
 #define SGDX_PATH_SEED_INDEX 1u   /* pigeonhole seed index exists (T+1 <= L, fits shared memory) */
 #define SGDX_PATH_EXACT 2u        /* exact-match front end (min pairwise table distance > min_delta) */
 #define SGDX_PATH_NEIGHBOURS 4u   /* one-substitution neighbour table (min pairwise distance > min_delta + 2) */
 #define SGDX_PATH_HOP_DIRECT 8u   /* direct-address hop tables (both index halves <= 11 bases) */
 /* 16u, 32u: flags of the round-1 compact kernel, retired (never set) */
-#define SGDX_PATH_PERFECT_HASH 64u /* compact records run sgdx_match_ph: every A/C/G/T string within max_mismatches of a
-                                     barcode sits in a perfect hash with its precomputed verdict (barcode_len <= 21 and at
-                                     most ~28 000 such strings; SGDX_DISABLE_PH=1 at sgdx_create turns it off) */
+#define SGDX_PATH_PERFECT_HASH 64u /* packed records run sgdx_match_ph (compact records for barcode_len <= 21, 16-byte
+                                     sgdx_read records above): the A/C/G/T strings within a radius of the barcodes (up to
+                                     max_mismatches, as many as ~28 000 slots hold) sit in a perfect hash with their
+                                     precomputed verdicts; SGDX_DISABLE_PH=1 at sgdx_create turns it off */
 uint32_t sgdx_path_flags(const sgdx_handle *h);
 /* Number of kernel launches issued through this handle so far. */
 uint64_t sgdx_launch_count(const sgdx_handle *h);

@@ -76,7 +76,7 @@ SYMBOLS = [
     "sgdx_last_error", "sgdx_version", "sgdx_create", "sgdx_destroy", "sgdx_get_config", "sgdx_alloc_host",
     "sgdx_free_host", "sgdx_match_batch", "sgdx_sync", "sgdx_match_device", "sgdx_pack_device",
     "sgdx_match_packed_device", "sgdx_pack_host", "sgdx_match_packed_batch", "sgdx_pack_compact_host", "sgdx_pack_compact_device", "sgdx_match_compact_batch",
-    "sgdx_match_compact_device", "sgdx_set_stream", "sgdx_kernel_name", "sgdx_compact_kernel_name", "sgdx_path_flags", "sgdx_launch_count", "sgdx_counters", "sgdx_reset_counters",
+    "sgdx_match_compact_device", "sgdx_set_stream", "sgdx_kernel_name", "sgdx_compact_kernel_name", "sgdx_packed_kernel_name", "sgdx_ph_probe_host_wide", "sgdx_path_flags", "sgdx_launch_count", "sgdx_counters", "sgdx_reset_counters",
     "sgdx_hop_count", "sgdx_hop_export", "sgdx_batcher_create", "sgdx_batcher_destroy", "sgdx_batcher_push",
     "sgdx_batcher_flush", "sgdx_batcher_set_compact", "sgdx_batcher_next", "sgdx_measure_int_peak",
     "sgdx_unmatched_enable", "sgdx_unmatched_info_get", "sgdx_unmatched_export", "sgdx_unmatched_top",
@@ -121,6 +121,9 @@ def lib() -> C.CDLL:
     L.sgdx_kernel_name.restype = C.c_char_p
     L.sgdx_compact_kernel_name.argtypes = [vp]
     L.sgdx_compact_kernel_name.restype = C.c_char_p
+    L.sgdx_packed_kernel_name.argtypes = [vp]
+    L.sgdx_packed_kernel_name.restype = C.c_char_p
+    L.sgdx_ph_probe_host_wide.argtypes = [C.POINTER(Config), vp, vp, u64, vp, vp, vp]
     L.sgdx_path_flags.argtypes = [vp]
     L.sgdx_path_flags.restype = u32
     L.sgdx_launch_count.argtypes = [vp]

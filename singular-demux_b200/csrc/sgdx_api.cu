@@ -243,7 +243,8 @@ static int build_ph_table(sgdx_handle *h, const std::vector<uint2> &table) {
     for (uint32_t s = 0; s < p.S; s++) planes[s] = PhPlanes{table[s].x, table[s].y};
     const PhRules rules{p.S, p.L, p.M, p.delta, p.pc_limit, h->mode};
     PhTables t;
-    if (!ph_build(rules, planes, 227u * 1024u, ph_smem_bytes, &t)) return SGDX_OK;
+    // barcodes of at most 21 bases: keys are compact records; longer ones: keys of the 16-byte sgdx_read records
+    if (!ph_build(rules, planes, p.L > kCompactMaxLen, 227u * 1024u, ph_smem_bytes, &t)) return SGDX_OK;
     CU(cudaMalloc(&h->d_ph_disp, t.disp.size() * sizeof(uint16_t)));
     CU(cudaMalloc(&h->d_ph_slots, t.slots.size() * sizeof(uint16_t)));
     CU(cudaMemcpy(h->d_ph_disp, t.disp.data(), t.disp.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
@@ -259,6 +260,8 @@ static int build_ph_table(sgdx_handle *h, const std::vector<uint2> &table) {
     h->ph.nm1 = t.nm1;
     h->ph.lmask = t.lmask;
     h->ph.single_ok = t.single_ok;
+    h->ph.radius = t.radius;
+    h->ph.wide = t.wide;
     h->ph_keys = t.nkeys;
     if (p.hop_on) {
         // hop key sets for the kernel's shared memory (PhParams::hop_*): the distinct halves without the all-N ones of
@@ -532,6 +535,16 @@ static int run_kernels(sgdx_handle *h, Slot &s, const uint8_t *d_ascii, const ui
     p.out_dist = d_dist;
     if (h->unm.on && !d_ascii && n)
         return fail(SGDX_ESTATE, "unmatched collection needs ASCII input (packed records do not keep foreign bytes)");
+    if (d_packed && h->ph.slots && h->ph.wide) {  // sgdx_match_ph on 16-byte records
+        PhParams c = h->ph;
+        c.reads_wide = d_packed;
+        CU(cudaEventRecord(s.e0, s.stream));
+        CU(launch_ph(p, c, h->mode, h->sms, s.stream));
+        if (n) h->launches.fetch_add(1);
+        CU(cudaEventRecord(s.e1, s.stream));
+        s.timed = true;
+        return SGDX_OK;
+    }
     std::unique_lock<std::mutex> lk(h->post_mu, std::defer_lock);
     if (h->unm.on) lk.lock();  // a downsize of the unmatched table must not overlap a batch
     CU(cudaEventRecord(s.e0, s.stream));
@@ -643,7 +656,7 @@ static int run_compact(sgdx_handle *h, Slot &s, const uint64_t *d_records, uint6
         s.timed = true;
         return SGDX_OK;
     }
-    if (h->ph.slots) {  // perfect hash of the match neighbourhood: sgdx_match_ph
+    if (h->ph.slots && !h->ph.wide) {  // perfect hash of the match neighbourhood: sgdx_match_ph
         DevParams p = h->base;
         p.n = n;
         p.out_idx = d_idx;
@@ -752,7 +765,13 @@ extern "C" const char *sgdx_kernel_name(const sgdx_handle *h) {
 extern "C" const char *sgdx_compact_kernel_name(const sgdx_handle *h) {
     if (!h || h->cfg.barcode_len > kCompactMaxLen) return "";
     if (h->single) return "sgdx_match_single";
-    return h->ph.slots ? "sgdx_match_ph" : sgdx_kernel_name(h);  // without a perfect hash: expanded records, general kernels
+    return h->ph.slots && !h->ph.wide ? "sgdx_match_ph" : sgdx_kernel_name(h);  // else: expanded records, general kernels
+}
+
+extern "C" const char *sgdx_packed_kernel_name(const sgdx_handle *h) {
+    if (!h) return "";
+    if (h->ph.slots && h->ph.wide) return "sgdx_match_ph";
+    return h->seeded ? "sgdx_match_seeded" : "sgdx_match_direct";
 }
 
 extern "C" uint32_t sgdx_path_flags(const sgdx_handle *h) {

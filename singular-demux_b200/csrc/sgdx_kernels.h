@@ -24,27 +24,31 @@ inline uint64_t compact_record(uint32_t lo, uint32_t hi) { return (uint64_t)lo |
 cudaError_t launch_pack_compact(const uint8_t *reads, uint64_t n, uint32_t L, uint64_t *out, int sms, cudaStream_t stream);
 cudaError_t launch_expand_compact(const uint64_t *in, uint64_t n, uint32_t L, uint4 *out, int sms, cudaStream_t stream);
 
-// Perfect-hash kernel for compact records (sgdx_ph.cu).  Key set K = every A/C/G/T string within max_mismatches
-// substitutions of an expected barcode.  For a read without invalid positions the verdict is a function of the
-// string alone, so sgdx_create computes it once per key (full scan, both rule sets) and stores the winning sample
-// (or "none") in a two-level perfect hash over K:
-//     h    = hi32(w0 * k0) + w0 * k1 + w1 * k2          (w0, w1 = the record's 32-bit words)
+// Perfect-hash kernel for packed records (sgdx_ph.cu).  Key set K = every A/C/G/T string within `radius`
+// substitutions of an expected barcode (radius = max_mismatches when K is small enough, else as large as fits).  For
+// a read without invalid positions the verdict is a function of the string alone, so sgdx_create computes it once
+// per key (full scan, both rule sets) and stores the winning sample (or "none") in a two-level perfect hash over K:
+//     h    = hi32(w0 * k0) + w0 * k1 + w1 * k2          (w0, w1 = the read's planes as two 32-bit words: the compact
+//                                                         record lo | hi << 21, or wide: w0 = lo, w1 = hi)
 //     slot = (h * disp[h >> bshift]) >> sshift           (disp: one odd 16-bit multiplier per bucket)
 //     e    = slots[slot]                                 (sample index; S = none)
 // The entry carries no tag: the kernel verifies by distance.  A read inside K finds its own entry, whose sample is
-// its best sample at distance <= max_mismatches (or S: planes[S] is a dummy that is > 10 away from everything); a
-// read outside K finds some other key's entry, and its distance to that sample is > max_mismatches because it is
-// further than that from every sample.  Reads with invalid positions (or stray bits) take the general path.
+// its best sample at distance <= radius (or S); a read outside K finds some other key's entry, and its distance to
+// that sample is > radius because it is further than that from every sample: NoMatch when radius = max_mismatches,
+// undecided (general path) otherwise.  Reads with invalid positions (or stray bits) take the general path.
 struct PhParams {
-    const uint64_t *reads;
-    const uint16_t *disp;   // [1 << (32 - bshift)]
-    const uint16_t *slots;  // [1 << (32 - sshift)]
+    const uint64_t *reads;     // compact records (wide == 0)
+    const uint4 *reads_wide;   // sgdx_read records (wide == 1)
+    const uint16_t *disp;      // [1 << (32 - bshift)]
+    const uint16_t *slots;     // [1 << (32 - sshift)]
     uint32_t bshift, sshift;
     uint32_t k0, k1, k2;
-    uint32_t nm0, nm1;      // bits of w0 / w1 that a record made of barcode_len A/C/G/T bases never has set
-    uint32_t lmask;         // (1 << barcode_len) - 1
-    uint32_t single_ok;     // min pairwise table distance > 2M + delta + 1: a read with ONE invalid base is decided by
-                            // the unique sample within M over its valid positions, found by probing its 4 completions
+    uint32_t wide;             // keys / records of up to 32 bases
+    uint32_t radius;           // <= max_mismatches
+    uint32_t nm0, nm1;         // compact: bits of w0 / w1 that a record made of barcode_len A/C/G/T bases never has set
+    uint32_t lmask;            // (1 << barcode_len) - 1
+    uint32_t single_ok;        // min pairwise table distance > 2M + delta + 1: a read with ONE invalid base is decided by
+                               // the unique sample within M over its valid positions, found by probing its 4 completions
     // hop key sets for shared memory (optional; hop_slots == nullptr: the kernel uses the global tables of DevParams):
     // one perfect hash of the same construction over the distinct index1 / index2 halves (without Undetermined's
     // all-N halves): key = lo bits | hi bits << half length | tag << 40 (tag = 1: an index2 half, only when the two
@@ -52,8 +56,6 @@ struct PhParams {
     const uint16_t *hop_disp;
     const uint64_t *hop_slots;
     uint32_t hop_bshift, hop_sshift, hop_k0, hop_k1, hop_k2;
-    uint32_t hop_smem;      // per launch: 1 = the hop tables are in shared memory
-    uint32_t clog;          // per launch: log2 of the copies of the planes table in shared memory
 };
 size_t ph_smem_bytes(uint32_t S, uint32_t bbits, uint32_t sbits);
 cudaError_t launch_ph(const DevParams &p, const PhParams &c, uint32_t mode, int sms, cudaStream_t stream);

@@ -144,93 +144,105 @@ bool ph_build_hop(const std::vector<uint64_t> &keys1, const std::vector<uint32_t
     return true;
 }
 
-bool ph_build(const PhRules &r, const std::vector<PhPlanes> &table, size_t smem_limit,
+bool ph_build(const PhRules &r, const std::vector<PhPlanes> &table, bool wide, size_t smem_limit,
               size_t (*smem_bytes)(uint32_t, uint32_t, uint32_t), PhTables *out) {
     const uint32_t S = r.S, L = r.L, M = r.M;
-    if (L > kField || M > 10u || S >= 0xFFFFu) return false;
-    {   // S * sum_k C(L,k) 3^k keys before deduplication
-        double per = 0.0, term = 1.0;
-        for (uint32_t k = 0; k <= M && k <= L; k++) {
-            per += term;
-            term = term * 3.0 * (double)(L - k) / (double)(k + 1u);
+    if (L > (wide ? 32u : kField) || S >= 0xFFFFu) return false;
+    auto key_of = [&](uint32_t lo, uint32_t hi) { return wide ? (uint64_t)lo | ((uint64_t)hi << 32) : record_of(lo, hi); };
+    // the largest radius <= M (and <= 10: the dummy row of the planes table) whose key set fits the slots
+    for (int radius = (int)std::min(std::min(M, L), 10u); radius >= 0; radius--) {
+        {   // S * sum_k C(L,k) 3^k keys before deduplication
+            double per = 0.0, term = 1.0;
+            for (uint32_t k = 0; k <= (uint32_t)radius; k++) {
+                per += term;
+                term = term * 3.0 * (double)(L - k) / (double)(k + 1u);
+            }
+            if (per * S > 3.0 * (double)(1u << kMaxSlotBits)) continue;
         }
-        if (per * S > 3.0 * (double)(1u << kMaxSlotBits)) return false;
-    }
-    // strings at exact distance k from sample s, each once (substituted positions ascending)
-    struct Node {
-        uint32_t lo, hi, next_pos;
-    };
-    std::vector<uint64_t> keys;
-    std::vector<Node> frontier, grown;
-    for (uint32_t s = 0; s < S; s++) {
-        frontier.assign(1, Node{table[s].lo, table[s].hi, 0u});
-        keys.push_back(record_of(table[s].lo, table[s].hi));
-        for (uint32_t k = 1; k <= M && k <= L; k++) {
-            grown.clear();
-            for (const Node &nd : frontier)
-                for (uint32_t j = nd.next_pos; j < L; j++) {
-                    const uint32_t cur = ((nd.lo >> j) & 1u) | (((nd.hi >> j) & 1u) << 1);
-                    for (uint32_t b = 0; b < 4; b++) {
-                        if (b == cur) continue;
-                        const uint32_t lo = (nd.lo & ~(1u << j)) | ((b & 1u) << j);
-                        const uint32_t hi = (nd.hi & ~(1u << j)) | ((b >> 1) << j);
-                        grown.push_back(Node{lo, hi, j + 1u});
-                        keys.push_back(record_of(lo, hi));
+        // strings at exact distance k from sample s, each once (substituted positions ascending)
+        struct Node {
+            uint32_t lo, hi, next_pos;
+        };
+        std::vector<uint64_t> keys;
+        std::vector<Node> frontier, grown;
+        for (uint32_t s = 0; s < S; s++) {
+            frontier.assign(1, Node{table[s].lo, table[s].hi, 0u});
+            keys.push_back(key_of(table[s].lo, table[s].hi));
+            for (uint32_t k = 1; k <= (uint32_t)radius; k++) {
+                grown.clear();
+                for (const Node &nd : frontier)
+                    for (uint32_t j = nd.next_pos; j < L; j++) {
+                        const uint32_t cur = ((nd.lo >> j) & 1u) | (((nd.hi >> j) & 1u) << 1);
+                        for (uint32_t b = 0; b < 4; b++) {
+                            if (b == cur) continue;
+                            const uint32_t lo = (nd.lo & ~(1u << j)) | ((b & 1u) << j);
+                            const uint32_t hi = (nd.hi & ~(1u << j)) | ((b >> 1) << j);
+                            grown.push_back(Node{lo, hi, j + 1u});
+                            keys.push_back(key_of(lo, hi));
+                        }
                     }
-                }
-            frontier.swap(grown);
+                frontier.swap(grown);
+            }
         }
-    }
-    std::sort(keys.begin(), keys.end());
-    keys.erase(std::unique(keys.begin(), keys.end()), keys.end());
-    const size_t nk = keys.size();
-    uint32_t sbits = 6;
-    while ((double)nk > 0.86 * (double)(1u << sbits)) sbits++;
-    if (sbits > kMaxSlotBits) return false;
-    uint32_t bbits = 4;
-    while (((size_t)3 << bbits) < nk) bbits++;  // <= 3 keys per bucket on average
-    std::vector<uint16_t> entry(nk);
-    for (size_t i = 0; i < nk; i++)
-        entry[i] = (uint16_t)verdict(r, table, (uint32_t)keys[i] & kFieldMask, (uint32_t)(keys[i] >> kField) & kFieldMask);
-
-    PhTables t;
-    std::vector<uint32_t> where;
-    if (!chd_place(keys, bbits, sbits, kMaxSlotBits, S, smem_limit, smem_bytes, &t.disp, &where, &t.bshift, &t.sshift, &t.k0)) return false;
-    {
-        const uint32_t *K = chd_multipliers(t.k0);
+        std::sort(keys.begin(), keys.end());
+        keys.erase(std::unique(keys.begin(), keys.end()), keys.end());
+        const size_t nk = keys.size();
+        uint32_t sbits = 6;
+        while ((double)nk > 0.86 * (double)(1u << sbits)) sbits++;
+        if (sbits > kMaxSlotBits) continue;
+        uint32_t bbits = 4;
+        while (((size_t)3 << bbits) < nk) bbits++;  // <= 3 keys per bucket on average
+        std::vector<uint16_t> entry(nk);
+        for (size_t i = 0; i < nk; i++) {
+            const uint32_t lo = wide ? (uint32_t)keys[i] : (uint32_t)keys[i] & kFieldMask;
+            const uint32_t hi = wide ? (uint32_t)(keys[i] >> 32) : (uint32_t)(keys[i] >> kField) & kFieldMask;
+            entry[i] = (uint16_t)verdict(r, table, lo, hi);
+        }
+        PhTables t;
+        std::vector<uint32_t> where;
+        uint32_t kset = 0;
+        if (!chd_place(keys, bbits, sbits, kMaxSlotBits, S, smem_limit, smem_bytes, &t.disp, &where, &t.bshift, &t.sshift, &kset))
+            continue;
+        const uint32_t *K = chd_multipliers(kset);
         t.k0 = K[0];
         t.k1 = K[1];
         t.k2 = K[2];
+        t.slots.assign((size_t)1 << (32u - t.sshift), (uint16_t)S);
+        for (size_t i = 0; i < nk; i++) t.slots[where[i]] = entry[i];
+        bool ok = true;
+        for (size_t i = 0; i < nk && ok; i++) ok = ph_lookup(t, keys[i]) == entry[i];  // every key reaches its own entry
+        if (!ok) continue;
+        const uint32_t lmask = L >= 32u ? 0xFFFFFFFFu : (1u << L) - 1u;
+        t.lmask = lmask;
+        t.nm0 = wide ? 0u : ~(lmask | (lmask << kField));
+        t.nm1 = wide ? 0u : ~(lmask >> (32u - kField));
+        uint32_t dmin = 0xFFFFu;
+        for (uint32_t i = 0; i < S && dmin > 0; i++)
+            for (uint32_t j = i + 1; j < S; j++)
+                dmin = std::min(dmin, (uint32_t)__builtin_popcount((table[i].lo ^ table[j].lo) | (table[i].hi ^ table[j].hi)));
+        t.dmin = dmin;
+        t.single_ok = (uint64_t)dmin > 2ull * M + r.delta + 1ull ? 1u : 0u;
+        t.nkeys = (uint32_t)nk;
+        t.radius = (uint32_t)radius;
+        t.wide = wide ? 1u : 0u;
+        *out = std::move(t);
+        return true;
     }
-    t.slots.assign((size_t)1 << (32u - t.sshift), (uint16_t)S);
-    for (size_t i = 0; i < nk; i++) t.slots[where[i]] = entry[i];
-    for (size_t i = 0; i < nk; i++)  // every key reaches its own entry through the kernel's arithmetic
-        if (ph_lookup(t, keys[i]) != entry[i]) return false;
-    const uint32_t lmask = (1u << L) - 1u;
-    t.lmask = lmask;
-    t.nm0 = ~(lmask | (lmask << kField));
-    t.nm1 = ~(lmask >> (32u - kField));
-    uint32_t dmin = 0xFFFFu;
-    for (uint32_t i = 0; i < S && dmin > 0; i++)
-        for (uint32_t j = i + 1; j < S; j++)
-            dmin = std::min(dmin, (uint32_t)__builtin_popcount((table[i].lo ^ table[j].lo) | (table[i].hi ^ table[j].hi)));
-    t.dmin = dmin;
-    t.single_ok = (uint64_t)dmin > 2ull * M + r.delta + 1ull ? 1u : 0u;
-    t.nkeys = (uint32_t)nk;
-    *out = std::move(t);
-    return true;
+    return false;
 }
 
 }  // namespace sgdx
 
 // Test support (include/sgdx_synth.h): build the tables for a configuration on the host and answer records the way the
-// kernel's fast path does.  No device, no matcher: records with invalid positions are reported as deferred.
-extern "C" int sgdx_ph_probe_host(const sgdx_config *cfg, const uint8_t *barcodes, const uint64_t *records, uint64_t n,
-                                  uint16_t *out_idx, uint8_t *out_dist, uint32_t *info) {
+// kernel's fast path does.  No device, no matcher: records the kernel defers come back marked.
+namespace {
+int probe(const sgdx_config *cfg, const uint8_t *barcodes, const uint64_t *compact, const sgdx_read *wide_records, uint64_t n,
+          uint16_t *out_idx, uint8_t *out_dist, uint32_t *info) {
     using namespace sgdx;
-    if (!cfg || !barcodes || (n && (!records || !out_idx || !out_dist))) return SGDX_EINVAL;
+    const bool wide = wide_records != nullptr;
+    if (!cfg || !barcodes || (n && (!(compact || wide_records) || !out_idx || !out_dist))) return SGDX_EINVAL;
     const uint32_t S = cfg->num_samples, L = cfg->barcode_len;
-    if (S < 1 || S > SGDX_MAX_SAMPLES || L < 1 || L > SGDX_COMPACT_MAX_LEN) return SGDX_EINVAL;
+    if (S < 1 || S > SGDX_MAX_SAMPLES || L < 1 || L > (wide ? SGDX_MAX_BARCODE_LEN : SGDX_COMPACT_MAX_LEN)) return SGDX_EINVAL;
     std::vector<PhPlanes> table(S);
     for (uint32_t s = 0; s < S; s++) {
         uint32_t lo = 0, hi = 0;
@@ -246,7 +258,7 @@ extern "C" int sgdx_ph_probe_host(const sgdx_config *cfg, const uint8_t *barcode
     PhRules r{S, L, std::min<uint32_t>(cfg->max_mismatches, 64u), std::min<uint32_t>(cfg->min_delta, 64u),
               ph_pc_limit(cfg->max_mismatches, cfg->min_delta, L), matcher == SGDX_MATCHER_PRECOMPUTE ? 1u : 0u};
     PhTables t;
-    const bool have = ph_build(r, table, 0, nullptr, &t);
+    const bool have = ph_build(r, table, wide, 0, nullptr, &t);
     if (info) {
         info[0] = have ? 1u : 0u;
         info[1] = t.nkeys;
@@ -254,22 +266,55 @@ extern "C" int sgdx_ph_probe_host(const sgdx_config *cfg, const uint8_t *barcode
         info[3] = have ? 32u - t.sshift : 0u;
         info[4] = t.single_ok;
         info[5] = t.dmin;
+        info[6] = t.radius;
     }
     if (!have) return SGDX_OK;
     for (uint64_t i = 0; i < n; i++) {
-        const uint32_t w0 = (uint32_t)records[i], w1 = (uint32_t)(records[i] >> 32);
-        if (((w0 & t.nm0) | (w1 & t.nm1)) != 0u) {  // general path on the device
+        uint32_t lo, hi;
+        bool stray;
+        uint64_t key;
+        if (wide) {
+            const sgdx_read &q = wide_records[i];
+            lo = q.lo, hi = q.hi;
+            stray = (q.nmask | q.xmask | ((q.lo | q.hi) & ~t.lmask)) != 0u;
+            key = (uint64_t)lo | ((uint64_t)hi << 32);
+        } else {
+            const uint32_t w0 = (uint32_t)compact[i], w1 = (uint32_t)(compact[i] >> 32);
+            stray = ((w0 & t.nm0) | (w1 & t.nm1)) != 0u;
+            lo = w0 & kFieldMask, hi = (uint32_t)(compact[i] >> kField) & kFieldMask;
+            key = compact[i];
+        }
+        if (stray) {  // general path on the device
             out_idx[i] = 0xFFFFu;
             out_dist[i] = 0xFEu;
             continue;
         }
-        const uint32_t e = ph_lookup(t, records[i]);
-        const uint32_t lo = w0 & kFieldMask, hi = (uint32_t)(records[i] >> kField) & kFieldMask;
+        const uint32_t e = ph_lookup(t, key);
         const uint32_t tlo = e < S ? table[e].lo : 0u, thi = e < S ? table[e].hi : 0xFFFFFFFFu;
         const uint32_t d = (uint32_t)__builtin_popcount((lo ^ tlo) | (hi ^ thi));
-        const bool ok = d <= r.M;
-        out_idx[i] = (uint16_t)(ok ? e : S);
-        out_dist[i] = (uint8_t)(ok ? d : SGDX_NO_DIST);
+        if (e < S && d <= t.radius) {
+            out_idx[i] = (uint16_t)e;
+            out_dist[i] = (uint8_t)d;
+        } else if (t.radius >= r.M) {
+            out_idx[i] = (uint16_t)S;
+            out_dist[i] = (uint8_t)SGDX_NO_DIST;
+        } else {  // undecided: the kernel's general path searches the seed index
+            out_idx[i] = 0xFFFFu;
+            out_dist[i] = 0xFDu;
+        }
     }
     return SGDX_OK;
+}
+}  // namespace
+
+extern "C" int sgdx_ph_probe_host(const sgdx_config *cfg, const uint8_t *barcodes, const uint64_t *records, uint64_t n,
+                                  uint16_t *out_idx, uint8_t *out_dist, uint32_t *info) {
+    return probe(cfg, barcodes, records, nullptr, n, out_idx, out_dist, info);
+}
+
+extern "C" int sgdx_ph_probe_host_wide(const sgdx_config *cfg, const uint8_t *barcodes, const sgdx_read *records, uint64_t n,
+                                       uint16_t *out_idx, uint8_t *out_dist, uint32_t *info) {
+    if (n && !records) return SGDX_EINVAL;
+    static const sgdx_read none{};
+    return probe(cfg, barcodes, nullptr, records ? records : &none, n, out_idx, out_dist, info);
 }

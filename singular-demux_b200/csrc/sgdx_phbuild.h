@@ -22,6 +22,8 @@ struct PhTables {
     std::vector<uint16_t> disp, slots;
     uint32_t bshift = 0, sshift = 0, k0 = 0, k1 = 0, k2 = 0;
     uint32_t nm0 = 0, nm1 = 0, lmask = 0, single_ok = 0, dmin = 0, nkeys = 0;
+    uint32_t radius = 0;  // keys = strings within this many substitutions of a barcode (<= max_mismatches)
+    uint32_t wide = 0;    // keys are lo | hi << 32 (barcodes of up to 32 bases) instead of compact records
 };
 
 struct PhHopTables {
@@ -47,10 +49,11 @@ inline uint32_t ph_pc_limit(uint32_t max_mismatches, uint32_t min_delta, uint32_
 }
 
 // false = this configuration gets no perfect hash (too many keys, tables beyond shared memory, barcode too long)
-bool ph_build(const PhRules &r, const std::vector<PhPlanes> &table, size_t smem_limit,
+bool ph_build(const PhRules &r, const std::vector<PhPlanes> &table, bool wide, size_t smem_limit,
               size_t (*smem_bytes)(uint32_t S, uint32_t bbits, uint32_t sbits), PhTables *out);
 
-// the kernel's probe in host arithmetic: entry (sample or S) for a record without invalid positions
+// the kernel's probe in host arithmetic: entry (sample or S) for a read without invalid positions, given as its key
+// (compact record, or lo | hi << 32 when t.wide)
 inline uint32_t ph_lookup(const PhTables &t, uint64_t rec) {
     const uint32_t w0 = (uint32_t)rec, w1 = (uint32_t)(rec >> 32);
     const uint32_t h = (uint32_t)(((uint64_t)w0 * t.k0) >> 32) + w0 * t.k1 + w1 * t.k2;

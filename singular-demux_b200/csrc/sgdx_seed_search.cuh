@@ -40,7 +40,8 @@ __device__ __forceinline__ bool cannot_match(const DevParams &p, const Rd &rd) {
 template <uint32_t MODE, bool EXPAND>
 __device__ __forceinline__ bool seed_search(const DevParams &p, const uint16_t *__restrict__ hdr,
                                             const uint16_t *__restrict__ ids, const uint2 *__restrict__ table,
-                                            const Rd &rd, uint32_t &best, uint32_t &nxt) {
+                                            const Rd &rd, uint32_t &best, uint32_t &nxt, uint32_t tstride = 1u) {
+    // tstride: distance of consecutive samples' planes in `table`, in entries (replicated tables of sgdx_ph.cu)
     const uint32_t inv = rd.nmask | rd.xmask;
     const uint32_t skip = (MODE == kModePreCompute && rd.nmask != 0u) ? p.M + 1u : 0xFFFFu;
     bool complete = true;
@@ -55,7 +56,7 @@ __device__ __forceinline__ bool seed_search(const DevParams &p, const uint16_t *
 #pragma unroll 1  // buckets hold 0-2 samples: an unrolled loop only adds its trip-count dispatch ladder
             for (uint32_t i = start; i < end; i++) {
                 const uint32_t s = ids[i];
-                const uint2 t = table[s];
+                const uint2 t = table[s * tstride];
                 score<MODE>(rd, inv, skip, t.x, t.y, s, best, nxt);
             }
             continue;
@@ -70,7 +71,7 @@ __device__ __forceinline__ bool seed_search(const DevParams &p, const uint16_t *
 #pragma unroll 1
             for (uint32_t i = start; i < end; i++) {
                 const uint32_t s = ids[i];
-                const uint2 t = table[s];
+                const uint2 t = table[s * tstride];
                 score<MODE>(rd, inv, skip, t.x, t.y, s, best, nxt);
             }
         }

@@ -252,6 +252,9 @@ class GpuMatcher:
     def compact_kernel_name(self) -> str:
         return lib().sgdx_compact_kernel_name(self._h).decode()
 
+    def packed_kernel_name(self) -> str:
+        return lib().sgdx_packed_kernel_name(self._h).decode()
+
     def path_flags(self) -> int:
         return int(lib().sgdx_path_flags(self._h))
 

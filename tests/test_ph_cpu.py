@@ -23,7 +23,7 @@ def probe(table, M, D, matcher, reads):
     rec = sg.pack_compact_host(reads)
     idx = np.empty(len(reads), dtype=np.uint16)
     dist = np.empty(len(reads), dtype=np.uint8)
-    info = (C.c_uint32 * 6)()
+    info = (C.c_uint32 * 7)()
     tb = np.ascontiguousarray(table)
     rc = sg.lib().sgdx_ph_probe_host(C.byref(cfg), tb.ctypes.data, rec.ctypes.data, len(reads), idx.ctypes.data,
                                      dist.ctypes.data, info)
@@ -110,7 +110,7 @@ def test_exhaustive_short_barcodes_both_rule_sets():
                 assert np.array_equal(dist, want_dist), (M, D, kind)
 
 
-def test_reads_with_invalid_positions_are_deferred_and_big_key_sets_refused():
+def test_reads_with_invalid_positions_are_deferred_and_big_key_sets_shrink():
     w = sg.synth.CONFIGS["C2"]
     table = w.table()
     reads = table[:64].copy()
@@ -120,7 +120,84 @@ def test_reads_with_invalid_positions_are_deferred_and_big_key_sets_refused():
     bad = (reads == ord("N")).any(1) | (reads == ord("R")).any(1)
     assert (idx[bad] == 0xFFFF).all() and (dist[bad] == 0xFE).all()
     assert np.array_equal(idx[~bad], np.arange(64)[~bad])
-    # 384 x 20 bases at two mismatches: 384 * 1771 keys -- no tables, the older kernels serve it
+    # 384 x 20 bases at two mismatches: 384 * 1771 strings are too many -- the key set falls back to radius 1
     _, _, info2 = probe(table, 2, 1, 1, reads[:1])
-    assert info2[0] == 0
+    assert info2[0] == 1 and info2[6] == 1 and info2[1] == 384 * 61
     assert info[4] == 1 and info[5] >= 6  # min pairwise distance 6 > 2*1 + 2 + 1: single-N shortcut valid
+
+
+def probe_wide(table, M, D, matcher, reads):
+    S, L = table.shape
+    cfg = sg._lib.Config(S, L, M, D, 1, -1, matcher, 0, 0, 0, 1, 0)
+    rec = sg.pack_host(reads)
+    idx = np.empty(len(reads), dtype=np.uint16)
+    dist = np.empty(len(reads), dtype=np.uint8)
+    info = (C.c_uint32 * 7)()
+    tb = np.ascontiguousarray(table)
+    rc = sg.lib().sgdx_ph_probe_host_wide(C.byref(cfg), tb.ctypes.data, rec.ctypes.data, len(reads), idx.ctypes.data,
+                                          dist.ctypes.data, info)
+    assert rc == 0
+    return idx, dist, list(info)
+
+
+def _check_decided(idx, dist, info, table, M, reads, want_idx, want_dist):
+    """Decided reads carry the oracle's verdict; the undecided ones (dist 0xFD) are exactly the plain reads further than
+    the radius from every barcode; with radius == M nothing is undecided."""
+    radius = info[6]
+    undecided = (idx == 0xFFFF) & (dist == 0xFD)
+    deferred = (idx == 0xFFFF) & (dist == 0xFE)
+    decided = ~(undecided | deferred)
+    assert np.array_equal(idx[decided], want_idx[decided]) and np.array_equal(dist[decided], want_dist[decided])
+    plain = np.isin(reads, LETTERS).all(1)
+    assert np.array_equal(deferred, ~plain)
+    dmin = (reads[:, None, :] != table[None, :, :]).sum(-1).min(1)
+    must = plain & (dmin > radius) & (radius < M)
+    assert (undecided[must]).all() and (plain[undecided]).all()
+    # a key whose precomputed verdict is NoMatch (tie, delta) is left to the general path too when the radius is short
+    assert (want_idx[undecided & ~must] == len(table)).all() and (radius < M or not undecided.any())
+    return radius
+
+
+@pytest.mark.parametrize("cfg_name,M,D", [("C3", 3, 1), ("C3", 1, 2), ("C3", 0, 0), ("C2", 2, 1), ("C2", 3, 0), ("C1", 2, 1)])
+def test_radius_smaller_than_max_mismatches_and_wide_keys(cfg_name, M, D):
+    """Tables whose full neighbourhood does not fit: the key set shrinks to a smaller radius (C3: the 1536 barcodes
+    themselves) and the rest is left to the general path; 24-base barcodes use the wide (16-byte record) keys."""
+    w = sg.synth.CONFIGS[cfg_name]
+    table = w.table()
+    S, L = table.shape
+    rng = np.random.default_rng(S + M)
+    reads = reads_near(table, rng, 6000, M + 2)
+    reads[::97, 3] = ord("N")
+    for kind, matcher in ((orc.MATCHER_CACHED_HAMMING, 1), (orc.MATCHER_PRECOMPUTE, 2)):
+        idx, dist, info = (probe_wide if L > 21 else probe)(table, M, D, matcher, reads)
+        assert info[0] == 1, info
+        want_idx, want_dist = oracle_run(table, M, D, kind, reads)
+        radius = _check_decided(idx, dist, info, table, M, reads, want_idx, want_dist)
+    if cfg_name == "C3":
+        assert radius == (1 if M >= 1 and S * (1 + 3 * L) < 28000 else 0) and (info[1] == 1536 or M == 0 or radius)
+    if cfg_name == "C2" and M >= 2:
+        assert radius == 1 and info[1] == 384 * 61
+
+
+@pytest.mark.parametrize("seed,S,L,M,D", [(21, 50, 24, 1, 1), (22, 20, 32, 1, 2), (23, 8, 32, 2, 0), (24, 100, 22, 1, 3), (25, 300, 26, 1, 1)])
+def test_wide_keys_on_close_tables(seed, S, L, M, D):
+    """22..32-base barcodes without a distance guarantee (ties, delta rejections), all-T / all-G reads included: a read
+    of 32 T's equals the dummy row's planes, which must not count as a match."""
+    rng = np.random.default_rng(seed)
+    table = np.unique(LETTERS[rng.integers(0, 4, (S * 2, L))], axis=0)
+    rng.shuffle(table)
+    table = np.ascontiguousarray(table[:S])
+    # near-duplicates so that ties and competitors within delta exist
+    for i in range(0, len(table) - 1, 5):
+        table[i + 1] = table[i]
+        table[i + 1, rng.integers(0, L)] = LETTERS[rng.integers(0, 4)]
+    table = np.unique(table, axis=0)
+    reads = reads_near(table, rng, 8000, M + 2)
+    reads[0] = ord("T")
+    reads[1] = ord("G")
+    reads[2] = ord("A")
+    for kind, matcher in ((orc.MATCHER_CACHED_HAMMING, 1), (orc.MATCHER_PRECOMPUTE, 2)):
+        idx, dist, info = probe_wide(table, M, D, matcher, reads)
+        assert info[0] == 1
+        want_idx, want_dist = oracle_run(table, M, D, kind, reads)
+        _check_decided(idx, dist, info, table, M, reads, want_idx, want_dist)
