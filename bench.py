@@ -247,8 +247,8 @@ def main():
     d_idx = torch.empty(n, dtype=torch.int16, device="cuda")
     d_dist = torch.empty(n, dtype=torch.uint8, device="cuda")
     m.set_stream(0, stream.cuda_stream)  # launches go on torch's current stream so torch events see them
-    d_rec = torch.empty(n, dtype=torch.int64, device="cuda") if compact_ok else None
-    keep_ascii = side or not compact_ok
+    d_rec = torch.empty(n, dtype=torch.int64, device="cuda") if compact_ok else torch.empty((n, 4), dtype=torch.int32, device="cuda")
+    keep_ascii = side
     d_in = torch.empty((n, L), dtype=torch.uint8, device="cuda") if keep_ascii else None
     piece = 100_000_000
     scratch = None if keep_ascii else torch.empty((min(piece, n), L), dtype=torch.uint8, device="cuda")
@@ -258,6 +258,8 @@ def main():
         w.reads_device(rank * n + off, c, d_table.data_ptr(), buf.data_ptr(), stream.cuda_stream)
         if compact_ok:
             m.pack_compact_device(buf.data_ptr(), c, d_rec.data_ptr() + 8 * off, slot=0)
+        else:
+            m.pack_device(buf.data_ptr(), c, d_rec.data_ptr() + 16 * off, slot=0)
     torch.cuda.synchronize()
     scratch = None
 
@@ -268,11 +270,12 @@ def main():
         def step():
             m.match_compact_device(d_rec.data_ptr(), n, d_idx.data_ptr(), d_dist.data_ptr(), slot=0)
     else:
-        kname = m.kernel_name()
-        in_bytes, in_desc = L, "ASCII barcodes resident in HBM (compact records hold at most 21 bases)"
+        kname = m.packed_kernel_name()
+        in_bytes, in_desc = 16, ("16-byte sgdx_read records (2-bit base planes + no-call and foreign-byte masks, include/sgdx.h) "
+                                 "resident in HBM; 12 of the 16 bytes are algorithmic (SURVEY 8d)")
 
         def step():
-            m.match_device(d_in.data_ptr(), n, d_idx.data_ptr(), d_dist.data_ptr(), slot=0)
+            m.match_packed_device(d_rec.data_ptr(), n, d_idx.data_ptr(), d_dist.data_ptr(), slot=0)
 
     def barrier():
         if world > 1:
@@ -471,28 +474,27 @@ def main():
     if not args.no_e2e and args.config != "C5":
         m.set_stream(0, 0)
         e2e_steps = max(1, min(args.steps, 5))
-        if compact_ok:
-            v, up, down, ok = e2e_measure(m.submit_compact_ptr, d_rec, 8, np.int64, e2e_steps)
-            ceil = copy_ceiling(8, e2e_steps)
-            e2e = {"value": v, "unit": UNIT, "h2d_bytes_per_step": up, "d2h_bytes_per_step": down, "steps": e2e_steps,
-                   "chunk_reads": chunk, "slots": nslots, "call": "sgdx_match_compact_batch",
-                   "input": "compact records in pinned host memory (written by the batching stage instead of its ASCII copy)",
-                   "timing": "wall clock around sgdx_match_compact_batch(host buffers)+sgdx_sync, max over ranks",
-                   "matches_device_resident_result": ok, "copy_ceiling": ceil,
-                   "frac_of_copy_ceiling": v / ceil["reads_per_s"], "numa": numa}
-        if keep_ascii and (side or not compact_ok):
+        row = 8 if compact_ok else 16
+        v, up, down, ok = e2e_measure(m.submit_compact_ptr if compact_ok else m.submit_packed_ptr, d_rec, row,
+                                      np.int64 if compact_ok else np.int32, e2e_steps)
+        ceil = copy_ceiling(row, e2e_steps)
+        call = "sgdx_match_compact_batch" if compact_ok else "sgdx_match_packed_batch"
+        e2e = {"value": v, "unit": UNIT, "h2d_bytes_per_step": up, "d2h_bytes_per_step": down, "steps": e2e_steps,
+               "chunk_reads": chunk, "slots": nslots, "call": call,
+               "input": f"{row}-byte records in pinned host memory (written by the batching stage instead of its ASCII copy)",
+               "timing": f"wall clock around {call}(host buffers)+sgdx_sync, max over ranks",
+               "matches_device_resident_result": ok, "copy_ceiling": ceil,
+               "frac_of_copy_ceiling": v / ceil["reads_per_s"], "numa": numa}
+        if keep_ascii and side:
             v, up, down, ok = e2e_measure(m.submit_ptr, d_in, L, np.uint8, e2e_steps)
             e2e_ascii = {"value": v, "unit": UNIT, "h2d_bytes_per_step": up, "d2h_bytes_per_step": down,
                          "steps": e2e_steps, "chunk_reads": chunk, "slots": nslots, "call": "sgdx_match_batch",
                          "matches_device_resident_result": ok}
-            if not compact_ok:
-                e2e_ascii["copy_ceiling"] = copy_ceiling(L, e2e_steps)
-                e2e, e2e_ascii = e2e_ascii, None
         m.set_stream(0, stream.cuda_stream)
 
     # ---- beside the headline: the ASCII entry point on the same reads, and the same kernel on unfriendly streams
     ascii_side, stress = None, None
-    if side and compact_ok:
+    if side:
         ref_idx, ref_dist = d_idx.clone(), d_dist.clone()
         per_a, _, _, _ = timed(lambda: m.match_device(d_in.data_ptr(), n, d_idx.data_ptr(), d_dist.data_ptr(), slot=0),
                             min(args.steps, 10), args.warmup)
@@ -517,7 +519,10 @@ def main():
                 cur = lut[d_in[rows, pos].to(torch.int64)]
                 d_in[rows, pos] = acgt[(cur + rot) & 3]
                 del pos, rot, rows, cur
-            m.pack_compact_device(d_in.data_ptr(), n, d_rec.data_ptr(), slot=0)
+            if compact_ok:
+                m.pack_compact_device(d_in.data_ptr(), n, d_rec.data_ptr(), slot=0)
+            else:
+                m.pack_device(d_in.data_ptr(), n, d_rec.data_ptr(), slot=0)
             m.reset_counters()
             per_s, _, _, _ = timed(step, min(args.steps, 10), args.warmup)
             pc, tt = m.counters()

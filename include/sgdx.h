@@ -157,10 +157,11 @@ int sgdx_set_stream(sgdx_handle *h, uint32_t slot, void *cuda_stream);
 /* Name of the assignment kernel this handle launches for ASCII input ("sgdx_match_direct",
  * "sgdx_match_seeded" or "sgdx_match_exact_first"); static storage. */
 const char *sgdx_kernel_name(const sgdx_handle *h);
-/* ... and for compact records ("sgdx_match_ph", "sgdx_match_single" for one sample without hop checker, or the ASCII name when the records are expanded for the general
+/* ... and for compact records ("sgdx_match_ph"; "sgdx_match_phx", its general form, when the key set stops short of
+ * max_mismatches; "sgdx_match_single" for one sample without hop checker; or the ASCII name when the records are expanded for the general
  * kernels; "" when barcode_len > SGDX_COMPACT_MAX_LEN). */
 const char *sgdx_compact_kernel_name(const sgdx_handle *h);
-/* ... and for 16-byte sgdx_read records ("sgdx_match_ph" for barcodes of 22..32 bases whose tables allow it, else
+/* ... and for 16-byte sgdx_read records ("sgdx_match_phx" for barcodes of 22..32 bases whose tables allow it, else
  * "sgdx_match_seeded" / "sgdx_match_direct"). */
 const char *sgdx_packed_kernel_name(const sgdx_handle *h);
 /* Which accelerations this handle's tables allow (they never change results, only speed). */

@@ -39,16 +39,17 @@ int sgdx_synth_reads_device(const sgdx_synth_params *p, const uint8_t *d_table, 
 /* Test support for the perfect-hash kernel (SGDX_PATH_PERFECT_HASH): builds that kernel's tables for `cfg` on the
  * host -- the same code sgdx_create runs -- and answers n compact records with the kernel's fast-path arithmetic,
  * so CPU tests can hold the tables against the oracle.  Records with invalid positions (general path on the
- * device) come back as idx 0xFFFF / dist 0xFE.  info[7] (nullable) = {tables exist, number of keys, bucket bits,
- * slot bits, single-invalid-base shortcut valid, min pairwise table distance, radius}.  It is not an assignment path: it
+ * device) come back as idx 0xFFFF / dist 0xFE.  info[9] (nullable) = {tables exist, number of keys, bucket bits,
+ * slot bits, single-invalid-base shortcut valid, min pairwise table distance, radius of the first level, radius of the
+ * second level (0 = none), number of second-level keys}.  It is not an assignment path: it
  * ignores no-calls, the hop checker and the counters. */
 struct sgdx_config;
 struct sgdx_read;
 int sgdx_ph_probe_host(const struct sgdx_config *cfg, const uint8_t *barcodes_ascii, const uint64_t *records,
                        uint64_t n, uint16_t *out_idx, uint8_t *out_dist, uint32_t *info);
-/* The same for 16-byte sgdx_read records (barcodes of up to 32 bases).  In both: info has 7 entries, info[6] = the
- * radius of the key set (<= max_mismatches); a read the kernel would hand to its general path because the radius is
- * smaller than max_mismatches comes back as idx 0xFFFF / dist 0xFD. */
+/* The same for 16-byte sgdx_read records (barcodes of up to 32 bases).  In both, a read that neither level decides
+ * (their radius is smaller than max_mismatches: the kernel's general path searches the seed index) comes back as
+ * idx 0xFFFF / dist 0xFD. */
 int sgdx_ph_probe_host_wide(const struct sgdx_config *cfg, const uint8_t *barcodes_ascii, const struct sgdx_read *records,
                             uint64_t n, uint16_t *out_idx, uint8_t *out_dist, uint32_t *info);
 

@@ -245,24 +245,39 @@ static int build_ph_table(sgdx_handle *h, const std::vector<uint2> &table) {
     PhTables t;
     // barcodes of at most 21 bases: keys are compact records; longer ones: keys of the 16-byte sgdx_read records
     if (!ph_build(rules, planes, p.L > kCompactMaxLen, 227u * 1024u, ph_smem_bytes, &t)) return SGDX_OK;
-    CU(cudaMalloc(&h->d_ph_disp, t.disp.size() * sizeof(uint16_t)));
-    CU(cudaMalloc(&h->d_ph_slots, t.slots.size() * sizeof(uint16_t)));
-    CU(cudaMemcpy(h->d_ph_disp, t.disp.data(), t.disp.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(h->d_ph_slots, t.slots.data(), t.slots.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    auto upload = [](const std::vector<uint16_t> &v, uint16_t **d) -> int {
+        CU(cudaMalloc(d, v.size() * sizeof(uint16_t)));
+        CU(cudaMemcpy(*d, v.data(), v.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+        return SGDX_OK;
+    };
+    if (int rc = upload(t.a.disp, &h->d_ph_disp)) return rc;
+    if (int rc = upload(t.a.slots, &h->d_ph_slots)) return rc;
     h->ph.disp = h->d_ph_disp;
     h->ph.slots = h->d_ph_slots;
-    h->ph.bshift = t.bshift;
-    h->ph.sshift = t.sshift;
-    h->ph.k0 = t.k0;
-    h->ph.k1 = t.k1;
-    h->ph.k2 = t.k2;
+    h->ph.bshift = t.a.bshift;
+    h->ph.sshift = t.a.sshift;
+    h->ph.k0 = t.a.k0;
+    h->ph.k1 = t.a.k1;
+    h->ph.k2 = t.a.k2;
+    h->ph.radius = t.a.radius;
+    if (!t.b.slots.empty()) {
+        if (int rc = upload(t.b.disp, &h->d_ph_b_disp)) return rc;
+        if (int rc = upload(t.b.slots, &h->d_ph_b_slots)) return rc;
+        h->ph.b_disp = h->d_ph_b_disp;
+        h->ph.b_slots = h->d_ph_b_slots;
+        h->ph.b_bshift = t.b.bshift;
+        h->ph.b_sshift = t.b.sshift;
+        h->ph.b_k0 = t.b.k0;
+        h->ph.b_k1 = t.b.k1;
+        h->ph.b_k2 = t.b.k2;
+        h->ph.b_radius = t.b.radius;
+    }
     h->ph.nm0 = t.nm0;
     h->ph.nm1 = t.nm1;
     h->ph.lmask = t.lmask;
     h->ph.single_ok = t.single_ok;
-    h->ph.radius = t.radius;
     h->ph.wide = t.wide;
-    h->ph_keys = t.nkeys;
+    h->ph_keys = t.a.nkeys;
     if (p.hop_on) {
         // hop key sets for the kernel's shared memory (PhParams::hop_*): the distinct halves without the all-N ones of
         // Undetermined (a read with a no-call takes the general path and the global tables)
@@ -490,6 +505,8 @@ extern "C" void sgdx_destroy(sgdx_handle *h) {
     cudaFree(h->d_nb_slots);
     cudaFree(h->d_ph_disp);
     cudaFree(h->d_ph_slots);
+    cudaFree(h->d_ph_b_disp);
+    cudaFree(h->d_ph_b_slots);
     cudaFree(h->d_ph_hop_slots);
     cudaFree(h->d_ph_hop_disp);
     cudaFree(h->d_hash1);
@@ -539,7 +556,7 @@ static int run_kernels(sgdx_handle *h, Slot &s, const uint8_t *d_ascii, const ui
         PhParams c = h->ph;
         c.reads_wide = d_packed;
         CU(cudaEventRecord(s.e0, s.stream));
-        CU(launch_ph(p, c, h->mode, h->sms, s.stream));
+        CU(launch_phx(p, c, h->mode, h->sms, s.stream));
         if (n) h->launches.fetch_add(1);
         CU(cudaEventRecord(s.e1, s.stream));
         s.timed = true;
@@ -664,7 +681,8 @@ static int run_compact(sgdx_handle *h, Slot &s, const uint64_t *d_records, uint6
         PhParams c = h->ph;
         c.reads = d_records;
         CU(cudaEventRecord(s.e0, s.stream));
-        CU(launch_ph(p, c, h->mode, h->sms, s.stream));
+        if (c.radius >= p.M) CU(launch_ph(p, c, h->mode, h->sms, s.stream));
+        else CU(launch_phx(p, c, h->mode, h->sms, s.stream));
         if (n) h->launches.fetch_add(1);
         CU(cudaEventRecord(s.e1, s.stream));
         s.timed = true;
@@ -765,12 +783,13 @@ extern "C" const char *sgdx_kernel_name(const sgdx_handle *h) {
 extern "C" const char *sgdx_compact_kernel_name(const sgdx_handle *h) {
     if (!h || h->cfg.barcode_len > kCompactMaxLen) return "";
     if (h->single) return "sgdx_match_single";
-    return h->ph.slots && !h->ph.wide ? "sgdx_match_ph" : sgdx_kernel_name(h);  // else: expanded records, general kernels
+    if (h->ph.slots && !h->ph.wide) return h->ph.radius >= h->base.M ? "sgdx_match_ph" : "sgdx_match_phx";
+    return sgdx_kernel_name(h);  // no perfect hash: expanded records, general kernels
 }
 
 extern "C" const char *sgdx_packed_kernel_name(const sgdx_handle *h) {
     if (!h) return "";
-    if (h->ph.slots && h->ph.wide) return "sgdx_match_ph";
+    if (h->ph.slots && h->ph.wide) return "sgdx_match_phx";
     return h->seeded ? "sgdx_match_seeded" : "sgdx_match_direct";
 }
 

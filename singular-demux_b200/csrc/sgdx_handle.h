@@ -84,7 +84,7 @@ struct sgdx_handle {
     bool seeded = false;  // launches use sgdx_match_seeded
     uint64_t *d_ph_hop_slots = nullptr;
     uint16_t *d_ph_hop_disp = nullptr;
-    uint16_t *d_ph_disp = nullptr, *d_ph_slots = nullptr;  // perfect-hash kernel (sgdx_ph.cu); ph.slots == nullptr: not available
+    uint16_t *d_ph_disp = nullptr, *d_ph_slots = nullptr, *d_ph_b_disp = nullptr, *d_ph_b_slots = nullptr;  // perfect-hash kernel (sgdx_ph.cu); ph.slots == nullptr: not available
     sgdx::PhParams ph{};
     uint32_t ph_keys = 0;
     bool single = false;  // compact records run sgdx_match_single

@@ -49,6 +49,12 @@ struct PhParams {
     uint32_t lmask;            // (1 << barcode_len) - 1
     uint32_t single_ok;        // min pairwise table distance > 2M + delta + 1: a read with ONE invalid base is decided by
                                // the unique sample within M over its valid positions, found by probing its 4 completions
+    // Second level (optional, global memory / L2; b_slots == nullptr: none): when radius < max_mismatches, the same
+    // construction over the strings within b_radius (radius < b_radius <= max_mismatches).  Only the undecided reads
+    // of the first level probe it, 32 at a time from their queue; what it leaves undecided searches the seed index.
+    const uint16_t *b_disp;
+    const uint16_t *b_slots;
+    uint32_t b_bshift, b_sshift, b_k0, b_k1, b_k2, b_radius;
     // hop key sets for shared memory (optional; hop_slots == nullptr: the kernel uses the global tables of DevParams):
     // one perfect hash of the same construction over the distinct index1 / index2 halves (without Undetermined's
     // all-N halves): key = lo bits | hi bits << half length | tag << 40 (tag = 1: an index2 half, only when the two
@@ -58,7 +64,9 @@ struct PhParams {
     uint32_t hop_bshift, hop_sshift, hop_k0, hop_k1, hop_k2;
 };
 size_t ph_smem_bytes(uint32_t S, uint32_t bbits, uint32_t sbits);
+// sgdx_match_ph (sgdx_ph.cu): compact records, radius == max_mismatches.  sgdx_match_phx (sgdx_phx.cu): everything else.
 cudaError_t launch_ph(const DevParams &p, const PhParams &c, uint32_t mode, int sms, cudaStream_t stream);
+cudaError_t launch_phx(const DevParams &p, const PhParams &c, uint32_t mode, int sms, cudaStream_t stream);
 
 // one expected barcode, no hop checker (sgdx_single.cu): compact records against a single pair of planes
 cudaError_t launch_single(const DevParams &p, const uint64_t *reads, uint32_t mode, int sms, cudaStream_t stream);

@@ -1,111 +1,109 @@
-// sgdx_ph.cu -- assignment on packed records through a perfect hash of the match neighbourhood (sm_100a).
+// sgdx_ph.cu -- sgdx_match_ph: assignment on compact records through a perfect hash of the match neighbourhood (sm_100a).
+// This is the kernel of the headline configuration: compact records and a key set that reaches max_mismatches.  Its
+// general form -- 16-byte records, key sets of a shorter radius with a second level -- is sgdx_match_phx (sgdx_phx.cu).
 //
 // Same results as every other assignment kernel (matcher.rs:273-348 / 121-262, demux.rs:524-538,
-// metrics.rs:428-437, 658-676).  Input: one 64-bit compact record per read (barcodes of at most 21 bases), or one
-// 16-byte sgdx_read record per read (WIDE, up to 32 bases) -- both "2-bit base planes + invalid masks" (include/sgdx.h).
+// metrics.rs:428-437, 658-676); input = one 64-bit compact record per read (include/sgdx.h).
 //
-// Idea.  For a read made of A/C/G/T only, Matcher::find is a pure function of the string.  sgdx_create enumerates the
-// strings within `radius` substitutions of an expected barcode (radius = max_mismatches when that set is small enough
-// -- 23 424 strings for 384 samples of 20 bases at one mismatch -- else as large as fits, down to 0 = the barcodes
-// themselves), decides each one with a full scan under the handle's rule set (best / second best, ties, delta,
-// PreCompute's visibility rules: exactly what the general kernels do per read) and stores "sample or none" in a
-// two-level perfect hash (PhParams, sgdx_kernels.h).  Per read the kernel does
+// Idea.  For a read made of A/C/G/T only, Matcher::find is a pure function of the string.  Only strings within
+// max_mismatches substitutions of some expected barcode can be a Match, and there are few of them
+// (S * sum_k C(L,k) 3^k: 23 424 for 384 samples of 20 bases at one mismatch).  sgdx_create enumerates that key set,
+// decides each key with a full scan under the handle's rule set (best / second best, ties, delta, PreCompute's
+// visibility rules -- exactly what the general kernels do per read), and stores "sample or none" in a two-level
+// perfect hash (PhParams, sgdx_kernels.h).  Per read the kernel then does
 //     three multiplies -> bucket multiplier (LDS.U16) -> entry (LDS.U16) -> that sample's planes (LDS.64)
-//     -> XOR / OR / POPC -> distance <= radius ?
-// The distance test is both the verification of the untagged entry and the reported hamming_dist.  A read that
-// passes is decided.  One that fails is NoMatch when radius = max_mismatches (it is further than that from every
-// sample) and undecided otherwise.  There is no search, no queue and no barrier on this path; everything else -- the
-// index-hop check of NoMatch reads, reads with invalid positions, undecided reads -- is deferred to per-warp queues
-// in shared memory and drained 32 at a time by the full warp (hop key sets and seed index in shared memory too, when
-// they fit).
+//     -> XOR / OR / POPC -> distance <= max_mismatches ?
+// The distance test is both the verification of the untagged entry and the reported hamming_dist.  There is no
+// search, no queue and no barrier on this path; every read that is not "A/C/G/T only" -- and the index-hop check of
+// the NoMatch reads -- is deferred to per-warp queues in shared memory and drained 32 at a time by the full warp.
 //
 // Layout.  One 1024-thread CTA per SM, warps are independent (no __syncthreads between the table load and the final
-// counter flush).  A warp takes chunks of consecutive reads: lane i owns 4 (WIDE: 2) consecutive reads, fetched by one
-// 256-bit load and answered by one 64-bit + one 32-bit (WIDE: 32-bit + 16-bit) store.  The next chunk's records are
-// requested before the current chunk is processed.  Buffers that are not aligned for this, and the last partial
-// chunk, take the same code with narrower accesses (!VEC: lane i owns reads i, i+32, ...).
+// counter flush).  A warp takes chunks of 128 consecutive reads: lane i owns reads 4i..4i+3 of the chunk, fetched by
+// one 256-bit load, answered by one 64-bit store (4 sample indices) and one 32-bit store (4 distances).  The next
+// chunk's records are requested before the current chunk is processed.  Buffers that are not aligned for this, and
+// the last partial chunk, take the same code with 64-bit loads and 16/8-bit stores (lane i owns reads i, i+32, ...).
 #include "sgdx_seed_search.cuh"
 
 namespace sgdx {
 
 constexpr uint32_t kPhThreads = 1024;
 constexpr uint32_t kPhWarps = kPhThreads / 32;
+constexpr uint32_t kPhChunk = 128;  // reads per warp per iteration
 constexpr uint32_t kPhQueue = 160;  // <= 31 left over + <= 128 pushed by one chunk
 constexpr uint32_t kPhQueue2 = 64;  // <= 31 left over + <= 32 pushed by one drain of the first queue
-constexpr size_t kPhSmemLimit = 227u * 1024u;
 
 struct PhSmem {
-    uint64_t *qrec;   // [warps][kPhQueue] deferred reads: planes (compact record, or lo | hi << 32) ...
-    uint32_t *qoff;   // [warps][kPhQueue] ... and (warp iteration * chunk + offset in chunk)
+    uint64_t *qrec;   // [warps][kPhQueue] deferred reads: record ...
+    uint32_t *qoff;   // [warps][kPhQueue] ... and (warp iteration * 128 + offset in chunk)
     uint64_t *q2rec;  // [warps][kPhQueue2] the deferred reads that need the general path ...
     uint32_t *q2off;  // [warps][kPhQueue2] ... same numbering
     uint64_t *hslots; // hop key sets (PhParams::hop_slots), optional
+    uint16_t *hdisp;
     uint2 *planes;    // [S + 1][copies]: barcode planes, replicated so that the lanes of a half warp read distinct banks;
-                      //                  row S = dummy
-    uint32_t *hist;   // [3][S + 1] perfect, one mismatch, other (metrics.rs:428-437)
+                      //                  row S = dummy that nothing matches
+    uint32_t *hist;   // [3][S + 1] perfect, one mismatch, other (metrics.rs:428-437), + 1 word nobody reads
     uint16_t *disp;   // [1 << bbits]
     uint16_t *slots;  // [1 << sbits]
-    uint16_t *hdisp;  // hop key sets
-    uint16_t *hdr;    // seed index of DevParams (general path of undecided reads), optional
-    uint16_t *ids;
 };
 
-struct PhFit {       // what of the optional tables goes into shared memory (decided per launch by ph_fit)
-    uint32_t clog;   // log2 of the copies of the planes table
-    uint32_t hsbits, hbbits;  // hop key sets: slot bits (0 = not in shared memory), bucket bits
-    uint32_t hdr_total, ids_total;  // seed index entries (0 = not in shared memory)
-};
-
-__host__ __device__ inline size_t ph_carve(unsigned char *base, uint32_t S, uint32_t bbits, uint32_t sbits, const PhFit &f,
-                                           PhSmem *out) {
+__host__ __device__ inline size_t ph_carve(unsigned char *base, uint32_t S, uint32_t bbits, uint32_t sbits, uint32_t clog,
+                                           uint32_t hsbits, uint32_t hbbits, PhSmem *out) {  // hsbits == 0: no hop tables
     size_t o = 0;
     PhSmem s;
     s.qrec = reinterpret_cast<uint64_t *>(base + o);   o += (size_t)kPhWarps * kPhQueue * 8;
     s.q2rec = reinterpret_cast<uint64_t *>(base + o);  o += (size_t)kPhWarps * kPhQueue2 * 8;
-    s.hslots = reinterpret_cast<uint64_t *>(base + o); o += f.hsbits ? (size_t)8 << f.hsbits : 0;
-    s.planes = reinterpret_cast<uint2 *>(base + o);    o += (((size_t)S + 1) * 8) << f.clog;
+    s.hslots = reinterpret_cast<uint64_t *>(base + o); o += hsbits ? (size_t)8 << hsbits : 0;
+    s.planes = reinterpret_cast<uint2 *>(base + o);    o += (((size_t)S + 1) * 8) << clog;
     s.qoff = reinterpret_cast<uint32_t *>(base + o);   o += (size_t)kPhWarps * kPhQueue * 4;
     s.q2off = reinterpret_cast<uint32_t *>(base + o);  o += (size_t)kPhWarps * kPhQueue2 * 4;
-    s.hist = reinterpret_cast<uint32_t *>(base + o);   o += (((size_t)S + 1) * 3 * 4 + 15) & ~(size_t)15;
+    s.hist = reinterpret_cast<uint32_t *>(base + o);   o += ((((size_t)S + 1) * 3 + 1) * 4 + 15) & ~(size_t)15;
     s.disp = reinterpret_cast<uint16_t *>(base + o);   o += (size_t)2 << bbits;
     s.slots = reinterpret_cast<uint16_t *>(base + o);  o += (size_t)2 << sbits;
-    s.hdisp = reinterpret_cast<uint16_t *>(base + o);  o += f.hsbits ? (size_t)2 << f.hbbits : 0;
-    s.hdr = reinterpret_cast<uint16_t *>(base + o);    o += ((size_t)f.hdr_total * 2 + 15) & ~(size_t)15;
-    s.ids = reinterpret_cast<uint16_t *>(base + o);    o += ((size_t)f.ids_total * 2 + 15) & ~(size_t)15;
+    s.hdisp = reinterpret_cast<uint16_t *>(base + o);  o += hsbits ? (size_t)2 << hbbits : 0;
     o = (o + 15) & ~(size_t)15;
     if (out) *out = s;
     return o;
 }
 
+constexpr size_t kPhSmemLimit = 227u * 1024u;
+
+// what either kernel needs at least (sgdx_match_phx has a third queue): the host builder sizes its tables against this
 size_t ph_smem_bytes(uint32_t S, uint32_t bbits, uint32_t sbits) {
-    return ph_carve(nullptr, S, bbits, sbits, PhFit{0u, 0u, 0u, 0u, 0u}, nullptr);
+    return ph_carve(nullptr, S, bbits, sbits, 0u, 0u, 0u, nullptr) + (size_t)kPhWarps * kPhQueue2 * 12;
 }
 
-// What is optional goes into shared memory as far as it fits, in the order of what it saves: the seed index (every
-// undecided read searches it), the hop key sets (without them every hop check is a round trip to L2), copies of the
-// planes table (up to one per lane of a half warp).
-static PhFit ph_fit(const DevParams &p, const PhParams &c) {
+// What is optional goes into shared memory as far as it fits: first the hop key sets (without them every hop check
+// is a round trip to L2), then copies of the planes table (up to one per lane of a half warp).
+struct PhLean {  // per launch: what of the optional tables is in shared memory
+    uint32_t clog;      // log2 of the copies of the planes table
+    uint32_t hop_smem;  // 1 = the hop key sets too
+};
+
+static PhLean ph_fit(uint32_t S, const PhParams &c) {
+    PhLean f{0u, 0u};
     const uint32_t bbits = 32u - c.bshift, sbits = 32u - c.sshift;
-    PhFit f{0u, 0u, 32u - c.hop_bshift, 0u, 0u};
-    auto fits = [&](const PhFit &x) { return ph_carve(nullptr, p.S, bbits, sbits, x, nullptr) <= kPhSmemLimit; };
-    if (c.radius < p.M && p.seed_C) {
-        PhFit g = f;
-        g.hdr_total = p.seed_hdr_total;
-        g.ids_total = p.seed_ids_total;
-        if (fits(g)) f = g;
-    }
-    if (c.hop_slots) {
-        PhFit g = f;
-        g.hsbits = 32u - c.hop_sshift;
-        if (fits(g)) f = g;
-    }
+    const uint32_t hs = 32u - c.hop_sshift, hb = 32u - c.hop_bshift;
+    f.hop_smem = c.hop_slots && ph_carve(nullptr, S, bbits, sbits, 0u, hs, hb, nullptr) <= kPhSmemLimit ? 1u : 0u;
     f.clog = 4u;
-    while (f.clog && !fits(f)) f.clog--;
+    while (f.clog && ph_carve(nullptr, S, bbits, sbits, f.clog, f.hop_smem ? hs : 0u, hb, nullptr) > kPhSmemLimit) f.clog--;
     return f;
 }
 
-// dense ids of a barcode half in the shared-memory key sets: (index1 id + 1) | (index2 id + 1) << 16, 0 in a field =
-// not such a key.  key = lo bits | hi bits << length | tag << 40 (PhParams::hop_*)
+// the perfect-hash probe of one record without invalid positions: entry (sample or S) and distance to it.
+// prow = this lane's copy of the planes table, rowbytes = bytes per row of that table.
+__device__ __forceinline__ void ph_probe(const PhSmem &sm, const PhParams &c, const unsigned char *prow, uint32_t rowbytes,
+                                         uint32_t w0, uint32_t w1, uint32_t &e, uint32_t &d) {
+    const uint32_t h = __umulhi(w0, c.k0) + w0 * c.k1 + w1 * c.k2;
+    const uint32_t mul = sm.disp[h >> c.bshift];
+    e = sm.slots[(h * mul) >> c.sshift];
+    const uint2 t = *reinterpret_cast<const uint2 *>(prow + e * rowbytes);
+    const uint32_t lo = w0 & kCompactMask;
+    const uint32_t hi = __funnelshift_r(w0, w1, kCompactField);  // bits 21..52 of the record; 42..52 are zero here
+    d = (uint32_t)__popc((lo ^ t.x) | (hi ^ t.y));
+}
+
+// A barcode half in the shared-memory key sets: (index1 id + 1) | (index2 id + 1) << 16, 0 in a field = not such a key.
+// key = lo bits | hi bits << length | tag << 40 (PhParams::hop_*)
 __device__ __forceinline__ uint32_t ph_hop_find(const PhSmem &sm, const PhParams &c, uint64_t key) {
     const uint32_t w0 = (uint32_t)key, w1 = (uint32_t)(key >> 32);
     const uint32_t h = __umulhi(w0, c.hop_k0) + w0 * c.hop_k1 + w1 * c.hop_k2;
@@ -134,75 +132,42 @@ __device__ __forceinline__ void ph_hop_check(const DevParams &p, const PhParams 
     else if (c1 && d2) atomicAdd(&p.hop_rev[(uint64_t)(c1 - 1u) * p.u2 + (d2 - 1u)], 1ull);
 }
 
-// planes of a read held as hash words: compact record (lo | hi << 21) or wide (w0 = lo, w1 = hi)
-template <bool WIDE>
-__device__ __forceinline__ void ph_planes(uint32_t w0, uint32_t w1, uint32_t &lo, uint32_t &hi) {
-    if (WIDE) {
-        lo = w0;
-        hi = w1;
-    } else {
-        lo = w0 & kCompactMask;
-        hi = __funnelshift_r(w0, w1, kCompactField);  // bits 21..52 of the record; 42..52 are zero for a plain read
-    }
-}
-
-// the perfect-hash probe of one plain read: entry (sample or S) and distance to it.
-// prow = this lane's copy of the planes table, rowbytes = bytes per row of that table.
-template <bool WIDE>
-__device__ __forceinline__ void ph_probe(const PhSmem &sm, const PhParams &c, const unsigned char *prow, uint32_t rowbytes,
-                                         uint32_t w0, uint32_t w1, uint32_t &e, uint32_t &d) {
-    const uint32_t h = __umulhi(w0, c.k0) + w0 * c.k1 + w1 * c.k2;
-    const uint32_t mul = sm.disp[h >> c.bshift];
-    e = sm.slots[(h * mul) >> c.sshift];
-    const uint2 t = *reinterpret_cast<const uint2 *>(prow + e * rowbytes);
-    uint32_t lo, hi;
-    ph_planes<WIDE>(w0, w1, lo, hi);
-    d = (uint32_t)__popc((lo ^ t.x) | (hi ^ t.y));
-}
-
 // verdict of one read of the general path: patch the placeholder the fast path stored and move its count from
 // "Undetermined", where the fast path booked it, to its bin; hop check
-__device__ __forceinline__ void ph_emit(const DevParams &p, const PhParams &c, const PhSmem &sm, bool hop_smem, uint32_t S1,
-                                        uint64_t r, const Rd &rd, const Verdict &v) {
+__device__ __forceinline__ void ph_emit(const DevParams &p, uint32_t *hist, uint32_t S1, uint64_t r, const Rd &rd,
+                                        const Verdict &v) {
     if (v.bin != p.S) {
         p.out_idx[r] = (uint16_t)v.bin;
         if (p.out_dist) p.out_dist[r] = (uint8_t)v.dist;
-        atomicAdd(&sm.hist[min(v.dist, 2u) * S1 + v.bin], 1u);  // metrics.rs:428-437
-        atomicSub(&sm.hist[2u * S1 + p.S], 1u);
-    } else if (p.hop_on) {
-        if (hop_smem && (rd.nmask | rd.xmask) == 0u) ph_hop_check(p, c, sm, rd.lo, rd.hi);
-        else hop_check(p, rd);
+        atomicAdd(&hist[min(v.dist, 2u) * S1 + v.bin], 1u);  // metrics.rs:428-437
+        atomicSub(&hist[2u * S1 + p.S], 1u);
     }
+    if (p.hop_on && v.bin == p.S) hop_check(p, rd);
 }
 
-// VEC: every chunk is full and the three buffers are aligned for the vector accesses (lane i owns consecutive reads).
-// !VEC: any alignment, ragged end (lane i owns reads i, i+32, ...).
-template <uint32_t MODE, bool VEC, bool WIDE>
-__global__ void __launch_bounds__(kPhThreads, 1) sgdx_match_ph(const DevParams p, const PhParams c, const PhFit fit) {
-    constexpr uint32_t RPL = WIDE ? 2u : 4u;  // reads per lane per chunk
-    constexpr uint32_t CHUNK = 32u * RPL;
+// VEC: every chunk is full and the three buffers are aligned for 256 / 64 / 32-bit accesses (lane i owns reads
+// 4i..4i+3 of a chunk).  !VEC: any alignment, ragged end (lane i owns reads i, i+32, i+64, i+96).
+template <uint32_t MODE, bool VEC>
+__global__ void __launch_bounds__(kPhThreads, 1) sgdx_match_ph(const DevParams p, const PhParams c, const PhLean f) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     PhSmem sm;
     const uint32_t bbits = 32u - c.bshift, sbits = 32u - c.sshift;
-    ph_carve(smem_raw, p.S, bbits, sbits, fit, &sm);
+    ph_carve(smem_raw, p.S, bbits, sbits, f.clog, f.hop_smem ? 32u - c.hop_sshift : 0u, 32u - c.hop_bshift, &sm);
     const uint32_t S1 = p.S + 1u, nbins = S1 * 3u;
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const uint32_t ncopies = 1u << fit.clog;
-    const uint32_t lmask = c.lmask;
+    const uint32_t ncopies = 1u << f.clog;
 
     for (uint32_t i = threadIdx.x; i < (1u << bbits); i += kPhThreads) sm.disp[i] = c.disp[i];
     for (uint32_t i = threadIdx.x; i < (1u << sbits); i += kPhThreads) sm.slots[i] = c.slots[i];
-    for (uint32_t i = threadIdx.x; i < (S1 << fit.clog); i += kPhThreads) {
-        const uint32_t s = i >> fit.clog;  // the dummy row is >= 11 mismatches away from any compact record
+    for (uint32_t i = threadIdx.x; i < (S1 << f.clog); i += kPhThreads) {
+        const uint32_t s = i >> f.clog;  // the dummy row is >= 11 mismatches away from any valid record
         sm.planes[i] = s < p.S ? p.table[s] : make_uint2(0u, 0xFFFFFFFFu);
     }
-    for (uint32_t i = threadIdx.x; i < nbins; i += kPhThreads) sm.hist[i] = 0u;
-    if (fit.hsbits) {
-        for (uint32_t i = threadIdx.x; i < (1u << fit.hsbits); i += kPhThreads) sm.hslots[i] = c.hop_slots[i];
-        for (uint32_t i = threadIdx.x; i < (1u << fit.hbbits); i += kPhThreads) sm.hdisp[i] = c.hop_disp[i];
+    for (uint32_t i = threadIdx.x; i <= nbins; i += kPhThreads) sm.hist[i] = 0u;
+    if (f.hop_smem) {
+        for (uint32_t i = threadIdx.x; i < (1u << (32u - c.hop_sshift)); i += kPhThreads) sm.hslots[i] = c.hop_slots[i];
+        for (uint32_t i = threadIdx.x; i < (1u << (32u - c.hop_bshift)); i += kPhThreads) sm.hdisp[i] = c.hop_disp[i];
     }
-    for (uint32_t i = threadIdx.x; i < fit.hdr_total; i += kPhThreads) sm.hdr[i] = p.seed_hdr[i];
-    for (uint32_t i = threadIdx.x; i < fit.ids_total; i += kPhThreads) sm.ids[i] = p.seed_ids[i];
     __syncthreads();
 
     uint64_t *const qrec = sm.qrec + warp * kPhQueue;
@@ -210,45 +175,29 @@ __global__ void __launch_bounds__(kPhThreads, 1) sgdx_match_ph(const DevParams p
     uint64_t *const q2rec = sm.q2rec + warp * kPhQueue2;
     uint32_t *const q2off = sm.q2off + warp * kPhQueue2;
     const unsigned char *const prow = reinterpret_cast<const unsigned char *>(sm.planes + (lane & (ncopies - 1u)));
-    const uint32_t rowbytes = 8u << fit.clog;
+    const uint32_t rowbytes = 8u << f.clog;
     const uint32_t qrec_s = (uint32_t)__cvta_generic_to_shared(qrec), qoff_s = (uint32_t)__cvta_generic_to_shared(qoff);
-    const uint16_t *const seed_hdr = fit.hdr_total ? sm.hdr : p.seed_hdr;
-    const uint16_t *const seed_ids = fit.ids_total ? sm.ids : p.seed_ids;
     uint32_t n1 = 0u, n2 = 0u;  // queue fills, warp-uniform
     const uint64_t total_warps = (uint64_t)gridDim.x * kPhWarps, gwarp = (uint64_t)blockIdx.x * kPhWarps + warp;
-    const uint64_t nchunks = (p.n + CHUNK - 1u) / CHUNK;
+    const uint64_t nchunks = (p.n + kPhChunk - 1u) / kPhChunk;
     const uint32_t below = (1u << lane) - 1u;
-    const bool hop = p.hop_on != 0u, hop_smem = fit.hsbits != 0u;
-    const bool final_radius = c.radius >= p.M;  // a plain read the probe does not decide is NoMatch
-    const uint32_t off0 = VEC ? lane * RPL : lane, offk = VEC ? 1u : 32u;  // chunk offset of my read k = off0 + k * offk
+    const bool hop = p.hop_on != 0u;
+    const uint32_t off0 = VEC ? lane * 4u : lane, offk = VEC ? 1u : 32u;  // chunk offset of my read k = off0 + k * offk
 
-    // The records of a chunk.  Compact: r[k] = record k.  Wide: r[2k] = lo | hi << 32, r[2k+1] = nmask | xmask << 32.
-    // Out-of-range reads of the last chunk look invalid; `live` keeps them out of the counters and the queues.
     auto fetch = [&](uint64_t ch, uint64_t (&r)[4]) {
         if (ch >= nchunks) return;
-        const uint64_t base = ch * CHUNK;
+        const uint64_t base = ch * kPhChunk;
         if (VEC) {
-            const void *src = WIDE ? static_cast<const void *>(c.reads_wide + base + off0) : static_cast<const void *>(c.reads + base + off0);
+            const uint64_t *src = c.reads + base + off0;
             asm volatile("ld.global.nc.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4];"
                          : "=l"(r[0]), "=l"(r[1]), "=l"(r[2]), "=l"(r[3]) : "l"(src));
         } else {
 #pragma unroll
-            for (uint32_t k = 0; k < RPL; k++) {
+            for (uint32_t k = 0; k < 4; k++) {  // out-of-range reads become all-ones records: they look invalid
                 const uint64_t i = base + k * 32u + lane;
-                if (WIDE) {
-                    uint4 v = make_uint4(~0u, ~0u, ~0u, ~0u);
-                    if (i < p.n) v = __ldg(c.reads_wide + i);
-                    r[2 * k] = (uint64_t)v.x | ((uint64_t)v.y << 32);
-                    r[2 * k + 1] = (uint64_t)v.z | ((uint64_t)v.w << 32);
-                } else {
-                    r[k] = i < p.n ? __ldg(c.reads + i) : ~0ull;
-                }
+                r[k] = i < p.n ? __ldg(c.reads + i) : ~0ull;
             }
         }
-    };
-    // wide: does the record carry anything but barcode_len plane bits?
-    auto wide_stray = [&](uint64_t planes, uint64_t masks) -> bool {
-        return ((uint32_t)masks | (uint32_t)(masks >> 32) | (((uint32_t)planes | (uint32_t)(planes >> 32)) & ~lmask)) != 0u;
     };
 
     uint64_t rec[4], nextrec[4];
@@ -258,61 +207,50 @@ __global__ void __launch_bounds__(kPhThreads, 1) sgdx_match_ph(const DevParams p
         const bool final = ch >= nchunks;
         if (!final) {
             fetch(ch + total_warps, nextrec);
-            const uint64_t base = ch * CHUNK;
-            // the reads of a lane phase by phase, so that their dependent shared-memory chains overlap
-            uint32_t bin[RPL], dist[RPL], h[RPL], e[RPL], defer = 0u;
-            uint2 t[RPL];
+            const uint64_t base = ch * kPhChunk;
+            // four reads per lane, phase by phase, so that the four dependent shared-memory chains overlap
+            uint32_t bin[4], dist[4], h[4], e[4], defer = 0u;
+            uint2 t[4];
 #pragma unroll
-            for (uint32_t k = 0; k < RPL; k++) {
-                const uint64_t key = WIDE ? rec[2 * k] : rec[k];
-                const uint32_t w0 = (uint32_t)key, w1 = (uint32_t)(key >> 32);
+            for (uint32_t k = 0; k < 4; k++) {
+                const uint32_t w0 = (uint32_t)rec[k], w1 = (uint32_t)(rec[k] >> 32);
                 h[k] = __umulhi(w0, c.k0) + w0 * c.k1 + w1 * c.k2;
                 e[k] = sm.disp[h[k] >> c.bshift];
             }
 #pragma unroll
-            for (uint32_t k = 0; k < RPL; k++) e[k] = sm.slots[(h[k] * e[k]) >> c.sshift];
+            for (uint32_t k = 0; k < 4; k++) e[k] = sm.slots[(h[k] * e[k]) >> c.sshift];
 #pragma unroll
-            for (uint32_t k = 0; k < RPL; k++) t[k] = *reinterpret_cast<const uint2 *>(prow + e[k] * rowbytes);
+            for (uint32_t k = 0; k < 4; k++) t[k] = *reinterpret_cast<const uint2 *>(prow + e[k] * rowbytes);
 #pragma unroll
-            for (uint32_t k = 0; k < RPL; k++) {
-                const uint64_t key = WIDE ? rec[2 * k] : rec[k];
-                const uint32_t w0 = (uint32_t)key, w1 = (uint32_t)(key >> 32);
-                uint32_t lo, hi;
-                ph_planes<WIDE>(w0, w1, lo, hi);
+            for (uint32_t k = 0; k < 4; k++) {
+                const uint32_t w0 = (uint32_t)rec[k], w1 = (uint32_t)(rec[k] >> 32);
+                const uint32_t lo = w0 & kCompactMask;
+                const uint32_t hi = __funnelshift_r(w0, w1, kCompactField);  // bits 21..52; 42..52 are zero unless stray
                 const uint32_t d = (uint32_t)__popc((lo ^ t[k].x) | (hi ^ t[k].y));
-                // stray: not "barcode_len A/C/G/T bases" -- an invalid position, or bits above the barcode's length
-                const bool stray = WIDE ? wide_stray(rec[2 * k], rec[2 * k + 1]) : ((w0 & c.nm0) | (w1 & c.nm1)) != 0u;
-                bool bad = d > c.radius || stray;
-                if (WIDE) bad = bad || e[k] >= p.S;  // (a compact record cannot come close to the dummy row)
+                const bool stray = ((w0 & c.nm0) | (w1 & c.nm1)) != 0u;  // not "barcode_len A/C/G/T bases"
+                const bool bad = d > p.M || stray;
                 bin[k] = bad ? p.S : e[k];
                 dist[k] = bad ? kNoDist : d;
-                // a read that is not decided here is booked as Undetermined for now; its drain moves the count
+                // a read of the general path is booked as Undetermined for now; its drain moves the count
                 const bool live = VEC || base + k * 32u + lane < p.n;
 #ifndef SGDX_PH_X_NOHIST  // (experiment builds only, tools/build_variants.sh: what the histogram costs)
                 if (live) atomicAdd(&sm.hist[min(dist[k], 2u) * S1 + bin[k]], 1u);
 #endif
-                // deferred: the hop check of a NoMatch read, or the whole read if it is invalid or undecided
-                if (bad && (hop || stray || !final_radius) && live) defer |= 1u << k;
+                // deferred: the hop check of a NoMatch read, or the whole read if it is not plain A/C/G/T
+                if (bad && (hop || stray) && live) defer |= 1u << k;
 #ifdef SGDX_PH_X_NOQ  // (experiment builds only: what the deferred reads cost)
                 defer = 0u;
 #endif
             }
-            // results: a deferred read gets "Undetermined / no distance" now and is patched later if it matches
+            // results: a read of the general path gets "Undetermined / no distance" now and is patched later
             if (VEC) {
                 const uint64_t at = base + off0;
-                if (WIDE) {
-                    *reinterpret_cast<uint32_t *>(p.out_idx + at) = bin[0] | (bin[1] << 16);
-                    if (p.out_dist) *reinterpret_cast<uint16_t *>(p.out_dist + at) = (uint16_t)(dist[0] | (dist[1] << 8));
-                } else {
-                    *reinterpret_cast<uint2 *>(p.out_idx + at) =
-                        make_uint2(bin[0] | (bin[1] << 16), bin[2 % RPL] | (bin[3 % RPL] << 16));
-                    if (p.out_dist)
-                        *reinterpret_cast<uint32_t *>(p.out_dist + at) =
-                            dist[0] | (dist[1] << 8) | (dist[2 % RPL] << 16) | (dist[3 % RPL] << 24);
-                }
+                *reinterpret_cast<uint2 *>(p.out_idx + at) = make_uint2(bin[0] | (bin[1] << 16), bin[2] | (bin[3] << 16));
+                if (p.out_dist)
+                    *reinterpret_cast<uint32_t *>(p.out_dist + at) = dist[0] | (dist[1] << 8) | (dist[2] << 16) | (dist[3] << 24);
             } else {
 #pragma unroll
-                for (uint32_t k = 0; k < RPL; k++) {
+                for (uint32_t k = 0; k < 4; k++) {
                     const uint64_t i = base + k * 32u + lane;
                     if (i < p.n) {
                         p.out_idx[i] = (uint16_t)bin[k];
@@ -322,15 +260,13 @@ __global__ void __launch_bounds__(kPhThreads, 1) sgdx_match_ph(const DevParams p
             }
             if (__any_sync(0xFFFFFFFFu, defer != 0u)) {
 #pragma unroll
-                for (uint32_t k = 0; k < RPL; k++) {
+                for (uint32_t k = 0; k < 4; k++) {
                     const bool mine = (defer >> k) & 1u;
                     const uint32_t votes = __ballot_sync(0xFFFFFFFFu, mine);
-                    if (mine) {  // wide: the planes travel, flagged if the general path has to fetch the masks too
+                    if (mine) {
                         const uint32_t at = n1 + (uint32_t)__popc(votes & below);
-                        uint32_t tag = iter * CHUNK + off0 + k * offk;
-                        if (WIDE && wide_stray(rec[2 * k], rec[(2 * k + 1) % 4])) tag |= 0x80000000u;
-                        asm volatile("st.shared.u64 [%0], %1;" ::"r"(qrec_s + at * 8u), "l"(WIDE ? rec[2 * k] : rec[k]) : "memory");
-                        asm volatile("st.shared.u32 [%0], %1;" ::"r"(qoff_s + at * 4u), "r"(tag) : "memory");
+                        asm volatile("st.shared.u64 [%0], %1;" ::"r"(qrec_s + at * 8u), "l"(rec[k]) : "memory");
+                        asm volatile("st.shared.u32 [%0], %1;" ::"r"(qoff_s + at * 4u), "r"(iter * kPhChunk + off0 + k * offk) : "memory");
                     }
                     n1 += (uint32_t)__popc(votes);
                 }
@@ -340,8 +276,8 @@ __global__ void __launch_bounds__(kPhThreads, 1) sgdx_match_ph(const DevParams p
             for (uint32_t k = 0; k < 4; k++) rec[k] = nextrec[k];
         }
 
-        // ---- deferred reads, 32 at a time: hop check of the plain NoMatch reads (metrics.rs:658-676); the others
-        // move on to the second queue
+        // ---- deferred reads, 32 at a time: hop check of the A/C/G/T-only NoMatch reads (metrics.rs:658-676); the
+        // others move on to the second queue
         while (n1 >= 32u || (final && (n1 | n2))) {
             const uint32_t take = min(n1, 32u);  // 0 when only the second queue is left to flush
             n1 -= take;
@@ -352,12 +288,10 @@ __global__ void __launch_bounds__(kPhThreads, 1) sgdx_match_ph(const DevParams p
                 q = qrec[n1 + lane];
                 off = qoff[n1 + lane];
                 const uint32_t w0 = (uint32_t)q, w1 = (uint32_t)(q >> 32);
-                general = !final_radius || (WIDE ? (off >> 31) != 0u : ((w0 & c.nm0) | (w1 & c.nm1)) != 0u);
+                general = ((w0 & c.nm0) | (w1 & c.nm1)) != 0u;
                 if (!general) {
-                    uint32_t lo, hi;
-                    ph_planes<WIDE>(w0, w1, lo, hi);
-                    if (!WIDE) hi &= kCompactMask;
-                    if (hop_smem) {
+                    const uint32_t lo = w0 & kCompactMask, hi = __funnelshift_r(w0, w1, kCompactField) & kCompactMask;
+                    if (f.hop_smem) {
                         ph_hop_check(p, c, sm, lo, hi);
                     } else {
                         const Rd rd = {lo, hi, 0u, 0u};
@@ -374,27 +308,20 @@ __global__ void __launch_bounds__(kPhThreads, 1) sgdx_match_ph(const DevParams p
             n2 += (uint32_t)__popc(votes);
             __syncwarp();
 
-            // ---- general path: reads with invalid positions or stray bits, and undecided plain reads
+            // ---- general path: reads with invalid positions or stray bits
             while (n2 >= 32u || (final && n1 == 0u && n2)) {
                 const uint32_t take2 = min(n2, 32u);
                 n2 -= take2;
                 bool scan = false;
                 uint64_t r = 0;
-                Rd rd = {0u, 0u, 0u, 0u};
                 if (lane < take2) {
-                    const uint32_t tag = q2off[n2 + lane], e = tag & 0x7FFFFFFFu;
-                    const uint64_t q2 = q2rec[n2 + lane];
-                    r = ((uint64_t)(e / CHUNK) * total_warps + gwarp) * CHUNK + (e % CHUNK);
-                    if (WIDE) {
-                        if (tag >> 31) rd = load_packed(c.reads_wide, r, p.L);  // (rare) the masks are not in the queue
-                        else rd.lo = (uint32_t)q2, rd.hi = (uint32_t)(q2 >> 32);
-                    } else {
-                        rd = rd_of_compact(q2, lmask);
-                    }
+                    const uint32_t e = q2off[n2 + lane];
+                    r = ((uint64_t)(e / kPhChunk) * total_warps + gwarp) * kPhChunk + (e % kPhChunk);
+                    const Rd rd = rd_of_compact(q2rec[n2 + lane], c.lmask);
                     const uint32_t inv = rd.nmask | rd.xmask;
                     uint32_t best = kInfKey, nxt = kInfKey;
                     if (!cannot_match<MODE>(p, rd)) {
-                        if (final_radius && (inv == 0u || (c.single_ok && (inv & (inv - 1u)) == 0u))) {
+                        if (inv == 0u || (c.single_ok && (inv & (inv - 1u)) == 0u)) {
                             // no invalid base (the record only had stray bits): its own key.  One invalid base: the
                             // unique sample within M over the valid positions, if any, is the entry of one of the 4
                             // completions; whatever else the probes return is a real sample scored at its real distance
@@ -402,26 +329,22 @@ __global__ void __launch_bounds__(kPhThreads, 1) sgdx_match_ph(const DevParams p
                             const uint32_t nvar = inv ? 4u : 1u;
                             for (uint32_t b = 0; b < nvar; b++) {
                                 const uint32_t lo = rd.lo | ((b & 1u) ? inv : 0u), hi = rd.hi | ((b >> 1) ? inv : 0u);
-                                const uint64_t key = (uint64_t)lo | ((uint64_t)hi << (WIDE ? 32u : kCompactField));
+                                const uint64_t key = (uint64_t)lo | ((uint64_t)hi << kCompactField);
                                 uint32_t pe, pd;
-                                ph_probe<WIDE>(sm, c, prow, rowbytes, (uint32_t)key, (uint32_t)(key >> 32), pe, pd);
+                                ph_probe(sm, c, prow, rowbytes, (uint32_t)key, (uint32_t)(key >> 32), pe, pd);
                                 if (pe < p.S) {
-                                    const uint2 tt = *reinterpret_cast<const uint2 *>(prow + pe * rowbytes);
-                                    score<MODE>(rd, inv, skip, tt.x, tt.y, pe, best, nxt);
+                                    const uint2 t = *reinterpret_cast<const uint2 *>(prow + pe * rowbytes);
+                                    score<MODE>(rd, inv, skip, t.x, t.y, pe, best, nxt);
                                 }
                             }
-                        } else if (p.seed_C == 0u || (final_radius && c.single_ok)) {
-                            // no seed index; or, with the shortcut valid, only reads with several invalid bases get
-                            // here: too few to be worth a chain of dependent loads at one or two active lanes
-                            scan = true;
-                        } else if (inv == 0u) {
-                            seed_search<MODE, false>(p, seed_hdr, seed_ids, reinterpret_cast<const uint2 *>(prow), rd, best, nxt, ncopies);
-                        } else if (!seed_search<MODE, true>(p, seed_hdr, seed_ids, reinterpret_cast<const uint2 *>(prow), rd, best, nxt,
-                                                            ncopies)) {
+                        } else if (c.single_ok || p.seed_C == 0u ||
+                                   !seed_search<MODE, true>(p, p.seed_hdr, p.seed_ids, p.table, rd, best, nxt)) {
+                            // with the shortcut valid only reads with several invalid bases get here: too few to be
+                            // worth a chain of dependent global loads at one or two active lanes
                             scan = true;
                         }
                     }
-                    if (!scan) ph_emit(p, c, sm, hop_smem, S1, r, rd, apply_rules<MODE>(p, rd, best, nxt));
+                    if (!scan) ph_emit(p, sm.hist, S1, r, rd, apply_rules<MODE>(p, rd, best, nxt));
                 }
                 // whatever the seed index cannot enumerate: one warp per read over all samples
                 uint32_t todo = __ballot_sync(0xFFFFFFFFu, scan);
@@ -429,13 +352,9 @@ __global__ void __launch_bounds__(kPhThreads, 1) sgdx_match_ph(const DevParams p
                     const uint32_t src = (uint32_t)__ffs(todo) - 1u;
                     todo &= todo - 1u;
                     const uint64_t qr = __shfl_sync(0xFFFFFFFFu, r, src);
-                    Rd qrd;
-                    qrd.lo = __shfl_sync(0xFFFFFFFFu, rd.lo, src);
-                    qrd.hi = __shfl_sync(0xFFFFFFFFu, rd.hi, src);
-                    qrd.nmask = __shfl_sync(0xFFFFFFFFu, rd.nmask, src);
-                    qrd.xmask = __shfl_sync(0xFFFFFFFFu, rd.xmask, src);
+                    const Rd qrd = rd_of_compact(__ldg(c.reads + qr), c.lmask);
                     const Verdict qv = warp_scan<MODE>(p, p.table, qrd, lane);
-                    if (lane == 0u) ph_emit(p, c, sm, hop_smem, S1, qr, qrd, qv);
+                    if (lane == 0u) ph_emit(p, sm.hist, S1, qr, qrd, qv);
                 }
                 __syncwarp();
             }
@@ -453,50 +372,41 @@ __global__ void __launch_bounds__(kPhThreads, 1) sgdx_match_ph(const DevParams p
     }
 }
 
-template <uint32_t MODE, bool VEC, bool WIDE>
-static cudaError_t launch_ph_t(const DevParams &p, const PhParams &c, const PhFit &fit, int sms, cudaStream_t stream) {
+template <uint32_t MODE, bool VEC>
+static cudaError_t launch_ph_t(const DevParams &p, const PhParams &c, const PhLean &f, int sms, cudaStream_t stream) {
     if (p.n == 0) return cudaSuccess;
-    constexpr uint32_t CHUNK = WIDE ? 64u : 128u;
-    const size_t smem = ph_carve(nullptr, p.S, 32u - c.bshift, 32u - c.sshift, fit, nullptr);
-    auto kern = sgdx_match_ph<MODE, VEC, WIDE>;
+    const size_t smem = ph_carve(nullptr, p.S, 32u - c.bshift, 32u - c.sshift, f.clog, f.hop_smem ? 32u - c.hop_sshift : 0u,
+                                 32u - c.hop_bshift, nullptr);
+    auto kern = sgdx_match_ph<MODE, VEC>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    const uint64_t chunks = (p.n + CHUNK - 1u) / CHUNK;
+    const uint64_t chunks = (p.n + kPhChunk - 1u) / kPhChunk;
     uint64_t grid = (chunks + kPhWarps - 1u) / kPhWarps;
     if (grid > (uint64_t)sms) grid = (uint64_t)sms;  // one persistent CTA per SM
-    kern<<<(uint32_t)grid, kPhThreads, smem, stream>>>(p, c, fit);
+    kern<<<(uint32_t)grid, kPhThreads, smem, stream>>>(p, c, f);
     return cudaGetLastError();
 }
 
-template <bool WIDE>
-static cudaError_t launch_ph_w(const DevParams &p0, const PhParams &c0, uint32_t mode, int sms, cudaStream_t stream) {
+// Aligned buffers: the full chunks go through the vector kernel and the last n % 128 reads through the general one
+// (a second, one-CTA launch); anything else through the general one.
+cudaError_t launch_ph(const DevParams &p0, const PhParams &c0, uint32_t mode, int sms, cudaStream_t stream) {
     DevParams p = p0;
     PhParams c = c0;
-    const PhFit fit = ph_fit(p, c);
+    const PhLean f = ph_fit(p.S, c);
     const bool ham = mode == kModeHamming;
-    const uint64_t chunk = WIDE ? 64u : 128u;
-    const void *in = WIDE ? static_cast<const void *>(c.reads_wide) : static_cast<const void *>(c.reads);
-    const bool aligned = (reinterpret_cast<uintptr_t>(in) & 31u) == 0u &&
-                         (reinterpret_cast<uintptr_t>(p.out_idx) & (WIDE ? 3u : 7u)) == 0u &&
-                         (reinterpret_cast<uintptr_t>(p.out_dist) & (WIDE ? 1u : 3u)) == 0u;
-    if (aligned) {  // the full chunks through the vector kernel, the last reads through the general one (a one-CTA launch)
-        const uint64_t n_main = p.n - p.n % chunk;
+    const bool aligned = (reinterpret_cast<uintptr_t>(c.reads) & 31u) == 0u && (reinterpret_cast<uintptr_t>(p.out_idx) & 7u) == 0u &&
+                         (reinterpret_cast<uintptr_t>(p.out_dist) & 3u) == 0u;
+    if (aligned) {
+        const uint64_t n_main = p.n & ~(uint64_t)(kPhChunk - 1u);
         p.n = n_main;
-        cudaError_t e = ham ? launch_ph_t<kModeHamming, true, WIDE>(p, c, fit, sms, stream)
-                            : launch_ph_t<kModePreCompute, true, WIDE>(p, c, fit, sms, stream);
+        cudaError_t e = ham ? launch_ph_t<kModeHamming, true>(p, c, f, sms, stream) : launch_ph_t<kModePreCompute, true>(p, c, f, sms, stream);
         if (e != cudaSuccess) return e;
         p.n = p0.n - n_main;
-        if (WIDE) c.reads_wide += n_main;
-        else c.reads += n_main;
+        c.reads += n_main;
         p.out_idx += n_main;
         if (p.out_dist) p.out_dist += n_main;
     }
-    return ham ? launch_ph_t<kModeHamming, false, WIDE>(p, c, fit, sms, stream)
-               : launch_ph_t<kModePreCompute, false, WIDE>(p, c, fit, sms, stream);
-}
-
-cudaError_t launch_ph(const DevParams &p, const PhParams &c, uint32_t mode, int sms, cudaStream_t stream) {
-    return c.wide ? launch_ph_w<true>(p, c, mode, sms, stream) : launch_ph_w<false>(p, c, mode, sms, stream);
+    return ham ? launch_ph_t<kModeHamming, false>(p, c, f, sms, stream) : launch_ph_t<kModePreCompute, false>(p, c, f, sms, stream);
 }
 
 }  // namespace sgdx

@@ -128,7 +128,7 @@ bool ph_build_hop(const std::vector<uint64_t> &keys1, const std::vector<uint32_t
             vals.push_back(e.first | e.second);
         }
     }
-    if (keys.empty() || keys.size() > 3000u) return false;  // 32 KB of slots at most
+    if (keys.empty() || keys.size() > 5000u) return false;  // 64 KB of slots at most
     uint32_t sbits = 4, bbits = 2;
     while ((double)keys.size() > 0.7 * (double)(1u << sbits)) sbits++;
     while (((size_t)3 << bbits) < keys.size()) bbits++;
@@ -144,91 +144,115 @@ bool ph_build_hop(const std::vector<uint64_t> &keys1, const std::vector<uint32_t
     return true;
 }
 
+// keys = the strings within `radius` substitutions of a barcode, entry[i] = verdict of keys[i]
+static void ph_enumerate(const PhRules &r, const std::vector<PhPlanes> &table, bool wide, uint32_t radius,
+                         std::vector<uint64_t> *keys_out, std::vector<uint16_t> *entry_out) {
+    const uint32_t S = r.S, L = r.L;
+    auto key_of = [&](uint32_t lo, uint32_t hi) { return wide ? (uint64_t)lo | ((uint64_t)hi << 32) : record_of(lo, hi); };
+    struct Node {  // strings at exact distance k from sample s, each once (substituted positions ascending)
+        uint32_t lo, hi, next_pos;
+    };
+    std::vector<uint64_t> &keys = *keys_out;
+    keys.clear();
+    std::vector<Node> frontier, grown;
+    for (uint32_t s = 0; s < S; s++) {
+        frontier.assign(1, Node{table[s].lo, table[s].hi, 0u});
+        keys.push_back(key_of(table[s].lo, table[s].hi));
+        for (uint32_t k = 1; k <= radius; k++) {
+            grown.clear();
+            for (const Node &nd : frontier)
+                for (uint32_t j = nd.next_pos; j < L; j++) {
+                    const uint32_t cur = ((nd.lo >> j) & 1u) | (((nd.hi >> j) & 1u) << 1);
+                    for (uint32_t b = 0; b < 4; b++) {
+                        if (b == cur) continue;
+                        const uint32_t lo = (nd.lo & ~(1u << j)) | ((b & 1u) << j);
+                        const uint32_t hi = (nd.hi & ~(1u << j)) | ((b >> 1) << j);
+                        grown.push_back(Node{lo, hi, j + 1u});
+                        keys.push_back(key_of(lo, hi));
+                    }
+                }
+            frontier.swap(grown);
+        }
+    }
+    std::sort(keys.begin(), keys.end());
+    keys.erase(std::unique(keys.begin(), keys.end()), keys.end());
+    entry_out->resize(keys.size());
+    for (size_t i = 0; i < keys.size(); i++) {
+        const uint32_t lo = wide ? (uint32_t)keys[i] : (uint32_t)keys[i] & kFieldMask;
+        const uint32_t hi = wide ? (uint32_t)(keys[i] >> 32) : (uint32_t)(keys[i] >> kField) & kFieldMask;
+        (*entry_out)[i] = (uint16_t)verdict(r, table, lo, hi);
+    }
+}
+
+static double ph_key_estimate(uint32_t S, uint32_t L, uint32_t radius) {  // S * sum_k C(L,k) 3^k, before deduplication
+    double per = 0.0, term = 1.0;
+    for (uint32_t k = 0; k <= radius; k++) {
+        per += term;
+        term = term * 3.0 * (double)(L - k) / (double)(k + 1u);
+    }
+    return per * S;
+}
+
+// one level: perfect hash of the radius-neighbourhood into at most 2^max_sbits slots
+static bool ph_level(const PhRules &r, const std::vector<PhPlanes> &table, bool wide, uint32_t radius, uint32_t max_sbits,
+                     size_t smem_limit, size_t (*smem_bytes)(uint32_t, uint32_t, uint32_t), PhLevel *out) {
+    if (ph_key_estimate(r.S, r.L, radius) > 3.0 * (double)(1u << max_sbits)) return false;
+    std::vector<uint64_t> keys;
+    std::vector<uint16_t> entry;
+    ph_enumerate(r, table, wide, radius, &keys, &entry);
+    const size_t nk = keys.size();
+    uint32_t sbits = 6;
+    while ((double)nk > 0.86 * (double)(1u << sbits)) sbits++;
+    if (sbits > max_sbits) return false;
+    uint32_t bbits = 4;
+    while (((size_t)3 << bbits) < nk) bbits++;  // <= 3 keys per bucket on average
+    PhLevel t;
+    std::vector<uint32_t> where;
+    uint32_t kset = 0;
+    if (!chd_place(keys, bbits, sbits, max_sbits, r.S, smem_limit, smem_bytes, &t.disp, &where, &t.bshift, &t.sshift, &kset)) return false;
+    const uint32_t *K = chd_multipliers(kset);
+    t.k0 = K[0];
+    t.k1 = K[1];
+    t.k2 = K[2];
+    t.slots.assign((size_t)1 << (32u - t.sshift), (uint16_t)r.S);
+    for (size_t i = 0; i < nk; i++) t.slots[where[i]] = entry[i];
+    for (size_t i = 0; i < nk; i++)  // every key reaches its own entry through the kernel's arithmetic
+        if (ph_level_lookup(t, keys[i]) != entry[i]) return false;
+    t.radius = radius;
+    t.nkeys = (uint32_t)nk;
+    *out = std::move(t);
+    return true;
+}
+
 bool ph_build(const PhRules &r, const std::vector<PhPlanes> &table, bool wide, size_t smem_limit,
               size_t (*smem_bytes)(uint32_t, uint32_t, uint32_t), PhTables *out) {
     const uint32_t S = r.S, L = r.L, M = r.M;
     if (L > (wide ? 32u : kField) || S >= 0xFFFFu) return false;
-    auto key_of = [&](uint32_t lo, uint32_t hi) { return wide ? (uint64_t)lo | ((uint64_t)hi << 32) : record_of(lo, hi); };
-    // the largest radius <= M (and <= 10: the dummy row of the planes table) whose key set fits the slots
-    for (int radius = (int)std::min(std::min(M, L), 10u); radius >= 0; radius--) {
-        {   // S * sum_k C(L,k) 3^k keys before deduplication
-            double per = 0.0, term = 1.0;
-            for (uint32_t k = 0; k <= (uint32_t)radius; k++) {
-                per += term;
-                term = term * 3.0 * (double)(L - k) / (double)(k + 1u);
-            }
-            if (per * S > 3.0 * (double)(1u << kMaxSlotBits)) continue;
-        }
-        // strings at exact distance k from sample s, each once (substituted positions ascending)
-        struct Node {
-            uint32_t lo, hi, next_pos;
-        };
-        std::vector<uint64_t> keys;
-        std::vector<Node> frontier, grown;
-        for (uint32_t s = 0; s < S; s++) {
-            frontier.assign(1, Node{table[s].lo, table[s].hi, 0u});
-            keys.push_back(key_of(table[s].lo, table[s].hi));
-            for (uint32_t k = 1; k <= (uint32_t)radius; k++) {
-                grown.clear();
-                for (const Node &nd : frontier)
-                    for (uint32_t j = nd.next_pos; j < L; j++) {
-                        const uint32_t cur = ((nd.lo >> j) & 1u) | (((nd.hi >> j) & 1u) << 1);
-                        for (uint32_t b = 0; b < 4; b++) {
-                            if (b == cur) continue;
-                            const uint32_t lo = (nd.lo & ~(1u << j)) | ((b & 1u) << j);
-                            const uint32_t hi = (nd.hi & ~(1u << j)) | ((b >> 1) << j);
-                            grown.push_back(Node{lo, hi, j + 1u});
-                            keys.push_back(key_of(lo, hi));
-                        }
-                    }
-                frontier.swap(grown);
-            }
-        }
-        std::sort(keys.begin(), keys.end());
-        keys.erase(std::unique(keys.begin(), keys.end()), keys.end());
-        const size_t nk = keys.size();
-        uint32_t sbits = 6;
-        while ((double)nk > 0.86 * (double)(1u << sbits)) sbits++;
-        if (sbits > kMaxSlotBits) continue;
-        uint32_t bbits = 4;
-        while (((size_t)3 << bbits) < nk) bbits++;  // <= 3 keys per bucket on average
-        std::vector<uint16_t> entry(nk);
-        for (size_t i = 0; i < nk; i++) {
-            const uint32_t lo = wide ? (uint32_t)keys[i] : (uint32_t)keys[i] & kFieldMask;
-            const uint32_t hi = wide ? (uint32_t)(keys[i] >> 32) : (uint32_t)(keys[i] >> kField) & kFieldMask;
-            entry[i] = (uint16_t)verdict(r, table, lo, hi);
-        }
-        PhTables t;
-        std::vector<uint32_t> where;
-        uint32_t kset = 0;
-        if (!chd_place(keys, bbits, sbits, kMaxSlotBits, S, smem_limit, smem_bytes, &t.disp, &where, &t.bshift, &t.sshift, &kset))
-            continue;
-        const uint32_t *K = chd_multipliers(kset);
-        t.k0 = K[0];
-        t.k1 = K[1];
-        t.k2 = K[2];
-        t.slots.assign((size_t)1 << (32u - t.sshift), (uint16_t)S);
-        for (size_t i = 0; i < nk; i++) t.slots[where[i]] = entry[i];
-        bool ok = true;
-        for (size_t i = 0; i < nk && ok; i++) ok = ph_lookup(t, keys[i]) == entry[i];  // every key reaches its own entry
-        if (!ok) continue;
-        const uint32_t lmask = L >= 32u ? 0xFFFFFFFFu : (1u << L) - 1u;
-        t.lmask = lmask;
-        t.nm0 = wide ? 0u : ~(lmask | (lmask << kField));
-        t.nm1 = wide ? 0u : ~(lmask >> (32u - kField));
-        uint32_t dmin = 0xFFFFu;
-        for (uint32_t i = 0; i < S && dmin > 0; i++)
-            for (uint32_t j = i + 1; j < S; j++)
-                dmin = std::min(dmin, (uint32_t)__builtin_popcount((table[i].lo ^ table[j].lo) | (table[i].hi ^ table[j].hi)));
-        t.dmin = dmin;
-        t.single_ok = (uint64_t)dmin > 2ull * M + r.delta + 1ull ? 1u : 0u;
-        t.nkeys = (uint32_t)nk;
-        t.radius = (uint32_t)radius;
-        t.wide = wide ? 1u : 0u;
-        *out = std::move(t);
-        return true;
-    }
-    return false;
+    const uint32_t top = std::min(std::min(M, L), 10u);  // 10: the dummy row of the planes table
+    // first level (shared memory): the largest radius whose key set fits the slots
+    PhTables t;
+    bool have = false;
+    for (int radius = (int)top; radius >= 0 && !have; radius--)
+        have = ph_level(r, table, wide, (uint32_t)radius, kMaxSlotBits, smem_limit, smem_bytes, &t.a);
+    if (!have) return false;
+    // second level (global memory, L2 resident): when the first stops short of max_mismatches, the largest radius
+    // above it that stays within 2^18 slots
+    if (t.a.radius < top)
+        for (uint32_t radius = top; radius > t.a.radius; radius--)
+            if (ph_level(r, table, wide, radius, 18u, 0, nullptr, &t.b)) break;
+    const uint32_t lmask = L >= 32u ? 0xFFFFFFFFu : (1u << L) - 1u;
+    t.lmask = lmask;
+    t.nm0 = wide ? 0u : ~(lmask | (lmask << kField));
+    t.nm1 = wide ? 0u : ~(lmask >> (32u - kField));
+    uint32_t dmin = 0xFFFFu;
+    for (uint32_t i = 0; i < S && dmin > 0; i++)
+        for (uint32_t j = i + 1; j < S; j++)
+            dmin = std::min(dmin, (uint32_t)__builtin_popcount((table[i].lo ^ table[j].lo) | (table[i].hi ^ table[j].hi)));
+    t.dmin = dmin;
+    t.single_ok = (uint64_t)dmin > 2ull * M + r.delta + 1ull ? 1u : 0u;
+    t.wide = wide ? 1u : 0u;
+    *out = std::move(t);
+    return true;
 }
 
 }  // namespace sgdx
@@ -261,12 +285,14 @@ int probe(const sgdx_config *cfg, const uint8_t *barcodes, const uint64_t *compa
     const bool have = ph_build(r, table, wide, 0, nullptr, &t);
     if (info) {
         info[0] = have ? 1u : 0u;
-        info[1] = t.nkeys;
-        info[2] = have ? 32u - t.bshift : 0u;
-        info[3] = have ? 32u - t.sshift : 0u;
+        info[1] = t.a.nkeys;
+        info[2] = have ? 32u - t.a.bshift : 0u;
+        info[3] = have ? 32u - t.a.sshift : 0u;
         info[4] = t.single_ok;
         info[5] = t.dmin;
-        info[6] = t.radius;
+        info[6] = t.a.radius;
+        info[7] = t.b.slots.empty() ? 0u : t.b.radius;
+        info[8] = t.b.nkeys;
     }
     if (!have) return SGDX_OK;
     for (uint64_t i = 0; i < n; i++) {
@@ -289,13 +315,23 @@ int probe(const sgdx_config *cfg, const uint8_t *barcodes, const uint64_t *compa
             out_dist[i] = 0xFEu;
             continue;
         }
-        const uint32_t e = ph_lookup(t, key);
-        const uint32_t tlo = e < S ? table[e].lo : 0u, thi = e < S ? table[e].hi : 0xFFFFFFFFu;
-        const uint32_t d = (uint32_t)__builtin_popcount((lo ^ tlo) | (hi ^ thi));
-        if (e < S && d <= t.radius) {
-            out_idx[i] = (uint16_t)e;
-            out_dist[i] = (uint8_t)d;
-        } else if (t.radius >= r.M) {
+        // first level, then (for what it leaves undecided) the second, as the kernel does
+        bool decided = false;
+        uint32_t reach = 0;
+        for (const PhLevel *lv : {&t.a, &t.b}) {
+            if (lv->slots.empty() || decided) continue;
+            const uint32_t e = ph_level_lookup(*lv, key);
+            const uint32_t tlo = e < S ? table[e].lo : 0u, thi = e < S ? table[e].hi : 0xFFFFFFFFu;
+            const uint32_t d = (uint32_t)__builtin_popcount((lo ^ tlo) | (hi ^ thi));
+            reach = lv->radius;
+            if (e < S && d <= lv->radius) {
+                out_idx[i] = (uint16_t)e;
+                out_dist[i] = (uint8_t)d;
+                decided = true;
+            }
+        }
+        if (decided) continue;
+        if (reach >= r.M) {
             out_idx[i] = (uint16_t)S;
             out_dist[i] = (uint8_t)SGDX_NO_DIST;
         } else {  // undecided: the kernel's general path searches the seed index

@@ -18,12 +18,17 @@ struct PhPlanes {
     uint32_t lo, hi;
 };
 
-struct PhTables {
+struct PhLevel {  // one perfect hash: keys = the strings within `radius` substitutions of a barcode
     std::vector<uint16_t> disp, slots;
     uint32_t bshift = 0, sshift = 0, k0 = 0, k1 = 0, k2 = 0;
-    uint32_t nm0 = 0, nm1 = 0, lmask = 0, single_ok = 0, dmin = 0, nkeys = 0;
-    uint32_t radius = 0;  // keys = strings within this many substitutions of a barcode (<= max_mismatches)
-    uint32_t wide = 0;    // keys are lo | hi << 32 (barcodes of up to 32 bases) instead of compact records
+    uint32_t radius = 0, nkeys = 0;
+};
+
+struct PhTables {
+    PhLevel a;  // first level (shared memory): the largest radius <= max_mismatches that fits 2^15 slots
+    PhLevel b;  // second level (global memory; empty when a.radius == max_mismatches or nothing larger fits 2^18 slots)
+    uint32_t nm0 = 0, nm1 = 0, lmask = 0, single_ok = 0, dmin = 0;
+    uint32_t wide = 0;  // keys are lo | hi << 32 (barcodes of up to 32 bases) instead of compact records
 };
 
 struct PhHopTables {
@@ -53,9 +58,9 @@ bool ph_build(const PhRules &r, const std::vector<PhPlanes> &table, bool wide, s
               size_t (*smem_bytes)(uint32_t S, uint32_t bbits, uint32_t sbits), PhTables *out);
 
 // the kernel's probe in host arithmetic: entry (sample or S) for a read without invalid positions, given as its key
-// (compact record, or lo | hi << 32 when t.wide)
-inline uint32_t ph_lookup(const PhTables &t, uint64_t rec) {
-    const uint32_t w0 = (uint32_t)rec, w1 = (uint32_t)(rec >> 32);
+// (compact record, or lo | hi << 32 for wide tables)
+inline uint32_t ph_level_lookup(const PhLevel &t, uint64_t key) {
+    const uint32_t w0 = (uint32_t)key, w1 = (uint32_t)(key >> 32);
     const uint32_t h = (uint32_t)(((uint64_t)w0 * t.k0) >> 32) + w0 * t.k1 + w1 * t.k2;
     return t.slots[(h * (uint32_t)t.disp[h >> t.bshift]) >> t.sshift];
 }

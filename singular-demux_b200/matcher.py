@@ -232,6 +232,9 @@ class GpuMatcher:
         self.sync(slot)
         return idx, dist
 
+    def submit_packed_ptr(self, rec_ptr: int, n: int, idx_ptr: int, dist_ptr: int, slot: int = 0) -> None:
+        check(lib().sgdx_match_packed_batch(self._h, slot, rec_ptr, n, idx_ptr, dist_ptr or None), "sgdx_match_packed_batch")
+
     def submit_compact_ptr(self, rec_ptr: int, n: int, idx_ptr: int, dist_ptr: int, slot: int = 0) -> None:
         check(lib().sgdx_match_compact_batch(self._h, slot, rec_ptr, n, idx_ptr, dist_ptr or None),
               "sgdx_match_compact_batch")

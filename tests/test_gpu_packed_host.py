@@ -82,7 +82,7 @@ def test_c3_table_runs_the_perfect_hash_kernel_on_16_byte_records(n, shift):
     for kind in (sg.MatcherKind.CachedHammingDistance, sg.MatcherKind.PreCompute):
         for (M, D, F, mnc) in [(3, 1, 1, None), (1, 2, 1, None), (3, 1, 0, 2), (0, 0, 0, None)]:
             m = CLS[kind]([bytes(t) for t in table], M, D, F, max_no_calls=mnc, index_lengths=il)
-            assert m.packed_kernel_name() == "sgdx_match_ph" and m.path_flags() & 64
+            assert m.packed_kernel_name() == "sgdx_match_phx" and m.path_flags() & 64
             idx, dist = _run_packed_device(m, reads, shift)
             per, totals = m.counters()
             assert totals["total_templates"] == n
@@ -121,7 +121,7 @@ def test_wide_records_on_close_tables(seed, S, L, i1, M, D):
     for kind in (sg.MatcherKind.CachedHammingDistance, sg.MatcherKind.PreCompute):
         for (F, mnc) in ((1, None), (0, 1)):
             m = CLS[kind]([bytes(t) for t in table], M, D, F, max_no_calls=mnc, index_lengths=il)
-            assert m.packed_kernel_name() == "sgdx_match_ph"
+            assert m.packed_kernel_name() == "sgdx_match_phx"
             idx, _ = _run_packed_device(m, reads, 0, with_dist=False)
             cfg = orc.Config(S, L, M, D, F, -1 if mnc is None else mnc, ORC_KIND[kind], il[0] if il else 0, il[1] if il else 0)
             want = orc.COracle(cfg, [bytes(t) for t in table], force_closed_form=True).run(reads, threads=8, use_cache=True)
@@ -146,7 +146,7 @@ def test_c2_at_two_mismatches_uses_radius_one_and_the_seed_index():
             st = sg.BarcodeAssignmentStage([sg.SampleMetadata(f"s{i}", bytes(b), i) for i, b in enumerate(table)] +
                                            [sg.SampleMetadata(sg.UNDETERMINED_NAME, b"N" * 20, len(table))],
                                            CLS[kind], M, D, 1, None, w.index_lengths)
-            assert st.matcher.compact_kernel_name() == "sgdx_match_ph"
+            assert st.matcher.compact_kernel_name() == "sgdx_match_phx"
             got = st.demultiplex(reads, compact=True, pack_threads=4)
             cfg = orc.Config(len(table), 20, M, D, 1, -1, ORC_KIND[kind], 10, 10)
             want = orc.COracle(cfg, [bytes(t) for t in table], force_closed_form=True).run(reads, threads=8, use_cache=True)

@@ -23,7 +23,7 @@ def probe(table, M, D, matcher, reads):
     rec = sg.pack_compact_host(reads)
     idx = np.empty(len(reads), dtype=np.uint16)
     dist = np.empty(len(reads), dtype=np.uint8)
-    info = (C.c_uint32 * 7)()
+    info = (C.c_uint32 * 9)()
     tb = np.ascontiguousarray(table)
     rc = sg.lib().sgdx_ph_probe_host(C.byref(cfg), tb.ctypes.data, rec.ctypes.data, len(reads), idx.ctypes.data,
                                      dist.ctypes.data, info)
@@ -122,7 +122,7 @@ def test_reads_with_invalid_positions_are_deferred_and_big_key_sets_shrink():
     assert np.array_equal(idx[~bad], np.arange(64)[~bad])
     # 384 x 20 bases at two mismatches: 384 * 1771 strings are too many -- the key set falls back to radius 1
     _, _, info2 = probe(table, 2, 1, 1, reads[:1])
-    assert info2[0] == 1 and info2[6] == 1 and info2[1] == 384 * 61
+    assert info2[0] == 1 and info2[6] == 1 and info2[1] == 384 * 61 and info2[7] == 0
     assert info[4] == 1 and info[5] >= 6  # min pairwise distance 6 > 2*1 + 2 + 1: single-N shortcut valid
 
 
@@ -132,7 +132,7 @@ def probe_wide(table, M, D, matcher, reads):
     rec = sg.pack_host(reads)
     idx = np.empty(len(reads), dtype=np.uint16)
     dist = np.empty(len(reads), dtype=np.uint8)
-    info = (C.c_uint32 * 7)()
+    info = (C.c_uint32 * 9)()
     tb = np.ascontiguousarray(table)
     rc = sg.lib().sgdx_ph_probe_host_wide(C.byref(cfg), tb.ctypes.data, rec.ctypes.data, len(reads), idx.ctypes.data,
                                           dist.ctypes.data, info)
@@ -143,7 +143,7 @@ def probe_wide(table, M, D, matcher, reads):
 def _check_decided(idx, dist, info, table, M, reads, want_idx, want_dist):
     """Decided reads carry the oracle's verdict; the undecided ones (dist 0xFD) are exactly the plain reads further than
     the radius from every barcode; with radius == M nothing is undecided."""
-    radius = info[6]
+    radius = max(info[6], info[7])  # what the two levels decide together
     undecided = (idx == 0xFFFF) & (dist == 0xFD)
     deferred = (idx == 0xFFFF) & (dist == 0xFE)
     decided = ~(undecided | deferred)
@@ -173,10 +173,10 @@ def test_radius_smaller_than_max_mismatches_and_wide_keys(cfg_name, M, D):
         assert info[0] == 1, info
         want_idx, want_dist = oracle_run(table, M, D, kind, reads)
         radius = _check_decided(idx, dist, info, table, M, reads, want_idx, want_dist)
-    if cfg_name == "C3":
-        assert radius == (1 if M >= 1 and S * (1 + 3 * L) < 28000 else 0) and (info[1] == 1536 or M == 0 or radius)
-    if cfg_name == "C2" and M >= 2:
-        assert radius == 1 and info[1] == 384 * 61
+    if cfg_name == "C3":  # first level: the 1536 barcodes; second level (global memory): their 73 x 1536 neighbours
+        assert info[6] == 0 and info[1] == 1536 and info[7] == min(M, 1) and (M == 0 or info[8] == 1536 * 73)
+    if cfg_name == "C2" and M >= 2:  # 384 x 1771 strings within two substitutions fit neither level
+        assert info[6] == 1 and info[1] == 384 * 61 and info[7] == 0
 
 
 @pytest.mark.parametrize("seed,S,L,M,D", [(21, 50, 24, 1, 1), (22, 20, 32, 1, 2), (23, 8, 32, 2, 0), (24, 100, 22, 1, 3), (25, 300, 26, 1, 1)])
