@@ -174,6 +174,9 @@ const char *sgdx_packed_kernel_name(const sgdx_handle *h);
                                      sgdx_read records above): the A/C/G/T strings within a radius of the barcodes (up to
                                      max_mismatches, as many as ~28 000 slots hold) sit in a perfect hash with their
                                      precomputed verdicts; SGDX_DISABLE_PH=1 at sgdx_create turns it off */
+#define SGDX_PATH_SHORT_SEED 128u  /* the perfect hash stops short of max_mismatches (C3: 1536 x 24 bases at 3 mismatches) and
+                                     what it leaves undecided searches a seed index of max_mismatches + 1 chunks whose
+                                     verdict is checked against the table's minimum pairwise distance */
 uint32_t sgdx_path_flags(const sgdx_handle *h);
 /* Number of kernel launches issued through this handle so far. */
 uint64_t sgdx_launch_count(const sgdx_handle *h);

@@ -16,6 +16,7 @@ KERNEL_AUTO, KERNEL_DIRECT, KERNEL_SEEDED = 0, 1, 2
 NO_DIST = 0xFF
 PATH_SEED_INDEX, PATH_EXACT, PATH_NEIGHBOURS, PATH_HOP_DIRECT = 1, 2, 4, 8
 PATH_PERFECT_HASH = 64
+PATH_SHORT_SEED = 128
 COMPACT_MAX_LEN = 21
 MAX_BARCODE_LEN = 32
 MAX_SAMPLES = 8192

@@ -272,6 +272,58 @@ static int build_ph_table(sgdx_handle *h, const std::vector<uint2> &table) {
         h->ph.b_k2 = t.b.k2;
         h->ph.b_radius = t.b.radius;
     }
+    if (t.a.radius < p.M && (uint64_t)p.M + 1u <= p.L && p.M + 1u <= 8u && (uint64_t)(p.M + 1u) * p.S <= 0xFFFFu) {
+        // short seed index (PhParams::ms_*): max_mismatches + 1 chunks keyed by their first <= 6 bases
+        const uint32_t C = p.M + 1u, S = p.S, L = p.L;
+        const uint32_t wmax = C <= 4u ? 6u : 5u;  // headers <= 32 KB
+        std::vector<uint32_t> pos(C), w(C), off(C);
+        uint32_t total = 0;
+        for (uint32_t c = 0; c < C; c++) {
+            const uint32_t a = (uint32_t)((uint64_t)c * L / C), b = (uint32_t)((uint64_t)(c + 1) * L / C);
+            pos[c] = a;
+            w[c] = std::min(b - a, wmax);
+            off[c] = total;
+            total += (1u << (2 * w[c])) + 1u;
+            h->ph.ms_desc[c] = pos[c] | (w[c] << 8) | (off[c] << 16);
+        }
+        std::vector<uint16_t> hdr(total, 0), ids((size_t)C * S, 0);
+        for (uint32_t c = 0; c < C; c++) {
+            const uint32_t wm = (1u << w[c]) - 1u, nb = 1u << (2 * w[c]);
+            auto key_of = [&](uint32_t s) { return ((table[s].x >> pos[c]) & wm) | (((table[s].y >> pos[c]) & wm) << w[c]); };
+            std::vector<uint32_t> cnt(nb, 0u);
+            for (uint32_t s = 0; s < S; s++) cnt[key_of(s)]++;
+            uint32_t run = c * S;
+            for (uint32_t k = 0; k < nb; k++) {
+                hdr[off[c] + k] = (uint16_t)run;
+                run += cnt[k];
+                cnt[k] = 0;
+            }
+            hdr[off[c] + nb] = (uint16_t)run;
+            for (uint32_t s = 0; s < S; s++) {
+                const uint32_t k = key_of(s);
+                ids[hdr[off[c] + k] + cnt[k]++] = (uint16_t)s;
+            }
+        }
+        if (total < 0x10000u) {  // chunk descriptors carry 16-bit header offsets
+            std::vector<uint8_t> nn(S, 255);  // distance to the nearest other barcode
+            for (uint32_t i = 0; i < S; i++)
+                for (uint32_t j = i + 1; j < S; j++) {
+                    const uint8_t d = (uint8_t)__builtin_popcount((table[i].x ^ table[j].x) | (table[i].y ^ table[j].y));
+                    nn[i] = std::min(nn[i], d);
+                    nn[j] = std::min(nn[j], d);
+                }
+            CU(cudaMalloc(&h->d_ph_nn, S));
+            CU(cudaMemcpy(h->d_ph_nn, nn.data(), S, cudaMemcpyHostToDevice));
+            h->ph.nn = h->d_ph_nn;
+            if (int rc = upload(hdr, &h->d_ph_ms_hdr)) return rc;
+            if (int rc = upload(ids, &h->d_ph_ms_ids)) return rc;
+            h->ph.ms_hdr = h->d_ph_ms_hdr;
+            h->ph.ms_ids = h->d_ph_ms_ids;
+            h->ph.ms_C = C;
+            h->ph.ms_hdr_total = total;
+            h->ph.ms_ids_total = C * S;
+        }
+    }
     h->ph.nm0 = t.nm0;
     h->ph.nm1 = t.nm1;
     h->ph.lmask = t.lmask;
@@ -507,6 +559,9 @@ extern "C" void sgdx_destroy(sgdx_handle *h) {
     cudaFree(h->d_ph_slots);
     cudaFree(h->d_ph_b_disp);
     cudaFree(h->d_ph_b_slots);
+    cudaFree(h->d_ph_ms_hdr);
+    cudaFree(h->d_ph_ms_ids);
+    cudaFree(h->d_ph_nn);
     cudaFree(h->d_ph_hop_slots);
     cudaFree(h->d_ph_hop_disp);
     cudaFree(h->d_hash1);
@@ -798,7 +853,7 @@ extern "C" uint32_t sgdx_path_flags(const sgdx_handle *h) {
     const DevParams &p = h->base;
     return (h->seeded ? SGDX_PATH_SEED_INDEX : 0u) | (h->seeded && p.ex_on ? SGDX_PATH_EXACT : 0u) |
            (h->seeded && p.ex_on && p.nb_on ? SGDX_PATH_NEIGHBOURS : 0u) | (p.hop_direct ? SGDX_PATH_HOP_DIRECT : 0u) |
-           (h->ph.slots ? SGDX_PATH_PERFECT_HASH : 0u);
+           (h->ph.slots ? SGDX_PATH_PERFECT_HASH : 0u) | (h->ph.slots && h->ph.ms_C ? SGDX_PATH_SHORT_SEED : 0u);
 }
 
 extern "C" uint64_t sgdx_launch_count(const sgdx_handle *h) { return h ? h->launches.load() : 0; }

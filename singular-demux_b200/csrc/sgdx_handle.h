@@ -84,6 +84,8 @@ struct sgdx_handle {
     bool seeded = false;  // launches use sgdx_match_seeded
     uint64_t *d_ph_hop_slots = nullptr;
     uint16_t *d_ph_hop_disp = nullptr;
+    uint16_t *d_ph_ms_hdr = nullptr, *d_ph_ms_ids = nullptr;  // short seed index of the perfect-hash kernel (PhParams::ms_*)
+    uint8_t *d_ph_nn = nullptr;                               // ... and PhParams::nn
     uint16_t *d_ph_disp = nullptr, *d_ph_slots = nullptr, *d_ph_b_disp = nullptr, *d_ph_b_slots = nullptr;  // perfect-hash kernel (sgdx_ph.cu); ph.slots == nullptr: not available
     sgdx::PhParams ph{};
     uint32_t ph_keys = 0;

@@ -55,6 +55,20 @@ struct PhParams {
     const uint16_t *b_disp;
     const uint16_t *b_slots;
     uint32_t b_bshift, b_sshift, b_k0, b_k1, b_k2, b_radius;
+    // Short seed index (optional; ms_C == 0: none) for what the levels above leave undecided when radius <
+    // max_mismatches: the layout of DevParams' seed index over max_mismatches + 1 chunks instead of T + 1, so with
+    // longer keys (<= 6 bases) and shorter buckets.  It enumerates every sample within max_mismatches of the read's
+    // valid positions (pigeonhole).  With best = the closest of them at p valid-position mismatches and ninv invalid
+    // positions, every other sample is >= nn[best] - ninv - p valid-position mismatches away (triangle inequality over
+    // the valid positions), so the enumeration decides the read when no sample is within max_mismatches (NoMatch) or
+    // when 2 p + min_delta + ninv < nn[best] (no competitor within min_delta of the best, in either rule set); the few
+    // other reads search the full index.
+    const uint16_t *ms_hdr;
+    const uint16_t *ms_ids;
+    uint32_t ms_C, ms_hdr_total, ms_ids_total;
+    uint32_t ms_desc[8];
+    const uint8_t *nn;         // [S] distance of every barcode to its nearest other barcode (255 for one sample): the
+                               // rule above with nn[best] in place of the table-wide minimum dmin
     // hop key sets for shared memory (optional; hop_slots == nullptr: the kernel uses the global tables of DevParams):
     // one perfect hash of the same construction over the distinct index1 / index2 halves (without Undetermined's
     // all-N halves): key = lo bits | hi bits << half length | tag << 40 (tag = 1: an index2 half, only when the two

@@ -130,7 +130,8 @@ bool ph_build_hop(const std::vector<uint64_t> &keys1, const std::vector<uint32_t
     }
     if (keys.empty() || keys.size() > 5000u) return false;  // 64 KB of slots at most
     uint32_t sbits = 4, bbits = 2;
-    while ((double)keys.size() > 0.7 * (double)(1u << sbits)) sbits++;
+    // load factor <= 0.7; up to 0.8 where that halves a table of 32 KB or more (placement retries with more slots if it fails)
+    while ((double)keys.size() > (sbits >= 12u ? 0.8 : 0.7) * (double)(1u << sbits)) sbits++;
     while (((size_t)3 << bbits) < keys.size()) bbits++;
     std::vector<uint32_t> where;
     uint32_t kset = 0;

@@ -40,10 +40,10 @@ constexpr size_t kPhSmemLimit = 227u * 1024u;
 struct PhSmem {
     uint64_t *qrec;   // [warps][qcap] deferred reads: planes (compact record, or lo | hi << 32) ...
     uint32_t *qoff;   // [warps][qcap] ... and (warp iteration * chunk + offset in chunk)
-    uint64_t *q2rec;  // [warps][kPhQueue2] the deferred reads that need the general path ...
+    uint64_t *q2rec;  // [warps][kPhQueue2] with a short radius: the plain reads the hash levels left undecided ...
     uint32_t *q2off;  // [warps][kPhQueue2] ... same numbering
-    uint64_t *q3rec;  // [warps][kPhQueue2] with a short radius: the reads with invalid positions, apart from the
-    uint32_t *q3off;  //                    undecided plain ones of the second queue
+    uint64_t *q3rec;  // [warps][kPhQueue2] the reads with invalid positions or stray bits
+    uint32_t *q3off;
     uint64_t *hslots; // hop key sets (PhParams::hop_slots), optional
     uint2 *planes;    // [S + 1][copies]: barcode planes, replicated so that the lanes of a half warp read distinct banks;
                       //                  row S = dummy
@@ -53,16 +53,19 @@ struct PhSmem {
     uint16_t *hdisp;  // hop key sets
     uint16_t *hdr;    // seed index of DevParams (general path of undecided reads), optional
     uint16_t *ids;
+    uint16_t *mhdr;   // short seed index of PhParams (ms_*), optional
+    uint16_t *mids;
 };
 
 struct PhFit {       // shared-memory layout of one launch (ph_fit)
     uint32_t qcap;   // entries of a warp's first queue: <= 31 left over + the reads of one chunk
-    uint32_t q3;     // 1 = the third queue exists (radius < max_mismatches)
+    uint32_t q2;     // 1 = the second queue exists (radius < max_mismatches)
     uint32_t clog;   // log2 of the copies of the planes table
     uint32_t hsbits, hbbits;  // hop key sets: slot bits (0 = not in shared memory), bucket bits
     uint32_t hdr_total, ids_total;  // seed index entries (0 = not in shared memory)
+    uint32_t mhdr_total, mids_total;  // short seed index entries (0 = not in shared memory)
     // byte offsets of the arrays of PhSmem, filled on the host (ph_layout) so that the kernel adds instead of carving
-    uint32_t o_hist, o_disp, o_slots, o_qrec, o_q2rec, o_q3rec, o_hslots, o_qoff, o_q2off, o_q3off, o_hdisp, o_hdr, o_ids;
+    uint32_t o_hist, o_disp, o_slots, o_qrec, o_q2rec, o_q3rec, o_hslots, o_qoff, o_q2off, o_q3off, o_hdisp, o_hdr, o_ids, o_mhdr, o_mids;
 };
 
 __host__ __device__ inline size_t ph_carve(unsigned char *base, uint32_t S, uint32_t bbits, uint32_t sbits, const PhFit &f,
@@ -76,15 +79,17 @@ __host__ __device__ inline size_t ph_carve(unsigned char *base, uint32_t S, uint
     s.slots = reinterpret_cast<uint16_t *>(base + o);  o += (size_t)2 << sbits;
     o = (o + 15) & ~(size_t)15;
     s.qrec = reinterpret_cast<uint64_t *>(base + o);   o += (size_t)kPhWarps * f.qcap * 8;
-    s.q2rec = reinterpret_cast<uint64_t *>(base + o);  o += (size_t)kPhWarps * kPhQueue2 * 8;
-    s.q3rec = reinterpret_cast<uint64_t *>(base + o);  o += f.q3 ? (size_t)kPhWarps * kPhQueue2 * 8 : 0;
+    s.q2rec = reinterpret_cast<uint64_t *>(base + o);  o += f.q2 ? (size_t)kPhWarps * kPhQueue2 * 8 : 0;
+    s.q3rec = reinterpret_cast<uint64_t *>(base + o);  o += (size_t)kPhWarps * kPhQueue2 * 8;
     s.hslots = reinterpret_cast<uint64_t *>(base + o); o += f.hsbits ? (size_t)8 << f.hsbits : 0;
     s.qoff = reinterpret_cast<uint32_t *>(base + o);   o += (size_t)kPhWarps * f.qcap * 4;
-    s.q2off = reinterpret_cast<uint32_t *>(base + o);  o += (size_t)kPhWarps * kPhQueue2 * 4;
-    s.q3off = reinterpret_cast<uint32_t *>(base + o);  o += f.q3 ? (size_t)kPhWarps * kPhQueue2 * 4 : 0;
+    s.q2off = reinterpret_cast<uint32_t *>(base + o);  o += f.q2 ? (size_t)kPhWarps * kPhQueue2 * 4 : 0;
+    s.q3off = reinterpret_cast<uint32_t *>(base + o);  o += (size_t)kPhWarps * kPhQueue2 * 4;
     s.hdisp = reinterpret_cast<uint16_t *>(base + o);  o += f.hsbits ? (size_t)2 << f.hbbits : 0;
     s.hdr = reinterpret_cast<uint16_t *>(base + o);    o += ((size_t)f.hdr_total * 2 + 15) & ~(size_t)15;
     s.ids = reinterpret_cast<uint16_t *>(base + o);    o += ((size_t)f.ids_total * 2 + 15) & ~(size_t)15;
+    s.mhdr = reinterpret_cast<uint16_t *>(base + o);   o += ((size_t)f.mhdr_total * 2 + 15) & ~(size_t)15;
+    s.mids = reinterpret_cast<uint16_t *>(base + o);   o += ((size_t)f.mids_total * 2 + 15) & ~(size_t)15;
     o = (o + 15) & ~(size_t)15;
     if (out) *out = s;
     return o;
@@ -97,30 +102,42 @@ static void ph_layout(uint32_t S, uint32_t bbits, uint32_t sbits, PhFit &f) {
     auto at = [](const void *q) { return (uint32_t)reinterpret_cast<uintptr_t>(q); };
     f.o_hist = at(s.hist), f.o_disp = at(s.disp), f.o_slots = at(s.slots), f.o_qrec = at(s.qrec), f.o_q2rec = at(s.q2rec);
     f.o_q3rec = at(s.q3rec), f.o_hslots = at(s.hslots), f.o_qoff = at(s.qoff), f.o_q2off = at(s.q2off), f.o_q3off = at(s.q3off);
-    f.o_hdisp = at(s.hdisp), f.o_hdr = at(s.hdr), f.o_ids = at(s.ids);
+    f.o_hdisp = at(s.hdisp), f.o_hdr = at(s.hdr), f.o_ids = at(s.ids), f.o_mhdr = at(s.mhdr), f.o_mids = at(s.mids);
 }
 
-// What is optional goes into shared memory as far as it fits, in the order of what it saves: the seed index (every
-// undecided read searches it), the hop key sets (without them every hop check is a round trip to L2), copies of the
-// planes table (up to one per lane of a half warp).
+// What is optional goes into shared memory as far as it fits, in the order of what it saves: the short seed index
+// (every read the hash levels leave undecided searches it), the hop key sets (without them every hop check is a round
+// trip to L2), the full seed index (without a short one every undecided read searches it; with one, only the few reads
+// the short one cannot decide), copies of the planes table (up to one per lane of a half warp).
 static PhFit ph_fit(const DevParams &p, const PhParams &c) {
     const uint32_t bbits = 32u - c.bshift, sbits = 32u - c.sshift;
     PhFit f{};
     f.qcap = c.wide ? 96u : 160u;
-    f.q3 = c.radius < p.M ? 1u : 0u;
+    f.q2 = c.radius < p.M ? 1u : 0u;
     f.hbbits = 32u - c.hop_bshift;
     auto fits = [&](const PhFit &x) { return ph_carve(nullptr, p.S, bbits, sbits, x, nullptr) <= kPhSmemLimit; };
-    if (c.radius < p.M && p.seed_C) {
+    if (c.radius < p.M && c.ms_C) {
+        PhFit g = f;
+        g.mhdr_total = c.ms_hdr_total;
+        g.mids_total = c.ms_ids_total;
+        if (fits(g)) f = g;
+    }
+    const bool full_first = c.radius < p.M && p.seed_C && !f.mhdr_total;
+    auto full_index = [&]() {
         PhFit g = f;
         g.hdr_total = p.seed_hdr_total;
         g.ids_total = p.seed_ids_total;
         if (fits(g)) f = g;
-    }
+    };
+    if (full_first) full_index();
     if (c.hop_slots) {
         PhFit g = f;
         g.hsbits = 32u - c.hop_sshift;
         if (fits(g)) f = g;
     }
+    f.clog = 1u;  // two copies of the planes before the full index, the rest after it
+    if (!fits(f)) f.clog = 0u;
+    if (c.radius < p.M && p.seed_C && !full_first) full_index();
     f.clog = 4u;
     while (f.clog && !fits(f)) f.clog--;
     ph_layout(p.S, bbits, sbits, f);
@@ -222,6 +239,8 @@ __global__ void __launch_bounds__(kPhThreads, 1) sgdx_match_phx(const DevParams 
     sm.hdisp = reinterpret_cast<uint16_t *>(smem_raw + fit.o_hdisp);
     sm.hdr = reinterpret_cast<uint16_t *>(smem_raw + fit.o_hdr);
     sm.ids = reinterpret_cast<uint16_t *>(smem_raw + fit.o_ids);
+    sm.mhdr = reinterpret_cast<uint16_t *>(smem_raw + fit.o_mhdr);
+    sm.mids = reinterpret_cast<uint16_t *>(smem_raw + fit.o_mids);
     const uint32_t S1 = p.S + 1u, nbins = S1 * 3u;
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const uint32_t ncopies = 1u << fit.clog;
@@ -240,6 +259,8 @@ __global__ void __launch_bounds__(kPhThreads, 1) sgdx_match_phx(const DevParams 
     }
     for (uint32_t i = threadIdx.x; i < fit.hdr_total; i += kPhThreads) sm.hdr[i] = p.seed_hdr[i];
     for (uint32_t i = threadIdx.x; i < fit.ids_total; i += kPhThreads) sm.ids[i] = p.seed_ids[i];
+    for (uint32_t i = threadIdx.x; i < fit.mhdr_total; i += kPhThreads) sm.mhdr[i] = c.ms_hdr[i];
+    for (uint32_t i = threadIdx.x; i < fit.mids_total; i += kPhThreads) sm.mids[i] = c.ms_ids[i];
     __syncthreads();
 
     uint64_t *const qrec = sm.qrec + warp * fit.qcap;
@@ -253,6 +274,8 @@ __global__ void __launch_bounds__(kPhThreads, 1) sgdx_match_phx(const DevParams 
     const uint32_t qrec_s = (uint32_t)__cvta_generic_to_shared(qrec), qoff_s = (uint32_t)__cvta_generic_to_shared(qoff);
     const uint16_t *const seed_hdr = fit.hdr_total ? sm.hdr : p.seed_hdr;
     const uint16_t *const seed_ids = fit.ids_total ? sm.ids : p.seed_ids;
+    const uint16_t *const ms_hdr = fit.mhdr_total ? sm.mhdr : c.ms_hdr;
+    const uint16_t *const ms_ids = fit.mids_total ? sm.mids : c.ms_ids;
     uint32_t n1 = 0u, n2 = 0u, n3 = 0u;  // queue fills, warp-uniform
     const uint64_t total_warps = (uint64_t)gridDim.x * kPhWarps, gwarp = (uint64_t)blockIdx.x * kPhWarps + warp;
     const uint64_t nchunks = (p.n + CHUNK - 1u) / CHUNK;
@@ -379,9 +402,36 @@ __global__ void __launch_bounds__(kPhThreads, 1) sgdx_match_phx(const DevParams 
             for (uint32_t k = 0; k < 4; k++) rec[k] = nextrec[k];
         }
 
-        // ---- deferred reads, 32 at a time: hop check of the plain NoMatch reads (metrics.rs:658-676); the others
-        // move on -- reads with invalid positions or stray bits to the queue of the general path; with a short
-        // radius the undecided plain reads go to the second queue and the invalid ones to the third
+        // ---- deferred reads, 32 at a time.  Plain reads: with the full radius they are NoMatch and only their hop check
+        // is left (metrics.rs:658-676); with a short radius they probe the second level here and what that leaves
+        // undecided moves on to the second queue (seed search, again 32 at a time).  Reads with invalid positions or
+        // stray bits move on to the third queue.
+        const auto read_of = [&](uint32_t tag) {  // global read number of a queue entry
+            const uint32_t e = tag & 0x7FFFFFFFu;
+            return ((uint64_t)(e / CHUNK) * total_warps + gwarp) * CHUNK + (e % CHUNK);
+        };
+        const auto scan_rest = [&](bool scan, uint64_t r, const Rd &rd) {  // one warp per read over all samples
+            uint32_t todo = __ballot_sync(0xFFFFFFFFu, scan);
+            while (todo) {
+                const uint32_t src = (uint32_t)__ffs(todo) - 1u;
+                todo &= todo - 1u;
+                const uint64_t qr = __shfl_sync(0xFFFFFFFFu, r, src);
+                Rd qrd;
+                qrd.lo = __shfl_sync(0xFFFFFFFFu, rd.lo, src);
+                qrd.hi = __shfl_sync(0xFFFFFFFFu, rd.hi, src);
+                qrd.nmask = __shfl_sync(0xFFFFFFFFu, rd.nmask, src);
+                qrd.xmask = __shfl_sync(0xFFFFFFFFu, rd.xmask, src);
+                const Verdict qv = warp_scan<MODE>(p, p.table, qrd, lane);
+                if (lane == 0u) ph_emit(p, c, sm, hop_smem, S1, qr, qrd, qv);
+            }
+        };
+        const uint2 *const tab = reinterpret_cast<const uint2 *>(prow);
+        const auto ms_desc_of = [&](uint32_t cc) { return c.ms_desc[cc]; };
+        // the short seed index decides a read (PhParams::ms_*) unless its best candidate is too close to call
+        const auto ms_sure = [&](uint32_t best, uint32_t ninv) {
+            const uint32_t pb = (best >> 16) - ninv;  // valid-position mismatches of the best candidate
+            return best == kInfKey || pb > p.M || 2u * pb + p.delta + ninv < (uint32_t)__ldg(c.nn + (best & 0xFFFFu));
+        };
         while (n1 >= 32u || (final && (n1 | n2 | n3))) {
             const uint32_t take = min(n1, 32u);  // 0 when only the other queues are left to flush
             n1 -= take;
@@ -392,29 +442,46 @@ __global__ void __launch_bounds__(kPhThreads, 1) sgdx_match_phx(const DevParams 
                 q = qrec[n1 + lane];
                 off = qoff[n1 + lane];
                 const uint32_t w0 = (uint32_t)q, w1 = (uint32_t)(q >> 32);
-                const bool invalid = WIDE ? (off >> 31) != 0u : ((w0 & c.nm0) | (w1 & c.nm1)) != 0u;
-                to2 = final_radius ? invalid : !invalid;
-                to3 = !final_radius && invalid;
-                if (final_radius && !invalid) {
-                    uint32_t lo, hi;
-                    ph_planes<WIDE>(w0, w1, lo, hi);
-                    if (!WIDE) hi &= kCompactMask;
-                    if (hop_smem) {
-                        ph_hop_check(p, c, sm, lo, hi);
+                to3 = WIDE ? (off >> 31) != 0u : ((w0 & c.nm0) | (w1 & c.nm1)) != 0u;
+                if (!to3) {
+                    Rd rd = {0u, 0u, 0u, 0u};
+                    ph_planes<WIDE>(w0, w1, rd.lo, rd.hi);
+                    if (!WIDE) rd.hi &= kCompactMask;
+                    if (final_radius) {
+                        if (hop_smem) ph_hop_check(p, c, sm, rd.lo, rd.hi);
+                        else hop_check(p, rd);
                     } else {
-                        const Rd rd = {lo, hi, 0u, 0u};
-                        hop_check(p, rd);
+                        to2 = true;
+                        if (c.b_slots) {  // second level: the strings within b_radius, in global memory (L2)
+                            const uint64_t key = WIDE ? q : ((uint64_t)rd.lo | ((uint64_t)rd.hi << kCompactField));
+                            const uint32_t k0 = (uint32_t)key, k1 = (uint32_t)(key >> 32);
+                            const uint32_t hb = __umulhi(k0, c.b_k0) + k0 * c.b_k1 + k1 * c.b_k2;
+                            const uint32_t pe = __ldg(c.b_slots + ((hb * (uint32_t)__ldg(c.b_disp + (hb >> c.b_bshift))) >> c.b_sshift));
+                            const uint2 tt = *reinterpret_cast<const uint2 *>(prow + pe * rowbytes);
+                            const uint32_t pd = (uint32_t)__popc((rd.lo ^ tt.x) | (rd.hi ^ tt.y));
+                            Verdict v = {p.S, kNoDist};
+                            if (pe < p.S && pd <= c.b_radius) {
+                                v.bin = pe;
+                                v.dist = pd;
+                                to2 = false;
+                            } else if (c.b_radius >= p.M) {
+                                to2 = false;  // further than max_mismatches from every sample
+                            }
+                            if (!to2) ph_emit(p, c, sm, hop_smem, S1, read_of(off), rd, v);
+                        }
                     }
                 }
             }
-            const uint32_t votes2 = __ballot_sync(0xFFFFFFFFu, to2);
-            if (to2) {
-                const uint32_t at = n2 + (uint32_t)__popc(votes2 & below);
-                q2rec[at] = q;
-                q2off[at] = off;
-            }
-            n2 += (uint32_t)__popc(votes2);
             if (!final_radius) {
+                const uint32_t votes2 = __ballot_sync(0xFFFFFFFFu, to2);
+                if (to2) {
+                    const uint32_t at = n2 + (uint32_t)__popc(votes2 & below);
+                    q2rec[at] = q;
+                    q2off[at] = off;
+                }
+                n2 += (uint32_t)__popc(votes2);
+            }
+            if (__any_sync(0xFFFFFFFFu, to3)) {
                 const uint32_t votes3 = __ballot_sync(0xFFFFFFFFu, to3);
                 if (to3) {
                     const uint32_t at = n3 + (uint32_t)__popc(votes3 & below);
@@ -424,37 +491,54 @@ __global__ void __launch_bounds__(kPhThreads, 1) sgdx_match_phx(const DevParams 
                 n3 += (uint32_t)__popc(votes3);
             }
             __syncwarp();
+            const bool flush = final && n1 == 0u;
 
-            // ---- general path
-            for (;;) {
-                // which queue: the one with a full batch; at the very end whatever is left
-                const bool flush = final && n1 == 0u;
-                const bool third = n3 >= 32u || (flush && n2 == 0u && n3);
-                if (!third && !(n2 >= 32u || (flush && n2))) break;
-                const uint64_t *const grec = third ? q3rec : q2rec;
-                const uint32_t *const goff = third ? q3off : q2off;
-                uint32_t nq = third ? n3 : n2;
-                const uint32_t takeg = min(nq, 32u);
-                nq -= takeg;
-                if (third) n3 = nq;
-                else n2 = nq;
+            // ---- second queue (short radius only): plain reads, seed search
+            while (!final_radius && (n2 >= 32u || (flush && n2))) {
+                const uint32_t takeg = min(n2, 32u);
+                n2 -= takeg;
+                const bool mine = lane < takeg;
                 bool scan = false;
                 uint64_t r = 0;
                 Rd rd = {0u, 0u, 0u, 0u};
-                if (lane < takeg) {
-                    const uint32_t tag = goff[nq + lane], e = tag & 0x7FFFFFFFu;
-                    const uint64_t g = grec[nq + lane];
-                    r = ((uint64_t)(e / CHUNK) * total_warps + gwarp) * CHUNK + (e % CHUNK);
-                    if (WIDE) {
-                        if (tag >> 31) rd = load_packed(c.reads_wide, r, p.L);  // (rare) the masks are not in the queue
-                        else rd.lo = (uint32_t)g, rd.hi = (uint32_t)(g >> 32);
-                    } else {
-                        rd = rd_of_compact(g, lmask);
+                if (mine) {
+                    const uint64_t g = q2rec[n2 + lane];
+                    r = read_of(q2off[n2 + lane]);
+                    ph_planes<WIDE>((uint32_t)g, (uint32_t)(g >> 32), rd.lo, rd.hi);
+                    if (!WIDE) rd.hi &= kCompactMask;
+                    uint32_t best = kInfKey, nxt = kInfKey;
+                    bool sure = false;
+                    if (c.ms_C) {
+                        seed_search_t<MODE, false, true>(p, c.ms_C, ms_desc_of, ms_hdr, ms_ids, tab, rd, best, nxt, ncopies);
+                        sure = ms_sure(best, 0u);
+                        if (!sure) best = nxt = kInfKey;
                     }
+                    if (!sure) {
+                        if (p.seed_C == 0u) scan = true;
+                        else seed_search<MODE, false>(p, seed_hdr, seed_ids, tab, rd, best, nxt, ncopies);
+                    }
+                    if (!scan) ph_emit(p, c, sm, hop_smem, S1, r, rd, apply_rules<MODE>(p, rd, best, nxt));
+                }
+                scan_rest(scan, r, rd);
+                __syncwarp();
+            }
+
+            // ---- third queue: reads with invalid positions or stray bits
+            while (n3 >= 32u || (flush && n2 == 0u && n3)) {
+                const uint32_t takeg = min(n3, 32u);
+                n3 -= takeg;
+                const bool mine = lane < takeg;
+                bool scan = false;
+                uint64_t r = 0;
+                Rd rd = {0u, 0u, 0u, 0u};
+                if (mine) {
+                    const uint32_t tag = q3off[n3 + lane];
+                    const uint64_t g = q3rec[n3 + lane];
+                    r = read_of(tag);
+                    if (WIDE) rd = load_packed(c.reads_wide, r, p.L);  // the masks are not in the queue
+                    else rd = rd_of_compact(g, lmask);
                     const uint32_t inv = rd.nmask | rd.xmask;
                     uint32_t best = kInfKey, nxt = kInfKey;
-                    bool decided = false;
-                    Verdict v = {p.S, kNoDist};
                     if (!cannot_match<MODE>(p, rd)) {
                         if (final_radius && (inv == 0u || (c.single_ok && (inv & (inv - 1u)) == 0u))) {
                             // no invalid base (the record only had stray bits): its own key.  One invalid base: the
@@ -473,53 +557,23 @@ __global__ void __launch_bounds__(kPhThreads, 1) sgdx_match_phx(const DevParams 
                                 }
                             }
                         } else {
-                            if (!final_radius && inv == 0u && c.b_slots) {
-                                // second level: the strings within b_radius, in global memory (L2)
-                                const uint64_t key = (uint64_t)rd.lo | ((uint64_t)rd.hi << (WIDE ? 32u : kCompactField));
-                                const uint32_t w0 = (uint32_t)key, w1 = (uint32_t)(key >> 32);
-                                const uint32_t hb = __umulhi(w0, c.b_k0) + w0 * c.b_k1 + w1 * c.b_k2;
-                                const uint32_t pe = __ldg(c.b_slots + ((hb * (uint32_t)__ldg(c.b_disp + (hb >> c.b_bshift))) >> c.b_sshift));
-                                const uint2 tt = *reinterpret_cast<const uint2 *>(prow + pe * rowbytes);
-                                const uint32_t pd = (uint32_t)__popc((rd.lo ^ tt.x) | (rd.hi ^ tt.y));
-                                if (pe < p.S && pd <= c.b_radius) {
-                                    v.bin = pe;
-                                    v.dist = pd;
-                                    decided = true;
-                                } else if (c.b_radius >= p.M) {
-                                    decided = true;  // further than max_mismatches from every sample
-                                }
+                            bool sure = false;
+                            if (!final_radius && c.ms_C) {
+                                sure = seed_search_t<MODE, true, false>(p, c.ms_C, ms_desc_of, ms_hdr, ms_ids, tab, rd, best, nxt, ncopies) &&
+                                       ms_sure(best, (uint32_t)__popc(inv));
+                                if (!sure) best = nxt = kInfKey;
                             }
-                            if (!decided) {
-                                if (p.seed_C == 0u || (final_radius && c.single_ok)) {
-                                    // no seed index; or, with the shortcut valid, only reads with several invalid
-                                    // bases get here: too few to be worth a chain of dependent loads at a lane or two
-                                    scan = true;
-                                } else if (inv == 0u) {
-                                    seed_search<MODE, false>(p, seed_hdr, seed_ids, reinterpret_cast<const uint2 *>(prow), rd, best, nxt,
-                                                             ncopies);
-                                } else if (!seed_search<MODE, true>(p, seed_hdr, seed_ids, reinterpret_cast<const uint2 *>(prow), rd,
-                                                                    best, nxt, ncopies)) {
-                                    scan = true;
-                                }
+                            if (!sure) {
+                                // no seed index; or, with the single-N shortcut valid, only reads with several invalid
+                                // bases get here: too few to be worth a chain of dependent loads at a lane or two
+                                if (p.seed_C == 0u || (final_radius && c.single_ok)) scan = true;
+                                else if (!seed_search<MODE, true>(p, seed_hdr, seed_ids, tab, rd, best, nxt, ncopies)) scan = true;
                             }
                         }
                     }
-                    if (!scan) ph_emit(p, c, sm, hop_smem, S1, r, rd, decided ? v : apply_rules<MODE>(p, rd, best, nxt));
+                    if (!scan) ph_emit(p, c, sm, hop_smem, S1, r, rd, apply_rules<MODE>(p, rd, best, nxt));
                 }
-                // whatever the seed index cannot enumerate: one warp per read over all samples
-                uint32_t todo = __ballot_sync(0xFFFFFFFFu, scan);
-                while (todo) {
-                    const uint32_t src = (uint32_t)__ffs(todo) - 1u;
-                    todo &= todo - 1u;
-                    const uint64_t qr = __shfl_sync(0xFFFFFFFFu, r, src);
-                    Rd qrd;
-                    qrd.lo = __shfl_sync(0xFFFFFFFFu, rd.lo, src);
-                    qrd.hi = __shfl_sync(0xFFFFFFFFu, rd.hi, src);
-                    qrd.nmask = __shfl_sync(0xFFFFFFFFu, rd.nmask, src);
-                    qrd.xmask = __shfl_sync(0xFFFFFFFFu, rd.xmask, src);
-                    const Verdict qv = warp_scan<MODE>(p, p.table, qrd, lane);
-                    if (lane == 0u) ph_emit(p, c, sm, hop_smem, S1, qr, qrd, qv);
-                }
+                scan_rest(scan, r, rd);
                 __syncwarp();
             }
         }

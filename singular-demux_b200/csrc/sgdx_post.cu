@@ -662,6 +662,8 @@ struct RouteParams {
     uint32_t ranges;     // one warp per range
     uint32_t chunk;      // reads per range (multiple of 32)
     uint32_t warps;      // per CTA
+    uint32_t row_words;  // shared-memory words per warp: bins counters / cursors + bins lane slots (bytes)
+    uint32_t vec;        // idx is 16-byte aligned and chunk a multiple of 8: the histogram loads eight indices at once
     uint32_t *matrix;    // [ranges][bins]
     unsigned long long *totals;  // [bins], then the exclusive scan in place
     uint32_t *order;
@@ -673,15 +675,29 @@ __global__ void sgdx_route_hist(const RouteParams p) {
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
     const uint32_t range = blockIdx.x * p.warps + warp;
     if (range >= p.ranges) return;
-    uint32_t *h = s_route + (size_t)warp * p.bins;
+    uint32_t *h = s_route + (size_t)warp * p.row_words;
     for (uint32_t b = lane; b < p.bins; b += 32u) h[b] = 0u;
     __syncwarp();
     const uint64_t lo = (uint64_t)range * p.chunk, hi = min(p.n, lo + p.chunk);
-#pragma unroll 4
-    for (uint64_t r = lo + lane; r < hi; r += 32u) {
-        const uint32_t b = min((uint32_t)__ldg(p.idx + r), p.bins - 1u);
-        atomicAdd(h + b, 1u);
+    const uint32_t last = p.bins - 1u;
+    uint64_t r = lo;
+    if (p.vec) {  // idx 16-byte aligned, chunk a multiple of 8: eight indices per lane and load (order is irrelevant here)
+        const uint4 *src = reinterpret_cast<const uint4 *>(p.idx + lo);
+        const uint64_t nvec = (hi - lo) >> 3;
+#pragma unroll 2
+        for (uint64_t i = lane; i < nvec; i += 32u) {
+            const uint4 v = __ldg(src + i);
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                atomicAdd(h + min(w[k] & 0xFFFFu, last), 1u);
+                atomicAdd(h + min(w[k] >> 16, last), 1u);
+            }
+        }
+        r = lo + (nvec << 3);
     }
+#pragma unroll 4
+    for (r += lane; r < hi; r += 32u) atomicAdd(h + min((uint32_t)__ldg(p.idx + r), last), 1u);
     __syncwarp();
     uint32_t *row = p.matrix + (size_t)range * p.bins;
     for (uint32_t b = lane; b < p.bins; b += 32u) row[b] = h[b];
@@ -744,40 +760,202 @@ __global__ void __launch_bounds__(1024) sgdx_route_scan_bins(const RouteParams p
     if (threadIdx.x == 1023u) p.offsets[p.bins] = p.n;
 }
 
-__global__ void sgdx_route_scatter(const RouteParams p) {
+// Ranked scatter.  A warp walks its range 32 reads at a time; lane i needs the lanes below it that hold the same bin.
+// __match_any_sync answers that, but it executes on the address-divergence unit at about 64 cycles per instruction
+// and SM, which made this kernel the slowest stage per byte.  Here the lanes of a bin find each other through a
+// per-warp byte array in shared memory instead: every lane that has not been seen yet writes its lane number into
+// slot[bin] (one of them wins), all lanes of the bin read the winner and add it to their peer mask; after as many
+// rounds as the most frequent bin of the step has lanes (2-4 for a few hundred samples) every lane knows its peers.
+// Steps dominated by one bin (few samples, or a run of Undetermined reads) stop after kRouteRounds rounds and take
+// the hardware match; two to four bins are ranked by one vote per bin.
+constexpr uint32_t kRouteRounds = 5;
+
+__global__ void __launch_bounds__(256) sgdx_route_scatter(const RouteParams p) {
     extern __shared__ uint32_t s_route[];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
     const uint32_t range = blockIdx.x * p.warps + warp;
     if (range >= p.ranges) return;
-    uint32_t *cur = s_route + (size_t)warp * p.bins;
+    // cursors and lane slots of the bins, plus one dummy bin (index `bins`) for the lanes past the end of the range
+    uint32_t *cur = s_route + (size_t)warp * p.row_words;
+    uint8_t *slot = reinterpret_cast<uint8_t *>(cur + p.bins + 1u);
     const uint32_t *row = p.matrix + (size_t)range * p.bins;
     for (uint32_t b = lane; b < p.bins; b += 32u) cur[b] = row[b] + (uint32_t)p.totals[b];
     __syncwarp();
     const uint64_t lo = (uint64_t)range * p.chunk, hi = min(p.n, lo + p.chunk);
-    const uint32_t lt = (1u << lane) - 1u;
+    const uint32_t lt = (1u << lane) - 1u, last = p.bins - 1u;
+    const bool few = p.bins <= 4u;
     for (uint64_t base = lo; base < hi; base += 128u) {
         uint32_t bb[4];
 #pragma unroll
         for (int j = 0; j < 4; j++) {  // four independent loads in flight per lane
             const uint64_t r = base + 32u * j + lane;
-            bb[j] = r < hi ? min((uint32_t)__ldg(p.idx + r), p.bins - 1u) : 0xFFFFFFFFu;
+            bb[j] = r < hi ? min((uint32_t)__ldg(p.idx + r), last) : p.bins;
         }
-#pragma unroll
+#pragma unroll 1
         for (int j = 0; j < 4; j++) {
-            const uint64_t r = base + 32u * j + lane;
+            const uint32_t r = (uint32_t)base + 32u * j + lane;
             const uint32_t b = bb[j];
-            const bool active = b != 0xFFFFFFFFu;
-            const uint32_t peers = __match_any_sync(0xFFFFFFFFu, b);
+            uint32_t peers = 0u;
+            if (few) {
+                for (uint32_t k = 0; k <= p.bins; k++) {
+                    const uint32_t v = __ballot_sync(0xFFFFFFFFu, b == k);
+                    if (b == k) peers = v;
+                }
+            } else {
+                uint32_t pending = 1u, rounds = 0u, more;
+                do {
+                    if (pending) slot[b] = (uint8_t)lane;
+                    __syncwarp();
+                    const uint32_t w = slot[b];
+                    peers |= 1u << w;
+                    pending = w != lane ? pending : 0u;
+                    more = __any_sync(0xFFFFFFFFu, pending != 0u);  // (also orders this round's reads before the next writes)
+                } while (more && ++rounds < kRouteRounds);
+                if (more) peers = __match_any_sync(0xFFFFFFFFu, b);
+            }
             const uint32_t rank = __popc(peers & lt);
             uint32_t at = 0;
-            if (active && rank == 0u) {  // lowest lane of each bin group advances the bin's cursor
+            if (rank == 0u) {  // lowest lane of each bin group advances the bin's cursor
                 at = cur[b];
                 cur[b] = at + __popc(peers);
             }
             at = __shfl_sync(0xFFFFFFFFu, at, __ffs(peers) - 1);
-            if (active) p.order[at + rank] = (uint32_t)r;
+            if (b != p.bins) p.order[at + rank] = r;
             __syncwarp();
         }
+    }
+}
+
+// ---- CTA-tile form (the one that runs whenever its tables fit shared memory) ------------------------------------
+// With one range per warp the scatter keeps ranges x bins output positions open at once; each sits in its own
+// 128-byte line of L2, a few thousand warps times a few hundred bins overflow it, and half-written sectors go to
+// DRAM and come back (measured at 50 M reads, 385 bins: 0.9 GB written for 0.2 GB of read ids).  Here a range belongs
+// to a CTA of W warps that walks it in tiles of 32 W reads, warp w taking reads 32 w .. 32 w + 31 of the tile, so that
+// the warps of a CTA write into the same lines and only (CTAs x bins) positions are open.
+//   ranking inside a warp: every lane ORs its lane bit into a per-warp word of its bin (ATOMS.OR), reads the word
+//     back -- the lanes of the bin -- and the bin's lowest lane clears it and publishes the count as byte
+//     cnts[bin][warp];
+//   after a barrier every lane reads the W count bytes of its bin: the bytes below its warp sum to its offset inside
+//     the tile (IDP.4A against 0x01010101), all of them to the tile's total; position = cursor[bin] + offset + rank;
+//   after a second barrier the lowest lane of the bin's last warp advances the cursor and clears the count bytes.
+// The count bytes are double-buffered by tile parity, so two barriers per tile are enough.
+struct RouteTileParams {
+    RouteParams r;
+    uint32_t o_cnts, o_bm;  // byte offsets in shared memory (cursors at 0)
+};
+
+template <uint32_t W>
+__host__ __device__ inline size_t route_tile_smem(uint32_t bins, uint32_t *o_cnts, uint32_t *o_bm) {
+    size_t o = ((size_t)bins * 4u + 15u) & ~(size_t)15u;  // cursors / histogram
+    if (o_cnts) *o_cnts = (uint32_t)o;
+    o += (size_t)2u * bins * W;                            // count bytes, two tiles
+    o = (o + 15u) & ~(size_t)15u;
+    if (o_bm) *o_bm = (uint32_t)o;
+    o += (size_t)W * (bins + 1u) * 4u;                     // lane words per warp, + the dummy bin
+    return o;
+}
+
+// histogram of one CTA range (all warps into one shared histogram) -> matrix row
+__global__ void __launch_bounds__(1024) sgdx_route_hist_cta(const RouteParams p) {
+    extern __shared__ uint32_t s_route[];
+    const uint32_t range = blockIdx.x;
+    for (uint32_t b = threadIdx.x; b < p.bins; b += blockDim.x) s_route[b] = 0u;
+    __syncthreads();
+    const uint64_t lo = (uint64_t)range * p.chunk, hi = min(p.n, lo + p.chunk);
+    const uint32_t last = p.bins - 1u;
+    uint64_t r = lo;
+    if (p.vec) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(p.idx + lo);
+        const uint64_t nvec = (hi - lo) >> 3;
+#pragma unroll 2
+        for (uint64_t i = threadIdx.x; i < nvec; i += blockDim.x) {
+            const uint4 v = __ldg(src + i);
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                atomicAdd(s_route + min(w[k] & 0xFFFFu, last), 1u);
+                atomicAdd(s_route + min(w[k] >> 16, last), 1u);
+            }
+        }
+        r = lo + (nvec << 3);
+    }
+    for (r += threadIdx.x; r < hi; r += blockDim.x) atomicAdd(s_route + min((uint32_t)__ldg(p.idx + r), last), 1u);
+    __syncthreads();
+    uint32_t *row = p.matrix + (size_t)range * p.bins;
+    for (uint32_t b = threadIdx.x; b < p.bins; b += blockDim.x) row[b] = s_route[b];
+}
+
+template <uint32_t W>
+__global__ void __launch_bounds__(W * 32u) sgdx_route_scatter_cta(const RouteTileParams q) {
+    extern __shared__ __align__(16) unsigned char s_tile[];
+    const RouteParams &p = q.r;
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    const uint32_t range = blockIdx.x, bins = p.bins;
+    uint32_t *cur = reinterpret_cast<uint32_t *>(s_tile);
+    uint8_t *cnts = s_tile + q.o_cnts;
+    uint32_t *bm = reinterpret_cast<uint32_t *>(s_tile + q.o_bm) + (size_t)warp * (bins + 1u);
+    const uint32_t *row = p.matrix + (size_t)range * bins;
+    for (uint32_t b = threadIdx.x; b < bins; b += W * 32u) cur[b] = row[b] + (uint32_t)p.totals[b];
+    for (uint32_t i = threadIdx.x; i < (2u * bins * W) / 4u; i += W * 32u) reinterpret_cast<uint32_t *>(cnts)[i] = 0u;
+    for (uint32_t b = lane; b <= bins; b += 32u) bm[b] = 0u;
+    __syncthreads();
+    const uint64_t lo = (uint64_t)range * p.chunk, hi = min(p.n, lo + p.chunk);
+    const uint32_t lt = (1u << lane) - 1u, last = bins - 1u;
+    // byte masks of the count words: bytes of the warps below mine
+    uint32_t below[W / 4u];
+#pragma unroll
+    for (uint32_t k = 0; k < W / 4u; k++)
+        below[k] = 4u * k + 4u <= warp ? 0xFFFFFFFFu : (4u * k >= warp ? 0u : (1u << (8u * (warp - 4u * k))) - 1u);
+    uint64_t r = lo + 32u * warp + lane;
+    uint32_t b = r < hi ? min((uint32_t)__ldg(p.idx + r), last) : bins;
+    for (uint32_t t = 0; lo + (uint64_t)t * (32u * W) < hi; t++) {
+        const uint64_t rn = r + 32u * W;
+        const uint32_t bn = rn < hi ? min((uint32_t)__ldg(p.idx + rn), last) : bins;  // next tile's index, early
+        uint8_t *cn = cnts + (size_t)(t & 1u) * bins * W;
+        atomicOr(bm + b, 1u << lane);
+        __syncwarp();
+        const uint32_t peers = bm[b];
+        const uint32_t rank = __popc(peers & lt), cnt = __popc(peers);
+        const bool real = b != bins;
+        __syncwarp();
+        if (rank == 0u) {
+            bm[b] = 0u;
+            if (real) cn[b * W + warp] = (uint8_t)cnt;
+        }
+        __syncthreads();
+        uint32_t prefix = 0u, tot = 0u;
+        if (real) {
+            const uint4 *cw = reinterpret_cast<const uint4 *>(cn + b * W);
+            uint32_t x[W / 4u];
+            if constexpr (W == 8u) {
+                const uint2 v = *reinterpret_cast<const uint2 *>(cw);
+                x[0] = v.x, x[1] = v.y;
+            } else {
+#pragma unroll
+                for (uint32_t k = 0; k < W / 16u; k++) {
+                    const uint4 v = cw[k];
+                    x[4 * k] = v.x, x[4 * k + 1] = v.y, x[4 * k + 2] = v.z, x[4 * k + 3] = v.w;
+                }
+            }
+#pragma unroll
+            for (uint32_t k = 0; k < W / 4u; k++) {
+                prefix = __dp4a(x[k] & below[k], 0x01010101u, prefix);
+                tot = __dp4a(x[k], 0x01010101u, tot);
+            }
+            p.order[cur[b] + prefix + rank] = (uint32_t)r;
+        }
+        __syncthreads();
+        if (real && rank == 0u && prefix + cnt == tot) {  // the bin's last warp of this tile
+            cur[b] += tot;
+            if constexpr (W == 8u) {
+                *reinterpret_cast<uint2 *>(cn + b * W) = make_uint2(0u, 0u);
+            } else {
+#pragma unroll
+                for (uint32_t k = 0; k < W / 16u; k++) reinterpret_cast<uint4 *>(cn + b * W)[k] = make_uint4(0u, 0u, 0u, 0u);
+            }
+        }
+        r = rn;
+        b = bn;
     }
 }
 
@@ -1328,12 +1506,28 @@ extern "C" int sgdx_route_device(sgdx_handle *h, uint32_t slot, const uint16_t *
     p.idx = d_idx;
     p.n = n;
     p.bins = h->cfg.num_samples + 1;
-    // one warp per contiguous range of reads; each warp keeps a private row of `bins` counters in shared memory
     const size_t row_bytes = (size_t)p.bins * sizeof(uint32_t);
-    p.warps = (uint32_t)std::max<size_t>(1, std::min<size_t>(8, (96u * 1024u) / row_bytes));
+    p.vec = (reinterpret_cast<uintptr_t>(d_idx) & 15u) == 0u ? 1u : 0u;  // (chunk is a multiple of 32 reads = 64 bytes)
+    // CTA-tile form when its tables fit shared memory (two CTAs per SM if possible), else per-warp ranges (W = 0).
+    // Measured at 50 M reads, 385 bins (ms for histogram + scans + scatter): W = 32: 0.58, W = 16: 0.44, W = 8: 0.48
+    // -- the count bytes of wide CTAs cost shared-memory wavefronts, narrow ones need more CTAs for the same warps.
+    uint32_t W = 0;
+    uint64_t per_sm = 12u;
+    if (route_tile_smem<16>(p.bins, nullptr, nullptr) <= 113u * 1024u) W = 16, per_sm = 2u;
+    else if (route_tile_smem<8>(p.bins, nullptr, nullptr) <= 113u * 1024u) W = 8, per_sm = 2u;
+    else if (route_tile_smem<8>(p.bins, nullptr, nullptr) <= 227u * 1024u) W = 8, per_sm = 1u;
+    if (W) {
+        p.warps = W;
+    } else {
+        // one warp per contiguous range of reads; each warp keeps a private row of `bins` counters (cursors) and
+        // `bins` one-byte lane slots in shared memory
+        p.row_words = (p.bins + 1u) + (p.bins + 4u) / 4u;  // + the dummy bin of sgdx_route_scatter
+        p.warps = (uint32_t)std::max<size_t>(1, std::min<size_t>(8, (96u * 1024u) / ((size_t)p.row_words * sizeof(uint32_t))));
+    }
     // few enough ranges that the (ranges x bins) offset matrix stays small next to the index array itself
-    const uint64_t max_ranges = (uint64_t)h->sms * 16u;
-    uint64_t ranges = std::min<uint64_t>(max_ranges, (n + 1023) / 1024);
+    const uint64_t max_ranges = (uint64_t)h->sms * per_sm;
+    const uint64_t min_chunk = W ? 32u * W : 1024u;
+    uint64_t ranges = std::min<uint64_t>(max_ranges, (n + min_chunk - 1) / min_chunk);
     if (ranges == 0) ranges = 1;
     uint64_t chunk = (n + ranges - 1) / ranges;
     chunk = (chunk + 31) & ~31ull;
@@ -1354,7 +1548,27 @@ extern "C" int sgdx_route_device(sgdx_handle *h, uint32_t slot, const uint16_t *
     p.matrix = reinterpret_cast<uint32_t *>(p.totals + p.bins);
     p.order = d_order;
     p.offsets = reinterpret_cast<unsigned long long *>(d_offsets);
-    const size_t smem = (size_t)p.warps * row_bytes;
+    if (W) {
+        RouteTileParams q{};
+        q.r = p;
+        const size_t smem = W == 16 ? route_tile_smem<16>(p.bins, &q.o_cnts, &q.o_bm) : route_tile_smem<8>(p.bins, &q.o_cnts, &q.o_bm);
+        CU(cudaFuncSetAttribute(sgdx_route_hist_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_bytes));
+        sgdx_route_hist_cta<<<p.ranges, 1024, row_bytes, s.stream>>>(p);
+        CU(cudaGetLastError());
+        sgdx_route_scan_ranges<<<(p.bins + 7u) / 8u, 256, 0, s.stream>>>(p);
+        CU(cudaGetLastError());
+        sgdx_route_scan_bins<<<1, 1024, 0, s.stream>>>(p);
+        CU(cudaGetLastError());
+        if (n) {
+            auto kern = W == 16 ? sgdx_route_scatter_cta<16> : sgdx_route_scatter_cta<8>;
+            CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kern<<<p.ranges, W * 32u, smem, s.stream>>>(q);
+            CU(cudaGetLastError());
+        }
+        h->launches.fetch_add(n ? 4 : 3);
+        return SGDX_OK;
+    }
+    const size_t smem = (size_t)p.warps * p.row_words * sizeof(uint32_t);
     CU(cudaFuncSetAttribute(sgdx_route_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CU(cudaFuncSetAttribute(sgdx_route_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const uint32_t grid = (p.ranges + p.warps - 1) / p.warps;

@@ -37,11 +37,71 @@ __device__ __forceinline__ bool cannot_match(const DevParams &p, const Rd &rd) {
 // Enumerate the seed buckets of one read.  Returns false when some key window holds two or more invalid
 // bases (best/nxt are then incomplete and the caller hands the read to the all-samples scan).  Loops are
 // kept free of early exits so that the lanes of a warp reconverge after every bucket.
+// C chunks, desc_of(c) = descriptor of chunk c (DevParams::seed_desc layout).
+// PEEL (only without EXPAND): for an index with long keys, whose buckets are mostly empty -- the first two entries of a
+// bucket are scored under predicates, so that the lanes of a warp stay together; a loop takes what is left.
+template <uint32_t MODE, bool EXPAND, bool PEEL = false, class DescFn>
+__device__ __forceinline__ bool seed_search_t(const DevParams &p, uint32_t C, DescFn desc_of, const uint16_t *__restrict__ hdr,
+                                              const uint16_t *__restrict__ ids, const uint2 *__restrict__ table,
+                                              const Rd &rd, uint32_t &best, uint32_t &nxt, uint32_t tstride) {
+    // tstride: distance of consecutive samples' planes in `table`, in entries (replicated tables of sgdx_ph.cu)
+    const uint32_t inv = rd.nmask | rd.xmask;
+    const uint32_t skip = (MODE == kModePreCompute && rd.nmask != 0u) ? p.M + 1u : 0xFFFFu;
+    bool complete = true;
+    for (uint32_t c = 0; c < C; c++) {
+        const uint32_t desc = desc_of(c);
+        const uint32_t pos = desc & 0xFFu, w = (desc >> 8) & 0xFFu, off = desc >> 16;
+        const uint32_t wm = (1u << w) - 1u;
+        const uint32_t iv = (inv >> pos) & wm;
+        const uint32_t key0 = ((rd.lo >> pos) & wm) | (((rd.hi >> pos) & wm) << w);
+        if (!EXPAND) {  // caller guarantees a read without invalid bases: exactly one bucket per chunk
+            uint32_t start = hdr[off + key0];
+            const uint32_t end = hdr[off + key0 + 1u];
+            if (PEEL) {
+#pragma unroll
+                for (uint32_t k = 0; k < 2u; k++) {
+                    const bool on = start + k < end;
+                    const uint32_t s = on ? ids[start + k] : 0u;
+                    const uint2 t = table[s * tstride];
+                    uint32_t b2 = best, n2 = nxt;
+                    score<MODE>(rd, inv, skip, t.x, t.y, s, b2, n2);
+                    best = on ? b2 : best;
+                    nxt = on ? n2 : nxt;
+                }
+                start += 2u;
+            }
+#pragma unroll 1  // buckets hold 0-2 samples: an unrolled loop only adds its trip-count dispatch ladder
+            for (uint32_t i = start; i < end; i++) {
+                const uint32_t s = ids[i];
+                const uint2 t = table[s * tstride];
+                score<MODE>(rd, inv, skip, t.x, t.y, s, best, nxt);
+            }
+            continue;
+        }
+        const bool several = (iv & (iv - 1u)) != 0u;
+        complete = complete && !several;
+        const uint32_t nvar = several ? 0u : (iv ? 4u : 1u);
+        const uint32_t j = iv ? (uint32_t)__ffs(iv) - 1u : 0u;
+        for (uint32_t b = 0; b < nvar; b++) {
+            const uint32_t key = key0 | ((b & 1u) << j) | ((b >> 1) << (w + j));
+            const uint32_t start = hdr[off + key], end = hdr[off + key + 1u];
+#pragma unroll 1
+            for (uint32_t i = start; i < end; i++) {
+                const uint32_t s = ids[i];
+                const uint2 t = table[s * tstride];
+                score<MODE>(rd, inv, skip, t.x, t.y, s, best, nxt);
+            }
+        }
+    }
+    return complete;
+}
+
+// the handle's full seed index (T + 1 chunks, DevParams) -- the same enumeration written out for DevParams::seed_*, as
+// the ASCII / seeded kernels and sgdx_match_ph were tuned with it
 template <uint32_t MODE, bool EXPAND>
 __device__ __forceinline__ bool seed_search(const DevParams &p, const uint16_t *__restrict__ hdr,
                                             const uint16_t *__restrict__ ids, const uint2 *__restrict__ table,
                                             const Rd &rd, uint32_t &best, uint32_t &nxt, uint32_t tstride = 1u) {
-    // tstride: distance of consecutive samples' planes in `table`, in entries (replicated tables of sgdx_ph.cu)
     const uint32_t inv = rd.nmask | rd.xmask;
     const uint32_t skip = (MODE == kModePreCompute && rd.nmask != 0u) ? p.M + 1u : 0xFFFFu;
     bool complete = true;

@@ -83,6 +83,7 @@ def test_c3_table_runs_the_perfect_hash_kernel_on_16_byte_records(n, shift):
         for (M, D, F, mnc) in [(3, 1, 1, None), (1, 2, 1, None), (3, 1, 0, 2), (0, 0, 0, None)]:
             m = CLS[kind]([bytes(t) for t in table], M, D, F, max_no_calls=mnc, index_lengths=il)
             assert m.packed_kernel_name() == "sgdx_match_phx" and m.path_flags() & 64
+            assert bool(m.path_flags() & 128) == (M >= 1)  # short seed index whenever the key set stops short of M
             idx, dist = _run_packed_device(m, reads, shift)
             per, totals = m.counters()
             assert totals["total_templates"] == n

@@ -373,6 +373,37 @@ def test_routing_is_a_stable_partition(S, n):
     m.close()
 
 
+@pytest.mark.parametrize("S,kind", [(2, "skew"), (3, "runs"), (4, "skew"), (384, "skew"), (384, "runs"), (384, "one"),
+                                    (1536, "skew"), (40, "unaligned")])
+def test_routing_of_skewed_index_arrays(S, kind):
+    """Steps of the ranked scatter dominated by one bin (the rounds give up and the hardware match takes over), runs of
+    equal indices, a single bin, and an index array that is not 16-byte aligned (scalar histogram loads)."""
+    import torch
+    n = 300_007
+    rng = np.random.default_rng(S * 7 + len(kind))
+    idx = rng.integers(0, S + 1, n).astype(np.uint16)
+    if kind == "skew":
+        idx[rng.random(n) < 0.9] = S // 2
+    elif kind == "runs":
+        idx = np.sort(idx)[::-1].copy()
+        idx[1000:5000] = rng.integers(0, S + 1, 4000)
+    elif kind == "one":
+        idx[:] = S
+    m = sg.CachedHammingDistanceMatcher([bytes(b) for b in sg.synth.Workload("r", S, 12, 0, 1, 1, table_seed=1, min_dist=1).table()], 1, 1, 1)
+    off_bytes = 2 if kind == "unaligned" else 0
+    buf = torch.zeros(n + 8, dtype=torch.int16, device="cuda")
+    d_idx = buf[off_bytes // 2: off_bytes // 2 + n]
+    d_idx.copy_(torch.from_numpy(idx.view(np.int16)))
+    d_order = torch.full((n,), -1, dtype=torch.int32, device="cuda")
+    d_off = torch.zeros(S + 2, dtype=torch.int64, device="cuda")
+    m.route_device(d_idx.data_ptr(), n, d_order.data_ptr(), d_off.data_ptr())
+    m.sync(0)
+    want_order, want_off = orc.route_reads(idx, S)
+    assert np.array_equal(d_off.cpu().numpy().astype(np.uint64), want_off)
+    assert np.array_equal(d_order.cpu().numpy().view(np.uint32), want_order)
+    m.close()
+
+
 def test_routing_after_assignment_c2():
     """Assignment -> routing on one stream, device resident: every sample's run holds exactly its reads, in order."""
     import torch

@@ -201,3 +201,61 @@ def test_wide_keys_on_close_tables(seed, S, L, M, D):
         assert info[0] == 1
         want_idx, want_dist = oracle_run(table, M, D, kind, reads)
         _check_decided(idx, dist, info, table, M, reads, want_idx, want_dist)
+
+
+@pytest.mark.parametrize("cfg_name,M,D,kind", [("C3", 3, 1, orc.MATCHER_CACHED_HAMMING), ("C3", 2, 2, orc.MATCHER_CACHED_HAMMING),
+                                               ("C2", 2, 1, orc.MATCHER_CACHED_HAMMING), ("C2", 2, 1, orc.MATCHER_PRECOMPUTE),
+                                               ("C1", 3, 0, orc.MATCHER_PRECOMPUTE), ("C3", 3, 1, orc.MATCHER_PRECOMPUTE)])
+def test_short_seed_index_rule_holds_in_the_oracle(cfg_name, M, D, kind):
+    """The claim behind PhParams::ms_* (sgdx_match_phx): enumerate the samples that agree with the read on every valid
+    position of one of max_mismatches + 1 chunks; with best = the closest of them (p valid-position mismatches, ninv
+    invalid positions) the read is decided by that enumeration alone when there is no candidate, when p > M, or when
+    2 p + min_delta + ninv < dmin -- the verdict of the rules applied to (best, second best of the enumeration) is then
+    Matcher::find's.  Restated here in numpy and compared with the oracle, reads with no-calls included."""
+    w = sg.synth.CONFIGS[cfg_name]
+    table = w.table()
+    S, L = table.shape
+    pair = (table[:, None, :] != table[None, :, :]).sum(-1)
+    np.fill_diagonal(pair, 99)
+    dmin = int(pair.min())
+    rng = np.random.default_rng(S + 10 * M + D + kind)
+    n = 3000
+    reads = reads_near(table, rng, n, M + 2)
+    if w.index1_len:  # index hops: halves of two different samples
+        a, b = rng.integers(0, S, 300), rng.integers(0, S, 300)
+        reads[:300] = np.concatenate([table[a, :w.index1_len], table[b, w.index1_len:]], axis=1)
+    nmask = rng.random((n, L)) < 0.02
+    nmask[: n // 2] = False
+    reads[nmask] = ord("N")
+    valid = reads != ord("N")
+    ninv = (~valid).sum(1)
+    p_all = ((reads[:, None, :] != table[None, :, :]) & valid[:, None, :]).sum(-1)  # [n, S]
+    C = M + 1
+    bounds = [(c * L // C, (c + 1) * L // C) for c in range(C)]
+    cand = np.zeros((n, S), dtype=bool)
+    for a, b in bounds:
+        cand |= (((reads[:, None, a:b] != table[None, :, a:b]) & valid[:, None, a:b]).sum(-1) == 0)
+    assert (cand | (p_all > M)).all(), "pigeonhole: every sample within M shares a chunk"
+    key = np.where(cand, (p_all + ninv[:, None]) * 65536 + np.arange(S)[None, :], 1 << 40)
+    order = np.sort(key, axis=1)
+    best, nxt = order[:, 0], (order[:, 1] if S > 1 else np.full(n, 1 << 40))
+    none = best >= (1 << 40)
+    bd, nd = best >> 16, np.where(nxt >= (1 << 40), 0xFFFF, nxt >> 16)
+    pb = bd - ninv
+    sure = none | (pb > M) | (2 * pb + D + ninv < dmin)
+    assert sure.mean() > 0.5  # (reads at 0..M+2 substitutions, uniformly: far more borderline reads than real data)
+    free_ns = 1
+    if kind == orc.MATCHER_CACHED_HAMMING:
+        rep = bd - np.minimum(ninv, free_ns)
+        ok = ~none & (rep <= M) & (nd - bd > D)
+    else:
+        pc_limit = max(M, M + D - 1) if M + D else L
+        nd_vis = np.where((ninv > 0) & (nd == M + 1), 0xFFFF, nd)  # (a second best at M + 1 is invisible: only matters unsure)
+        rep = bd
+        ok = ~none & (bd <= M) & ~((nd_vis <= bd + D) & (nd_vis <= pc_limit))
+    want_idx = np.where(ok, best & 0xFFFF, S).astype(np.uint16)
+    want_dist = np.where(ok, rep, 0xFF).astype(np.uint8)
+    cfg = orc.Config(S, L, M, D, free_ns, -1, kind, 0, 0)
+    got = orc.COracle(cfg, [bytes(t) for t in table], force_closed_form=True).run(reads, threads=2, use_cache=False)
+    assert np.array_equal(got["idx"][sure], want_idx[sure])
+    assert np.array_equal(got["dist"][sure], want_dist[sure])
