@@ -50,7 +50,8 @@ extern "C" {
 #define SGDX_KERNEL_DIRECT 1u     /* per (read, sample) XOR/OR/POPC scan with best/second-best keys */
 #define SGDX_KERNEL_SEEDED 2u     /* pigeonhole seed index -> verify only the candidate samples; falls back to DIRECT when the seed index does not apply */
 
-#define SGDX_MAX_BARCODE_LEN 32u
+#define SGDX_MAX_BARCODE_LEN 64u  /* ASCII entry points; 33..64 bases run sgdx_match_long (each index half <= 32 bases) */
+#define SGDX_MAX_PACKED_LEN 32u   /* sgdx_read records, the unmatched table and the synthetic generator */
 #define SGDX_MAX_SAMPLES 8192u
 #define SGDX_NO_DIST 0xFFu        /* out_dist value of a NoMatch read */
 
@@ -124,7 +125,9 @@ int sgdx_match_packed_device(sgdx_handle *h, uint32_t slot, const sgdx_read *d_p
  * converts n ASCII barcodes of any barcode_len <= 32 into 16-byte sgdx_read records (host code, `threads` workers,
  * AVX2 when the CPU has it; same records as sgdx_pack_device), sgdx_match_packed_batch is sgdx_match_batch for such
  * a buffer (16 instead of barcode_len bytes per read over PCIe: worth it above 16 bases; for <= 21 bases the compact
- * records below are smaller).  Runs the general kernels; unmatched collection needs ASCII. */
+ * records below are smaller).  The unmatched table (sgdx_unmatched_enable) is keyed from the records; a NoMatch barcode
+ * with a byte that is none of A/C/G/T/N cannot be keyed from a record (the byte itself is not kept) and is counted
+ * in sgdx_unmatched_info.dropped_reads -- the ASCII entry points count those as well. */
 int sgdx_pack_host(const uint8_t *barcodes_ascii, uint64_t n, uint32_t barcode_len, sgdx_read *out_records,
                    uint32_t threads /* 0 -> 1 */);
 int sgdx_match_packed_batch(sgdx_handle *h, uint32_t slot, const sgdx_read *records, uint64_t n,
@@ -142,7 +145,7 @@ int sgdx_match_packed_batch(sgdx_handle *h, uint32_t slot, const sgdx_read *reco
  * cross PCIe, and the kernel (sgdx_match_ph, see SGDX_PATH_PERFECT_HASH) reads four of them with one 256-bit load.
  * Results are identical to the ASCII entry points for every configuration; tables too large for the perfect hash
  * are served through the 16-byte packed form of the general kernels.  Bits above barcode_len in any plane, and
- * bit 63, are ignored.  Unmatched collection needs ASCII. */
+ * bit 63, are ignored.  The unmatched table is keyed from the records (see above for bytes outside A/C/G/T/N). */
 #define SGDX_COMPACT_MAX_LEN 21u
 int sgdx_pack_compact_host(const uint8_t *barcodes_ascii, uint64_t n, uint32_t barcode_len, uint64_t *out_records,
                            uint32_t threads /* 0 -> 1 */);

@@ -18,7 +18,8 @@ PATH_SEED_INDEX, PATH_EXACT, PATH_NEIGHBOURS, PATH_HOP_DIRECT = 1, 2, 4, 8
 PATH_PERFECT_HASH = 64
 PATH_SHORT_SEED = 128
 COMPACT_MAX_LEN = 21
-MAX_BARCODE_LEN = 32
+MAX_BARCODE_LEN = 64
+MAX_PACKED_LEN = 32
 MAX_SAMPLES = 8192
 
 

@@ -398,11 +398,23 @@ static int fill_handle(sgdx_handle *h, const sgdx_config *cfg, const uint8_t *ba
     p.i1 = cfg->index1_len;
     p.i2 = cfg->index2_len;
 
+    const bool is_long = L > SGDX_MAX_PACKED_LEN;  // two halves of planes, sgdx_match_long only (sgdx_long.cu)
     std::vector<uint2> table(p.table_pad, make_uint2(0u, 0u));
-    for (uint32_t s = 0; s < S; s++) encode_planes(barcodes + (uint64_t)s * L, L, &table[s].x, &table[s].y);
-    CU(cudaMalloc(&h->d_table, table.size() * sizeof(uint2)));
-    CU(cudaMemcpy(h->d_table, table.data(), table.size() * sizeof(uint2), cudaMemcpyHostToDevice));
-    p.table = h->d_table;
+    if (is_long) {
+        std::vector<uint4> tl(S);
+        for (uint32_t s = 0; s < S; s++) {
+            const uint8_t *bc = barcodes + (uint64_t)s * L;
+            encode_planes(bc, 32u, &tl[s].x, &tl[s].y);
+            encode_planes(bc + 32, L - 32u, &tl[s].z, &tl[s].w);
+        }
+        CU(cudaMalloc(&h->d_table_long, tl.size() * sizeof(uint4)));
+        CU(cudaMemcpy(h->d_table_long, tl.data(), tl.size() * sizeof(uint4), cudaMemcpyHostToDevice));
+    } else {
+        for (uint32_t s = 0; s < S; s++) encode_planes(barcodes + (uint64_t)s * L, L, &table[s].x, &table[s].y);
+        CU(cudaMalloc(&h->d_table, table.size() * sizeof(uint2)));
+        CU(cudaMemcpy(h->d_table, table.data(), table.size() * sizeof(uint2), cudaMemcpyHostToDevice));
+        p.table = h->d_table;
+    }
 
     const size_t ncounters = (size_t)(S + 1) * 3;
     CU(cudaMalloc(&h->d_counters, ncounters * sizeof(unsigned long long)));
@@ -462,7 +474,10 @@ static int fill_handle(sgdx_handle *h, const sgdx_config *cfg, const uint8_t *ba
 
     // kernel choice: the seeded kernel needs its index to exist (T+1 <= L, shared memory fits); AUTO takes
     // it when the expected number of candidates per read is well below a full scan of the table
-    {
+    if (is_long) {
+        h->seeded = false;
+        h->cfg.kernel = SGDX_KERNEL_DIRECT;  // (the long form of the per-pair scan)
+    } else {
         double est = 0.0;
         bool have = false;
         if (h->cfg.kernel != SGDX_KERNEL_DIRECT) {
@@ -509,6 +524,9 @@ extern "C" int sgdx_create(const sgdx_config *cfg, const uint8_t *barcodes, sgdx
     if ((cfg->index1_len == 0) != (cfg->index2_len == 0) ||
         (cfg->index1_len && cfg->index1_len + cfg->index2_len != L))
         return fail(SGDX_EINVAL, "index1_len + index2_len must equal barcode_len (or both be 0)");
+    if (cfg->index1_len > SGDX_MAX_PACKED_LEN || cfg->index2_len > SGDX_MAX_PACKED_LEN)
+        return fail(SGDX_EINVAL, "index halves of %u + %u bases: the hop checker takes at most %u bases per half", cfg->index1_len,
+                    cfg->index2_len, SGDX_MAX_PACKED_LEN);
     for (uint64_t i = 0; i < (uint64_t)S * L; i++) {
         uint8_t c = barcodes[i];
         if (c != 'A' && c != 'C' && c != 'G' && c != 'T')
@@ -550,6 +568,7 @@ extern "C" void sgdx_destroy(sgdx_handle *h) {
         if (s.own) cudaStreamDestroy(s.own);
     }
     cudaFree(h->d_table);
+    cudaFree(h->d_table_long);
     cudaFree(h->d_seed_hdr);
     cudaFree(h->d_seed_ids);
     cudaFree(h->d_ex_slots);
@@ -605,13 +624,10 @@ static int run_kernels(sgdx_handle *h, Slot &s, const uint8_t *d_ascii, const ui
     p.n = n;
     p.out_idx = d_idx;
     p.out_dist = d_dist;
-    if (h->unm.on && !d_ascii && n)
-        return fail(SGDX_ESTATE, "unmatched collection needs ASCII input (packed records do not keep foreign bytes)");
-    if (d_packed && h->ph.slots && h->ph.wide) {  // sgdx_match_ph on 16-byte records
-        PhParams c = h->ph;
-        c.reads_wide = d_packed;
+    if (h->d_table_long) {  // 33..64 bases
+        if (!d_ascii && n) return fail(SGDX_EINVAL, "barcode_len %u: records hold at most %u bases, use the ASCII entry points", p.L, SGDX_MAX_PACKED_LEN);
         CU(cudaEventRecord(s.e0, s.stream));
-        CU(launch_phx(p, c, h->mode, h->sms, s.stream));
+        CU(launch_long(p, h->d_table_long, h->mode, h->sms, s.stream));
         if (n) h->launches.fetch_add(1);
         CU(cudaEventRecord(s.e1, s.stream));
         s.timed = true;
@@ -620,11 +636,18 @@ static int run_kernels(sgdx_handle *h, Slot &s, const uint8_t *d_ascii, const ui
     std::unique_lock<std::mutex> lk(h->post_mu, std::defer_lock);
     if (h->unm.on) lk.lock();  // a downsize of the unmatched table must not overlap a batch
     CU(cudaEventRecord(s.e0, s.stream));
-    if (h->seeded) CU(launch_seeded(p, h->mode, d_packed != nullptr, h->sms, s.stream));
-    else CU(launch_direct(p, h->mode, d_packed != nullptr, h->sms, s.stream));
+    if (d_packed && h->ph.slots && h->ph.wide) {  // sgdx_match_phx on 16-byte records
+        PhParams c = h->ph;
+        c.reads_wide = d_packed;
+        CU(launch_phx(p, c, h->mode, h->sms, s.stream));
+    } else if (h->seeded) {
+        CU(launch_seeded(p, h->mode, d_packed != nullptr, h->sms, s.stream));
+    } else {
+        CU(launch_direct(p, h->mode, d_packed != nullptr, h->sms, s.stream));
+    }
     if (n) h->launches.fetch_add(1);
     if (h->unm.on && n)
-        if (int rc = post_after_match(h, s, d_ascii, d_idx, n)) return rc;
+        if (int rc = post_after_match(h, s, d_ascii, nullptr, d_ascii ? nullptr : d_packed, d_idx, n)) return rc;
     CU(cudaEventRecord(s.e1, s.stream));
     s.timed = true;
     return SGDX_OK;
@@ -652,6 +675,7 @@ extern "C" int sgdx_pack_device(sgdx_handle *h, uint32_t slot, const uint8_t *d_
     if (int rc = check_slot(h, slot)) return rc;
     if (n && (!d_ascii || !d_packed)) return fail(SGDX_EINVAL, "sgdx_pack_device: null buffer");
     if (reinterpret_cast<uintptr_t>(d_packed) & 15u) return fail(SGDX_EINVAL, "packed records must be 16-byte aligned");
+    if (h->cfg.barcode_len > SGDX_MAX_PACKED_LEN) return fail(SGDX_EINVAL, "sgdx_read records hold at most %u bases", SGDX_MAX_PACKED_LEN);
     CU(cudaSetDevice(h->cfg.device));
     CU(launch_pack(d_ascii, n, h->cfg.barcode_len, reinterpret_cast<uint4 *>(d_packed), h->sms, h->slots[slot].stream));
     if (n) h->launches.fetch_add(1);
@@ -714,31 +738,25 @@ static int run_compact(sgdx_handle *h, Slot &s, const uint64_t *d_records, uint6
     if (h->cfg.barcode_len > kCompactMaxLen)
         return fail(SGDX_EINVAL, "compact records hold at most %u bases, barcode_len is %u", kCompactMaxLen, h->cfg.barcode_len);
     if (reinterpret_cast<uintptr_t>(d_records) & 7u) return fail(SGDX_EINVAL, "compact records must be 8-byte aligned");
-    if (h->unm.on && n)
-        return fail(SGDX_ESTATE, "unmatched collection needs ASCII input (compact records do not keep foreign bytes)");
-    if (h->single) {  // one barcode: sgdx_match_single
+    if (h->single || (h->ph.slots && !h->ph.wide)) {
         DevParams p = h->base;
         p.n = n;
         p.out_idx = d_idx;
         p.out_dist = d_dist;
+        std::unique_lock<std::mutex> lk(h->post_mu, std::defer_lock);
+        if (h->unm.on) lk.lock();  // a downsize of the unmatched table must not overlap a batch
         CU(cudaEventRecord(s.e0, s.stream));
-        CU(launch_single(p, d_records, h->mode, h->sms, s.stream));
+        if (h->single) {  // one barcode: sgdx_match_single
+            CU(launch_single(p, d_records, h->mode, h->sms, s.stream));
+        } else {  // perfect hash of the match neighbourhood: sgdx_match_ph / sgdx_match_phx
+            PhParams c = h->ph;
+            c.reads = d_records;
+            if (c.radius >= p.M) CU(launch_ph(p, c, h->mode, h->sms, s.stream));
+            else CU(launch_phx(p, c, h->mode, h->sms, s.stream));
+        }
         if (n) h->launches.fetch_add(1);
-        CU(cudaEventRecord(s.e1, s.stream));
-        s.timed = true;
-        return SGDX_OK;
-    }
-    if (h->ph.slots && !h->ph.wide) {  // perfect hash of the match neighbourhood: sgdx_match_ph
-        DevParams p = h->base;
-        p.n = n;
-        p.out_idx = d_idx;
-        p.out_dist = d_dist;
-        PhParams c = h->ph;
-        c.reads = d_records;
-        CU(cudaEventRecord(s.e0, s.stream));
-        if (c.radius >= p.M) CU(launch_ph(p, c, h->mode, h->sms, s.stream));
-        else CU(launch_phx(p, c, h->mode, h->sms, s.stream));
-        if (n) h->launches.fetch_add(1);
+        if (h->unm.on && n)  // most frequent unmatched barcodes (demux.rs:553-555), keyed from the records
+            if (int rc = post_after_match(h, s, nullptr, d_records, nullptr, d_idx, n)) return rc;
         CU(cudaEventRecord(s.e1, s.stream));
         s.timed = true;
         return SGDX_OK;
@@ -831,6 +849,7 @@ extern "C" int sgdx_set_stream(sgdx_handle *h, uint32_t slot, void *stream) {
 
 extern "C" const char *sgdx_kernel_name(const sgdx_handle *h) {
     if (!h) return "";
+    if (h->d_table_long) return "sgdx_match_long";
     if (!h->seeded) return "sgdx_match_direct";
     return h->base.ex_on ? "sgdx_match_exact_first" : "sgdx_match_seeded";
 }
@@ -843,7 +862,7 @@ extern "C" const char *sgdx_compact_kernel_name(const sgdx_handle *h) {
 }
 
 extern "C" const char *sgdx_packed_kernel_name(const sgdx_handle *h) {
-    if (!h) return "";
+    if (!h || h->d_table_long) return "";
     if (h->ph.slots && h->ph.wide) return "sgdx_match_phx";
     return h->seeded ? "sgdx_match_seeded" : "sgdx_match_direct";
 }
@@ -1011,7 +1030,6 @@ extern "C" int sgdx_batcher_set_compact(sgdx_batcher *b, int on) {
     if (b->fill || !b->inflight.empty()) return fail(SGDX_ESTATE, "sgdx_batcher_set_compact: batches are in flight");
     if (on && b->L > kCompactMaxLen)
         return fail(SGDX_EINVAL, "compact records hold at most %u bases, barcode_len is %u", kCompactMaxLen, b->L);
-    if (on && b->h->unm.on) return fail(SGDX_ESTATE, "unmatched collection needs ASCII input");
     b->compact = on != 0;
     return SGDX_OK;
 }

@@ -90,6 +90,7 @@ struct sgdx_handle {
     sgdx::PhParams ph{};
     uint32_t ph_keys = 0;
     bool single = false;  // compact records run sgdx_match_single
+    uint4 *d_table_long = nullptr;  // barcode_len > 32: {loA, hiA, loB, hiB} per sample, the handle runs sgdx_match_long
     sgdx::HopSlot *d_hash1 = nullptr, *d_hash2 = nullptr;
     uint16_t *d_hop_lut1 = nullptr, *d_hop_lut2 = nullptr;
     unsigned long long *d_hop_fwd = nullptr, *d_hop_rev = nullptr;
@@ -105,7 +106,8 @@ struct sgdx_handle {
 
 namespace sgdx {
 // hooks of sgdx_post.cu called by sgdx_api.cu
-int post_after_match(sgdx_handle *h, Slot &s, const uint8_t *d_ascii, const uint16_t *d_idx, uint64_t n);
+int post_after_match(sgdx_handle *h, Slot &s, const uint8_t *d_ascii, const uint64_t *d_compact, const uint4 *d_packed,
+                     const uint16_t *d_idx, uint64_t n);
 int post_on_sync(sgdx_handle *h, Slot &s);
 int post_reset(sgdx_handle *h);
 void post_destroy(sgdx_handle *h);

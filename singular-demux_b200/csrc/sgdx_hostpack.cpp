@@ -171,8 +171,8 @@ extern "C" int sgdx_pack_compact_host(const uint8_t *ascii, uint64_t n, uint32_t
 }
 
 extern "C" int sgdx_pack_host(const uint8_t *ascii, uint64_t n, uint32_t barcode_len, sgdx_read *out, uint32_t threads) {
-    if (barcode_len < 1 || barcode_len > SGDX_MAX_BARCODE_LEN)
-        return sgdx::fail(SGDX_EINVAL, "barcode_len %u outside 1..%u", barcode_len, SGDX_MAX_BARCODE_LEN);
+    if (barcode_len < 1 || barcode_len > SGDX_MAX_PACKED_LEN)
+        return sgdx::fail(SGDX_EINVAL, "barcode_len %u outside 1..%u", barcode_len, SGDX_MAX_PACKED_LEN);
     if (n && (!ascii || !out)) return sgdx::fail(SGDX_EINVAL, "sgdx_pack_host: null buffer");
     run_threads(planes_range, ascii, n, barcode_len, out, threads);
     return SGDX_OK;

@@ -85,6 +85,9 @@ cudaError_t launch_phx(const DevParams &p, const PhParams &c, uint32_t mode, int
 // one expected barcode, no hop checker (sgdx_single.cu): compact records against a single pair of planes
 cudaError_t launch_single(const DevParams &p, const uint64_t *reads, uint32_t mode, int sms, cudaStream_t stream);
 
+// barcodes of 33..64 bases (sgdx_long.cu): ASCII input against {loA, hiA, loB, hiB} planes of the expected barcodes
+cudaError_t launch_long(const DevParams &p, const uint4 *table, uint32_t mode, int sms, cudaStream_t stream);
+
 // integer-pipe micro-benchmark (sgdx_microbench.cu)
 cudaError_t measure_int_peak(int sms, double *popc_per_s, double *lop3_per_s);
 

@@ -267,7 +267,7 @@ int probe(const sgdx_config *cfg, const uint8_t *barcodes, const uint64_t *compa
     const bool wide = wide_records != nullptr;
     if (!cfg || !barcodes || (n && (!(compact || wide_records) || !out_idx || !out_dist))) return SGDX_EINVAL;
     const uint32_t S = cfg->num_samples, L = cfg->barcode_len;
-    if (S < 1 || S > SGDX_MAX_SAMPLES || L < 1 || L > (wide ? SGDX_MAX_BARCODE_LEN : SGDX_COMPACT_MAX_LEN)) return SGDX_EINVAL;
+    if (S < 1 || S > SGDX_MAX_SAMPLES || L < 1 || L > (wide ? SGDX_MAX_PACKED_LEN : SGDX_COMPACT_MAX_LEN)) return SGDX_EINVAL;
     std::vector<PhPlanes> table(S);
     for (uint32_t s = 0; s < S; s++) {
         uint32_t lo = 0, hi = 0;

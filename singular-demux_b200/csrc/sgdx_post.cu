@@ -15,6 +15,7 @@
 #include <cstring>
 
 #include "sgdx_handle.h"
+#include "sgdx_seed_search.cuh"  // rd_of_compact
 
 using namespace sgdx;
 
@@ -109,9 +110,21 @@ constexpr uint32_t kUnmThreads = 256;
 // thread tests eight index entries of a tile (eight independent loads) and queues the NoMatch ones in shared
 // memory; whenever the queue holds a full batch of 256 the CTA drains it, one thread per queued read (word loads,
 // SWAR key, one 128-bit CAS + one add).
-__global__ void __launch_bounds__(kUnmThreads) sgdx_unmatched_count(const uint8_t *__restrict__ reads,
+// INPUT 0: ASCII barcodes.  1: compact 64-bit records, 2: 16-byte sgdx_read records -- the key comes from the planes
+// (every plane byte is spread to every third bit through a 256-entry table in shared memory).  A packed record does
+// not keep a byte that is none of A/C/G/T/N, so such a barcode cannot be keyed: it is counted as dropped.
+template <int INPUT>
+__global__ void __launch_bounds__(kUnmThreads) sgdx_unmatched_count(const void *__restrict__ reads_any,
                                                                     const uint16_t *__restrict__ idx, uint64_t n,
                                                                     uint32_t S, uint32_t L, const UnmTable t) {
+    const uint8_t *__restrict__ reads = static_cast<const uint8_t *>(reads_any);
+    __shared__ uint32_t s_spread[INPUT ? 256 : 1];  // bit j of the index -> bit 3 j
+    if (INPUT)
+        for (uint32_t i = threadIdx.x; i < 256u; i += kUnmThreads) {
+            uint32_t v = 0u;
+            for (uint32_t j = 0; j < 8u; j++) v |= ((i >> j) & 1u) << (3u * j);
+            s_spread[i] = v;
+        }
     // the number of distinct keys is published in steps of kUnmPublish per CTA (one global atomic per step instead
     // of one per key on a single word); the key limit is therefore enforced to within gridDim.x * kUnmPublish keys
     __shared__ unsigned int s_drop, s_new, s_qn;
@@ -124,7 +137,31 @@ __global__ void __launch_bounds__(kUnmThreads) sgdx_unmatched_count(const uint8_
     uint32_t seen = 0;  // thread 0 only
 
     auto drain = [&](uint32_t from, uint32_t count) {  // queue entries [from, from + count), count <= 256
-        if (threadIdx.x < count) {
+        if (INPUT && threadIdx.x < count) {
+            const uint32_t e = s_queue[from + threadIdx.x];
+            const uint64_t r = ((uint64_t)blockIdx.x + (uint64_t)(e >> 11) * gridDim.x) * kUnmTile + (e & 2047u);
+            const unsigned long long distinct = *reinterpret_cast<volatile unsigned long long *>(t.stats);
+            Rd rd;
+            if (INPUT == 1) rd = rd_of_compact(__ldg(static_cast<const uint64_t *>(reads_any) + r), L >= 32u ? 0xFFFFFFFFu : (1u << L) - 1u);
+            else rd = load_packed(static_cast<const uint4 *>(reads_any), r, L);
+            bool ok = rd.xmask == 0u;
+            if (ok) {
+                const uint32_t b0 = rd.lo | rd.nmask, b1 = rd.hi | rd.nmask, b2 = rd.nmask;  // N = 7
+                unsigned long long sp[4];
+#pragma unroll
+                for (uint32_t k = 0; k < 4u; k++)  // bases 8k .. 8k+7 -> 24 bits
+                    sp[k] = s_spread[(b0 >> (8u * k)) & 0xFFu] | (s_spread[(b1 >> (8u * k)) & 0xFFu] << 1) |
+                            (s_spread[(b2 >> (8u * k)) & 0xFFu] << 2);
+                const unsigned long long k0 = sp[0] | (sp[1] << 24) | (sp[2] << 48);
+                const unsigned long long k1 = (sp[2] >> 16) | (sp[3] << 8);
+                const uint32_t how = unm_add(t, k0, (1ull << 63) | k1, 1ull, distinct >= t.key_limit);
+                ok = how != 0u;
+                if (how == 2u && (atomicAdd(&s_new, 1u) + 1u) % kUnmPublish == 0u)
+                    atomicAdd(t.stats + 0, (unsigned long long)kUnmPublish);
+            }
+            if (!ok) atomicAdd(&s_drop, 1u);
+        }
+        if (!INPUT && threadIdx.x < count) {
             const uint32_t e = s_queue[from + threadIdx.x];
             const uint64_t r = ((uint64_t)blockIdx.x + (uint64_t)(e >> 11) * gridDim.x) * kUnmTile + (e & 2047u);
             const uint8_t *p = reads + r * (uint64_t)L;
@@ -973,11 +1010,15 @@ static UnmTable unm_table(const UnmatchedState &u) {
     return t;
 }
 
-int post_after_match(sgdx_handle *h, Slot &s, const uint8_t *d_ascii, const uint16_t *d_idx, uint64_t n) {
+// exactly one of the three inputs is non-null: ASCII barcodes, compact records, 16-byte records
+int post_after_match(sgdx_handle *h, Slot &s, const uint8_t *d_ascii, const uint64_t *d_compact, const uint4 *d_packed,
+                     const uint16_t *d_idx, uint64_t n) {
     UnmatchedState &u = h->unm;
     const uint32_t grid = grid_cap(n, kUnmTile, h->sms, u.ctas_per_sm);  // exactly one wave of resident CTAs
-    sgdx_unmatched_count<<<grid, kUnmThreads, 0, s.stream>>>(d_ascii, d_idx, n, h->cfg.num_samples,
-                                                             h->cfg.barcode_len, unm_table(u));
+    const uint32_t S = h->cfg.num_samples, L = h->cfg.barcode_len;
+    if (d_ascii) sgdx_unmatched_count<0><<<grid, kUnmThreads, 0, s.stream>>>(d_ascii, d_idx, n, S, L, unm_table(u));
+    else if (d_compact) sgdx_unmatched_count<1><<<grid, kUnmThreads, 0, s.stream>>>(d_compact, d_idx, n, S, L, unm_table(u));
+    else sgdx_unmatched_count<2><<<grid, kUnmThreads, 0, s.stream>>>(d_packed, d_idx, n, S, L, unm_table(u));
     CU(cudaGetLastError());
     h->launches.fetch_add(1);
     if (!s.h_unm_stats) CU(cudaMallocHost(&s.h_unm_stats, kUnmStats * sizeof(unsigned long long)));
@@ -1188,6 +1229,8 @@ void post_destroy(sgdx_handle *h) {
 extern "C" int sgdx_unmatched_enable(sgdx_handle *h, uint64_t max_map_size, uint64_t downsize_to) {
     if (!h) return fail(SGDX_EINVAL, "null handle");
     if (h->unm.on) return fail(SGDX_ESTATE, "unmatched collection is already enabled");
+    if (h->cfg.barcode_len > SGDX_MAX_PACKED_LEN)
+        return fail(SGDX_EINVAL, "the unmatched table keys barcodes of at most %u bases (96-bit keys)", SGDX_MAX_PACKED_LEN);
     if (max_map_size == 0) max_map_size = 5000000ull;  // opts.rs:185
     if (downsize_to == 0) downsize_to = 5000ull;       // opts.rs:189
     if (downsize_to > max_map_size) downsize_to = max_map_size;
@@ -1199,7 +1242,7 @@ extern "C" int sgdx_unmatched_enable(sgdx_handle *h, uint64_t max_map_size, uint
     u.max_map_size = max_map_size;
     u.downsize_to = downsize_to;
     int per_sm = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sgdx_unmatched_count, (int)kUnmThreads, 0));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sgdx_unmatched_count<1>, (int)kUnmThreads, 0));  // (the form with the most shared memory)
     u.ctas_per_sm = per_sm < 1 ? 1 : per_sm;
     // room for a batch's worth of new keys between two syncs: 4x the limit, at least 2^21 slots (64 MB)
     uint64_t cap = 1ull << 21;  // key_limit must stay above the publishing lag of the distinct-key count

@@ -30,7 +30,7 @@ extern "C" int sgdx_synth_reads_host(const sgdx_synth_params *p, const uint8_t *
 
 extern "C" int sgdx_synth_reads_device(const sgdx_synth_params *p, const uint8_t *d_table, uint64_t first, uint64_t n,
                                        uint8_t *d_out, void *stream) {
-    if (!p || !d_table || (n && !d_out) || p->barcode_len == 0 || p->barcode_len > SGDX_MAX_BARCODE_LEN) return SGDX_EINVAL;
+    if (!p || !d_table || (n && !d_out) || p->barcode_len == 0 || p->barcode_len > SGDX_MAX_PACKED_LEN) return SGDX_EINVAL;
     if (n == 0) return SGDX_OK;
     uint64_t blocks = (n + 255) / 256;
     if (blocks > 148 * 32) blocks = 148 * 32;

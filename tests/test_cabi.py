@@ -46,7 +46,8 @@ def test_create_validates_before_touching_cuda():
         return L.sgdx_create(C.byref(cfg), table, C.byref(h))
 
     assert create(0, 8, b"") == -1 and b"num_samples" in L.sgdx_last_error()
-    assert create(1, 33, b"A" * 33) == -1 and b"barcode_len" in L.sgdx_last_error()
+    assert create(1, 65, b"A" * 65) == -1 and b"barcode_len" in L.sgdx_last_error()
+    assert create(1, 40, b"A" * 40, i1=36, i2=4) == -1 and b"hop checker" in L.sgdx_last_error()
     assert create(1, 8, b"ACGTNACG") == -1 and b"upper-case ACGT" in L.sgdx_last_error()
     assert create(1, 8, b"acgtacgt") == -1
     assert create(1, 8, b"ACGTACGT", i1=3, i2=4) == -1

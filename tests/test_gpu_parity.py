@@ -161,8 +161,9 @@ def test_baseline_tables_take_every_fast_path(cfg):
         want |= _lib.PATH_NEIGHBOURS
     if max(w.index_lengths) <= 11:
         want |= _lib.PATH_HOP_DIRECT
-    if w.barcode_len <= _lib.COMPACT_MAX_LEN:  # compact records: the perfect hash of the match neighbourhood
-        want |= _lib.PATH_PERFECT_HASH
+    want |= _lib.PATH_PERFECT_HASH  # compact records (C3: 16-byte records): the perfect hash of the match neighbourhood
+    if cfg == "C3":                 # ... which stops at the barcodes themselves there: second level + short seed index
+        want |= _lib.PATH_SHORT_SEED
     assert m.path_flags() == want and m.kernel_name() == "sgdx_match_exact_first"
     m.close()
 

@@ -167,7 +167,7 @@ def test_unmatched_long_barcodes_and_all_n():
     st.close()
 
 
-def test_unmatched_needs_ascii_input_and_enable():
+def test_unmatched_enable_state_checks():
     w = sg.synth.C1
     table = w.table()
     st = _stage(w, table)
@@ -176,11 +176,45 @@ def test_unmatched_needs_ascii_input_and_enable():
     st.matcher.unmatched_enable(1000, 10)
     with pytest.raises(sg.SgdxError):
         st.matcher.unmatched_enable(1000, 10)  # twice
-    import torch
-    d = torch.zeros(64, dtype=torch.uint8, device="cuda")
-    o = torch.zeros(4, dtype=torch.int16, device="cuda")
-    with pytest.raises(sg.SgdxError):
-        st.matcher.match_packed_device(d.data_ptr(), 4, o.data_ptr())
+    st.close()
+
+
+@pytest.mark.parametrize("cfg,n,form", [("C1", 300_000, "compact"), ("C2", 400_000, "compact"), ("C4", 400_000, "compact"),
+                                        ("C3", 200_000, "packed"), ("C2", 200_000, "packed"), ("C2m2", 200_000, "compact"),
+                                        ("C2m4", 60_000, "compact")])
+def test_unmatched_counts_from_compact_and_packed_records(cfg, n, form):
+    """Config 4's most_frequent_unmatched on the fast input formats: the unmatched table is keyed from the records
+    (compact 64-bit records through sgdx_match_ph / sgdx_match_phx / sgdx_match_single, 16-byte records through
+    sgdx_match_phx or the general kernels) and holds exactly the oracle's counts; a NoMatch barcode with a byte that is
+    none of A/C/G/T/N has no key in a record and is reported as dropped."""
+    import dataclasses
+    base = sg.synth.CONFIGS[cfg[:2]]
+    w = base if len(cfg) == 2 else dataclasses.replace(base, max_mismatches=int(cfg[3]), min_delta=1)
+    table = w.table()
+    reads = dataclasses.replace(w, p_n=0.01).reads_host(0, n, table)
+    reads[::50] = ord("N")
+    reads[7::997, 3] = ord("R")
+    st = _stage(w, table, unmatched_on_device=True, slots=2)
+    cuts = [0, n // 3, n // 2, n]
+    parts = []
+    for i, (a, b) in enumerate(zip(cuts, cuts[1:])):
+        if form == "compact":
+            parts.append(st.demultiplex(reads[a:b], slot=i % 2, compact=True, pack_threads=2).sample_indices)
+        else:
+            parts.append(st.matcher.find_batch_packed(reads[a:b], slot=i % 2, threads=2)[0])
+    idx = np.concatenate(parts)
+    want_idx = _oracle_idx(w, table, reads)
+    assert np.array_equal(idx, want_idx)
+    um = want_idx == w.num_samples
+    foreign = (~np.isin(reads, np.frombuffer(b"ACGTN", dtype=np.uint8))).any(axis=1)
+    keyable = um & ~foreign
+    want = orc.unmatched_counts(reads[keyable], want_idx[keyable], w.num_samples)
+    got = st.matcher.unmatched_counts()
+    assert got == want
+    info = st.matcher.unmatched_info()
+    assert info["unmatched_reads"] == int(um.sum()) and info["dropped_reads"] == int((um & foreign).sum())
+    assert info["distinct_keys"] == len(want)
+    assert (b"N" * w.barcode_len) in got
     st.close()
 
 
