@@ -534,6 +534,34 @@ def main():
         stress["note"] = ("same table and kernel as the headline; parity of both streams against the oracle: "
                           "tests/test_gpu_ph.py::test_stress_streams_equal_the_oracle")
 
+    # ---- config 4's most_frequent_unmatched on the fast path: the unmatched table fed from the compact
+    # records by the same launch sequence, top keys read back; parity of the counts: tests/test_gpu_post.py
+    unmatched_fast = None
+    if rank == 0 and world == 1 and side and compact_ok and args.config in ("C4", "C1"):
+        st2 = sg.BarcodeAssignmentStage(samples, cls, w.max_mismatches, w.min_delta, w.free_ns, w.max_no_calls, w.index_lengths,
+                                        device=local, slots=1, unmatched_on_device=True)
+        m2 = st2.matcher
+        m2.set_stream(0, stream.cuda_stream)
+        w.reads_device(rank * n, n, d_table.data_ptr(), d_in.data_ptr(), stream.cuda_stream)
+        m.pack_compact_device(d_in.data_ptr(), n, d_rec.data_ptr(), slot=0)
+        torch.cuda.synchronize()
+
+        def step_um():
+            m2.match_compact_device(d_rec.data_ptr(), n, d_idx.data_ptr(), d_dist.data_ptr(), slot=0)
+        m_saved = m
+        m = m2  # (timed() counts launches on m)
+        per_u, _, _, _ = timed(step_um, min(args.steps, 5), args.warmup)
+        m = m_saved
+        info = m2.unmatched_info()
+        top = m2.unmatched_top(5)
+        runs = min(args.steps, 5) + max(args.warmup, 3)
+        unmatched_fast = {"kernel": m2.compact_kernel_name() + " + sgdx_unmatched_count (keys from the compact records)",
+                          "avg_ms": sum(per_u) / len(per_u), "reads_per_s": n / (sum(per_u) / len(per_u) * 1e-3),
+                          "unmatched_reads_per_pass": info["unmatched_reads"] // runs, "distinct_keys": info["distinct_keys"],
+                          "dropped_reads": info["dropped_reads"],
+                          "top": [[k.decode(), c // runs] for k, c in top]}
+        st2.close()
+
     cb = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cb = cpu_baseline(w)
@@ -562,7 +590,7 @@ def main():
                        "l2": f"inputs {n * in_bytes / 1e6:.0f} MB + outputs {n * 3 / 1e6:.0f} MB per step, larger than the 126 MB L2"},
             "roofline": roofline, "cpu_baseline": cb, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": clocks, "matched_fraction": matched_frac, "merged_check": merged_check,
-            "ascii": ascii_side, "stress": stress, "post": post,
+            "ascii": ascii_side, "stress": stress, "unmatched_fast_path": unmatched_fast, "post": post,
         }
         os.write(json_fd, (json.dumps(out) + "\n").encode())
     if world > 1:

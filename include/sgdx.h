@@ -38,7 +38,7 @@ extern "C" {
 #define SGDX_EINVAL (-1)   /* bad argument / unsupported configuration */
 #define SGDX_ECUDA (-2)    /* CUDA runtime error (no device, launch failure, ...) */
 #define SGDX_ENOMEM (-3)
-#define SGDX_ESTATE (-4)   /* call made in the wrong state (e.g. slot busy with an unsynced batch) */
+#define SGDX_ESTATE (-4)   /* call made in the wrong state (e.g. unmatched table enabled twice, batcher results not taken) */
 
 /* matcher kinds: MatcherKind, matcher.rs:49-53 */
 #define SGDX_MATCHER_AUTO 0u              /* run.rs:196 rule: barcode_len <= 12 -> PreCompute, else CachedHamming */
@@ -59,7 +59,7 @@ typedef struct sgdx_handle sgdx_handle;
 
 typedef struct sgdx_config {
     uint32_t num_samples;     /* S, Undetermined excluded (run.rs:201,220); 1..SGDX_MAX_SAMPLES */
-    uint32_t barcode_len;     /* L, 1..32 */
+    uint32_t barcode_len;     /* L, 1..SGDX_MAX_BARCODE_LEN (records and the unmatched table: 1..SGDX_MAX_PACKED_LEN) */
     uint32_t max_mismatches;  /* --allowed-mismatches, opts.rs:118 */
     uint32_t min_delta;       /* --min-delta, opts.rs:123 */
     uint32_t free_ns;         /* --free-ns, opts.rs:127 (ignored by PreCompute, as in the reference) */
@@ -200,7 +200,11 @@ int sgdx_hop_export(sgdx_handle *h, uint8_t *keys /* cap*L */, uint64_t *counts 
 typedef struct sgdx_batcher sgdx_batcher;
 int sgdx_batcher_create(sgdx_handle *h, uint64_t batch_reads, sgdx_batcher **out);
 void sgdx_batcher_destroy(sgdx_batcher *b);
-/* append n barcodes (n*L ASCII bytes); launches a batch whenever one fills */
+/* append n barcodes (n*L ASCII bytes); launches a batch whenever one fills.  At most 2 x slots batches may wait for
+ * sgdx_batcher_next (each holds pinned result buffers): beyond that the push stops with SGDX_ESTATE.  On any failure
+ * *consumed (if not NULL) says how many of the n barcodes were taken, so that the caller can resume behind them
+ * instead of pushing them twice; sgdx_batcher_push is the same call without that count. */
+int sgdx_batcher_push_n(sgdx_batcher *b, const uint8_t *barcodes_ascii, uint64_t n, uint64_t *consumed);
 int sgdx_batcher_push(sgdx_batcher *b, const uint8_t *barcodes_ascii, uint64_t n);
 /* launch the partially filled batch, if any */
 int sgdx_batcher_flush(sgdx_batcher *b);

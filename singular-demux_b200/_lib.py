@@ -79,7 +79,7 @@ SYMBOLS = [
     "sgdx_free_host", "sgdx_match_batch", "sgdx_sync", "sgdx_match_device", "sgdx_pack_device",
     "sgdx_match_packed_device", "sgdx_pack_host", "sgdx_match_packed_batch", "sgdx_pack_compact_host", "sgdx_pack_compact_device", "sgdx_match_compact_batch",
     "sgdx_match_compact_device", "sgdx_set_stream", "sgdx_kernel_name", "sgdx_compact_kernel_name", "sgdx_packed_kernel_name", "sgdx_ph_probe_host_wide", "sgdx_path_flags", "sgdx_launch_count", "sgdx_counters", "sgdx_reset_counters",
-    "sgdx_hop_count", "sgdx_hop_export", "sgdx_batcher_create", "sgdx_batcher_destroy", "sgdx_batcher_push",
+    "sgdx_hop_count", "sgdx_hop_export", "sgdx_batcher_create", "sgdx_batcher_destroy", "sgdx_batcher_push", "sgdx_batcher_push_n",
     "sgdx_batcher_flush", "sgdx_batcher_set_compact", "sgdx_batcher_next", "sgdx_measure_int_peak",
     "sgdx_unmatched_enable", "sgdx_unmatched_info_get", "sgdx_unmatched_export", "sgdx_unmatched_top",
     "sgdx_unmatched_downsize", "sgdx_extract_device", "sgdx_match_segments_device", "sgdx_qual_counts_device",
@@ -138,6 +138,7 @@ def lib() -> C.CDLL:
     L.sgdx_batcher_destroy.argtypes = [vp]
     L.sgdx_batcher_destroy.restype = None
     L.sgdx_batcher_push.argtypes = [vp, vp, u64]
+    L.sgdx_batcher_push_n.argtypes = [vp, vp, u64, vp]
     L.sgdx_batcher_flush.argtypes = [vp]
     L.sgdx_batcher_set_compact.argtypes = [vp, i32]
     L.sgdx_batcher_next.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(u64)]

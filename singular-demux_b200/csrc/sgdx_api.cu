@@ -12,6 +12,7 @@
 #include <string>
 #include <vector>
 
+#include "sgdx_guard.h"
 #include "sgdx_handle.h"
 #include "sgdx_phbuild.h"
 
@@ -31,6 +32,18 @@ int sgdx::fail(int code, const char *fmt, ...) {
 
 extern "C" const char *sgdx_last_error(void) { return g_err.c_str(); }
 extern "C" const char *sgdx_version(void) { return "sgdx 0.1.0 (sm_100a)"; }
+
+// Test hooks: environment variables read by sgdx_create that switch an acceleration off (or force one on) so that the
+// parity tests can run the slower kernels on the same tables.  They never change results; a build with
+// -DSGDX_NO_TEST_HOOKS ignores them.
+static inline bool test_hook(const char *name) {
+#ifdef SGDX_NO_TEST_HOOKS
+    (void)name;
+    return false;
+#else
+    return getenv(name) != nullptr;
+#endif
+}
 
 static inline uint32_t base_code(uint8_t c) { return (c >> 1) & 3u; }  // A0 C1 T2 G3
 
@@ -172,7 +185,7 @@ static int build_exact_table(sgdx_handle *h, const uint8_t *barcodes, const std:
     uint32_t bits = 6;
     while ((1u << bits) < 4u * S) bits++;
     p.ex_bits = bits;
-    if (getenv("SGDX_DISABLE_EXACT")) return SGDX_OK;          // test hook: plain seeded kernel
+    if (test_hook("SGDX_DISABLE_EXACT")) return SGDX_OK;          // test hook: plain seeded kernel
     if (dmin <= p.delta) return SGDX_OK;                       // an exact hit could still be delta-rejected
     if (exact_block_threads(p) == 0u) return SGDX_OK;          // tables that do not fit one SM: general path only
     std::vector<uint32_t> rows((size_t)S * p.Lw, 0x41414141u), slots((size_t)1 << bits, 0u), owner((size_t)1 << bits, 0u);
@@ -195,12 +208,12 @@ static int build_exact_table(sgdx_handle *h, const uint8_t *barcodes, const std:
     // neighbour table: a string at distance 1 from a barcode decides the read when every other barcode is
     // then still further than min_delta away from it: (dmin - 1) - 1 > delta
     p.nb_on = 0;
-    if (getenv("SGDX_DISABLE_NEIGHBOURS")) return SGDX_OK;  // test hook: exercise the seed search on every miss
+    if (test_hook("SGDX_DISABLE_NEIGHBOURS")) return SGDX_OK;  // test hook: exercise the seed search on every miss
     if ((uint64_t)dmin <= (uint64_t)p.delta + 2u || S > 0x1FFFu) return SGDX_OK;
     // The neighbour stage costs two L2 probes per missed read; it pays when the seed search it saves is long
     // (measured on a B200: C3, ~12 expected candidates per read: 2.11 ms with, 2.82 ms without per 100 M reads;
     // C2, ~1.5 candidates: 1.65 ms with, 1.56 ms without)
-    if (est_candidates < 4.0 && !getenv("SGDX_FORCE_NEIGHBOURS")) return SGDX_OK;
+    if (est_candidates < 4.0 && !test_hook("SGDX_FORCE_NEIGHBOURS")) return SGDX_OK;
     const uint64_t entries = (uint64_t)S * L * 4u;
     uint32_t nbits = 8;
     while ((1ull << nbits) < 4u * entries) nbits++;
@@ -238,7 +251,7 @@ static int build_exact_table(sgdx_handle *h, const uint8_t *barcodes, const std:
 static int build_ph_table(sgdx_handle *h, const std::vector<uint2> &table) {
     const DevParams &p = h->base;
     h->ph = PhParams{};
-    if (getenv("SGDX_DISABLE_PH")) return SGDX_OK;  // test hook: the older compact kernels
+    if (test_hook("SGDX_DISABLE_PH")) return SGDX_OK;  // test hook: the older compact kernels
     std::vector<PhPlanes> planes(p.S);
     for (uint32_t s = 0; s < p.S; s++) planes[s] = PhPlanes{table[s].x, table[s].y};
     const PhRules rules{p.S, p.L, p.M, p.delta, p.pc_limit, h->mode};
@@ -495,7 +508,7 @@ static int fill_handle(sgdx_handle *h, const sgdx_config *cfg, const uint8_t *ba
         if (int rc = build_ph_table(h, table)) return rc;
         // one expected barcode and no hop checker: compact records need no table at all (sgdx_single.cu);
         // SGDX_DISABLE_SINGLE is a test hook (the perfect-hash kernel serves the same records)
-        h->single = S == 1 && !p.hop_on && L <= kCompactMaxLen && !getenv("SGDX_DISABLE_SINGLE");
+        h->single = S == 1 && !p.hop_on && L <= kCompactMaxLen && !test_hook("SGDX_DISABLE_SINGLE");
     }
 
     h->slots.resize(h->cfg.slots);
@@ -513,6 +526,7 @@ static int fill_handle(sgdx_handle *h, const sgdx_config *cfg, const uint8_t *ba
 
 
 extern "C" int sgdx_create(const sgdx_config *cfg, const uint8_t *barcodes, sgdx_handle **out) {
+    return sgdx::guarded("sgdx_create", [&]() -> int {
     if (!cfg || !barcodes || !out) return fail(SGDX_EINVAL, "sgdx_create: null argument");
     *out = nullptr;
     const uint32_t S = cfg->num_samples, L = cfg->barcode_len;
@@ -549,6 +563,7 @@ extern "C" int sgdx_create(const sgdx_config *cfg, const uint8_t *barcodes, sgdx
     }
     *out = h;
     return SGDX_OK;
+    });
 }
 
 extern "C" void sgdx_destroy(sgdx_handle *h) {
@@ -589,25 +604,33 @@ extern "C" void sgdx_destroy(sgdx_handle *h) {
     cudaFree(h->d_hop_lut2);
     cudaFree(h->d_hop_fwd);
     cudaFree(h->d_hop_rev);
+    cudaFree(h->d_hop_list);
+    cudaFree(h->d_hop_stat);
     cudaFree(h->d_counters);
     post_destroy(h);
     delete h;
 }
 
 extern "C" int sgdx_get_config(const sgdx_handle *h, sgdx_config *effective) {
+    return sgdx::guarded("sgdx_get_config", [&]() -> int {
     if (!h || !effective) return fail(SGDX_EINVAL, "sgdx_get_config: null argument");
     *effective = h->cfg;
     return SGDX_OK;
+    });
 }
 
 extern "C" int sgdx_alloc_host(size_t bytes, void **out) {
+    return sgdx::guarded("sgdx_alloc_host", [&]() -> int {
     if (!out) return fail(SGDX_EINVAL, "sgdx_alloc_host: null out");
     CU(cudaMallocHost(out, bytes ? bytes : 1));
     return SGDX_OK;
+    });
 }
 extern "C" int sgdx_free_host(void *p) {
+    return sgdx::guarded("sgdx_free_host", [&]() -> int {
     if (p) CU(cudaFreeHost(p));
     return SGDX_OK;
+    });
 }
 
 static int check_slot(sgdx_handle *h, uint32_t slot) {
@@ -655,23 +678,28 @@ static int run_kernels(sgdx_handle *h, Slot &s, const uint8_t *d_ascii, const ui
 
 extern "C" int sgdx_match_device(sgdx_handle *h, uint32_t slot, const uint8_t *d_ascii, uint64_t n, uint16_t *d_idx,
                                  uint8_t *d_dist) {
+    return sgdx::guarded("sgdx_match_device", [&]() -> int {
     if (int rc = check_slot(h, slot)) return rc;
     if (n && (!d_ascii || !d_idx)) return fail(SGDX_EINVAL, "sgdx_match_device: null buffer");
     if (n >> 40) return fail(SGDX_EINVAL, "batch too large");
     CU(cudaSetDevice(h->cfg.device));
     return run_kernels(h, h->slots[slot], d_ascii, nullptr, n, d_idx, d_dist);
+    });
 }
 
 extern "C" int sgdx_match_packed_device(sgdx_handle *h, uint32_t slot, const sgdx_read *d_packed, uint64_t n,
                                         uint16_t *d_idx, uint8_t *d_dist) {
+    return sgdx::guarded("sgdx_match_packed_device", [&]() -> int {
     if (int rc = check_slot(h, slot)) return rc;
     if (n && (!d_packed || !d_idx)) return fail(SGDX_EINVAL, "sgdx_match_packed_device: null buffer");
     if (reinterpret_cast<uintptr_t>(d_packed) & 15u) return fail(SGDX_EINVAL, "packed records must be 16-byte aligned");
     CU(cudaSetDevice(h->cfg.device));
     return run_kernels(h, h->slots[slot], nullptr, reinterpret_cast<const uint4 *>(d_packed), n, d_idx, d_dist);
+    });
 }
 
 extern "C" int sgdx_pack_device(sgdx_handle *h, uint32_t slot, const uint8_t *d_ascii, uint64_t n, sgdx_read *d_packed) {
+    return sgdx::guarded("sgdx_pack_device", [&]() -> int {
     if (int rc = check_slot(h, slot)) return rc;
     if (n && (!d_ascii || !d_packed)) return fail(SGDX_EINVAL, "sgdx_pack_device: null buffer");
     if (reinterpret_cast<uintptr_t>(d_packed) & 15u) return fail(SGDX_EINVAL, "packed records must be 16-byte aligned");
@@ -680,6 +708,7 @@ extern "C" int sgdx_pack_device(sgdx_handle *h, uint32_t slot, const uint8_t *d_
     CU(launch_pack(d_ascii, n, h->cfg.barcode_len, reinterpret_cast<uint4 *>(d_packed), h->sms, h->slots[slot].stream));
     if (n) h->launches.fetch_add(1);
     return SGDX_OK;
+    });
 }
 
 static int ensure_capacity(Slot &s, uint64_t n, uint32_t L) {
@@ -702,6 +731,7 @@ static int ensure_capacity(Slot &s, uint64_t n, uint32_t L) {
 
 extern "C" int sgdx_match_batch(sgdx_handle *h, uint32_t slot, const uint8_t *ascii, uint64_t n, uint16_t *out_idx,
                                 uint8_t *out_dist) {
+    return sgdx::guarded("sgdx_match_batch", [&]() -> int {
     if (int rc = check_slot(h, slot)) return rc;
     if (n && (!ascii || !out_idx)) return fail(SGDX_EINVAL, "sgdx_match_batch: null buffer");
     if (n >> 34) return fail(SGDX_EINVAL, "batch of %llu reads too large; split it", (unsigned long long)n);
@@ -716,6 +746,7 @@ extern "C" int sgdx_match_batch(sgdx_handle *h, uint32_t slot, const uint8_t *as
         if (out_dist) CU(cudaMemcpyAsync(out_dist, s.d_dist, n, cudaMemcpyDeviceToHost, s.stream));
     }
     return SGDX_OK;
+    });
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -770,15 +801,18 @@ static int run_compact(sgdx_handle *h, Slot &s, const uint64_t *d_records, uint6
 
 extern "C" int sgdx_match_compact_device(sgdx_handle *h, uint32_t slot, const uint64_t *d_records, uint64_t n,
                                          uint16_t *d_idx, uint8_t *d_dist) {
+    return sgdx::guarded("sgdx_match_compact_device", [&]() -> int {
     if (int rc = check_slot(h, slot)) return rc;
     if (n && (!d_records || !d_idx)) return fail(SGDX_EINVAL, "sgdx_match_compact_device: null buffer");
     if (n >> 40) return fail(SGDX_EINVAL, "batch too large");
     CU(cudaSetDevice(h->cfg.device));
     return run_compact(h, h->slots[slot], d_records, n, d_idx, d_dist);
+    });
 }
 
 extern "C" int sgdx_pack_compact_device(sgdx_handle *h, uint32_t slot, const uint8_t *d_ascii, uint64_t n,
                                         uint64_t *d_records) {
+    return sgdx::guarded("sgdx_pack_compact_device", [&]() -> int {
     if (int rc = check_slot(h, slot)) return rc;
     if (n && (!d_ascii || !d_records)) return fail(SGDX_EINVAL, "sgdx_pack_compact_device: null buffer");
     if (h->cfg.barcode_len > kCompactMaxLen)
@@ -788,10 +822,12 @@ extern "C" int sgdx_pack_compact_device(sgdx_handle *h, uint32_t slot, const uin
     CU(launch_pack_compact(d_ascii, n, h->cfg.barcode_len, d_records, h->sms, h->slots[slot].stream));
     if (n) h->launches.fetch_add(1);
     return SGDX_OK;
+    });
 }
 
 extern "C" int sgdx_match_compact_batch(sgdx_handle *h, uint32_t slot, const uint64_t *records, uint64_t n,
                                         uint16_t *out_idx, uint8_t *out_dist) {
+    return sgdx::guarded("sgdx_match_compact_batch", [&]() -> int {
     if (int rc = check_slot(h, slot)) return rc;
     if (n && (!records || !out_idx)) return fail(SGDX_EINVAL, "sgdx_match_compact_batch: null buffer");
     if (n >> 34) return fail(SGDX_EINVAL, "batch of %llu reads too large; split it", (unsigned long long)n);
@@ -806,11 +842,13 @@ extern "C" int sgdx_match_compact_batch(sgdx_handle *h, uint32_t slot, const uin
         if (out_dist) CU(cudaMemcpyAsync(out_dist, s.d_dist, n, cudaMemcpyDeviceToHost, s.stream));
     }
     return SGDX_OK;
+    });
 }
 
 // sgdx_match_batch for a host buffer of 16-byte sgdx_read records (any barcode_len <= 32; sgdx_pack_host writes them)
 extern "C" int sgdx_match_packed_batch(sgdx_handle *h, uint32_t slot, const sgdx_read *records, uint64_t n,
                                        uint16_t *out_idx, uint8_t *out_dist) {
+    return sgdx::guarded("sgdx_match_packed_batch", [&]() -> int {
     if (int rc = check_slot(h, slot)) return rc;
     if (n && (!records || !out_idx)) return fail(SGDX_EINVAL, "sgdx_match_packed_batch: null buffer");
     if (n >> 34) return fail(SGDX_EINVAL, "batch of %llu reads too large; split it", (unsigned long long)n);
@@ -825,9 +863,11 @@ extern "C" int sgdx_match_packed_batch(sgdx_handle *h, uint32_t slot, const sgdx
         if (out_dist) CU(cudaMemcpyAsync(out_dist, s.d_dist, n, cudaMemcpyDeviceToHost, s.stream));
     }
     return SGDX_OK;
+    });
 }
 
 extern "C" int sgdx_sync(sgdx_handle *h, uint32_t slot, float *device_ms) {
+    return sgdx::guarded("sgdx_sync", [&]() -> int {
     if (int rc = check_slot(h, slot)) return rc;
     Slot &s = h->slots[slot];
     CU(cudaStreamSynchronize(s.stream));
@@ -836,15 +876,18 @@ extern "C" int sgdx_sync(sgdx_handle *h, uint32_t slot, float *device_ms) {
         if (s.timed) CU(cudaEventElapsedTime(device_ms, s.e0, s.e1));
     }
     return post_on_sync(h, s);
+    });
 }
 
 extern "C" int sgdx_set_stream(sgdx_handle *h, uint32_t slot, void *stream) {
+    return sgdx::guarded("sgdx_set_stream", [&]() -> int {
     if (int rc = check_slot(h, slot)) return rc;
     Slot &s = h->slots[slot];
     CU(cudaStreamSynchronize(s.stream));
     s.stream = stream ? static_cast<cudaStream_t>(stream) : s.own;
     s.timed = false;
     return SGDX_OK;
+    });
 }
 
 extern "C" const char *sgdx_kernel_name(const sgdx_handle *h) {
@@ -877,16 +920,58 @@ extern "C" uint32_t sgdx_path_flags(const sgdx_handle *h) {
 
 extern "C" uint64_t sgdx_launch_count(const sgdx_handle *h) { return h ? h->launches.load() : 0; }
 
-static int fetch_hop(sgdx_handle *h, std::vector<unsigned long long> &fwd, std::vector<unsigned long long> &rev) {
-    size_t cells = (size_t)h->base.u1 * h->base.u2;
-    fwd.resize(cells);
-    rev.resize(cells);
-    CU(cudaMemcpy(fwd.data(), h->d_hop_fwd, cells * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-    CU(cudaMemcpy(rev.data(), h->d_hop_rev, cells * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-    return SGDX_OK;
+// The hop counters are two dense u1 x u2 matrices (38 MB at 1536 unique dual indexes, 1 GB at the sample limit) of
+// which real runs touch a few thousand cells: the non-zero ones are compacted on the device and only those cross PCIe.
+// entry = {cell (+ cells for the reversed-orientation matrix), count}; stat[0] = entries, stat[1] = sum of the counts
+__global__ void __launch_bounds__(256) sgdx_hop_compact(const unsigned long long *__restrict__ fwd,
+                                                        const unsigned long long *__restrict__ rev, uint64_t cells,
+                                                        ulonglong2 *__restrict__ out, uint64_t cap, unsigned long long *stat) {
+    unsigned long long local = 0ull;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < 2 * cells; i += (uint64_t)gridDim.x * blockDim.x) {
+        const unsigned long long c = i < cells ? fwd[i] : rev[i - cells];
+        if (c) {
+            local += c;
+            const unsigned long long at = atomicAdd(stat, 1ull);
+            if (at < cap) out[at] = make_ulonglong2(i, c);
+        }
+    }
+    for (int d = 16; d; d >>= 1) local += __shfl_xor_sync(0xFFFFFFFFu, local, d);
+    if ((threadIdx.x & 31u) == 0u && local) atomicAdd(stat + 1, local);
+}
+
+// want_list = false: only the sum of the counts.  Device idle (callers synchronise first).
+static int fetch_hop(sgdx_handle *h, bool want_list, std::vector<ulonglong2> &list, uint64_t *hop_reads) {
+    const uint64_t cells = (uint64_t)h->base.u1 * h->base.u2;
+    std::lock_guard<std::mutex> lk(h->hop_mu);
+    if (!h->d_hop_stat) CU(cudaMalloc(&h->d_hop_stat, 2 * sizeof(unsigned long long)));
+    if (want_list && !h->d_hop_list) {
+        h->hop_list_cap = 1u << 16;
+        CU(cudaMalloc(&h->d_hop_list, h->hop_list_cap * sizeof(ulonglong2)));
+    }
+    const uint32_t grid = (uint32_t)std::min<uint64_t>((2 * cells + 255) / 256, (uint64_t)h->sms * 8u);
+    for (int attempt = 0; attempt < 2; attempt++) {
+        unsigned long long st[2] = {0ull, 0ull};
+        CU(cudaMemset(h->d_hop_stat, 0, sizeof st));
+        sgdx_hop_compact<<<grid, 256>>>(h->d_hop_fwd, h->d_hop_rev, cells, h->d_hop_list, want_list ? h->hop_list_cap : 0, h->d_hop_stat);
+        CU(cudaGetLastError());
+        CU(cudaMemcpy(st, h->d_hop_stat, sizeof st, cudaMemcpyDeviceToHost));
+        if (hop_reads) *hop_reads = st[1];
+        if (!want_list) return SGDX_OK;
+        if (st[0] <= h->hop_list_cap) {
+            list.resize(st[0]);
+            if (st[0]) CU(cudaMemcpy(list.data(), h->d_hop_list, st[0] * sizeof(ulonglong2), cudaMemcpyDeviceToHost));
+            return SGDX_OK;
+        }
+        cudaFree(h->d_hop_list);  // more non-zero cells than the list holds: once more with room for all of them
+        h->d_hop_list = nullptr;
+        h->hop_list_cap = st[0] + st[0] / 8;
+        CU(cudaMalloc(&h->d_hop_list, h->hop_list_cap * sizeof(ulonglong2)));
+    }
+    return fail(SGDX_ECUDA, "hop counters changed while they were read");
 }
 
 extern "C" int sgdx_counters(sgdx_handle *h, uint64_t *per_sample, sgdx_totals *totals) {
+    return sgdx::guarded("sgdx_counters", [&]() -> int {
     if (!h) return fail(SGDX_EINVAL, "null handle");
     CU(cudaSetDevice(h->cfg.device));
     CU(cudaDeviceSynchronize());
@@ -906,15 +991,16 @@ extern "C" int sgdx_counters(sgdx_handle *h, uint64_t *per_sample, sgdx_totals *
         (b < S ? t.matched : t.undetermined) += total;
     }
     if (h->base.hop_on) {
-        std::vector<unsigned long long> fwd, rev;
-        if (int rc = fetch_hop(h, fwd, rev)) return rc;
-        for (size_t i = 0; i < fwd.size(); i++) t.hop_reads += fwd[i] + rev[i];
+        std::vector<ulonglong2> none;
+        if (int rc = fetch_hop(h, false, none, &t.hop_reads)) return rc;
     }
     if (totals) *totals = t;
     return SGDX_OK;
+    });
 }
 
 extern "C" int sgdx_reset_counters(sgdx_handle *h) {
+    return sgdx::guarded("sgdx_reset_counters", [&]() -> int {
     if (!h) return fail(SGDX_EINVAL, "null handle");
     CU(cudaSetDevice(h->cfg.device));
     CU(cudaDeviceSynchronize());
@@ -927,6 +1013,7 @@ extern "C" int sgdx_reset_counters(sgdx_handle *h) {
     if (int rc = post_reset(h)) return rc;
     CU(cudaDeviceSynchronize());  // the memsets are on the default stream, batches on non-blocking ones
     return SGDX_OK;
+    });
 }
 
 // dense (index1 id, index2 id) cells -> {observed barcode: count}; a barcode that satisfies the forward
@@ -935,25 +1022,29 @@ static int hop_entries(sgdx_handle *h, std::map<std::string, uint64_t> &out) {
     if (!h->base.hop_on) return SGDX_OK;
     CU(cudaSetDevice(h->cfg.device));
     CU(cudaDeviceSynchronize());
-    std::vector<unsigned long long> fwd, rev;
-    if (int rc = fetch_hop(h, fwd, rev)) return rc;
-    const uint32_t u2 = h->base.u2;
-    for (size_t i = 0; i < fwd.size(); i++) {
-        if (fwd[i]) out[h->keys1[i / u2] + h->keys2[i % u2]] += fwd[i];
-        if (rev[i]) out[h->keys2[i % u2] + h->keys1[i / u2]] += rev[i];
+    std::vector<ulonglong2> list;
+    if (int rc = fetch_hop(h, true, list, nullptr)) return rc;
+    const uint64_t u2 = h->base.u2, cells = (uint64_t)h->base.u1 * u2;
+    for (const ulonglong2 &e : list) {
+        const uint64_t i = e.x < cells ? e.x : e.x - cells;
+        if (e.x < cells) out[h->keys1[i / u2] + h->keys2[i % u2]] += e.y;
+        else out[h->keys2[i % u2] + h->keys1[i / u2]] += e.y;
     }
     return SGDX_OK;
 }
 
 extern "C" int sgdx_hop_count(sgdx_handle *h, uint64_t *n_keys) {
+    return sgdx::guarded("sgdx_hop_count", [&]() -> int {
     if (!h || !n_keys) return fail(SGDX_EINVAL, "sgdx_hop_count: null argument");
     std::map<std::string, uint64_t> m;
     if (int rc = hop_entries(h, m)) return rc;
     *n_keys = m.size();
     return SGDX_OK;
+    });
 }
 
 extern "C" int sgdx_hop_export(sgdx_handle *h, uint8_t *keys, uint64_t *counts, uint64_t cap, uint64_t *n_written) {
+    return sgdx::guarded("sgdx_hop_export", [&]() -> int {
     if (!h || !n_written) return fail(SGDX_EINVAL, "sgdx_hop_export: null argument");
     std::map<std::string, uint64_t> m;
     if (int rc = hop_entries(h, m)) return rc;
@@ -967,9 +1058,11 @@ extern "C" int sgdx_hop_export(sgdx_handle *h, uint8_t *keys, uint64_t *counts, 
     }
     *n_written = i;
     return SGDX_OK;
+    });
 }
 
 extern "C" int sgdx_measure_int_peak(int device, double *popc_per_s, double *lop3_per_s) {
+    return sgdx::guarded("sgdx_measure_int_peak", [&]() -> int {
     if (!popc_per_s || !lop3_per_s) return fail(SGDX_EINVAL, "sgdx_measure_int_peak: null argument");
     int ndev = 0;
     cudaError_t ce = cudaGetDeviceCount(&ndev);
@@ -979,6 +1072,7 @@ extern "C" int sgdx_measure_int_peak(int device, double *popc_per_s, double *lop
     CU(cudaGetDeviceProperties(&prop, device));
     CU(measure_int_peak(prop.multiProcessorCount, popc_per_s, lop3_per_s));
     return SGDX_OK;
+    });
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1006,6 +1100,7 @@ struct sgdx_batcher {
 };
 
 extern "C" int sgdx_batcher_create(sgdx_handle *h, uint64_t batch_reads, sgdx_batcher **out) {
+    return sgdx::guarded("sgdx_batcher_create", [&]() -> int {
     if (!h || !out || batch_reads == 0) return fail(SGDX_EINVAL, "sgdx_batcher_create: bad argument");
     sgdx_batcher *b = new sgdx_batcher();
     b->h = h;
@@ -1023,15 +1118,18 @@ extern "C" int sgdx_batcher_create(sgdx_handle *h, uint64_t batch_reads, sgdx_ba
     }
     *out = b;
     return SGDX_OK;
+    });
 }
 
 extern "C" int sgdx_batcher_set_compact(sgdx_batcher *b, int on) {
+    return sgdx::guarded("sgdx_batcher_set_compact", [&]() -> int {
     if (!b) return fail(SGDX_EINVAL, "null batcher");
     if (b->fill || !b->inflight.empty()) return fail(SGDX_ESTATE, "sgdx_batcher_set_compact: batches are in flight");
     if (on && b->L > kCompactMaxLen)
         return fail(SGDX_EINVAL, "compact records hold at most %u bases, barcode_len is %u", kCompactMaxLen, b->L);
     b->compact = on != 0;
     return SGDX_OK;
+    });
 }
 
 static void release_result(sgdx_batcher *b, Batch &r) {
@@ -1055,6 +1153,8 @@ extern "C" void sgdx_batcher_destroy(sgdx_batcher *b) {
 
 static int submit(sgdx_batcher *b) {
     if (b->fill == 0) return SGDX_OK;
+    if (b->inflight.size() >= 2 * b->in.size())  // every waiting batch holds pinned result buffers
+        return fail(SGDX_ESTATE, "sgdx_batcher: %zu batches wait for sgdx_batcher_next", b->inflight.size());
     Batch r;
     if (!b->free_results.empty()) {
         r = b->free_results.back();
@@ -1090,8 +1190,19 @@ static int submit(sgdx_batcher *b) {
 }
 
 extern "C" int sgdx_batcher_push(sgdx_batcher *b, const uint8_t *ascii, uint64_t n) {
+    return sgdx::guarded("sgdx_batcher_push", [&]() -> int {
+    return sgdx_batcher_push_n(b, ascii, n, nullptr);
+    });
+}
+
+extern "C" int sgdx_batcher_push_n(sgdx_batcher *b, const uint8_t *ascii, uint64_t n, uint64_t *consumed) {
+    return sgdx::guarded("sgdx_batcher_push_n", [&]() -> int {
+    if (consumed) *consumed = 0;
     if (!b || (n && !ascii)) return fail(SGDX_EINVAL, "sgdx_batcher_push: null argument");
     while (n) {
+        // a full buffer that could not be submitted earlier (failed launch, results not taken) goes first
+        if (b->fill == b->batch_reads)
+            if (int rc = submit(b)) return rc;
         uint64_t take = std::min(n, b->batch_reads - b->fill);
         if (b->compact) {  // the copy into the pinned buffer is the packing pass
             if (int rc = sgdx_pack_compact_host(ascii, take, b->L, reinterpret_cast<uint64_t *>(b->in[b->cur]) + b->fill, 1))
@@ -1102,18 +1213,23 @@ extern "C" int sgdx_batcher_push(sgdx_batcher *b, const uint8_t *ascii, uint64_t
         b->fill += take;
         ascii += take * b->L;
         n -= take;
+        if (consumed) *consumed += take;
         if (b->fill == b->batch_reads)
             if (int rc = submit(b)) return rc;
     }
     return SGDX_OK;
+    });
 }
 
 extern "C" int sgdx_batcher_flush(sgdx_batcher *b) {
+    return sgdx::guarded("sgdx_batcher_flush", [&]() -> int {
     if (!b) return fail(SGDX_EINVAL, "null batcher");
     return submit(b);
+    });
 }
 
 extern "C" int sgdx_batcher_next(sgdx_batcher *b, const uint16_t **idx, const uint8_t **dist, uint64_t *n) {
+    return sgdx::guarded("sgdx_batcher_next", [&]() -> int {
     if (!b || !idx || !dist || !n) return fail(SGDX_EINVAL, "sgdx_batcher_next: null argument");
     release_result(b, b->handed);
     *idx = nullptr;
@@ -1132,4 +1248,5 @@ extern "C" int sgdx_batcher_next(sgdx_batcher *b, const uint16_t **idx, const ui
     *dist = r.dist;
     *n = r.n;
     return SGDX_OK;
+    });
 }

@@ -94,6 +94,10 @@ struct sgdx_handle {
     sgdx::HopSlot *d_hash1 = nullptr, *d_hash2 = nullptr;
     uint16_t *d_hop_lut1 = nullptr, *d_hop_lut2 = nullptr;
     unsigned long long *d_hop_fwd = nullptr, *d_hop_rev = nullptr;
+    ulonglong2 *d_hop_list = nullptr;            // scratch of the hop export: the non-zero cells, compacted on the device
+    unsigned long long *d_hop_stat = nullptr;
+    uint64_t hop_list_cap = 0;
+    std::mutex hop_mu;
     unsigned long long *d_counters = nullptr;
     std::vector<std::string> keys1, keys2;  // distinct index1 / index2 halves (ASCII), id order
     std::vector<sgdx::Slot> slots;

@@ -16,6 +16,7 @@
 #include <immintrin.h>
 #endif
 
+#include "sgdx_guard.h"
 #include "../../include/sgdx.h"
 
 namespace sgdx {
@@ -23,6 +24,15 @@ int fail(int code, const char *fmt, ...);  // sgdx_api.cu: sets the thread's sgd
 }
 
 namespace {
+
+// test hook (latched at first use): run the scalar packer on a CPU that has AVX2; ignored with -DSGDX_NO_TEST_HOOKS
+inline bool no_avx2_hook() {
+#ifdef SGDX_NO_TEST_HOOKS
+    return false;
+#else
+    return getenv("SGDX_PACK_NO_AVX2") != nullptr;
+#endif
+}
 
 constexpr uint32_t kField = 21;
 
@@ -129,7 +139,7 @@ __attribute__((target("avx2"))) void planes_range_avx2(const uint8_t *ascii, uin
 
 void planes_range(const uint8_t *ascii, uint64_t begin, uint64_t end, uint32_t L, uint64_t total, sgdx_read *out) {
 #if defined(__x86_64__)
-    static const bool have_avx2 = __builtin_cpu_supports("avx2") && !getenv("SGDX_PACK_NO_AVX2");
+    static const bool have_avx2 = __builtin_cpu_supports("avx2") && !no_avx2_hook();
     if (have_avx2) return planes_range_avx2(ascii, begin, end, L, total, out);
 #endif
     (void)total;
@@ -145,14 +155,20 @@ void run_threads(Fn fn, const uint8_t *ascii, uint64_t n, uint32_t L, Out *out, 
     std::vector<std::thread> pool;
     pool.reserve(nt - 1);
     const uint64_t per = (n + nt - 1) / nt;
-    for (uint64_t t = 1; t < nt; t++) pool.emplace_back(fn, ascii, std::min(n, t * per), std::min(n, (t + 1) * per), L, n, out);
+    uint64_t started = 1;  // ranges [1, started) run on their own threads
+    try {
+        for (; started < nt; started++)
+            pool.emplace_back(fn, ascii, std::min(n, started * per), std::min(n, (started + 1) * per), L, n, out);
+    } catch (...) {  // thread limit reached: this thread takes what is left
+    }
     fn(ascii, 0, std::min(n, per), L, n, out);
+    for (uint64_t t = started; t < nt; t++) fn(ascii, std::min(n, t * per), std::min(n, (t + 1) * per), L, n, out);
     for (auto &th : pool) th.join();
 }
 
 void pack_range(const uint8_t *ascii, uint64_t begin, uint64_t end, uint32_t L, uint64_t total, uint64_t *out) {
 #if defined(__x86_64__)
-    static const bool have_avx2 = __builtin_cpu_supports("avx2") && !getenv("SGDX_PACK_NO_AVX2");
+    static const bool have_avx2 = __builtin_cpu_supports("avx2") && !no_avx2_hook();
     if (have_avx2) return pack_range_avx2(ascii, begin, end, L, total, out);
 #endif
     (void)total;
@@ -163,17 +179,21 @@ void pack_range(const uint8_t *ascii, uint64_t begin, uint64_t end, uint32_t L, 
 
 extern "C" int sgdx_pack_compact_host(const uint8_t *ascii, uint64_t n, uint32_t barcode_len, uint64_t *out,
                                       uint32_t threads) {
+    return sgdx::guarded("sgdx_pack_compact_host", [&]() -> int {
     if (barcode_len < 1 || barcode_len > SGDX_COMPACT_MAX_LEN)
         return sgdx::fail(SGDX_EINVAL, "compact records hold 1..%u bases, barcode_len is %u", SGDX_COMPACT_MAX_LEN, barcode_len);
     if (n && (!ascii || !out)) return sgdx::fail(SGDX_EINVAL, "sgdx_pack_compact_host: null buffer");
     run_threads(pack_range, ascii, n, barcode_len, out, threads);
     return SGDX_OK;
+    });
 }
 
 extern "C" int sgdx_pack_host(const uint8_t *ascii, uint64_t n, uint32_t barcode_len, sgdx_read *out, uint32_t threads) {
+    return sgdx::guarded("sgdx_pack_host", [&]() -> int {
     if (barcode_len < 1 || barcode_len > SGDX_MAX_PACKED_LEN)
         return sgdx::fail(SGDX_EINVAL, "barcode_len %u outside 1..%u", barcode_len, SGDX_MAX_PACKED_LEN);
     if (n && (!ascii || !out)) return sgdx::fail(SGDX_EINVAL, "sgdx_pack_host: null buffer");
     run_threads(planes_range, ascii, n, barcode_len, out, threads);
     return SGDX_OK;
+    });
 }

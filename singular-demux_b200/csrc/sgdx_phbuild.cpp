@@ -2,6 +2,7 @@
 // expected barcode.  Each key's verdict is computed here exactly as the kernels compute it per read (score +
 // apply_rules of sgdx_device.cuh for a read without invalid positions): best / second-best (distance << 16 | sample)
 // keys over the whole table, then matcher.rs:295-299 or the PreCompute visibility rule.
+#include "sgdx_guard.h"
 #include "sgdx_phbuild.h"
 
 #include <algorithm>
@@ -346,12 +347,16 @@ int probe(const sgdx_config *cfg, const uint8_t *barcodes, const uint64_t *compa
 
 extern "C" int sgdx_ph_probe_host(const sgdx_config *cfg, const uint8_t *barcodes, const uint64_t *records, uint64_t n,
                                   uint16_t *out_idx, uint8_t *out_dist, uint32_t *info) {
+    return sgdx::guarded("sgdx_ph_probe_host", [&]() -> int {
     return probe(cfg, barcodes, records, nullptr, n, out_idx, out_dist, info);
+    });
 }
 
 extern "C" int sgdx_ph_probe_host_wide(const sgdx_config *cfg, const uint8_t *barcodes, const sgdx_read *records, uint64_t n,
                                        uint16_t *out_idx, uint8_t *out_dist, uint32_t *info) {
+    return sgdx::guarded("sgdx_ph_probe_host_wide", [&]() -> int {
     if (n && !records) return SGDX_EINVAL;
     static const sgdx_read none{};
     return probe(cfg, barcodes, nullptr, records ? records : &none, n, out_idx, out_dist, info);
+    });
 }

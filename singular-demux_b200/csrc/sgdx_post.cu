@@ -14,6 +14,7 @@
 #include <algorithm>
 #include <cstring>
 
+#include "sgdx_guard.h"
 #include "sgdx_handle.h"
 #include "sgdx_seed_search.cuh"  // rd_of_compact
 
@@ -1227,6 +1228,7 @@ void post_destroy(sgdx_handle *h) {
 // C ABI: unmatched
 // ------------------------------------------------------------------------------------------------
 extern "C" int sgdx_unmatched_enable(sgdx_handle *h, uint64_t max_map_size, uint64_t downsize_to) {
+    return sgdx::guarded("sgdx_unmatched_enable", [&]() -> int {
     if (!h) return fail(SGDX_EINVAL, "null handle");
     if (h->unm.on) return fail(SGDX_ESTATE, "unmatched collection is already enabled");
     if (h->cfg.barcode_len > SGDX_MAX_PACKED_LEN)
@@ -1259,6 +1261,7 @@ extern "C" int sgdx_unmatched_enable(sgdx_handle *h, uint64_t max_map_size, uint
     CU(cudaDeviceSynchronize());
     u.on = true;
     return SGDX_OK;
+    });
 }
 
 #define UNM_ENTER(h)                                                                       \
@@ -1269,6 +1272,7 @@ extern "C" int sgdx_unmatched_enable(sgdx_handle *h, uint64_t max_map_size, uint
     CU(cudaDeviceSynchronize())
 
 extern "C" int sgdx_unmatched_info_get(sgdx_handle *h, sgdx_unmatched_info *out) {
+    return sgdx::guarded("sgdx_unmatched_info_get", [&]() -> int {
     if (!out) return fail(SGDX_EINVAL, "sgdx_unmatched_info_get: null out");
     UNM_ENTER(h);
     if (int rc = unm_drain_odd(h)) return rc;
@@ -1279,6 +1283,7 @@ extern "C" int sgdx_unmatched_info_get(sgdx_handle *h, sgdx_unmatched_info *out)
     out->dropped_reads = st[2];
     out->downsizes = h->unm.downsizes;
     return SGDX_OK;
+    });
 }
 
 static int unm_write(sgdx_handle *h, const std::vector<UnmEntry> &v, uint8_t *keys, uint64_t *counts, uint64_t cap,
@@ -1294,24 +1299,30 @@ static int unm_write(sgdx_handle *h, const std::vector<UnmEntry> &v, uint8_t *ke
 }
 
 extern "C" int sgdx_unmatched_export(sgdx_handle *h, uint8_t *keys, uint64_t *counts, uint64_t cap, uint64_t *n_written) {
+    return sgdx::guarded("sgdx_unmatched_export", [&]() -> int {
     if (!n_written || (cap && (!keys || !counts))) return fail(SGDX_EINVAL, "sgdx_unmatched_export: null argument");
     UNM_ENTER(h);
     std::vector<UnmEntry> v;
     if (int rc = unm_top_entries(h, ~0ull, v)) return rc;
     return unm_write(h, v, keys, counts, cap, n_written);
+    });
 }
 
 extern "C" int sgdx_unmatched_top(sgdx_handle *h, uint64_t n, uint8_t *keys, uint64_t *counts, uint64_t *n_written) {
+    return sgdx::guarded("sgdx_unmatched_top", [&]() -> int {
     if (!n_written || (n && (!keys || !counts))) return fail(SGDX_EINVAL, "sgdx_unmatched_top: null argument");
     UNM_ENTER(h);
     std::vector<UnmEntry> v;
     if (int rc = unm_top_entries(h, n, v)) return rc;
     return unm_write(h, v, keys, counts, n, n_written);
+    });
 }
 
 extern "C" int sgdx_unmatched_downsize(sgdx_handle *h) {
+    return sgdx::guarded("sgdx_unmatched_downsize", [&]() -> int {
     UNM_ENTER(h);
     return unm_downsize_locked(h);
+    });
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1357,6 +1368,7 @@ static int check_slot_post(sgdx_handle *h, uint32_t slot) {
 extern "C" int sgdx_extract_device(sgdx_handle *h, uint32_t slot, uint32_t num_sources, const uint8_t *const *d_bases,
                                    const uint32_t *strides, const sgdx_segment *segs, uint32_t nsegs, uint64_t n,
                                    uint8_t *d_out) {
+    return sgdx::guarded("sgdx_extract_device", [&]() -> int {
     if (int rc = check_slot_post(h, slot)) return rc;
     ExtractParams p;
     if (int rc = fill_extract(h, num_sources, d_bases, strides, segs, nsegs, &p)) return rc;
@@ -1370,12 +1382,14 @@ extern "C" int sgdx_extract_device(sgdx_handle *h, uint32_t slot, uint32_t num_s
     CU(cudaGetLastError());
     h->launches.fetch_add(1);
     return SGDX_OK;
+    });
 }
 
 extern "C" int sgdx_match_segments_device(sgdx_handle *h, uint32_t slot, uint32_t num_sources,
                                           const uint8_t *const *d_bases, const uint32_t *strides,
                                           const sgdx_segment *segs, uint32_t nsegs, uint64_t n, uint16_t *d_idx,
                                           uint8_t *d_dist) {
+    return sgdx::guarded("sgdx_match_segments_device", [&]() -> int {
     if (int rc = check_slot_post(h, slot)) return rc;
     Slot &s = h->slots[slot];
     CU(cudaSetDevice(h->cfg.device));
@@ -1390,6 +1404,7 @@ extern "C" int sgdx_match_segments_device(sgdx_handle *h, uint32_t slot, uint32_
     }
     if (int rc = sgdx_extract_device(h, slot, num_sources, d_bases, strides, segs, nsegs, n, s.d_extract)) return rc;
     return sgdx_match_device(h, slot, s.d_extract, n, d_idx, d_dist);
+    });
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1411,6 +1426,7 @@ static int ensure_qual_counters(sgdx_handle *h) {
 extern "C" int sgdx_qual_counts_device(sgdx_handle *h, uint32_t slot, const uint8_t *d_quals, uint64_t n,
                                        uint32_t stride, const uint32_t *d_lens, const sgdx_segment *segs,
                                        uint32_t nsegs, const uint16_t *d_idx) {
+    return sgdx::guarded("sgdx_qual_counts_device", [&]() -> int {
     if (int rc = check_slot_post(h, slot)) return rc;
     if (!segs || nsegs < 1 || nsegs > SGDX_MAX_SEGMENTS) return fail(SGDX_EINVAL, "sgdx_qual_counts_device: 1..%u segments", SGDX_MAX_SEGMENTS);
     if (stride < 1 || stride > 3072u) return fail(SGDX_EINVAL, "stride %u outside 1..3072", stride);
@@ -1515,9 +1531,11 @@ extern "C" int sgdx_qual_counts_device(sgdx_handle *h, uint32_t slot, const uint
     CU(cudaGetLastError());
     h->launches.fetch_add(1);
     return SGDX_OK;
+    });
 }
 
 extern "C" int sgdx_base_qual_counters(sgdx_handle *h, sgdx_base_qual *per_sample, uint64_t *short_reads) {
+    return sgdx::guarded("sgdx_base_qual_counters", [&]() -> int {
     if (!h || !per_sample) return fail(SGDX_EINVAL, "sgdx_base_qual_counters: null argument");
     CU(cudaSetDevice(h->cfg.device));
     CU(cudaDeviceSynchronize());
@@ -1533,6 +1551,7 @@ extern "C" int sgdx_base_qual_counters(sgdx_handle *h, sgdx_base_qual *per_sampl
     }
     if (short_reads) *short_reads = raw.back();
     return SGDX_OK;
+    });
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1540,6 +1559,7 @@ extern "C" int sgdx_base_qual_counters(sgdx_handle *h, sgdx_base_qual *per_sampl
 // ------------------------------------------------------------------------------------------------
 extern "C" int sgdx_route_device(sgdx_handle *h, uint32_t slot, const uint16_t *d_idx, uint64_t n, uint32_t *d_order,
                                  uint64_t *d_offsets) {
+    return sgdx::guarded("sgdx_route_device", [&]() -> int {
     if (int rc = check_slot_post(h, slot)) return rc;
     if (!d_offsets || (n && (!d_idx || !d_order))) return fail(SGDX_EINVAL, "sgdx_route_device: null buffer");
     if (n >> 32) return fail(SGDX_EINVAL, "sgdx_route_device: %llu reads, at most 2^32 - 1 per call", (unsigned long long)n);
@@ -1627,6 +1647,7 @@ extern "C" int sgdx_route_device(sgdx_handle *h, uint32_t slot, const uint16_t *
     }
     h->launches.fetch_add(n ? 4 : 3);
     return SGDX_OK;
+    });
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1634,6 +1655,7 @@ extern "C" int sgdx_route_device(sgdx_handle *h, uint32_t slot, const uint16_t *
 // ------------------------------------------------------------------------------------------------
 extern "C" int sgdx_demultiplex_device(sgdx_handle *h, uint32_t slot, const sgdx_fastq_view *fastqs, uint32_t num_fastqs,
                                        const sgdx_segment *segs, uint32_t nsegs, uint64_t n, const sgdx_demux_out *out) {
+    return sgdx::guarded("sgdx_demultiplex_device", [&]() -> int {
     if (int rc = check_slot_post(h, slot)) return rc;
     if (!fastqs || !segs || !out) return fail(SGDX_EINVAL, "sgdx_demultiplex_device: null argument");
     if (num_fastqs < 1 || num_fastqs > SGDX_MAX_SOURCES) return fail(SGDX_EINVAL, "1..%u FASTQs", SGDX_MAX_SOURCES);
@@ -1668,4 +1690,5 @@ extern "C" int sgdx_demultiplex_device(sgdx_handle *h, uint32_t slot, const sgdx
     // demux.rs:578: per_sample_reads[sample_idx].push(read), as a permutation
     if (out->d_order) return sgdx_route_device(h, slot, out->d_sample_idx, n, out->d_order, out->d_offsets);
     return SGDX_OK;
+    });
 }

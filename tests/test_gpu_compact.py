@@ -168,18 +168,34 @@ def test_batcher_in_compact_mode_returns_the_same_batches():
     check(lib().sgdx_batcher_create(st.matcher.handle, 16_384, C.byref(b)))
     check(lib().sgdx_batcher_set_compact(b, 1))
     got_idx, got_dist = [], []
-    for chunk in np.array_split(reads, 100):  # 1000-read chunks like --chunksize
-        c = np.ascontiguousarray(chunk)
-        check(lib().sgdx_batcher_push(b, c.ctypes.data, c.shape[0]))
-    assert lib().sgdx_batcher_set_compact(b, 0) != 0  # refused while batches are in flight
-    check(lib().sgdx_batcher_flush(b))
-    while True:
+
+    def take():
         pi, pd, n = C.c_void_p(), C.c_void_p(), C.c_uint64(0)
         check(lib().sgdx_batcher_next(b, C.byref(pi), C.byref(pd), C.byref(n)))
-        if n.value == 0:
-            break
-        got_idx.append(np.ctypeslib.as_array(C.cast(pi, C.POINTER(C.c_uint16)), (n.value,)).copy())
-        got_dist.append(np.ctypeslib.as_array(C.cast(pd, C.POINTER(C.c_uint8)), (n.value,)).copy())
+        if n.value:
+            got_idx.append(np.ctypeslib.as_array(C.cast(pi, C.POINTER(C.c_uint16)), (n.value,)).copy())
+            got_dist.append(np.ctypeslib.as_array(C.cast(pd, C.POINTER(C.c_uint8)), (n.value,)).copy())
+        return n.value
+
+    refused = 0
+    for chunk in np.array_split(reads, 100):  # 1000-read chunks like --chunksize
+        c = np.ascontiguousarray(chunk)
+        off = 0
+        while off < c.shape[0]:  # 2 x slots batches may wait for sgdx_batcher_next: then the push stops and says how far it got
+            took = C.c_uint64(0)
+            rc = lib().sgdx_batcher_push_n(b, c.ctypes.data + off * c.shape[1], c.shape[0] - off, C.byref(took))
+            off += took.value
+            if rc == -4:
+                refused += 1
+                assert take() > 0
+            else:
+                check(rc)
+    assert refused >= 1
+    assert lib().sgdx_batcher_set_compact(b, 0) != 0  # refused while batches are in flight
+    while lib().sgdx_batcher_flush(b) == -4:
+        assert take() > 0
+    while take():
+        pass
     lib().sgdx_batcher_destroy(b)
     assert np.array_equal(np.concatenate(got_idx), want["idx"])
     assert np.array_equal(np.concatenate(got_dist), want["dist"])

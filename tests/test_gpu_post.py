@@ -764,16 +764,23 @@ def test_batcher_feeds_the_unmatched_table():
     b = C.c_void_p()
     check(lib().sgdx_batcher_create(st.matcher.handle, 32_768, C.byref(b)))
     got = []
-    for chunk in np.array_split(reads, 200):
+
+    def take(everything):
+        while True:
+            pi, pd, k = C.c_void_p(), C.c_void_p(), C.c_uint64(0)
+            check(lib().sgdx_batcher_next(b, C.byref(pi), C.byref(pd), C.byref(k)))
+            if k.value:
+                got.append(np.ctypeslib.as_array(C.cast(pi, C.POINTER(C.c_uint16)), (k.value,)).copy())
+            if k.value == 0 or not everything:
+                return
+
+    for i, chunk in enumerate(np.array_split(reads, 200)):
         c = np.ascontiguousarray(chunk)
         check(lib().sgdx_batcher_push(b, c.ctypes.data, c.shape[0]))
+        if i % 40 == 39:  # results are taken as the run goes (at most 2 x slots batches may wait)
+            take(False)
     check(lib().sgdx_batcher_flush(b))
-    while True:
-        pi, pd, k = C.c_void_p(), C.c_void_p(), C.c_uint64(0)
-        check(lib().sgdx_batcher_next(b, C.byref(pi), C.byref(pd), C.byref(k)))
-        if k.value == 0:
-            break
-        got.append(np.ctypeslib.as_array(C.cast(pi, C.POINTER(C.c_uint16)), (k.value,)).copy())
+    take(True)
     lib().sgdx_batcher_destroy(b)
     idx = np.concatenate(got)
     want_idx = _oracle_idx(w, table, reads)

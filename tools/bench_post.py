@@ -109,7 +109,7 @@ def measure(reads=50_000_000, steps=10, warmup=3, only="qual,qual_index,unmatche
         d_order = torch.empty(n, dtype=torch.int32, device="cuda")
         d_off = torch.zeros(S + 2, dtype=torch.int64, device="cuda")
         ms, best = timed(lambda: m.route_device(d_idx.data_ptr(), n, d_order.data_ptr(), d_off.data_ptr()))
-        line("route", ms, best, n * (2 + 2 + 4), "sgdx_route_hist + scan + sgdx_route_scatter",
+        line("route", ms, best, n * (2 + 2 + 4), "sgdx_route_hist_cta + scans + sgdx_route_scatter_cta",
              {"bytes_per_read": 8, "note": "index array read twice (histogram, scatter), 4-byte read id written once"})
         del d_order
     if "demultiplex" in only:
@@ -153,6 +153,18 @@ def measure(reads=50_000_000, steps=10, warmup=3, only="qual,qual_index,unmatche
             "extra_ms": extra_ms, "unmatched_reads": um, "distinct_keys": info["distinct_keys"],
             "dropped_reads": info["dropped_reads"], "unmatched_reads_per_s": um / (extra_ms * 1e-3) if extra_ms > 0 else None,
             "bytes": n * 2 + um * (L + 24), "note": "every step starts from an empty table (first-touch claims included)"}
+        # the same on the fast input format: compact records through sgdx_match_ph, keys built from the planes
+        d_rec = torch.empty(n, dtype=torch.int64, device="cuda")
+        m2.pack_compact_device(d_in.data_ptr(), n, d_rec.data_ptr(), slot=0)
+        ref_keys = m2.unmatched_info()["distinct_keys"]
+        msc, _ = timed(lambda: m2.match_compact_device(d_rec.data_ptr(), n, d_idx.data_ptr(), slot=0), before=m2.reset_counters)
+        ic = m2.unmatched_info()
+        assert ic["distinct_keys"] == ref_keys and ic["unmatched_reads"] == um, (ic, info)
+        out["unmatched_count_compact"] = {
+            "kernel": m2.compact_kernel_name() + " + sgdx_unmatched_count<compact records>", "match_plus_count_ms": msc,
+            "unmatched_reads": ic["unmatched_reads"], "distinct_keys": ic["distinct_keys"], "dropped_reads": ic["dropped_reads"],
+            "note": "same table of keys as the ASCII run (asserted)"}
+        del d_rec
         import time
         t0 = time.perf_counter()
         top = m2.unmatched_top(1000)
