@@ -112,12 +112,25 @@ __device__ __forceinline__ uint32_t ph_hop_find(const PhSmem &sm, const PhParams
     return (e & ((1ull << 41) - 1ull)) == key ? (ids & 0x7FFu) | ((ids >> 11) << 16) : 0u;
 }
 
+// the same for a key of at most 32 bits (halves of at most 16 bases): the upper word of the key is zero, so it drops
+// out of the hash and the slot's upper word is nothing but the ids
+__device__ __forceinline__ uint32_t ph_hop_find32(const PhSmem &sm, const PhParams &c, uint32_t key) {
+    const uint32_t h = __umulhi(key, c.hop_k0) + key * c.hop_k1;
+    const uint2 e = *reinterpret_cast<const uint2 *>(sm.hslots + ((h * (uint32_t)sm.hdisp[h >> c.hop_bshift]) >> c.hop_sshift));
+    const uint32_t ids = e.y >> 9;  // 11 + 11 bits; bits 32..40 of the slot are key bits (zero here)
+    return (e.x == key && (e.y & 0x1FFu) == 0u) ? (ids & 0x7FFu) | ((ids >> 11) << 16) : 0u;
+}
+
 // metrics.rs:658-676 for an A/C/G/T-only NoMatch read, key sets in shared memory.  Halves of equal length share
 // their keys: two look-ups give all four memberships; otherwise four.
 __device__ __forceinline__ void ph_hop_check(const DevParams &p, const PhParams &c, const PhSmem &sm, uint32_t lo, uint32_t hi) {
     const uint32_t m1 = (1u << p.i1) - 1u, m2 = (1u << p.i2) - 1u;
     uint32_t a, b, c1, d2;  // ids + 1 of: index1 key in bc[..i1], index2 key in bc[i1..], index1 key in bc[i2..], index2 key in bc[..i2]
-    if (p.i1 == p.i2) {
+    if (p.i1 == p.i2 && p.i1 <= 16u) {
+        const uint32_t x = ph_hop_find32(sm, c, (lo & m1) | ((hi & m1) << p.i1));
+        const uint32_t y = ph_hop_find32(sm, c, ((lo >> p.i1) & m1) | (((hi >> p.i1) & m1) << p.i1));
+        a = x & 0xFFFFu, b = y >> 16, c1 = y & 0xFFFFu, d2 = x >> 16;
+    } else if (p.i1 == p.i2) {
         const uint32_t x = ph_hop_find(sm, c, (uint64_t)(lo & m1) | ((uint64_t)(hi & m1) << p.i1));
         const uint32_t y = ph_hop_find(sm, c, (uint64_t)((lo >> p.i1) & m1) | ((uint64_t)((hi >> p.i1) & m1) << p.i1));
         a = x & 0xFFFFu, b = y >> 16, c1 = y & 0xFFFFu, d2 = x >> 16;

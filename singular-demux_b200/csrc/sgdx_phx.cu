@@ -322,7 +322,7 @@ __global__ void __launch_bounds__(kPhThreads, 1) sgdx_match_phx(const DevParams 
             fetch(ch + total_warps, nextrec);
             const uint64_t base = ch * CHUNK;
             // the reads of a lane phase by phase, so that their dependent shared-memory chains overlap
-            uint32_t bin[RPL], dist[RPL], h[RPL], e[RPL], defer = 0u;
+            uint32_t bin[RPL], dist[RPL], h[RPL], e[RPL], defer = 0u, strays = 0u;
             uint2 t[RPL];
 #pragma unroll
             for (uint32_t k = 0; k < RPL; k++) {
@@ -344,6 +344,7 @@ __global__ void __launch_bounds__(kPhThreads, 1) sgdx_match_phx(const DevParams 
                 const uint32_t d = (uint32_t)__popc((lo ^ t[k].x) | (hi ^ t[k].y));
                 // stray: not "barcode_len A/C/G/T bases" -- an invalid position, or bits above the barcode's length
                 const bool stray = WIDE ? wide_stray(rec[2 * k], rec[2 * k + 1]) : ((w0 & c.nm0) | (w1 & c.nm1)) != 0u;
+                strays |= stray ? 1u << k : 0u;
                 bool bad = d > c.radius || stray;
                 if (WIDE) bad = bad || e[k] >= p.S;  // (a compact record cannot come close to the dummy row)
                 bin[k] = bad ? p.S : e[k];
@@ -390,7 +391,7 @@ __global__ void __launch_bounds__(kPhThreads, 1) sgdx_match_phx(const DevParams 
                     if (mine) {  // wide: the planes travel, flagged if the general path has to fetch the masks too
                         const uint32_t at = n1 + (uint32_t)__popc(votes & below);
                         uint32_t tag = iter * CHUNK + off0 + k * offk;
-                        if (WIDE && wide_stray(rec[2 * k], rec[(2 * k + 1) % 4])) tag |= 0x80000000u;
+                        if (WIDE && ((strays >> k) & 1u)) tag |= 0x80000000u;
                         asm volatile("st.shared.u64 [%0], %1;" ::"r"(qrec_s + at * 8u), "l"(WIDE ? rec[2 * k] : rec[k]) : "memory");
                         asm volatile("st.shared.u32 [%0], %1;" ::"r"(qoff_s + at * 4u), "r"(tag) : "memory");
                     }
