@@ -944,11 +944,14 @@ __global__ void __launch_bounds__(W * 32u) sgdx_route_scatter_cta(const RouteTil
 #pragma unroll
     for (uint32_t k = 0; k < W / 4u; k++)
         below[k] = 4u * k + 4u <= warp ? 0xFFFFFFFFu : (4u * k >= warp ? 0u : (1u << (8u * (warp - 4u * k))) - 1u);
+    // the index of the tile after the next one is requested at the top of an iteration and first looked at two
+    // iterations later (a use right behind the load would stall the warp for a DRAM round trip in every tile)
     uint64_t r = lo + 32u * warp + lane;
     uint32_t b = r < hi ? min((uint32_t)__ldg(p.idx + r), last) : bins;
+    uint32_t raw1 = r + 32u * W < hi ? (uint32_t)__ldg(p.idx + r + 32u * W) : 0xFFFFFFFFu;  // next tile, unclamped
     for (uint32_t t = 0; lo + (uint64_t)t * (32u * W) < hi; t++) {
-        const uint64_t rn = r + 32u * W;
-        const uint32_t bn = rn < hi ? min((uint32_t)__ldg(p.idx + rn), last) : bins;  // next tile's index, early
+        const uint64_t rn = r + 32u * W, rnn = r + 64u * W;
+        const uint32_t raw2 = rnn < hi ? (uint32_t)__ldg(p.idx + rnn) : 0xFFFFFFFFu;
         uint8_t *cn = cnts + (size_t)(t & 1u) * bins * W;
         atomicOr(bm + b, 1u << lane);
         __syncwarp();
@@ -993,7 +996,8 @@ __global__ void __launch_bounds__(W * 32u) sgdx_route_scatter_cta(const RouteTil
             }
         }
         r = rn;
-        b = bn;
+        b = raw1 == 0xFFFFFFFFu ? bins : min(raw1, last);
+        raw1 = raw2;
     }
 }
 
@@ -1579,6 +1583,10 @@ extern "C" int sgdx_route_device(sgdx_handle *h, uint32_t slot, const uint16_t *
     if (route_tile_smem<16>(p.bins, nullptr, nullptr) <= 113u * 1024u) W = 16, per_sm = 2u;
     else if (route_tile_smem<8>(p.bins, nullptr, nullptr) <= 113u * 1024u) W = 8, per_sm = 2u;
     else if (route_tile_smem<8>(p.bins, nullptr, nullptr) <= 227u * 1024u) W = 8, per_sm = 1u;
+#ifndef SGDX_NO_TEST_HOOKS  // measurement hook: ranges (= CTAs of the tile form) per SM
+    if (const char *e = getenv("SGDX_ROUTE_PER_SM"))
+        if (atoi(e) > 0) per_sm = (uint64_t)atoi(e);
+#endif
     if (W) {
         p.warps = W;
     } else {
