@@ -22,6 +22,8 @@
 // one 256-bit load, answered by one 64-bit store (4 sample indices) and one 32-bit store (4 distances).  The next
 // chunk's records are requested before the current chunk is processed.  Buffers that are not aligned for this, and
 // the last partial chunk, take the same code with 64-bit loads and 16/8-bit stores (lane i owns reads i, i+32, ...).
+#include <cstdlib>
+
 #include "sgdx_seed_search.cuh"
 
 namespace sgdx {
@@ -66,6 +68,10 @@ __host__ __device__ inline size_t ph_carve(unsigned char *base, uint32_t S, uint
 }
 
 constexpr size_t kPhSmemLimit = 227u * 1024u;
+// A ragged batch (n % 128 != 0) costs a second launch for its last reads, and every launch loads the tables (~14 us),
+// while the general kernel is only ~8 % slower per read than the vector one: ragged batches of up to 32 M reads take
+// the general kernel alone (measured: 1 M reads 41 -> 27 us, 4 M 49 -> 40 us, 16 M 105 -> 98 us).
+constexpr uint64_t kPhOneLaunchBelow = 32u << 20;
 
 // what either kernel needs at least (sgdx_match_phx has a third queue): the host builder sizes its tables against this
 size_t ph_smem_bytes(uint32_t S, uint32_t bbits, uint32_t sbits) {
@@ -409,7 +415,12 @@ cudaError_t launch_ph(const DevParams &p0, const PhParams &c0, uint32_t mode, in
     const bool ham = mode == kModeHamming;
     const bool aligned = (reinterpret_cast<uintptr_t>(c.reads) & 31u) == 0u && (reinterpret_cast<uintptr_t>(p.out_idx) & 7u) == 0u &&
                          (reinterpret_cast<uintptr_t>(p.out_dist) & 3u) == 0u;
-    if (aligned) {
+#ifndef SGDX_NO_TEST_HOOKS  // measurement hook: batches of at most this many reads go through the general kernel alone
+    static const uint64_t novec_below = getenv("SGDX_PH_NOVEC_BELOW") ? strtoull(getenv("SGDX_PH_NOVEC_BELOW"), nullptr, 10) : kPhOneLaunchBelow;
+#else
+    static const uint64_t novec_below = kPhOneLaunchBelow;
+#endif
+    if (aligned && !((p.n & (kPhChunk - 1u)) != 0u && p.n <= novec_below)) {
         const uint64_t n_main = p.n & ~(uint64_t)(kPhChunk - 1u);
         p.n = n_main;
         cudaError_t e = ham ? launch_ph_t<kModeHamming, true>(p, c, f, sms, stream) : launch_ph_t<kModePreCompute, true>(p, c, f, sms, stream);

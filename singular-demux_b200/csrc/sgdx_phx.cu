@@ -320,6 +320,13 @@ __global__ void __launch_bounds__(kPhThreads, 1) sgdx_match_phx(const DevParams 
         const bool final = ch >= nchunks;
         if (!final) {
             fetch(ch + total_warps, nextrec);
+            // 16-byte records: the chunk after the next one is requested into L2 (no registers held; C3 0.910 ->
+            // 0.884 ms on one box -- the same request made sgdx_match_ph's compact stream 3 % slower)
+            if (VEC && WIDE && ch + 2u * total_warps < nchunks) {
+                const uint64_t base2 = (ch + 2u * total_warps) * CHUNK;
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(WIDE ? static_cast<const void *>(c.reads_wide + base2 + off0)
+                                                                   : static_cast<const void *>(c.reads + base2 + off0)));
+            }
             const uint64_t base = ch * CHUNK;
             // the reads of a lane phase by phase, so that their dependent shared-memory chains overlap
             uint32_t bin[RPL], dist[RPL], h[RPL], e[RPL], defer = 0u, strays = 0u;
@@ -617,7 +624,9 @@ static cudaError_t launch_ph_w(const DevParams &p0, const PhParams &c0, uint32_t
     const bool aligned = (reinterpret_cast<uintptr_t>(in) & 31u) == 0u &&
                          (reinterpret_cast<uintptr_t>(p.out_idx) & (WIDE ? 3u : 7u)) == 0u &&
                          (reinterpret_cast<uintptr_t>(p.out_dist) & (WIDE ? 1u : 3u)) == 0u;
-    if (aligned) {  // the full chunks through the vector kernel, the last reads through the general one (a one-CTA launch)
+    // the full chunks through the vector kernel, the last reads through the general one (a one-CTA launch that loads
+    // the tables again: ragged batches of up to 32 M reads take the general kernel alone, see sgdx_ph.cu)
+    if (aligned && !(p.n % chunk != 0u && p.n <= (32ull << 20))) {
         const uint64_t n_main = p.n - p.n % chunk;
         p.n = n_main;
         cudaError_t e = ham ? launch_ph_t<kModeHamming, true, WIDE, SHORT>(p, c, fit, sms, stream)

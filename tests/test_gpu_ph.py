@@ -247,6 +247,52 @@ def test_full_size_properties_and_agreement_with_the_older_kernels():
     assert np.array_equal(res["ph"][1][:k].numpy(), want["dist"])
 
 
+@pytest.mark.parametrize("cfg", ["C2", "C3"])
+def test_ragged_batch_above_the_one_launch_threshold(cfg):
+    """A batch of more than 32 M reads whose size is not a multiple of the chunk: the vector kernel takes the full
+    chunks and a second launch the last reads (smaller ragged batches take the general kernel alone).  Same arrays,
+    counters and hop map as the ASCII kernel over all reads; the oracle on both ends."""
+    import torch
+    w = sg.synth.CONFIGS[cfg]
+    table = w.table()
+    L = w.barcode_len
+    n = (32 << 20) + 4096 + 77
+    d_table = torch.from_numpy(table).cuda()
+    d_in = torch.empty((n, L), dtype=torch.uint8, device="cuda")
+    w.reads_device(0, n, d_table.data_ptr(), d_in.data_ptr(), 0)
+    d_in[n - 40:n - 30] = ord("N")
+    torch.cuda.synchronize()
+    res = {}
+    for mode in ("records", "ascii"):
+        st = _stage(table, HAM, w.max_mismatches, w.min_delta, 1, None, w.index_lengths)
+        m = st.matcher
+        d_idx = torch.full((n,), -1, dtype=torch.int16, device="cuda")
+        d_dist = torch.full((n,), 0x77, dtype=torch.uint8, device="cuda")
+        if mode == "ascii":
+            m.match_device(d_in.data_ptr(), n, d_idx.data_ptr(), d_dist.data_ptr())
+        elif L <= 21:
+            d_rec = torch.empty(n, dtype=torch.int64, device="cuda")
+            m.pack_compact_device(d_in.data_ptr(), n, d_rec.data_ptr())
+            m.match_compact_device(d_rec.data_ptr(), n, d_idx.data_ptr(), d_dist.data_ptr())
+        else:
+            d_rec = torch.empty((n, 4), dtype=torch.int32, device="cuda")
+            m.pack_device(d_in.data_ptr(), n, d_rec.data_ptr())
+            m.match_packed_device(d_rec.data_ptr(), n, d_idx.data_ptr(), d_dist.data_ptr())
+        m.sync()
+        torch.cuda.synchronize()
+        met = st.metrics()
+        assert met.total_templates == n
+        res[mode] = (d_idx.cpu(), d_dist.cpu(), met.per_sample_array(), met.sample_barcode_hop_tracker.count_tracker)
+        st.close()
+        del d_idx, d_dist
+    assert torch.equal(res["records"][0], res["ascii"][0]) and torch.equal(res["records"][1], res["ascii"][1])
+    assert np.array_equal(res["records"][2], res["ascii"][2]) and res["records"][3] == res["ascii"][3]
+    for sl in (slice(0, 100_000), slice(n - 100_000, n)):
+        want = _oracle(table, HAM, w.max_mismatches, w.min_delta, 1, None, w.index_lengths, d_in[sl].cpu().numpy())
+        assert np.array_equal(res["records"][0][sl].numpy().view(np.uint16), want["idx"])
+        assert np.array_equal(res["records"][1][sl].numpy(), want["dist"])
+
+
 def test_stress_streams_equal_the_oracle():
     """bench.py's "stress" streams on C2's table: 5 % substitutions per base (a third of the reads end up one
     mismatch away, a third unmatched) and exactly one substituted base in every read."""
