@@ -176,16 +176,14 @@ __global__ void __launch_bounds__(kPhThreads, 1) sgdx_match_ph(const DevParams p
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const uint32_t ncopies = 1u << f.clog;
 
-    for (uint32_t i = threadIdx.x; i < (1u << bbits); i += kPhThreads) sm.disp[i] = c.disp[i];
-    for (uint32_t i = threadIdx.x; i < (1u << sbits); i += kPhThreads) sm.slots[i] = c.slots[i];
-    for (uint32_t i = threadIdx.x; i < (S1 << f.clog); i += kPhThreads) {
-        const uint32_t s = i >> f.clog;  // the dummy row is >= 11 mismatches away from any valid record
-        sm.planes[i] = s < p.S ? p.table[s] : make_uint2(0u, 0xFFFFFFFFu);
-    }
+    copy_table(sm.disp, c.disp, 2u << bbits, threadIdx.x, kPhThreads);
+    copy_table(sm.slots, c.slots, 2u << sbits, threadIdx.x, kPhThreads);
+    // (the dummy row is >= 11 mismatches away from any valid record)
+    fill_planes(sm.planes, p.table, p.S, f.clog, make_uint2(0u, 0xFFFFFFFFu), threadIdx.x, kPhThreads);
     for (uint32_t i = threadIdx.x; i <= nbins; i += kPhThreads) sm.hist[i] = 0u;
     if (f.hop_smem) {
-        for (uint32_t i = threadIdx.x; i < (1u << (32u - c.hop_sshift)); i += kPhThreads) sm.hslots[i] = c.hop_slots[i];
-        for (uint32_t i = threadIdx.x; i < (1u << (32u - c.hop_bshift)); i += kPhThreads) sm.hdisp[i] = c.hop_disp[i];
+        copy_table(sm.hslots, c.hop_slots, 8u << (32u - c.hop_sshift), threadIdx.x, kPhThreads);
+        copy_table(sm.hdisp, c.hop_disp, 2u << (32u - c.hop_bshift), threadIdx.x, kPhThreads);
     }
     __syncthreads();
 

@@ -246,21 +246,19 @@ __global__ void __launch_bounds__(kPhThreads, 1) sgdx_match_phx(const DevParams 
     const uint32_t ncopies = 1u << fit.clog;
     const uint32_t lmask = c.lmask;
 
-    for (uint32_t i = threadIdx.x; i < (1u << bbits); i += kPhThreads) sm.disp[i] = c.disp[i];
-    for (uint32_t i = threadIdx.x; i < (1u << sbits); i += kPhThreads) sm.slots[i] = c.slots[i];
-    for (uint32_t i = threadIdx.x; i < (S1 << fit.clog); i += kPhThreads) {
-        const uint32_t s = i >> fit.clog;  // the dummy row is >= 11 mismatches away from any compact record
-        sm.planes[i] = s < p.S ? p.table[s] : make_uint2(0u, 0xFFFFFFFFu);
-    }
+    copy_table(sm.disp, c.disp, 2u << bbits, threadIdx.x, kPhThreads);
+    copy_table(sm.slots, c.slots, 2u << sbits, threadIdx.x, kPhThreads);
+    // (the dummy row is >= 11 mismatches away from any compact record)
+    fill_planes(sm.planes, p.table, p.S, fit.clog, make_uint2(0u, 0xFFFFFFFFu), threadIdx.x, kPhThreads);
     for (uint32_t i = threadIdx.x; i < nbins; i += kPhThreads) sm.hist[i] = 0u;
     if (fit.hsbits) {
-        for (uint32_t i = threadIdx.x; i < (1u << fit.hsbits); i += kPhThreads) sm.hslots[i] = c.hop_slots[i];
-        for (uint32_t i = threadIdx.x; i < (1u << fit.hbbits); i += kPhThreads) sm.hdisp[i] = c.hop_disp[i];
+        copy_table(sm.hslots, c.hop_slots, 8u << fit.hsbits, threadIdx.x, kPhThreads);
+        copy_table(sm.hdisp, c.hop_disp, 2u << fit.hbbits, threadIdx.x, kPhThreads);
     }
-    for (uint32_t i = threadIdx.x; i < fit.hdr_total; i += kPhThreads) sm.hdr[i] = p.seed_hdr[i];
-    for (uint32_t i = threadIdx.x; i < fit.ids_total; i += kPhThreads) sm.ids[i] = p.seed_ids[i];
-    for (uint32_t i = threadIdx.x; i < fit.mhdr_total; i += kPhThreads) sm.mhdr[i] = c.ms_hdr[i];
-    for (uint32_t i = threadIdx.x; i < fit.mids_total; i += kPhThreads) sm.mids[i] = c.ms_ids[i];
+    copy_table(sm.hdr, p.seed_hdr, 2u * fit.hdr_total, threadIdx.x, kPhThreads);
+    copy_table(sm.ids, p.seed_ids, 2u * fit.ids_total, threadIdx.x, kPhThreads);
+    copy_table(sm.mhdr, c.ms_hdr, 2u * fit.mhdr_total, threadIdx.x, kPhThreads);
+    copy_table(sm.mids, c.ms_ids, 2u * fit.mids_total, threadIdx.x, kPhThreads);
     __syncthreads();
 
     uint64_t *const qrec = sm.qrec + warp * fit.qcap;

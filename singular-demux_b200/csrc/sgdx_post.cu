@@ -310,6 +310,10 @@ constexpr uint32_t kExtractThreads = 256;  // = reads per tile
 // counter, so it comes through the uniform datapath; inside a run the addresses are consecutive) into a
 // shared-memory tile; the CTA then writes the tile with coalesced 32-bit stores.  A 20-byte row stride is
 // conflict-free for the byte stores (bank = 5 * lane + pos / 4).
+// OUT 0: the L-byte ASCII barcodes.  1 / 2: the barcode goes straight into a compact 64-bit record / a 16-byte
+// sgdx_read record (the thread that gathered a row folds it into planes: BASELINE's "reads packed into 2-bit base
+// planes plus an N mask" inside the kernels), so that sgdx_match_segments_device never writes or re-reads the ASCII form.
+template <int OUT>
 __global__ void __launch_bounds__(kExtractThreads) sgdx_extract(const ExtractParams p) {
     __shared__ __align__(16) uint8_t s_tile[kExtractThreads * SGDX_MAX_BARCODE_LEN];
     const uint32_t L = p.L;
@@ -327,6 +331,27 @@ __global__ void __launch_bounds__(kExtractThreads) sgdx_extract(const ExtractPar
                 for (uint32_t k = 0; k < len; k++) row[k] = __ldg(from + k);
                 row += len;
             }
+        }
+        if (OUT != 0) {
+            if (threadIdx.x < cnt) {
+                const uint8_t *row = s_tile + threadIdx.x * L;  // written by this thread
+                Rd rd = {0u, 0u, 0u, 0u};
+                if ((L & 3u) == 0u) {  // rows start on word boundaries
+                    for (uint32_t j = 0; j < L; j += 4) fold_word(*reinterpret_cast<const uint32_t *>(row + j), j, rd);
+                } else {
+                    for (uint32_t j = 0; j < L; j += 4) {
+                        uint32_t w = 0x41414141u;  // pad with 'A': contributes zero bits to every plane
+                        for (uint32_t k = 0; k < 4 && j + k < L; k++) w = (w & ~(0xFFu << (8 * k))) | ((uint32_t)row[j + k] << (8 * k));
+                        fold_word(w, j, rd);
+                    }
+                }
+                const uint32_t inv = rd.nmask | rd.xmask;
+                rd.lo &= ~inv;
+                rd.hi &= ~inv;
+                if (OUT == 1) reinterpret_cast<uint64_t *>(p.out)[first + threadIdx.x] = compact_of_rd(rd);
+                else reinterpret_cast<uint4 *>(p.out)[first + threadIdx.x] = make_uint4(rd.lo, rd.hi, rd.nmask, rd.xmask & ~rd.nmask);
+            }
+            continue;  // (rows are private to their threads: no barrier needed)
         }
         __syncthreads();
         const uint32_t bytes = cnt * L;
@@ -1382,7 +1407,7 @@ extern "C" int sgdx_extract_device(sgdx_handle *h, uint32_t slot, uint32_t num_s
     p.n = n;
     p.out = d_out;
     p.words_ok = (reinterpret_cast<uintptr_t>(d_out) & 3u) == 0u;
-    sgdx_extract<<<grid_cap(n, kExtractThreads, h->sms, 8), kExtractThreads, 0, h->slots[slot].stream>>>(p);
+    sgdx_extract<0><<<grid_cap(n, kExtractThreads, h->sms, 8), kExtractThreads, 0, h->slots[slot].stream>>>(p);
     CU(cudaGetLastError());
     h->launches.fetch_add(1);
     return SGDX_OK;
@@ -1397,14 +1422,34 @@ extern "C" int sgdx_match_segments_device(sgdx_handle *h, uint32_t slot, uint32_
     if (int rc = check_slot_post(h, slot)) return rc;
     Slot &s = h->slots[slot];
     CU(cudaSetDevice(h->cfg.device));
+    const uint32_t L = h->cfg.barcode_len;
     if (n > s.extract_cap) {
         CU(cudaStreamSynchronize(s.stream));
         cudaFree(s.d_extract);
         s.d_extract = nullptr;
         s.extract_cap = 0;
         const uint64_t cap = n + n / 8 + 1024;
-        CU(cudaMalloc(&s.d_extract, cap * h->cfg.barcode_len));
+        CU(cudaMalloc(&s.d_extract, cap * std::max<uint32_t>(L, 16u)));  // L ASCII bytes, or an 8- / 16-byte record
         s.extract_cap = cap;
+    }
+    // Handles whose tables run the perfect-hash kernels take the barcodes as records, written by the extraction
+    // kernel itself.  With the unmatched table on the ASCII form is kept: a barcode with a byte that is none of
+    // A/C/G/T/N has a key only there.
+    const bool compact = L <= kCompactMaxLen && (h->single || (h->ph.slots && !h->ph.wide));
+    const bool packed = !compact && L <= SGDX_MAX_PACKED_LEN && h->ph.slots && h->ph.wide;
+    if ((compact || packed) && !h->unm.on) {
+        ExtractParams p;
+        if (int rc = fill_extract(h, num_sources, d_bases, strides, segs, nsegs, &p)) return rc;
+        if (n) {
+            p.n = n;
+            p.out = s.d_extract;
+            if (compact) sgdx_extract<1><<<grid_cap(n, kExtractThreads, h->sms, 8), kExtractThreads, 0, s.stream>>>(p);
+            else sgdx_extract<2><<<grid_cap(n, kExtractThreads, h->sms, 8), kExtractThreads, 0, s.stream>>>(p);
+            CU(cudaGetLastError());
+            h->launches.fetch_add(1);
+        }
+        return compact ? sgdx_match_compact_device(h, slot, reinterpret_cast<const uint64_t *>(s.d_extract), n, d_idx, d_dist)
+                       : sgdx_match_packed_device(h, slot, reinterpret_cast<const sgdx_read *>(s.d_extract), n, d_idx, d_dist);
     }
     if (int rc = sgdx_extract_device(h, slot, num_sources, d_bases, strides, segs, nsegs, n, s.d_extract)) return rc;
     return sgdx_match_device(h, slot, s.d_extract, n, d_idx, d_dist);

@@ -188,6 +188,30 @@ __device__ __forceinline__ uint64_t compact_of_rd(const Rd &rd) {
            ((uint64_t)inv << (2u * kCompactField));
 }
 
+// Table prologue of the perfect-hash kernels: global -> shared copies in 16-byte pieces (both sides 16-byte aligned;
+// a tail of less than 16 bytes goes byte-wise), and the planes table written `copies` times per sample (copies = a
+// power of two).  The u16-at-a-time loops they replace were 40 % of a 1 M-read launch.
+__device__ __forceinline__ void copy_table(void *dst_smem, const void *src_global, uint32_t bytes, uint32_t tid, uint32_t nthreads) {
+    const uint32_t vec = bytes >> 4;
+    for (uint32_t i = tid; i < vec; i += nthreads) static_cast<uint4 *>(dst_smem)[i] = __ldg(static_cast<const uint4 *>(src_global) + i);
+    for (uint32_t i = (vec << 4) + tid; i < bytes; i += nthreads)
+        static_cast<unsigned char *>(dst_smem)[i] = __ldg(static_cast<const unsigned char *>(src_global) + i);
+}
+
+__device__ __forceinline__ void fill_planes(uint2 *dst_smem, const uint2 *__restrict__ table, uint32_t S, uint32_t clog, uint2 dummy,
+                                            uint32_t tid, uint32_t nthreads) {
+    const uint32_t copies = 1u << clog;
+    for (uint32_t s = tid; s <= S; s += nthreads) {  // row S = the dummy row
+        const uint2 t = s < S ? __ldg(table + s) : dummy;
+        uint2 *row = dst_smem + ((size_t)s << clog);
+        if (copies >= 2u) {
+            for (uint32_t k = 0; k < copies / 2u; k++) reinterpret_cast<uint4 *>(row)[k] = make_uint4(t.x, t.y, t.x, t.y);
+        } else {
+            row[0] = t;
+        }
+    }
+}
+
 inline uint32_t persistent_grid(uint64_t n, uint32_t threads, int sms, int per_sm) {
     uint64_t tiles = (n + threads - 1) / threads;
     uint64_t cap = (uint64_t)sms * (uint64_t)per_sm;  // persistent grid: a multiple of the SM count

@@ -132,7 +132,7 @@ def measure(reads=50_000_000, steps=10, warmup=3, only="qual,qual_index,unmatche
                                                       d_order.data_ptr(), d_off.data_ptr()))
         nbytes = nd * (20 + 20 + 300 + 20 + 3 + 8)
         out["demultiplex_device"] = {
-            "kernel": "sgdx_extract + sgdx_match_exact_first + 4 x sgdx_qual_counts + sgdx_route_*", "templates": nd,
+            "kernel": "sgdx_extract (barcodes written as compact records) + " + m.compact_kernel_name() + " + 4 x sgdx_qual_counts + sgdx_route_*", "templates": nd,
             "avg_ms": ms, "best_ms": best, "templates_per_s": nd / (ms * 1e-3), "bytes": nbytes,
             "achieved_gbs": nbytes / (ms * 1e-3) / 1e9, "frac_of_hbm_peak": nbytes / (ms * 1e-3) / 1e9 / peak,
             "layout": "I1 10B + I2 10B + R1 150T + R2 150T, qualities of all four FASTQs counted, routing on"}
