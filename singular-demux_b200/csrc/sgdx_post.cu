@@ -1627,7 +1627,7 @@ extern "C" int sgdx_route_device(sgdx_handle *h, uint32_t slot, const uint16_t *
     uint64_t per_sm = 12u;
     if (route_tile_smem<16>(p.bins, nullptr, nullptr) <= 113u * 1024u) W = 16, per_sm = 2u;
     else if (route_tile_smem<8>(p.bins, nullptr, nullptr) <= 113u * 1024u) W = 8, per_sm = 2u;
-    else if (route_tile_smem<8>(p.bins, nullptr, nullptr) <= 227u * 1024u) W = 8, per_sm = 1u;
+    // (more than ~2200 bins: one 8-warp CTA per SM would be all that fits -- the per-warp ranges have more warps)
 #ifndef SGDX_NO_TEST_HOOKS  // measurement hook: ranges (= CTAs of the tile form) per SM
     if (const char *e = getenv("SGDX_ROUTE_PER_SM"))
         if (atoi(e) > 0) per_sm = (uint64_t)atoi(e);

@@ -387,7 +387,7 @@ def test_base_qual_rejects_bad_arguments():
 # 4. routing
 # ------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("S,n", [(1, 0), (1, 1), (3, 31), (3, 33), (96, 100_003), (384, 1_000_000), (1536, 250_000),
-                                 (8192, 40_000), (384, 5_000_000)])
+                                 (8192, 40_000), (384, 5_000_000), (2200, 300_000), (3000, 300_000)])
 def test_routing_is_a_stable_partition(S, n):
     import torch
     rng = np.random.default_rng(S + n)
