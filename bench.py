@@ -433,12 +433,14 @@ def main():
         return world * n * steps / float(t2.item()), n * row_bytes, n * 3, ok
 
     def copy_ceiling(row_bytes, steps):
-        """The same chunks, bytes and stream count as e2e_measure, copies only (no kernel): what this host can move."""
-        hin, hout = alloc_host(n * row_bytes), alloc_host(n * 3)
-        h_in = torch.from_numpy(np.ctypeslib.as_array(C.cast(hin, C.POINTER(C.c_uint8)), (n * row_bytes,)))
+        """The same chunks, bytes and stream count as e2e_measure, copies only (no kernel): what this host can move.
+        row_bytes may be fractional (dense records + their exception list): chunks copy round(c * row_bytes) bytes."""
+        up_total = int(n * row_bytes) + 64
+        hin, hout = alloc_host(up_total), alloc_host(n * 3)
+        h_in = torch.from_numpy(np.ctypeslib.as_array(C.cast(hin, C.POINTER(C.c_uint8)), (up_total,)))
         h_out = torch.from_numpy(np.ctypeslib.as_array(C.cast(hout, C.POINTER(C.c_uint8)), (n * 3,)))
         streams = [torch.cuda.Stream() for _ in range(nslots)]
-        d_up = [torch.empty(chunk * row_bytes, dtype=torch.uint8, device="cuda") for _ in range(nslots)]
+        d_up = [torch.empty(int(chunk * row_bytes) + 64, dtype=torch.uint8, device="cuda") for _ in range(nslots)]
         d_dn = [torch.empty(chunk * 3, dtype=torch.uint8, device="cuda") for _ in range(nslots)]
 
         def one_pass():
@@ -447,7 +449,8 @@ def main():
                 c = min(chunk, n - off)
                 s = i % nslots
                 with torch.cuda.stream(streams[s]):
-                    d_up[s][: c * row_bytes].copy_(h_in[off * row_bytes:(off + c) * row_bytes], non_blocking=True)
+                    a, b = int(off * row_bytes), int((off + c) * row_bytes)
+                    d_up[s][: b - a].copy_(h_in[a:b], non_blocking=True)
                     h_out[off * 3:(off + c) * 3].copy_(d_dn[s][: c * 3], non_blocking=True)
                 off += c
                 i += 1
@@ -467,8 +470,60 @@ def main():
         secs = float(t2.item()) / steps
         return {"reads_per_s": world * n / secs, "h2d_gbs": world * n * row_bytes / secs / 1e9,
                 "d2h_gbs": world * n * 3 / secs / 1e9,
-                "what": f"bare cudaMemcpyAsync of the same {row_bytes}+3 bytes per read, same chunks and {nslots} streams, "
+                "what": f"bare cudaMemcpyAsync of the same {row_bytes:.3g}+3 bytes per read, same chunks and {nslots} streams, "
                         f"all {world} rank(s) at once, no kernel"}
+
+    def e2e_dense(steps):
+        """Dense records (2 bits per base + exception list) in pinned host memory through sgdx_match_dense_batch; the
+        chunks are packed beforehand (untimed), like the records of the other e2e legs."""
+        B = sg.dense_bytes(L)
+        host_ascii = d_in.cpu().numpy()
+        hden, hidx, hdist = alloc_host(n * B + 64), alloc_host(n * 2), alloc_host(n)
+        h_den = np.ctypeslib.as_array(C.cast(hden, C.POINTER(C.c_uint8)), (n * B + 64,))
+        h_idx = np.ctypeslib.as_array(C.cast(hidx, C.POINTER(C.c_uint16)), (n,))
+        chunks, eis, ers = [], [], []
+        off = 0
+        while off < n:
+            c = min(chunk, n - off)
+            dn, ei, er = sg.pack_dense_host(host_ascii[off:off + c], threads=os.cpu_count() or 1)
+            h_den[off * B:(off + c) * B] = dn
+            chunks.append((off, c, sum(len(x) for x in eis), len(ei)))
+            eis.append(ei)
+            ers.append(er)
+            off += c
+        n_exc = sum(len(x) for x in eis)
+        hei, her = alloc_host(n_exc * 4 + 8), alloc_host(n_exc * 8 + 8)
+        if n_exc:
+            np.ctypeslib.as_array(C.cast(hei, C.POINTER(C.c_uint32)), (n_exc,))[:] = np.concatenate(eis)
+            np.ctypeslib.as_array(C.cast(her, C.POINTER(C.c_uint64)), (n_exc,))[:] = np.concatenate(ers)
+        del host_ascii, eis, ers
+
+        def one_pass():
+            for i, (o, c, e0, ne) in enumerate(chunks):
+                slot = i % nslots
+                if i >= nslots:
+                    m.sync(slot)
+                m.submit_dense_ptr(hden.value + o * B, c, hei.value + 4 * e0, her.value + 8 * e0, ne, hidx.value + o * 2,
+                                   hdist.value + o, slot)
+            for s_ in range(nslots):
+                m.sync(s_)
+
+        one_pass()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            one_pass()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        t2 = torch.tensor([dt], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+        k = min(n, 1 << 20)
+        ok = bool(np.array_equal(h_idx[:k], d_idx[:k].cpu().numpy().view(np.uint16)))
+        for p_ in (hden, hidx, hdist, hei, her):
+            lib.sgdx_free_host(p_)
+        up = n * B + n_exc * 12
+        return world * n * steps / float(t2.item()), up, n * 3, ok, n_exc
 
     e2e, e2e_ascii = None, None
     if not args.no_e2e and args.config != "C5":
@@ -485,6 +540,18 @@ def main():
                "timing": f"wall clock around {call}(host buffers)+sgdx_sync, max over ranks",
                "matches_device_resident_result": ok, "copy_ceiling": ceil,
                "frac_of_copy_ceiling": v / ceil["reads_per_s"], "numa": numa}
+        if compact_ok and keep_ascii and side:
+            # the PCIe form of the same records: 2 bits per base + an exception list for the reads with a no-call
+            vd, upd, downd, okd, n_exc = e2e_dense(e2e_steps)
+            ceild = copy_ceiling(upd / n, e2e_steps)
+            e2e = {"value": vd, "unit": UNIT, "h2d_bytes_per_step": upd, "d2h_bytes_per_step": downd, "steps": e2e_steps,
+                   "chunk_reads": chunk, "slots": nslots, "call": "sgdx_match_dense_batch",
+                   "input": f"dense records in pinned host memory: {sg.dense_bytes(L)} bytes per read (2 bits per base) + "
+                            f"{n_exc} exceptions of 12 bytes (reads with a no-call or a foreign byte), include/sgdx.h",
+                   "timing": "wall clock around sgdx_match_dense_batch(host buffers)+sgdx_sync, max over ranks",
+                   "matches_device_resident_result": okd, "copy_ceiling": ceild,
+                   "frac_of_copy_ceiling": vd / ceild["reads_per_s"], "numa": numa,
+                   "compact_records": e2e}
         if keep_ascii and side:
             v, up, down, ok = e2e_measure(m.submit_ptr, d_in, L, np.uint8, e2e_steps)
             e2e_ascii = {"value": v, "unit": UNIT, "h2d_bytes_per_step": up, "d2h_bytes_per_step": down,

@@ -147,6 +147,21 @@ int sgdx_match_packed_batch(sgdx_handle *h, uint32_t slot, const sgdx_read *reco
  * are served through the 16-byte packed form of the general kernels.  Bits above barcode_len in any plane, and
  * bit 63, are ignored.  The unmatched table is keyed from the records (see above for bytes outside A/C/G/T/N). */
 #define SGDX_COMPACT_MAX_LEN 21u
+/* Dense records: the compact records as they cross PCIe in batches from the host -- 2 bits per base and nothing else,
+ * SGDX_DENSE_BYTES(barcode_len) bytes per read (5 bytes at 20 bases instead of 8): bits 0..L-1 the lo plane, bits
+ * L..2L-1 the hi plane, little endian, read r at byte r * SGDX_DENSE_BYTES(L).  The invalid plane travels as a list of
+ * exceptions: a read that is not made of A/C/G/T only (a no-call, any other byte: about 2 % of real reads) has an
+ * arbitrary placeholder in the dense stream and an entry (read index, compact record) in the list.  On the device a
+ * streaming kernel rebuilds the compact records (sgdx_unpack_dense + sgdx_patch_exceptions) and the assignment runs on
+ * those: same results as every other entry point.
+ * sgdx_pack_dense_host: out_dense = n * SGDX_DENSE_BYTES(L) bytes; exceptions in ascending read order; if there are
+ * more than exc_cap of them the call fails with SGDX_ENOMEM and *n_exc says how many there are.
+ * sgdx_match_dense_batch: sgdx_match_batch for such a batch (n < 2^32). */
+#define SGDX_DENSE_BYTES(barcode_len) ((2u * (barcode_len) + 7u) / 8u)
+int sgdx_pack_dense_host(const uint8_t *barcodes_ascii, uint64_t n, uint32_t barcode_len, uint8_t *out_dense,
+                         uint32_t *exc_index, uint64_t *exc_record, uint64_t exc_cap, uint64_t *n_exc, uint32_t threads);
+int sgdx_match_dense_batch(sgdx_handle *h, uint32_t slot, const uint8_t *dense, uint64_t n, const uint32_t *exc_index,
+                           const uint64_t *exc_record, uint64_t n_exc, uint16_t *out_idx, uint8_t *out_dist);
 int sgdx_pack_compact_host(const uint8_t *barcodes_ascii, uint64_t n, uint32_t barcode_len, uint64_t *out_records,
                            uint32_t threads /* 0 -> 1 */);
 int sgdx_pack_compact_device(sgdx_handle *h, uint32_t slot, const uint8_t *d_barcodes_ascii, uint64_t n,
@@ -208,9 +223,10 @@ int sgdx_batcher_push_n(sgdx_batcher *b, const uint8_t *barcodes_ascii, uint64_t
 int sgdx_batcher_push(sgdx_batcher *b, const uint8_t *barcodes_ascii, uint64_t n);
 /* launch the partially filled batch, if any */
 int sgdx_batcher_flush(sgdx_batcher *b);
-/* on != 0: sgdx_batcher_push packs each barcode into a compact record as it copies it into the pinned buffer, and
- * batches go up as 8 bytes per read (barcode_len <= SGDX_COMPACT_MAX_LEN, no unmatched collection).  Call before
- * the first push or after the last result was taken. */
+/* on = 1: sgdx_batcher_push packs each barcode into a compact record as it copies it into the pinned buffer, and
+ * batches go up as 8 bytes per read; on = 2: as dense records (2 bits per base + the exception list, see below), about
+ * 5 bytes per read at 20 bases (barcode_len <= SGDX_COMPACT_MAX_LEN).  Call before the first push or after the last
+ * result was taken. */
 int sgdx_batcher_set_compact(sgdx_batcher *b, int on);
 /* Oldest unconsumed batch: blocks until it is done; pointers stay valid until the next call of
  * sgdx_batcher_next/destroy.  *n == 0 when nothing is pending. */

@@ -511,6 +511,29 @@ def compact_records(reads: np.ndarray) -> np.ndarray:
             ((inv << j).sum(axis=1) << np.uint64(42))).astype(np.uint64)
 
 
+def dense_records(reads: np.ndarray):
+    """The dense records of include/sgdx.h, stated with numpy: per read ceil(2L/8) bytes, bits 0..L-1 the lo plane, bits
+    L..2L-1 the hi plane (code = (ascii >> 1) & 3), little endian; reads with a byte outside A/C/G/T are exceptions
+    (index, compact record) and their dense bytes are unspecified.  Returns (dense [n, B] uint8, exception indices,
+    exception compact records, mask of the plain reads).  Checker of sgdx_pack_dense_host."""
+    reads = np.asarray(reads, dtype=np.uint8)
+    n, L = reads.shape
+    assert L <= 21
+    B = (2 * L + 7) // 8
+    ok = np.isin(reads, np.frombuffer(b"ACGT", dtype=np.uint8))
+    plain = ok.all(axis=1)
+    a = reads.astype(np.uint64)
+    j = np.arange(L, dtype=np.uint64)
+    lo = (np.where(ok, (a >> np.uint64(1)) & np.uint64(1), np.uint64(0)) << j).sum(axis=1).astype(np.uint64) if n else np.zeros(0, np.uint64)
+    hi = (np.where(ok, (a >> np.uint64(2)) & np.uint64(1), np.uint64(0)) << j).sum(axis=1).astype(np.uint64) if n else np.zeros(0, np.uint64)
+    x = lo | (hi << np.uint64(L))
+    dense = np.zeros((n, B), dtype=np.uint8)
+    for b in range(B):
+        dense[:, b] = ((x >> np.uint64(8 * b)) & np.uint64(0xFF)).astype(np.uint8)
+    exc = np.nonzero(~plain)[0].astype(np.uint32)
+    return dense, exc, compact_records(reads[exc]) if len(exc) else np.zeros(0, np.uint64), plain
+
+
 def packed_records(reads: np.ndarray) -> np.ndarray:
     """The 16-byte sgdx_read records of include/sgdx.h, stated with numpy: (n, 4) uint32 {lo, hi, nmask, xmask},
     bit j = base j; code = (ascii >> 1) & 3 at A/C/G/T positions (planes zero elsewhere), nmask = byte == 'N',

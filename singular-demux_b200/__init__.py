@@ -7,7 +7,8 @@ include/sgdx.h.  Import name: ``singular_demux_b200`` (the directory is ``singul
 from ._lib import (KERNEL_AUTO, KERNEL_SEEDED, KERNEL_DIRECT, LIB_PATH, MATCHER_AUTO, MATCHER_CACHED_HAMMING,
                    MATCHER_PRECOMPUTE, NO_DIST, SgdxError, lib)
 from .matcher import (UNDETERMINED_NAME, CachedHammingDistanceMatcher, GpuMatcher, MatcherKind, MatchResult,
-                      PreComputeMatcher, SampleMetadata, pack_compact_host, pack_host, select_matcher)
+                      PreComputeMatcher, SampleMetadata, dense_bytes, pack_compact_host, pack_dense_host, pack_host,
+                      select_matcher)
 from .metrics import (BarcodeCount, BaseQualCounter, DemuxedGroupMetrics, DemuxedGroupSampleMetrics,
                       SampleBarcodeHopTracker, UnmatchedCounter, delimit_barcode)
 from .read_structure import ReadSegment, ReadStructure, barcode_segment_lengths

@@ -77,7 +77,7 @@ class SynthParams(C.Structure):
 SYMBOLS = [
     "sgdx_last_error", "sgdx_version", "sgdx_create", "sgdx_destroy", "sgdx_get_config", "sgdx_alloc_host",
     "sgdx_free_host", "sgdx_match_batch", "sgdx_sync", "sgdx_match_device", "sgdx_pack_device",
-    "sgdx_match_packed_device", "sgdx_pack_host", "sgdx_match_packed_batch", "sgdx_pack_compact_host", "sgdx_pack_compact_device", "sgdx_match_compact_batch",
+    "sgdx_match_packed_device", "sgdx_pack_host", "sgdx_match_packed_batch", "sgdx_pack_compact_host", "sgdx_pack_compact_device", "sgdx_match_compact_batch", "sgdx_pack_dense_host", "sgdx_match_dense_batch",
     "sgdx_match_compact_device", "sgdx_set_stream", "sgdx_kernel_name", "sgdx_compact_kernel_name", "sgdx_packed_kernel_name", "sgdx_ph_probe_host_wide", "sgdx_path_flags", "sgdx_launch_count", "sgdx_counters", "sgdx_reset_counters",
     "sgdx_hop_count", "sgdx_hop_export", "sgdx_batcher_create", "sgdx_batcher_destroy", "sgdx_batcher_push", "sgdx_batcher_push_n",
     "sgdx_batcher_flush", "sgdx_batcher_set_compact", "sgdx_batcher_next", "sgdx_measure_int_peak",
@@ -117,6 +117,8 @@ def lib() -> C.CDLL:
     L.sgdx_pack_compact_host.argtypes = [vp, u64, u32, vp, u32]
     L.sgdx_pack_compact_device.argtypes = [vp, u32, vp, u64, vp]
     L.sgdx_match_compact_batch.argtypes = [vp, u32, vp, u64, vp, vp]
+    L.sgdx_pack_dense_host.argtypes = [vp, u64, u32, vp, vp, vp, u64, vp, u32]
+    L.sgdx_match_dense_batch.argtypes = [vp, u32, vp, u64, vp, vp, u64, vp, vp]
     L.sgdx_match_compact_device.argtypes = [vp, u32, vp, u64, vp, vp]
     L.sgdx_set_stream.argtypes = [vp, u32, vp]
     L.sgdx_kernel_name.argtypes = [vp]

@@ -577,6 +577,9 @@ extern "C" void sgdx_destroy(sgdx_handle *h) {
         cudaFree(s.d_extract);
         cudaFree(s.d_route);
         cudaFree(s.d_cexp);
+        cudaFree(s.d_dense);
+        cudaFree(s.d_exc_idx);
+        cudaFree(s.d_exc_rec);
         if (s.h_unm_stats) cudaFreeHost(s.h_unm_stats);
         if (s.e0) cudaEventDestroy(s.e0);
         if (s.e1) cudaEventDestroy(s.e1);
@@ -845,6 +848,61 @@ extern "C" int sgdx_match_compact_batch(sgdx_handle *h, uint32_t slot, const uin
     });
 }
 
+// sgdx_match_batch for a host batch of dense records + exception list (include/sgdx.h): 2 L bits per read over PCIe
+extern "C" int sgdx_match_dense_batch(sgdx_handle *h, uint32_t slot, const uint8_t *dense, uint64_t n, const uint32_t *exc_index,
+                                      const uint64_t *exc_record, uint64_t n_exc, uint16_t *out_idx, uint8_t *out_dist) {
+    return sgdx::guarded("sgdx_match_dense_batch", [&]() -> int {
+    if (int rc = check_slot(h, slot)) return rc;
+    const uint32_t L = h->cfg.barcode_len;
+    if (L > kCompactMaxLen) return fail(SGDX_EINVAL, "dense records hold at most %u bases, barcode_len is %u", kCompactMaxLen, L);
+    if (n && (!dense || !out_idx)) return fail(SGDX_EINVAL, "sgdx_match_dense_batch: null buffer");
+    if (n_exc && (!exc_index || !exc_record)) return fail(SGDX_EINVAL, "sgdx_match_dense_batch: null exception list");
+    if (n >> 32 || n_exc > n) return fail(SGDX_EINVAL, "sgdx_match_dense_batch: %llu reads / %llu exceptions", (unsigned long long)n, (unsigned long long)n_exc);
+    CU(cudaSetDevice(h->cfg.device));
+    Slot &s = h->slots[slot];
+    if (int rc = ensure_capacity(s, n, L)) return rc;
+    const uint64_t bytes = n * SGDX_DENSE_BYTES(L);
+    if (bytes + 64 > s.dense_cap || n_exc > s.exc_cap) {
+        CU(cudaStreamSynchronize(s.stream));
+        if (bytes + 64 > s.dense_cap) {
+            cudaFree(s.d_dense);
+            s.d_dense = nullptr;
+            s.dense_cap = 0;
+            const uint64_t cap = bytes + bytes / 8 + 4096;
+            CU(cudaMalloc(&s.d_dense, cap));
+            s.dense_cap = cap;
+        }
+        if (n_exc > s.exc_cap) {
+            cudaFree(s.d_exc_idx);
+            cudaFree(s.d_exc_rec);
+            s.d_exc_idx = nullptr;
+            s.d_exc_rec = nullptr;
+            s.exc_cap = 0;
+            const uint64_t cap = n_exc + n_exc / 4 + 1024;
+            CU(cudaMalloc(&s.d_exc_idx, cap * sizeof(uint32_t)));
+            CU(cudaMalloc(&s.d_exc_rec, cap * sizeof(uint64_t)));
+            s.exc_cap = cap;
+        }
+    }
+    uint64_t *d_rec = reinterpret_cast<uint64_t *>(s.d_in);
+    if (n) {
+        CU(cudaMemcpyAsync(s.d_dense, dense, bytes, cudaMemcpyHostToDevice, s.stream));
+        if (n_exc) {
+            CU(cudaMemcpyAsync(s.d_exc_idx, exc_index, n_exc * sizeof(uint32_t), cudaMemcpyHostToDevice, s.stream));
+            CU(cudaMemcpyAsync(s.d_exc_rec, exc_record, n_exc * sizeof(uint64_t), cudaMemcpyHostToDevice, s.stream));
+        }
+        CU(launch_unpack_dense(s.d_dense, n, L, s.d_exc_idx, s.d_exc_rec, n_exc, d_rec, h->sms, s.stream));
+        h->launches.fetch_add(n_exc ? 2 : 1);
+    }
+    if (int rc = run_compact(h, s, d_rec, n, s.d_idx, s.d_dist)) return rc;
+    if (n) {
+        CU(cudaMemcpyAsync(out_idx, s.d_idx, n * sizeof(uint16_t), cudaMemcpyDeviceToHost, s.stream));
+        if (out_dist) CU(cudaMemcpyAsync(out_dist, s.d_dist, n, cudaMemcpyDeviceToHost, s.stream));
+    }
+    return SGDX_OK;
+    });
+}
+
 // sgdx_match_batch for a host buffer of 16-byte sgdx_read records (any barcode_len <= 32; sgdx_pack_host writes them)
 extern "C" int sgdx_match_packed_batch(sgdx_handle *h, uint32_t slot, const sgdx_read *records, uint64_t n,
                                        uint16_t *out_idx, uint8_t *out_dist) {
@@ -1090,7 +1148,11 @@ struct sgdx_batcher {
     uint64_t batch_reads = 0;
     uint32_t L = 0;
     bool compact = false;           // the pinned buffers hold 64-bit compact records instead of L ASCII bytes
+    bool dense = false;             // ... or dense records (2 bits per base) + the exception lists below
     std::vector<uint8_t *> in;      // one pinned input buffer per slot
+    std::vector<uint32_t *> exc_idx;  // dense mode: pinned exception lists per slot (room for every read of a batch)
+    std::vector<uint64_t *> exc_rec;
+    uint64_t n_exc = 0;             // exceptions of the batch being filled
     std::vector<bool> slot_busy;    // slot has an unsynced batch
     uint32_t cur = 0;               // slot being filled
     uint64_t fill = 0;
@@ -1127,7 +1189,20 @@ extern "C" int sgdx_batcher_set_compact(sgdx_batcher *b, int on) {
     if (b->fill || !b->inflight.empty()) return fail(SGDX_ESTATE, "sgdx_batcher_set_compact: batches are in flight");
     if (on && b->L > kCompactMaxLen)
         return fail(SGDX_EINVAL, "compact records hold at most %u bases, barcode_len is %u", kCompactMaxLen, b->L);
-    b->compact = on != 0;
+    if (on == 2 && b->exc_idx.empty()) {  // dense records: the exception lists, worst case every read
+        if (b->batch_reads >> 32) return fail(SGDX_EINVAL, "dense records: batches of at most 2^32 - 1 reads");
+        b->exc_idx.assign(b->in.size(), nullptr);
+        b->exc_rec.assign(b->in.size(), nullptr);
+        for (size_t i = 0; i < b->in.size(); i++) {
+            void *q = nullptr;
+            if (int rc = sgdx_alloc_host(b->batch_reads * sizeof(uint32_t), &q)) return rc;
+            b->exc_idx[i] = static_cast<uint32_t *>(q);
+            if (int rc = sgdx_alloc_host(b->batch_reads * sizeof(uint64_t), &q)) return rc;
+            b->exc_rec[i] = static_cast<uint64_t *>(q);
+        }
+    }
+    b->compact = on == 1;
+    b->dense = on == 2;
     return SGDX_OK;
     });
 }
@@ -1142,6 +1217,8 @@ extern "C" void sgdx_batcher_destroy(sgdx_batcher *b) {
     for (uint32_t s = 0; s < b->slot_busy.size(); s++)
         if (b->slot_busy[s]) sgdx_sync(b->h, s, nullptr);
     for (auto p : b->in) cudaFreeHost(p);
+    for (auto p : b->exc_idx) cudaFreeHost(p);
+    for (auto p : b->exc_rec) cudaFreeHost(p);
     release_result(b, b->handed);
     for (auto &r : b->inflight) b->free_results.push_back(r);
     for (auto &r : b->free_results) {
@@ -1171,9 +1248,10 @@ static int submit(sgdx_batcher *b) {
     }
     r.n = b->fill;
     r.slot = b->cur;
-    const int rc_submit = b->compact ? sgdx_match_compact_batch(b->h, b->cur, reinterpret_cast<const uint64_t *>(b->in[b->cur]),
-                                                                r.n, r.idx, r.dist)
-                                     : sgdx_match_batch(b->h, b->cur, b->in[b->cur], r.n, r.idx, r.dist);
+    const int rc_submit =
+        b->dense ? sgdx_match_dense_batch(b->h, b->cur, b->in[b->cur], r.n, b->exc_idx[b->cur], b->exc_rec[b->cur], b->n_exc, r.idx, r.dist)
+        : b->compact ? sgdx_match_compact_batch(b->h, b->cur, reinterpret_cast<const uint64_t *>(b->in[b->cur]), r.n, r.idx, r.dist)
+                     : sgdx_match_batch(b->h, b->cur, b->in[b->cur], r.n, r.idx, r.dist);
     if (int rc = rc_submit) {
         b->free_results.push_back(r);  // the reads stay in the slot's input buffer; a retry re-submits them
         return rc;
@@ -1181,6 +1259,7 @@ static int submit(sgdx_batcher *b) {
     b->slot_busy[b->cur] = true;
     b->inflight.push_back(r);
     b->fill = 0;
+    b->n_exc = 0;
     b->cur = (b->cur + 1) % (uint32_t)b->in.size();
     if (b->slot_busy[b->cur]) {  // about to overwrite this slot's input buffer: its batch must have left the host
         if (int rc = sgdx_sync(b->h, b->cur, nullptr)) return rc;
@@ -1204,7 +1283,15 @@ extern "C" int sgdx_batcher_push_n(sgdx_batcher *b, const uint8_t *ascii, uint64
         if (b->fill == b->batch_reads)
             if (int rc = submit(b)) return rc;
         uint64_t take = std::min(n, b->batch_reads - b->fill);
-        if (b->compact) {  // the copy into the pinned buffer is the packing pass
+        if (b->dense) {  // the copy into the pinned buffer is the packing pass: 2 bits per base + exceptions
+            uint64_t k = 0;
+            uint32_t *ei = b->exc_idx[b->cur] + b->n_exc;
+            if (int rc = sgdx_pack_dense_host(ascii, take, b->L, b->in[b->cur] + b->fill * SGDX_DENSE_BYTES(b->L), ei,
+                                              b->exc_rec[b->cur] + b->n_exc, b->batch_reads - b->n_exc, &k, 1))
+                return rc;
+            for (uint64_t e = 0; e < k; e++) ei[e] += (uint32_t)b->fill;  // read numbers of the batch, not of this push
+            b->n_exc += k;
+        } else if (b->compact) {  // the copy into the pinned buffer is the packing pass
             if (int rc = sgdx_pack_compact_host(ascii, take, b->L, reinterpret_cast<uint64_t *>(b->in[b->cur]) + b->fill, 1))
                 return rc;
         } else {

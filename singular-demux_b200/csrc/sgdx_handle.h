@@ -43,6 +43,11 @@ struct Slot {
     std::vector<uint32_t> qmasks_key;
     uint4 *d_cexp = nullptr;                    // scratch of the compact-input general path (16-byte records)
     uint64_t cexp_cap = 0;
+    uint8_t *d_dense = nullptr;                 // dense records of a batch as they arrive (sgdx_match_dense_batch)
+    uint64_t dense_cap = 0;                     // bytes
+    uint32_t *d_exc_idx = nullptr;              // ... and its exception list
+    uint64_t *d_exc_rec = nullptr;
+    uint64_t exc_cap = 0;                       // entries
 };
 
 struct UnmSlot;

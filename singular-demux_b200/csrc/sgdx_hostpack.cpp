@@ -175,7 +175,77 @@ void pack_range(const uint8_t *ascii, uint64_t begin, uint64_t end, uint32_t L, 
     pack_range_scalar(ascii, begin, end, L, out);
 }
 
+// Dense records (include/sgdx.h): compact records of a tile (hot in L1) -> 2 L bits per read + the exception list
+struct DenseExc {
+    std::vector<uint32_t> idx;
+    std::vector<uint64_t> rec;
+};
+
+void dense_range(const uint8_t *ascii, uint64_t begin, uint64_t end, uint32_t L, uint64_t total, uint8_t *out, DenseExc *exc) {
+    const uint32_t B = SGDX_DENSE_BYTES(L);
+    const uint64_t fmask = (1ull << L) - 1ull;
+    uint64_t tile[1024];
+    for (uint64_t r0 = begin; r0 < end; r0 += 1024) {
+        const uint64_t cnt = std::min<uint64_t>(1024, end - r0);
+        pack_range(ascii + r0 * L, 0, cnt, L, total - r0, tile);
+        for (uint64_t i = 0; i < cnt; i++) {
+            const uint64_t rec = tile[i], r = r0 + i;
+            uint64_t d = 0;  // placeholder of an exception
+            if (rec >> (2u * kField)) {
+                exc->idx.push_back((uint32_t)r);
+                exc->rec.push_back(rec);
+            } else {
+                d = (rec & fmask) | (((rec >> kField) & fmask) << L);
+            }
+            // one 8-byte store per read; what it spills past its B bytes is overwritten by the next reads of this range,
+            // and the last 8 reads of a range are copied exactly (the next range may belong to another thread)
+            if (r + 8 < end) memcpy(out + r * B, &d, 8);
+            else memcpy(out + r * B, &d, B);
+        }
+    }
+}
+
 }  // namespace
+
+extern "C" int sgdx_pack_dense_host(const uint8_t *ascii, uint64_t n, uint32_t barcode_len, uint8_t *out_dense,
+                                    uint32_t *exc_index, uint64_t *exc_record, uint64_t exc_cap, uint64_t *n_exc,
+                                    uint32_t threads) {
+    return sgdx::guarded("sgdx_pack_dense_host", [&]() -> int {
+    if (n_exc) *n_exc = 0;
+    if (barcode_len < 1 || barcode_len > SGDX_COMPACT_MAX_LEN)
+        return sgdx::fail(SGDX_EINVAL, "dense records hold 1..%u bases, barcode_len is %u", SGDX_COMPACT_MAX_LEN, barcode_len);
+    if (!n_exc || (n && (!ascii || !out_dense))) return sgdx::fail(SGDX_EINVAL, "sgdx_pack_dense_host: null buffer");
+    if (n >> 32) return sgdx::fail(SGDX_EINVAL, "sgdx_pack_dense_host: %llu reads, at most 2^32 - 1 per batch", (unsigned long long)n);
+    if (threads == 0) threads = 1;
+    const uint64_t min_per_thread = 1u << 16;
+    const uint64_t nt = std::max<uint64_t>(1, std::min<uint64_t>(threads, (n + min_per_thread - 1) / min_per_thread));
+    std::vector<DenseExc> exc(nt);
+    const uint64_t per = (n + nt - 1) / nt;
+    auto work = [&](uint64_t t) { dense_range(ascii, std::min(n, t * per), std::min(n, (t + 1) * per), barcode_len, n, out_dense, &exc[t]); };
+    std::vector<std::thread> pool;
+    uint64_t started = 1;
+    try {
+        for (; started < nt; started++) pool.emplace_back(work, started);
+    } catch (...) {  // thread limit reached: this thread takes what is left
+    }
+    work(0);
+    for (uint64_t t = started; t < nt; t++) work(t);
+    for (auto &th : pool) th.join();
+    uint64_t total = 0;
+    for (const auto &e : exc) total += e.idx.size();
+    *n_exc = total;
+    if (total > exc_cap) return sgdx::fail(SGDX_ENOMEM, "sgdx_pack_dense_host: %llu exceptions, room for %llu", (unsigned long long)total, (unsigned long long)exc_cap);
+    if (total && (!exc_index || !exc_record)) return sgdx::fail(SGDX_EINVAL, "sgdx_pack_dense_host: null exception buffer");
+    uint64_t at = 0;
+    for (const auto &e : exc) {  // thread order = ascending read order
+        if (e.idx.empty()) continue;
+        memcpy(exc_index + at, e.idx.data(), e.idx.size() * sizeof(uint32_t));
+        memcpy(exc_record + at, e.rec.data(), e.rec.size() * sizeof(uint64_t));
+        at += e.idx.size();
+    }
+    return SGDX_OK;
+    });
+}
 
 extern "C" int sgdx_pack_compact_host(const uint8_t *ascii, uint64_t n, uint32_t barcode_len, uint64_t *out,
                                       uint32_t threads) {

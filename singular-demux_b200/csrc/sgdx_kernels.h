@@ -22,6 +22,10 @@ constexpr uint32_t kCompactField = 21;  // bits per plane
 constexpr uint32_t kCompactMask = (1u << kCompactField) - 1u;
 inline uint64_t compact_record(uint32_t lo, uint32_t hi) { return (uint64_t)lo | ((uint64_t)hi << 21); }
 cudaError_t launch_pack_compact(const uint8_t *reads, uint64_t n, uint32_t L, uint64_t *out, int sms, cudaStream_t stream);
+// dense records (2 L bits per read) + exception list -> compact records (sgdx_unpack_dense, sgdx_patch_exceptions);
+// `dense` 4-byte aligned and padded by 32 bytes, `out` 16-byte aligned
+cudaError_t launch_unpack_dense(const uint8_t *dense, uint64_t n, uint32_t L, const uint32_t *exc_idx, const uint64_t *exc_rec,
+                                uint64_t n_exc, uint64_t *out, int sms, cudaStream_t stream);
 cudaError_t launch_expand_compact(const uint64_t *in, uint64_t n, uint32_t L, uint4 *out, int sms, cudaStream_t stream);
 
 // Perfect-hash kernel for packed records (sgdx_ph.cu).  Key set K = every A/C/G/T string within `radius`

@@ -109,6 +109,26 @@ def pack_compact_host(barcodes: np.ndarray, threads: int = 1, out: Optional[np.n
     return rec
 
 
+def dense_bytes(barcode_len: int) -> int:
+    """SGDX_DENSE_BYTES: bytes of one dense record (2 bits per base)."""
+    return (2 * barcode_len + 7) // 8
+
+
+def pack_dense_host(barcodes: np.ndarray, threads: int = 1, exc_cap: Optional[int] = None):
+    """sgdx_pack_dense_host: (n, L) ASCII barcodes, L <= 21 -> (dense bytes [n * dense_bytes(L)], exception read
+    indices [k] uint32, their compact records [k] uint64).  exc_cap: room for exceptions (default: every read)."""
+    arr = np.ascontiguousarray(barcodes, dtype=np.uint8)
+    n, L = arr.shape
+    cap = n if exc_cap is None else int(exc_cap)
+    dense = np.empty(n * dense_bytes(L), dtype=np.uint8)
+    eidx = np.empty(max(cap, 1), dtype=np.uint32)
+    erec = np.empty(max(cap, 1), dtype=np.uint64)
+    k = C.c_uint64(0)
+    check(lib().sgdx_pack_dense_host(arr.ctypes.data, n, L, dense.ctypes.data, eidx.ctypes.data, erec.ctypes.data, cap,
+                                     C.byref(k), threads), "sgdx_pack_dense_host")
+    return dense, eidx[:k.value], erec[:k.value]
+
+
 def pack_host(barcodes: np.ndarray, threads: int = 1) -> np.ndarray:
     """sgdx_pack_host: (n, L) ASCII barcodes, L <= 32 -> (n, 4) uint32 sgdx_read records {lo, hi, nmask, xmask}."""
     arr = np.ascontiguousarray(barcodes, dtype=np.uint8)
@@ -220,6 +240,22 @@ class GpuMatcher:
         self.submit_compact_ptr(rec.ctypes.data, rec.size, idx.ctypes.data, dist.ctypes.data, slot)
         self.sync(slot)
         return idx, dist
+
+    def find_batch_dense(self, barcodes, slot: int = 0, threads: int = 1) -> Tuple[np.ndarray, np.ndarray]:
+        """find_batch through dense records: 2 bits per base + an exception list over PCIe (barcode_len <= 21)."""
+        dense, eidx, erec = pack_dense_host(as_barcode_array(barcodes, self.barcode_len), threads)
+        n = dense.size // dense_bytes(self.barcode_len)
+        idx = np.empty(n, dtype=np.uint16)
+        dist = np.empty(n, dtype=np.uint8)
+        self.submit_dense_ptr(dense.ctypes.data, n, eidx.ctypes.data, erec.ctypes.data, eidx.size, idx.ctypes.data,
+                              dist.ctypes.data, slot)
+        self.sync(slot)
+        return idx, dist
+
+    def submit_dense_ptr(self, dense_ptr: int, n: int, exc_idx_ptr: int, exc_rec_ptr: int, n_exc: int, idx_ptr: int,
+                         dist_ptr: int, slot: int = 0) -> None:
+        check(lib().sgdx_match_dense_batch(self._h, slot, dense_ptr, n, exc_idx_ptr or None, exc_rec_ptr or None, n_exc,
+                                           idx_ptr, dist_ptr or None), "sgdx_match_dense_batch")
 
     def find_batch_packed(self, barcodes, slot: int = 0, threads: int = 1) -> Tuple[np.ndarray, np.ndarray]:
         """find_batch through 16-byte records packed on the host (any barcode_len): sgdx_match_packed_batch."""

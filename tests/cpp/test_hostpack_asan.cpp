@@ -1,6 +1,6 @@
 // Host packers (csrc/sgdx_hostpack.cpp) under AddressSanitizer + UBSan: exact-size heap buffers for every barcode
 // length and a range of batch sizes, so any byte the 32-byte vector loads read past the end of the input is flagged;
-// also checks that the 8-byte and the 16-byte record of every read agree.  Built and run by
+// also checks that the 8-byte, the 16-byte and the dense record of every read agree.  Built and run by
 // tests/test_compact_cpu.py::test_host_packers_are_clean_under_asan (no GPU, no libsgdx.so: the source is compiled in).
 #include <cstdint>
 #include <cstdio>
@@ -26,6 +26,29 @@ int main() {
                     uint32_t lo = rec & 0x1FFFFF, hi = (rec >> 21) & 0x1FFFFF, inv = (rec >> 42) & 0x1FFFFF;
                     if ((lo & ~inv) != o16[r].lo || hi != o16[r].hi || (inv & ~lo) != o16[r].nmask || (inv & lo) != o16[r].xmask) return 3;
                 }
+                // dense records: exact-size output (n * B bytes), exceptions agree with the compact records
+                const uint32_t B = SGDX_DENSE_BYTES(L);
+                uint8_t *od = (uint8_t *)malloc(n * B ? n * B : 1);
+                uint32_t *ei = (uint32_t *)malloc(n ? n * 4 : 1);
+                uint64_t *er = (uint64_t *)malloc(n ? n * 8 : 1);
+                uint64_t ne = 0;
+                if (sgdx_pack_dense_host(in, n, L, od, ei, er, n, &ne, 3)) return 4;
+                uint64_t e = 0;
+                for (uint64_t r = 0; r < n; r++) {
+                    const uint64_t rec = o8[r];
+                    if (rec >> 42) {
+                        if (e >= ne || ei[e] != r || er[e] != rec) return 5;
+                        e++;
+                    } else {
+                        uint64_t d = 0;
+                        memcpy(&d, od + r * B, B);
+                        if (d != ((rec & 0x1FFFFF) | (((rec >> 21) & 0x1FFFFF) << L))) return 6;
+                    }
+                }
+                if (e != ne) return 7;
+                free(od);
+                free(ei);
+                free(er);
                 free(o8);
             }
             free(o16);

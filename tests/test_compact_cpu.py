@@ -142,3 +142,27 @@ def test_host_packers_are_clean_under_asan(tmp_path):
         r = subprocess.run([exe], capture_output=True, text=True, env={**os.environ, **env}, timeout=300)
         assert r.returncode == 0 and r.stdout.strip() == "ok", r.stdout + r.stderr
 
+
+
+@pytest.mark.parametrize("L", [1, 3, 4, 8, 12, 16, 20, 21])
+def test_host_packer_of_dense_records_equals_the_format_definition(L):
+    """sgdx_pack_dense_host: 2 bits per base for the plain reads, (index, compact record) for the others, in ascending
+    read order, for any thread count; the exception room is checked."""
+    rng = np.random.default_rng(3000 + L)
+    n = 140_003
+    arr = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=(n, L))]
+    odd = rng.random((n, L)) < 0.01
+    arr[odd] = ALPHABET[rng.integers(0, ALPHABET.size, int(odd.sum()))]
+    arr[:3] = ord("N")
+    want_dense, want_idx, want_rec, plain = orc.dense_records(arr)
+    for threads in (1, 3):
+        dense, eidx, erec = sg.pack_dense_host(arr, threads=threads)
+        assert dense.shape == (n * sg.dense_bytes(L),)
+        assert np.array_equal(dense.reshape(n, -1)[plain], want_dense[plain])
+        assert np.array_equal(eidx, want_idx) and np.array_equal(erec, want_rec)
+    with pytest.raises(sg.SgdxError):
+        sg.pack_dense_host(arr, exc_cap=2)           # fewer slots than exceptions
+    d0, i0, r0 = sg.pack_dense_host(arr[:0])
+    assert d0.size == 0 and i0.size == 0
+    with pytest.raises(sg.SgdxError):
+        sg.pack_dense_host(np.full((4, 22), ord("A"), dtype=np.uint8))

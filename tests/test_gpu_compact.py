@@ -157,8 +157,10 @@ def test_compact_empty_tiny_and_refused_inputs():  # (unmatched table from recor
     long.close()
 
 
-def test_batcher_in_compact_mode_returns_the_same_batches():
-    """sgdx_batcher_set_compact: push packs into the pinned buffer, batches go up as 8 bytes per read."""
+@pytest.mark.parametrize("mode", [1, 2])
+def test_batcher_in_compact_mode_returns_the_same_batches(mode):
+    """sgdx_batcher_set_compact: push packs into the pinned buffer, batches go up as 8 bytes per read (mode 1) or as dense
+    records + exception list (mode 2)."""
     from singular_demux_b200._lib import check, lib
     rng = np.random.default_rng(3)
     w, table, reads = _random_case(rng, 96, 16, 8, n=100_000)
@@ -166,7 +168,7 @@ def test_batcher_in_compact_mode_returns_the_same_batches():
     st = _stage(table, sg.MatcherKind.CachedHammingDistance, 1, 2, 1, None, w.index_lengths, slots=2)
     b = C.c_void_p()
     check(lib().sgdx_batcher_create(st.matcher.handle, 16_384, C.byref(b)))
-    check(lib().sgdx_batcher_set_compact(b, 1))
+    check(lib().sgdx_batcher_set_compact(b, mode))
     got_idx, got_dist = [], []
 
     def take():
@@ -201,3 +203,38 @@ def test_batcher_in_compact_mode_returns_the_same_batches():
     assert np.array_equal(np.concatenate(got_dist), want["dist"])
     assert np.array_equal(st.metrics().per_sample_array(), want["per_sample"])
     st.close()
+
+
+@pytest.mark.parametrize("S,L,i1", [(96, 16, 8), (384, 20, 10), (1, 8, 0), (40, 21, 10), (33, 13, 5), (4, 4, 0)])
+def test_dense_records_give_the_same_results(S, L, i1):
+    """sgdx_pack_dense_host + sgdx_match_dense_batch: 2 bits per base over PCIe, the reads with a no-call or a foreign
+    byte as an exception list; the device rebuilds the compact records and runs the same kernels.  Oracle parity on
+    index, distance, counters and hop map; ragged sizes (the unpack kernel takes four reads per thread), no exceptions,
+    nothing but exceptions."""
+    rng = np.random.default_rng(S * 53 + L)
+    w, table, reads = _random_case(rng, S, L, i1, n=60_003)
+    il = w.index_lengths
+    for kind in (sg.MatcherKind.CachedHammingDistance, sg.MatcherKind.PreCompute):
+        want = _oracle(table, kind, 1, 2, 1, None, il, reads)
+        st = _stage(table, kind, 1, 2, 1, None, il)
+        idx, dist = st.matcher.find_batch_dense(reads, threads=2)
+        assert np.array_equal(idx, want["idx"]) and np.array_equal(dist, want["dist"])
+        m = st.metrics()
+        assert np.array_equal(m.per_sample_array(), want["per_sample"]) and m.total_templates == len(reads)
+        if il:
+            assert m.sample_barcode_hop_tracker.count_tracker == want["hops"]
+        # ragged and tiny batches, on the other slot
+        for n in (0, 1, 2, 3, 5, 4097):
+            part = reads[:n]
+            i2, d2 = st.matcher.find_batch_dense(part, slot=1)
+            assert np.array_equal(i2, want["idx"][:n]) and np.array_equal(d2, want["dist"][:n])
+        plain = np.isin(reads, np.frombuffer(b"ACGT", dtype=np.uint8)).all(axis=1)
+        for sel in (plain, ~plain):  # no exception at all / every read an exception
+            part = np.ascontiguousarray(reads[sel][:5001])
+            i3, d3 = st.matcher.find_batch_dense(part)
+            assert np.array_equal(i3, want["idx"][sel][:5001]) and np.array_equal(d3, want["dist"][sel][:5001])
+        st.close()
+    long = sg.CachedHammingDistanceMatcher([b"ACGT" * 6, b"TTGA" * 6], 1, 2, 1)
+    with pytest.raises(sg.SgdxError):
+        long.submit_dense_ptr(0, 0, 0, 0, 0, 0, 0)
+    long.close()

@@ -1,7 +1,8 @@
 // bench_batcher.cpp -- the batching stage (sgdx_batcher_*, the new stage between demux.rs:522 and :528) fed the way the
 // host pipeline feeds it: T producer threads, each with its own handle + batcher, push 1000-read chunks of barcodes
 // that are hot in cache (what the segment extractor has just written) -- once with the plain ASCII copy into the
-// pinned buffer, once with the copy replaced by the compact-record packing pass (sgdx_batcher_set_compact).  Wall
+// pinned buffer, once with the copy replaced by the compact-record packing pass, once by the dense-record one
+// (sgdx_batcher_set_compact 1 / 2).  Wall
 // clock over push + flush + taking every result; H2D, kernel and D2H included.  Plain C ABI, like a Rust host would.
 //
 //   g++ -O2 -std=c++17 -I include tools/bench_batcher.cpp -o gpurun_out/bench_batcher -L singular-demux_b200 -lsgdx \
@@ -62,7 +63,7 @@ int main(int argc, char **argv) {
     for (int T : counts) {
         printf("%s{\"threads\": %d", first_row ? "" : ", ", T);
         first_row = false;
-        for (int compact = 0; compact < 2; compact++) {
+        for (int compact = 0; compact < 3; compact++) {  // 0 ASCII copy, 1 compact records, 2 dense records
             std::vector<sgdx_handle *> hs(T);
             std::vector<sgdx_batcher *> bs(T);
             for (int i = 0; i < T; i++) {
@@ -109,8 +110,9 @@ int main(int argc, char **argv) {
                 secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
             }
             const double rps = (double)T * (double)per_thread / secs;
-            printf(", \"%s\": {\"reads_per_s\": %.4g, \"seconds\": %.3f, \"pcie_up_gbs\": %.2f}", compact ? "compact" : "ascii", rps, secs,
-                   rps * (compact ? 8 : L) / 1e9);
+            printf(", \"%s\": {\"reads_per_s\": %.4g, \"seconds\": %.3f, \"pcie_up_gbs\": %.2f}",
+                   compact == 2 ? "dense" : (compact ? "compact" : "ascii"), rps, secs,
+                   rps * (compact == 2 ? 5.25 : (compact ? 8 : L)) / 1e9);
             for (int i = 0; i < T; i++) {
                 sgdx_batcher_destroy(bs[i]);
                 sgdx_destroy(hs[i]);
