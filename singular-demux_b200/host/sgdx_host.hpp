@@ -135,6 +135,19 @@ class GpuMatcher : public Matcher {
         check(sgdx_match_compact_batch(h_, slot, records, n, idx, dist), "sgdx_match_compact_batch");
         check(sgdx_sync(h_, slot, nullptr), "sgdx_sync");
     }
+    // ... and through dense records (2 bits per base + an exception list for the reads with a no-call or a foreign
+    // byte: SGDX_DENSE_BYTES(barcode_len()) bytes per read over PCIe).  The buffers are the library's vectors here;
+    // a pipeline keeps pinned ones and calls sgdx_pack_dense_host / sgdx_match_dense_batch itself.
+    void find_batch_dense(const uint8_t *barcodes, uint64_t n, uint16_t *idx, uint8_t *dist, unsigned slot = 0,
+                          unsigned pack_threads = 1) {
+        std::vector<uint8_t> dense(n * SGDX_DENSE_BYTES((uint32_t)L_) + 8);
+        std::vector<uint32_t> ei(n ? n : 1);
+        std::vector<uint64_t> er(n ? n : 1);
+        uint64_t k = 0;
+        check(sgdx_pack_dense_host(barcodes, n, (uint32_t)L_, dense.data(), ei.data(), er.data(), n, &k, pack_threads), "sgdx_pack_dense_host");
+        check(sgdx_match_dense_batch(h_, slot, dense.data(), n, ei.data(), er.data(), k, idx, dist), "sgdx_match_dense_batch");
+        check(sgdx_sync(h_, slot, nullptr), "sgdx_sync");
+    }
 
   private:
     sgdx_handle *h_ = nullptr;

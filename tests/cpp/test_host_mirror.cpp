@@ -45,6 +45,23 @@ static void test_find_two_samples() {  // matcher.rs:550-622
     }
 }
 
+static void test_record_forms_agree() {  // the same batch as ASCII, compact records and dense records + exceptions
+    for (MatcherKind k : kBoth) {
+        GpuMatcher m(samples_of({"AAAAAAAA", "CCCCGGGG", "ACGTACGT"}, false), k, 1, 1, 1);
+        const std::string reads = "AAAAAAAA" "AAAAAAAT" "CCCCGGGG" "NCCCGGGG" "ACGTACGA" "TTTTTTTT" "ACGTNNGT" "RAAAAAAA" "CCCCGGGC";
+        const uint64_t n = reads.size() / 8;
+        std::vector<uint16_t> a(n), b(n), c(n);
+        std::vector<uint8_t> da(n), db(n), dc(n);
+        std::vector<uint64_t> rec(n);
+        const uint8_t *p = reinterpret_cast<const uint8_t *>(reads.data());
+        m.find_batch(p, n, a.data(), da.data());
+        m.find_batch_compact(p, n, rec.data(), b.data(), db.data());
+        m.find_batch_dense(p, n, c.data(), dc.data());
+        EXPECT(a == b && a == c && da == db && da == dc);
+        EXPECT(a[0] == 0 && da[0] == 0 && a[1] == 0 && da[1] == 1 && a[5] == 3);
+    }
+}
+
 static void test_readme_examples() {  // matcher.rs:682-727: max_mismatches 3, min_delta 1
     struct Case { std::vector<std::string> samples; std::string observed; bool match; size_t dist; };
     const Case cases[] = {
@@ -200,6 +217,7 @@ static void test_unmatched_and_read_structures() {
 int main() {
     try {
         test_find_two_samples();
+        test_record_forms_agree();
         test_readme_examples();
         test_demux_known_answers();
         test_end_to_end_simple();
