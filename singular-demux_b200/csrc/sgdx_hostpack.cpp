@@ -175,34 +175,83 @@ void pack_range(const uint8_t *ascii, uint64_t begin, uint64_t end, uint32_t L, 
     pack_range_scalar(ascii, begin, end, L, out);
 }
 
-// Dense records (include/sgdx.h): compact records of a tile (hot in L1) -> 2 L bits per read + the exception list
-struct DenseExc {
-    std::vector<uint32_t> idx;
-    std::vector<uint64_t> rec;
-};
+#if defined(__x86_64__)
+// Dense records straight from the vector masks of pack_range_avx2: a plain read is b1 | b2 << L, stored with one
+// overlapping 8-byte store; anything else is an exception whose compact record the scalar packer forms.  Handles the
+// reads whose 32-byte load stays inside the buffer and whose 8-byte store stays inside the range ([begin, fast_end)).
+__attribute__((target("avx2"))) void dense_range_avx2(const uint8_t *ascii, uint64_t begin, uint64_t fast_end, uint32_t L, uint8_t *out,
+                                                      uint32_t *idx, uint64_t *rec_out, uint64_t cap, uint64_t *count) {
+    const uint32_t B = SGDX_DENSE_BYTES(L);
+    const __m256i lut = _mm256_setr_epi8(1, 'A', 1, 'C', 'T', 1, 1, 'G', 1, 1, 1, 1, 1, 1, 1, 1,
+                                         1, 'A', 1, 'C', 'T', 1, 1, 'G', 1, 1, 1, 1, 1, 1, 1, 1);
+    const __m256i nib = _mm256_set1_epi8(0x0F);
+    const uint32_t m = (1u << L) - 1u;
+    uint64_t k = *count;
+    const uint8_t *src = ascii + begin * L;
+    uint8_t *dst = out + begin * B;
+    for (uint64_t r = begin; r < fast_end; r++, src += L, dst += B) {
+        const __m256i x = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(src));
+        const uint32_t b1 = (uint32_t)_mm256_movemask_epi8(_mm256_slli_epi16(x, 6));
+        const uint32_t b2 = (uint32_t)_mm256_movemask_epi8(_mm256_slli_epi16(x, 5));
+        const uint32_t ok = (uint32_t)_mm256_movemask_epi8(_mm256_cmpeq_epi8(_mm256_shuffle_epi8(lut, _mm256_and_si256(x, nib)), x));
+        uint64_t d = (uint64_t)(b1 & m) | ((uint64_t)(b2 & m) << L);
+        if (__builtin_expect((ok & m) != m, 0)) {
+            if (k < cap) {  // the compact record, as pack_range_avx2 forms it
+                const uint32_t isn = (uint32_t)_mm256_movemask_epi8(_mm256_cmpeq_epi8(x, _mm256_set1_epi8('N')));
+                const uint32_t inv = ~ok & m;
+                idx[k] = (uint32_t)r;
+                rec_out[k] = (uint64_t)((b1 & ok & m) | (inv & ~isn)) | ((uint64_t)(b2 & ok & m) << kField) | ((uint64_t)inv << (2 * kField));
+            }
+            k++;
+            d = 0;  // placeholder of an exception
+        }
+        memcpy(dst, &d, 8);
+    }
+    *count = k;
+}
+#endif
 
-void dense_range(const uint8_t *ascii, uint64_t begin, uint64_t end, uint32_t L, uint64_t total, uint8_t *out, DenseExc *exc) {
+// Dense records (include/sgdx.h): compact records of a tile (hot in L1) -> 2 L bits per read + the exception list.
+// Exceptions go to idx/rec[*count ...] while there is room (cap); *count keeps counting beyond it.
+void dense_range(const uint8_t *ascii, uint64_t begin, uint64_t end, uint32_t L, uint64_t total, uint8_t *out, uint32_t *idx,
+                 uint64_t *rec_out, uint64_t cap, uint64_t *count) {
     const uint32_t B = SGDX_DENSE_BYTES(L);
     const uint64_t fmask = (1ull << L) - 1ull;
-    uint64_t tile[1024];
-    for (uint64_t r0 = begin; r0 < end; r0 += 1024) {
-        const uint64_t cnt = std::min<uint64_t>(1024, end - r0);
+    uint64_t tile[512];
+#if defined(__x86_64__)
+    static const bool have_avx2 = __builtin_cpu_supports("avx2") && !no_avx2_hook();
+    if (have_avx2) {  // the reads whose 32-byte load and 8-byte store are safe, in one fused pass; the rest below
+        uint64_t fast_end = end > begin + 8 ? end - 8 : begin;
+        const uint64_t bytes = total * L;
+        while (fast_end > begin && (fast_end - 1) * L + 32 > bytes) fast_end--;
+        dense_range_avx2(ascii, begin, fast_end, L, out, idx, rec_out, cap, count);
+        begin = fast_end;
+    }
+#endif
+    uint64_t k = *count;
+    for (uint64_t r0 = begin; r0 < end; r0 += 512) {
+        const uint64_t cnt = std::min<uint64_t>(512, end - r0);
         pack_range(ascii + r0 * L, 0, cnt, L, total - r0, tile);
-        for (uint64_t i = 0; i < cnt; i++) {
-            const uint64_t rec = tile[i], r = r0 + i;
-            uint64_t d = 0;  // placeholder of an exception
-            if (rec >> (2u * kField)) {
-                exc->idx.push_back((uint32_t)r);
-                exc->rec.push_back(rec);
-            } else {
-                d = (rec & fmask) | (((rec >> kField) & fmask) << L);
+        // one 8-byte store per read; what it spills past its B bytes is overwritten by the next reads of this range,
+        // and the last 8 reads of a range are copied exactly (the next range may belong to another thread)
+        const uint64_t fast = std::min<uint64_t>(cnt, end > r0 + 8 ? end - 8 - r0 : 0);  // reads with r + 8 < end
+        uint8_t *dst = out + r0 * B;
+        for (uint64_t i = 0; i < cnt; i++, dst += B) {
+            const uint64_t rec = tile[i];
+            uint64_t d = (rec & fmask) | (((rec >> kField) & fmask) << L);
+            if (__builtin_expect((rec >> (2u * kField)) != 0, 0)) {
+                if (k < cap) {
+                    idx[k] = (uint32_t)(r0 + i);
+                    rec_out[k] = rec;
+                }
+                k++;
+                d = 0;  // placeholder of an exception
             }
-            // one 8-byte store per read; what it spills past its B bytes is overwritten by the next reads of this range,
-            // and the last 8 reads of a range are copied exactly (the next range may belong to another thread)
-            if (r + 8 < end) memcpy(out + r * B, &d, 8);
-            else memcpy(out + r * B, &d, B);
+            if (i < fast) memcpy(dst, &d, 8);
+            else memcpy(dst, &d, B);
         }
     }
+    *count = k;
 }
 
 }  // namespace
@@ -216,33 +265,58 @@ extern "C" int sgdx_pack_dense_host(const uint8_t *ascii, uint64_t n, uint32_t b
         return sgdx::fail(SGDX_EINVAL, "dense records hold 1..%u bases, barcode_len is %u", SGDX_COMPACT_MAX_LEN, barcode_len);
     if (!n_exc || (n && (!ascii || !out_dense))) return sgdx::fail(SGDX_EINVAL, "sgdx_pack_dense_host: null buffer");
     if (n >> 32) return sgdx::fail(SGDX_EINVAL, "sgdx_pack_dense_host: %llu reads, at most 2^32 - 1 per batch", (unsigned long long)n);
+    if (exc_cap && (!exc_index || !exc_record)) return sgdx::fail(SGDX_EINVAL, "sgdx_pack_dense_host: null exception buffer");
     if (threads == 0) threads = 1;
     const uint64_t min_per_thread = 1u << 16;
     const uint64_t nt = std::max<uint64_t>(1, std::min<uint64_t>(threads, (n + min_per_thread - 1) / min_per_thread));
-    std::vector<DenseExc> exc(nt);
-    const uint64_t per = (n + nt - 1) / nt;
-    auto work = [&](uint64_t t) { dense_range(ascii, std::min(n, t * per), std::min(n, (t + 1) * per), barcode_len, n, out_dense, &exc[t]); };
-    std::vector<std::thread> pool;
-    uint64_t started = 1;
-    try {
-        for (; started < nt; started++) pool.emplace_back(work, started);
-    } catch (...) {  // thread limit reached: this thread takes what is left
-    }
-    work(0);
-    for (uint64_t t = started; t < nt; t++) work(t);
-    for (auto &th : pool) th.join();
     uint64_t total = 0;
-    for (const auto &e : exc) total += e.idx.size();
-    *n_exc = total;
-    if (total > exc_cap) return sgdx::fail(SGDX_ENOMEM, "sgdx_pack_dense_host: %llu exceptions, room for %llu", (unsigned long long)total, (unsigned long long)exc_cap);
-    if (total && (!exc_index || !exc_record)) return sgdx::fail(SGDX_EINVAL, "sgdx_pack_dense_host: null exception buffer");
-    uint64_t at = 0;
-    for (const auto &e : exc) {  // thread order = ascending read order
-        if (e.idx.empty()) continue;
-        memcpy(exc_index + at, e.idx.data(), e.idx.size() * sizeof(uint32_t));
-        memcpy(exc_record + at, e.rec.data(), e.rec.size() * sizeof(uint64_t));
-        at += e.idx.size();
+    if (nt == 1) {  // (the batching stage's 1000-read pushes: no allocation, exceptions straight into the caller's arrays)
+        dense_range(ascii, 0, n, barcode_len, n, out_dense, exc_index, exc_record, exc_cap, &total);
+    } else {
+        struct Part {
+            std::vector<uint32_t> idx;
+            std::vector<uint64_t> rec;
+            uint64_t count = 0;
+        };
+        std::vector<Part> parts(nt);
+        const uint64_t per = (n + nt - 1) / nt;
+        auto work = [&](uint64_t t) {
+            const uint64_t b0 = std::min(n, t * per), b1 = std::min(n, (t + 1) * per);
+            Part &p = parts[t];
+            uint64_t cap = std::max<uint64_t>(1024, (b1 - b0) / 16);
+            for (;;) {  // exceptions are few; if a range holds more than its list takes, once more with room for all
+                p.idx.resize(cap);
+                p.rec.resize(cap);
+                p.count = 0;
+                dense_range(ascii, b0, b1, barcode_len, n, out_dense, p.idx.data(), p.rec.data(), cap, &p.count);
+                if (p.count <= cap) break;
+                cap = p.count;
+            }
+        };
+        std::vector<std::thread> pool;
+        uint64_t started = 1;
+        try {
+            for (; started < nt; started++) pool.emplace_back(work, started);
+        } catch (...) {  // thread limit reached: this thread takes what is left
+        }
+        work(0);
+        for (uint64_t t = started; t < nt; t++) work(t);
+        for (auto &th : pool) th.join();
+        for (const auto &p : parts) total += p.count;
+        if (total <= exc_cap) {
+            uint64_t at = 0;
+            for (const auto &p : parts) {  // thread order = ascending read order
+                if (p.count) {
+                    memcpy(exc_index + at, p.idx.data(), p.count * sizeof(uint32_t));
+                    memcpy(exc_record + at, p.rec.data(), p.count * sizeof(uint64_t));
+                }
+                at += p.count;
+            }
+        }
     }
+    *n_exc = total;
+    if (total > exc_cap)
+        return sgdx::fail(SGDX_ENOMEM, "sgdx_pack_dense_host: %llu exceptions, room for %llu", (unsigned long long)total, (unsigned long long)exc_cap);
     return SGDX_OK;
     });
 }
