@@ -492,10 +492,12 @@ def main():
             ers.append(er)
             off += c
         n_exc = sum(len(x) for x in eis)
-        hei, her = alloc_host(n_exc * 4 + 8), alloc_host(n_exc * 8 + 8)
+        esz = 8 if L <= 21 else 16  # compact records, or sgdx_read records above 21 bases
+        hei, her = alloc_host(n_exc * 4 + 8), alloc_host(n_exc * esz + 8)
         if n_exc:
             np.ctypeslib.as_array(C.cast(hei, C.POINTER(C.c_uint32)), (n_exc,))[:] = np.concatenate(eis)
-            np.ctypeslib.as_array(C.cast(her, C.POINTER(C.c_uint64)), (n_exc,))[:] = np.concatenate(ers)
+            np.ctypeslib.as_array(C.cast(her, C.POINTER(C.c_uint8)), (n_exc * esz,))[:] = np.concatenate(
+                [np.ascontiguousarray(x).view(np.uint8).reshape(-1) for x in ers])
         del host_ascii, eis, ers
 
         def one_pass():
@@ -503,7 +505,7 @@ def main():
                 slot = i % nslots
                 if i >= nslots:
                     m.sync(slot)
-                m.submit_dense_ptr(hden.value + o * B, c, hei.value + 4 * e0, her.value + 8 * e0, ne, hidx.value + o * 2,
+                m.submit_dense_ptr(hden.value + o * B, c, hei.value + 4 * e0, her.value + esz * e0, ne, hidx.value + o * 2,
                                    hdist.value + o, slot)
             for s_ in range(nslots):
                 m.sync(s_)
@@ -522,7 +524,7 @@ def main():
         ok = bool(np.array_equal(h_idx[:k], d_idx[:k].cpu().numpy().view(np.uint16)))
         for p_ in (hden, hidx, hdist, hei, her):
             lib.sgdx_free_host(p_)
-        up = n * B + n_exc * 12
+        up = n * B + n_exc * (4 + esz)
         return world * n * steps / float(t2.item()), up, n * 3, ok, n_exc
 
     e2e, e2e_ascii = None, None
@@ -540,18 +542,18 @@ def main():
                "timing": f"wall clock around {call}(host buffers)+sgdx_sync, max over ranks",
                "matches_device_resident_result": ok, "copy_ceiling": ceil,
                "frac_of_copy_ceiling": v / ceil["reads_per_s"], "numa": numa}
-        if compact_ok and keep_ascii and side:
+        if L <= 32 and keep_ascii and side:
             # the PCIe form of the same records: 2 bits per base + an exception list for the reads with a no-call
             vd, upd, downd, okd, n_exc = e2e_dense(e2e_steps)
             ceild = copy_ceiling(upd / n, e2e_steps)
             e2e = {"value": vd, "unit": UNIT, "h2d_bytes_per_step": upd, "d2h_bytes_per_step": downd, "steps": e2e_steps,
                    "chunk_reads": chunk, "slots": nslots, "call": "sgdx_match_dense_batch",
                    "input": f"dense records in pinned host memory: {sg.dense_bytes(L)} bytes per read (2 bits per base) + "
-                            f"{n_exc} exceptions of 12 bytes (reads with a no-call or a foreign byte), include/sgdx.h",
+                            f"{n_exc} exceptions of {12 if L <= 21 else 20} bytes (reads with a no-call or a foreign byte), include/sgdx.h",
                    "timing": "wall clock around sgdx_match_dense_batch(host buffers)+sgdx_sync, max over ranks",
                    "matches_device_resident_result": okd, "copy_ceiling": ceild,
                    "frac_of_copy_ceiling": vd / ceild["reads_per_s"], "numa": numa,
-                   "compact_records": e2e}
+                   "compact_records" if compact_ok else "packed_records": e2e}
         if keep_ascii and side:
             v, up, down, ok = e2e_measure(m.submit_ptr, d_in, L, np.uint8, e2e_steps)
             e2e_ascii = {"value": v, "unit": UNIT, "h2d_bytes_per_step": up, "d2h_bytes_per_step": down,

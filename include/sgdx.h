@@ -147,21 +147,24 @@ int sgdx_match_packed_batch(sgdx_handle *h, uint32_t slot, const sgdx_read *reco
  * are served through the 16-byte packed form of the general kernels.  Bits above barcode_len in any plane, and
  * bit 63, are ignored.  The unmatched table is keyed from the records (see above for bytes outside A/C/G/T/N). */
 #define SGDX_COMPACT_MAX_LEN 21u
-/* Dense records: the compact records as they cross PCIe in batches from the host -- 2 bits per base and nothing else,
- * SGDX_DENSE_BYTES(barcode_len) bytes per read (5 bytes at 20 bases instead of 8): bits 0..L-1 the lo plane, bits
- * L..2L-1 the hi plane, little endian, read r at byte r * SGDX_DENSE_BYTES(L).  The invalid plane travels as a list of
- * exceptions: a read that is not made of A/C/G/T only (a no-call, any other byte: about 2 % of real reads) has an
- * arbitrary placeholder in the dense stream and an entry (read index, compact record) in the list.  On the device a
- * streaming kernel rebuilds the compact records (sgdx_unpack_dense + sgdx_patch_exceptions) and the assignment runs on
- * those: same results as every other entry point.
+/* Dense records: the packed records as they cross PCIe in batches from the host -- 2 bits per base and nothing else,
+ * SGDX_DENSE_BYTES(barcode_len) bytes per read (5 bytes at 20 bases instead of 8, 6 at 24 instead of 16), for
+ * barcode_len <= SGDX_MAX_PACKED_LEN: bits 0..L-1 the lo plane, bits L..2L-1 the hi plane, little endian, read r at
+ * byte r * SGDX_DENSE_BYTES(L).  The invalid plane travels as a list of exceptions: a read that is not made of A/C/G/T
+ * only (a no-call, any other byte: about 2 % of real reads) has an arbitrary placeholder in the dense stream and an
+ * entry (read index, record) in the list -- the record is a 64-bit compact record for barcode_len <=
+ * SGDX_COMPACT_MAX_LEN and a 16-byte sgdx_read above (SGDX_DENSE_EXC_BYTES).  On the device a streaming kernel rebuilds
+ * the packed records (sgdx_unpack_dense + sgdx_patch_exceptions) and the assignment runs on those: same results as
+ * every other entry point.
  * sgdx_pack_dense_host: out_dense = n * SGDX_DENSE_BYTES(L) bytes; exceptions in ascending read order; if there are
  * more than exc_cap of them the call fails with SGDX_ENOMEM and *n_exc says how many there are.
  * sgdx_match_dense_batch: sgdx_match_batch for such a batch (n < 2^32). */
 #define SGDX_DENSE_BYTES(barcode_len) ((2u * (barcode_len) + 7u) / 8u)
+#define SGDX_DENSE_EXC_BYTES(barcode_len) ((barcode_len) <= SGDX_COMPACT_MAX_LEN ? 8u : 16u)
 int sgdx_pack_dense_host(const uint8_t *barcodes_ascii, uint64_t n, uint32_t barcode_len, uint8_t *out_dense,
-                         uint32_t *exc_index, uint64_t *exc_record, uint64_t exc_cap, uint64_t *n_exc, uint32_t threads);
+                         uint32_t *exc_index, void *exc_record, uint64_t exc_cap, uint64_t *n_exc, uint32_t threads);
 int sgdx_match_dense_batch(sgdx_handle *h, uint32_t slot, const uint8_t *dense, uint64_t n, const uint32_t *exc_index,
-                           const uint64_t *exc_record, uint64_t n_exc, uint16_t *out_idx, uint8_t *out_dist);
+                           const void *exc_record, uint64_t n_exc, uint16_t *out_idx, uint8_t *out_dist);
 int sgdx_pack_compact_host(const uint8_t *barcodes_ascii, uint64_t n, uint32_t barcode_len, uint64_t *out_records,
                            uint32_t threads /* 0 -> 1 */);
 int sgdx_pack_compact_device(sgdx_handle *h, uint32_t slot, const uint8_t *d_barcodes_ascii, uint64_t n,

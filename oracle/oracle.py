@@ -518,7 +518,7 @@ def dense_records(reads: np.ndarray):
     exception compact records, mask of the plain reads).  Checker of sgdx_pack_dense_host."""
     reads = np.asarray(reads, dtype=np.uint8)
     n, L = reads.shape
-    assert L <= 21
+    assert L <= 32  # (above 21 bases the exceptions are sgdx_read records, see packed_records)
     B = (2 * L + 7) // 8
     ok = np.isin(reads, np.frombuffer(b"ACGT", dtype=np.uint8))
     plain = ok.all(axis=1)
@@ -531,7 +531,11 @@ def dense_records(reads: np.ndarray):
     for b in range(B):
         dense[:, b] = ((x >> np.uint64(8 * b)) & np.uint64(0xFF)).astype(np.uint8)
     exc = np.nonzero(~plain)[0].astype(np.uint32)
-    return dense, exc, compact_records(reads[exc]) if len(exc) else np.zeros(0, np.uint64), plain
+    if L <= 21:
+        recs = compact_records(reads[exc]) if len(exc) else np.zeros(0, np.uint64)
+    else:
+        recs = packed_records(reads[exc]) if len(exc) else np.zeros((0, 4), np.uint32)
+    return dense, exc, recs, plain
 
 
 def packed_records(reads: np.ndarray) -> np.ndarray:

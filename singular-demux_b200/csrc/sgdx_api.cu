@@ -850,17 +850,21 @@ extern "C" int sgdx_match_compact_batch(sgdx_handle *h, uint32_t slot, const uin
 
 // sgdx_match_batch for a host batch of dense records + exception list (include/sgdx.h): 2 L bits per read over PCIe
 extern "C" int sgdx_match_dense_batch(sgdx_handle *h, uint32_t slot, const uint8_t *dense, uint64_t n, const uint32_t *exc_index,
-                                      const uint64_t *exc_record, uint64_t n_exc, uint16_t *out_idx, uint8_t *out_dist) {
+                                      const void *exc_record, uint64_t n_exc, uint16_t *out_idx, uint8_t *out_dist) {
     return sgdx::guarded("sgdx_match_dense_batch", [&]() -> int {
     if (int rc = check_slot(h, slot)) return rc;
     const uint32_t L = h->cfg.barcode_len;
-    if (L > kCompactMaxLen) return fail(SGDX_EINVAL, "dense records hold at most %u bases, barcode_len is %u", kCompactMaxLen, L);
+    if (L > SGDX_MAX_PACKED_LEN) return fail(SGDX_EINVAL, "dense records hold at most %u bases, barcode_len is %u", SGDX_MAX_PACKED_LEN, L);
     if (n && (!dense || !out_idx)) return fail(SGDX_EINVAL, "sgdx_match_dense_batch: null buffer");
     if (n_exc && (!exc_index || !exc_record)) return fail(SGDX_EINVAL, "sgdx_match_dense_batch: null exception list");
     if (n >> 32 || n_exc > n) return fail(SGDX_EINVAL, "sgdx_match_dense_batch: %llu reads / %llu exceptions", (unsigned long long)n, (unsigned long long)n_exc);
     CU(cudaSetDevice(h->cfg.device));
     Slot &s = h->slots[slot];
+    const bool wide = L > kCompactMaxLen;  // 16-byte records on the device, 16-byte exception records
+    const size_t esz = SGDX_DENSE_EXC_BYTES(L);
     if (int rc = ensure_capacity(s, n, L)) return rc;
+    if (wide)
+        if (int rc = ensure_packed_scratch(s, n)) return rc;
     const uint64_t bytes = n * SGDX_DENSE_BYTES(L);
     if (bytes + 64 > s.dense_cap || n_exc > s.exc_cap) {
         CU(cudaStreamSynchronize(s.stream));
@@ -880,7 +884,7 @@ extern "C" int sgdx_match_dense_batch(sgdx_handle *h, uint32_t slot, const uint8
             s.exc_cap = 0;
             const uint64_t cap = n_exc + n_exc / 4 + 1024;
             CU(cudaMalloc(&s.d_exc_idx, cap * sizeof(uint32_t)));
-            CU(cudaMalloc(&s.d_exc_rec, cap * sizeof(uint64_t)));
+            CU(cudaMalloc(&s.d_exc_rec, cap * 16u));
             s.exc_cap = cap;
         }
     }
@@ -889,12 +893,19 @@ extern "C" int sgdx_match_dense_batch(sgdx_handle *h, uint32_t slot, const uint8
         CU(cudaMemcpyAsync(s.d_dense, dense, bytes, cudaMemcpyHostToDevice, s.stream));
         if (n_exc) {
             CU(cudaMemcpyAsync(s.d_exc_idx, exc_index, n_exc * sizeof(uint32_t), cudaMemcpyHostToDevice, s.stream));
-            CU(cudaMemcpyAsync(s.d_exc_rec, exc_record, n_exc * sizeof(uint64_t), cudaMemcpyHostToDevice, s.stream));
+            CU(cudaMemcpyAsync(s.d_exc_rec, exc_record, n_exc * esz, cudaMemcpyHostToDevice, s.stream));
         }
-        CU(launch_unpack_dense(s.d_dense, n, L, s.d_exc_idx, s.d_exc_rec, n_exc, d_rec, h->sms, s.stream));
+        if (wide)
+            CU(launch_unpack_dense_wide(s.d_dense, n, L, s.d_exc_idx, static_cast<const uint4 *>(s.d_exc_rec), n_exc, s.d_cexp, h->sms, s.stream));
+        else
+            CU(launch_unpack_dense(s.d_dense, n, L, s.d_exc_idx, static_cast<const uint64_t *>(s.d_exc_rec), n_exc, d_rec, h->sms, s.stream));
         h->launches.fetch_add(n_exc ? 2 : 1);
     }
-    if (int rc = run_compact(h, s, d_rec, n, s.d_idx, s.d_dist)) return rc;
+    if (wide) {
+        if (int rc = run_kernels(h, s, nullptr, s.d_cexp, n, s.d_idx, s.d_dist)) return rc;
+    } else {
+        if (int rc = run_compact(h, s, d_rec, n, s.d_idx, s.d_dist)) return rc;
+    }
     if (n) {
         CU(cudaMemcpyAsync(out_idx, s.d_idx, n * sizeof(uint16_t), cudaMemcpyDeviceToHost, s.stream));
         if (out_dist) CU(cudaMemcpyAsync(out_dist, s.d_dist, n, cudaMemcpyDeviceToHost, s.stream));
@@ -1151,7 +1162,7 @@ struct sgdx_batcher {
     bool dense = false;             // ... or dense records (2 bits per base) + the exception lists below
     std::vector<uint8_t *> in;      // one pinned input buffer per slot
     std::vector<uint32_t *> exc_idx;  // dense mode: pinned exception lists per slot (room for every read of a batch)
-    std::vector<uint64_t *> exc_rec;
+    std::vector<uint8_t *> exc_rec;   //   (SGDX_DENSE_EXC_BYTES per entry)
     uint64_t n_exc = 0;             // exceptions of the batch being filled
     std::vector<bool> slot_busy;    // slot has an unsynced batch
     uint32_t cur = 0;               // slot being filled
@@ -1187,8 +1198,10 @@ extern "C" int sgdx_batcher_set_compact(sgdx_batcher *b, int on) {
     return sgdx::guarded("sgdx_batcher_set_compact", [&]() -> int {
     if (!b) return fail(SGDX_EINVAL, "null batcher");
     if (b->fill || !b->inflight.empty()) return fail(SGDX_ESTATE, "sgdx_batcher_set_compact: batches are in flight");
-    if (on && b->L > kCompactMaxLen)
+    if (on == 1 && b->L > kCompactMaxLen)
         return fail(SGDX_EINVAL, "compact records hold at most %u bases, barcode_len is %u", kCompactMaxLen, b->L);
+    if (on == 2 && b->L > SGDX_MAX_PACKED_LEN)
+        return fail(SGDX_EINVAL, "dense records hold at most %u bases, barcode_len is %u", SGDX_MAX_PACKED_LEN, b->L);
     if (on == 2 && b->exc_idx.empty()) {  // dense records: the exception lists, worst case every read
         if (b->batch_reads >> 32) return fail(SGDX_EINVAL, "dense records: batches of at most 2^32 - 1 reads");
         b->exc_idx.assign(b->in.size(), nullptr);
@@ -1197,8 +1210,8 @@ extern "C" int sgdx_batcher_set_compact(sgdx_batcher *b, int on) {
             void *q = nullptr;
             if (int rc = sgdx_alloc_host(b->batch_reads * sizeof(uint32_t), &q)) return rc;
             b->exc_idx[i] = static_cast<uint32_t *>(q);
-            if (int rc = sgdx_alloc_host(b->batch_reads * sizeof(uint64_t), &q)) return rc;
-            b->exc_rec[i] = static_cast<uint64_t *>(q);
+            if (int rc = sgdx_alloc_host(b->batch_reads * SGDX_DENSE_EXC_BYTES(b->L), &q)) return rc;
+            b->exc_rec[i] = static_cast<uint8_t *>(q);
         }
     }
     b->compact = on == 1;
@@ -1287,7 +1300,7 @@ extern "C" int sgdx_batcher_push_n(sgdx_batcher *b, const uint8_t *ascii, uint64
             uint64_t k = 0;
             uint32_t *ei = b->exc_idx[b->cur] + b->n_exc;
             if (int rc = sgdx_pack_dense_host(ascii, take, b->L, b->in[b->cur] + b->fill * SGDX_DENSE_BYTES(b->L), ei,
-                                              b->exc_rec[b->cur] + b->n_exc, b->batch_reads - b->n_exc, &k, 1))
+                                              b->exc_rec[b->cur] + b->n_exc * SGDX_DENSE_EXC_BYTES(b->L), b->batch_reads - b->n_exc, &k, 1))
                 return rc;
             for (uint64_t e = 0; e < k; e++) ei[e] += (uint32_t)b->fill;  // read numbers of the batch, not of this push
             b->n_exc += k;

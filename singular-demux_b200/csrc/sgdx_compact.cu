@@ -63,6 +63,34 @@ __global__ void __launch_bounds__(256) sgdx_unpack_dense(const uint32_t *__restr
     }
 }
 
+// the same for barcodes of 22..32 bases: dense records -> 16-byte sgdx_read records {lo, hi, 0, 0}
+template <uint32_t B>
+__global__ void __launch_bounds__(256) sgdx_unpack_dense_wide(const uint32_t *__restrict__ dense, uint64_t n, uint32_t L,
+                                                              uint4 *__restrict__ out) {
+    const uint64_t groups = (n + 3u) / 4u, fmask = L >= 32u ? 0xFFFFFFFFull : (1ull << L) - 1ull;
+    for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t w[B + 2];
+#pragma unroll
+        for (uint32_t i = 0; i < B; i++) w[i] = __ldg(dense + g * B + i);
+        w[B] = w[B + 1] = 0u;
+#pragma unroll
+        for (uint32_t k = 0; k < 4; k++) {
+            const uint32_t o = 8u * k * B, i = o >> 5, sh = o & 31u;  // compile-time after unrolling
+            const uint32_t x0 = __funnelshift_r(w[i], w[i + 1], sh), x1 = __funnelshift_r(w[i + 1], w[i + 2], sh);
+            const uint64_t x = (uint64_t)x0 | ((uint64_t)x1 << 32);
+            if (4u * g + k < n) out[4u * g + k] = make_uint4((uint32_t)(x & fmask), (uint32_t)((x >> L) & fmask), 0u, 0u);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) sgdx_patch_exceptions_wide(const uint32_t *__restrict__ idx, const uint4 *__restrict__ rec,
+                                                                  uint64_t n_exc, uint64_t n, uint4 *__restrict__ out) {
+    for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n_exc; e += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t r = __ldg(idx + e);
+        if (r < n) out[r] = __ldg(rec + e);
+    }
+}
+
 // the reads that are not plain A/C/G/T: their compact records over the placeholders
 __global__ void __launch_bounds__(256) sgdx_patch_exceptions(const uint32_t *__restrict__ idx, const uint64_t *__restrict__ rec,
                                                              uint64_t n_exc, uint64_t n, uint64_t *__restrict__ out) {
@@ -88,6 +116,22 @@ cudaError_t launch_unpack_dense(const uint8_t *dense, uint64_t n, uint32_t L, co
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess || n_exc == 0) return e;
     sgdx_patch_exceptions<<<persistent_grid(n_exc, 256, sms, 8), 256, 0, stream>>>(exc_idx, exc_rec, n_exc, n, out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_unpack_dense_wide(const uint8_t *dense, uint64_t n, uint32_t L, const uint32_t *exc_idx, const uint4 *exc_rec,
+                                     uint64_t n_exc, uint4 *out, int sms, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(dense);
+    const uint32_t grid = persistent_grid((n + 3u) / 4u, 256, sms, 8);
+    switch ((2u * L + 7u) / 8u) {
+        case 6: sgdx_unpack_dense_wide<6><<<grid, 256, 0, stream>>>(w, n, L, out); break;
+        case 7: sgdx_unpack_dense_wide<7><<<grid, 256, 0, stream>>>(w, n, L, out); break;
+        default: sgdx_unpack_dense_wide<8><<<grid, 256, 0, stream>>>(w, n, L, out); break;
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess || n_exc == 0) return e;
+    sgdx_patch_exceptions_wide<<<persistent_grid(n_exc, 256, sms, 8), 256, 0, stream>>>(exc_idx, exc_rec, n_exc, n, out);
     return cudaGetLastError();
 }
 

@@ -46,7 +46,7 @@ struct Slot {
     uint8_t *d_dense = nullptr;                 // dense records of a batch as they arrive (sgdx_match_dense_batch)
     uint64_t dense_cap = 0;                     // bytes
     uint32_t *d_exc_idx = nullptr;              // ... and its exception list
-    uint64_t *d_exc_rec = nullptr;
+    void *d_exc_rec = nullptr;                  // (8- or 16-byte records: SGDX_DENSE_EXC_BYTES)
     uint64_t exc_cap = 0;                       // entries
 };
 

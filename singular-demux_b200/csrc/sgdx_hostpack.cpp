@@ -211,11 +211,40 @@ __attribute__((target("avx2"))) void dense_range_avx2(const uint8_t *ascii, uint
 }
 #endif
 
-// Dense records (include/sgdx.h): compact records of a tile (hot in L1) -> 2 L bits per read + the exception list.
-// Exceptions go to idx/rec[*count ...] while there is room (cap); *count keeps counting beyond it.
+// Dense records (include/sgdx.h): packed records of a tile (hot in L1) -> 2 L bits per read + the exception list.
+// Exceptions go to idx/rec[*count ...] while there is room (cap); *count keeps counting beyond it.  Records of the
+// list: compact 64-bit records up to 21 bases, 16-byte sgdx_read records above.
 void dense_range(const uint8_t *ascii, uint64_t begin, uint64_t end, uint32_t L, uint64_t total, uint8_t *out, uint32_t *idx,
-                 uint64_t *rec_out, uint64_t cap, uint64_t *count) {
+                 void *rec_any, uint64_t cap, uint64_t *count) {
     const uint32_t B = SGDX_DENSE_BYTES(L);
+    if (L > kField) {  // 22..32 bases: from the 16-byte records
+        sgdx_read *rec_out = static_cast<sgdx_read *>(rec_any);
+        sgdx_read tile[256];
+        uint64_t k = *count;
+        for (uint64_t r0 = begin; r0 < end; r0 += 256) {
+            const uint64_t cnt = std::min<uint64_t>(256, end - r0);
+            planes_range(ascii + r0 * L, 0, cnt, L, total - r0, tile);
+            const uint64_t fast = std::min<uint64_t>(cnt, end > r0 + 8 ? end - 8 - r0 : 0);  // reads with r + 8 < end
+            uint8_t *dst = out + r0 * B;
+            for (uint64_t i = 0; i < cnt; i++, dst += B) {
+                const sgdx_read v = tile[i];
+                uint64_t d = (uint64_t)v.lo | ((uint64_t)v.hi << L);
+                if (__builtin_expect((v.nmask | v.xmask) != 0u, 0)) {
+                    if (k < cap) {
+                        idx[k] = (uint32_t)(r0 + i);
+                        rec_out[k] = v;
+                    }
+                    k++;
+                    d = 0;
+                }
+                if (i < fast || B == 8) memcpy(dst, &d, 8);
+                else memcpy(dst, &d, B);
+            }
+        }
+        *count = k;
+        return;
+    }
+    uint64_t *rec_out = static_cast<uint64_t *>(rec_any);
     const uint64_t fmask = (1ull << L) - 1ull;
     uint64_t tile[512];
 #if defined(__x86_64__)
@@ -257,12 +286,13 @@ void dense_range(const uint8_t *ascii, uint64_t begin, uint64_t end, uint32_t L,
 }  // namespace
 
 extern "C" int sgdx_pack_dense_host(const uint8_t *ascii, uint64_t n, uint32_t barcode_len, uint8_t *out_dense,
-                                    uint32_t *exc_index, uint64_t *exc_record, uint64_t exc_cap, uint64_t *n_exc,
+                                    uint32_t *exc_index, void *exc_record, uint64_t exc_cap, uint64_t *n_exc,
                                     uint32_t threads) {
     return sgdx::guarded("sgdx_pack_dense_host", [&]() -> int {
     if (n_exc) *n_exc = 0;
-    if (barcode_len < 1 || barcode_len > SGDX_COMPACT_MAX_LEN)
-        return sgdx::fail(SGDX_EINVAL, "dense records hold 1..%u bases, barcode_len is %u", SGDX_COMPACT_MAX_LEN, barcode_len);
+    if (barcode_len < 1 || barcode_len > SGDX_MAX_PACKED_LEN)
+        return sgdx::fail(SGDX_EINVAL, "dense records hold 1..%u bases, barcode_len is %u", SGDX_MAX_PACKED_LEN, barcode_len);
+    const size_t esz = SGDX_DENSE_EXC_BYTES(barcode_len);
     if (!n_exc || (n && (!ascii || !out_dense))) return sgdx::fail(SGDX_EINVAL, "sgdx_pack_dense_host: null buffer");
     if (n >> 32) return sgdx::fail(SGDX_EINVAL, "sgdx_pack_dense_host: %llu reads, at most 2^32 - 1 per batch", (unsigned long long)n);
     if (exc_cap && (!exc_index || !exc_record)) return sgdx::fail(SGDX_EINVAL, "sgdx_pack_dense_host: null exception buffer");
@@ -275,7 +305,7 @@ extern "C" int sgdx_pack_dense_host(const uint8_t *ascii, uint64_t n, uint32_t b
     } else {
         struct Part {
             std::vector<uint32_t> idx;
-            std::vector<uint64_t> rec;
+            std::vector<uint8_t> rec;  // esz bytes per exception
             uint64_t count = 0;
         };
         std::vector<Part> parts(nt);
@@ -286,7 +316,7 @@ extern "C" int sgdx_pack_dense_host(const uint8_t *ascii, uint64_t n, uint32_t b
             uint64_t cap = std::max<uint64_t>(1024, (b1 - b0) / 16);
             for (;;) {  // exceptions are few; if a range holds more than its list takes, once more with room for all
                 p.idx.resize(cap);
-                p.rec.resize(cap);
+                p.rec.resize(cap * esz);
                 p.count = 0;
                 dense_range(ascii, b0, b1, barcode_len, n, out_dense, p.idx.data(), p.rec.data(), cap, &p.count);
                 if (p.count <= cap) break;
@@ -308,7 +338,7 @@ extern "C" int sgdx_pack_dense_host(const uint8_t *ascii, uint64_t n, uint32_t b
             for (const auto &p : parts) {  // thread order = ascending read order
                 if (p.count) {
                     memcpy(exc_index + at, p.idx.data(), p.count * sizeof(uint32_t));
-                    memcpy(exc_record + at, p.rec.data(), p.count * sizeof(uint64_t));
+                    memcpy(static_cast<uint8_t *>(exc_record) + at * esz, p.rec.data(), p.count * esz);
                 }
                 at += p.count;
             }

@@ -26,6 +26,8 @@ cudaError_t launch_pack_compact(const uint8_t *reads, uint64_t n, uint32_t L, ui
 // `dense` 4-byte aligned and padded by 32 bytes, `out` 16-byte aligned
 cudaError_t launch_unpack_dense(const uint8_t *dense, uint64_t n, uint32_t L, const uint32_t *exc_idx, const uint64_t *exc_rec,
                                 uint64_t n_exc, uint64_t *out, int sms, cudaStream_t stream);
+cudaError_t launch_unpack_dense_wide(const uint8_t *dense, uint64_t n, uint32_t L, const uint32_t *exc_idx, const uint4 *exc_rec,
+                                     uint64_t n_exc, uint4 *out, int sms, cudaStream_t stream);  // 22..32 bases -> sgdx_read records
 cudaError_t launch_expand_compact(const uint64_t *in, uint64_t n, uint32_t L, uint4 *out, int sms, cudaStream_t stream);
 
 // Perfect-hash kernel for packed records (sgdx_ph.cu).  Key set K = every A/C/G/T string within `radius`

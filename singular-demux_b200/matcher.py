@@ -115,14 +115,15 @@ def dense_bytes(barcode_len: int) -> int:
 
 
 def pack_dense_host(barcodes: np.ndarray, threads: int = 1, exc_cap: Optional[int] = None):
-    """sgdx_pack_dense_host: (n, L) ASCII barcodes, L <= 21 -> (dense bytes [n * dense_bytes(L)], exception read
-    indices [k] uint32, their compact records [k] uint64).  exc_cap: room for exceptions (default: every read)."""
+    """sgdx_pack_dense_host: (n, L) ASCII barcodes, L <= 32 -> (dense bytes [n * dense_bytes(L)], exception read
+    indices [k] uint32, their records: compact records [k] uint64 for L <= 21, sgdx_read records [k, 4] uint32 above).
+    exc_cap: room for exceptions (default: every read)."""
     arr = np.ascontiguousarray(barcodes, dtype=np.uint8)
     n, L = arr.shape
     cap = n if exc_cap is None else int(exc_cap)
     dense = np.empty(n * dense_bytes(L), dtype=np.uint8)
     eidx = np.empty(max(cap, 1), dtype=np.uint32)
-    erec = np.empty(max(cap, 1), dtype=np.uint64)
+    erec = np.empty(max(cap, 1), dtype=np.uint64) if L <= 21 else np.empty((max(cap, 1), 4), dtype=np.uint32)
     k = C.c_uint64(0)
     check(lib().sgdx_pack_dense_host(arr.ctypes.data, n, L, dense.ctypes.data, eidx.ctypes.data, erec.ctypes.data, cap,
                                      C.byref(k), threads), "sgdx_pack_dense_host")
@@ -242,12 +243,12 @@ class GpuMatcher:
         return idx, dist
 
     def find_batch_dense(self, barcodes, slot: int = 0, threads: int = 1) -> Tuple[np.ndarray, np.ndarray]:
-        """find_batch through dense records: 2 bits per base + an exception list over PCIe (barcode_len <= 21)."""
+        """find_batch through dense records: 2 bits per base + an exception list over PCIe (barcode_len <= 32)."""
         dense, eidx, erec = pack_dense_host(as_barcode_array(barcodes, self.barcode_len), threads)
         n = dense.size // dense_bytes(self.barcode_len)
         idx = np.empty(n, dtype=np.uint16)
         dist = np.empty(n, dtype=np.uint8)
-        self.submit_dense_ptr(dense.ctypes.data, n, eidx.ctypes.data, erec.ctypes.data, eidx.size, idx.ctypes.data,
+        self.submit_dense_ptr(dense.ctypes.data, n, eidx.ctypes.data, erec.ctypes.data, len(eidx), idx.ctypes.data,
                               dist.ctypes.data, slot)
         self.sync(slot)
         return idx, dist

@@ -50,6 +50,27 @@ int main() {
                 free(ei);
                 free(er);
                 free(o8);
+            } else {  // 22..32 bases: dense records against the 16-byte records, exceptions are 16-byte records
+                const uint32_t B = SGDX_DENSE_BYTES(L);
+                uint8_t *od = (uint8_t *)malloc(n * B ? n * B : 1);
+                uint32_t *ei = (uint32_t *)malloc(n ? n * 4 : 1);
+                sgdx_read *er = (sgdx_read *)malloc(n ? n * sizeof(sgdx_read) : 1);
+                uint64_t ne = 0, e = 0;
+                if (sgdx_pack_dense_host(in, n, L, od, ei, er, n, &ne, 3)) return 8;
+                for (uint64_t r = 0; r < n; r++) {
+                    if (o16[r].nmask | o16[r].xmask) {
+                        if (e >= ne || ei[e] != r || memcmp(&er[e], &o16[r], sizeof(sgdx_read))) return 9;
+                        e++;
+                    } else {
+                        uint64_t d = 0;
+                        memcpy(&d, od + r * B, B);
+                        if (d != ((uint64_t)o16[r].lo | ((uint64_t)o16[r].hi << L))) return 10;
+                    }
+                }
+                if (e != ne) return 11;
+                free(od);
+                free(ei);
+                free(er);
             }
             free(o16);
             free(in);

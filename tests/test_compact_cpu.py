@@ -144,7 +144,7 @@ def test_host_packers_are_clean_under_asan(tmp_path):
 
 
 
-@pytest.mark.parametrize("L", [1, 3, 4, 8, 12, 16, 20, 21])
+@pytest.mark.parametrize("L", [1, 3, 4, 8, 12, 16, 20, 21, 22, 24, 25, 28, 29, 32])
 def test_host_packer_of_dense_records_equals_the_format_definition(L):
     """sgdx_pack_dense_host: 2 bits per base for the plain reads, (index, compact record) for the others, in ascending
     read order, for any thread count; the exception room is checked."""
@@ -165,4 +165,4 @@ def test_host_packer_of_dense_records_equals_the_format_definition(L):
     d0, i0, r0 = sg.pack_dense_host(arr[:0])
     assert d0.size == 0 and i0.size == 0
     with pytest.raises(sg.SgdxError):
-        sg.pack_dense_host(np.full((4, 22), ord("A"), dtype=np.uint8))
+        sg.pack_dense_host(np.full((4, 33), ord("A"), dtype=np.uint8))

@@ -234,7 +234,7 @@ def test_dense_records_give_the_same_results(S, L, i1):
             i3, d3 = st.matcher.find_batch_dense(part)
             assert np.array_equal(i3, want["idx"][sel][:5001]) and np.array_equal(d3, want["dist"][sel][:5001])
         st.close()
-    long = sg.CachedHammingDistanceMatcher([b"ACGT" * 6, b"TTGA" * 6], 1, 2, 1)
+    long = sg.CachedHammingDistanceMatcher([b"ACGT" * 10, b"TTGA" * 10], 1, 2, 1)  # 40 bases: ASCII entry points only
     with pytest.raises(sg.SgdxError):
         long.submit_dense_ptr(0, 0, 0, 0, 0, 0, 0)
     long.close()

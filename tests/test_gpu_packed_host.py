@@ -156,3 +156,42 @@ def test_c2_at_two_mismatches_uses_radius_one_and_the_seed_index():
             assert np.array_equal(met.per_sample_array(), want["per_sample"])
             assert met.sample_barcode_hop_tracker.count_tracker == want["hops"]
             st.close()
+
+
+@pytest.mark.parametrize("S,L,i1", [(300, 24, 12), (50, 32, 16), (64, 22, 11), (40, 29, 0), (1536, 24, 12)])
+def test_dense_records_of_long_barcodes_give_the_same_results(S, L, i1):
+    """22..32 bases as dense records (6..8 bytes per read over PCIe instead of 16) + an exception list of 16-byte records:
+    the device rebuilds the sgdx_read records and runs the same kernels.  Oracle parity, ragged sizes, no exceptions,
+    nothing but exceptions."""
+    rng = np.random.default_rng(S * 17 + L)
+    n = 50_003
+    if S == 1536:
+        w = sg.synth.C3
+        table = w.table()
+    else:
+        w = sg.synth.Workload("r", S, L, i1, 1, 2, n_reads=n, table_seed=int(rng.integers(1 << 30)), read_seed=int(rng.integers(1 << 30)),
+                              p_true=0.80, p_hop=0.08 if i1 else 0.0, p_sub=0.03, p_n=0.02, p_x=0.004, min_dist=2)
+        table = w.table()
+    import dataclasses
+    reads = dataclasses.replace(w, p_n=0.02, p_x=0.004).reads_host(0, n, table)
+    il = w.index_lengths
+    for kind in (sg.MatcherKind.CachedHammingDistance, sg.MatcherKind.PreCompute):
+        M, D = (3, 1) if S == 1536 else (1, 2)
+        m = CLS[kind]([bytes(t) for t in table], M, D, 1, index_lengths=il)
+        cfg = orc.Config(len(table), L, M, D, 1, -1, ORC_KIND[kind], il[0] if il else 0, il[1] if il else 0)
+        want = orc.COracle(cfg, [bytes(t) for t in table], force_closed_form=True).run(reads, threads=8, use_cache=True)
+        idx, dist = m.find_batch_dense(reads, threads=2)
+        assert np.array_equal(idx, want["idx"]) and np.array_equal(dist, want["dist"])
+        per, totals = m.counters()
+        assert np.array_equal(per, want["per_sample"]) and totals["total_templates"] == n
+        if il:
+            assert m.hop_counts() == want["hops"]
+        for k in (0, 1, 3, 5, 4097):
+            i2, d2 = m.find_batch_dense(reads[:k], slot=1)
+            assert np.array_equal(i2, want["idx"][:k]) and np.array_equal(d2, want["dist"][:k])
+        plain = np.isin(reads, LETTERS).all(axis=1)
+        for sel in (plain, ~plain):
+            part = np.ascontiguousarray(reads[sel][:3001])
+            i3, d3 = m.find_batch_dense(part)
+            assert np.array_equal(i3, want["idx"][sel][:3001]) and np.array_equal(d3, want["dist"][sel][:3001])
+        m.close()
