@@ -152,3 +152,20 @@ def test_headers_are_plain_c(tmp_path):
     r = subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
                         "-fsyntax-only", str(src)], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+
+
+def test_every_c_entry_point_runs_behind_the_exception_guard():
+    """include/sgdx.h promises that no exception crosses the boundary: every `extern "C" int` function of the library
+    wraps its body in sgdx::guarded (csrc/sgdx_guard.h)."""
+    import glob
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    total = 0
+    for path in glob.glob(os.path.join(root, "singular-demux_b200", "csrc", "*.c*")):
+        src = open(path).read()
+        for m in re.finditer(r'^extern "C" int (\w+)\(', src, re.M):
+            body_at = src.index(") {\n", m.start()) + 4
+            assert src[body_at:body_at + 200].lstrip().startswith("return sgdx::guarded("), (os.path.basename(path), m.group(1))
+            total += 1
+    assert total >= 40
