@@ -438,6 +438,58 @@ def test_routing_of_skewed_index_arrays(S, kind):
     m.close()
 
 
+@pytest.mark.parametrize("S,n,kind", [(1, 4099, "flat"), (3, 70_001, "skew"), (96, 513, "flat"), (384, 1_000_003, "flat"),
+                                      (384, 300_007, "skew"), (384, 200_000, "runs"), (700, 300_000, "flat"),
+                                      (2200, 300_000, "flat"), (3000, 100_000, "flat")])
+def test_routing_staged_form_on_small_batches(S, n, kind, monkeypatch):
+    """The scatter that large batches take (votes for the ranking, turns between the warps of a CTA, whole sectors
+    through a ring per bin), forced onto small batches through its hook: stable partition against the oracle for flat,
+    skewed and sorted index arrays, with `order` at every word offset inside a 32-byte sector (the sector phase `a`),
+    nothing written outside order[0..n); 3000 bins do not fit its rings and take the per-warp form."""
+    import torch
+    monkeypatch.setenv("SGDX_ROUTE_STAGED_FROM", "0")
+    rng = np.random.default_rng(S * 11 + n)
+    idx = rng.integers(0, S + 1, n).astype(np.uint16)
+    if kind == "skew":
+        idx[rng.random(n) < 0.9] = S
+    elif kind == "runs":
+        idx = np.sort(idx)[::-1].copy()
+        idx[1000:5000] = rng.integers(0, S + 1, 4000)
+    want_order, want_off = orc.route_reads(idx, S)
+    m = sg.CachedHammingDistanceMatcher([bytes(b) for b in sg.synth.Workload("r", S, 12, 0, 1, 1, table_seed=1, min_dist=1).table()], 1, 1, 1)
+    d_idx = _cuda(idx)
+    for k in (0, 1, 3, 7):
+        buf = torch.full((n + 16,), -1, dtype=torch.int32, device="cuda")
+        d_off = torch.zeros(S + 2, dtype=torch.int64, device="cuda")
+        m.route_device(d_idx.data_ptr(), n, buf.data_ptr() + 4 * k, d_off.data_ptr())
+        m.sync(0)
+        got = buf.cpu().numpy()
+        assert (got[:k] == -1).all() and (got[k + n:] == -1).all()
+        assert np.array_equal(got[k:k + n].view(np.uint32), want_order)
+        assert np.array_equal(d_off.cpu().numpy().astype(np.uint64), want_off)
+    m.close()
+
+
+def test_routing_of_a_large_batch_takes_the_staged_form():
+    """70 M reads (above the 64 M switch) without any hook: stable partition against numpy's stable argsort."""
+    import torch
+    S, n = 384, 70_000_037
+    rng = np.random.default_rng(70)
+    idx = rng.integers(0, S + 1, n, dtype=np.uint16)
+    idx[::11] = S
+    m = sg.CachedHammingDistanceMatcher([bytes(b) for b in sg.synth.Workload("r", S, 12, 0, 1, 1, table_seed=1, min_dist=1).table()], 1, 1, 1)
+    d_idx = _cuda(idx)
+    d_order = torch.full((n,), -1, dtype=torch.int32, device="cuda")
+    d_off = torch.zeros(S + 2, dtype=torch.int64, device="cuda")
+    m.route_device(d_idx.data_ptr(), n, d_order.data_ptr(), d_off.data_ptr())
+    m.sync(0)
+    want = np.argsort(idx, kind="stable").astype(np.uint32)
+    assert np.array_equal(d_order.cpu().numpy().view(np.uint32), want)
+    counts = np.bincount(idx, minlength=S + 1)
+    assert np.array_equal(d_off.cpu().numpy()[:S + 2].astype(np.int64), np.concatenate([[0], np.cumsum(counts)]))
+    m.close()
+
+
 def test_routing_after_assignment_c2():
     """Assignment -> routing on one stream, device resident: every sample's run holds exactly its reads, in order."""
     import torch
