@@ -499,8 +499,12 @@ cudaError_t launch_exact_words(const DevParams &p, uint32_t mode, int sms, cudaS
     const bool big = exact_block_threads_impl(p) == 1024u;
     // staged front end: 512-thread CTAs, rows of whole words, 16-byte aligned input, and the table + stage must
     // still leave room for three CTAs per SM
+#ifndef SGDX_NO_TEST_HOOKS  // (an experiment kept for its parity test and DESIGN.md 9; slower than the default)
     const bool staged = getenv("SGDX_STAGED") && aligned && !big && (reinterpret_cast<uintptr_t>(p.reads_ascii) & 15u) == 0u &&
                         exact_smem_bytes_impl(p, 512, kStagedReadsPerThread, 512u * kStagedReadsPerThread * LW * 4u) <= 113u * 1024u;
+#else
+    const bool staged = false;
+#endif
     if (staged)
         return mode == kModeHamming ? launch_exact_t<kModeHamming, LW, true, 512, true>(p, sms, stream)
                                     : launch_exact_t<kModePreCompute, LW, true, 512, true>(p, sms, stream);
